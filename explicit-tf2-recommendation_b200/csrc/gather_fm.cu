@@ -1,0 +1,572 @@
+// K0/K1/K2: input assembly, embedding gather + bag pooling + FM terms (forward
+// and backward).  HBM-bound: every table row is fetched exactly once per pass
+// with 128-bit loads by a group of LPR lanes (LPR*CPL 16-byte chunks cover one
+// row), pooled/FM-reduced in registers and never written back unless a GEMM
+// operand ("flat") is requested.
+//
+// Reference arithmetic replaced: 2.FM/CustomLayers.py:138-155 (FM),
+// :280-300 (DeepFM gather/Flatten), 3.DCN/CustomLayers.py:240-259 (DCN input).
+#include "etr_common.cuh"
+
+namespace etr {
+
+struct GatherParams {
+  const char* table;
+  long long rows;
+  int row_bytes;   // stride * esize
+  int nchunks;     // 16-byte chunks holding the first `width` columns
+  int k;
+  int has_w;
+  const long long* ids;
+  const int* csr;
+  long long B;
+  int F, L;
+  long long sb, sf, sl;
+  long long pad;
+  int has_pad;
+  int mean;
+  const float* bias;
+  float* logit;
+  float* prob;
+  float* sumv;
+  void* flat;
+  int flat_bf16;
+  long long flat_ld;
+  int flat_col0;
+  int flat_vec;    // 1: 16B/8B vector stores are aligned
+  // backward only
+  const float* dlogit;
+  float* bag_grad;
+  int grad_ld;
+  unsigned long long* err;
+};
+
+// rows in flight per lane: keep <= 32 fp32 registers of row data
+template <int CPL, int VEC>
+struct UnrollFor {
+  static constexpr int value = (CPL * VEC >= 16) ? 2 : ((CPL * VEC >= 8) ? 4 : 8);
+};
+
+template <typename Elem>
+__device__ __forceinline__ void store_flat(const GatherParams& p, long long b, int f, int col,
+                                           const float* v) {
+  constexpr int VEC = Chunk<Elem>::kElems;
+  if (col >= p.k) return;
+  const long long e0 = b * p.flat_ld + p.flat_col0 + (long long)f * p.k + col;
+  const bool full = (col + VEC <= p.k) && p.flat_vec;
+  if (!p.flat_bf16) {
+    float* o = reinterpret_cast<float*>(p.flat) + e0;
+    if (full) {
+#pragma unroll
+      for (int i = 0; i < VEC; i += 4) stg_stream16(o + i, make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]));
+    } else {
+#pragma unroll
+      for (int i = 0; i < VEC; ++i)
+        if (col + i < p.k) o[i] = v[i];
+    }
+  } else {
+    __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(p.flat) + e0;
+    if (full) {
+      uint32_t w[VEC / 2];
+#pragma unroll
+      for (int i = 0; i < VEC / 2; ++i) {
+        __nv_bfloat162 h = __floats2bfloat162_rn(v[2 * i], v[2 * i + 1]);
+        w[i] = *reinterpret_cast<uint32_t*>(&h);
+      }
+      if (VEC == 4) {
+        *reinterpret_cast<uint2*>(o) = make_uint2(w[0], w[1]);
+      } else {
+        *reinterpret_cast<uint4*>(o) = make_uint4(w[0], w[1], w[VEC / 2 - 2], w[VEC / 2 - 1]);
+      }
+    } else {
+#pragma unroll
+      for (int i = 0; i < VEC; ++i)
+        if (col + i < p.k) o[i] = __float2bfloat16_rn(v[i]);
+    }
+  }
+}
+
+// Pools bag (b,f) into e[CPL][VEC]; returns the number of valid ids.
+template <typename Elem, int LPR, int CPL>
+__device__ __forceinline__ int pool_bag(const GatherParams& p, long long b, int f, int gl, bool active,
+                                        float (&e)[CPL][Chunk<Elem>::kElems]) {
+  constexpr int VEC = Chunk<Elem>::kElems;
+  constexpr int kUnroll = UnrollFor<CPL, VEC>::value;
+#pragma unroll
+  for (int j = 0; j < CPL; ++j)
+#pragma unroll
+    for (int i = 0; i < VEC; ++i) e[j][i] = 0.f;
+  if (!active) return 0;
+  const long long* base;
+  long long step;
+  int n;
+  if (p.csr) {
+    const int o0 = p.csr[b * p.F + f];
+    n = p.csr[b * p.F + f + 1] - o0;
+    base = p.ids + o0;
+    step = 1;
+  } else {
+    base = p.ids + b * p.sb + (long long)f * p.sf;
+    step = p.sl;
+    n = p.L;
+  }
+  int cnt = 0;
+  for (int l0 = 0; l0 < n; l0 += kUnroll) {
+    long long id[kUnroll];
+    bool ok[kUnroll];
+#pragma unroll
+    for (int u = 0; u < kUnroll; ++u) {
+      const bool in = (l0 + u) < n;
+      id[u] = in ? __ldg(base + (long long)(l0 + u) * step) : 0;
+      ok[u] = in && !(p.has_pad && id[u] == p.pad);
+      if (ok[u] && (unsigned long long)id[u] >= (unsigned long long)p.rows) {
+        flag_bad_id(p.err, id[u]);
+        ok[u] = false;
+      }
+    }
+    Chunk<Elem> r[kUnroll][CPL];
+#pragma unroll
+    for (int u = 0; u < kUnroll; ++u)
+#pragma unroll
+      for (int j = 0; j < CPL; ++j) {
+        const int c = gl + j * LPR;
+        if (ok[u] && c < p.nchunks)
+          r[u][j].load(p.table + id[u] * (long long)p.row_bytes + c * 16);
+        else
+          r[u][j].zero();
+      }
+#pragma unroll
+    for (int u = 0; u < kUnroll; ++u) {
+      cnt += ok[u] ? 1 : 0;
+#pragma unroll
+      for (int j = 0; j < CPL; ++j)
+#pragma unroll
+        for (int i = 0; i < VEC; ++i) e[j][i] += r[u][j].v[i];
+    }
+  }
+  if (p.mean && cnt > 1) {
+    const float inv = 1.0f / (float)cnt;
+#pragma unroll
+    for (int j = 0; j < CPL; ++j)
+#pragma unroll
+      for (int i = 0; i < VEC; ++i) e[j][i] *= inv;
+  }
+  return cnt;
+}
+
+// ---------------------------------------------------------------- forward
+// BAG=false: single-hot [B,F] fast path -- kUnroll fields in flight per lane.
+template <typename Elem, int LPR, int CPL, bool BAG>
+__global__ void __launch_bounds__(256) gather_fm_fwd_kernel(const GatherParams p) {
+  constexpr int VEC = Chunk<Elem>::kElems;
+  constexpr int kUnroll = UnrollFor<CPL, VEC>::value;
+  constexpr int GPW = 32 / LPR;
+  const int lane = threadIdx.x & 31;
+  const int gl = lane % LPR;
+  const int g = lane / LPR;
+  const long long warp_global = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const long long nwarps = (long long)gridDim.x * (blockDim.x >> 5);
+  const bool want_fm = (p.logit != nullptr) || (p.prob != nullptr) || (p.sumv != nullptr);
+
+  for (long long b0 = warp_global * GPW; b0 < p.B; b0 += nwarps * GPW) {
+    const long long b = b0 + g;
+    const bool active = b < p.B;
+    float S[CPL][VEC], Q[CPL][VEC];
+#pragma unroll
+    for (int j = 0; j < CPL; ++j)
+#pragma unroll
+      for (int i = 0; i < VEC; ++i) S[j][i] = Q[j][i] = 0.f;
+
+    if (!BAG) {
+      for (int f0 = 0; f0 < p.F; f0 += kUnroll) {
+        long long id[kUnroll];
+        bool ok[kUnroll];
+#pragma unroll
+        for (int u = 0; u < kUnroll; ++u) {
+          const bool in = active && (f0 + u) < p.F;
+          id[u] = in ? __ldg(p.ids + b * p.sb + (long long)(f0 + u) * p.sf) : 0;
+          ok[u] = in && !(p.has_pad && id[u] == p.pad);
+          if (ok[u] && (unsigned long long)id[u] >= (unsigned long long)p.rows) {
+            flag_bad_id(p.err, id[u]);
+            ok[u] = false;
+          }
+        }
+        Chunk<Elem> r[kUnroll][CPL];
+#pragma unroll
+        for (int u = 0; u < kUnroll; ++u)
+#pragma unroll
+          for (int j = 0; j < CPL; ++j) {
+            const int c = gl + j * LPR;
+            if (ok[u] && c < p.nchunks)
+              r[u][j].load(p.table + id[u] * (long long)p.row_bytes + c * 16);
+            else
+              r[u][j].zero();
+          }
+#pragma unroll
+        for (int u = 0; u < kUnroll; ++u) {
+          if (f0 + u < p.F) {
+#pragma unroll
+            for (int j = 0; j < CPL; ++j) {
+#pragma unroll
+              for (int i = 0; i < VEC; ++i) {
+                const float x = r[u][j].v[i];
+                S[j][i] += x;
+                Q[j][i] += x * x;
+              }
+              if (p.flat && active) store_flat<Elem>(p, b, f0 + u, (gl + j * LPR) * VEC, r[u][j].v);
+            }
+          }
+        }
+      }
+    } else {
+      for (int f = 0; f < p.F; ++f) {
+        float e[CPL][VEC];
+        pool_bag<Elem, LPR, CPL>(p, b, f, gl, active, e);
+#pragma unroll
+        for (int j = 0; j < CPL; ++j) {
+#pragma unroll
+          for (int i = 0; i < VEC; ++i) {
+            S[j][i] += e[j][i];
+            Q[j][i] += e[j][i] * e[j][i];
+          }
+          if (p.flat && active) store_flat<Elem>(p, b, f, (gl + j * LPR) * VEC, e[j]);
+        }
+      }
+    }
+
+    if (want_fm) {
+      // second = 0.5 * sum_{c<k} (S_c^2 - Q_c); first = S_k (the fused w column)
+      float second = 0.f, first = 0.f;
+#pragma unroll
+      for (int j = 0; j < CPL; ++j)
+#pragma unroll
+        for (int i = 0; i < VEC; ++i) {
+          const int col = (gl + j * LPR) * VEC + i;
+          if (col < p.k) {
+            second += S[j][i] * S[j][i] - Q[j][i];
+            if (p.sumv && active) p.sumv[b * p.k + col] = S[j][i];
+          } else if (col == p.k && p.has_w) {
+            first = S[j][i];
+          }
+        }
+      second = group_sum<LPR>(second);
+      first = group_sum<LPR>(first);
+      if (gl == 0 && active) {
+        const float z = ((p.bias ? p.bias[0] : 0.f) + first) + 0.5f * second;
+        if (p.logit) p.logit[b] = z;
+        if (p.prob) p.prob[b] = sigmoidf_exact(z);
+      }
+    }
+  }
+}
+
+// --------------------------------------------------------------- backward
+// bag_grad[(b*F+f), c] = dlogit*(S_c - e_fc) (+ dflat)  for c<k ; dlogit at c==k.
+template <typename Elem, int LPR, int CPL>
+__global__ void __launch_bounds__(256) gather_fm_bwd_kernel(const GatherParams p) {
+  constexpr int VEC = Chunk<Elem>::kElems;
+  constexpr int GPW = 32 / LPR;
+  const int lane = threadIdx.x & 31;
+  const int gl = lane % LPR;
+  const int g = lane / LPR;
+  const long long warp_global = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const long long nwarps = (long long)gridDim.x * (blockDim.x >> 5);
+  const bool need_rows = p.dlogit != nullptr;
+  const int grad_chunks = p.grad_ld / 4;   // fp32 chunks per gradient row
+
+  for (long long b0 = warp_global * GPW; b0 < p.B; b0 += nwarps * GPW) {
+    const long long b = b0 + g;
+    const bool active = b < p.B;
+    float S[CPL][VEC];
+#pragma unroll
+    for (int j = 0; j < CPL; ++j)
+#pragma unroll
+      for (int i = 0; i < VEC; ++i) S[j][i] = 0.f;
+    float dl = 0.f;
+    if (need_rows) {
+      dl = active ? p.dlogit[b] : 0.f;
+      for (int f = 0; f < p.F; ++f) {
+        float e[CPL][VEC];
+        pool_bag<Elem, LPR, CPL>(p, b, f, gl, active, e);
+#pragma unroll
+        for (int j = 0; j < CPL; ++j)
+#pragma unroll
+          for (int i = 0; i < VEC; ++i) S[j][i] += e[j][i];
+      }
+    }
+    for (int f = 0; f < p.F; ++f) {
+      float e[CPL][VEC];
+      int cnt = 1;
+      if (need_rows) {
+        cnt = pool_bag<Elem, LPR, CPL>(p, b, f, gl, active, e);   // rows now come from L2
+      } else if (p.mean && active) {
+        // only the bag count is needed
+        cnt = 0;
+        if (p.csr) {
+          cnt = p.csr[b * p.F + f + 1] - p.csr[b * p.F + f];
+        } else {
+          for (int l = 0; l < p.L; ++l) {
+            const long long id = __ldg(p.ids + b * p.sb + (long long)f * p.sf + (long long)l * p.sl);
+            cnt += (p.has_pad && id == p.pad) ? 0 : 1;
+          }
+        }
+      }
+      if (!active) continue;
+      const float scale = (p.mean && cnt > 1) ? 1.0f / (float)cnt : 1.0f;
+      float* grow = p.bag_grad + (b * p.F + f) * (long long)p.grad_ld;
+#pragma unroll
+      for (int j = 0; j < CPL; ++j) {
+        const int c = gl + j * LPR;
+        float gout[VEC];
+#pragma unroll
+        for (int i = 0; i < VEC; ++i) {
+          const int col = c * VEC + i;
+          float gv = 0.f;
+          if (col < p.k) {
+            if (need_rows) gv = dl * (S[j][i] - e[j][i]);
+            if (p.flat) {
+              const long long e0 = b * p.flat_ld + p.flat_col0 + (long long)f * p.k + col;
+              gv += p.flat_bf16 ? __bfloat162float(reinterpret_cast<const __nv_bfloat16*>(p.flat)[e0])
+                                : reinterpret_cast<const float*>(p.flat)[e0];
+            }
+          } else if (col == p.k && p.has_w) {
+            gv = dl;
+          }
+          gout[i] = gv * scale;
+        }
+        // VEC fp32 values = VEC/4 16-byte chunks of the gradient row
+#pragma unroll
+        for (int q = 0; q < VEC / 4; ++q) {
+          const int gc = c * (VEC / 4) + q;
+          if (gc < grad_chunks)
+            stg_stream16(grow + gc * 4, make_float4(gout[4 * q], gout[4 * q + 1], gout[4 * q + 2], gout[4 * q + 3]));
+        }
+      }
+    }
+  }
+}
+
+// ------------------------------------------------------------ row dump
+template <typename Elem>
+__global__ void __launch_bounds__(256) embedding_gather_kernel(const char* table, long long rows, int row_bytes,
+                                                               int width, const long long* ids, long long count,
+                                                               float* out, long long out_ld,
+                                                               unsigned long long* err) {
+  constexpr int VEC = Chunk<Elem>::kElems;
+  const int nchunks = (width + VEC - 1) / VEC;
+  const long long total = count * nchunks;
+  for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < total;
+       t += (long long)gridDim.x * blockDim.x) {
+    const long long n = t / nchunks;
+    const int c = (int)(t % nchunks);
+    const long long id = ids[n];
+    Chunk<Elem> r;
+    if ((unsigned long long)id >= (unsigned long long)rows) {
+      flag_bad_id(err, id);
+      r.zero();
+    } else {
+      r.load(table + id * (long long)row_bytes + c * 16);
+    }
+#pragma unroll
+    for (int i = 0; i < VEC; ++i)
+      if (c * VEC + i < width) out[n * out_ld + c * VEC + i] = r.v[i];
+  }
+}
+
+// ------------------------------------------------------------ K0 assemble
+struct ColPtrs {
+  const long long* col[64];
+};
+__global__ void __launch_bounds__(256) assemble_ids_kernel(const ColPtrs cols, int fields, long long batch,
+                                                           long long* out) {
+  const long long total = (long long)fields * batch;
+  for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < total;
+       t += (long long)gridDim.x * blockDim.x) {
+    const int f = (int)(t / batch);
+    const long long b = t % batch;
+    out[t] = cols.col[f][b];
+  }
+}
+
+// ------------------------------------------------------------ dispatch
+static int fill_params(const char* fn, const etr_table* table, int k, int has_w, const etr_ids* ids,
+                       GatherParams* p, etr_ctx* ctx) {
+  if (!ctx || !table || !ids) { etr_set_error("%s: NULL argument", fn); return ETR_EINVAL; }
+  if (!table->d_data || !ids->d_ids) { etr_set_error("%s: NULL device pointer", fn); return ETR_EINVAL; }
+  const int esize = table->dtype == ETR_BF16 ? 2 : 4;
+  if (table->dtype != ETR_F32 && table->dtype != ETR_BF16) { etr_set_error("%s: bad table dtype", fn); return ETR_EINVAL; }
+  if (k <= 0 || k + (has_w ? 1 : 0) > table->width || table->width > table->stride) {
+    etr_set_error("%s: k=%d has_w=%d does not fit table width=%d stride=%d", fn, k, has_w, table->width, table->stride);
+    return ETR_EINVAL;
+  }
+  if ((table->stride * esize) % 16 != 0 || ((uintptr_t)table->d_data & 15)) {
+    etr_set_error("%s: table rows must be 16-byte aligned (stride*esize %% 16 == 0)", fn);
+    return ETR_EINVAL;
+  }
+  if (ids->batch < 0 || ids->fields <= 0 || (!ids->d_csr_offsets && ids->bag <= 0)) {
+    etr_set_error("%s: bad ids shape", fn);
+    return ETR_EINVAL;
+  }
+  memset(p, 0, sizeof(*p));
+  p->table = (const char*)table->d_data;
+  p->rows = table->rows;
+  p->row_bytes = table->stride * esize;
+  const int used = k + (has_w ? 1 : 0);
+  p->nchunks = (used * esize + 15) / 16;
+  p->k = k;
+  p->has_w = has_w ? 1 : 0;
+  p->ids = (const long long*)ids->d_ids;
+  p->csr = ids->d_csr_offsets;
+  p->B = ids->batch;
+  p->F = ids->fields;
+  p->L = ids->d_csr_offsets ? 0 : ids->bag;
+  p->sb = ids->stride_b; p->sf = ids->stride_f; p->sl = ids->stride_l;
+  p->pad = ids->pad_id;
+  p->has_pad = ids->has_pad;
+  p->mean = ids->pooling == ETR_POOL_MEAN;
+  p->err = ctx->d_err;
+  return ETR_OK;
+}
+
+template <typename Elem, bool BWD>
+static int launch_gather(etr_ctx* ctx, const GatherParams& p, bool bag, cudaStream_t s) {
+  // lanes per row: smallest power of two covering the chunks, at most 32; then CPL
+  int lpr = 1;
+  while (lpr < p.nchunks && lpr < 32) lpr <<= 1;
+  const int cpl = (p.nchunks + lpr - 1) / lpr;
+  if (cpl > 4) {
+    etr_set_error("gather: row of %d 16-byte chunks is wider than the kernels cover (2 KiB)", p.nchunks);
+    return ETR_EUNSUPPORTED;
+  }
+  const int gpw = 32 / lpr;
+  const int threads = 256;
+  const int grid = grid_for(p.B, (threads / 32) * gpw, ctx->sm_count, 8);
+#define ETR_LAUNCH(LPR, CPL)                                                              \
+  do {                                                                                    \
+    if (BWD)                                                                              \
+      gather_fm_bwd_kernel<Elem, LPR, CPL><<<grid, threads, 0, s>>>(p);                   \
+    else if (bag)                                                                         \
+      gather_fm_fwd_kernel<Elem, LPR, CPL, true><<<grid, threads, 0, s>>>(p);             \
+    else                                                                                  \
+      gather_fm_fwd_kernel<Elem, LPR, CPL, false><<<grid, threads, 0, s>>>(p);            \
+  } while (0)
+  if (cpl == 1) {
+    switch (lpr) {
+      case 1: ETR_LAUNCH(1, 1); break;
+      case 2: ETR_LAUNCH(2, 1); break;
+      case 4: ETR_LAUNCH(4, 1); break;
+      case 8: ETR_LAUNCH(8, 1); break;
+      case 16: ETR_LAUNCH(16, 1); break;
+      default: ETR_LAUNCH(32, 1); break;
+    }
+  } else if (cpl == 2) {
+    ETR_LAUNCH(32, 2);
+  } else {
+    ETR_LAUNCH(32, 4);
+  }
+#undef ETR_LAUNCH
+  ETR_LAUNCH_CHECK(ctx);
+  return ETR_OK;
+}
+
+}  // namespace etr
+
+using namespace etr;
+
+extern "C" {
+
+int etr_assemble_ids(etr_ctx* ctx, const int64_t* const* h_cols, int32_t fields, int64_t batch,
+                     int64_t* d_out, void* stream) {
+  ETR_CHECK_ARG(ctx && h_cols && d_out, "NULL argument");
+  ETR_CHECK_ARG(fields > 0 && fields <= 64, "fields must be in [1,64] per call");
+  ETR_CHECK_ARG(batch >= 0, "negative batch");
+  if (batch == 0) return ETR_OK;
+  ColPtrs cols;
+  for (int f = 0; f < fields; ++f) {
+    ETR_CHECK_ARG(h_cols[f] != nullptr, "NULL column pointer");
+    cols.col[f] = (const long long*)h_cols[f];
+  }
+  const int grid = grid_for((long long)fields * batch, 256 * 4, ctx->sm_count, 8);
+  assemble_ids_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(cols, fields, batch, (long long*)d_out);
+  ETR_LAUNCH_CHECK(ctx);
+  return ETR_OK;
+}
+
+int etr_gather_fm_forward(etr_ctx* ctx, const etr_table* table, int32_t k, int32_t has_w,
+                          const etr_ids* ids, const float* d_bias, float* d_logit, float* d_prob,
+                          float* d_sumv, void* d_flat, int32_t flat_dtype, int64_t flat_ld,
+                          int32_t flat_col0, void* stream) {
+  GatherParams p;
+  int st = fill_params(__func__, table, k, has_w, ids, &p, ctx);
+  if (st != ETR_OK) return st;
+  if (p.B == 0) return ETR_OK;
+  p.bias = d_bias; p.logit = d_logit; p.prob = d_prob; p.sumv = d_sumv;
+  p.flat = d_flat;
+  p.flat_bf16 = flat_dtype == ETR_BF16;
+  p.flat_ld = flat_ld;
+  p.flat_col0 = flat_col0;
+  if (d_flat) {
+    ETR_CHECK_ARG(flat_ld >= flat_col0 + (int64_t)p.F * k, "flat_ld too small");
+    // one lane stores VEC output elements per chunk: alignment min(16, VEC*osz) bytes
+    const int vec = table->dtype == ETR_BF16 ? 8 : 4;
+    const int osz = p.flat_bf16 ? 2 : 4;
+    const int align = vec * osz > 16 ? 16 : vec * osz;
+    p.flat_vec = ((flat_col0 * osz) % align == 0) && ((flat_ld * osz) % align == 0) &&
+                 ((k * osz) % align == 0) && (((uintptr_t)d_flat & 15) == 0);
+  }
+  const bool bag = ids->d_csr_offsets != nullptr || ids->bag != 1;
+  if (table->dtype == ETR_BF16)
+    return launch_gather<__nv_bfloat16, false>(ctx, p, bag, (cudaStream_t)stream);
+  return launch_gather<float, false>(ctx, p, bag, (cudaStream_t)stream);
+}
+
+int etr_gather_fm_backward(etr_ctx* ctx, const etr_table* table, int32_t k, int32_t has_w,
+                           const etr_ids* ids, const float* d_dlogit, const void* d_dflat,
+                           int32_t flat_dtype, int64_t flat_ld, int32_t flat_col0, float* d_bag_grad,
+                           int32_t grad_ld, void* stream) {
+  GatherParams p;
+  int st = fill_params(__func__, table, k, has_w, ids, &p, ctx);
+  if (st != ETR_OK) return st;
+  if (p.B == 0) return ETR_OK;
+  ETR_CHECK_ARG(d_bag_grad != nullptr, "d_bag_grad is NULL");
+  ETR_CHECK_ARG(d_dlogit || d_dflat, "need d_dlogit and/or d_dflat");
+  ETR_CHECK_ARG(grad_ld % 4 == 0 && grad_ld >= k + (has_w ? 1 : 0), "grad_ld must be a multiple of 4 and >= k+has_w");
+  ETR_CHECK_ARG(((uintptr_t)d_bag_grad & 15) == 0, "d_bag_grad must be 16-byte aligned");
+  p.dlogit = d_dlogit;
+  p.flat = const_cast<void*>(d_dflat);
+  p.flat_bf16 = flat_dtype == ETR_BF16;
+  p.flat_ld = flat_ld;
+  p.flat_col0 = flat_col0;
+  p.bag_grad = d_bag_grad;
+  p.grad_ld = grad_ld;
+  // the gradient row may be wider (in chunks) than the table row for bf16 tables:
+  // lanes are assigned by table chunks, each producing VEC fp32 values.
+  if (table->dtype == ETR_BF16)
+    return launch_gather<__nv_bfloat16, true>(ctx, p, true, (cudaStream_t)stream);
+  return launch_gather<float, true>(ctx, p, true, (cudaStream_t)stream);
+}
+
+int etr_embedding_gather(etr_ctx* ctx, const etr_table* table, const int64_t* d_ids, int64_t count,
+                         float* d_out, int64_t out_ld, void* stream) {
+  ETR_CHECK_ARG(ctx && table && table->d_data && d_ids && d_out, "NULL argument");
+  ETR_CHECK_ARG(out_ld >= table->width, "out_ld < width");
+  const int esize = table->dtype == ETR_BF16 ? 2 : 4;
+  ETR_CHECK_ARG((table->stride * esize) % 16 == 0 && ((uintptr_t)table->d_data & 15) == 0,
+                "table rows must be 16-byte aligned");
+  if (count == 0) return ETR_OK;
+  const int vec = 16 / esize;
+  const int nchunks = (table->width + vec - 1) / vec;
+  const int grid = grid_for(count * nchunks, 256, ctx->sm_count, 8);
+  if (table->dtype == ETR_BF16)
+    embedding_gather_kernel<__nv_bfloat16><<<grid, 256, 0, (cudaStream_t)stream>>>(
+        (const char*)table->d_data, table->rows, table->stride * esize, table->width,
+        (const long long*)d_ids, count, d_out, out_ld, ctx->d_err);
+  else
+    embedding_gather_kernel<float><<<grid, 256, 0, (cudaStream_t)stream>>>(
+        (const char*)table->d_data, table->rows, table->stride * esize, table->width,
+        (const long long*)d_ids, count, d_out, out_ld, ctx->d_err);
+  ETR_LAUNCH_CHECK(ctx);
+  return ETR_OK;
+}
+
+}  // extern "C"

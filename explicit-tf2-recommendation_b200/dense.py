@@ -1,0 +1,198 @@
+"""Dense (replicated) parameters and the MLP tower -- host side of K7.
+
+``MLPLayer`` mirrors the reference class of the same name
+(2.FM/CustomLayers.py:15-84; copy in 3.DCN/CustomLayers.py:20-90): same ctor
+arguments, ``kernels`` / ``biases`` lists named ``kernel_i`` / ``bias_i``.
+"""
+from __future__ import annotations
+
+import math
+from typing import Dict, List, Optional, Tuple
+
+import torch
+
+from . import _lib
+from ._lib import check
+from .runtime import Runtime, gemm_f32, _p
+
+
+class DenseParams:
+    """All small replicated variables of one model in ONE flat fp32 buffer (with
+    matching flat grad / Adam m / v buffers) so the dense Adam apply is a single
+    launch.  Variables are views into the flat buffers."""
+
+    def __init__(self, rt: Runtime):
+        self.rt = rt
+        self._specs: List[Tuple[str, Tuple[int, ...], torch.Tensor]] = []
+        self.value = self.grad = self.m = self.v = None
+        self._views: Dict[str, Tuple[int, Tuple[int, ...]]] = {}
+
+    def add(self, name: str, init: torch.Tensor) -> str:
+        assert self.value is None, "DenseParams already finalized"
+        assert name not in [s[0] for s in self._specs], name
+        self._specs.append((name, tuple(init.shape), init.detach().to(torch.float32).reshape(-1)))
+        return name
+
+    def finalize(self):
+        # every variable starts on a 16-byte boundary
+        off = 0
+        for name, shape, _ in self._specs:
+            self._views[name] = (off, shape)
+            off += (math.prod(shape) + 3) // 4 * 4
+        n = max(off, 4)
+        self.value = self.rt.zeros((n,))
+        self.grad = self.rt.zeros((n,))
+        self.m = self.rt.zeros((n,))
+        self.v = self.rt.zeros((n,))
+        for name, shape, init in self._specs:
+            o, _ = self._views[name]
+            self.value[o:o + init.numel()] = init.to(self.rt.device)
+        return self
+
+    def __getitem__(self, name: str) -> torch.Tensor:
+        o, shape = self._views[name]
+        return self.value[o:o + math.prod(shape)].view(shape)
+
+    def g(self, name: str) -> torch.Tensor:
+        o, shape = self._views[name]
+        return self.grad[o:o + math.prod(shape)].view(shape)
+
+    def names(self) -> List[str]:
+        return [s[0] for s in self._specs]
+
+    def set(self, name: str, value) -> None:
+        self[name].copy_(torch.as_tensor(value, dtype=torch.float32).reshape(self[name].shape))
+
+    def adam_step(self, lr_t: float, d_lr_t: Optional[torch.Tensor], b1: float, b2: float, eps: float) -> None:
+        rt = self.rt
+        check(rt.lib.etr_dense_adam_apply(rt.ctx, self.value.data_ptr(), self.m.data_ptr(), self.v.data_ptr(),
+                                          self.grad.data_ptr(), self.value.numel(), lr_t, _p(d_lr_t), b1, b2, eps,
+                                          rt.stream))
+
+
+# ------------------------------------------------------------ initializers
+def glorot_uniform(shape, gen: torch.Generator, device) -> torch.Tensor:
+    """Keras glorot_uniform: limit = sqrt(6/(fan_in+fan_out)); for rank>2 the
+    leading dims are the receptive field (Keras ``_compute_fans``)."""
+    if len(shape) == 1:
+        fan_in = fan_out = shape[0]
+    elif len(shape) == 2:
+        fan_in, fan_out = shape
+    else:
+        rec = math.prod(shape[:-2])
+        fan_in, fan_out = shape[-2] * rec, shape[-1] * rec
+    lim = math.sqrt(6.0 / (fan_in + fan_out))
+    return torch.empty(shape, device=device).uniform_(-lim, lim, generator=gen)
+
+
+def random_normal(shape, gen: torch.Generator, device, std=0.05) -> torch.Tensor:
+    return torch.empty(shape, device=device).normal_(0.0, std, generator=gen)
+
+
+_INIT = {
+    "glorot_uniform": glorot_uniform,
+    "random_normal": random_normal,
+    "zeros": lambda shape, gen, device: torch.zeros(shape, device=device),
+}
+
+
+class MLPLayer:
+    """per layer: act(x @ kernel_i + bias_i) -- MatMul, BiasAdd, activation
+    (2.FM/CustomLayers.py:72-84).  Batch norm is not on the hot path (never
+    enabled by any hot-path caller) and raises; dropout is keyed on a private
+    ``is_train`` flag Keras never passes (:72,82) so it is never active in the
+    reference either and is ignored here."""
+
+    def __init__(self, units, activation=None, use_bias=True, is_batch_norm=False, is_dropput=0,
+                 kernel_initializer="glorot_uniform", bias_initializer="zeros", name="mlp", **kwargs):
+        self.units = [units] if not isinstance(units, list) else list(units)
+        if len(self.units) <= 0:
+            raise ValueError(f"Received an invalid value for `units`, expected a positive integer, got {units}.")
+        if is_batch_norm:
+            raise NotImplementedError("is_batch_norm=True is outside the B200 hot path")
+        if activation not in _lib.ACT:
+            raise ValueError(f"unsupported activation {activation!r}")
+        self.activation, self.use_bias, self.is_dropout = activation, use_bias, is_dropput
+        self.kernel_initializer, self.bias_initializer = kernel_initializer, bias_initializer
+        self.name = name
+        self.params: Optional[DenseParams] = None
+        self.in_dim: Optional[int] = None
+        self._saved = None
+        self._owns_params = False
+
+    # -- build ---------------------------------------------------------------
+    def build(self, in_dim: int, params: DenseParams, gen: torch.Generator):
+        self.in_dim, self.params = int(in_dim), params
+        dims = [self.in_dim] + self.units
+        for i in range(len(dims) - 1):
+            params.add(f"{self.name}/kernel_{i}", _INIT[self.kernel_initializer]((dims[i], dims[i + 1]), gen,
+                                                                                 params.rt.device))
+            if self.use_bias:
+                params.add(f"{self.name}/bias_{i}", _INIT[self.bias_initializer]((dims[i + 1],), gen,
+                                                                               params.rt.device))
+        return self
+
+    @property
+    def kernels(self) -> List[torch.Tensor]:
+        return [self.params[f"{self.name}/kernel_{i}"] for i in range(len(self.units))]
+
+    @property
+    def biases(self) -> List[torch.Tensor]:
+        return [self.params[f"{self.name}/bias_{i}"] for i in range(len(self.units))] if self.use_bias else []
+
+    # -- forward / backward ----------------------------------------------------
+    def __call__(self, inputs, training: bool = False, is_train: bool = False) -> torch.Tensor:
+        if self.params is None:                       # stand-alone use, as in the reference docstring
+            rt = Runtime.get(inputs.device if isinstance(inputs, torch.Tensor) and inputs.is_cuda else None)
+            gen = torch.Generator(device=rt.device)
+            gen.manual_seed(0)
+            self.build(inputs.shape[-1], DenseParams(rt), gen)
+            self.params.finalize()
+            self._owns_params = True
+        rt = self.params.rt
+        x = rt.to_device(inputs, torch.float32)
+        assert x.dim() == 2 and x.shape[1] == self.in_dim and x.stride(1) == 1
+        acts = [x]
+        for i, n_out in enumerate(self.units):
+            k = self.params[f"{self.name}/kernel_{i}"]
+            b = self.params[f"{self.name}/bias_{i}"] if self.use_bias else None
+            y = rt.empty((x.shape[0], n_out))
+            gemm_f32(rt, x, k, y, x.shape[0], n_out, x.shape[1], x.stride(0), n_out, n_out, bias=b,
+                     act=self.activation)
+            acts.append(y)
+            x = y
+        if training:
+            self._saved = acts
+        return x
+
+    def backward(self, dy: torch.Tensor, need_input_grad: bool = True) -> Optional[torch.Tensor]:
+        """dy = dL/d(output) (post-activation).  Fills the kernel/bias grads in
+        ``params.grad``; returns dL/d(input).  dy is consumed (modified in place)."""
+        assert self._saved is not None, "call with training=True first"
+        rt = self.params.rt
+        acts = self._saved
+        d = dy
+        for i in reversed(range(len(self.units))):
+            x, y = acts[i], acts[i + 1]
+            B, n_in, n_out = x.shape[0], x.shape[1], self.units[i]
+            check(rt.lib.etr_act_backward(rt.ctx, d.data_ptr(), y.data_ptr(), d.numel(), _lib.ACT[self.activation],
+                                          rt.stream))
+            gk = self.params.g(f"{self.name}/kernel_{i}")
+            # dK = x^T d : A stored [K=B, M=n_in] -> trans_a
+            gemm_f32(rt, x, d, gk, n_in, n_out, B, x.stride(0), n_out, n_out, trans_a=True)
+            if self.use_bias:
+                gb = self.params.g(f"{self.name}/bias_{i}")
+                check(rt.lib.etr_colsum_f32(rt.ctx, d.data_ptr(), B, n_out, n_out, gb.data_ptr(), rt.stream))
+            if i > 0 or need_input_grad:
+                k = self.params[f"{self.name}/kernel_{i}"]
+                dx = rt.empty((B, n_in))
+                # dx = d K^T : B(k,n) = K[n,k] -> trans_b
+                gemm_f32(rt, d, k, dx, B, n_in, n_out, n_out, n_out, n_in, trans_b=True)
+                d = dx
+            else:
+                d = None
+        self._saved = None
+        return d
+
+
+DenseLayer = MLPLayer      # 3.DCN/CustomLayers.py:153-167: a chain of Dense(x, activation)

@@ -1,0 +1,332 @@
+"""Host-side runtime: device context, HBM-resident tables, id batches, and thin
+typed wrappers over the C ABI.  torch is used for device memory, streams and
+DLPack only (plumbing); all arithmetic happens in libetr.so.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import math
+from typing import Dict, List, Optional, Sequence
+
+import numpy as np
+import torch
+
+from . import _lib
+from ._lib import check
+
+_TORCH2ETR = {torch.float32: _lib.ETR_F32, torch.bfloat16: _lib.ETR_BF16}
+
+
+def _p(t: Optional[torch.Tensor]) -> Optional[int]:
+    return None if t is None else t.data_ptr()
+
+
+class Runtime:
+    """One etr_ctx per CUDA device (created lazily, shared by all layers)."""
+
+    _instances: Dict[int, "Runtime"] = {}
+
+    @classmethod
+    def get(cls, device=None) -> "Runtime":
+        if not torch.cuda.is_available():
+            raise RuntimeError("explicit-tf2-recommendation_b200 needs a CUDA device (B200, sm_100a); "
+                               "there is no CPU fallback")
+        idx = torch.cuda.current_device() if device is None else torch.device(device).index
+        if idx is None:
+            idx = torch.cuda.current_device()
+        if idx not in cls._instances:
+            cls._instances[idx] = Runtime(idx)
+        return cls._instances[idx]
+
+    def __init__(self, index: int):
+        self.lib = _lib.load()
+        self.index = index
+        self.device = torch.device("cuda", index)
+        torch.cuda.set_device(index)
+        torch.zeros(1, device=self.device)          # make sure the primary context exists
+        h = C.c_void_p()
+        check(self.lib.etr_ctx_create(index, C.byref(h)))
+        self.ctx = h
+
+    @property
+    def stream(self) -> int:
+        return torch.cuda.current_stream(self.device).cuda_stream
+
+    @property
+    def launches(self) -> int:
+        return int(self.lib.etr_ctx_launch_count(self.ctx))
+
+    def poll_error(self) -> None:
+        """Raise EtrIdRangeError if a kernel saw an out-of-range id (synchronises)."""
+        bad = C.c_int64(0)
+        check(self.lib.etr_ctx_poll_error(self.ctx, self.stream, C.byref(bad)))
+
+    # ------------------------------------------------------------ tensors
+    def to_device(self, x, dtype: torch.dtype) -> torch.Tensor:
+        """Accept a torch tensor (any device), a numpy array, or any DLPack
+        producer (e.g. ``tf.Tensor`` via ``__dlpack__``) -> torch tensor on this
+        device (zero-copy when it already lives there)."""
+        if isinstance(x, torch.Tensor):
+            t = x
+        elif isinstance(x, np.ndarray):
+            t = torch.from_numpy(x)
+        elif hasattr(x, "__dlpack__"):
+            t = torch.from_dlpack(x)
+        else:
+            t = torch.as_tensor(x)
+        if t.device != self.device:
+            t = t.to(self.device, non_blocking=True)
+        if t.dtype != dtype:
+            t = t.to(dtype)
+        return t
+
+    def empty(self, shape, dtype=torch.float32) -> torch.Tensor:
+        return torch.empty(shape, dtype=dtype, device=self.device)
+
+    def zeros(self, shape, dtype=torch.float32) -> torch.Tensor:
+        return torch.zeros(shape, dtype=dtype, device=self.device)
+
+
+# ---------------------------------------------------------------------------
+class EmbeddingTable:
+    """HBM-resident table [rows, stride]; the first ``width`` columns of a row
+    are meaningful, the rest are zero padding so that a row is a whole number of
+    16-byte chunks.  Replaces the tf.Variable of tf.keras.layers.Embedding
+    (2.FM/CustomLayers.py:129-134).  For the FM family the [V,1] ``w`` Embedding
+    is fused in as column ``k`` (one DRAM burst serves v and w)."""
+
+    def __init__(self, rt: Runtime, rows: int, width: int, dtype: torch.dtype = torch.float32):
+        assert dtype in _TORCH2ETR
+        self.rt, self.rows, self.width, self.dtype = rt, int(rows), int(width), dtype
+        epc = 16 // torch.empty((), dtype=dtype).element_size()       # elements per 16-byte chunk
+        self.stride = ((self.width + epc - 1) // epc) * epc
+        self.data = rt.zeros((self.rows, self.stride), dtype)
+        self._m = self._v = None
+
+    def desc(self) -> _lib.etr_table:
+        return _lib.etr_table(self.data.data_ptr(), self.rows, self.width, self.stride, _TORCH2ETR[self.dtype], 0)
+
+    def cols(self, c0: int, c1: int) -> torch.Tensor:
+        """Strided view of columns [c0,c1) -- e.g. ``embed/embeddings`` = cols(0,k),
+        ``w/embeddings`` = cols(k,k+1).  Exportable with ``__dlpack__``."""
+        return self.data[:, c0:c1]
+
+    def init_uniform(self, lo: float, hi: float, gen: torch.Generator, c0: int = 0, c1: Optional[int] = None):
+        c1 = self.width if c1 is None else c1
+        vals = torch.empty((self.rows, c1 - c0), dtype=torch.float32, device=self.rt.device)
+        vals.uniform_(lo, hi, generator=gen)
+        self.data[:, c0:c1] = vals.to(self.dtype)
+
+    @property
+    def m(self) -> torch.Tensor:
+        if self._m is None:
+            self._m = self.rt.zeros((self.rows, self.stride), torch.float32)
+        return self._m
+
+    @property
+    def v(self) -> torch.Tensor:
+        if self._v is None:
+            self._v = self.rt.zeros((self.rows, self.stride), torch.float32)
+        return self._v
+
+    @property
+    def grad_ld(self) -> int:
+        return self.stride            # gradient rows use the table row layout (fp32)
+
+
+# ---------------------------------------------------------------------------
+class IdsBatch:
+    """The categorical input of one batch on the device (a1):
+    dict name -> [B] / [B,1] / [B,L]   or   X [B,F] / [B,F,L]   or   CSR."""
+
+    def __init__(self, rt: Runtime, ids: torch.Tensor, B: int, F: int, L: int, sb: int, sf: int, sl: int,
+                 pad_id: Optional[int] = None, pooling: str = "sum", csr_offsets: Optional[torch.Tensor] = None):
+        self.rt, self.ids, self.B, self.F, self.L = rt, ids, B, F, L
+        self.sb, self.sf, self.sl = sb, sf, sl
+        self.pad_id, self.pooling, self.csr = pad_id, pooling, csr_offsets
+        self.nnz = int(ids.numel()) if csr_offsets is not None else None
+
+    @property
+    def is_bag(self) -> bool:
+        return self.csr is not None or self.L != 1
+
+    @property
+    def n_slots(self) -> int:
+        return self.nnz if self.csr is not None else self.B * self.F * self.L
+
+    def desc(self) -> _lib.etr_ids:
+        return _lib.etr_ids(self.ids.data_ptr(), _p(self.csr), self.B, self.F, self.L, self.sb, self.sf, self.sl,
+                            0 if self.pad_id is None else int(self.pad_id), 0 if self.pad_id is None else 1,
+                            _lib.POOL_MEAN if self.pooling == "mean" else _lib.POOL_SUM)
+
+    # -- constructors -------------------------------------------------------
+    @staticmethod
+    def from_matrix(rt: Runtime, X, pad_id=None, pooling="sum") -> "IdsBatch":
+        t = rt.to_device(X, torch.int64)
+        if t.dim() == 2:
+            t = t.contiguous()
+            B, F = t.shape
+            return IdsBatch(rt, t, B, F, 1, F, 1, 1, pad_id, pooling)
+        assert t.dim() == 3, "ids must be [B,F] or [B,F,L]"
+        t = t.contiguous()
+        B, F, L = t.shape
+        return IdsBatch(rt, t, B, F, L, F * L, L, 1, pad_id, pooling)
+
+    @staticmethod
+    def from_csr(rt: Runtime, values, offsets, B: int, F: int, pad_id=None, pooling="sum") -> "IdsBatch":
+        v = rt.to_device(values, torch.int64).contiguous()
+        o = rt.to_device(offsets, torch.int32).contiguous()
+        assert o.numel() == B * F + 1
+        return IdsBatch(rt, v, B, F, 1, 0, 0, 0, pad_id, pooling, csr_offsets=o)
+
+    @staticmethod
+    def from_dict(rt: Runtime, inputs, names: Sequence[str], pad_id=None, pooling="sum") -> "IdsBatch":
+        """The reference input idiom (2.FM/CustomLayers.py:138-144): every
+        feature is [B] or [B,1] int64.  Produces a field-major [F,B] buffer: one
+        H2D copy per host column, or ONE assemble kernel for device columns.  A
+        [B,L] feature makes the whole batch a padded-bag batch [B,F,L]."""
+        first = inputs[names[0]]
+        cols = [inputs[n] for n in names]
+        shapes = [tuple(c.shape) for c in cols]
+        L = max((s[1] if len(s) == 2 else 1) for s in shapes)
+        B = shapes[0][0]
+        F = len(names)
+        if L > 1:
+            ts = []
+            for c, s in zip(cols, shapes):
+                t = rt.to_device(c, torch.int64).reshape(B, -1)
+                if t.shape[1] != L:
+                    assert pad_id is not None, "ragged bag widths need a pad_id"
+                    t = torch.nn.functional.pad(t, (0, L - t.shape[1]), value=pad_id)
+                ts.append(t)
+            X = torch.stack(ts, dim=1).contiguous()
+            return IdsBatch(rt, X, B, F, L, F * L, L, 1, pad_id, pooling)
+        out = rt.empty((F, B), torch.int64)
+        on_device = all(isinstance(c, torch.Tensor) and c.device == rt.device and c.dtype == torch.int64
+                        for c in cols)
+        if on_device:
+            flat = [c.reshape(-1).contiguous() for c in cols]
+            for f0 in range(0, F, 64):
+                chunk = flat[f0:f0 + 64]
+                arr = (C.c_void_p * len(chunk))(*[c.data_ptr() for c in chunk])
+                check(rt.lib.etr_assemble_ids(rt.ctx, arr, len(chunk), B, out[f0:].data_ptr(), rt.stream))
+        else:
+            for f, c in enumerate(cols):
+                if isinstance(c, np.ndarray):
+                    c = torch.from_numpy(c)
+                elif not isinstance(c, torch.Tensor):
+                    c = torch.from_dlpack(c) if hasattr(c, "__dlpack__") else torch.as_tensor(c)
+                out[f].copy_(c.reshape(-1), non_blocking=True)
+        del first
+        return IdsBatch(rt, out, B, F, 1, 1, B, 1, pad_id, pooling)
+
+    @staticmethod
+    def make(rt: Runtime, inputs, names: Sequence[str], pad_id=None, pooling="sum") -> "IdsBatch":
+        if isinstance(inputs, IdsBatch):
+            return inputs
+        if isinstance(inputs, dict):
+            return IdsBatch.from_dict(rt, inputs, names, pad_id, pooling)
+        return IdsBatch.from_matrix(rt, inputs, pad_id, pooling)
+
+
+# ---------------------------------------------------------------------------
+class SparsePlan:
+    """Sorted-ID plan of one batch (shared by every table indexed by the same ids)."""
+
+    def __init__(self, rt: Runtime, ids: IdsBatch, table_rows: int):
+        n = ids.n_slots
+        self.n_slots = n
+        self.sorted_bag = rt.empty((max(n, 1),), torch.int32)
+        self.unique_ids = rt.empty((max(n, 1),), torch.int64)
+        self.seg_start = rt.empty((n + 1,), torch.int32)
+        self.counts = rt.zeros((2,), torch.int32)        # [n_unique, n_valid]
+        d = ids.desc()
+        check(rt.lib.etr_sparse_plan(rt.ctx, C.byref(d), ids.nnz or 0, table_rows, self.sorted_bag.data_ptr(),
+                                     self.unique_ids.data_ptr(), self.seg_start.data_ptr(),
+                                     self.counts[0:].data_ptr(), self.counts[1:].data_ptr(), rt.stream))
+
+    @property
+    def n_unique(self) -> int:        # synchronises; tests / export only
+        return int(self.counts[0].item())
+
+
+class SparseGrad:
+    """IndexedSlices analogue: per-bag gradient rows (table row layout) + ids."""
+
+    def __init__(self, table: EmbeddingTable, ids: IdsBatch, bag_grad: torch.Tensor):
+        self.table, self.ids, self.bag_grad = table, ids, bag_grad
+        self.plan: Optional[SparsePlan] = None
+        self.unique_grad: Optional[torch.Tensor] = None
+
+    def reduce(self, plan: Optional[SparsePlan] = None) -> "SparseGrad":
+        """sort + segment-reduce -> (unique ids, summed rows) = deduplicated IndexedSlices."""
+        rt = self.table.rt
+        self.plan = plan or SparsePlan(rt, self.ids, self.table.rows)
+        ld = self.bag_grad.shape[1]
+        self.unique_grad = rt.empty((max(self.plan.n_slots, 1), ld), torch.float32)
+        check(rt.lib.etr_sparse_segment_reduce(rt.ctx, self.plan.sorted_bag.data_ptr(), self.plan.seg_start.data_ptr(),
+                                               self.plan.counts.data_ptr(), self.plan.n_slots,
+                                               self.bag_grad.data_ptr(), ld, self.unique_grad.data_ptr(), rt.stream))
+        return self
+
+    def indexed_slices(self):
+        """(unique ids [U], grads [U,width]) -- synchronises; for tests/export."""
+        if self.unique_grad is None:
+            self.reduce()
+        u = self.plan.n_unique
+        return self.plan.unique_ids[:u], self.unique_grad[:u, : self.table.width]
+
+
+# ---------------------------------------------------------------------------
+# thin op wrappers
+def gather_fm_forward(table: EmbeddingTable, k: int, has_w: bool, ids: IdsBatch, bias=None, logit=None, prob=None,
+                      sumv=None, flat=None, flat_col0: int = 0):
+    rt = table.rt
+    t, d = table.desc(), ids.desc()
+    flat_dtype = _TORCH2ETR[flat.dtype] if flat is not None else 0
+    flat_ld = flat.stride(0) if flat is not None else 0
+    check(rt.lib.etr_gather_fm_forward(rt.ctx, C.byref(t), k, int(has_w), C.byref(d), _p(bias), _p(logit), _p(prob),
+                                       _p(sumv), _p(flat), flat_dtype, flat_ld, flat_col0, rt.stream))
+
+
+def gather_fm_backward(table: EmbeddingTable, k: int, has_w: bool, ids: IdsBatch, dlogit=None, dflat=None,
+                       flat_col0: int = 0) -> torch.Tensor:
+    rt = table.rt
+    t, d = table.desc(), ids.desc()
+    bag_grad = rt.empty((ids.B * ids.F, table.grad_ld), torch.float32)
+    flat_dtype = _TORCH2ETR[dflat.dtype] if dflat is not None else 0
+    flat_ld = dflat.stride(0) if dflat is not None else 0
+    check(rt.lib.etr_gather_fm_backward(rt.ctx, C.byref(t), k, int(has_w), C.byref(d), _p(dlogit), _p(dflat),
+                                        flat_dtype, flat_ld, flat_col0, bag_grad.data_ptr(), table.grad_ld,
+                                        rt.stream))
+    return bag_grad
+
+
+def embedding_gather(table: EmbeddingTable, ids) -> torch.Tensor:
+    """Generic Embedding.call: ids [...] -> [..., width] fp32 (bit-exact rows)."""
+    rt = table.rt
+    t = rt.to_device(ids, torch.int64).contiguous()
+    out = rt.empty(tuple(t.shape) + (table.width,), torch.float32)
+    d = table.desc()
+    check(rt.lib.etr_embedding_gather(rt.ctx, C.byref(d), t.data_ptr(), t.numel(), out.data_ptr(), table.width,
+                                      rt.stream))
+    return out
+
+
+def gemm_f32(rt: Runtime, A, B, C_out, M, N, K, lda, ldb, ldc, trans_a=False, trans_b=False, alpha=1.0, beta=0.0,
+             bias=None, act=None):
+    check(rt.lib.etr_gemm_f32(rt.ctx, int(trans_a), int(trans_b), M, N, K, alpha, A.data_ptr(), lda, B.data_ptr(),
+                              ldb, beta, C_out.data_ptr(), ldc, _p(bias), _lib.ACT[act], rt.stream))
+
+
+def bce_forward_backward(rt: Runtime, prob: torch.Tensor, label: torch.Tensor, want_grad=True):
+    B = prob.numel()
+    loss = rt.empty((1,), torch.float32)
+    dlogit = rt.empty((B,), torch.float32) if want_grad else None
+    check(rt.lib.etr_bce_forward_backward(rt.ctx, prob.data_ptr(), label.data_ptr(), B, loss.data_ptr(), _p(dlogit),
+                                          rt.stream))
+    return loss, dlogit
+
+
+def lr_t(lr: float, b1: float, b2: float, t: int) -> float:
+    return lr * math.sqrt(1.0 - b2 ** t) / (1.0 - b1 ** t)

@@ -1,0 +1,217 @@
+/*
+ * etr.h -- C ABI of libetr.so: the B200 (sm_100a) sparse-embedding +
+ * feature-interaction hot path of PatrickHwang/Explicit-tf2-Recommendation.
+ *
+ * The reference has NO FFI for this path: the boundary it sits behind is the
+ * Keras ``Layer`` protocol (class name + ctor kwargs + ``call(inputs)``,
+ * selected in 2.FM/ModelManager.py:61-84 and 3.DCN/ModelManager.py:64-97).
+ * Every entry point below therefore cites the reference ``call()`` body (or
+ * TF-op call site) whose arithmetic it replaces; the Python layer shims in
+ * explicit-tf2-recommendation_b200/CustomLayers.py bind them with ctypes and
+ * keep the reference class names / signatures.  See INTEGRATION.md.
+ *
+ * Conventions
+ *  - plain C types only; every pointer named d_* is a DEVICE pointer owned by
+ *    the caller (the library never frees or keeps it); row-major everywhere.
+ *  - every call is asynchronous on ``stream`` (a cudaStream_t passed as void*).
+ *  - every call returns an etr_status; the message for the last failure on the
+ *    calling thread is etr_last_error().  No C++ exception crosses the ABI.
+ *  - out-of-range ids are detected in-kernel, flagged in a device error word
+ *    and surfaced by etr_ctx_poll_error() (TF-CPU raises InvalidArgumentError
+ *    for them; the offending lookup contributes a zero row).
+ *  - a ctx is bound to one device; calls on one ctx must be serialised by the
+ *    caller (the reference only ever calls from one thread,
+ *    2.FM/ModelManager.py:187, 2.FM/OnlineServer.py:144).
+ */
+#ifndef ETR_H_
+#define ETR_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define ETR_VERSION 100
+
+typedef enum {
+  ETR_OK = 0,
+  ETR_EINVAL = 1,        /* bad argument (shape, alignment, null pointer)   */
+  ETR_ERANGE = 2,        /* an embedding id was < 0 or >= rows              */
+  ETR_ECUDA = 3,         /* CUDA runtime error (see etr_last_error)         */
+  ETR_ENOMEM = 4,        /* workspace allocation failed                     */
+  ETR_EUNSUPPORTED = 5   /* shape / dtype outside what the kernels cover    */
+} etr_status;
+
+typedef enum { ETR_F32 = 0, ETR_BF16 = 1 } etr_dtype;
+typedef enum { ETR_POOL_SUM = 0, ETR_POOL_MEAN = 1 } etr_pooling;
+typedef enum { ETR_ACT_NONE = 0, ETR_ACT_RELU = 1, ETR_ACT_SIGMOID = 2, ETR_ACT_TANH = 3 } etr_act;
+typedef enum { ETR_ADAM_ROWWISE = 0, ETR_ADAM_KERAS_DENSE = 1 } etr_adam_mode;
+
+typedef struct etr_ctx etr_ctx;
+
+/* An embedding table resident in HBM: [rows, stride] elements, of which the
+ * first ``width`` columns of each row are meaningful; (stride*esize) % 16 == 0
+ * and d_data 16-byte aligned so that a row is fetched with 128-bit loads.
+ * Columns [width, stride) must be zero.  Replaces the tf.Variable behind
+ * tf.keras.layers.Embedding (2.FM/CustomLayers.py:129-134).                  */
+typedef struct {
+  void*   d_data;
+  int64_t rows;
+  int32_t width;
+  int32_t stride;
+  int32_t dtype;      /* etr_dtype */
+  int32_t reserved;
+} etr_table;
+
+/* The categorical input of one batch.  Replaces the dict -> X[B,F] assembly
+ * (2.FM/CustomLayers.py:138-144).  Element strides make [B,F] row-major,
+ * field-major [F,B] and padded bags [B,F,L] all the same descriptor.  With
+ * d_csr_offsets != NULL the bags are CSR: bag (b,f) is
+ * d_ids[offsets[b*F+f] .. offsets[b*F+f+1]) and bag/stride_l are ignored.   */
+typedef struct {
+  const int64_t* d_ids;
+  const int32_t* d_csr_offsets;  /* [B*F+1] or NULL */
+  int64_t batch;                 /* B */
+  int32_t fields;                /* F */
+  int32_t bag;                   /* L (1 = single-hot)                       */
+  int64_t stride_b, stride_f, stride_l;
+  int64_t pad_id;                /* slots equal to pad_id are skipped ...    */
+  int32_t has_pad;               /* ... when has_pad != 0                    */
+  int32_t pooling;               /* etr_pooling                              */
+} etr_ids;
+
+/* ---------------------------------------------------------------- context */
+int         etr_version(void);
+const char* etr_last_error(void);
+int etr_ctx_create(int device, etr_ctx** out);
+int etr_ctx_destroy(etr_ctx* ctx);
+/* Synchronises ``stream``, reads and clears the device error word.  Returns
+ * ETR_ERANGE (and the first offending id in *bad_id) if any kernel since the
+ * last poll saw an out-of-range id.                                          */
+int etr_ctx_poll_error(etr_ctx* ctx, void* stream, int64_t* bad_id);
+/* number of kernels of THIS library launched through ctx since creation     */
+int64_t etr_ctx_launch_count(etr_ctx* ctx);
+
+/* ------------------------------------------------- K0: input assembly (a1)
+ * F separate device columns (each [B] int64, contiguous) -> one [F,B]
+ * field-major buffer.  2.FM/CustomLayers.py:138-144 (ExpandDims + ConcatV2). */
+int etr_assemble_ids(etr_ctx* ctx, const int64_t* const* h_cols /* host array of F device ptrs */,
+                     int32_t fields, int64_t batch, int64_t* d_out, void* stream);
+
+/* ------------------------------------- K1: gather + pool + FM terms (a2-a4)
+ * One pass over the batch: rows are fetched once with 128-bit loads, bags are
+ * pooled in registers, and any of the following are produced (NULL = skip):
+ *   d_logit[b]  = (d_bias?*d_bias:0) + sum_f w + 0.5*sum_k((sum_f v)^2 - sum_f v^2)
+ *                 (2.FM/CustomLayers.py:149-155; table col ``k`` is the linear
+ *                 weight w when has_w != 0 -- the [V,1] ``w`` Embedding fused
+ *                 into the row so one DRAM burst serves both)
+ *   d_prob[b]   = sigmoid(d_logit[b])                       (:155)
+ *   d_flat[b, flat_col0 + f*k + c] = pooled embedding, c<k  (Flatten, :300;
+ *                 3.DCN/CustomLayers.py:256-259), fp32 or bf16, leading dim
+ *                 flat_ld elements -- written straight into the GEMM operand.
+ *   d_sumv[b, c] = sum_f v_f[c]  (the NFM bi-interaction / backward helper)  */
+int etr_gather_fm_forward(etr_ctx* ctx, const etr_table* table, int32_t k, int32_t has_w,
+                          const etr_ids* ids, const float* d_bias,
+                          float* d_logit, float* d_prob, float* d_sumv,
+                          void* d_flat, int32_t flat_dtype, int64_t flat_ld, int32_t flat_col0,
+                          void* stream);
+
+/* Bit-exact row dump / generic Embedding.call (2.FM/CustomLayers.py:146-147):
+ * d_out[n, 0:width] = table[d_ids[n], 0:width] for n < count, fp32 out.      */
+int etr_embedding_gather(etr_ctx* ctx, const etr_table* table, const int64_t* d_ids, int64_t count,
+                         float* d_out, int64_t out_ld, void* stream);
+
+/* ------------------------- K2: backward of K1 -> per-bag row gradients (a')
+ * d_bag_grad[(b*F+f), c] = dlogit[b]*(S_b[c]-e_bf[c]) + dflat[b, col0+f*k+c], c<k
+ *                        = dlogit[b]                                       , c==k (has_w)
+ * (mean pooling: divided by the bag count).  d_dlogit or d_dflat may be NULL.
+ * Gradient rows use the TABLE ROW LAYOUT: leading dim grad_ld (fp32 elements,
+ * multiple of 4, normally the table stride), columns >= k+has_w written as 0.
+ * This is the ``values`` of the IndexedSlices that tape.gradient returns
+ * (2.FM/ModelManager.py:176), one row per bag instead of one per id.         */
+int etr_gather_fm_backward(etr_ctx* ctx, const etr_table* table, int32_t k, int32_t has_w,
+                           const etr_ids* ids, const float* d_dlogit,
+                           const void* d_dflat, int32_t flat_dtype, int64_t flat_ld, int32_t flat_col0,
+                           float* d_bag_grad, int32_t grad_ld, void* stream);
+
+/* ---------------------------- K8: sorted-ID segment reduction + Adam (a16)
+ * Plan: stable radix sort of every valid (id, bag index) pair of the batch,
+ * then run heads.  n_slots = etr_sparse_plan_slots() = B*F*L (nnz for CSR).
+ * Caller-allocated outputs: d_sorted_bag [n_slots] (bag index b*F+f of every
+ * sorted occurrence), d_unique_ids [n_slots] (ascending), d_seg_start
+ * [n_slots+1] (run u covers sorted positions [seg_start[u], seg_start[u+1])),
+ * *d_n_unique and *d_n_valid (device int32; pad slots are excluded).         */
+int64_t etr_sparse_plan_slots(const etr_ids* ids, int64_t nnz_if_csr);
+int etr_sparse_plan(etr_ctx* ctx, const etr_ids* ids, int64_t nnz_if_csr, int64_t table_rows,
+                    int32_t* d_sorted_bag, int64_t* d_unique_ids, int32_t* d_seg_start,
+                    int32_t* d_n_unique, int32_t* d_n_valid, void* stream);
+
+/* Segment-reduce the bag gradients by id (deterministic: ascending occurrence
+ * order inside a run; long runs are cut into fixed chunks combined in order)
+ * into d_unique_grad[u, 0:grad_ld] -- the deduplicated IndexedSlices Keras'
+ * optimizer sees (first step of apply_gradients).                            */
+int etr_sparse_segment_reduce(etr_ctx* ctx, const int32_t* d_sorted_bag, const int32_t* d_seg_start,
+                              const int32_t* d_n_unique, int64_t n_slots,
+                              const float* d_bag_grad, int32_t grad_ld,
+                              float* d_unique_grad, void* stream);
+
+/* Adam on the unique rows (replaces opt.apply_gradients for IndexedSlices,
+ * 2.FM/ModelManager.py:178).  table/m/v share rows/width/stride (fp32 slots).
+ * ROWWISE touches only the unique rows; KERAS_DENSE restates Keras 2.8
+ * _resource_apply_sparse (m,v decayed and var updated for ALL rows).         */
+int etr_sparse_adam_apply(etr_ctx* ctx, const etr_table* table, float* d_m, float* d_v,
+                          const int64_t* d_unique_ids, const int32_t* d_n_unique, int64_t max_unique,
+                          const float* d_unique_grad, int32_t grad_ld,
+                          float lr_t, const float* d_lr_t, float beta1, float beta2, float eps, int32_t mode,
+                          void* stream);
+
+/* Dense Adam for the small replicated variables (bias, MLP, cross W/b).      */
+int etr_dense_adam_apply(etr_ctx* ctx, float* d_var, float* d_m, float* d_v, const float* d_grad,
+                         int64_t n, float lr_t, const float* d_lr_t, float beta1, float beta2, float eps,
+                         void* stream);
+/* Device-resident optimizer clock (so a captured CUDA graph of the train step
+ * can be replayed): d_state[0] += 1 (= Keras ``optimizer.iterations``),
+ * d_state[1] = lr*sqrt(1-beta2^t)/(1-beta1^t).  Pass &d_state[1] as d_lr_t
+ * (non-NULL d_lr_t overrides the host lr_t).                                 */
+int etr_adam_step_begin(etr_ctx* ctx, float* d_state, float lr, float beta1, float beta2, void* stream);
+
+/* ---------------------------------------------- loss (2.FM/ModelManager.py:99,175)
+ * Keras BinaryCrossentropy on probabilities, mean over the batch:
+ * *d_loss = mean(-(y log(clip(p)+eps) + (1-y) log(1-clip(p)+eps)));
+ * d_dlogit[b] = dLoss/dz_b for p = sigmoid(z) (NULL = skip).                 */
+int etr_bce_forward_backward(etr_ctx* ctx, const float* d_prob, const float* d_label, int64_t batch,
+                             float* d_loss, float* d_dlogit, void* stream);
+/* d_prob[b] = sigmoid(a[b] + b2[b]) (DeepFM output, 2.FM/CustomLayers.py:305) */
+int etr_add_sigmoid(etr_ctx* ctx, const float* d_a, const float* d_b, int64_t n, float* d_logit,
+                    float* d_prob, void* stream);
+
+/* ------------------------------------------------ K7: MLP tower GEMMs (a15)
+ * fp32 SIMT GEMM, row-major: C[M,N] = act(alpha*op(A)op(B) + beta*C + bias[N]).
+ * op(A) is [M,K], op(B) is [K,N].  Replaces MatMul + BiasAdd + activation
+ * (2.FM/CustomLayers.py:72-84; 3.DCN/CustomLayers.py:163-167).               */
+int etr_gemm_f32(etr_ctx* ctx, int32_t trans_a, int32_t trans_b, int64_t M, int64_t N, int64_t K,
+                 float alpha, const float* d_A, int64_t lda, const float* d_B, int64_t ldb,
+                 float beta, float* d_C, int64_t ldc, const float* d_bias, int32_t act, void* stream);
+/* dpre = dY (.) act'(Y)  in place on d_dy, Y = post-activation output.       */
+int etr_act_backward(etr_ctx* ctx, float* d_dy, const float* d_y, int64_t n, int32_t act, void* stream);
+/* d_out[n] = sum_m X[m, n]  (bias gradients), deterministic two-pass.        */
+int etr_colsum_f32(etr_ctx* ctx, const float* d_X, int64_t M, int64_t N, int64_t ldx, float* d_out,
+                   void* stream);
+
+/* ------------------------------------------ K6: DCN cross-matrix layer (a13)
+ * One layer: out = x0 (.) (xl W^T + b) + xl  (3.DCN/CustomLayers.py:300-303,
+ * y = W x).  fp32 SIMT form (exact-parity path); optionally stores U = xl W^T + b
+ * for the backward.                                                          */
+int etr_cross_mat_layer_f32(etr_ctx* ctx, const float* d_x0, const float* d_xl, int64_t ldx,
+                            int64_t batch, int32_t D, const float* d_W /* [D,D] */, const float* d_b,
+                            float* d_out, int64_t ldo, float* d_u, int64_t ldu, void* stream);
+/* elementwise helpers of the cross-matrix backward:
+ * du = g (.) x0 ; dx0 += g (.) u   (SURVEY a', cross-matrix).                 */
+int etr_cross_mat_bwd_elementwise(etr_ctx* ctx, const float* d_g, const float* d_x0, const float* d_u,
+                                  int64_t n, float* d_du, float* d_dx0_accum, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* ETR_H_ */

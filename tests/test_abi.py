@@ -1,0 +1,64 @@
+"""The C ABI: libetr.so builds for sm_100a here (no GPU), loads, and exports
+every function include/etr.h declares; the ctypes prototypes cover all of them.
+No compute calls."""
+import ctypes
+import os
+import re
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _declared():
+    src = open(os.path.join(ROOT, "include", "etr.h")).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"\b(etr_[a-z0-9_]+)\s*\(", src)))
+
+
+def test_header_declares_entry_points():
+    names = _declared()
+    assert "etr_gather_fm_forward" in names and "etr_sparse_adam_apply" in names and len(names) >= 20
+
+
+def test_library_exports_every_declared_symbol(lib_path):
+    lib = ctypes.CDLL(lib_path)
+    missing = [n for n in _declared() if not hasattr(lib, n)]
+    assert not missing, missing
+
+
+def test_ctypes_prototypes_cover_the_header(lib_path):
+    from etr_b200 import _lib
+    assert sorted(_lib.PROTOTYPES) == _declared()
+    lib = _lib.load()
+    assert lib.etr_version() == 100
+    assert lib.etr_last_error() is not None
+
+
+def test_struct_layouts_match_header():
+    from etr_b200 import _lib
+    assert ctypes.sizeof(_lib.etr_table) == 32
+    assert ctypes.sizeof(_lib.etr_ids) == 72
+
+
+def test_sass_is_sm100a(lib_path):
+    import subprocess
+    out = subprocess.run(["cuobjdump", "-lelf", lib_path], capture_output=True, text=True).stdout
+    assert "sm_100a" in out and "sm_90" not in out
+
+
+def test_no_cpu_fallback_without_gpu():
+    import pytest
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    from etr_b200 import CustomLayers
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        CustomLayers.FMRankingLayer(["a"], 4, 4)
+
+
+def test_product_never_imports_oracle():
+    pkg = os.path.join(ROOT, "explicit-tf2-recommendation_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h")):
+                txt = open(os.path.join(dirpath, f)).read()
+                assert not re.search(r"^\s*(from|import)\s+oracle\b", txt, flags=re.M), f

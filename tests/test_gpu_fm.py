@@ -1,0 +1,315 @@
+"""GPU parity: embedding gather, FM / DeepFM forward + backward, sparse plan,
+segment reduction, Adam -- CUDA path (through the C ABI) vs the CPU oracle."""
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+from oracle import reference_layers as R                     # noqa: E402
+from tests.util import (assert_close, cpu, dense_table_grad_to_slices, oracle_deepfm, oracle_fm,  # noqa: E402
+                        zipf_ids)
+
+FP32_RTOL = 1e-5      # north_star: fp32 outputs and gradients within 1e-5 relative
+BF16_RTOL = 1e-2
+
+
+@pytest.fixture(scope="module")
+def L():
+    from etr_b200 import CustomLayers
+    return CustomLayers
+
+
+def _names(F):
+    return [f"f{i}" for i in range(F)]
+
+
+def _dict_inputs(X, names, rank2_every=2):
+    d = {}
+    for i, n in enumerate(names):
+        col = torch.tensor(X[:, i])
+        d[n] = col.reshape(-1, 1) if i % rank2_every == 0 else col       # mix [B,1] and [B] like Keras Input / tf.constant
+    return d
+
+
+# ------------------------------------------------------------------ gather
+@pytest.mark.parametrize("V,k,dtype", [(20, 16, "float32"), (1000, 8, "float32"), (777, 10, "float32"),
+                                        (5000, 64, "float32"), (300, 16, "bfloat16"), (300, 64, "bfloat16")])
+def test_embedding_gather_bit_exact(L, V, k, dtype):
+    emb = L.Embedding(V, k, table_dtype=dtype, seed=1)
+    rng = np.random.default_rng(0)
+    ids = rng.integers(0, V, size=(37, 5))
+    out = emb(torch.tensor(ids))
+    ref = emb.embeddings.float().cpu()[torch.tensor(ids)]
+    assert out.shape == (37, 5, k)
+    assert torch.equal(out.cpu(), ref)                         # gathered rows bit-exact
+
+
+def test_out_of_range_id_raises(L):
+    from etr_b200 import EtrIdRangeError
+    lay = L.FMRankingLayer(_names(3), feature_dims=20, embedding_dims=16)
+    with pytest.raises(EtrIdRangeError):
+        lay(torch.tensor([[0, 1, 20]]))
+    with pytest.raises(IndexError):
+        lay(torch.tensor([[0, -1, 2]]))
+    out = lay(torch.tensor([[0, 1, 19]]))["output"]           # error word was cleared
+    assert out.shape == (1, 1)
+
+
+# -------------------------------------------------------------- FM forward
+@pytest.mark.parametrize("B,F,k,V", [(3, 3, 16, 20), (4096, 26, 16, 160000), (257, 5, 8, 5600), (100, 7, 10, 999),
+                                      (64, 26, 64, 4000), (33, 4, 128, 500), (1, 1, 4, 3)])
+def test_fm_forward_matches_oracle(L, B, F, k, V):
+    rng = np.random.default_rng(B + F)
+    lay = L.FMRankingLayer(_names(F), feature_dims=V, embedding_dims=k, seed=3)
+    X = zipf_ids(rng, [V // F] * F, B) if V >= F else rng.integers(0, V, size=(B, F))
+    out = lay(_dict_inputs(X, lay.feature_names))["output"]
+    assert out.shape == (B, 1) and out.dtype == torch.float32
+    ref32 = oracle_fm(lay, torch.float32).call(torch.tensor(X))["output"].detach().numpy()
+    ref64 = oracle_fm(lay, torch.float64).call(torch.tensor(X))["output"].detach().numpy()
+    assert_close(out.cpu().numpy(), ref32, FP32_RTOL, "vs fp32 oracle")
+    assert_close(out.cpu().numpy(), ref64, FP32_RTOL, "vs fp64 oracle")
+    # [B,F] matrix input is the same function
+    out2 = lay(torch.tensor(X))["output"]
+    assert torch.equal(out, out2)
+
+
+def test_fm_reference_docstring_inputs(L):
+    """2.FM/CustomLayers.py:88-90 docstring: ids 0..8 over 3 features, V=20."""
+    lay = L.FMRankingLayer(feature_names=['item_tag1', 'item_tag2', 'item_tag3'])
+    inp = {'item_tag1': torch.tensor([0, 1, 2]), 'item_tag2': torch.tensor([3, 4, 5]),
+           'item_tag3': torch.tensor([6, 7, 8])}
+    out = lay(inp)["output"]
+    X = torch.tensor([[0, 3, 6], [1, 4, 7], [2, 5, 8]])
+    assert_close(out.cpu().numpy(), oracle_fm(lay).call(X)["output"].detach().numpy(), FP32_RTOL)
+    assert [tuple(v.shape) for v in lay.variables] == [(1,), (20, 16), (20, 1)]      # bias, embed, w
+
+
+def test_fm_numpy_and_dlpack_inputs(L):
+    lay = L.FMRankingLayer(_names(4), feature_dims=50, embedding_dims=16)
+    X = np.random.default_rng(5).integers(0, 50, size=(9, 4))
+    a = lay({n: X[:, i] for i, n in enumerate(lay.feature_names)})["output"]
+
+    class Producer:                       # any DLPack producer (tf.Tensor implements the same protocol)
+        def __init__(self, t):
+            self.t = t
+
+        def __dlpack__(self, **kw):
+            return self.t.__dlpack__(**kw)
+
+        def __dlpack_device__(self):
+            return self.t.__dlpack_device__()
+
+        shape = property(lambda s: s.t.shape)
+
+    b = lay({n: Producer(torch.tensor(X[:, i]).cuda()) for i, n in enumerate(lay.feature_names)})["output"]
+    assert torch.equal(a, b)
+    assert torch.equal(torch.from_dlpack(a), a)                # output exports DLPack
+
+
+def test_fm_bf16_table(L):
+    rng = np.random.default_rng(11)
+    lay = L.FMRankingLayer(_names(26), feature_dims=10000, embedding_dims=16, table_dtype="bfloat16")
+    X = rng.integers(0, 10000, size=(512, 26))
+    out = lay(torch.tensor(X))["output"]
+    ref = oracle_fm(lay, torch.float64).call(torch.tensor(X))["output"].detach().numpy()   # same (rounded) weights
+    assert_close(out.cpu().numpy(), ref, FP32_RTOL, "bf16 rows, fp32 accumulate")
+
+
+# --------------------------------------------------------------------- bags
+@pytest.mark.parametrize("pooling", ["sum", "mean"])
+@pytest.mark.parametrize("Lmax", [1, 5, 50])
+def test_fm_bags_padded_and_csr(L, pooling, Lmax):
+    rng = np.random.default_rng(Lmax)
+    B, F, k, V = 65, 6, 16, 400
+    lay = L.FMRankingLayer(_names(F), feature_dims=V, embedding_dims=k, pad_id=0, pooling=pooling)
+    lens = rng.integers(0 if Lmax > 1 else 1, Lmax + 1, size=(B, F))      # empty bags included
+    X = np.zeros((B, F, Lmax), dtype=np.int64)
+    for b in range(B):
+        for f in range(F):
+            X[b, f, : lens[b, f]] = rng.integers(1, V, size=lens[b, f])
+    out = lay(torch.tensor(X))["output"]
+    ref = oracle_fm(lay, torch.float64).call(torch.tensor(X))["output"].detach().numpy()
+    assert_close(out.cpu().numpy(), ref, FP32_RTOL, "padded bags")
+    # CSR form of the same bags
+    from etr_b200 import IdsBatch
+    vals = np.concatenate([X[b, f, : lens[b, f]] for b in range(B) for f in range(F)] + [np.zeros(0, np.int64)])
+    offs = np.concatenate([[0], np.cumsum(lens.ravel())]).astype(np.int32)
+    ids = IdsBatch.from_csr(lay.rt, vals, offs, B, F, pooling=pooling)
+    out_csr = lay(ids)["output"]
+    assert_close(out_csr.cpu().numpy(), ref, FP32_RTOL, "CSR bags")
+
+
+def test_bag_L1_is_single_hot(L):
+    lay = L.FMRankingLayer(_names(5), feature_dims=100, embedding_dims=16, pad_id=None)
+    X = np.random.default_rng(1).integers(0, 100, size=(40, 5))
+    assert torch.equal(lay(torch.tensor(X))["output"], lay(torch.tensor(X[:, :, None]))["output"])
+
+
+# ------------------------------------------------------------- FM backward
+def _fm_grad_check(L, lay, orc, X, rtol):
+    B = X.shape[0]
+    rng = np.random.default_rng(7)
+    dz = rng.normal(size=(B,)).astype(np.float32)
+    lay(torch.tensor(X), training=True)
+    grads = lay.backward(torch.tensor(dz).cuda())
+    ids, rows = grads[0].indexed_slices()
+    z = orc.logit(torch.tensor(X))
+    (z.squeeze(1) * torch.tensor(dz, dtype=z.dtype)).sum().backward()
+    k = lay.embedding_dims
+    full = torch.cat([orc.embed.grad, orc.w.grad], dim=1)
+    ref_ids, ref_rows = dense_table_grad_to_slices(full)
+    got_ids = ids.cpu().numpy()
+    keep = np.abs(rows.cpu().numpy()).sum(1) > 0
+    assert np.array_equal(got_ids[keep], ref_ids)               # ID routing bit-exact
+    assert_close(rows.cpu().numpy()[keep], ref_rows, rtol, "table grads (IndexedSlices, dedup'd)")
+    assert_close(lay.params.g("bias").cpu().numpy(), orc.bias.grad.numpy(), rtol, "bias grad")
+
+
+@pytest.mark.parametrize("B,F,k,V", [(16, 3, 16, 20), (4096, 26, 16, 160000), (300, 5, 8, 64), (128, 26, 64, 3000)])
+def test_fm_backward_matches_autograd(L, B, F, k, V):
+    rng = np.random.default_rng(B)
+    lay = L.FMRankingLayer(_names(F), feature_dims=V, embedding_dims=k, seed=2)
+    X = zipf_ids(rng, [V // F] * F, B)
+    _fm_grad_check(L, lay, oracle_fm(lay, torch.float64), X, FP32_RTOL)
+
+
+def test_fm_backward_bags_mean(L):
+    rng = np.random.default_rng(4)
+    B, F, Lm, V = 50, 4, 7, 60
+    lay = L.FMRankingLayer(_names(F), feature_dims=V, embedding_dims=16, pad_id=0, pooling="mean")
+    X = rng.integers(0, V, size=(B, F, Lm))                    # zeros are pads
+    _fm_grad_check(L, lay, oracle_fm(lay, torch.float64), X, FP32_RTOL)
+
+
+# ------------------------------------------------- segment reduce: long runs
+def test_segment_reduce_long_runs(L):
+    """ids drawn from 3 values -> runs far longer than the short-run and chunk
+    thresholds (64 / 1024); result must equal an fp64 scatter-add."""
+    from etr_b200 import EmbeddingTable, IdsBatch, Runtime, SparseGrad
+    rt = Runtime.get()
+    rng = np.random.default_rng(0)
+    B, F = 20000, 2
+    X = np.stack([rng.integers(0, 3, size=B), 3 + (rng.random(B) ** 3 * 5000).astype(np.int64)], axis=1)
+    table = EmbeddingTable(rt, 6000, 17)
+    ids = IdsBatch.from_matrix(rt, X)
+    g = torch.randn(B * F, table.grad_ld, device=rt.device)
+    sg = SparseGrad(table, ids, g).reduce()
+    uid, rows = sg.indexed_slices()
+    ref = np.zeros((6000, 17))
+    np.add.at(ref, X.ravel(), g.cpu().numpy().astype(np.float64)[:, :17])
+    ref_ids = np.unique(X)
+    assert np.array_equal(uid.cpu().numpy(), ref_ids)
+    got = rows.cpu().numpy()
+    # fp32 summation of up to ~7000 N(0,1) terms: error ~ 1e-7 * sqrt(n) * |terms|
+    assert np.max(np.abs(got - ref[ref_ids])) < 2e-3
+    sg2 = SparseGrad(table, ids, g).reduce()
+    assert torch.equal(sg2.indexed_slices()[1], rows)           # deterministic
+
+
+# ------------------------------------------------------------------ DeepFM
+@pytest.mark.parametrize("B,F,k,V,C", [(4, 5, 8, 20, 0), (513, 26, 16, 50000, 13), (200, 5, 16, 300, 3)])
+def test_deepfm_forward_backward(L, B, F, k, V, C):
+    rng = np.random.default_rng(B)
+    cont = [f"c{i}" for i in range(C)]
+    lay = L.DeepFMRankingLayer(_names(F), feature_dims=V, embedding_dims=k, continuous_features=cont, seed=5)
+    X = zipf_ids(rng, [V // F] * F, B)
+    Xc = rng.normal(size=(B, C)).astype(np.float32)
+    inputs = _dict_inputs(X, lay.feature_names)
+    inputs.update({n: torch.tensor(Xc[:, i]) for i, n in enumerate(cont)})
+    out = lay(inputs, training=True)["output"]
+    orc = oracle_deepfm(lay, torch.float64)
+    xc64 = torch.tensor(Xc, dtype=torch.float64) if C else None
+    z = orc.logit(torch.tensor(X), xc64)
+    assert_close(out.cpu().numpy(), torch.sigmoid(z).detach().numpy(), FP32_RTOL, "DeepFM output")
+    orc32 = oracle_deepfm(lay, torch.float32)
+    z32 = orc32.logit(torch.tensor(X), torch.tensor(Xc) if C else None)
+    assert_close(out.cpu().numpy(), torch.sigmoid(z32).detach().numpy(), FP32_RTOL, "DeepFM output vs fp32")
+    dz = rng.normal(size=(B,)).astype(np.float32)
+    grads = lay.backward(torch.tensor(dz).cuda())
+    (z.squeeze(1) * torch.tensor(dz, dtype=torch.float64)).sum().backward()
+    ids, rows = grads[0].indexed_slices()
+    full = torch.cat([orc.embed.grad, orc.w.grad], dim=1)
+    ref_ids, ref_rows = dense_table_grad_to_slices(full)
+    assert np.array_equal(ids.cpu().numpy(), ref_ids)
+    assert_close(rows.cpu().numpy(), ref_rows, FP32_RTOL, "DeepFM table grads")
+    for dev_mlp, o_mlp in ((lay.MLP_layer1, orc.MLP_layer1), (lay.MLP_layer2, orc.MLP_layer2)):
+        for i in range(len(dev_mlp.units)):
+            assert_close(lay.params.g(f"{dev_mlp.name}/kernel_{i}").cpu().numpy(), o_mlp.kernels[i].grad.numpy(),
+                         FP32_RTOL, f"{dev_mlp.name} kernel_{i} grad")
+            assert_close(lay.params.g(f"{dev_mlp.name}/bias_{i}").cpu().numpy(), o_mlp.biases[i].grad.numpy(),
+                         FP32_RTOL, f"{dev_mlp.name} bias_{i} grad")
+
+
+def test_deepfm_reference_docstring(L):
+    """2.FM/CustomLayers.py:242-254 docstring inputs; embedding_dims=8."""
+    lay = L.DeepFMRankingLayer(embedding_dims=8)
+    inp = {'user_tag0': torch.tensor([12, 13, 14, 15]), 'user_tag1': torch.tensor([16, 17, 18, 19]),
+           'item_tag1': torch.tensor([0, 1, 2, 3]), 'item_tag2': torch.tensor([4, 5, 6, 7]),
+           'item_tag3': torch.tensor([8, 9, 10, 11])}
+    out = lay(inp)["output"]
+    X = torch.stack([inp[n] for n in lay.feature_names], dim=1)
+    ref = torch.sigmoid(oracle_deepfm(lay, torch.float64).logit(X)).detach().numpy()
+    assert_close(out.cpu().numpy(), ref, FP32_RTOL)
+
+
+# --------------------------------------------------------------- train step
+@pytest.mark.parametrize("mode", ["rowwise", "keras_dense"])
+@pytest.mark.parametrize("model", ["fm", "deepfm"])
+def test_train_steps_match_oracle_adam(L, mode, model):
+    """3 steps of the reference train loop (BCE -> tape.gradient -> Adam,
+    2.FM/ModelManager.py:171-181): weights after each step vs the CPU oracle."""
+    rng = np.random.default_rng(9)
+    B, F, k, V = 256, 6, 16, 120
+    if model == "fm":
+        lay = L.FMRankingLayer(_names(F), feature_dims=V, embedding_dims=k, seed=8)
+        orc = oracle_fm(lay, torch.float64)
+    else:
+        lay = L.DeepFMRankingLayer(_names(F), feature_dims=V, embedding_dims=k, seed=8)
+        orc = oracle_deepfm(lay, torch.float64)
+    tr = L.Trainer(lay, lr=1e-2, apply_mode=mode)
+    opt = R.KerasAdam(lr=1e-2, mode=mode)
+    for step in range(3):
+        X = zipf_ids(rng, [V // F] * F, B)
+        y = (rng.random(B) < 0.25).astype(np.float32)
+        loss = tr.train_step(torch.tensor(X), torch.tensor(y))
+        # oracle step
+        for v in orc.variables():
+            v.grad = None
+        p = torch.sigmoid(orc.logit(torch.tensor(X)))
+        l_ref = R.keras_bce(torch.tensor(y, dtype=torch.float64).reshape(-1, 1), p)
+        l_ref.backward()
+        lr_t = opt.step_begin()
+        sparse = {id(orc.embed), id(orc.w)}
+        for v in orc.variables():
+            if id(v) in sparse:
+                nz, rows = R.dedup_dense_grad(v.grad)
+                opt.apply_sparse(v, nz, rows, lr_t)
+            else:
+                opt.apply_dense(v, v.grad, lr_t)
+        assert abs(float(loss.item()) - float(l_ref)) <= 1e-5 * abs(float(l_ref)), step
+        # Adam divides by sqrt(v)+eps: tiny grads are amplified, so compare updates at 1e-4 of the step size
+        assert_close(cpu(lay.embed).numpy(), orc.embed.detach().numpy(), 2e-5, f"embed after step {step}")
+        assert_close(cpu(lay.w).numpy(), orc.w.detach().numpy(), 2e-5, f"w after step {step}")
+        assert_close(cpu(lay.bias).numpy(), orc.bias.detach().numpy(), 2e-5, f"bias after step {step}")
+
+
+# --------------------------------------------------------------------- GEMM
+@pytest.mark.parametrize("M,N,K,ta,tb", [(513, 32, 429, 0, 0), (1000, 8, 32, 0, 0), (777, 1, 8, 0, 0),
+                                           (429, 32, 20000, 1, 0), (300, 429, 32, 0, 1), (130, 70, 50, 1, 1),
+                                           (64, 1677, 1677, 0, 1)])
+def test_gemm_f32(L, M, N, K, ta, tb):
+    from etr_b200 import Runtime
+    from etr_b200.runtime import gemm_f32
+    rt = Runtime.get()
+    g = torch.Generator(device=rt.device)
+    g.manual_seed(M + N)
+    A = torch.randn((K, M) if ta else (M, K), device=rt.device, generator=g)
+    Bm = torch.randn((N, K) if tb else (K, N), device=rt.device, generator=g)
+    bias = torch.randn(N, device=rt.device, generator=g)
+    Cm = rt.empty((M, N))
+    gemm_f32(rt, A, Bm, Cm, M, N, K, A.stride(0), Bm.stride(0), N, trans_a=bool(ta), trans_b=bool(tb), bias=bias,
+             act="relu")
+    ref = torch.relu((A.double().T if ta else A.double()) @ (Bm.double().T if tb else Bm.double()) + bias.double())
+    err = (Cm.double() - ref).abs().max().item()
+    assert err <= 1e-5 * ref.abs().max().item() * max(1.0, (K / 1000) ** 0.5), err
