@@ -1,0 +1,367 @@
+#!/usr/bin/env python
+"""Headline benchmark: DeepFM train step (fwd + bwd + Adam) on synthetic
+Criteo-shaped data (BASELINE.json configs[1]): 13 dense + 26 sparse fields,
+33.76 M-row shared table, k = 16, batch 65 536, fp32.
+
+  python bench.py --gpus N --steps K --warmup W        # this framework (CUDA)
+  python bench.py --impl reference ...                 # CPU restatement of the reference
+
+Prints ONE JSON line (see the task contract).  ``value`` = samples/s with the
+inputs resident in HBM; ``e2e`` = the same step through the public layer API
+from pinned HOST buffers (H2D of the 39 input columns + labels and a D2H read
+of the loss inside the timed region); ``roofline`` = the fused gather + FM
+kernel against the measured HBM copy peak; ``cpu_baseline`` = the oracle port
+timed on this box's host cores on a bounded sample.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+
+CRITEO_CARDS = [1460, 583, 10131227, 2202608, 305, 24, 12517, 633, 3, 93145, 5683, 8351593, 3194, 27, 14992,
+                5461306, 10, 5652, 2173, 4, 7046547, 18, 15, 286181, 105, 142572]      # sum = 33 762 577
+F, K_EMB, C_DENSE = 26, 16, 13
+BATCH = 65536
+SEED = 20261          # 20260 + config index
+
+
+def make_batches(n_batches: int, B: int, dist: str, seed: int = SEED):
+    """SURVEY 8d id space: field f owns [offset_f, offset_f + card_f)."""
+    rng = np.random.Generator(np.random.PCG64(seed))
+    cards = np.asarray(CRITEO_CARDS, dtype=np.int64)
+    offs = np.concatenate([[0], np.cumsum(cards)[:-1]])
+    out = []
+    for _ in range(n_batches):
+        u = rng.random((B, F))
+        r = np.floor(cards[None, :] * (u ** 3 if dist == "zipf" else u)).astype(np.int64)
+        X = offs[None, :] + np.minimum(r, cards[None, :] - 1)
+        Xc = rng.standard_normal((B, C_DENSE)).astype(np.float32)
+        y = (rng.random(B) < 0.25).astype(np.float32)
+        out.append((X, Xc, y))
+    return out
+
+
+def load_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return float(d["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+class ClockSampler:
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index: int):
+        self.path = f"/tmp/etr_clocks_{os.getpid()}.csv"
+        self.proc = None
+        self.idx = gpu_index
+
+    def start(self):
+        try:
+            self.fh = open(self.path, "w")
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.idx), f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "100"], stdout=self.fh,
+                                         stderr=subprocess.DEVNULL)
+        except Exception:
+            self.proc = None
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        self.fh.close()
+        sm, mx, reasons = [], [], set()
+        for line in open(self.path):
+            parts = [p.strip() for p in line.split(",")]
+            if len(parts) < 9:
+                continue
+            try:
+                sm.append(float(parts[1])); mx.append(float(parts[2]))
+            except ValueError:
+                continue
+            for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"),
+                                 parts[5:9]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        try:
+            os.remove(self.path)
+        except OSError:
+            pass
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
+        # "under load": the upper half of the samples (idle samples at the ends drag the median down)
+        sm_sorted = sorted(sm)
+        load = sm_sorted[len(sm_sorted) // 2:]
+        return {"sm_mhz": statistics.median(load), "sm_max_mhz": max(mx), "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+def cpu_baseline_run(budget_s: float, B_cpu: int, n_batches: int, dist: str):
+    import torch
+    from oracle.cpu_baseline import DeepFMCpuStep, time_cpu_steps
+    V = int(sum(CRITEO_CARDS))
+    stepper = DeepFMCpuStep(V, F, K_EMB, C_DENSE, mode="rowwise")
+    batches = [(torch.from_numpy(X), torch.from_numpy(Xc), torch.from_numpy(y))
+               for X, Xc, y in make_batches(n_batches, B_cpu, dist, seed=SEED + 1)]
+    sps, steps, secs = time_cpu_steps(stepper, batches, budget_s=budget_s)
+    return {"value": sps, "unit": "samples/s", "cores": stepper.threads, "kind": "port",
+            "sample": f"{steps} DeepFM train steps of batch {B_cpu} ({steps * B_cpu} samples, {secs:.1f} s) on the "
+                      f"same 33.76M-row Criteo-shaped workload; torch-CPU fp32 restatement of the reference "
+                      f"(TensorFlow unavailable), row-wise Adam"}
+
+
+def run_reference(args):
+    """--impl reference: the reference's CPU path for this step.  TensorFlow 2.8
+    cannot be installed in this image, so this times the op-for-op CPU
+    restatement (oracle port) with every host thread."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    B_cpu = 8192
+    budget = 12.0
+    import torch
+    from oracle.cpu_baseline import DeepFMCpuStep
+    V = int(sum(CRITEO_CARDS))
+    stepper = DeepFMCpuStep(V, F, K_EMB, C_DENSE, mode="rowwise")
+    batches = [(torch.from_numpy(X), torch.from_numpy(Xc), torch.from_numpy(y))
+               for X, Xc, y in make_batches(4, B_cpu, args.dist, seed=SEED + 1)]
+    for i in range(max(args.warmup, 1)):
+        stepper.step(*batches[i % 4])
+    # a "step" here is a bounded sample (one 8192-sample batch) of the 65 536-sample workload step
+    steps = max(1, min(args.steps, 200))
+    t0 = time.perf_counter()
+    done = 0
+    for i in range(steps):
+        stepper.step(*batches[i % 4])
+        done += 1
+        if time.perf_counter() - t0 > 120:
+            break
+    dt = time.perf_counter() - t0
+    sps = done * B_cpu / dt
+    line = {
+        "impl": "reference", "metric": "train samples/sec DeepFM (Criteo-shape)", "value": sps, "unit": "samples/s",
+        "n_gpus": args.gpus, "steps": done, "warmup": max(args.warmup, 1), "ms_per_step": 1e3 * dt / done,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": workload_config(args, B_cpu, graph=False),
+        "cpu_baseline": {"value": sps, "unit": "samples/s", "cores": stepper.threads, "kind": "port",
+                         "sample": f"each step = one batch of {B_cpu} samples of the 65536-sample workload step"},
+        "e2e": {"value": sps, "unit": "samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line))
+
+
+def workload_config(args, B, graph):
+    return {"workload": "c2: DeepFM train step (fwd+bwd+Adam), Criteo shape: 13 dense + 26 sparse, one shared "
+                        "33 762 577-row table, k=16, MLP [429->32->8->1]",
+            "global_batch": B * max(args.gpus, 1), "per_gpu_batch": B, "table_rows": int(sum(CRITEO_CARDS)),
+            "embedding_dims": K_EMB, "table_dtype": "f32", "mlp": "fp32 SIMT", "id_distribution": args.dist,
+            "apply_mode": "rowwise Adam", "parallelism": f"dp{max(args.gpus, 1)}",
+            "l2": "L2 flushed (512 MiB write) before every timed step", "cuda_graph": graph}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=30)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="etr", choices=["etr", "reference"])
+    ap.add_argument("--dist", default="zipf", choices=["zipf", "uniform"])
+    ap.add_argument("--batch", type=int, default=BATCH)
+    ap.add_argument("--no-graph", action="store_true")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--cpu-budget", type=float, default=12.0)
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3)
+    if args.impl == "reference":
+        return run_reference(args)
+
+    import torch
+    import torch.distributed as dist
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    import etr_b200  # noqa: F401
+    from etr_b200 import CustomLayers as L
+    from etr_b200.runtime import IdsBatch, gather_fm_forward
+
+    dev = torch.device("cuda", local_rank)
+    B = args.batch
+    V = int(sum(CRITEO_CARDS))
+    names = [f"C{i + 1}" for i in range(F)]
+    cont = [f"I{i + 1}" for i in range(C_DENSE)]
+    # Replicas only at N>1 for this config: each rank owns a full copy of
+    # the table and its own batch; the row-sharded path is the c5 config.
+    layer = L.DeepFMRankingLayer(names, feature_dims=V, embedding_dims=K_EMB, continuous_features=cont,
+                                 seed=1 + rank, check_ids=False)
+    rt = layer.rt
+    n_batches = 6
+    host = make_batches(n_batches, B, args.dist, seed=SEED + 17 * rank)
+    pinned = []
+    for X, Xc, y in host:
+        d = {n: torch.from_numpy(np.ascontiguousarray(X[:, i])).pin_memory() for i, n in enumerate(names)}
+        d.update({n: torch.from_numpy(np.ascontiguousarray(Xc[:, i])).pin_memory() for i, n in enumerate(cont)})
+        pinned.append((d, torch.from_numpy(y).pin_memory()))
+    dev_batches = []
+    for X, Xc, y in host:
+        ids = torch.from_numpy(np.ascontiguousarray(X.T)).to(dev)            # field-major [F,B]
+        dev_batches.append((ids, torch.from_numpy(np.ascontiguousarray(Xc.T)).to(dev), torch.from_numpy(y).to(dev)))
+
+    use_graph = not args.no_graph
+    trainer = L.Trainer(layer, lr=1e-3, apply_mode="rowwise", graph=use_graph)
+    flush = torch.empty(512 << 20, dtype=torch.uint8, device=dev)
+
+    def stage_from_device(i):
+        ids, xc, y = dev_batches[i % n_batches]
+        batch = trainer.stage({**{n: ids[f] for f, n in enumerate(names)}, **{n: xc[c] for c, n in enumerate(cont)}}, y)
+        return batch
+
+    # ---- warm-up (also captures the graph)
+    try:
+        for i in range(args.warmup):
+            b = stage_from_device(i)
+            trainer.train_step(b)
+        torch.cuda.synchronize(dev)
+    except Exception as e:  # graph capture failed on this box: fall back to eager launches, say so
+        if not use_graph:
+            raise
+        sys.stderr.write(f"[bench] CUDA-graph capture failed ({e!r}); falling back to eager launches\n")
+        torch.cuda.synchronize(dev)
+        use_graph = False
+        trainer = L.Trainer(layer, lr=1e-3, apply_mode="rowwise", graph=False)
+        for i in range(args.warmup):
+            b = stage_from_device(i)
+            trainer._eager_step(b)
+        torch.cuda.synchronize(dev)
+    step_fn = trainer.train_step if use_graph else trainer._eager_step
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    # ---- timed region 1: inputs resident in HBM (value)
+    clocks = ClockSampler(local_rank)
+    launches0 = rt.launches
+    barrier()
+    clocks.start()
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    for i in range(args.steps):
+        b = stage_from_device(args.warmup + i)
+        flush.zero_()                                   # evict L2 (untimed)
+        ev[i][0].record()
+        step_fn(b)
+        ev[i][1].record()
+    barrier()
+    step_ms = [a.elapsed_time(b_) for a, b_ in ev]
+    total_ms = sum(step_ms)
+    eager_launches_per_step = None
+    if not use_graph:
+        eager_launches_per_step = (rt.launches - launches0) / args.steps
+
+    # ---- timed region 2: end to end from pinned host buffers through the public API
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t_wall0 = time.perf_counter()
+    e0.record()
+    last = 0.0
+    for i in range(args.steps):
+        d, y = pinned[(args.warmup + i) % n_batches]
+        loss = trainer.train_step(d, y) if use_graph else trainer._eager_step(d, y)
+        last = float(loss.item())                       # D2H read of the step's result
+    e1.record()
+    barrier()
+    e2e_ms = max(e0.elapsed_time(e1), 1e3 * (time.perf_counter() - t_wall0))
+    clk = clocks.stop()
+    h2d = F * B * 8 + C_DENSE * B * 4 + B * 4
+    d2h = 4
+
+    # ---- launches per step (count one eager step; the graph replays exactly these)
+    l0 = rt.launches
+    trainer._eager_step(stage_from_device(0))
+    torch.cuda.synchronize(dev)
+    launches_per_step = rt.launches - l0
+
+    # ---- roofline of the fused gather + FM kernel, timed alone, L2 flushed
+    ids0 = IdsBatch(rt, dev_batches[0][0], B, F, 1, 1, B, 1)
+    x = rt.empty((B, C_DENSE + F * K_EMB))
+    logit = rt.empty((B,))
+    kt = []
+    for i in range(max(args.steps, 10)):
+        ids_i = IdsBatch(rt, dev_batches[i % n_batches][0], B, F, 1, 1, B, 1)
+        flush.zero_()
+        a, b_ = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        gather_fm_forward(layer.table, K_EMB, True, ids_i, bias=layer.bias, logit=logit, flat=x, flat_col0=C_DENSE)
+        b_.record()
+        kt.append((a, b_))
+    torch.cuda.synchronize(dev)
+    k_ms = statistics.mean(a.elapsed_time(b_) for a, b_ in kt[2:])
+    peak, peak_src = load_peaks()
+    # algorithmic bytes per sample: F*(k*4 + 4 [w] + 8 [id]) + 4 [logit]  (+ F*k*4 flat written for the MLP)
+    alg_fm = F * (K_EMB * 4 + 4 + 8) + 4
+    alg_flat = F * K_EMB * 4
+    achieved = (alg_fm + alg_flat) * B / (k_ms * 1e-3) / 1e9
+    del ids0
+
+    # ---- max over ranks
+    t = torch.tensor([total_ms, e2e_ms], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    total_ms, e2e_ms = float(t[0]), float(t[1])
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    value = B * world * args.steps / (total_ms * 1e-3)
+    e2e_value = B * world * args.steps / (e2e_ms * 1e-3)
+    cpu = None
+    if world == 1 and not args.no_cpu_baseline:
+        cpu = cpu_baseline_run(args.cpu_budget, 8192, 4, args.dist)
+    line = {
+        "metric": "train samples/sec DeepFM (Criteo-shape)", "value": value, "unit": "samples/s",
+        "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": total_ms / args.steps,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": workload_config(args, B, use_graph),
+        "clocks": clk,
+        "e2e": {"value": e2e_value, "unit": "samples/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                "ms_per_step": e2e_ms / args.steps, "last_loss": last},
+        "gpu_launches": launches_per_step * args.steps,
+        "gpu_launches_per_step": launches_per_step,
+        "roofline": {"bound": "hbm", "kernel": "gather_fm_fwd_kernel (gather + FM terms + Flatten, one launch)",
+                     "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                     "traffic": None, "peak_source": peak_src, "kernel_ms": k_ms,
+                     "algorithmic_bytes_per_launch": (alg_fm + alg_flat) * B,
+                     "note": "algorithmic bytes = B*(F*(4k+4+8)+4) FM terms + B*F*k*4 flattened operand written "
+                             "for the MLP; timed alone with CUDA events, L2 flushed before each launch"},
+        "step_ms_min_median_max": [min(step_ms), statistics.median(step_ms), max(step_ms)],
+    }
+    if cpu:
+        line["cpu_baseline"] = cpu
+    print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

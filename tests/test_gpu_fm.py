@@ -313,3 +313,26 @@ def test_gemm_f32(L, M, N, K, ta, tb):
     ref = torch.relu((A.double().T if ta else A.double()) @ (Bm.double().T if tb else Bm.double()) + bias.double())
     err = (Cm.double() - ref).abs().max().item()
     assert err <= 1e-5 * ref.abs().max().item() * max(1.0, (K / 1000) ** 0.5), err
+
+
+def test_graph_trainer_matches_eager(L):
+    """The captured-CUDA-graph train step (static staged inputs, device-resident
+    optimizer clock) must produce exactly the eager step's weights."""
+    rng = np.random.default_rng(21)
+    B, F, k, V, C = 512, 6, 16, 3000, 3
+    names, cont = _names(F), [f"c{i}" for i in range(C)]
+    lays = [L.DeepFMRankingLayer(names, feature_dims=V, embedding_dims=k, continuous_features=cont, seed=4)
+            for _ in range(2)]
+    trs = [L.Trainer(lays[0], lr=1e-2, graph=False), L.Trainer(lays[1], lr=1e-2, graph=True)]
+    for step in range(4):
+        X = zipf_ids(rng, [V // F] * F, B)
+        Xc = rng.normal(size=(B, C)).astype(np.float32)
+        y = (rng.random(B) < 0.3).astype(np.float32)
+        d = {n: torch.tensor(X[:, i]) for i, n in enumerate(names)}
+        d.update({n: torch.tensor(Xc[:, i]) for i, n in enumerate(cont)})
+        la = trs[0].train_step(d, torch.tensor(y))
+        lb = trs[1].train_step(d, torch.tensor(y))
+        assert float(la.item()) == float(lb.item()), step
+    assert torch.equal(lays[0].table.data, lays[1].table.data)
+    assert torch.equal(lays[0].params.value, lays[1].params.value)
+    assert trs[1].iterations == 4 + 2        # 2 warm-up steps precede the capture ... on the same batch
