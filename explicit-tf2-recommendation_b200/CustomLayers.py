@@ -21,7 +21,7 @@ import torch
 
 from . import _lib
 from ._lib import check
-from .dense import DenseLayer, DenseParams, MLPLayer, glorot_uniform, random_normal
+from .dense import DenseLayer, DenseParams, MLPLayer, glorot_uniform, random_normal  # noqa: F401
 from .runtime import (EmbeddingTable, IdsBatch, Runtime, SparseGrad, SparsePlan, bce_forward_backward,
                       embedding_gather, gather_fm_backward, gather_fm_forward, lr_t, _p)
 
@@ -202,10 +202,13 @@ class DeepFMRankingLayer(FMRankingLayer):
         super().__init__(feature_names, feature_dims, embedding_dims, **kwargs)
 
     def _build_extra(self):
-        in_dim = len(self.continuous_features) + len(self.feature_names) * self.embedding_dims
+        C_ = len(self.continuous_features)
+        in_dim = C_ + len(self.feature_names) * self.embedding_dims
+        # front padding so that Flatten(emb) starts on a 16-byte boundary behind [pad | X_cont]
+        self.front_pad = (-C_) % 4
         self.MLP_layer1 = MLPLayer(units=self.mlp_dims, activation="relu", name="MLP_layer1")
         self.MLP_layer2 = MLPLayer(units=[1], name="MLP_layer2")
-        self.MLP_layer1.build(in_dim, self.params, self.gen)
+        self.MLP_layer1.build(in_dim, self.params, self.gen, front_pad=self.front_pad)
         self.MLP_layer2.build(self.mlp_dims[-1], self.params, self.gen)
 
     @property
@@ -221,11 +224,11 @@ class DeepFMRankingLayer(FMRankingLayer):
         ids = self._ids(inputs, self.feature_names)
         C_ = len(self.continuous_features)
         k, F = self.embedding_dims, len(self.feature_names)
-        x = rt.empty((ids.B, C_ + F * k))
-        if C_:
-            x[:, :C_] = self._cont(inputs, self.continuous_features)
+        col0 = self.front_pad + C_
+        x = rt.empty((ids.B, col0 + F * k))                  # [pad | X_cont | Flatten(emb)]
+        cont = self._cont(inputs, self.continuous_features) if C_ else None
         fm_logit = rt.empty((ids.B,))
-        gather_fm_forward(self.table, k, True, ids, bias=self.bias, logit=fm_logit, flat=x, flat_col0=C_)
+        gather_fm_forward(self.table, k, True, ids, bias=self.bias, logit=fm_logit, flat=x, flat_col0=col0, cont=cont)
         dnn = self.MLP_layer2(self.MLP_layer1(x, training=training), training=training)      # [B,1]
         prob = rt.empty((ids.B, 1))
         check(rt.lib.etr_add_sigmoid(rt.ctx, fm_logit.data_ptr(), dnn.data_ptr(), ids.B, None, prob.data_ptr(),
@@ -239,12 +242,547 @@ class DeepFMRankingLayer(FMRankingLayer):
         rt = self.rt
         ids = self._ctx["ids"]
         dl = dlogit.reshape(-1)
-        C_ = len(self.continuous_features)
+        col0 = self.front_pad + len(self.continuous_features)
         d_dnn = dl.clone().reshape(-1, 1)                    # d(fm+dnn)/d dnn = 1
         dh = self.MLP_layer2.backward(d_dnn)
-        dx = self.MLP_layer1.backward(dh)                    # [B, C + F*k]
-        bag = gather_fm_backward(self.table, self.embedding_dims, True, ids, dlogit=dl, dflat=dx, flat_col0=C_)
+        dx = self.MLP_layer1.backward(dh)                    # [B, pad + C + F*k]
+        bag = gather_fm_backward(self.table, self.embedding_dims, True, ids, dlogit=dl, dflat=dx, flat_col0=col0)
         check(rt.lib.etr_colsum_f32(rt.ctx, dl.data_ptr(), ids.B, 1, 1, self.params.g("bias").data_ptr(), rt.stream))
+        return [SparseGrad(self.table, ids, bag)]
+
+
+# ---------------------------------------------------------------------------
+class FieldAwareInteractionLayer(_Layer):
+    """``call(X[B,F]) -> [B,P,k]``: I[b,(a,c),:] = T[x_a,c,:] * T[x_c,a,:], a<c in
+    row-major order (2.FM/CustomLayers.py:428-462); weight ``v`` [V,F,k] with the
+    reference's ctor defaults feature_dims=20, embedding_dims=16 (:430)."""
+
+    def __init__(self, fields_cnt, feature_dims=20, embedding_dims=16, _table: Optional[EmbeddingTable] = None,
+                 **kwargs):
+        self._setup(kwargs)
+        self.fields_cnt, self.feature_dims, self.embedding_dims = int(fields_cnt), int(feature_dims), int(embedding_dims)
+        Fk = self.fields_cnt * self.embedding_dims
+        if _table is None:
+            self.table = EmbeddingTable(self.rt, self.feature_dims, Fk)
+            init = glorot_uniform((self.feature_dims, self.fields_cnt, self.embedding_dims), self.gen, self.rt.device)
+            self.table.data[:, :Fk] = init.reshape(self.feature_dims, Fk)
+            self.has_w = False
+        else:                                   # shared with an FFM/FwFM head (w fused at column F*k)
+            self.table, self.has_w = _table, True
+        self.params.finalize()
+
+    @property
+    def embedding_lookup_table(self) -> torch.Tensor:          # 'v' [V,F,k]
+        Fk = self.fields_cnt * self.embedding_dims
+        return self.table.data[:, :Fk].unflatten(1, (self.fields_cnt, self.embedding_dims))
+
+    def sparse_tables(self):
+        return [self.table]
+
+    def call(self, X, training: bool = False):
+        rt = self.rt
+        ids = IdsBatch.make(rt, X, None, self.pad_id, self.pooling)
+        F, k = self.fields_cnt, self.embedding_dims
+        assert ids.F == F
+        P = F * (F - 1) // 2
+        out = rt.empty((ids.B, P, k))
+        pooled = rt.empty((ids.B, F, F * k)) if training else None
+        t, d = self.table.desc(), ids.desc()
+        check(rt.lib.etr_field_pair_forward(rt.ctx, C.byref(t), k, int(self.has_w), C.byref(d), None, None, None,
+                                            out.data_ptr(), None, None, None, _p(pooled), rt.stream))
+        if training:
+            self._ctx = {"ids": ids, "pooled": pooled}
+        self._finish(training)
+        return out
+
+    def backward(self, dpairvec: torch.Tensor) -> List[SparseGrad]:
+        rt = self.rt
+        ids, pooled = self._ctx["ids"], self._ctx["pooled"]
+        bag = rt.empty((ids.B * ids.F, self.table.grad_ld))
+        d = ids.desc()
+        dpv = dpairvec.contiguous()
+        check(rt.lib.etr_field_pair_backward(rt.ctx, self.embedding_dims, int(self.has_w), C.byref(d),
+                                             pooled.data_ptr(), None, None, dpv.data_ptr(), bag.data_ptr(),
+                                             self.table.grad_ld, rt.stream))
+        return [SparseGrad(self.table, ids, bag)]
+
+
+class _FieldPairHead(_Layer):
+    """Shared body of FFMLayer / FwFMLayer / FFMRankingLayer: one fused HBM table
+    [V, F*k + 1] (pair rows + the linear weight w at column F*k), one kernel per
+    forward, one per backward."""
+
+    fwfm = False
+
+    def _init_head(self, feature_names, feature_dims, embedding_dims, kwargs, table_init):
+        self._setup(kwargs)
+        self.feature_names = list(feature_names)
+        self.feature_dims, self.embedding_dims = int(feature_dims), int(embedding_dims)
+        self.fields_cnt = len(self.feature_names)
+        F, k, V = self.fields_cnt, self.embedding_dims, self.feature_dims
+        self.P = F * (F - 1) // 2
+        self.params.add("bias", glorot_uniform((1,), self.gen, self.rt.device))
+        if self.fwfm:                                           # tf.keras.layers.Dense(1): glorot kernel, zero bias
+            self.params.add("interaction_weights/kernel", glorot_uniform((self.P, 1), self.gen, self.rt.device))
+            self.params.add("interaction_weights/bias", torch.zeros(1, device=self.rt.device))
+        self.table = EmbeddingTable(self.rt, V, F * k + 1)
+        table_init(self.table)
+        self.params.finalize()
+
+    @property
+    def bias(self):
+        return self.params["bias"]
+
+    @property
+    def w(self) -> torch.Tensor:
+        Fk = self.fields_cnt * self.embedding_dims
+        return self.table.cols(Fk, Fk + 1)
+
+    def sparse_tables(self):
+        return [self.table]
+
+    def call(self, inputs, training: bool = False):
+        rt = self.rt
+        ids = self._ids(inputs, self.feature_names)
+        F, k = self.fields_cnt, self.embedding_dims
+        prob = rt.empty((ids.B, 1))
+        pooled = rt.empty((ids.B, F, F * k)) if training else None
+        pairdot = rt.empty((ids.B, self.P)) if (training and self.fwfm) else None
+        r = self.params["interaction_weights/kernel"] if self.fwfm else None
+        r0 = self.params["interaction_weights/bias"] if self.fwfm else None
+        t, d = self.table.desc(), ids.desc()
+        check(rt.lib.etr_field_pair_forward(rt.ctx, C.byref(t), k, 1, C.byref(d), self.bias.data_ptr(), _p(r), _p(r0),
+                                            None, _p(pairdot), None, prob.data_ptr(), _p(pooled), rt.stream))
+        if training:
+            self._ctx = {"ids": ids, "pooled": pooled, "pairdot": pairdot}
+        self._finish(training)
+        return {"output": prob}
+
+    def backward(self, dlogit: torch.Tensor) -> List[SparseGrad]:
+        rt = self.rt
+        ids, pooled, pairdot = self._ctx["ids"], self._ctx["pooled"], self._ctx["pairdot"]
+        dl = dlogit.reshape(-1).contiguous()
+        bag = rt.empty((ids.B * ids.F, self.table.grad_ld))
+        r = self.params["interaction_weights/kernel"] if self.fwfm else None
+        d = ids.desc()
+        check(rt.lib.etr_field_pair_backward(rt.ctx, self.embedding_dims, 1, C.byref(d), pooled.data_ptr(),
+                                             dl.data_ptr(), _p(r), None, bag.data_ptr(), self.table.grad_ld,
+                                             rt.stream))
+        check(rt.lib.etr_colsum_f32(rt.ctx, dl.data_ptr(), ids.B, 1, 1, self.params.g("bias").data_ptr(), rt.stream))
+        if self.fwfm:
+            from .runtime import gemm_f32
+            # dr = pairdot^T dlogit  ([P,B] x [B,1]); dr0 = sum_b dlogit
+            gemm_f32(rt, pairdot, dl, self.params.g("interaction_weights/kernel"), self.P, 1, ids.B, self.P, 1, 1,
+                     trans_a=True)
+            check(rt.lib.etr_colsum_f32(rt.ctx, dl.data_ptr(), ids.B, 1, 1,
+                                        self.params.g("interaction_weights/bias").data_ptr(), rt.stream))
+        return [SparseGrad(self.table, ids, bag)]
+
+
+class FFMLayer(_FieldPairHead):
+    """sigma(bias + sum_f w[x_f] + sum_{p,k} I)  (2.FM/CustomLayers.py:465-497).
+
+    Decision on a reference quirk: the reference builds
+    ``FieldAwareInteractionLayer(self.fields_cnt)`` WITHOUT forwarding
+    feature_dims / embedding_dims (:477), so its pair table is always (20,F,16)
+    and any id >= 20 is out of range; here they are forwarded."""
+
+    def __init__(self, feature_names=['item_tag1', 'item_tag2', 'item_tag3', 'user_tag0', 'user_tag1'],
+                 feature_dims=20, embedding_dims=16, **kwargs):
+        def init(table):
+            F, k, V = len(feature_names), embedding_dims, feature_dims
+            table.data[:, :F * k] = glorot_uniform((V, F, k), self.gen, self.rt.device).reshape(V, F * k)
+            table.data[:, F * k:F * k + 1] = glorot_uniform((V, 1), self.gen, self.rt.device)   # add_weight default
+        self._init_head(feature_names, feature_dims, embedding_dims, kwargs, init)
+        self.fa_interaction_layer = FieldAwareInteractionLayer(self.fields_cnt, self.feature_dims,
+                                                               self.embedding_dims, _table=self.table,
+                                                               device=self.rt.device, pad_id=self.pad_id,
+                                                               pooling=self.pooling)
+
+    @property
+    def variables(self):
+        v = [self.bias, self.w, self.fa_interaction_layer.embedding_lookup_table]
+        if self.fwfm:
+            v += [self.params["interaction_weights/kernel"], self.params["interaction_weights/bias"]]
+        return v
+
+
+class FwFMLayer(FFMLayer):
+    """sigma(bias + sum w + Dense(1)(sum_k I))  (2.FM/CustomLayers.py:500-533)."""
+    fwfm = True
+
+
+class FFMRankingLayer(_FieldPairHead):
+    """F separate Embedding tables T_i [V,k] (2.FM/CustomLayers.py:370-425):
+    sum_{i<j} <T_i[x_j], T_j[x_i]> + sum w + bias -> sigma.  Stored as one fused
+    [V, F*k+1] table with T_i at columns i*k..(i+1)*k (T_i[v] == T[v,i], KAT-2)."""
+
+    def __init__(self, feature_names=['item_tag1', 'item_tag2', 'item_tag3'], feature_dims=20, embedding_dims=16,
+                 **kwargs):
+        self._init_head(feature_names, feature_dims, embedding_dims, kwargs,
+                        lambda table: table.init_uniform(-0.05, 0.05, self.gen))
+
+    @property
+    def embedding_list(self) -> List[torch.Tensor]:
+        k = self.embedding_dims
+        return [self.table.cols(i * k, (i + 1) * k) for i in range(self.fields_cnt)]
+
+    @property
+    def variables(self):
+        return [self.bias, self.w] + self.embedding_list
+
+
+# ---------------------------------------------------------------------------
+_PNN_TYPE = {"inner": 0, "mat": 1, "vec": 2, "num": 3}
+
+
+class InnerProductNetwork(_Layer):
+    """``call(x[B,F,k]) -> [B,P]``, out[b,p] = <x_i,x_j>, pairs i<j in combinations
+    order (2.FM/CustomLayers.py:601-624; vectorised twin IpnLayer :775-792)."""
+
+    kernel_type = "inner"
+
+    def __init__(self, **kwargs):
+        self._setup(kwargs)
+        self.kernel = None
+        self.params.finalize()
+
+    def call(self, x, training: bool = False):
+        rt = self.rt
+        x = rt.to_device(x, torch.float32).contiguous()
+        B, F, k = x.shape
+        P = F * (F - 1) // 2
+        out = rt.empty((B, P))
+        check(rt.lib.etr_pnn_forward(rt.ctx, x.data_ptr(), F * k, B, F, k, _PNN_TYPE[self.kernel_type],
+                                     _p(self.kernel), out.data_ptr(), P, rt.stream))
+        if training:
+            self._ctx = {"x": x}
+        return out
+
+    def backward(self, g: torch.Tensor):
+        """returns dx [B,F,k]; the kernel gradient lands in ``self.kernel_grad``."""
+        rt = self.rt
+        x = self._ctx["x"]
+        B, F, k = x.shape
+        g = g.contiguous()
+        dx = rt.zeros((B, F, k))
+        self.kernel_grad = torch.zeros_like(self.kernel) if self.kernel is not None else None
+        check(rt.lib.etr_pnn_backward(rt.ctx, x.data_ptr(), F * k, B, F, k, _PNN_TYPE[self.kernel_type],
+                                      _p(self.kernel), g.data_ptr(), g.shape[1], dx.data_ptr(), F * k,
+                                      _p(self.kernel_grad), rt.stream))
+        return dx
+
+
+IpnLayer = InnerProductNetwork
+
+
+class OuterProductNetwork(InnerProductNetwork):
+    """kernel 'mat' [k,P,k]: out[b,p] = sum_{a,c} x_i[c] K[a,p,c] x_j[a]; 'vec' [P,k];
+    'num' [P,1]; init random_normal (2.FM/CustomLayers.py:627-682; OpnLayer :795-851)."""
+
+    def __init__(self, fields_cnt, embedding_dims, kernel_type=None, **kwargs):
+        self._setup(kwargs)
+        kernel_type = kernel_type or "mat"
+        assert kernel_type in ("mat", "vec", "num")
+        self.kernel_type = kernel_type
+        P = fields_cnt * (fields_cnt - 1) // 2
+        self.kernel_shape = {"mat": (embedding_dims, P, embedding_dims), "vec": (P, embedding_dims),
+                             "num": (P, 1)}[kernel_type]
+        self.kernel = random_normal(self.kernel_shape, self.gen, self.rt.device)
+        self.params.finalize()
+
+
+OpnLayer = OuterProductNetwork
+
+
+class PNNRankingLayer(_Layer):
+    """MLP2(sigmoid)(MLP1(relu)(concat[Flatten(emb), product]))
+    (2.FM/CustomLayers.py:536-599; vectorised twin PNNLayer :685-753)."""
+
+    def __init__(self, feature_names=['user_tag0', 'user_tag1', 'item_tag1', 'item_tag2', 'item_tag3'],
+                 feature_dims=20, embedding_dims=16, mlp_dims=[32, 8], dropout=0, method='inner', kernel_type=None,
+                 **kwargs):
+        assert method in ('inner', 'outer')
+        self._setup(kwargs)
+        self.feature_names = list(feature_names)
+        self.feature_dims, self.embedding_dims = int(feature_dims), int(embedding_dims)
+        self.fields_cnt = len(self.feature_names)
+        self.mlp_dims, self.method, self.dropout = list(mlp_dims), method, dropout
+        self.kernel_type = "inner" if method == "inner" else (kernel_type or "mat")
+        F, k = self.fields_cnt, self.embedding_dims
+        self.P = F * (F - 1) // 2
+        self.table = EmbeddingTable(self.rt, self.feature_dims, k, self.table_dtype)
+        self.table.init_uniform(-0.05, 0.05, self.gen)
+        if method == "outer":
+            shape = {"mat": (k, self.P, k), "vec": (self.P, k), "num": (self.P, 1)}[self.kernel_type]
+            self.params.add("pn/kernel", random_normal(shape, self.gen, self.rt.device))
+        self.MLP_layer1 = MLPLayer(units=self.mlp_dims, activation='relu', is_dropput=dropout, name="MLP_layer1")
+        self.MLP_layer2 = MLPLayer(units=[1], activation='sigmoid', name="MLP_layer2")
+        self.MLP_layer1.build(F * k + self.P, self.params, self.gen)
+        self.MLP_layer2.build(self.mlp_dims[-1], self.params, self.gen)
+        self.params.finalize()
+
+    @property
+    def embed(self):
+        return self.table.cols(0, self.embedding_dims)
+
+    @property
+    def pn_kernel(self):
+        return self.params["pn/kernel"] if self.method == "outer" else None
+
+    def sparse_tables(self):
+        return [self.table]
+
+    def call(self, inputs, training: bool = False):
+        rt = self.rt
+        ids = self._ids(inputs, self.feature_names)
+        F, k, P = self.fields_cnt, self.embedding_dims, self.P
+        comb = rt.empty((ids.B, F * k + P))                        # concat fused: [Flatten(emb) | product]
+        gather_fm_forward(self.table, k, False, ids, flat=comb, flat_col0=0)
+        check(rt.lib.etr_pnn_forward(rt.ctx, comb.data_ptr(), F * k + P, ids.B, F, k, _PNN_TYPE[self.kernel_type],
+                                     _p(self.pn_kernel), comb[:, F * k:].data_ptr(), F * k + P, rt.stream))
+        out = self.MLP_layer2(self.MLP_layer1(comb, training=training), training=training)
+        if training:
+            self._ctx = {"ids": ids, "comb": comb}
+        self._finish(training)
+        return {"output": out}
+
+    def backward(self, dlogit: torch.Tensor) -> List[SparseGrad]:
+        """dlogit = dL/dz, z the pre-sigmoid input of MLP_layer2's activation."""
+        rt = self.rt
+        ids, comb = self._ctx["ids"], self._ctx["comb"]
+        F, k, P = self.fields_cnt, self.embedding_dims, self.P
+        dz = dlogit.reshape(-1, 1).clone()
+        dh = self.MLP_layer2.backward(dz, dy_is_preact=True)
+        dcomb = self.MLP_layer1.backward(dh)                       # [B, F*k + P]
+        dk = None
+        if self.method == "outer":
+            dk = self.params.g("pn/kernel")
+            dk.zero_()
+        check(rt.lib.etr_pnn_backward(rt.ctx, comb.data_ptr(), F * k + P, ids.B, F, k, _PNN_TYPE[self.kernel_type],
+                                      _p(self.pn_kernel), dcomb[:, F * k:].data_ptr(), F * k + P, dcomb.data_ptr(),
+                                      F * k + P, _p(dk), rt.stream))
+        bag = gather_fm_backward(self.table, k, False, ids, dflat=dcomb, flat_col0=0)
+        return [SparseGrad(self.table, ids, bag)]
+
+
+PNNLayer = PNNRankingLayer
+
+
+# ---------------------------------------------------------------------------
+class CrossLayer(_Layer):
+    """x_{l+1} = x0*(x_l^T w_l) + b_l + x_l  (3.DCN/CustomLayers.py:170-203);
+    ``cross_weight`` / ``cross_bias``: layer_num variables of shape [D,1]."""
+
+    matrix = False
+
+    def __init__(self, layer_num, reg_w=1e-4, reg_b=1e-4, **kwargs):
+        self._setup(kwargs)
+        self.layer_num, self.reg_w, self.reg_b = int(layer_num), reg_w, reg_b
+        self.D = None
+        self.front_pad = 0
+        self._external_params = False
+
+    def build(self, D: int, params: Optional[DenseParams] = None, gen=None, front_pad: int = 0):
+        self.D, self.front_pad = int(D), int(front_pad)
+        Di = self.D + self.front_pad
+        gen = gen or self.gen
+        if params is not None:
+            self.params, self._external_params = params, True
+        L = self.layer_num
+        if self.matrix:
+            W = torch.zeros((L, Di, Di), device=self.rt.device)
+            W[:, front_pad:, front_pad:] = random_normal((L, self.D, self.D), gen, self.rt.device)
+            self.params.add("cross/W", W)
+        else:
+            w = torch.zeros((L, Di), device=self.rt.device)
+            w[:, front_pad:] = random_normal((L, self.D), gen, self.rt.device)
+            self.params.add("cross/w", w)
+        self.params.add("cross/b", torch.zeros((L, Di), device=self.rt.device))
+        if not self._external_params:
+            self.params.finalize()
+        return self
+
+    @property
+    def cross_weight(self) -> List[torch.Tensor]:
+        p0 = self.front_pad
+        if self.matrix:
+            return [self.params["cross/W"][i, p0:, p0:] for i in range(self.layer_num)]
+        return [self.params["cross/w"][i, p0:].unsqueeze(1) for i in range(self.layer_num)]
+
+    @property
+    def cross_bias(self) -> List[torch.Tensor]:
+        return [self.params["cross/b"][i, self.front_pad:].unsqueeze(1) for i in range(self.layer_num)]
+
+    def call(self, inputs, training: bool = False, out: Optional[torch.Tensor] = None):
+        """inputs [B, front_pad + D] fp32 (unit column stride); ``out`` may be a
+        strided [B, front_pad + D] view (e.g. the left part of the DCN concat)."""
+        rt = self.rt
+        x = rt.to_device(inputs, torch.float32)
+        if self.D is None:
+            self.build(x.shape[1])
+        Di = self.D + self.front_pad
+        assert x.dim() == 2 and x.shape[1] == Di and x.stride(1) == 1
+        B = x.shape[0]
+        if out is None:
+            out = rt.empty((B, Di))
+        check(rt.lib.etr_cross_vec_forward(rt.ctx, x.data_ptr(), x.stride(0), B, Di, self.layer_num,
+                                           self.params["cross/w"].data_ptr(), self.params["cross/b"].data_ptr(),
+                                           out.data_ptr(), out.stride(0), rt.stream))
+        if training:
+            self._ctx = {"x0": x}
+        return out
+
+    def backward(self, gout: torch.Tensor) -> torch.Tensor:
+        """gout [B, Di] (unit column stride, any row stride) -> dx0 [B, Di]."""
+        from .runtime import gemm_f32
+        rt = self.rt
+        x0 = self._ctx["x0"]
+        B, Di, L = x0.shape[0], self.D + self.front_pad, self.layer_num
+        dx0 = rt.empty((B, Di))
+        scal = rt.empty((B, 2 * L))
+        w, b = self.params["cross/w"], self.params["cross/b"]
+        check(rt.lib.etr_cross_vec_backward(rt.ctx, x0.data_ptr(), x0.stride(0), B, Di, L, w.data_ptr(), b.data_ptr(),
+                                            gout.data_ptr(), gout.stride(0), dx0.data_ptr(), Di, scal.data_ptr(),
+                                            rt.stream))
+        XtC = rt.empty((Di, 2 * L))
+        gemm_f32(rt, x0, scal, XtC, Di, 2 * L, B, x0.stride(0), 2 * L, 2 * L, trans_a=True)
+        sums, gsum = rt.empty((2 * L,)), rt.empty((Di,))
+        check(rt.lib.etr_colsum_f32(rt.ctx, scal.data_ptr(), B, 2 * L, 2 * L, sums.data_ptr(), rt.stream))
+        check(rt.lib.etr_colsum_f32(rt.ctx, gout.data_ptr(), B, Di, gout.stride(0), gsum.data_ptr(), rt.stream))
+        check(rt.lib.etr_cross_vec_finish(rt.ctx, XtC.data_ptr(), sums.data_ptr(), gsum.data_ptr(), w.data_ptr(),
+                                          b.data_ptr(), Di, L, self.params.g("cross/w").data_ptr(),
+                                          self.params.g("cross/b").data_ptr(), rt.stream))
+        return dx0
+
+
+class MatrixCrossLayer(CrossLayer):
+    """x_{l+1} = x0 (.) (W_l x_l + b_l) + x_l  (3.DCN/CustomLayers.py:272-305);
+    ``tf.matmul(W, x[B,D,1])`` is y = W x, i.e. X_l W_l^T in batch form (KAT-4).
+    This is the fp32 exact-parity path; the bf16 tcgen05 path is
+    ``precision='bf16'`` (tensor cores, fp32 accumulate)."""
+
+    matrix = True
+
+    def call(self, inputs, training: bool = False, out: Optional[torch.Tensor] = None):
+        rt = self.rt
+        x = rt.to_device(inputs, torch.float32)
+        if self.D is None:
+            self.build(x.shape[1])
+        Di = self.D + self.front_pad
+        assert x.dim() == 2 and x.shape[1] == Di and x.stride(1) == 1
+        B = x.shape[0]
+        W, b = self.params["cross/W"], self.params["cross/b"]
+        xs, us = [x], []
+        xl = x
+        for l in range(self.layer_num):
+            last = l == self.layer_num - 1
+            nxt = out if (last and out is not None) else rt.empty((B, Di))
+            u = rt.empty((B, Di))
+            assert xl.stride(0) == x.stride(0)
+            check(rt.lib.etr_cross_mat_layer_f32(rt.ctx, x.data_ptr(), xl.data_ptr(), xl.stride(0), B, Di,
+                                                 W[l].data_ptr(), b[l].data_ptr(), nxt.data_ptr(), nxt.stride(0),
+                                                 u.data_ptr(), Di, rt.stream))
+            xs.append(nxt)
+            us.append(u)
+            xl = nxt
+        if training:
+            self._ctx = {"xs": xs, "us": us}
+        return xl
+
+    def backward(self, gout: torch.Tensor) -> torch.Tensor:
+        from .runtime import gemm_f32
+        rt = self.rt
+        xs, us = self._ctx["xs"], self._ctx["us"]
+        x0 = xs[0]
+        B, Di = x0.shape[0], self.D + self.front_pad
+        W = self.params["cross/W"]
+        G = gout.contiguous().clone() if gout.stride(0) != Di else gout.clone()
+        x0c = x0 if x0.stride(0) == Di else x0.contiguous()
+        dx0 = rt.zeros((B, Di))
+        du = rt.empty((B, Di))
+        for l in reversed(range(self.layer_num)):
+            # du = G (.) x0 ; dx0 += G (.) U_l
+            check(rt.lib.etr_cross_mat_bwd_elementwise(rt.ctx, G.data_ptr(), x0c.data_ptr(), us[l].data_ptr(), B * Di,
+                                                       du.data_ptr(), dx0.data_ptr(), rt.stream))
+            xl = xs[l]
+            # dW_l = du^T X_l   ([Di,B] x [B,Di])
+            gemm_f32(rt, du, xl, self.params.g("cross/W")[l], Di, Di, B, Di, xl.stride(0), Di, trans_a=True)
+            check(rt.lib.etr_colsum_f32(rt.ctx, du.data_ptr(), B, Di, Di, self.params.g("cross/b")[l].data_ptr(),
+                                        rt.stream))
+            # G_l = G_{l+1} + du W_l
+            gemm_f32(rt, du, W[l], G, B, Di, Di, Di, Di, Di, beta=1.0)
+        check(rt.lib.etr_add_sigmoid(rt.ctx, dx0.data_ptr(), G.data_ptr(), B * Di, dx0.data_ptr(), None, rt.stream))
+        return dx0
+
+
+# ---------------------------------------------------------------------------
+class DeepCrossNetworkLayer(_Layer):
+    """_input = [X_cont || Flatten(Embedding(X))] (continuous FIRST, :259) -> cross
+    (vector or matrix by ``type``) || DenseLayer(units, activation) -> concat ->
+    Dense(1, sigmoid)  (3.DCN/CustomLayers.py:206-269)."""
+
+    def __init__(self, categorical_features=['uid', 'iid', 'utag1', 'utag2', 'utag3', 'utag4', 'itag1', 'itag2',
+                                             'itag3', 'itag4'],
+                 continuous_features=['itag4_origin', 'itag4_square', 'itag4_cube'], feature_dims=160000,
+                 embedding_dims=16, units=[64, 8], activation='relu', layer_num=3, reg_w=1e-4, reg_b=1e-4,
+                 type='vec', **kwargs):
+        self._setup(kwargs)
+        self.categorical_features = list(categorical_features)
+        self.continuous_features = list(continuous_features)
+        self.feature_names = self.categorical_features
+        self.feature_dims, self.embedding_dims = int(feature_dims), int(embedding_dims)
+        self.units, self.type = list(units), type
+        C_, F, k = len(self.continuous_features), len(self.categorical_features), self.embedding_dims
+        self.D = C_ + F * k
+        self.front_pad = (-C_) % 4
+        self.embedding_layer = self.table = EmbeddingTable(self.rt, self.feature_dims, k, self.table_dtype)
+        self.table.init_uniform(-0.05, 0.05, self.gen)
+        cls = CrossLayer if type == 'vec' else MatrixCrossLayer
+        self.cross_layer = cls(layer_num, reg_w, reg_b, device=self.rt.device)
+        self.cross_layer.build(self.D, self.params, self.gen, front_pad=self.front_pad)
+        self.dense_layer = DenseLayer(self.units, activation, name="dense_layer")
+        self.dense_layer.build(self.D, self.params, self.gen, front_pad=self.front_pad)
+        self.output_layer = MLPLayer([1], 'sigmoid', name="output_layer")
+        self.output_layer.build(self.D + self.units[-1], self.params, self.gen, front_pad=self.front_pad)
+        self.params.finalize()
+
+    @property
+    def embeddings(self):
+        return self.table.cols(0, self.embedding_dims)
+
+    def sparse_tables(self):
+        return [self.table]
+
+    def call(self, inputs, training: bool = False):
+        rt = self.rt
+        ids = self._ids(inputs, self.categorical_features)
+        C_, k = len(self.continuous_features), self.embedding_dims
+        Di = self.front_pad + self.D
+        x = rt.empty((ids.B, Di))                               # [pad | X_cont | Flatten(emb)]
+        cont = self._cont(inputs, self.continuous_features) if C_ else None
+        gather_fm_forward(self.table, k, False, ids, flat=x, flat_col0=self.front_pad + C_, cont=cont)
+        comb = rt.empty((ids.B, Di + self.units[-1]))           # concat fused: [cross_output | dnn_output]
+        self.cross_layer.call(x, training=training, out=comb[:, :Di])
+        dnn = self.dense_layer(x, training=training)
+        comb[:, Di:] = dnn
+        out = self.output_layer(comb, training=training)
+        if training:
+            self._ctx = {"ids": ids}
+        self._finish(training)
+        return {"output": out}
+
+    def backward(self, dlogit: torch.Tensor) -> List[SparseGrad]:
+        rt = self.rt
+        ids = self._ctx["ids"]
+        Di = self.front_pad + self.D
+        dz = dlogit.reshape(-1, 1).clone()
+        dcomb = self.output_layer.backward(dz, dy_is_preact=True)           # [B, Di + units[-1]]
+        dx = self.cross_layer.backward(dcomb[:, :Di])                       # [B, Di]
+        ddnn = dcomb[:, Di:].contiguous()
+        self.dense_layer.backward(ddnn, accumulate_into=dx)
+        bag = gather_fm_backward(self.table, self.embedding_dims, False, ids, dflat=dx,
+                                 flat_col0=self.front_pad + len(self.continuous_features))
         return [SparseGrad(self.table, ids, bag)]
 
 
@@ -333,18 +871,19 @@ class Trainer:
         return batch
 
     def _graph_step(self, inputs, labels) -> torch.Tensor:
+        """Calls 1-2 at a new batch size run eagerly on the static buffers (they are
+        real training steps and size the workspace); call 3 captures the step into a
+        CUDA graph; from then on every call is one graph replay."""
         batch = inputs if isinstance(inputs, DeviceBatch) else self.stage(inputs, labels)
         key = (batch.ids.B,)
         slot = self._graphs.setdefault(key, [batch, None, None, None, None, None])
+        if len(slot) == 6:
+            slot.append(0)
         if slot[4] is None:
             assert slot[0] is batch, "graph mode needs the static DeviceBatch returned by stage()"
-            # warm-up eagerly on a side stream (sizes the workspace), then capture
-            s = torch.cuda.Stream(device=self.rt.device)
-            s.wait_stream(torch.cuda.current_stream(self.rt.device))
-            with torch.cuda.stream(s):
-                for _ in range(2):
-                    self._eager_step(batch)
-            torch.cuda.current_stream(self.rt.device).wait_stream(s)
+            if slot[6] < 2:
+                slot[6] += 1
+                return self._eager_step(batch)
             torch.cuda.synchronize(self.rt.device)
             g = torch.cuda.CUDAGraph()
             with torch.cuda.graph(g):

@@ -53,7 +53,7 @@ PROTOTYPES = {
     "etr_ctx_poll_error": (C.c_int, [_vp, _vp, C.POINTER(_i64)]),
     "etr_ctx_launch_count": (_i64, [_vp]),
     "etr_assemble_ids": (C.c_int, [_vp, C.POINTER(_vp), _i32, _i64, _vp, _vp]),
-    "etr_gather_fm_forward": (C.c_int, [_vp, _T, _i32, _i32, _I, _vp, _vp, _vp, _vp, _vp, _i32, _i64, _i32, _vp]),
+    "etr_gather_fm_forward": (C.c_int, [_vp, _T, _i32, _i32, _I, _vp, _vp, _vp, _vp, _vp, _i32, _i64, _i32, _vp, _i32, _i64, _i64, _vp]),
     "etr_embedding_gather": (C.c_int, [_vp, _T, _vp, _i64, _vp, _i64, _vp]),
     "etr_gather_fm_backward": (C.c_int, [_vp, _T, _i32, _i32, _I, _vp, _vp, _i32, _i64, _i32, _vp, _i32, _vp]),
     "etr_sparse_plan_slots": (_i64, [_I, _i64]),
@@ -67,6 +67,13 @@ PROTOTYPES = {
     "etr_gemm_f32": (C.c_int, [_vp, _i32, _i32, _i64, _i64, _i64, _f32, _vp, _i64, _vp, _i64, _f32, _vp, _i64, _vp, _i32, _vp]),
     "etr_act_backward": (C.c_int, [_vp, _vp, _vp, _i64, _i32, _vp]),
     "etr_colsum_f32": (C.c_int, [_vp, _vp, _i64, _i64, _i64, _vp, _vp]),
+    "etr_field_pair_forward": (C.c_int, [_vp, _T, _i32, _i32, _I, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "etr_field_pair_backward": (C.c_int, [_vp, _i32, _i32, _I, _vp, _vp, _vp, _vp, _vp, _i32, _vp]),
+    "etr_pnn_forward": (C.c_int, [_vp, _vp, _i64, _i64, _i32, _i32, _i32, _vp, _vp, _i64, _vp]),
+    "etr_pnn_backward": (C.c_int, [_vp, _vp, _i64, _i64, _i32, _i32, _i32, _vp, _vp, _i64, _vp, _i64, _vp, _vp]),
+    "etr_cross_vec_forward": (C.c_int, [_vp, _vp, _i64, _i64, _i32, _i32, _vp, _vp, _vp, _i64, _vp]),
+    "etr_cross_vec_backward": (C.c_int, [_vp, _vp, _i64, _i64, _i32, _i32, _vp, _vp, _vp, _i64, _vp, _i64, _vp, _vp]),
+    "etr_cross_vec_finish": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _vp, _i32, _i32, _vp, _vp, _vp]),
     "etr_cross_mat_layer_f32": (C.c_int, [_vp, _vp, _vp, _i64, _i64, _i32, _vp, _vp, _vp, _i64, _vp, _i64, _vp]),
     "etr_cross_mat_bwd_elementwise": (C.c_int, [_vp, _vp, _vp, _vp, _i64, _vp, _vp, _vp]),
 }

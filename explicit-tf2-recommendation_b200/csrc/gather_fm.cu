@@ -34,6 +34,12 @@ struct GatherParams {
   long long flat_ld;
   int flat_col0;
   int flat_vec;    // 1: 16B/8B vector stores are aligned
+  // optional dense ("continuous") columns written in front of the flattened
+  // embedding: flat[b, j] = 0 for j < col0-cont_n, cont[b, j-(col0-cont_n)] after
+  const float* cont;
+  long long cont_sb, cont_sc;
+  int cont_n;
+  int fill_front;  // 1: this launch owns columns [0, flat_col0) of d_flat
   // backward only
   const float* dlogit;
   float* bag_grad;
@@ -177,6 +183,15 @@ __global__ void __launch_bounds__(256) gather_fm_fwd_kernel(const GatherParams p
 #pragma unroll
       for (int i = 0; i < VEC; ++i) S[j][i] = Q[j][i] = 0.f;
 
+    if (p.fill_front && active) {
+      const int z = p.flat_col0 - p.cont_n;
+      for (int j = gl; j < p.flat_col0; j += LPR) {
+        const float v = (j < z) ? 0.f : p.cont[b * p.cont_sb + (long long)(j - z) * p.cont_sc];
+        if (p.flat_bf16) reinterpret_cast<__nv_bfloat16*>(p.flat)[b * p.flat_ld + j] = __float2bfloat16_rn(v);
+        else reinterpret_cast<float*>(p.flat)[b * p.flat_ld + j] = v;
+      }
+    }
+
     if (!BAG) {
       for (int f0 = 0; f0 < p.F; f0 += kUnroll) {
         long long id[kUnroll];
@@ -262,9 +277,63 @@ __global__ void __launch_bounds__(256) gather_fm_fwd_kernel(const GatherParams p
 
 // --------------------------------------------------------------- backward
 // bag_grad[(b*F+f), c] = dlogit*(S_c - e_fc) (+ dflat)  for c<k ; dlogit at c==k.
-template <typename Elem, int LPR, int CPL>
+template <typename Elem, int CPL>
+__device__ __forceinline__ void emit_bag_grad(const GatherParams& p, long long b, int f, int gl, int LPR_,
+                                              const float (&S)[CPL][Chunk<Elem>::kElems],
+                                              const float (&e)[CPL][Chunk<Elem>::kElems], float dl, float scale,
+                                              bool need_rows) {
+  constexpr int VEC = Chunk<Elem>::kElems;
+  const int grad_chunks = p.grad_ld / 4;
+  float* grow = p.bag_grad + (b * p.F + f) * (long long)p.grad_ld;
+#pragma unroll
+  for (int j = 0; j < CPL; ++j) {
+    const int c = gl + j * LPR_;
+    float gout[VEC];
+    const int col0 = c * VEC;
+    float df[VEC];
+#pragma unroll
+    for (int i = 0; i < VEC; ++i) df[i] = 0.f;
+    if (p.flat && col0 < p.k) {
+      const long long e0 = b * p.flat_ld + p.flat_col0 + (long long)f * p.k + col0;
+      if (p.flat_vec && col0 + VEC <= p.k && !p.flat_bf16) {
+#pragma unroll
+        for (int i = 0; i < VEC; i += 4) {
+          const float4 t = *reinterpret_cast<const float4*>(reinterpret_cast<const float*>(p.flat) + e0 + i);
+          df[i] = t.x; df[i + 1] = t.y; df[i + 2] = t.z; df[i + 3] = t.w;
+        }
+      } else {
+#pragma unroll
+        for (int i = 0; i < VEC; ++i)
+          if (col0 + i < p.k)
+            df[i] = p.flat_bf16 ? __bfloat162float(reinterpret_cast<const __nv_bfloat16*>(p.flat)[e0 + i])
+                                : reinterpret_cast<const float*>(p.flat)[e0 + i];
+      }
+    }
+#pragma unroll
+    for (int i = 0; i < VEC; ++i) {
+      const int col = col0 + i;
+      float gv = 0.f;
+      if (col < p.k) {
+        if (need_rows) gv = dl * (S[j][i] - e[j][i]);
+        gv += df[i];
+      } else if (col == p.k && p.has_w) {
+        gv = dl;
+      }
+      gout[i] = gv * scale;
+    }
+#pragma unroll
+    for (int q = 0; q < VEC / 4; ++q) {
+      const int gc = c * (VEC / 4) + q;
+      if (gc < grad_chunks)
+        stg_stream16(grow + gc * 4, make_float4(gout[4 * q], gout[4 * q + 1], gout[4 * q + 2], gout[4 * q + 3]));
+    }
+  }
+}
+
+template <typename Elem, int LPR, int CPL, bool BAG>
 __global__ void __launch_bounds__(256) gather_fm_bwd_kernel(const GatherParams p) {
   constexpr int VEC = Chunk<Elem>::kElems;
+  constexpr int kUnroll = UnrollFor<CPL, VEC>::value;
   constexpr int GPW = 32 / LPR;
   const int lane = threadIdx.x & 31;
   const int gl = lane % LPR;
@@ -272,7 +341,6 @@ __global__ void __launch_bounds__(256) gather_fm_bwd_kernel(const GatherParams p
   const long long warp_global = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   const long long nwarps = (long long)gridDim.x * (blockDim.x >> 5);
   const bool need_rows = p.dlogit != nullptr;
-  const int grad_chunks = p.grad_ld / 4;   // fp32 chunks per gradient row
 
   for (long long b0 = warp_global * GPW; b0 < p.B; b0 += nwarps * GPW) {
     const long long b = b0 + g;
@@ -282,65 +350,105 @@ __global__ void __launch_bounds__(256) gather_fm_bwd_kernel(const GatherParams p
     for (int j = 0; j < CPL; ++j)
 #pragma unroll
       for (int i = 0; i < VEC; ++i) S[j][i] = 0.f;
-    float dl = 0.f;
-    if (need_rows) {
-      dl = active ? p.dlogit[b] : 0.f;
+    const float dl = (need_rows && active) ? p.dlogit[b] : 0.f;
+
+    if (!BAG) {
+      // ---- single-hot: kUnroll fields in flight per lane in both passes
+      if (need_rows) {
+        for (int f0 = 0; f0 < p.F; f0 += kUnroll) {
+          long long id[kUnroll];
+          bool ok[kUnroll];
+#pragma unroll
+          for (int u = 0; u < kUnroll; ++u) {
+            const bool in = active && (f0 + u) < p.F;
+            id[u] = in ? __ldg(p.ids + b * p.sb + (long long)(f0 + u) * p.sf) : 0;
+            ok[u] = in && !(p.has_pad && id[u] == p.pad) && (unsigned long long)id[u] < (unsigned long long)p.rows;
+          }
+          Chunk<Elem> r[kUnroll][CPL];
+#pragma unroll
+          for (int u = 0; u < kUnroll; ++u)
+#pragma unroll
+            for (int j = 0; j < CPL; ++j) {
+              const int c = gl + j * LPR;
+              if (ok[u] && c < p.nchunks) r[u][j].load(p.table + id[u] * (long long)p.row_bytes + c * 16);
+              else r[u][j].zero();
+            }
+#pragma unroll
+          for (int u = 0; u < kUnroll; ++u)
+#pragma unroll
+            for (int j = 0; j < CPL; ++j)
+#pragma unroll
+              for (int i = 0; i < VEC; ++i) S[j][i] += r[u][j].v[i];
+        }
+      }
+      for (int f0 = 0; f0 < p.F; f0 += kUnroll) {
+        Chunk<Elem> r[kUnroll][CPL];
+        if (need_rows) {
+          long long id[kUnroll];
+          bool ok[kUnroll];
+#pragma unroll
+          for (int u = 0; u < kUnroll; ++u) {
+            const bool in = active && (f0 + u) < p.F;
+            id[u] = in ? __ldg(p.ids + b * p.sb + (long long)(f0 + u) * p.sf) : 0;
+            ok[u] = in && !(p.has_pad && id[u] == p.pad) && (unsigned long long)id[u] < (unsigned long long)p.rows;
+          }
+#pragma unroll
+          for (int u = 0; u < kUnroll; ++u)
+#pragma unroll
+            for (int j = 0; j < CPL; ++j) {
+              const int c = gl + j * LPR;
+              if (ok[u] && c < p.nchunks) r[u][j].load(p.table + id[u] * (long long)p.row_bytes + c * 16);
+              else r[u][j].zero();
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < kUnroll; ++u) {
+          if (active && f0 + u < p.F) {
+            float e[CPL][VEC];
+#pragma unroll
+            for (int j = 0; j < CPL; ++j)
+#pragma unroll
+              for (int i = 0; i < VEC; ++i) e[j][i] = need_rows ? r[u][j].v[i] : 0.f;
+            emit_bag_grad<Elem, CPL>(p, b, f0 + u, gl, LPR, S, e, dl, 1.0f, need_rows);
+          }
+        }
+      }
+    } else {
+      if (need_rows) {
+        for (int f = 0; f < p.F; ++f) {
+          float e[CPL][VEC];
+          pool_bag<Elem, LPR, CPL>(p, b, f, gl, active, e);
+#pragma unroll
+          for (int j = 0; j < CPL; ++j)
+#pragma unroll
+            for (int i = 0; i < VEC; ++i) S[j][i] += e[j][i];
+        }
+      }
       for (int f = 0; f < p.F; ++f) {
         float e[CPL][VEC];
-        pool_bag<Elem, LPR, CPL>(p, b, f, gl, active, e);
-#pragma unroll
-        for (int j = 0; j < CPL; ++j)
-#pragma unroll
-          for (int i = 0; i < VEC; ++i) S[j][i] += e[j][i];
-      }
-    }
-    for (int f = 0; f < p.F; ++f) {
-      float e[CPL][VEC];
-      int cnt = 1;
-      if (need_rows) {
-        cnt = pool_bag<Elem, LPR, CPL>(p, b, f, gl, active, e);   // rows now come from L2
-      } else if (p.mean && active) {
-        // only the bag count is needed
-        cnt = 0;
-        if (p.csr) {
-          cnt = p.csr[b * p.F + f + 1] - p.csr[b * p.F + f];
+        int cnt = 1;
+        if (need_rows) {
+          cnt = pool_bag<Elem, LPR, CPL>(p, b, f, gl, active, e);   // rows now come from L2
         } else {
-          for (int l = 0; l < p.L; ++l) {
-            const long long id = __ldg(p.ids + b * p.sb + (long long)f * p.sf + (long long)l * p.sl);
-            cnt += (p.has_pad && id == p.pad) ? 0 : 1;
-          }
-        }
-      }
-      if (!active) continue;
-      const float scale = (p.mean && cnt > 1) ? 1.0f / (float)cnt : 1.0f;
-      float* grow = p.bag_grad + (b * p.F + f) * (long long)p.grad_ld;
 #pragma unroll
-      for (int j = 0; j < CPL; ++j) {
-        const int c = gl + j * LPR;
-        float gout[VEC];
+          for (int j = 0; j < CPL; ++j)
 #pragma unroll
-        for (int i = 0; i < VEC; ++i) {
-          const int col = c * VEC + i;
-          float gv = 0.f;
-          if (col < p.k) {
-            if (need_rows) gv = dl * (S[j][i] - e[j][i]);
-            if (p.flat) {
-              const long long e0 = b * p.flat_ld + p.flat_col0 + (long long)f * p.k + col;
-              gv += p.flat_bf16 ? __bfloat162float(reinterpret_cast<const __nv_bfloat16*>(p.flat)[e0])
-                                : reinterpret_cast<const float*>(p.flat)[e0];
+            for (int i = 0; i < VEC; ++i) e[j][i] = 0.f;
+          if (p.mean && active) {                                    // only the bag count is needed
+            cnt = 0;
+            if (p.csr) {
+              cnt = p.csr[b * p.F + f + 1] - p.csr[b * p.F + f];
+            } else {
+              for (int l = 0; l < p.L; ++l) {
+                const long long id = __ldg(p.ids + b * p.sb + (long long)f * p.sf + (long long)l * p.sl);
+                cnt += (p.has_pad && id == p.pad) ? 0 : 1;
+              }
             }
-          } else if (col == p.k && p.has_w) {
-            gv = dl;
           }
-          gout[i] = gv * scale;
         }
-        // VEC fp32 values = VEC/4 16-byte chunks of the gradient row
-#pragma unroll
-        for (int q = 0; q < VEC / 4; ++q) {
-          const int gc = c * (VEC / 4) + q;
-          if (gc < grad_chunks)
-            stg_stream16(grow + gc * 4, make_float4(gout[4 * q], gout[4 * q + 1], gout[4 * q + 2], gout[4 * q + 3]));
-        }
+        if (!active) continue;
+        const float scale = (p.mean && cnt > 1) ? 1.0f / (float)cnt : 1.0f;
+        emit_bag_grad<Elem, CPL>(p, b, f, gl, LPR, S, e, dl, scale, need_rows);
       }
     }
   }
@@ -443,8 +551,10 @@ static int launch_gather(etr_ctx* ctx, const GatherParams& p, bool bag, cudaStre
   const int grid = grid_for(p.B, (threads / 32) * gpw, ctx->sm_count, 8);
 #define ETR_LAUNCH(LPR, CPL)                                                              \
   do {                                                                                    \
-    if (BWD)                                                                              \
-      gather_fm_bwd_kernel<Elem, LPR, CPL><<<grid, threads, 0, s>>>(p);                   \
+    if (BWD && bag)                                                                       \
+      gather_fm_bwd_kernel<Elem, LPR, CPL, true><<<grid, threads, 0, s>>>(p);             \
+    else if (BWD)                                                                         \
+      gather_fm_bwd_kernel<Elem, LPR, CPL, false><<<grid, threads, 0, s>>>(p);            \
     else if (bag)                                                                         \
       gather_fm_fwd_kernel<Elem, LPR, CPL, true><<<grid, threads, 0, s>>>(p);             \
     else                                                                                  \
@@ -495,7 +605,8 @@ int etr_assemble_ids(etr_ctx* ctx, const int64_t* const* h_cols, int32_t fields,
 int etr_gather_fm_forward(etr_ctx* ctx, const etr_table* table, int32_t k, int32_t has_w,
                           const etr_ids* ids, const float* d_bias, float* d_logit, float* d_prob,
                           float* d_sumv, void* d_flat, int32_t flat_dtype, int64_t flat_ld,
-                          int32_t flat_col0, void* stream) {
+                          int32_t flat_col0, const float* d_cont, int32_t cont_n, int64_t cont_stride_b,
+                          int64_t cont_stride_c, void* stream) {
   GatherParams p;
   int st = fill_params(__func__, table, k, has_w, ids, &p, ctx);
   if (st != ETR_OK) return st;
@@ -513,6 +624,14 @@ int etr_gather_fm_forward(etr_ctx* ctx, const etr_table* table, int32_t k, int32
     const int align = vec * osz > 16 ? 16 : vec * osz;
     p.flat_vec = ((flat_col0 * osz) % align == 0) && ((flat_ld * osz) % align == 0) &&
                  ((k * osz) % align == 0) && (((uintptr_t)d_flat & 15) == 0);
+  }
+  // front columns [0, flat_col0): cont_n < 0 leaves them to the caller; otherwise the
+  // kernel writes zeros to [0, flat_col0-cont_n) and the dense features after them.
+  if (d_flat && flat_col0 > 0 && cont_n >= 0) {
+    ETR_CHECK_ARG(cont_n <= flat_col0, "cont_n > flat_col0");
+    ETR_CHECK_ARG(cont_n == 0 || d_cont != nullptr, "d_cont is NULL");
+    p.fill_front = 1;
+    p.cont = d_cont; p.cont_n = cont_n; p.cont_sb = cont_stride_b; p.cont_sc = cont_stride_c;
   }
   const bool bag = ids->d_csr_offsets != nullptr || ids->bag != 1;
   if (table->dtype == ETR_BF16)
@@ -539,11 +658,17 @@ int etr_gather_fm_backward(etr_ctx* ctx, const etr_table* table, int32_t k, int3
   p.flat_col0 = flat_col0;
   p.bag_grad = d_bag_grad;
   p.grad_ld = grad_ld;
+  if (d_dflat) {
+    ETR_CHECK_ARG(flat_ld >= flat_col0 + (int64_t)p.F * k, "flat_ld too small");
+    p.flat_vec = !p.flat_bf16 && (flat_col0 % 4 == 0) && (flat_ld % 4 == 0) && (k % 4 == 0) &&
+                 (((uintptr_t)d_dflat & 15) == 0);
+  }
   // the gradient row may be wider (in chunks) than the table row for bf16 tables:
   // lanes are assigned by table chunks, each producing VEC fp32 values.
+  const bool bag = ids->d_csr_offsets != nullptr || ids->bag != 1;
   if (table->dtype == ETR_BF16)
-    return launch_gather<__nv_bfloat16, true>(ctx, p, true, (cudaStream_t)stream);
-  return launch_gather<float, true>(ctx, p, true, (cudaStream_t)stream);
+    return launch_gather<__nv_bfloat16, true>(ctx, p, bag, (cudaStream_t)stream);
+  return launch_gather<float, true>(ctx, p, bag, (cudaStream_t)stream);
 }
 
 int etr_embedding_gather(etr_ctx* ctx, const etr_table* table, const int64_t* d_ids, int64_t count,

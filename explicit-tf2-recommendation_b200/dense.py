@@ -26,11 +26,20 @@ class DenseParams:
         self._specs: List[Tuple[str, Tuple[int, ...], torch.Tensor]] = []
         self.value = self.grad = self.m = self.v = None
         self._views: Dict[str, Tuple[int, Tuple[int, ...]]] = {}
+        self._pad: Dict[str, int] = {}
 
-    def add(self, name: str, init: torch.Tensor) -> str:
+    def add(self, name: str, init: torch.Tensor, front_pad_rows: int = 0) -> str:
+        """``front_pad_rows`` zero rows are stored in front of a 2-D variable (the
+        operand it multiplies has that many zero padding columns in front so that
+        its embedding part starts 16-byte aligned); ``self[name]`` is the
+        reference-shaped view behind them, ``self.full(name)`` the padded one."""
         assert self.value is None, "DenseParams already finalized"
         assert name not in [s[0] for s in self._specs], name
-        self._specs.append((name, tuple(init.shape), init.detach().to(torch.float32).reshape(-1)))
+        init = init.detach().to(torch.float32)
+        if front_pad_rows:
+            init = torch.cat([torch.zeros((front_pad_rows,) + tuple(init.shape[1:]), device=init.device), init], 0)
+        self._pad[name] = int(front_pad_rows)
+        self._specs.append((name, tuple(init.shape), init.reshape(-1)))
         return name
 
     def finalize(self):
@@ -49,13 +58,19 @@ class DenseParams:
             self.value[o:o + init.numel()] = init.to(self.rt.device)
         return self
 
-    def __getitem__(self, name: str) -> torch.Tensor:
+    def full(self, name: str) -> torch.Tensor:
         o, shape = self._views[name]
         return self.value[o:o + math.prod(shape)].view(shape)
 
-    def g(self, name: str) -> torch.Tensor:
+    def gfull(self, name: str) -> torch.Tensor:
         o, shape = self._views[name]
         return self.grad[o:o + math.prod(shape)].view(shape)
+
+    def __getitem__(self, name: str) -> torch.Tensor:
+        return self.full(name)[self._pad[name]:]
+
+    def g(self, name: str) -> torch.Tensor:
+        return self.gfull(name)[self._pad[name]:]
 
     def names(self) -> List[str]:
         return [s[0] for s in self._specs]
@@ -119,14 +134,18 @@ class MLPLayer:
         self.in_dim: Optional[int] = None
         self._saved = None
         self._owns_params = False
+        self.front_pad = 0
 
     # -- build ---------------------------------------------------------------
-    def build(self, in_dim: int, params: DenseParams, gen: torch.Generator):
-        self.in_dim, self.params = int(in_dim), params
+    def build(self, in_dim: int, params: DenseParams, gen: torch.Generator, front_pad: int = 0):
+        """``front_pad``: the input operand carries that many zero columns in front
+        (kernel_0 gets as many zero rows; the variable is the view behind them)."""
+        self.in_dim, self.params, self.front_pad = int(in_dim), params, int(front_pad)
         dims = [self.in_dim] + self.units
         for i in range(len(dims) - 1):
             params.add(f"{self.name}/kernel_{i}", _INIT[self.kernel_initializer]((dims[i], dims[i + 1]), gen,
-                                                                                 params.rt.device))
+                                                                                 params.rt.device),
+                       front_pad_rows=self.front_pad if i == 0 else 0)
             if self.use_bias:
                 params.add(f"{self.name}/bias_{i}", _INIT[self.bias_initializer]((dims[i + 1],), gen,
                                                                                params.rt.device))
@@ -151,10 +170,10 @@ class MLPLayer:
             self._owns_params = True
         rt = self.params.rt
         x = rt.to_device(inputs, torch.float32)
-        assert x.dim() == 2 and x.shape[1] == self.in_dim and x.stride(1) == 1
+        assert x.dim() == 2 and x.shape[1] == self.front_pad + self.in_dim and x.stride(1) == 1
         acts = [x]
         for i, n_out in enumerate(self.units):
-            k = self.params[f"{self.name}/kernel_{i}"]
+            k = self.params.full(f"{self.name}/kernel_{i}")
             b = self.params[f"{self.name}/bias_{i}"] if self.use_bias else None
             y = rt.empty((x.shape[0], n_out))
             gemm_f32(rt, x, k, y, x.shape[0], n_out, x.shape[1], x.stride(0), n_out, n_out, bias=b,
@@ -165,29 +184,37 @@ class MLPLayer:
             self._saved = acts
         return x
 
-    def backward(self, dy: torch.Tensor, need_input_grad: bool = True) -> Optional[torch.Tensor]:
-        """dy = dL/d(output) (post-activation).  Fills the kernel/bias grads in
-        ``params.grad``; returns dL/d(input).  dy is consumed (modified in place)."""
+    def backward(self, dy: torch.Tensor, need_input_grad: bool = True, dy_is_preact: bool = False,
+                 accumulate_into: Optional[torch.Tensor] = None) -> Optional[torch.Tensor]:
+        """dy = dL/d(output) (post-activation; pre-activation of the LAST layer when
+        ``dy_is_preact``), contiguous [B, units[-1]]; it is consumed (modified in
+        place).  Fills the kernel/bias grads in ``params.grad``; returns
+        dL/d(input) [B, front_pad+in_dim] (added into ``accumulate_into`` if given)."""
         assert self._saved is not None, "call with training=True first"
         rt = self.params.rt
         acts = self._saved
         d = dy
+        assert d.is_contiguous()
+        last = len(self.units) - 1
         for i in reversed(range(len(self.units))):
             x, y = acts[i], acts[i + 1]
             B, n_in, n_out = x.shape[0], x.shape[1], self.units[i]
-            check(rt.lib.etr_act_backward(rt.ctx, d.data_ptr(), y.data_ptr(), d.numel(), _lib.ACT[self.activation],
-                                          rt.stream))
-            gk = self.params.g(f"{self.name}/kernel_{i}")
+            if not (dy_is_preact and i == last):
+                check(rt.lib.etr_act_backward(rt.ctx, d.data_ptr(), y.data_ptr(), d.numel(),
+                                              _lib.ACT[self.activation], rt.stream))
+            gk = self.params.gfull(f"{self.name}/kernel_{i}")
             # dK = x^T d : A stored [K=B, M=n_in] -> trans_a
             gemm_f32(rt, x, d, gk, n_in, n_out, B, x.stride(0), n_out, n_out, trans_a=True)
             if self.use_bias:
                 gb = self.params.g(f"{self.name}/bias_{i}")
                 check(rt.lib.etr_colsum_f32(rt.ctx, d.data_ptr(), B, n_out, n_out, gb.data_ptr(), rt.stream))
             if i > 0 or need_input_grad:
-                k = self.params[f"{self.name}/kernel_{i}"]
-                dx = rt.empty((B, n_in))
+                k = self.params.full(f"{self.name}/kernel_{i}")
+                acc = accumulate_into if (i == 0 and accumulate_into is not None) else None
+                dx = acc if acc is not None else rt.empty((B, n_in))
                 # dx = d K^T : B(k,n) = K[n,k] -> trans_b
-                gemm_f32(rt, d, k, dx, B, n_in, n_out, n_out, n_out, n_in, trans_b=True)
+                gemm_f32(rt, d, k, dx, B, n_in, n_out, n_out, n_out, dx.stride(0), trans_b=True,
+                         beta=1.0 if acc is not None else 0.0)
                 d = dx
             else:
                 d = None

@@ -280,13 +280,21 @@ class SparseGrad:
 # ---------------------------------------------------------------------------
 # thin op wrappers
 def gather_fm_forward(table: EmbeddingTable, k: int, has_w: bool, ids: IdsBatch, bias=None, logit=None, prob=None,
-                      sumv=None, flat=None, flat_col0: int = 0):
+                      sumv=None, flat=None, flat_col0: int = 0, cont: Optional[torch.Tensor] = None):
+    """``cont`` [B,C] fp32 (any strides): the kernel also writes the front columns
+    [0, flat_col0) of ``flat`` = zero padding then the dense features."""
     rt = table.rt
     t, d = table.desc(), ids.desc()
     flat_dtype = _TORCH2ETR[flat.dtype] if flat is not None else 0
     flat_ld = flat.stride(0) if flat is not None else 0
+    if cont is not None:
+        assert cont.dtype == torch.float32 and cont.shape[0] == ids.B
+        cn, csb, csc = cont.shape[1], cont.stride(0), cont.stride(1)
+    else:
+        cn, csb, csc = 0, 0, 0
     check(rt.lib.etr_gather_fm_forward(rt.ctx, C.byref(t), k, int(has_w), C.byref(d), _p(bias), _p(logit), _p(prob),
-                                       _p(sumv), _p(flat), flat_dtype, flat_ld, flat_col0, rt.stream))
+                                       _p(sumv), _p(flat), flat_dtype, flat_ld, flat_col0, _p(cont), cn, csb, csc,
+                                       rt.stream))
 
 
 def gather_fm_backward(table: EmbeddingTable, k: int, has_w: bool, ids: IdsBatch, dlogit=None, dflat=None,

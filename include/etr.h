@@ -110,11 +110,18 @@ int etr_assemble_ids(etr_ctx* ctx, const int64_t* const* h_cols /* host array of
  *   d_flat[b, flat_col0 + f*k + c] = pooled embedding, c<k  (Flatten, :300;
  *                 3.DCN/CustomLayers.py:256-259), fp32 or bf16, leading dim
  *                 flat_ld elements -- written straight into the GEMM operand.
- *   d_sumv[b, c] = sum_f v_f[c]  (the NFM bi-interaction / backward helper)  */
+ *   d_sumv[b, c] = sum_f v_f[c]  (the NFM bi-interaction / backward helper)
+ * Dense ("continuous") inputs ride along: with cont_n >= 0 the kernel also
+ * owns columns [0, flat_col0) of d_flat -- zeros in [0, flat_col0-cont_n), then
+ * d_cont[b*cont_stride_b + j*cont_stride_c], j < cont_n -- i.e. the concat
+ * [X_cont || Flatten(emb)] of 3.DCN/CustomLayers.py:259 with the embedding part
+ * starting on a 16-byte boundary (front padding) and no separate copy kernel.
+ * cont_n < 0: the caller fills those columns.                                 */
 int etr_gather_fm_forward(etr_ctx* ctx, const etr_table* table, int32_t k, int32_t has_w,
                           const etr_ids* ids, const float* d_bias,
                           float* d_logit, float* d_prob, float* d_sumv,
                           void* d_flat, int32_t flat_dtype, int64_t flat_ld, int32_t flat_col0,
+                          const float* d_cont, int32_t cont_n, int64_t cont_stride_b, int64_t cont_stride_c,
                           void* stream);
 
 /* Bit-exact row dump / generic Embedding.call (2.FM/CustomLayers.py:146-147):
@@ -198,6 +205,62 @@ int etr_act_backward(etr_ctx* ctx, float* d_dy, const float* d_y, int64_t n, int
 /* d_out[n] = sum_m X[m, n]  (bias gradients), deterministic two-pass.        */
 int etr_colsum_f32(etr_ctx* ctx, const float* d_X, int64_t M, int64_t N, int64_t ldx, float* d_out,
                    void* stream);
+
+/* --------------------------------- K3: field-aware pair interaction (a5-a8)
+ * table rows are [F*k (+1 linear weight when has_w)] wide (fp32): T[v,c,:] at
+ * cols c*k..c*k+k-1.  I[b,(a,c),:] = E_b[a][c][:] * E_b[c][a][:], a<c row-major,
+ * E_b[a] the (pooled) row of field a (2.FM/CustomLayers.py:438-461).  Outputs
+ * (NULL = skip):
+ *   d_pairvec [B,P,k]   pair vectors (FieldAwareInteractionLayer.call)
+ *   d_pairdot [B,P]     sum_k of them (FwFM's Dense(1) input, :529)
+ *   d_logit   [B]       (bias) + sum_f w + sum_p r_p*<.,.>_p + r0   with
+ *                       d_r == NULL meaning r == 1 (FFM, :493) -- fused head
+ *   d_prob    [B]       sigmoid(d_logit)
+ *   d_pooled  [B,F,F*k] the pooled rows (saved for the backward)             */
+int etr_field_pair_forward(etr_ctx* ctx, const etr_table* table, int32_t k, int32_t has_w,
+                           const etr_ids* ids, const float* d_bias, const float* d_r, const float* d_r0,
+                           float* d_pairvec, float* d_pairdot, float* d_logit, float* d_prob,
+                           float* d_pooled, void* stream);
+/* d_bag_grad[(b*F+a), c*k+d] = dlogit[b] * r_(a,c) * E_b[c][a][d]  (c != a; 0 for c == a),
+ * col F*k = dlogit[b] when has_w (mean pooling: divided by the bag count); rows
+ * use the table layout with leading dim grad_ld.  With d_dpairvec [B,P,k] != NULL
+ * the upstream gradient is per pair vector instead of the scalar head.  (dr and
+ * dr0 are plain reductions of pairdot: etr_gemm_f32 / etr_colsum_f32.)        */
+int etr_field_pair_backward(etr_ctx* ctx, int32_t k, int32_t has_w, const etr_ids* ids,
+                            const float* d_pooled, const float* d_dlogit, const float* d_r,
+                            const float* d_dpairvec, float* d_bag_grad, int32_t grad_ld, void* stream);
+
+/* ------------------------------------- K4: PNN inner / outer products (a9-a10)
+ * x [B,F,k] fp32 (row b at d_x + b*ldx): out[b,p] for pairs i<j in combinations
+ * order.  kernel_type: 0 inner (2.FM/CustomLayers.py:614-624), 1 'mat' K[k,P,k],
+ * 2 'vec' K[P,k], 3 'num' K[P] (:658-682).  Output written at d_out[b*ldo+p]
+ * so it lands behind the flattened embedding (the concat of :591).           */
+int etr_pnn_forward(etr_ctx* ctx, const float* d_x, int64_t ldx, int64_t batch, int32_t fields, int32_t k,
+                    int32_t kernel_type, const float* d_kernel, float* d_out, int64_t ldo, void* stream);
+/* d_dx[b,i,:] += sum_j G[b,p(i,j)] * dOut_p/dx_i (ACCUMULATES: pre-fill with the
+ * Flatten gradient); d_dkernel += batch sum (caller zeroes it; fp32 atomics).  */
+int etr_pnn_backward(etr_ctx* ctx, const float* d_x, int64_t ldx, int64_t batch, int32_t fields, int32_t k,
+                     int32_t kernel_type, const float* d_kernel, const float* d_g, int64_t ldg,
+                     float* d_dx, int64_t lddx, float* d_dkernel, void* stream);
+
+/* ------------------------------------------ K5: DCN cross-vector layer (a12)
+ * x_{l+1} = x0*(x_l . w_l) + b_l + x_l, l < layers <= 8; d_w, d_b are [layers, D]
+ * (3.DCN/CustomLayers.py:195-203).  One read of x0, one write of the output. */
+int etr_cross_vec_forward(etr_ctx* ctx, const float* d_x0, int64_t ldx, int64_t batch, int32_t D,
+                          int32_t layers, const float* d_w, const float* d_b,
+                          float* d_out, int64_t ldo, void* stream);
+/* Backward without saved activations (x_l = c_l x0 + Bc_l in closed form):
+ * writes d_dx0 and the per-sample scalars d_scal[b, 0:L] = ds_l,
+ * d_scal[b, L:2L] = ds_l*c_l.  etr_cross_vec_finish then turns
+ * XtC = X0^T scal [D,2L] (etr_gemm_f32), sums = colsum(scal) [2L] and
+ * gsum = colsum(gout) [D] into dw, db [layers, D] -- deterministic.           */
+int etr_cross_vec_backward(etr_ctx* ctx, const float* d_x0, int64_t ldx, int64_t batch, int32_t D,
+                           int32_t layers, const float* d_w, const float* d_b,
+                           const float* d_gout, int64_t ldg, float* d_dx0, int64_t lddx,
+                           float* d_scal, void* stream);
+int etr_cross_vec_finish(etr_ctx* ctx, const float* d_XtC, const float* d_sums, const float* d_gsum,
+                         const float* d_w, const float* d_b, int32_t D, int32_t layers,
+                         float* d_dw, float* d_db, void* stream);
 
 /* ------------------------------------------ K6: DCN cross-matrix layer (a13)
  * One layer: out = x0 (.) (xl W^T + b) + xl  (3.DCN/CustomLayers.py:300-303,

@@ -162,8 +162,8 @@ def _fm_grad_check(L, lay, orc, X, rtol):
     got_ids = ids.cpu().numpy()
     keep = np.abs(rows.cpu().numpy()).sum(1) > 0
     assert np.array_equal(got_ids[keep], ref_ids)               # ID routing bit-exact
-    assert_close(rows.cpu().numpy()[keep], ref_rows, rtol, "table grads (IndexedSlices, dedup'd)")
-    assert_close(lay.params.g("bias").cpu().numpy(), orc.bias.grad.numpy(), rtol, "bias grad")
+    assert_close(rows.cpu().numpy()[keep], ref_rows, rtol, "table grads (IndexedSlices, dedup'd)", grad=True)
+    assert_close(lay.params.g("bias").cpu().numpy(), orc.bias.grad.numpy(), rtol, "bias grad", grad=True)
 
 
 @pytest.mark.parametrize("B,F,k,V", [(16, 3, 16, 20), (4096, 26, 16, 160000), (300, 5, 8, 64), (128, 26, 64, 3000)])
@@ -232,13 +232,13 @@ def test_deepfm_forward_backward(L, B, F, k, V, C):
     full = torch.cat([orc.embed.grad, orc.w.grad], dim=1)
     ref_ids, ref_rows = dense_table_grad_to_slices(full)
     assert np.array_equal(ids.cpu().numpy(), ref_ids)
-    assert_close(rows.cpu().numpy(), ref_rows, FP32_RTOL, "DeepFM table grads")
+    assert_close(rows.cpu().numpy(), ref_rows, FP32_RTOL, "DeepFM table grads", grad=True)
     for dev_mlp, o_mlp in ((lay.MLP_layer1, orc.MLP_layer1), (lay.MLP_layer2, orc.MLP_layer2)):
         for i in range(len(dev_mlp.units)):
             assert_close(lay.params.g(f"{dev_mlp.name}/kernel_{i}").cpu().numpy(), o_mlp.kernels[i].grad.numpy(),
-                         FP32_RTOL, f"{dev_mlp.name} kernel_{i} grad")
+                         FP32_RTOL, f"{dev_mlp.name} kernel_{i} grad", grad=True)
             assert_close(lay.params.g(f"{dev_mlp.name}/bias_{i}").cpu().numpy(), o_mlp.biases[i].grad.numpy(),
-                         FP32_RTOL, f"{dev_mlp.name} bias_{i} grad")
+                         FP32_RTOL, f"{dev_mlp.name} bias_{i} grad", grad=True)
 
 
 def test_deepfm_reference_docstring(L):
@@ -288,10 +288,12 @@ def test_train_steps_match_oracle_adam(L, mode, model):
             else:
                 opt.apply_dense(v, v.grad, lr_t)
         assert abs(float(loss.item()) - float(l_ref)) <= 1e-5 * abs(float(l_ref)), step
-        # Adam divides by sqrt(v)+eps: tiny grads are amplified, so compare updates at 1e-4 of the step size
-        assert_close(cpu(lay.embed).numpy(), orc.embed.detach().numpy(), 2e-5, f"embed after step {step}")
-        assert_close(cpu(lay.w).numpy(), orc.w.detach().numpy(), 2e-5, f"w after step {step}")
-        assert_close(cpu(lay.bias).numpy(), orc.bias.detach().numpy(), 2e-5, f"bias after step {step}")
+        # Adam's update lr*m/(sqrt(v)+eps) is ill-conditioned where a row gradient cancels to ~eps, so
+        # weights are compared in units of the step size: |dw| <= 2e-3 * lr per step taken
+        tol = 2e-3 * 1e-2 * (step + 1)
+        for name, got, ref in (("embed", lay.embed, orc.embed), ("w", lay.w, orc.w), ("bias", lay.bias, orc.bias)):
+            err = np.abs(cpu(got, torch.float64).numpy() - ref.detach().numpy()).max()
+            assert err <= tol, (name, step, err)
 
 
 # --------------------------------------------------------------------- GEMM
@@ -324,7 +326,7 @@ def test_graph_trainer_matches_eager(L):
     lays = [L.DeepFMRankingLayer(names, feature_dims=V, embedding_dims=k, continuous_features=cont, seed=4)
             for _ in range(2)]
     trs = [L.Trainer(lays[0], lr=1e-2, graph=False), L.Trainer(lays[1], lr=1e-2, graph=True)]
-    for step in range(4):
+    for step in range(5):
         X = zipf_ids(rng, [V // F] * F, B)
         Xc = rng.normal(size=(B, C)).astype(np.float32)
         y = (rng.random(B) < 0.3).astype(np.float32)
@@ -335,4 +337,4 @@ def test_graph_trainer_matches_eager(L):
         assert float(la.item()) == float(lb.item()), step
     assert torch.equal(lays[0].table.data, lays[1].table.data)
     assert torch.equal(lays[0].params.value, lays[1].params.value)
-    assert trs[1].iterations == 4 + 2        # 2 warm-up steps precede the capture ... on the same batch
+    assert trs[0].iterations == trs[1].iterations == 5        # steps 1-2 eager, 3 captured+replayed, 4-5 replayed
