@@ -862,7 +862,7 @@ class Trainer:
             ids = IdsBatch(rt, ids_buf, B, len(names), 1, 1, B, 1, lay.pad_id, lay.pooling)
             batch = DeviceBatch(ids, cont_buf[: len(cont_names)].t() if cont_names else None, lab_buf)
             self._graphs[key] = [batch, ids_buf, cont_buf, lab_buf, None, None]
-        batch, ids_buf, cont_buf, lab_buf, _, _ = self._graphs[key]
+        batch, ids_buf, cont_buf, lab_buf = self._graphs[key][:4]
         for f, n in enumerate(names):
             ids_buf[f].copy_(torch.as_tensor(inputs[n]).reshape(-1), non_blocking=True)
         for c, n in enumerate(cont_names):

@@ -127,6 +127,90 @@ __global__ void __launch_bounds__(256) gemm_splitk_finish_kernel(const GemmParam
   }
 }
 
+
+// ---- skinny shapes of the MLP tail (e.g. [B,32]x[32,8], [B,8]x[8,1] and their dgrads):
+// one thread per output row, NT accumulators in registers, the whole weight
+// matrix broadcast from shared memory.  C = act(alpha*A B + beta*C + bias).
+template <int NT>
+__global__ void __launch_bounds__(256) gemm_skinny_rows_kernel(const GemmParams p) {
+  extern __shared__ __align__(16) float Ws[];          // [K][NT], zero padded
+  const int K = (int)p.K, N = (int)p.N;
+  for (int e = threadIdx.x; e < K * NT; e += blockDim.x) {
+    const int kk = e / NT, nn = e % NT;
+    Ws[e] = nn < N ? p.B[kk * p.sbk + nn * p.sbn] : 0.f;
+  }
+  __syncthreads();
+  const bool vec_a = (p.sam % 4 == 0) && ((((uintptr_t)p.A) & 15) == 0);
+  for (long long m = (long long)blockIdx.x * blockDim.x + threadIdx.x; m < p.M; m += (long long)gridDim.x * blockDim.x) {
+    float acc[NT];
+#pragma unroll
+    for (int n = 0; n < NT; ++n) acc[n] = 0.f;
+    const float* a = p.A + m * p.sam;
+    int k = 0;
+    if (vec_a) {
+      for (; k + 4 <= K; k += 4) {
+        const float4 x = *reinterpret_cast<const float4*>(a + k);
+        const float xs[4] = {x.x, x.y, x.z, x.w};
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+#pragma unroll
+          for (int n = 0; n < NT; ++n) acc[n] = fmaf(xs[q], Ws[(k + q) * NT + n], acc[n]);
+        }
+      }
+    }
+    for (; k < K; ++k) {
+      const float x = a[k];
+#pragma unroll
+      for (int n = 0; n < NT; ++n) acc[n] = fmaf(x, Ws[k * NT + n], acc[n]);
+    }
+#pragma unroll
+    for (int n = 0; n < NT; ++n) {
+      if (n < N) {
+        float x = p.alpha * acc[n];
+        if (p.beta != 0.f) x += p.beta * p.C[m * p.ldc + n];
+        if (p.bias) x += p.bias[n];
+        p.C[m * p.ldc + n] = apply_act(x, p.act);
+      }
+    }
+  }
+}
+
+// wgrad of the tail: C[M,N] = A^T B with M*N <= 256 and K = batch: each block
+// reduces a slab of kSkinnySlab batch rows (thread t owns output (t / N, t % N)),
+// slab partials are summed in fixed order by gemm_splitk_finish_kernel.
+constexpr int kSkinnySlab = 1024;
+__global__ void __launch_bounds__(256) gemm_skinny_wgrad_kernel(const GemmParams p) {
+  __shared__ float As[32][65];     // [row in sub-slab][m]  (M <= 64)
+  __shared__ float Bs[32][33];     // [row in sub-slab][n]  (N <= 32)
+  const int M = (int)p.M, N = (int)p.N;
+  const int t = threadIdx.x;
+  const int om = t / N, on = t % N;
+  const bool own = t < M * N;
+  const long long r0 = (long long)blockIdx.x * kSkinnySlab;
+  long long r1 = r0 + kSkinnySlab;
+  if (r1 > p.K) r1 = p.K;
+  float acc = 0.f;
+  for (long long rb = r0; rb < r1; rb += 32) {
+    for (int e = t; e < 32 * M; e += 256) {
+      const int rr = e / M, mm = e % M;
+      const long long r = rb + rr;
+      As[rr][mm] = r < r1 ? p.A[mm * p.sam + r * p.sak] : 0.f;
+    }
+    for (int e = t; e < 32 * N; e += 256) {
+      const int rr = e / N, nn = e % N;
+      const long long r = rb + rr;
+      Bs[rr][nn] = r < r1 ? p.B[r * p.sbk + nn * p.sbn] : 0.f;
+    }
+    __syncthreads();
+    if (own) {
+#pragma unroll 8
+      for (int rr = 0; rr < 32; ++rr) acc = fmaf(As[rr][om], Bs[rr][on], acc);
+    }
+    __syncthreads();
+  }
+  if (own) p.partial[(long long)blockIdx.x * M * N + t] = acc;
+}
+
 __global__ void __launch_bounds__(256) act_backward_kernel(float* dy, const float* y, long long n, int act) {
   for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < n; t += (long long)gridDim.x * blockDim.x) {
     const float yy = y[t];
@@ -141,25 +225,25 @@ __global__ void __launch_bounds__(256) act_backward_kernel(float* dy, const floa
   }
 }
 
-// column sums: stage 1 -- each block sums a slab of rows for 32 columns
+// column sums: stage 1 -- each block sums a slab of rows for CB (power of two <= 32)
+// columns; the 256 threads are arranged as (256/CB) row lanes x CB columns.
 constexpr int kColRowsPerBlock = 2048;
 __global__ void __launch_bounds__(256) colsum_stage1_kernel(const float* X, long long M, long long N, long long ldx,
-                                                            float* partial /* [slabs, N] */) {
-  __shared__ float sm[8][33];
-  const int cx = threadIdx.x & 31, ry = threadIdx.x >> 5;
-  const long long n = (long long)blockIdx.x * 32 + cx;
+                                                            int CB, float* partial /* [slabs, N] */) {
+  __shared__ float sm[256];
+  const int cx = threadIdx.x % CB, ry = threadIdx.x / CB, RY = 256 / CB;
+  const long long n = (long long)blockIdx.x * CB + cx;
   const long long r0 = (long long)blockIdx.y * kColRowsPerBlock;
   long long r1 = r0 + kColRowsPerBlock;
   if (r1 > M) r1 = M;
   float s = 0.f;
   if (n < N)
-    for (long long r = r0 + ry; r < r1; r += 8) s += X[r * ldx + n];
-  sm[ry][cx] = s;
+    for (long long r = r0 + ry; r < r1; r += RY) s += X[r * ldx + n];
+  sm[threadIdx.x] = s;
   __syncthreads();
   if (ry == 0 && n < N) {
     float t = 0.f;
-#pragma unroll
-    for (int q = 0; q < 8; ++q) t += sm[q][cx];
+    for (int q = 0; q < RY; ++q) t += sm[q * CB + cx];
     partial[(long long)blockIdx.y * N + n] = t;
   }
 }
@@ -235,6 +319,30 @@ __global__ void __launch_bounds__(256) cross_mat_fwd_elem_kernel(const float* x0
 }
 
 static int gemm_dispatch(etr_ctx* ctx, GemmParams& p, cudaStream_t s) {
+  // skinny shapes first: rows x tiny weight matrix (forward / dgrad of the MLP tail)
+  if (p.sak == 1 && p.N <= 32 && p.K <= 128 && p.M >= 1024) {
+    const int nt = p.N <= 1 ? 1 : (p.N <= 8 ? 8 : (p.N <= 16 ? 16 : 32));
+    const size_t smem = (size_t)p.K * nt * sizeof(float);
+    const int grid = grid_for(p.M, 256, ctx->sm_count, 8);
+    if (nt == 1) gemm_skinny_rows_kernel<1><<<grid, 256, smem, s>>>(p);
+    else if (nt == 8) gemm_skinny_rows_kernel<8><<<grid, 256, smem, s>>>(p);
+    else if (nt == 16) gemm_skinny_rows_kernel<16><<<grid, 256, smem, s>>>(p);
+    else gemm_skinny_rows_kernel<32><<<grid, 256, smem, s>>>(p);
+    ETR_LAUNCH_CHECK(ctx);
+    return ETR_OK;
+  }
+  // wgrad of the tail: tiny output, reduction over the batch
+  if (p.M * p.N <= 256 && p.M <= 64 && p.N <= 32 && p.K >= 4096) {
+    p.splits = (int)ceil_div(p.K, kSkinnySlab);
+    int st = etr_ws_reserve(ctx, sizeof(float) * (size_t)p.splits * p.M * p.N);
+    if (st != ETR_OK) return st;
+    p.partial = (float*)ctx->d_ws;
+    gemm_skinny_wgrad_kernel<<<p.splits, 256, 0, s>>>(p);
+    ETR_LAUNCH_CHECK(ctx);
+    gemm_splitk_finish_kernel<<<1, 256, 0, s>>>(p);
+    ETR_LAUNCH_CHECK(ctx);
+    return ETR_OK;
+  }
   // tile selection by N; split-K when the MN grid cannot fill the machine
   int bm, bn;
   if (p.N <= 8) { bm = 256; bn = 8; } else if (p.N <= 32) { bm = 256; bn = 32; } else { bm = 128; bn = 64; }
@@ -305,8 +413,10 @@ int etr_colsum_f32(etr_ctx* ctx, const float* d_X, int64_t M, int64_t N, int64_t
   ETR_CHECK_ARG(slabs <= 65535, "M too large");
   int st = etr_ws_reserve(ctx, sizeof(float) * (size_t)slabs * N);
   if (st != ETR_OK) return st;
-  dim3 grid((unsigned)ceil_div(N, 32), (unsigned)slabs);
-  colsum_stage1_kernel<<<grid, 256, 0, s>>>(d_X, M, N, ldx, (float*)ctx->d_ws);
+  int cb = 1;
+  while (cb < 32 && cb < N) cb <<= 1;
+  dim3 grid((unsigned)ceil_div(N, cb), (unsigned)slabs);
+  colsum_stage1_kernel<<<grid, 256, 0, s>>>(d_X, M, N, ldx, cb, (float*)ctx->d_ws);
   ETR_LAUNCH_CHECK(ctx);
   colsum_stage2_kernel<<<grid_for(N, 256, ctx->sm_count, 1), 256, 0, s>>>((const float*)ctx->d_ws, slabs, N, d_out);
   ETR_LAUNCH_CHECK(ctx);

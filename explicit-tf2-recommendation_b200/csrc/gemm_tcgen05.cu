@@ -1,0 +1,553 @@
+// K6 / K7 tensor-core path: bf16 GEMM on the 5th-gen tensor cores.
+//
+//   C[M,N] = epilogue( A[M,K] * B[N,K]^T )      A, B bf16, K contiguous ("TN")
+//
+// Operand tiles are brought in by TMA (cp.async.bulk.tensor, 128-byte swizzle)
+// into a multi-stage shared-memory ring; one elected thread issues
+// tcgen05.mma.cta_group::1.kind::f16 (UMMA 128 x BLOCK_N x 16, fp32 accumulate)
+// with the accumulator living in TMEM; four epilogue warps read it back with
+// tcgen05.ld and apply the fused epilogue:
+//   EPI_LINEAR : C = act(acc + bias)                      (MLP layers, dgrad)
+//   EPI_CROSS  : u = acc + b ; out = x0 (.) u + xl        (DCN-matrix cross layer,
+//                3.DCN/CustomLayers.py:300-303 -- y = W x  ==  X_l W^T, so W
+//                itself, row-major [D,D], IS the [N,K] operand)
+//   EPI_PARTIAL: fp32 partial tile for split-K (wgrad shapes, K = batch)
+// Two CTAs are resident per SM (shared memory and TMEM are budgeted for it), so
+// one CTA's epilogue overlaps the other's main loop.
+//
+// Warp roles (192 threads): warp 0 = TMA producer, warp 1 = TMEM allocator +
+// MMA issuer, warps 2..5 = epilogue (TMEM lane quarter = warp_id % 4).
+#include <cuda.h>
+
+#include "etr_common.cuh"
+
+namespace etr {
+namespace tc {
+
+constexpr int BLOCK_M = 128;
+constexpr int BLOCK_K = 64;            // 64 bf16 = 128 bytes = one swizzle atom row
+constexpr int UMMA_K = 16;
+constexpr int kThreads = 192;
+
+enum { EPI_LINEAR = 0, EPI_CROSS = 1, EPI_PARTIAL = 2 };
+
+struct EpiParams {
+  int mode;
+  long long M, N;
+  void* C; long long ldc; int c_bf16;            // LINEAR: output
+  const float* bias; int act;
+  const __nv_bfloat16* x0; const __nv_bfloat16* xl; long long ldx;   // CROSS inputs
+  __nv_bfloat16* out; long long ldo;             // CROSS: x_{l+1}
+  __nv_bfloat16* u; long long ldu;               // CROSS: optional U = xl W^T + b
+  float* partial;                                // PARTIAL: [splits, M, N]
+  int k_blocks_total; int k_blocks_per_split;
+};
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred P1;\n"
+      "LAB_WAIT:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n"
+      "@P1 bra DONE;\n"
+      "bra LAB_WAIT;\n"
+      "DONE:\n"
+      "}\n" ::"r"(bar),
+      "r"(parity)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c_inner, int c_outer) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(dst),
+      "l"(reinterpret_cast<uint64_t>(map)), "r"(bar), "r"(c_inner), "r"(c_outer)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_alloc(uint32_t dst_smem, uint32_t ncols) {
+  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(dst_smem), "r"(ncols) : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
+  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+__device__ __forceinline__ void fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "setp.ne.b32 p, %4, 0;\n"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n"
+      "}\n" ::"r"(tmem_d),
+      "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+        "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]),
+        "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]),
+        "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+      : "r"(taddr)
+      : "memory");
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+// K-major, 128-byte-swizzled shared-memory operand descriptor (sm_100 UMMA):
+// start address >> 4 in bits [0,14); LBO unused for swizzled K-major (0);
+// SBO = 8 rows * 128 B = 1024 B (>> 4) in bits [32,46); descriptor version 1 in
+// bits [46,48); layout type SWIZZLE_128B = 2 in bits [61,64).
+__device__ __forceinline__ uint64_t make_kmajor_sw128_desc(uint32_t smem_addr) {
+  uint64_t d = 0;
+  d |= (uint64_t)((smem_addr & 0x3FFFF) >> 4);
+  d |= (uint64_t)(1024 >> 4) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)2 << 61;
+  return d;
+}
+
+// kind::f16 instruction descriptor: D = F32 (bits 4-5 = 1), A = B = BF16 (bits 7-9,
+// 10-12 = 1), both K-major (bits 15, 16 = 0), N >> 3 in bits [17,23), M >> 4 in [24,29).
+__device__ __forceinline__ uint32_t make_idesc(int umma_m, int umma_n) {
+  return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(umma_n >> 3) << 17) | ((uint32_t)(umma_m >> 4) << 24);
+}
+
+__device__ __forceinline__ float act_apply(float x, int act) {
+  switch (act) {
+    case ETR_ACT_RELU: return x > 0.f ? x : 0.f;
+    case ETR_ACT_SIGMOID: return 1.0f / (1.0f + expf(-x));
+    case ETR_ACT_TANH: return tanhf(x);
+    default: return x;
+  }
+}
+
+template <int BLOCK_N, int STAGES>
+__global__ void __launch_bounds__(kThreads, 1)
+gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b, const EpiParams ep) {
+  constexpr uint32_t A_BYTES = BLOCK_M * BLOCK_K * 2;        // 16 KiB
+  constexpr uint32_t B_BYTES = BLOCK_N * BLOCK_K * 2;
+  constexpr uint32_t TMEM_COLS = BLOCK_N <= 32 ? 32 : (BLOCK_N <= 64 ? 64 : (BLOCK_N <= 128 ? 128 : 256));
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  // 1024-byte alignment is required by the 128B swizzle atoms
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint8_t* smem_a = smem;
+  uint8_t* smem_b = smem + STAGES * A_BYTES;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem_b + STAGES * B_BYTES);
+  uint64_t* full_bar = bars;                 // [STAGES]
+  uint64_t* empty_bar = bars + STAGES;       // [STAGES]
+  uint64_t* tmem_full_bar = bars + 2 * STAGES;
+  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 1);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int n_tile = blockIdx.x, m_tile = blockIdx.y, split = blockIdx.z;
+  const int kb_begin = split * ep.k_blocks_per_split;
+  int kb_end = kb_begin + ep.k_blocks_per_split;
+  if (kb_end > ep.k_blocks_total) kb_end = ep.k_blocks_total;
+  const int nkb = kb_end - kb_begin;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < STAGES; ++s) { mbar_init(smem_u32(&full_bar[s]), 1); mbar_init(smem_u32(&empty_bar[s]), 1); }
+    mbar_init(smem_u32(tmem_full_bar), 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&map_a)) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&map_b)) : "memory");
+  }
+  if (warp == 1) tmem_alloc(smem_u32(tmem_ptr_smem), TMEM_COLS);
+  fence_before();
+  __syncthreads();
+  fence_after();
+  const uint32_t tmem_base = *tmem_ptr_smem;
+
+  if (warp == 0) {
+    // ===== TMA producer =====
+    if (lane == 0) {
+      for (int i = 0; i < nkb; ++i) {
+        const int s = i % STAGES;
+        const uint32_t ph = (i / STAGES) & 1;
+        mbar_wait(smem_u32(&empty_bar[s]), ph ^ 1);
+        mbar_expect_tx(smem_u32(&full_bar[s]), A_BYTES + B_BYTES);
+        const int k0 = (kb_begin + i) * BLOCK_K;
+        tma_load_2d(smem_u32(smem_a + s * A_BYTES), &map_a, smem_u32(&full_bar[s]), k0, m_tile * BLOCK_M);
+        tma_load_2d(smem_u32(smem_b + s * B_BYTES), &map_b, smem_u32(&full_bar[s]), k0, n_tile * BLOCK_N);
+      }
+    }
+  } else if (warp == 1) {
+    // ===== MMA issuer =====
+    if (lane == 0) {
+      const uint32_t idesc = make_idesc(BLOCK_M, BLOCK_N);
+      for (int i = 0; i < nkb; ++i) {
+        const int s = i % STAGES;
+        const uint32_t ph = (i / STAGES) & 1;
+        mbar_wait(smem_u32(&full_bar[s]), ph);
+        fence_after();
+        const uint64_t da = make_kmajor_sw128_desc(smem_u32(smem_a + s * A_BYTES));
+        const uint64_t db = make_kmajor_sw128_desc(smem_u32(smem_b + s * B_BYTES));
+#pragma unroll
+        for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
+          // advance 16 bf16 = 32 bytes inside the swizzle atom: +2 in the (>>4) address field
+          umma_f16(tmem_base, da + (uint64_t)(k * 2), db + (uint64_t)(k * 2), idesc, (i | k) != 0 ? 1u : 0u);
+        }
+        umma_commit(smem_u32(&empty_bar[s]));        // frees the smem stage once these MMAs retire
+      }
+      umma_commit(smem_u32(tmem_full_bar));            // accumulator complete
+    }
+  } else {
+    // ===== epilogue warps 2..5 =====
+    const int q = warp & 3;                            // TMEM lane quarter this warp may read
+    mbar_wait(smem_u32(tmem_full_bar), 0);
+    fence_after();
+    const long long row = (long long)m_tile * BLOCK_M + q * 32 + lane;
+    const bool row_ok = row < ep.M;
+#pragma unroll 1
+    for (int c0 = 0; c0 < BLOCK_N; c0 += 32) {
+      const long long col0 = (long long)n_tile * BLOCK_N + c0;
+      if (col0 >= ep.N) break;                         // warp-uniform
+      uint32_t v[32];
+      if (nkb > 0) {
+        tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, v);
+      } else {
+#pragma unroll
+        for (int i = 0; i < 32; ++i) v[i] = 0u;
+      }
+      if (!row_ok) continue;
+      const int ncol = (ep.N - col0) < 32 ? (int)(ep.N - col0) : 32;
+      if (ep.mode == EPI_PARTIAL) {
+        float* dst = ep.partial + ((long long)split * ep.M + row) * ep.N + col0;
+#pragma unroll
+        for (int i = 0; i < 32; ++i)
+          if (i < ncol) dst[i] = __uint_as_float(v[i]);
+      } else if (ep.mode == EPI_LINEAR) {
+        if (ep.c_bf16) {
+          __nv_bfloat16* dst = reinterpret_cast<__nv_bfloat16*>(ep.C) + row * ep.ldc + col0;
+          const bool vec = (ncol == 32) && ((reinterpret_cast<uintptr_t>(dst) & 15) == 0);
+          if (vec) {
+#pragma unroll
+            for (int i = 0; i < 32; i += 8) {
+              uint32_t w[4];
+#pragma unroll
+              for (int j = 0; j < 4; ++j) {
+                const float a = act_apply(__uint_as_float(v[i + 2 * j]) + (ep.bias ? ep.bias[col0 + i + 2 * j] : 0.f), ep.act);
+                const float b = act_apply(__uint_as_float(v[i + 2 * j + 1]) + (ep.bias ? ep.bias[col0 + i + 2 * j + 1] : 0.f), ep.act);
+                __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
+                w[j] = *reinterpret_cast<uint32_t*>(&h);
+              }
+              *reinterpret_cast<uint4*>(dst + i) = make_uint4(w[0], w[1], w[2], w[3]);
+            }
+          } else {
+#pragma unroll
+            for (int i = 0; i < 32; ++i)
+              if (i < ncol)
+                dst[i] = __float2bfloat16_rn(act_apply(__uint_as_float(v[i]) + (ep.bias ? ep.bias[col0 + i] : 0.f), ep.act));
+          }
+        } else {
+          float* dst = reinterpret_cast<float*>(ep.C) + row * ep.ldc + col0;
+          const bool vec = (ncol == 32) && ((reinterpret_cast<uintptr_t>(dst) & 15) == 0);
+          if (vec) {
+#pragma unroll
+            for (int i = 0; i < 32; i += 4) {
+              float4 o;
+              o.x = act_apply(__uint_as_float(v[i]) + (ep.bias ? ep.bias[col0 + i] : 0.f), ep.act);
+              o.y = act_apply(__uint_as_float(v[i + 1]) + (ep.bias ? ep.bias[col0 + i + 1] : 0.f), ep.act);
+              o.z = act_apply(__uint_as_float(v[i + 2]) + (ep.bias ? ep.bias[col0 + i + 2] : 0.f), ep.act);
+              o.w = act_apply(__uint_as_float(v[i + 3]) + (ep.bias ? ep.bias[col0 + i + 3] : 0.f), ep.act);
+              *reinterpret_cast<float4*>(dst + i) = o;
+            }
+          } else {
+#pragma unroll
+            for (int i = 0; i < 32; ++i)
+              if (i < ncol) dst[i] = act_apply(__uint_as_float(v[i]) + (ep.bias ? ep.bias[col0 + i] : 0.f), ep.act);
+          }
+        }
+      } else {   // EPI_CROSS: u = acc + b ; out = x0 * u + xl
+        const __nv_bfloat16* px0 = ep.x0 + row * ep.ldx + col0;
+        const __nv_bfloat16* pxl = ep.xl + row * ep.ldx + col0;
+        __nv_bfloat16* po = ep.out + row * ep.ldo + col0;
+        __nv_bfloat16* pu = ep.u ? ep.u + row * ep.ldu + col0 : nullptr;
+        const bool vec = (ncol == 32) && (((reinterpret_cast<uintptr_t>(px0) | reinterpret_cast<uintptr_t>(pxl) |
+                                            reinterpret_cast<uintptr_t>(po) | reinterpret_cast<uintptr_t>(pu)) & 15) == 0);
+        if (vec) {
+#pragma unroll
+          for (int i = 0; i < 32; i += 8) {
+            const uint4 a0 = *reinterpret_cast<const uint4*>(px0 + i);
+            const uint4 al = *reinterpret_cast<const uint4*>(pxl + i);
+            const uint32_t w0[4] = {a0.x, a0.y, a0.z, a0.w};
+            const uint32_t wl[4] = {al.x, al.y, al.z, al.w};
+            uint32_t wo[4], wu[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              const float2 f0 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&w0[j]));
+              const float2 fl = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&wl[j]));
+              const float ua = __uint_as_float(v[i + 2 * j]) + ep.bias[col0 + i + 2 * j];
+              const float ub = __uint_as_float(v[i + 2 * j + 1]) + ep.bias[col0 + i + 2 * j + 1];
+              __nv_bfloat162 ho = __floats2bfloat162_rn(f0.x * ua + fl.x, f0.y * ub + fl.y);
+              __nv_bfloat162 hu = __floats2bfloat162_rn(ua, ub);
+              wo[j] = *reinterpret_cast<uint32_t*>(&ho);
+              wu[j] = *reinterpret_cast<uint32_t*>(&hu);
+            }
+            *reinterpret_cast<uint4*>(po + i) = make_uint4(wo[0], wo[1], wo[2], wo[3]);
+            if (pu) *reinterpret_cast<uint4*>(pu + i) = make_uint4(wu[0], wu[1], wu[2], wu[3]);
+          }
+        } else {
+#pragma unroll
+          for (int i = 0; i < 32; ++i) {
+            if (i < ncol) {
+              const float uu = __uint_as_float(v[i]) + ep.bias[col0 + i];
+              po[i] = __float2bfloat16_rn(__bfloat162float(px0[i]) * uu + __bfloat162float(pxl[i]));
+              if (pu) pu[i] = __float2bfloat16_rn(uu);
+            }
+          }
+        }
+      }
+    }
+  }
+  fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    fence_after();
+    tmem_dealloc(tmem_base, TMEM_COLS);
+  }
+}
+
+// split-K finish: C = act(sum_z partial[z] + bias) (fixed order), fp32 or bf16 out
+__global__ void __launch_bounds__(256) splitk_finish_kernel(const float* partial, int splits, long long M, long long N,
+                                                            void* C, long long ldc, int c_bf16, const float* bias, int act,
+                                                            float beta) {
+  const long long total = M * N;
+  for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (long long)gridDim.x * blockDim.x) {
+    const long long m = t / N, n = t % N;
+    float s = 0.f;
+    for (int z = 0; z < splits; ++z) s += partial[(long long)z * total + t];
+    if (bias) s += bias[n];
+    if (c_bf16) {
+      reinterpret_cast<__nv_bfloat16*>(C)[m * ldc + n] = __float2bfloat16_rn(act_apply(s, act));
+    } else {
+      float* c = reinterpret_cast<float*>(C) + m * ldc + n;
+      if (beta != 0.f) s += beta * *c;
+      *c = act_apply(s, act);
+    }
+  }
+}
+
+// fp32 [rows, cols] (ld_src) -> bf16, optionally transposed, into a zero-padded
+// [rows_dst, ld_dst] buffer (dst rows >= rows (or cols when transposing)).
+__global__ void __launch_bounds__(256) cast_bf16_kernel(const float* src, long long rows, long long cols, long long ld_src,
+                                                        __nv_bfloat16* dst, long long ld_dst, int transpose) {
+  __shared__ float tile[32][33];
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;    // 32 x 8
+  const long long r0 = (long long)blockIdx.y * 32, c0 = (long long)blockIdx.x * 32;
+  for (int i = ty; i < 32; i += 8) {
+    const long long r = r0 + i, c = c0 + tx;
+    tile[i][tx] = (r < rows && c < cols) ? src[r * ld_src + c] : 0.f;
+  }
+  __syncthreads();
+  if (!transpose) {
+    for (int i = ty; i < 32; i += 8) {
+      const long long r = r0 + i, c = c0 + tx;
+      if (r < rows && c < ld_dst) dst[r * ld_dst + c] = __float2bfloat16_rn(c < cols ? tile[i][tx] : 0.f);
+    }
+  } else {
+    for (int i = ty; i < 32; i += 8) {
+      const long long orow = c0 + i, ocol = r0 + tx;          // dst[c][r]
+      if (orow < cols && ocol < ld_dst) dst[orow * ld_dst + ocol] = __float2bfloat16_rn(ocol < rows ? tile[tx][i] : 0.f);
+    }
+  }
+}
+// bf16 [rows, cols] -> bf16 transposed [cols, ld_dst]
+__global__ void __launch_bounds__(256) transpose_bf16_kernel(const __nv_bfloat16* src, long long rows, long long cols,
+                                                             long long ld_src, __nv_bfloat16* dst, long long ld_dst) {
+  __shared__ __nv_bfloat16 tile[32][34];
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  const long long r0 = (long long)blockIdx.y * 32, c0 = (long long)blockIdx.x * 32;
+  for (int i = ty; i < 32; i += 8) {
+    const long long r = r0 + i, c = c0 + tx;
+    tile[i][tx] = (r < rows && c < cols) ? src[r * ld_src + c] : __float2bfloat16_rn(0.f);
+  }
+  __syncthreads();
+  for (int i = ty; i < 32; i += 8) {
+    const long long orow = c0 + i, ocol = r0 + tx;
+    if (orow < cols && ocol < ld_dst) dst[orow * ld_dst + ocol] = ocol < rows ? tile[tx][i] : __float2bfloat16_rn(0.f);
+  }
+}
+
+// ------------------------------------------------------------------ host side
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn get_encode() {
+  static EncodeTiledFn fn = nullptr;
+  if (!fn) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = (EncodeTiledFn)p;
+  }
+  return fn;
+}
+
+// 2-D bf16 tensor map: [rows, cols] with leading dimension ld (elements), box = [box_rows, 64 cols], 128B swizzle.
+static int make_map(CUtensorMap* map, const void* base, long long rows, long long cols, long long ld, int box_rows) {
+  EncodeTiledFn enc = get_encode();
+  if (!enc) { etr_set_error("cuTensorMapEncodeTiled is not available from the driver"); return ETR_ECUDA; }
+  if (((uintptr_t)base & 15) || (ld * 2) % 16 != 0) {
+    etr_set_error("tcgen05 GEMM operands need 16-byte aligned base and row pitch (ld %% 8 == 0)");
+    return ETR_EINVAL;
+  }
+  cuuint64_t gdim[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+  cuuint64_t gstride[1] = {(cuuint64_t)ld * 2};
+  cuuint32_t box[2] = {(cuuint32_t)BLOCK_K, (cuuint32_t)box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), gdim, gstride, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) { etr_set_error("cuTensorMapEncodeTiled failed with CUresult %d", (int)r); return ETR_ECUDA; }
+  return ETR_OK;
+}
+
+template <int BLOCK_N, int STAGES>
+static int launch_tile(etr_ctx* ctx, const CUtensorMap& ma, const CUtensorMap& mb, const EpiParams& ep, dim3 grid,
+                       cudaStream_t s) {
+  constexpr size_t smem = (size_t)STAGES * (BLOCK_M * BLOCK_K * 2 + BLOCK_N * BLOCK_K * 2) + (2 * STAGES + 2) * 8 + 1024;
+  static bool attr_done = false;
+  if (!attr_done) {
+    ETR_CUDA(cudaFuncSetAttribute(gemm_bf16_tn_kernel<BLOCK_N, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    attr_done = true;
+  }
+  gemm_bf16_tn_kernel<BLOCK_N, STAGES><<<grid, kThreads, smem, s>>>(ma, mb, ep);
+  ETR_LAUNCH_CHECK(ctx);
+  return ETR_OK;
+}
+
+// BLOCK_N choice: widest tile that does not waste more than ~7% of the N extent.
+static int pick_block_n(long long N) {
+  if (N <= 32) return 32;
+  if (N <= 64) return 64;
+  if (N <= 128) return 128;
+  const long long t240 = ceil_div(N, 240) * 240, t256 = ceil_div(N, 256) * 256, t128 = ceil_div(N, 128) * 128;
+  if (t240 <= t256 && t240 <= t128 + t128 / 16) return 240;
+  if (t256 <= t128 + t128 / 16) return 256;
+  return 128;
+}
+
+static int run_gemm(etr_ctx* ctx, long long M, long long N, long long K, const void* A, long long lda, const void* B,
+                    long long ldb, EpiParams ep, int allow_split, cudaStream_t s, void* C, long long ldc, int c_bf16,
+                    const float* bias, int act, float beta) {
+  const int bn = pick_block_n(N);
+  CUtensorMap ma, mb;
+  int st = make_map(&ma, A, M, K, lda, BLOCK_M);
+  if (st != ETR_OK) return st;
+  st = make_map(&mb, B, N, K, ldb, bn);
+  if (st != ETR_OK) return st;
+  const long long mt = ceil_div(M, BLOCK_M), nt = ceil_div(N, bn);
+  const int kbt = (int)ceil_div(K, BLOCK_K);
+  int splits = 1;
+  if (allow_split && mt * nt < ctx->sm_count && kbt >= 64) {
+    splits = (int)((2LL * ctx->sm_count) / (mt * nt));
+    if (splits > kbt / 16) splits = kbt / 16;
+    if (splits < 1) splits = 1;
+  }
+  ep.M = M; ep.N = N;
+  ep.k_blocks_total = kbt;
+  ep.k_blocks_per_split = (int)ceil_div(kbt, splits);
+  splits = (int)ceil_div(kbt, ep.k_blocks_per_split);
+  if (splits > 1) {
+    st = etr_ws_reserve(ctx, sizeof(float) * (size_t)splits * M * N);
+    if (st != ETR_OK) return st;
+    ep.mode = EPI_PARTIAL;
+    ep.partial = (float*)ctx->d_ws;
+  }
+  if (mt > 65535 || nt > 65535) { etr_set_error("tcgen05 GEMM: too many tiles"); return ETR_EUNSUPPORTED; }
+  dim3 grid((unsigned)nt, (unsigned)mt, (unsigned)splits);
+  switch (bn) {
+    case 32: st = launch_tile<32, 4>(ctx, ma, mb, ep, grid, s); break;
+    case 64: st = launch_tile<64, 4>(ctx, ma, mb, ep, grid, s); break;
+    case 128: st = launch_tile<128, 3>(ctx, ma, mb, ep, grid, s); break;
+    case 240: st = launch_tile<240, 2>(ctx, ma, mb, ep, grid, s); break;
+    default: st = launch_tile<256, 2>(ctx, ma, mb, ep, grid, s); break;
+  }
+  if (st != ETR_OK) return st;
+  if (splits > 1) {
+    splitk_finish_kernel<<<grid_for(M * N, 256, ctx->sm_count, 8), 256, 0, s>>>((const float*)ctx->d_ws, splits, M, N, C,
+                                                                              ldc, c_bf16, bias, act, beta);
+    ETR_LAUNCH_CHECK(ctx);
+  }
+  return ETR_OK;
+}
+
+}  // namespace tc
+}  // namespace etr
+
+using namespace etr;
+
+extern "C" {
+
+int etr_gemm_bf16_tn(etr_ctx* ctx, int64_t M, int64_t N, int64_t K, const void* d_A, int64_t lda, const void* d_B,
+                     int64_t ldb, void* d_C, int64_t ldc, int32_t c_dtype, const float* d_bias, int32_t act,
+                     void* stream) {
+  ETR_CHECK_ARG(ctx && d_A && d_B && d_C, "NULL argument");
+  ETR_CHECK_ARG(M > 0 && N > 0 && K > 0, "empty GEMM");
+  tc::EpiParams ep;
+  memset(&ep, 0, sizeof(ep));
+  ep.mode = tc::EPI_LINEAR;
+  ep.C = d_C; ep.ldc = ldc; ep.c_bf16 = c_dtype == ETR_BF16; ep.bias = d_bias; ep.act = act;
+  return tc::run_gemm(ctx, M, N, K, d_A, lda, d_B, ldb, ep, 1, (cudaStream_t)stream, d_C, ldc, ep.c_bf16, d_bias, act, 0.f);
+}
+
+int etr_cross_mat_layer_bf16(etr_ctx* ctx, const void* d_x0, const void* d_xl, int64_t ldx, int64_t batch, int32_t D,
+                             const void* d_W, int64_t ldw, const float* d_b, void* d_out, int64_t ldo, void* d_u,
+                             int64_t ldu, void* stream) {
+  ETR_CHECK_ARG(ctx && d_x0 && d_xl && d_W && d_b && d_out, "NULL argument");
+  ETR_CHECK_ARG(batch > 0 && D > 0, "empty problem");
+  tc::EpiParams ep;
+  memset(&ep, 0, sizeof(ep));
+  ep.mode = tc::EPI_CROSS;
+  ep.bias = d_b;
+  ep.x0 = (const __nv_bfloat16*)d_x0; ep.xl = (const __nv_bfloat16*)d_xl; ep.ldx = ldx;
+  ep.out = (__nv_bfloat16*)d_out; ep.ldo = ldo; ep.u = (__nv_bfloat16*)d_u; ep.ldu = ldu;
+  // U = X_l W^T : A = X_l [B, D], B operand = W [N = D, K = D] row-major
+  return tc::run_gemm(ctx, batch, D, D, d_xl, ldx, d_W, ldw, ep, 0, (cudaStream_t)stream, nullptr, 0, 1, nullptr, 0, 0.f);
+}
+
+int etr_cast_bf16(etr_ctx* ctx, const float* d_src, int64_t rows, int64_t cols, int64_t ld_src, void* d_dst,
+                  int64_t ld_dst, int32_t transpose, void* stream) {
+  ETR_CHECK_ARG(ctx && d_src && d_dst, "NULL argument");
+  if (rows <= 0 || cols <= 0) return ETR_OK;
+  // cover the padded destination width too (zero fill up to ld_dst)
+  const long long out_cols = transpose ? rows : cols;
+  const long long span_c = transpose ? cols : (ld_dst > cols ? ld_dst : cols);
+  const long long span_r = transpose ? (ld_dst > rows ? ld_dst : rows) : rows;
+  (void)out_cols;
+  dim3 grid((unsigned)ceil_div(span_c, 32), (unsigned)ceil_div(span_r, 32));
+  tc::cast_bf16_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(d_src, rows, cols, ld_src, (__nv_bfloat16*)d_dst, ld_dst,
+                                                              transpose);
+  ETR_LAUNCH_CHECK(ctx);
+  return ETR_OK;
+}
+
+int etr_transpose_bf16(etr_ctx* ctx, const void* d_src, int64_t rows, int64_t cols, int64_t ld_src, void* d_dst,
+                       int64_t ld_dst, void* stream) {
+  ETR_CHECK_ARG(ctx && d_src && d_dst, "NULL argument");
+  if (rows <= 0 || cols <= 0) return ETR_OK;
+  const long long span_r = ld_dst > rows ? ld_dst : rows;
+  dim3 grid((unsigned)ceil_div(cols, 32), (unsigned)ceil_div(span_r, 32));
+  tc::transpose_bf16_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>((const __nv_bfloat16*)d_src, rows, cols, ld_src,
+                                                                   (__nv_bfloat16*)d_dst, ld_dst);
+  ETR_LAUNCH_CHECK(ctx);
+  return ETR_OK;
+}
+
+}  // extern "C"

@@ -105,7 +105,42 @@ struct SegParams {
   int max_long, max_items;
 };
 
-template <int LPR>
+// Sums gradient rows sorted_bag[i0..i1) into acc[CPL] (lane gl of an LPR-lane
+// group owns 16-byte chunks gl, gl+LPR, ...), 4 rows in flight.
+template <int LPR, int CPL>
+__device__ __forceinline__ void sum_rows(const SegParams& p, int i0, int i1, int gl, int nchunks, float4 (&acc)[CPL]) {
+  int i = i0;
+  for (; i + 4 <= i1; i += 4) {
+    int bg[4];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) bg[q] = __ldg(p.sorted_bag + i + q);
+#pragma unroll
+    for (int j = 0; j < CPL; ++j) {
+      const int c = gl + j * LPR;
+      if (c < nchunks) {
+        float4 r[4];
+#pragma unroll
+        for (int q = 0; q < 4; ++q)
+          r[q] = *reinterpret_cast<const float4*>(p.bag_grad + (long long)bg[q] * p.grad_ld + c * 4);
+#pragma unroll
+        for (int q = 0; q < 4; ++q) { acc[j].x += r[q].x; acc[j].y += r[q].y; acc[j].z += r[q].z; acc[j].w += r[q].w; }
+      }
+    }
+  }
+  for (; i < i1; ++i) {
+    const long long row = (long long)__ldg(p.sorted_bag + i) * p.grad_ld;
+#pragma unroll
+    for (int j = 0; j < CPL; ++j) {
+      const int c = gl + j * LPR;
+      if (c < nchunks) {
+        const float4 r = *reinterpret_cast<const float4*>(p.bag_grad + row + c * 4);
+        acc[j].x += r.x; acc[j].y += r.y; acc[j].z += r.z; acc[j].w += r.w;
+      }
+    }
+  }
+}
+
+template <int LPR, int CPL>
 __global__ void __launch_bounds__(256) seg_reduce_short_kernel(const SegParams p) {
   constexpr int GPW = 32 / LPR;
   const int lane = threadIdx.x & 31;
@@ -129,36 +164,24 @@ __global__ void __launch_bounds__(256) seg_reduce_short_kernel(const SegParams p
       }
       continue;
     }
-    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (gl < nchunks) {
-      int i = s0;
-      for (; i + 4 <= s1; i += 4) {
-        int bg[4];
-        float4 r[4];
+    float4 acc[CPL];
 #pragma unroll
-        for (int q = 0; q < 4; ++q) bg[q] = __ldg(p.sorted_bag + i + q);
+    for (int j = 0; j < CPL; ++j) acc[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+    sum_rows<LPR, CPL>(p, s0, s1, gl, nchunks, acc);
 #pragma unroll
-        for (int q = 0; q < 4; ++q)
-          r[q] = *reinterpret_cast<const float4*>(p.bag_grad + (long long)bg[q] * p.grad_ld + gl * 4);
-#pragma unroll
-        for (int q = 0; q < 4; ++q) { acc.x += r[q].x; acc.y += r[q].y; acc.z += r[q].z; acc.w += r[q].w; }
-      }
-      for (; i < s1; ++i) {
-        const float4 r = *reinterpret_cast<const float4*>(
-            p.bag_grad + (long long)__ldg(p.sorted_bag + i) * p.grad_ld + gl * 4);
-        acc.x += r.x; acc.y += r.y; acc.z += r.z; acc.w += r.w;
-      }
-      *reinterpret_cast<float4*>(p.unique_grad + u * (long long)p.grad_ld + gl * 4) = acc;
+    for (int j = 0; j < CPL; ++j) {
+      const int c = gl + j * LPR;
+      if (c < nchunks) *reinterpret_cast<float4*>(p.unique_grad + u * (long long)p.grad_ld + c * 4) = acc[j];
     }
   }
 }
 
 // one CTA per chunk item: 256 threads = (256/LPR) lane groups, each summing a
 // contiguous sub-range in order; sub-range partials combined in order by group 0.
-template <int LPR>
+template <int LPR, int CPL>
 __global__ void __launch_bounds__(256) seg_reduce_chunk_kernel(const SegParams p) {
   constexpr int NG = 256 / LPR;
-  __shared__ float4 sm[NG][LPR];
+  extern __shared__ __align__(16) float4 sm4[];      // [NG][nchunks]
   const int gl = threadIdx.x % LPR, g = threadIdx.x / LPR;
   const int nchunks = p.grad_ld / 4;
   int n_items = p.counters[1];
@@ -172,42 +195,31 @@ __global__ void __launch_bounds__(256) seg_reduce_chunk_kernel(const SegParams p
     const int len = s1 - s0;
     const int per = (len + NG - 1) / NG;
     int a = s0 + g * per, b = a + per;
+    if (a > s1) a = s1;
     if (b > s1) b = s1;
-    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (gl < nchunks) {
-      int i = a;
-      for (; i + 4 <= b; i += 4) {
-        int bg[4];
-        float4 r[4];
+    float4 acc[CPL];
 #pragma unroll
-        for (int q = 0; q < 4; ++q) bg[q] = __ldg(p.sorted_bag + i + q);
+    for (int j = 0; j < CPL; ++j) acc[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+    sum_rows<LPR, CPL>(p, a, b, gl, nchunks, acc);
 #pragma unroll
-        for (int q = 0; q < 4; ++q)
-          r[q] = *reinterpret_cast<const float4*>(p.bag_grad + (long long)bg[q] * p.grad_ld + gl * 4);
-#pragma unroll
-        for (int q = 0; q < 4; ++q) { acc.x += r[q].x; acc.y += r[q].y; acc.z += r[q].z; acc.w += r[q].w; }
-      }
-      for (; i < b; ++i) {
-        const float4 r = *reinterpret_cast<const float4*>(
-            p.bag_grad + (long long)__ldg(p.sorted_bag + i) * p.grad_ld + gl * 4);
-        acc.x += r.x; acc.y += r.y; acc.z += r.z; acc.w += r.w;
-      }
+    for (int j = 0; j < CPL; ++j) {
+      const int c = gl + j * LPR;
+      if (c < nchunks) sm4[g * nchunks + c] = acc[j];
     }
-    sm[g][gl] = acc;
     __syncthreads();
-    if (g == 0 && gl < nchunks) {
-      float4 t = sm[0][gl];
+    for (int c = threadIdx.x; c < nchunks; c += blockDim.x) {
+      float4 t = sm4[c];
       for (int q = 1; q < NG; ++q) {
-        const float4 r = sm[q][gl];
+        const float4 r = sm4[q * nchunks + c];
         t.x += r.x; t.y += r.y; t.z += r.z; t.w += r.w;
       }
-      *reinterpret_cast<float4*>(p.partials + (long long)it * p.grad_ld + gl * 4) = t;
+      *reinterpret_cast<float4*>(p.partials + (long long)it * p.grad_ld + c * 4) = t;
     }
     __syncthreads();
   }
 }
 
-template <int LPR>
+template <int LPR, int CPL>
 __global__ void __launch_bounds__(256) seg_reduce_combine_kernel(const SegParams p) {
   constexpr int GPW = 32 / LPR;
   const int lane = threadIdx.x & 31;
@@ -219,13 +231,17 @@ __global__ void __launch_bounds__(256) seg_reduce_combine_kernel(const SegParams
   const long long ngroups = (long long)gridDim.x * (blockDim.x >> 5) * GPW;
   for (long long r = group_global; r < n_long; r += ngroups) {
     const LongRun lr = p.long_runs[r];
-    if (gl >= nchunks) continue;
-    float4 t = make_float4(0.f, 0.f, 0.f, 0.f);
-    for (int c = 0; c < lr.nchunks; ++c) {
-      const float4 x = *reinterpret_cast<const float4*>(p.partials + (long long)(lr.base + c) * p.grad_ld + gl * 4);
-      t.x += x.x; t.y += x.y; t.z += x.z; t.w += x.w;
+#pragma unroll
+    for (int j = 0; j < CPL; ++j) {
+      const int c = gl + j * LPR;
+      if (c >= nchunks) continue;
+      float4 t = make_float4(0.f, 0.f, 0.f, 0.f);
+      for (int q = 0; q < lr.nchunks; ++q) {
+        const float4 x = *reinterpret_cast<const float4*>(p.partials + (long long)(lr.base + q) * p.grad_ld + c * 4);
+        t.x += x.x; t.y += x.y; t.z += x.z; t.w += x.w;
+      }
+      *reinterpret_cast<float4*>(p.unique_grad + (long long)lr.u * p.grad_ld + c * 4) = t;
     }
-    *reinterpret_cast<float4*>(p.unique_grad + (long long)lr.u * p.grad_ld + gl * 4) = t;
   }
 }
 
@@ -420,7 +436,7 @@ int etr_sparse_segment_reduce(etr_ctx* ctx, const int32_t* d_sorted_bag, const i
                               const int32_t* d_n_unique, int64_t n_slots, const float* d_bag_grad,
                               int32_t grad_ld, float* d_unique_grad, void* stream) {
   ETR_CHECK_ARG(ctx && d_sorted_bag && d_seg_start && d_n_unique && d_bag_grad && d_unique_grad, "NULL argument");
-  ETR_CHECK_ARG(grad_ld > 0 && grad_ld % 4 == 0 && grad_ld <= 512, "grad_ld must be a multiple of 4, <= 512");
+  ETR_CHECK_ARG(grad_ld > 0 && grad_ld % 4 == 0, "grad_ld must be a positive multiple of 4");
   ETR_CHECK_ARG((((uintptr_t)d_bag_grad | (uintptr_t)d_unique_grad) & 15) == 0, "gradients must be 16-byte aligned");
   if (n_slots == 0) return ETR_OK;
   cudaStream_t s = (cudaStream_t)stream;
@@ -442,26 +458,34 @@ int etr_sparse_segment_reduce(etr_ctx* ctx, const int32_t* d_sorted_bag, const i
   p.partials = (float*)(ws + b_cnt + b_runs + b_items);
   ETR_CUDA(cudaMemsetAsync(p.counters, 0, 2 * sizeof(int), s));
   const int nchunks = grad_ld / 4;
-  if (nchunks > 32) { etr_set_error("segment_reduce: grad rows wider than 128 floats need the wide kernel"); return ETR_EUNSUPPORTED; }
   const int lpr = lpr_for(nchunks);
+  const int cpl = (nchunks + lpr - 1) / lpr;
+  if (cpl > 4) { etr_set_error("segment_reduce: grad rows wider than 512 floats are not covered"); return ETR_EUNSUPPORTED; }
   const int gshort = grid_for(n_slots, 8 * (32 / lpr), ctx->sm_count, 8);
   const int gchunk = ctx->sm_count * 4;
-#define ETR_SEG(LPR)                                                     \
-  do {                                                                   \
-    seg_reduce_short_kernel<LPR><<<gshort, 256, 0, s>>>(p);              \
-    ETR_LAUNCH_CHECK(ctx);                                               \
-    seg_reduce_chunk_kernel<LPR><<<gchunk, 256, 0, s>>>(p);              \
-    ETR_LAUNCH_CHECK(ctx);                                               \
-    seg_reduce_combine_kernel<LPR><<<ctx->sm_count, 256, 0, s>>>(p);     \
-    ETR_LAUNCH_CHECK(ctx);                                               \
+  const size_t csm = (size_t)(256 / lpr) * nchunks * sizeof(float4);
+#define ETR_SEG(LPR, CPL)                                                    \
+  do {                                                                       \
+    seg_reduce_short_kernel<LPR, CPL><<<gshort, 256, 0, s>>>(p);             \
+    ETR_LAUNCH_CHECK(ctx);                                                   \
+    seg_reduce_chunk_kernel<LPR, CPL><<<gchunk, 256, csm, s>>>(p);           \
+    ETR_LAUNCH_CHECK(ctx);                                                   \
+    seg_reduce_combine_kernel<LPR, CPL><<<ctx->sm_count, 256, 0, s>>>(p);    \
+    ETR_LAUNCH_CHECK(ctx);                                                   \
   } while (0)
-  switch (lpr) {
-    case 1: ETR_SEG(1); break;
-    case 2: ETR_SEG(2); break;
-    case 4: ETR_SEG(4); break;
-    case 8: ETR_SEG(8); break;
-    case 16: ETR_SEG(16); break;
-    default: ETR_SEG(32); break;
+  if (cpl == 1) {
+    switch (lpr) {
+      case 1: ETR_SEG(1, 1); break;
+      case 2: ETR_SEG(2, 1); break;
+      case 4: ETR_SEG(4, 1); break;
+      case 8: ETR_SEG(8, 1); break;
+      case 16: ETR_SEG(16, 1); break;
+      default: ETR_SEG(32, 1); break;
+    }
+  } else if (cpl == 2) {
+    ETR_SEG(32, 2);
+  } else {
+    ETR_SEG(32, 4);
   }
 #undef ETR_SEG
   return ETR_OK;

@@ -338,3 +338,36 @@ def bce_forward_backward(rt: Runtime, prob: torch.Tensor, label: torch.Tensor, w
 
 def lr_t(lr: float, b1: float, b2: float, t: int) -> float:
     return lr * math.sqrt(1.0 - b2 ** t) / (1.0 - b1 ** t)
+
+
+# ---------------------------------------------------------------------------
+# tensor-core (tcgen05) wrappers
+def gemm_bf16_tn(rt: Runtime, A: torch.Tensor, B: torch.Tensor, C_out: torch.Tensor, M: int, N: int, K: int,
+                 bias: Optional[torch.Tensor] = None, act=None):
+    """C[M,N] = act(A[M,K] B[N,K]^T + bias): A, B bf16 with unit column stride and
+    row strides that are multiples of 8 elements; C fp32 or bf16."""
+    assert A.dtype == torch.bfloat16 and B.dtype == torch.bfloat16 and A.stride(1) == 1 and B.stride(1) == 1
+    check(rt.lib.etr_gemm_bf16_tn(rt.ctx, M, N, K, A.data_ptr(), A.stride(0), B.data_ptr(), B.stride(0),
+                                  C_out.data_ptr(), C_out.stride(0), _TORCH2ETR[C_out.dtype], _p(bias), _lib.ACT[act],
+                                  rt.stream))
+
+
+def cast_bf16(rt: Runtime, src: torch.Tensor, transpose: bool = False, ld_dst: Optional[int] = None) -> torch.Tensor:
+    """fp32 [rows, cols] -> bf16 [rows, ld] (or [cols, ld] transposed), ld rounded up to 8, zero padded."""
+    assert src.dtype == torch.float32 and src.dim() == 2 and src.stride(1) == 1
+    rows, cols = src.shape
+    inner = rows if transpose else cols
+    ld = ld_dst or ((inner + 7) // 8 * 8)
+    dst = rt.empty((cols if transpose else rows, ld), torch.bfloat16)
+    check(rt.lib.etr_cast_bf16(rt.ctx, src.data_ptr(), rows, cols, src.stride(0), dst.data_ptr(), ld, int(transpose),
+                               rt.stream))
+    return dst
+
+
+def transpose_bf16(rt: Runtime, src: torch.Tensor, rows: int, cols: int) -> torch.Tensor:
+    """bf16 [rows, cols] (row stride src.stride(0)) -> bf16 [cols, ld], ld = rows rounded up to 8, zero padded."""
+    assert src.dtype == torch.bfloat16 and src.stride(1) == 1
+    ld = (rows + 7) // 8 * 8
+    dst = rt.empty((cols, ld), torch.bfloat16)
+    check(rt.lib.etr_transpose_bf16(rt.ctx, src.data_ptr(), rows, cols, src.stride(0), dst.data_ptr(), ld, rt.stream))
+    return dst

@@ -269,6 +269,28 @@ int etr_cross_vec_finish(etr_ctx* ctx, const float* d_XtC, const float* d_sums, 
 int etr_cross_mat_layer_f32(etr_ctx* ctx, const float* d_x0, const float* d_xl, int64_t ldx,
                             int64_t batch, int32_t D, const float* d_W /* [D,D] */, const float* d_b,
                             float* d_out, int64_t ldo, float* d_u, int64_t ldu, void* stream);
+/* bf16 tensor-core form of one cross-matrix layer (tcgen05.mma + TMA, fp32
+ * accumulate in TMEM, epilogue out = x0 (.) (acc + b) + xl fused).  x0, xl, out
+ * (and the optional u = xl W^T + b) are bf16 [batch, ld*] with ld % 8 == 0 and
+ * zero padding columns; d_W is the bf16 copy of W [D, D] (row-major, ldw % 8 == 0):
+ * y = W x means W itself is the [N,K] operand of X_l W^T (3.DCN/CustomLayers.py:301). */
+int etr_cross_mat_layer_bf16(etr_ctx* ctx, const void* d_x0, const void* d_xl, int64_t ldx,
+                             int64_t batch, int32_t D, const void* d_W, int64_t ldw, const float* d_b,
+                             void* d_out, int64_t ldo, void* d_u, int64_t ldu, void* stream);
+/* Generic bf16 tensor-core GEMM (tcgen05 + TMA): C[M,N] = act(A[M,K] B[N,K]^T + bias),
+ * A, B bf16 row-major with K contiguous (lda, ldb % 8 == 0), C fp32 or bf16.
+ * MLP layers (2.FM/CustomLayers.py:72-84), their dgrad, and -- with split-K over
+ * the batch, reduced in fixed order -- their wgrad.                           */
+int etr_gemm_bf16_tn(etr_ctx* ctx, int64_t M, int64_t N, int64_t K,
+                     const void* d_A, int64_t lda, const void* d_B, int64_t ldb,
+                     void* d_C, int64_t ldc, int32_t c_dtype, const float* d_bias, int32_t act,
+                     void* stream);
+/* fp32 [rows, cols] -> bf16 (optionally transposed) into a buffer with leading
+ * dim ld_dst whose padding columns are written as zeros; bf16 -> bf16 transpose. */
+int etr_cast_bf16(etr_ctx* ctx, const float* d_src, int64_t rows, int64_t cols, int64_t ld_src,
+                  void* d_dst, int64_t ld_dst, int32_t transpose, void* stream);
+int etr_transpose_bf16(etr_ctx* ctx, const void* d_src, int64_t rows, int64_t cols, int64_t ld_src,
+                       void* d_dst, int64_t ld_dst, void* stream);
 /* elementwise helpers of the cross-matrix backward:
  * du = g (.) x0 ; dx0 += g (.) u   (SURVEY a', cross-matrix).                 */
 int etr_cross_mat_bwd_elementwise(etr_ctx* ctx, const float* d_g, const float* d_x0, const float* d_u,

@@ -3,8 +3,10 @@
 mkdir -p gpurun_out
 nvidia-smi --query-gpu=name,driver_version,memory.total --format=csv > gpurun_out/gpu.txt 2>&1
 nproc >> gpurun_out/gpu.txt
-timeout 900 python -m pytest tests -m gpu -q --timeout 300 > gpurun_out/pytest_gpu.log 2>&1; echo "pytest exit $?" >> gpurun_out/pytest_gpu.log
+timeout 900 python -m pytest tests -m gpu -q --timeout 300 --ignore tests/test_gpu_tcgen05.py > gpurun_out/pytest_gpu.log 2>&1; echo "pytest exit $?" >> gpurun_out/pytest_gpu.log
 tail -5 gpurun_out/pytest_gpu.log
+timeout 240 python -m pytest tests/test_gpu_tcgen05.py -m gpu -q --timeout 60 > gpurun_out/pytest_tcgen05.log 2>&1; echo "pytest tcgen05 exit $?" >> gpurun_out/pytest_tcgen05.log
+tail -15 gpurun_out/pytest_tcgen05.log
 timeout 300 python -c "import __graft_entry__ as g; g.smoke()" > gpurun_out/smoke.log 2>&1; echo "smoke exit $?" >> gpurun_out/smoke.log
 tail -3 gpurun_out/smoke.log
 timeout 600 python bench.py > gpurun_out/bench.json 2> gpurun_out/bench.err; echo "bench exit $?"

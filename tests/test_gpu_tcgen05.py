@@ -1,0 +1,103 @@
+"""GPU numerics of the tcgen05 / TMA / TMEM bf16 GEMM and the fused DCN-matrix
+cross epilogue.  Reference = the same bf16-rounded operands multiplied in fp64
+(a floating-point kernel: tolerance is about accumulation order only), plus the
+CPU oracle for the cross layer within the bf16 tolerance (1e-2)."""
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+from oracle import reference_layers as R        # noqa: E402
+
+
+@pytest.fixture(scope="module")
+def rt():
+    from etr_b200 import Runtime
+    return Runtime.get()
+
+
+def _rand_bf16(rt, shape, ld, seed, scale=1.0):
+    g = torch.Generator(device=rt.device)
+    g.manual_seed(seed)
+    buf = torch.zeros((shape[0], ld), dtype=torch.bfloat16, device=rt.device)
+    buf[:, : shape[1]] = (torch.randn(shape, device=rt.device, generator=g) * scale).to(torch.bfloat16)
+    return buf
+
+
+@pytest.mark.parametrize("M,N,K", [(128, 32, 64), (128, 128, 128), (300, 32, 432), (1000, 240, 1680),
+                                    (257, 1677, 1677), (129, 64, 40), (4096, 500, 1000)])
+@pytest.mark.parametrize("out_dtype", [torch.float32, torch.bfloat16])
+def test_gemm_bf16_tn(rt, M, N, K, out_dtype):
+    from etr_b200.runtime import gemm_bf16_tn
+    ldk = (K + 7) // 8 * 8
+    A = _rand_bf16(rt, (M, K), ldk, 1)
+    B = _rand_bf16(rt, (N, K), ldk, 2)
+    bias = torch.randn(N, device=rt.device)
+    ldc = (N + 7) // 8 * 8
+    C = torch.full((M, ldc), 7.0, dtype=out_dtype, device=rt.device)
+    gemm_bf16_tn(rt, A, B, C, M, N, K, bias=bias, act="relu")
+    torch.cuda.synchronize()
+    ref = torch.relu(A[:, :K].double() @ B[:, :K].double().T + bias.double())
+    got = C[:, :N].double()
+    tol = 2e-3 if out_dtype == torch.float32 else 1e-2
+    err = (got - ref).abs().max().item()
+    assert err <= tol * max(1.0, ref.abs().max().item()), (err, ref.abs().max().item())
+    if ldc > N:
+        assert torch.all(C[:, N:] == 7.0)               # padding columns untouched
+
+
+def test_gemm_bf16_split_k_wgrad_shape(rt):
+    """wgrad of MLP layer 1: [432, B] x [B, 32] with K = batch -> split-K, fixed-order reduce."""
+    from etr_b200.runtime import gemm_bf16_tn
+    M, N, K = 432, 32, 65536
+    A = _rand_bf16(rt, (M, K), K, 3, scale=0.1)
+    B = _rand_bf16(rt, (N, K), K, 4, scale=0.1)
+    C = rt.empty((M, N))
+    gemm_bf16_tn(rt, A, B, C, M, N, K)
+    C2 = rt.empty((M, N))
+    gemm_bf16_tn(rt, A, B, C2, M, N, K)
+    ref = A.double() @ B.double().T
+    err = (C.double() - ref).abs().max().item()
+    assert err <= 2e-3 * ref.abs().max().item(), err
+    assert torch.equal(C, C2)                            # deterministic
+
+
+def test_cast_and_transpose_bf16(rt):
+    from etr_b200.runtime import cast_bf16, transpose_bf16
+    x = torch.randn(37, 13, device=rt.device)
+    a = cast_bf16(rt, x)
+    assert a.shape == (37, 16) and torch.equal(a[:, :13], x.to(torch.bfloat16)) and torch.all(a[:, 13:] == 0)
+    b = cast_bf16(rt, x, transpose=True)
+    assert b.shape == (13, 40) and torch.equal(b[:, :37], x.T.to(torch.bfloat16)) and torch.all(b[:, 37:] == 0)
+    c = transpose_bf16(rt, a, 37, 13)
+    assert torch.equal(c[:, :37], a[:, :13].T) and torch.all(c[:, 37:] == 0)
+
+
+@pytest.mark.parametrize("B,D", [(256, 163), (1000, 1677), (130, 64)])
+def test_cross_mat_layer_bf16(rt, B, D):
+    import ctypes as C
+    from etr_b200._lib import check
+    ld = (D + 7) // 8 * 8
+    x0 = _rand_bf16(rt, (B, D), ld, 5)
+    xl = _rand_bf16(rt, (B, D), ld, 6)
+    W = _rand_bf16(rt, (D, D), ld, 7, scale=0.05)
+    b = torch.randn(ld, device=rt.device) * 0.1
+    b[D:] = 0
+    out = torch.zeros((B, ld), dtype=torch.bfloat16, device=rt.device)
+    u = torch.zeros((B, ld), dtype=torch.bfloat16, device=rt.device)
+    check(rt.lib.etr_cross_mat_layer_bf16(rt.ctx, x0.data_ptr(), xl.data_ptr(), ld, B, D, W.data_ptr(), ld,
+                                          b.data_ptr(), out.data_ptr(), ld, u.data_ptr(), ld, rt.stream))
+    torch.cuda.synchronize()
+    x0d, xld, Wd, bd = x0[:, :D].double().cpu(), xl[:, :D].double().cpu(), W[:, :D].double().cpu(), b[:D].double().cpu()
+    # one layer of the oracle's matrix cross with xl as the running state: x0*(W xl + b) + xl
+    ref_u = xld @ Wd.T + bd
+    ref = x0d * ref_u + xld
+    assert (u[:, :D].double().cpu() - ref_u).abs().max().item() <= 1e-2 * max(1.0, ref_u.abs().max().item())
+    assert (out[:, :D].double().cpu() - ref).abs().max().item() <= 1e-2 * max(1.0, ref.abs().max().item())
+    # and it is the reference formula (KAT-4 orientation): matches R.matrix_cross_layer for a single layer from x0 == xl
+    ref1 = R.matrix_cross_layer(x0d, [Wd], [bd.reshape(-1, 1)])
+    out1 = torch.zeros_like(out)
+    check(rt.lib.etr_cross_mat_layer_bf16(rt.ctx, x0.data_ptr(), x0.data_ptr(), ld, B, D, W.data_ptr(), ld,
+                                          b.data_ptr(), out1.data_ptr(), ld, None, 0, rt.stream))
+    assert (out1[:, :D].double().cpu() - ref1).abs().max().item() <= 1e-2 * max(1.0, ref1.abs().max().item())

@@ -107,8 +107,12 @@ def oracle_dcn(layer, dtype=torch.float64):
 
 
 def table_slices(grads, width=None):
+    """(ids, rows) of the deduplicated table gradient; rows that are exactly zero
+    are dropped (the oracle's dense autograd gradient cannot tell them from
+    untouched rows)."""
     ids, rows = grads[0].indexed_slices()
     rows = rows.cpu().numpy()
     if width is not None:
         rows = rows[:, :width]
-    return ids.cpu().numpy(), rows
+    keep = np.abs(rows).sum(1) > 0
+    return ids.cpu().numpy()[keep], rows[keep]
