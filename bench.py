@@ -171,7 +171,9 @@ def workload_config(args, B, graph):
     return {"workload": "c2: DeepFM train step (fwd+bwd+Adam), Criteo shape: 13 dense + 26 sparse, one shared "
                         "33 762 577-row table, k=16, MLP [429->32->8->1]",
             "global_batch": B * max(args.gpus, 1), "per_gpu_batch": B, "table_rows": int(sum(CRITEO_CARDS)),
-            "embedding_dims": K_EMB, "table_dtype": "f32", "mlp": "fp32 SIMT", "id_distribution": args.dist,
+            "embedding_dims": K_EMB, "table_dtype": "f32",
+            "mlp": ("layer 1 on tcgen05 (bf16 operands, fp32 accumulate), tail layers fp32" if getattr(args, "mlp", "bf16") == "bf16"
+                    else "fp32 SIMT"), "id_distribution": args.dist,
             "apply_mode": "rowwise Adam", "parallelism": f"dp{max(args.gpus, 1)}",
             "l2": "L2 flushed (512 MiB write) before every timed step", "cuda_graph": graph}
 
@@ -185,6 +187,8 @@ def main():
     ap.add_argument("--dist", default="zipf", choices=["zipf", "uniform"])
     ap.add_argument("--batch", type=int, default=BATCH)
     ap.add_argument("--no-graph", action="store_true")
+    ap.add_argument("--mlp", default="bf16", choices=["bf16", "fp32"],
+                    help="first MLP layer: bf16 tcgen05 tensor cores (fp32 accumulate) or the fp32 SIMT exact-parity path")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-budget", type=float, default=12.0)
     args = ap.parse_args()
@@ -212,7 +216,7 @@ def main():
     # Replicas only at N>1 for this config: each rank owns a full copy of
     # the table and its own batch; the row-sharded path is the c5 config.
     layer = L.DeepFMRankingLayer(names, feature_dims=V, embedding_dims=K_EMB, continuous_features=cont,
-                                 seed=1 + rank, check_ids=False)
+                                 seed=1 + rank, check_ids=False, mlp_precision=args.mlp)
     rt = layer.rt
     n_batches = 6
     host = make_batches(n_batches, B, args.dist, seed=SEED + 17 * rank)
@@ -303,7 +307,9 @@ def main():
 
     # ---- roofline of the fused gather + FM kernel, timed alone, L2 flushed
     ids0 = IdsBatch(rt, dev_batches[0][0], B, F, 1, 1, B, 1)
-    x = rt.empty((B, C_DENSE + F * K_EMB))
+    col0 = layer.front_pad + C_DENSE
+    x = rt.empty((B, col0 + F * K_EMB), torch.bfloat16 if args.mlp == "bf16" else torch.float32)
+    xc_dev = dev_batches[0][1].t()
     logit = rt.empty((B,))
     kt = []
     for i in range(max(args.steps, 10)):
@@ -311,7 +317,8 @@ def main():
         flush.zero_()
         a, b_ = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         a.record()
-        gather_fm_forward(layer.table, K_EMB, True, ids_i, bias=layer.bias, logit=logit, flat=x, flat_col0=C_DENSE)
+        gather_fm_forward(layer.table, K_EMB, True, ids_i, bias=layer.bias, logit=logit, flat=x, flat_col0=col0,
+                          cont=xc_dev)
         b_.record()
         kt.append((a, b_))
     torch.cuda.synchronize(dev)
@@ -319,7 +326,7 @@ def main():
     peak, peak_src = load_peaks()
     # algorithmic bytes per sample: F*(k*4 + 4 [w] + 8 [id]) + 4 [logit]  (+ F*k*4 flat written for the MLP)
     alg_fm = F * (K_EMB * 4 + 4 + 8) + 4
-    alg_flat = F * K_EMB * 4
+    alg_flat = F * K_EMB * (2 if args.mlp == "bf16" else 4)
     achieved = (alg_fm + alg_flat) * B / (k_ms * 1e-3) / 1e9
     del ids0
 
@@ -341,7 +348,9 @@ def main():
     line = {
         "metric": "train samples/sec DeepFM (Criteo-shape)", "value": value, "unit": "samples/s",
         "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": total_ms / args.steps,
-        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f32 (tables, FM terms, Adam)" + (" + bf16 tensor-core MLP layer 1" if args.mlp == "bf16" else ""),
+        "data": "synthetic",
         "config": workload_config(args, B, use_graph),
         "clocks": clk,
         "e2e": {"value": e2e_value, "unit": "samples/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
@@ -352,8 +361,9 @@ def main():
                      "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                      "traffic": None, "peak_source": peak_src, "kernel_ms": k_ms,
                      "algorithmic_bytes_per_launch": (alg_fm + alg_flat) * B,
-                     "note": "algorithmic bytes = B*(F*(4k+4+8)+4) FM terms + B*F*k*4 flattened operand written "
-                             "for the MLP; timed alone with CUDA events, L2 flushed before each launch"},
+                     "note": "algorithmic bytes = B*(F*(4k+4+8)+4) FM terms + B*F*k*osize flattened operand written "
+                             "for the MLP (osize 2 for the bf16 tensor-core MLP, 4 for fp32); timed alone with CUDA "
+                             "events, L2 flushed before each launch"},
         "step_ms_min_median_max": [min(step_ms), statistics.median(step_ms), max(step_ms)],
     }
     if cpu:

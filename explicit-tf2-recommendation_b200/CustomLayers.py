@@ -196,17 +196,22 @@ class DeepFMRankingLayer(FMRankingLayer):
     for the MLP only, as 3.DCN/CustomLayers.py:259 does."""
 
     def __init__(self, feature_names=['user_tag0', 'user_tag1', 'item_tag1', 'item_tag2', 'item_tag3'],
-                 feature_dims=20, embedding_dims=16, mlp_dims=[32, 8], continuous_features=(), **kwargs):
+                 feature_dims=20, embedding_dims=16, mlp_dims=[32, 8], continuous_features=(),
+                 mlp_precision="fp32", **kwargs):
         self.mlp_dims = list(mlp_dims)
         self.continuous_features = list(continuous_features)
+        # "bf16": the wide first MLP layer runs on the tensor cores (bf16 operands, fp32 accumulate;
+        # parity 1e-2); "fp32": exact-parity SIMT path (1e-5)
+        self.mlp_precision = mlp_precision
         super().__init__(feature_names, feature_dims, embedding_dims, **kwargs)
 
     def _build_extra(self):
         C_ = len(self.continuous_features)
         in_dim = C_ + len(self.feature_names) * self.embedding_dims
         # front padding so that Flatten(emb) starts on a 16-byte boundary behind [pad | X_cont]
-        self.front_pad = (-C_) % 4
-        self.MLP_layer1 = MLPLayer(units=self.mlp_dims, activation="relu", name="MLP_layer1")
+        self.front_pad = (-C_) % (8 if self.mlp_precision == "bf16" else 4)
+        self.MLP_layer1 = MLPLayer(units=self.mlp_dims, activation="relu", name="MLP_layer1",
+                                   precision=self.mlp_precision)
         self.MLP_layer2 = MLPLayer(units=[1], name="MLP_layer2")
         self.MLP_layer1.build(in_dim, self.params, self.gen, front_pad=self.front_pad)
         self.MLP_layer2.build(self.mlp_dims[-1], self.params, self.gen)
@@ -225,7 +230,8 @@ class DeepFMRankingLayer(FMRankingLayer):
         C_ = len(self.continuous_features)
         k, F = self.embedding_dims, len(self.feature_names)
         col0 = self.front_pad + C_
-        x = rt.empty((ids.B, col0 + F * k))                  # [pad | X_cont | Flatten(emb)]
+        x = rt.empty((ids.B, col0 + F * k),                  # [pad | X_cont | Flatten(emb)]
+                     torch.bfloat16 if self.mlp_precision == "bf16" else torch.float32)
         cont = self._cont(inputs, self.continuous_features) if C_ else None
         fm_logit = rt.empty((ids.B,))
         gather_fm_forward(self.table, k, True, ids, bias=self.bias, logit=fm_logit, flat=x, flat_col0=col0, cont=cont)

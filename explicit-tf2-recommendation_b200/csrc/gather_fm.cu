@@ -454,6 +454,204 @@ __global__ void __launch_bounds__(256) gather_fm_bwd_kernel(const GatherParams p
   }
 }
 
+// ================================================================ tiled single-hot kernels
+// The common case (single-hot ids, row <= 32 chunks).  A CTA works on tiles of
+// SPB = 8 warps * (32/LPR) samples.  The ids of the NEXT tile are brought into
+// shared memory with cp.async while the rows of the current tile are being
+// fetched, so a lane's row loads never wait on an id load (the id -> row
+// dependent-load chain is what bounds the simple kernel), and the register
+// budget is capped so that 3 CTAs (24 warps) stay resident per SM.
+__device__ __forceinline__ void cp_async8(void* smem_dst, const void* gsrc) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"((unsigned)__cvta_generic_to_shared(smem_dst)), "l"(gsrc)
+               : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
+
+template <int SPB>
+__device__ __forceinline__ void stage_ids_tile(const GatherParams& p, long long tile, long long* dst) {
+  const long long b0 = tile * SPB;
+  const int total = SPB * p.F;
+  const bool field_major = (p.sb == 1);
+  for (int e = threadIdx.x; e < total; e += blockDim.x) {
+    int sl, f;
+    if (field_major) { sl = e % SPB; f = e / SPB; } else { f = e % p.F; sl = e / p.F; }
+    const long long b = b0 + sl;
+    if (b < p.B) cp_async8(dst + sl * p.F + f, p.ids + b * p.sb + (long long)f * p.sf);
+  }
+}
+
+template <typename Elem, int LPR>
+__global__ void __launch_bounds__(256, 3) gather_fm_fwd_tile_kernel(const GatherParams p) {
+  constexpr int VEC = Chunk<Elem>::kElems;
+  constexpr int U = (VEC >= 8) ? 4 : 8;
+  constexpr int GPW = 32 / LPR;
+  constexpr int SPB = 8 * GPW;
+  extern __shared__ __align__(16) long long ids_s[];          // [2][SPB * F]
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int gl = lane % LPR, g = lane / LPR;
+  const int sl = warp * GPW + g;
+  const long long ntiles = (p.B + SPB - 1) / SPB;
+  const bool want_fm = (p.logit != nullptr) || (p.prob != nullptr) || (p.sumv != nullptr);
+  const int c = gl;
+  const bool has_chunk = c < p.nchunks;
+  int buf = 0;
+  long long tile = blockIdx.x;
+  if (tile < ntiles) stage_ids_tile<SPB>(p, tile, ids_s);
+  cp_async_commit();
+  cp_async_wait_all();
+  __syncthreads();
+  for (; tile < ntiles; tile += gridDim.x) {
+    const long long next = tile + gridDim.x;
+    if (next < ntiles) stage_ids_tile<SPB>(p, next, ids_s + (buf ^ 1) * SPB * p.F);
+    cp_async_commit();
+
+    const long long b = tile * SPB + sl;
+    const bool active = b < p.B;
+    const long long* my = ids_s + buf * SPB * p.F + sl * p.F;
+    float S[VEC], Q[VEC];
+#pragma unroll
+    for (int i = 0; i < VEC; ++i) S[i] = Q[i] = 0.f;
+    if (p.fill_front && active) {
+      const int z = p.flat_col0 - p.cont_n;
+      for (int j = gl; j < p.flat_col0; j += LPR) {
+        const float v = (j < z) ? 0.f : p.cont[b * p.cont_sb + (long long)(j - z) * p.cont_sc];
+        if (p.flat_bf16) reinterpret_cast<__nv_bfloat16*>(p.flat)[b * p.flat_ld + j] = __float2bfloat16_rn(v);
+        else reinterpret_cast<float*>(p.flat)[b * p.flat_ld + j] = v;
+      }
+    }
+    for (int f0 = 0; f0 < p.F; f0 += U) {
+      Chunk<Elem> r[U];
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        bool ok = active && (f0 + u) < p.F;
+        long long id = ok ? my[f0 + u] : 0;
+        ok = ok && !(p.has_pad && id == p.pad);
+        if (ok && (unsigned long long)id >= (unsigned long long)p.rows) { flag_bad_id(p.err, id); ok = false; }
+        if (ok && has_chunk) r[u].load(p.table + id * (long long)p.row_bytes + c * 16);
+        else r[u].zero();
+      }
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        if (f0 + u < p.F) {
+#pragma unroll
+          for (int i = 0; i < VEC; ++i) {
+            const float x = r[u].v[i];
+            S[i] += x;
+            Q[i] += x * x;
+          }
+          if (p.flat && active) store_flat<Elem>(p, b, f0 + u, c * VEC, r[u].v);
+        }
+      }
+    }
+    if (want_fm) {
+      float second = 0.f, first = 0.f;
+#pragma unroll
+      for (int i = 0; i < VEC; ++i) {
+        const int col = c * VEC + i;
+        if (col < p.k) {
+          second += S[i] * S[i] - Q[i];
+          if (p.sumv && active) p.sumv[b * p.k + col] = S[i];
+        } else if (col == p.k && p.has_w) {
+          first = S[i];
+        }
+      }
+      second = group_sum<LPR>(second);
+      first = group_sum<LPR>(first);
+      if (gl == 0 && active) {
+        const float z = ((p.bias ? p.bias[0] : 0.f) + first) + 0.5f * second;
+        if (p.logit) p.logit[b] = z;
+        if (p.prob) p.prob[b] = sigmoidf_exact(z);
+      }
+    }
+    cp_async_wait_all();
+    __syncthreads();
+    buf ^= 1;
+  }
+}
+
+template <typename Elem, int LPR>
+__global__ void __launch_bounds__(256, 3) gather_fm_bwd_tile_kernel(const GatherParams p) {
+  constexpr int VEC = Chunk<Elem>::kElems;
+  constexpr int U = (VEC >= 8) ? 4 : 8;
+  constexpr int GPW = 32 / LPR;
+  constexpr int SPB = 8 * GPW;
+  extern __shared__ __align__(16) long long ids_s[];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int gl = lane % LPR, g = lane / LPR;
+  const int sl = warp * GPW + g;
+  const long long ntiles = (p.B + SPB - 1) / SPB;
+  const bool need_rows = p.dlogit != nullptr;
+  const int c = gl;
+  const bool has_chunk = c < p.nchunks;
+  int buf = 0;
+  long long tile = blockIdx.x;
+  if (need_rows) {
+    if (tile < ntiles) stage_ids_tile<SPB>(p, tile, ids_s);
+    cp_async_commit();
+    cp_async_wait_all();
+    __syncthreads();
+  }
+  for (; tile < ntiles; tile += gridDim.x) {
+    if (need_rows) {
+      const long long next = tile + gridDim.x;
+      if (next < ntiles) stage_ids_tile<SPB>(p, next, ids_s + (buf ^ 1) * SPB * p.F);
+      cp_async_commit();
+    }
+    const long long b = tile * SPB + sl;
+    const bool active = b < p.B;
+    const long long* my = ids_s + buf * SPB * p.F + sl * p.F;
+    float S[1][VEC];
+#pragma unroll
+    for (int i = 0; i < VEC; ++i) S[0][i] = 0.f;
+    const float dl = (need_rows && active) ? p.dlogit[b] : 0.f;
+    if (need_rows) {
+      for (int f0 = 0; f0 < p.F; f0 += U) {
+        Chunk<Elem> r[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+          bool ok = active && (f0 + u) < p.F;
+          const long long id = ok ? my[f0 + u] : 0;
+          ok = ok && !(p.has_pad && id == p.pad) && (unsigned long long)id < (unsigned long long)p.rows;
+          if (ok && has_chunk) r[u].load(p.table + id * (long long)p.row_bytes + c * 16);
+          else r[u].zero();
+        }
+#pragma unroll
+        for (int u = 0; u < U; ++u)
+#pragma unroll
+          for (int i = 0; i < VEC; ++i) S[0][i] += r[u].v[i];
+      }
+    }
+    for (int f0 = 0; f0 < p.F; f0 += U) {
+      Chunk<Elem> r[U];
+      if (need_rows) {
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+          bool ok = active && (f0 + u) < p.F;
+          const long long id = ok ? my[f0 + u] : 0;
+          ok = ok && !(p.has_pad && id == p.pad) && (unsigned long long)id < (unsigned long long)p.rows;
+          if (ok && has_chunk) r[u].load(p.table + id * (long long)p.row_bytes + c * 16);   // L2 hits now
+          else r[u].zero();
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        if (active && f0 + u < p.F) {
+          float e[1][VEC];
+#pragma unroll
+          for (int i = 0; i < VEC; ++i) e[0][i] = need_rows ? r[u].v[i] : 0.f;
+          emit_bag_grad<Elem, 1>(p, b, f0 + u, gl, LPR, S, e, dl, 1.0f, need_rows);
+        }
+      }
+    }
+    if (need_rows) {
+      cp_async_wait_all();
+      __syncthreads();
+      buf ^= 1;
+    }
+  }
+}
+
 // ------------------------------------------------------------ row dump
 template <typename Elem>
 __global__ void __launch_bounds__(256) embedding_gather_kernel(const char* table, long long rows, int row_bytes,
@@ -548,6 +746,34 @@ static int launch_gather(etr_ctx* ctx, const GatherParams& p, bool bag, cudaStre
   }
   const int gpw = 32 / lpr;
   const int threads = 256;
+  // tiled single-hot kernels: ids double-buffered in shared memory
+  const size_t tile_smem = 2 * (size_t)(8 * gpw) * p.F * sizeof(long long);
+  if (!bag && cpl == 1 && tile_smem <= 64 * 1024) {
+    const int tgrid = grid_for(p.B, 8 * gpw, ctx->sm_count, 3);
+#define ETR_TILE(LPR)                                                                                   \
+  do {                                                                                                  \
+    if (BWD) {                                                                                          \
+      if (tile_smem > 48 * 1024)                                                                        \
+        cudaFuncSetAttribute(gather_fm_bwd_tile_kernel<Elem, LPR>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tile_smem); \
+      gather_fm_bwd_tile_kernel<Elem, LPR><<<tgrid, threads, tile_smem, s>>>(p);                        \
+    } else {                                                                                            \
+      if (tile_smem > 48 * 1024)                                                                        \
+        cudaFuncSetAttribute(gather_fm_fwd_tile_kernel<Elem, LPR>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tile_smem); \
+      gather_fm_fwd_tile_kernel<Elem, LPR><<<tgrid, threads, tile_smem, s>>>(p);                        \
+    }                                                                                                   \
+  } while (0)
+    switch (lpr) {
+      case 1: ETR_TILE(1); break;
+      case 2: ETR_TILE(2); break;
+      case 4: ETR_TILE(4); break;
+      case 8: ETR_TILE(8); break;
+      case 16: ETR_TILE(16); break;
+      default: ETR_TILE(32); break;
+    }
+#undef ETR_TILE
+    ETR_LAUNCH_CHECK(ctx);
+    return ETR_OK;
+  }
   const int grid = grid_for(p.B, (threads / 32) * gpw, ctx->sm_count, 8);
 #define ETR_LAUNCH(LPR, CPL)                                                              \
   do {                                                                                    \

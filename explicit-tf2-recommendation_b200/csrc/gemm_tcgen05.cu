@@ -223,7 +223,8 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
         for (int i = 0; i < 32; ++i) v[i] = 0u;
       }
       if (!row_ok) continue;
-      const int ncol = (ep.N - col0) < 32 ? (int)(ep.N - col0) : 32;
+      int ncol = (ep.N - col0) < 32 ? (int)(ep.N - col0) : 32;
+      if (ncol > BLOCK_N - c0) ncol = BLOCK_N - c0;     // BLOCK_N = 240: the last chunk is 16 columns wide
       if (ep.mode == EPI_PARTIAL) {
         float* dst = ep.partial + ((long long)split * ep.M + row) * ep.N + col0;
 #pragma unroll

@@ -13,7 +13,7 @@ import torch
 
 from . import _lib
 from ._lib import check
-from .runtime import Runtime, gemm_f32, _p
+from .runtime import Runtime, cast_bf16, gemm_bf16_tn, gemm_f32, transpose_bf16, _p
 
 
 class DenseParams:
@@ -118,8 +118,12 @@ class MLPLayer:
     ``is_train`` flag Keras never passes (:72,82) so it is never active in the
     reference either and is ignored here."""
 
+    # layers whose input is at least this wide run on the tensor cores when precision == "bf16"
+    TC_MIN_IN = 64
+
     def __init__(self, units, activation=None, use_bias=True, is_batch_norm=False, is_dropput=0,
-                 kernel_initializer="glorot_uniform", bias_initializer="zeros", name="mlp", **kwargs):
+                 kernel_initializer="glorot_uniform", bias_initializer="zeros", name="mlp", precision="fp32",
+                 **kwargs):
         self.units = [units] if not isinstance(units, list) else list(units)
         if len(self.units) <= 0:
             raise ValueError(f"Received an invalid value for `units`, expected a positive integer, got {units}.")
@@ -130,6 +134,8 @@ class MLPLayer:
         self.activation, self.use_bias, self.is_dropout = activation, use_bias, is_dropput
         self.kernel_initializer, self.bias_initializer = kernel_initializer, bias_initializer
         self.name = name
+        assert precision in ("fp32", "bf16")
+        self.precision = precision      # "bf16": wide layers use tcgen05 (bf16 operands, fp32 accumulate)
         self.params: Optional[DenseParams] = None
         self.in_dim: Optional[int] = None
         self._saved = None
@@ -169,20 +175,32 @@ class MLPLayer:
             self.params.finalize()
             self._owns_params = True
         rt = self.params.rt
-        x = rt.to_device(inputs, torch.float32)
+        x = inputs if (isinstance(inputs, torch.Tensor) and inputs.dtype == torch.bfloat16 and
+                       inputs.device == rt.device) else rt.to_device(inputs, torch.float32)
         assert x.dim() == 2 and x.shape[1] == self.front_pad + self.in_dim and x.stride(1) == 1
         acts = [x]
         for i, n_out in enumerate(self.units):
             k = self.params.full(f"{self.name}/kernel_{i}")
             b = self.params[f"{self.name}/bias_{i}"] if self.use_bias else None
             y = rt.empty((x.shape[0], n_out))
-            gemm_f32(rt, x, k, y, x.shape[0], n_out, x.shape[1], x.stride(0), n_out, n_out, bias=b,
-                     act=self.activation)
+            if self._tc(i, x):
+                # tensor cores: Y = X K  ==  X [B,in] x (K^T)[out,in]^T ; K^T is a small bf16 copy made per call
+                xb = x if x.dtype == torch.bfloat16 else cast_bf16(rt, x)
+                acts[i] = xb
+                kt = cast_bf16(rt, k, transpose=True)
+                gemm_bf16_tn(rt, xb, kt, y, x.shape[0], n_out, x.shape[1], bias=b, act=self.activation)
+            else:
+                assert x.dtype == torch.float32
+                gemm_f32(rt, x, k, y, x.shape[0], n_out, x.shape[1], x.stride(0), n_out, n_out, bias=b,
+                         act=self.activation)
             acts.append(y)
             x = y
         if training:
             self._saved = acts
         return x
+
+    def _tc(self, i: int, x: torch.Tensor) -> bool:
+        return self.precision == "bf16" and x.shape[1] >= self.TC_MIN_IN and x.stride(0) % 8 == 0
 
     def backward(self, dy: torch.Tensor, need_input_grad: bool = True, dy_is_preact: bool = False,
                  accumulate_into: Optional[torch.Tensor] = None) -> Optional[torch.Tensor]:
@@ -203,18 +221,32 @@ class MLPLayer:
                 check(rt.lib.etr_act_backward(rt.ctx, d.data_ptr(), y.data_ptr(), d.numel(),
                                               _lib.ACT[self.activation], rt.stream))
             gk = self.params.gfull(f"{self.name}/kernel_{i}")
-            # dK = x^T d : A stored [K=B, M=n_in] -> trans_a
-            gemm_f32(rt, x, d, gk, n_in, n_out, B, x.stride(0), n_out, n_out, trans_a=True)
+            tc = x.dtype == torch.bfloat16
+            if tc:
+                # dK = X^T d : [in,B] x [B,out]  ->  A = X^T (bf16 transpose), B operand = d^T; split-K over the batch
+                xt = transpose_bf16(rt, x, B, n_in)
+                dt = cast_bf16(rt, d, transpose=True)
+                gemm_bf16_tn(rt, xt, dt, gk, n_in, n_out, B)
+            else:
+                # dK = x^T d : A stored [K=B, M=n_in] -> trans_a
+                gemm_f32(rt, x, d, gk, n_in, n_out, B, x.stride(0), n_out, n_out, trans_a=True)
             if self.use_bias:
                 gb = self.params.g(f"{self.name}/bias_{i}")
                 check(rt.lib.etr_colsum_f32(rt.ctx, d.data_ptr(), B, n_out, n_out, gb.data_ptr(), rt.stream))
             if i > 0 or need_input_grad:
                 k = self.params.full(f"{self.name}/kernel_{i}")
                 acc = accumulate_into if (i == 0 and accumulate_into is not None) else None
-                dx = acc if acc is not None else rt.empty((B, n_in))
-                # dx = d K^T : B(k,n) = K[n,k] -> trans_b
-                gemm_f32(rt, d, k, dx, B, n_in, n_out, n_out, n_out, dx.stride(0), trans_b=True,
-                         beta=1.0 if acc is not None else 0.0)
+                if tc and acc is None:
+                    # dx = d K^T : A = d (bf16) [B,out], B operand = K [in,out] as stored; bf16 result
+                    db_ = cast_bf16(rt, d)
+                    kb = cast_bf16(rt, k)
+                    dx = rt.empty((B, n_in), torch.bfloat16)
+                    gemm_bf16_tn(rt, db_, kb, dx, B, n_in, n_out)
+                else:
+                    dx = acc if acc is not None else rt.empty((B, n_in))
+                    # dx = d K^T : B(k,n) = K[n,k] -> trans_b
+                    gemm_f32(rt, d, k, dx, B, n_in, n_out, n_out, n_out, dx.stride(0), trans_b=True,
+                             beta=1.0 if acc is not None else 0.0)
                 d = dx
             else:
                 d = None
