@@ -241,7 +241,7 @@ def main():
 
     # ---- warm-up (also captures the graph)
     try:
-        for i in range(args.warmup):
+        for i in range(max(args.warmup, 8 if use_graph else 0)):      # 2 buffer sets x (2 eager + capture) first
             b = stage_from_device(i)
             trainer.train_step(b)
         torch.cuda.synchronize(dev)
@@ -288,10 +288,22 @@ def main():
     t_wall0 = time.perf_counter()
     e0.record()
     last = 0.0
-    for i in range(args.steps):
-        d, y = pinned[(args.warmup + i) % n_batches]
-        loss = trainer.train_step(d, y) if use_graph else trainer._eager_step(d, y)
-        last = float(loss.item())                       # D2H read of the step's result
+    if use_graph:
+        # pipelined: H2D of step i+1 (copy stream) overlaps the compute of step i; the loss of
+        # every step is read back on the host (one step late, through pinned memory)
+        handle = None
+        for i in range(args.steps):
+            d, y = pinned[(args.warmup + i) % n_batches]
+            h = trainer.train_step_async(d, y)
+            if handle is not None:
+                last = handle.result()                  # D2H read of the previous step's result
+            handle = h
+        last = handle.result()
+    else:
+        for i in range(args.steps):
+            d, y = pinned[(args.warmup + i) % n_batches]
+            loss = trainer._eager_step(d, y)
+            last = float(loss.item())                   # D2H read of the step's result
     e1.record()
     barrier()
     e2e_ms = max(e0.elapsed_time(e1), 1e3 * (time.perf_counter() - t_wall0))

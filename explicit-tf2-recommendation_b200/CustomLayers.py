@@ -811,7 +811,9 @@ class Trainer:
         self.state = self.rt.zeros((2,))            # [iterations, lr_t] on the device
         self.last_grads: List[SparseGrad] = []
         self.use_graph = graph
-        self._graphs: Dict[tuple, tuple] = {}
+        self.depth = 2 if graph else 1
+        self._graphs: Dict[tuple, list] = {}
+        self._copy_stream = self._d2h_stream = None
 
     @property
     def iterations(self) -> int:                     # synchronises
@@ -828,11 +830,17 @@ class Trainer:
         rt = self.rt
         if labels is None and isinstance(inputs, DeviceBatch):
             labels = inputs.labels
+        sl = getattr(inputs, "_slot", None)
+        if sl is not None and not torch.cuda.is_current_stream_capturing():
+            torch.cuda.current_stream(rt.device).wait_event(sl.copy_done)     # staged on the copy stream
         out = self.layer(inputs, training=True)["output"]
         y = rt.to_device(labels, torch.float32).reshape(-1)
         loss, dlogit = bce_forward_backward(rt, out.reshape(-1), y)
         grads = self.layer.backward(dlogit)
         self.apply_gradients(grads)
+        if sl is not None and not torch.cuda.is_current_stream_capturing():
+            sl.used = True
+            sl.compute_done.record(torch.cuda.current_stream(rt.device))
         return loss
 
     def apply_gradients(self, grads: List[SparseGrad]) -> None:
@@ -854,50 +862,122 @@ class Trainer:
         self.last_grads = grads
 
     # ----------------------------------------------------------- graph step
+    # Pipelined: ``depth`` sets of static input buffers, each with its own captured
+    # graph.  Host columns are copied on a dedicated copy stream (H2D of step i+1
+    # overlaps the compute of step i); the loss is read back on a third stream into
+    # pinned memory so that reading step i's loss never waits for step i+1.
+    class _Slot:
+        def __init__(self):
+            self.batch = self.ids_buf = self.cont_buf = self.lab_buf = None
+            self.graph = self.loss = None
+            self.eager_steps = 0
+            self.copy_done = torch.cuda.Event()
+            self.compute_done = torch.cuda.Event()
+            self.used = False
+            self.host_loss = torch.zeros(1, dtype=torch.float32).pin_memory()
+            self.loss_ready = torch.cuda.Event()
+
+    class LossHandle:
+        """Result of ``train_step_async``: ``result()`` waits for that step's loss only."""
+
+        def __init__(self, slot):
+            self._slot, self._value = slot, None
+
+        def result(self) -> float:
+            if self._value is None:
+                self._slot.loss_ready.synchronize()
+                self._value = float(self._slot.host_loss[0])
+            return self._value
+
+    def _slots_for(self, B: int):
+        lay, rt = self.layer, self.rt
+        key = (B,)
+        if key not in self._graphs:
+            names = getattr(lay, "feature_names", None) or lay.categorical_features
+            cont_names = list(getattr(lay, "continuous_features", []))
+            slots = []
+            for _ in range(self.depth):
+                sl = Trainer._Slot()
+                sl.ids_buf = rt.empty((len(names), B), torch.int64)
+                sl.cont_buf = rt.empty((max(len(cont_names), 1), B), torch.float32)
+                sl.lab_buf = rt.empty((B,), torch.float32)
+                ids = IdsBatch(rt, sl.ids_buf, B, len(names), 1, 1, B, 1, lay.pad_id, lay.pooling)
+                sl.batch = DeviceBatch(ids, sl.cont_buf[: len(cont_names)].t() if cont_names else None, sl.lab_buf)
+                sl.batch._slot = sl
+                slots.append(sl)
+            self._graphs[key] = [slots, 0]
+        return self._graphs[key]
+
     def stage(self, inputs, labels) -> DeviceBatch:
-        """Copy one step's host (or device) inputs into the static buffers."""
+        """Copy one step's host (or device) inputs into the next set of static buffers
+        (asynchronously, on the copy stream)."""
         lay, rt = self.layer, self.rt
         names = getattr(lay, "feature_names", None) or lay.categorical_features
         cont_names = list(getattr(lay, "continuous_features", []))
         B = int(inputs[names[0]].shape[0])
-        key = (B,)
-        if key not in self._graphs:
-            ids_buf = rt.empty((len(names), B), torch.int64)
-            cont_buf = rt.empty((max(len(cont_names), 1), B), torch.float32)
-            lab_buf = rt.empty((B,), torch.float32)
-            ids = IdsBatch(rt, ids_buf, B, len(names), 1, 1, B, 1, lay.pad_id, lay.pooling)
-            batch = DeviceBatch(ids, cont_buf[: len(cont_names)].t() if cont_names else None, lab_buf)
-            self._graphs[key] = [batch, ids_buf, cont_buf, lab_buf, None, None]
-        batch, ids_buf, cont_buf, lab_buf = self._graphs[key][:4]
-        for f, n in enumerate(names):
-            ids_buf[f].copy_(torch.as_tensor(inputs[n]).reshape(-1), non_blocking=True)
-        for c, n in enumerate(cont_names):
-            cont_buf[c].copy_(torch.as_tensor(inputs[n]).reshape(-1), non_blocking=True)
-        lab_buf.copy_(torch.as_tensor(labels).reshape(-1), non_blocking=True)
-        return batch
+        entry = self._slots_for(B)
+        slots, nxt = entry
+        sl = slots[nxt % self.depth]
+        entry[1] = nxt + 1
+        if self._copy_stream is None:
+            self._copy_stream = torch.cuda.Stream(device=rt.device)
+            self._d2h_stream = torch.cuda.Stream(device=rt.device)
+        cur = torch.cuda.current_stream(rt.device)
+        cols = [inputs[n] for n in names] + [inputs[n] for n in cont_names] + [labels]
+        if any(isinstance(c, torch.Tensor) and c.is_cuda for c in cols):
+            self._copy_stream.wait_stream(cur)            # device-resident inputs: order after their producer
+        with torch.cuda.stream(self._copy_stream):
+            if sl.used:
+                self._copy_stream.wait_event(sl.compute_done)      # the buffers' previous consumer has finished
+            for f, n in enumerate(names):
+                sl.ids_buf[f].copy_(torch.as_tensor(inputs[n]).reshape(-1), non_blocking=True)
+            for c, n in enumerate(cont_names):
+                sl.cont_buf[c].copy_(torch.as_tensor(inputs[n]).reshape(-1), non_blocking=True)
+            sl.lab_buf.copy_(torch.as_tensor(labels).reshape(-1), non_blocking=True)
+            sl.copy_done.record(self._copy_stream)
+        return sl.batch
 
     def _graph_step(self, inputs, labels) -> torch.Tensor:
-        """Calls 1-2 at a new batch size run eagerly on the static buffers (they are
-        real training steps and size the workspace); call 3 captures the step into a
-        CUDA graph; from then on every call is one graph replay."""
+        """Per buffer set: calls 1-2 run eagerly on the static buffers (real training
+        steps; they size the workspace), call 3 captures the step into a CUDA graph,
+        every later call is one graph replay."""
         batch = inputs if isinstance(inputs, DeviceBatch) else self.stage(inputs, labels)
-        key = (batch.ids.B,)
-        slot = self._graphs.setdefault(key, [batch, None, None, None, None, None])
-        if len(slot) == 6:
-            slot.append(0)
-        if slot[4] is None:
-            assert slot[0] is batch, "graph mode needs the static DeviceBatch returned by stage()"
-            if slot[6] < 2:
-                slot[6] += 1
-                return self._eager_step(batch)
-            torch.cuda.synchronize(self.rt.device)
-            g = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(g):
-                loss = self._eager_step(batch)
-            slot[4], slot[5] = g, loss          # capture does not execute: replay runs the step
-        return self._replay(slot)
+        sl = getattr(batch, "_slot", None)
+        assert sl is not None, "graph mode needs the static DeviceBatch returned by stage()"
+        cur = torch.cuda.current_stream(self.rt.device)
+        cur.wait_event(sl.copy_done)
+        if sl.graph is None and sl.eager_steps < 2:
+            sl.eager_steps += 1
+            loss = self._eager_step(batch)
+            if sl.loss is None:
+                sl.loss = self.rt.empty((1,))
+            sl.loss.copy_(loss)
+        else:
+            if sl.graph is None:
+                torch.cuda.synchronize(self.rt.device)
+                g = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(g):
+                    loss = self._eager_step(batch)
+                    sl.loss.copy_(loss)
+                sl.graph = g                  # capture does not execute: the replay below runs the step
+                cur = torch.cuda.current_stream(self.rt.device)
+            sl.graph.replay()
+        sl.used = True
+        sl.compute_done.record(cur)
+        return sl.loss
 
-    @staticmethod
-    def _replay(slot) -> torch.Tensor:
-        slot[4].replay()
-        return slot[5]
+    def train_step_async(self, inputs, labels=None) -> "Trainer.LossHandle":
+        """Graph mode: enqueue the step and an asynchronous read-back of its loss;
+        returns immediately.  ``handle.result()`` blocks only until THIS step is done."""
+        assert self.use_graph, "train_step_async needs graph=True"
+        loss = self._graph_step(inputs, labels)
+        batch_slot = None
+        for slots, _ in self._graphs.values():
+            for sl in slots:
+                if sl.loss is loss:
+                    batch_slot = sl
+        with torch.cuda.stream(self._d2h_stream):
+            self._d2h_stream.wait_event(batch_slot.compute_done)
+            batch_slot.host_loss.copy_(batch_slot.loss, non_blocking=True)
+            batch_slot.loss_ready.record(self._d2h_stream)
+        return Trainer.LossHandle(batch_slot)

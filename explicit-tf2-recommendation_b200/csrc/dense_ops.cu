@@ -178,7 +178,7 @@ __global__ void __launch_bounds__(256) gemm_skinny_rows_kernel(const GemmParams 
 // wgrad of the tail: C[M,N] = A^T B with M*N <= 256 and K = batch: each block
 // reduces a slab of kSkinnySlab batch rows (thread t owns output (t / N, t % N)),
 // slab partials are summed in fixed order by gemm_splitk_finish_kernel.
-constexpr int kSkinnySlab = 1024;
+constexpr int kSkinnySlab = 128;     // 65 536-row batch -> 512 CTAs
 __global__ void __launch_bounds__(256) gemm_skinny_wgrad_kernel(const GemmParams p) {
   __shared__ float As[32][65];     // [row in sub-slab][m]  (M <= 64)
   __shared__ float Bs[32][33];     // [row in sub-slab][n]  (N <= 32)

@@ -296,6 +296,20 @@ int etr_transpose_bf16(etr_ctx* ctx, const void* d_src, int64_t rows, int64_t co
 int etr_cross_mat_bwd_elementwise(etr_ctx* ctx, const float* d_g, const float* d_x0, const float* d_u,
                                   int64_t n, float* d_du, float* d_dx0_accum, void* stream);
 
+/* --------------------------------- K9: sharded-table routing (a18)
+ * Row-sharded tables: owner(id) = id mod world, local row = id div world.  Stable
+ * partition of n ids by owner (deterministic; the un-permute is an exact inverse):
+ *   d_send_rows[j]  local row of the j-th id in owner-grouped order (send buffer)
+ *   d_send_pos[j]   original slot of that id (int64, usable as gather ids)
+ *   d_inv_pos[slot] position j of the slot in the grouped order
+ *   d_counts[g]     number of ids owned by rank g
+ * The all-to-all itself is NCCL (torch.distributed) on the host side; rows that
+ * come back in send order are consumed in place by etr_gather_fm_forward with
+ * ids = d_inv_pos (the received buffer acts as the table: no un-permute pass).  */
+int etr_shard_partition(etr_ctx* ctx, const int64_t* d_ids, int64_t n, int32_t world, int64_t rows_global,
+                        int64_t* d_send_rows, int64_t* d_send_pos, int64_t* d_inv_pos, int32_t* d_counts,
+                        void* stream);
+
 #ifdef __cplusplus
 }
 #endif

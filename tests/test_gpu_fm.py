@@ -326,7 +326,7 @@ def test_graph_trainer_matches_eager(L):
     lays = [L.DeepFMRankingLayer(names, feature_dims=V, embedding_dims=k, continuous_features=cont, seed=4)
             for _ in range(2)]
     trs = [L.Trainer(lays[0], lr=1e-2, graph=False), L.Trainer(lays[1], lr=1e-2, graph=True)]
-    for step in range(5):
+    for step in range(9):
         X = zipf_ids(rng, [V // F] * F, B)
         Xc = rng.normal(size=(B, C)).astype(np.float32)
         y = (rng.random(B) < 0.3).astype(np.float32)
@@ -337,4 +337,8 @@ def test_graph_trainer_matches_eager(L):
         assert float(la.item()) == float(lb.item()), step
     assert torch.equal(lays[0].table.data, lays[1].table.data)
     assert torch.equal(lays[0].params.value, lays[1].params.value)
-    assert trs[0].iterations == trs[1].iterations == 5        # steps 1-2 eager, 3 captured+replayed, 4-5 replayed
+    assert trs[0].iterations == trs[1].iterations == 9        # per buffer set: 2 eager steps, capture, replays
+    # asynchronous stepping reads every loss, one step late
+    hs = [trs[1].train_step_async(d, torch.tensor(y)) for _ in range(3)]
+    vals = [h.result() for h in hs]
+    assert all(np.isfinite(v) for v in vals) and trs[1].iterations == 12

@@ -1,0 +1,90 @@
+"""Host logic of the row-sharded tables (K9 protocol) on CPU: pure-function
+checks for G in {1,2,4,8} and a real 2-process gloo run of the exchange."""
+import os
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from oracle.shard_cpu import CpuShardOps
+
+
+def _router(world, rank, V, group=None):
+    import etr_b200  # noqa: F401
+    from etr_b200.sharded import ShardRouter
+    return ShardRouter(world, rank, V, CpuShardOps(), group)
+
+
+@pytest.mark.parametrize("G", [1, 2, 4, 8])
+def test_partition_is_stable_and_invertible(G):
+    rng = np.random.default_rng(G)
+    V = 1000
+    ids = torch.tensor(rng.integers(0, V, size=500))
+    send_rows, send_pos, inv_pos, counts = CpuShardOps().partition(ids, G, V)
+    assert int(counts.sum()) == ids.numel()
+    owner = ids[send_pos] % G
+    assert torch.all(owner[1:] >= owner[:-1])                               # grouped by owner
+    for g in range(G):                                                      # stable inside a group
+        pos = send_pos[owner == g]
+        assert torch.all(pos[1:] > pos[:-1])
+    assert torch.equal(send_rows * G + owner, ids[send_pos])                # local row <-> global id
+    assert torch.equal(send_pos[inv_pos], torch.arange(ids.numel()))       # exact inverse
+    assert counts.tolist() == [int((ids % G == g).sum()) for g in range(G)]
+
+
+@pytest.mark.parametrize("G", [1, 2, 4, 8])
+def test_local_rows_cover_the_table(G):
+    V = 1003
+    rows = [_router(G, r, V).local_rows() for r in range(G)]
+    assert sum(rows) == V
+    assert rows == [len(range(r, V, G)) for r in range(G)]
+
+
+def _worker(rank, world, port, V, width, seed, results):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        g = torch.Generator().manual_seed(seed)
+        full = torch.randn(V, width, generator=g)                           # same on every rank
+        shard = full[rank::world].contiguous()                              # this rank's rows
+        rng = np.random.default_rng(100 + rank)
+        ids = torch.tensor((rng.random(300) ** 3 * V).astype(np.int64))     # Zipf-like, duplicates
+        router = _router(world, rank, V)
+        route = router.dispatch(ids)
+        served = CpuShardOps().take_rows(shard, shard.shape[0], width, width, 0, route.recv_rows)
+        rows = router.return_rows(route, served)
+        looked_up = rows[route.inv_pos]                                     # un-permute
+        ok_fwd = torch.equal(looked_up, full[ids])                          # bit-exact vs the unsharded gather
+        # backward: per-slot grads -> owners; every owner scatter-adds into its shard
+        grads = torch.randn(ids.numel(), width, generator=torch.Generator().manual_seed(7 + rank))
+        recv = router.send_grads(route, grads[route.send_pos])
+        local = torch.zeros(shard.shape[0], width, dtype=torch.float64)
+        local.index_add_(0, route.recv_rows, recv.double())
+        # reference: gather everyone's (ids, grads) and scatter-add densely
+        all_ids = [torch.empty_like(ids) for _ in range(world)]
+        all_g = [torch.empty_like(grads) for _ in range(world)]
+        dist.all_gather(all_ids, ids)
+        dist.all_gather(all_g, grads)
+        dense = torch.zeros(V, width, dtype=torch.float64)
+        for i_, g_ in zip(all_ids, all_g):
+            dense.index_add_(0, i_, g_.double())
+        ok_bwd = torch.allclose(local, dense[rank::world], atol=1e-12)
+        results[rank] = (ok_fwd, ok_bwd, int(sum(route.send_counts)), route.n_recv)
+    finally:
+        dist.destroy_process_group()
+
+
+def test_exchange_protocol_over_gloo_world2():
+    world = 2
+    mgr = mp.Manager()
+    results = mgr.dict()
+    mp.spawn(_worker, args=(world, 29650 + os.getpid() % 200, 997, 20, 3, results), nprocs=world, join=True)
+    assert len(results) == world
+    for r in range(world):
+        ok_fwd, ok_bwd, n_sent, n_recv = results[r]
+        assert ok_fwd and ok_bwd, (r, ok_fwd, ok_bwd)
+        assert n_sent == 300
+    assert sum(results[r][3] for r in range(world)) == 600
