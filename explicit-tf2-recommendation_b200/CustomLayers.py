@@ -49,6 +49,15 @@ class _Layer:
         self.pooling = kwargs.pop("pooling", "sum")
         self.check_ids = bool(kwargs.pop("check_ids", True))
         self.name = kwargs.pop("name", type(self).__name__)
+        # row-sharded tables: shard=True (world/rank from torch.distributed) or shard=(world, rank)
+        shard = kwargs.pop("shard", None)
+        self.shard_spec = None
+        if shard:
+            if shard is True:
+                import torch.distributed as dist
+                shard = (dist.get_world_size(), dist.get_rank())
+            self.shard_spec = (int(shard[0]), int(shard[1]))
+        self.shard = None
         kwargs.pop("trainable", None)
         kwargs.pop("dtype", None)
         if kwargs:
@@ -133,8 +142,17 @@ class FMRankingLayer(_Layer):
     def _build_fm(self):
         k = self.embedding_dims
         self.params.add("bias", glorot_uniform((1,), self.gen, self.rt.device))
-        self.table = EmbeddingTable(self.rt, self.feature_dims, k + 1, self.table_dtype)
-        self.table.init_uniform(-0.05, 0.05, self.gen)      # Keras Embedding default for embed and w
+        if self.shard_spec:
+            from .sharded import ShardedTable
+            self.shard = ShardedTable(self.rt, self.feature_dims, k + 1, self.shard_spec[0], self.shard_spec[1],
+                                      self.table_dtype)
+            self.table = self.shard.local                   # this rank's rows r, r+G, r+2G, ...
+            shard_gen = torch.Generator(device=self.rt.device)
+            shard_gen.manual_seed(self.seed * 1000003 + self.shard_spec[1])
+            self.table.init_uniform(-0.05, 0.05, shard_gen)
+        else:
+            self.table = EmbeddingTable(self.rt, self.feature_dims, k + 1, self.table_dtype)
+            self.table.init_uniform(-0.05, 0.05, self.gen)  # Keras Embedding default for embed and w
 
     def _build_extra(self):
         pass
@@ -171,21 +189,34 @@ class FMRankingLayer(_Layer):
     def call(self, inputs, training: bool = False):
         ids = self._ids(inputs, self.feature_names)
         prob = self.rt.empty((ids.B, 1))
-        gather_fm_forward(self.table, self.embedding_dims, True, ids, bias=self.bias, prob=prob)
+        tab, vids, route = self._lookup(ids)
+        gather_fm_forward(tab, self.embedding_dims, True, vids, bias=self.bias, prob=prob)
         if training:
-            self._ctx = {"ids": ids}
+            self._ctx = {"ids": vids, "table": tab, "route": route}
         self._finish(training)
         return {"output": prob}
+
+    def _lookup(self, ids: IdsBatch):
+        """(table, ids, route): the local table, or -- row-sharded -- the rows fetched over
+        the all-to-all presented as a virtual table indexed by the inverse permutation."""
+        if self.shard is None:
+            return self.table, ids, None
+        return self.shard.lookup(ids)
+
+    def _table_grad(self, bag: torch.Tensor) -> SparseGrad:
+        if self.shard is None:
+            return SparseGrad(self.table, self._ctx["ids"], bag)
+        return self.shard.sparse_grad(self._ctx["route"], bag)
 
     def backward(self, dlogit: torch.Tensor) -> List[SparseGrad]:
         """dlogit = dL/dz [B] (z the pre-sigmoid logit).  Dense grads land in
         ``self.params.grad``; the table gradient is returned as a SparseGrad."""
         ids = self._ctx["ids"]
         dl = dlogit.reshape(-1)
-        bag = gather_fm_backward(self.table, self.embedding_dims, True, ids, dlogit=dl)
+        bag = gather_fm_backward(self._ctx["table"], self.embedding_dims, True, ids, dlogit=dl)
         check(self.rt.lib.etr_colsum_f32(self.rt.ctx, dl.data_ptr(), ids.B, 1, 1, self.params.g("bias").data_ptr(),
                                          self.rt.stream))
-        return [SparseGrad(self.table, ids, bag)]
+        return [self._table_grad(bag)]
 
 
 # ---------------------------------------------------------------------------
@@ -234,13 +265,14 @@ class DeepFMRankingLayer(FMRankingLayer):
                      torch.bfloat16 if self.mlp_precision == "bf16" else torch.float32)
         cont = self._cont(inputs, self.continuous_features) if C_ else None
         fm_logit = rt.empty((ids.B,))
-        gather_fm_forward(self.table, k, True, ids, bias=self.bias, logit=fm_logit, flat=x, flat_col0=col0, cont=cont)
+        tab, vids, route = self._lookup(ids)
+        gather_fm_forward(tab, k, True, vids, bias=self.bias, logit=fm_logit, flat=x, flat_col0=col0, cont=cont)
         dnn = self.MLP_layer2(self.MLP_layer1(x, training=training), training=training)      # [B,1]
         prob = rt.empty((ids.B, 1))
         check(rt.lib.etr_add_sigmoid(rt.ctx, fm_logit.data_ptr(), dnn.data_ptr(), ids.B, None, prob.data_ptr(),
                                      rt.stream))
         if training:
-            self._ctx = {"ids": ids}
+            self._ctx = {"ids": vids, "table": tab, "route": route}
         self._finish(training)
         return {"output": prob}
 
@@ -252,9 +284,10 @@ class DeepFMRankingLayer(FMRankingLayer):
         d_dnn = dl.clone().reshape(-1, 1)                    # d(fm+dnn)/d dnn = 1
         dh = self.MLP_layer2.backward(d_dnn)
         dx = self.MLP_layer1.backward(dh)                    # [B, pad + C + F*k]
-        bag = gather_fm_backward(self.table, self.embedding_dims, True, ids, dlogit=dl, dflat=dx, flat_col0=col0)
+        bag = gather_fm_backward(self._ctx["table"], self.embedding_dims, True, ids, dlogit=dl, dflat=dx,
+                                 flat_col0=col0)
         check(rt.lib.etr_colsum_f32(rt.ctx, dl.data_ptr(), ids.B, 1, 1, self.params.g("bias").data_ptr(), rt.stream))
-        return [SparseGrad(self.table, ids, bag)]
+        return [self._table_grad(bag)]
 
 
 # ---------------------------------------------------------------------------
@@ -811,6 +844,9 @@ class Trainer:
         self.state = self.rt.zeros((2,))            # [iterations, lr_t] on the device
         self.last_grads: List[SparseGrad] = []
         self.use_graph = graph
+        # data parallel over the ranks of a sharded layer: local batches, global-mean loss
+        self.dp_world = layer.shard_spec[0] if getattr(layer, "shard_spec", None) else 1
+        assert not (graph and self.dp_world > 1), "the sharded step syncs split sizes on the host: no CUDA graph"
         self.depth = 2 if graph else 1
         self._graphs: Dict[tuple, list] = {}
         self._copy_stream = self._d2h_stream = None
@@ -836,7 +872,12 @@ class Trainer:
         out = self.layer(inputs, training=True)["output"]
         y = rt.to_device(labels, torch.float32).reshape(-1)
         loss, dlogit = bce_forward_backward(rt, out.reshape(-1), y)
+        if self.dp_world > 1:
+            dlogit.mul_(1.0 / self.dp_world)          # the loss is the mean over the GLOBAL batch
         grads = self.layer.backward(dlogit)
+        if self.dp_world > 1:
+            import torch.distributed as dist
+            dist.all_reduce(self.layer.params.grad)   # replicated dense variables: sum of the ranks' grads
         self.apply_gradients(grads)
         if sl is not None and not torch.cuda.is_current_stream_capturing():
             sl.used = True
