@@ -615,8 +615,10 @@ class CrossLayer(_Layer):
 
     matrix = False
 
-    def __init__(self, layer_num, reg_w=1e-4, reg_b=1e-4, **kwargs):
+    def __init__(self, layer_num, reg_w=1e-4, reg_b=1e-4, precision="fp32", **kwargs):
         self._setup(kwargs)
+        assert precision in ("fp32", "bf16")
+        self.precision = precision
         self.layer_num, self.reg_w, self.reg_b = int(layer_num), reg_w, reg_b
         self.D = None
         self.front_pad = 0
@@ -703,8 +705,71 @@ class MatrixCrossLayer(CrossLayer):
 
     matrix = True
 
+    # ---- bf16 tensor-core path (tcgen05 + TMA, fp32 accumulate; parity 1e-2) ------------------
+    def _call_bf16(self, x: torch.Tensor, training: bool, out: Optional[torch.Tensor]):
+        from .runtime import cast_bf16
+        rt = self.rt
+        Di = self.D + self.front_pad
+        assert x.dtype == torch.bfloat16 and x.shape[1] == Di and x.stride(1) == 1 and x.stride(0) % 8 == 0
+        B = x.shape[0]
+        W, b = self.params["cross/W"], self.params["cross/b"]
+        xs, us = [x], []
+        xl = x
+        for l in range(self.layer_num):
+            last = l == self.layer_num - 1
+            nxt = out if (last and out is not None) else rt.empty((B, Di), torch.bfloat16)
+            u = rt.empty((B, Di), torch.bfloat16) if training else None
+            Wb = cast_bf16(rt, W[l])                      # [Di, Di] bf16: W itself is the [N,K] operand (y = W x)
+            assert xl.stride(0) == x.stride(0)
+            check(rt.lib.etr_cross_mat_layer_bf16(rt.ctx, x.data_ptr(), xl.data_ptr(), x.stride(0), B, Di,
+                                                  Wb.data_ptr(), Wb.stride(0), b[l].data_ptr(), nxt.data_ptr(),
+                                                  nxt.stride(0), _p(u), Di, rt.stream))
+            xs.append(nxt)
+            us.append(u)
+            xl = nxt
+        if training:
+            self._ctx = {"xs": xs, "us": us, "bf16": True}
+        return xl
+
+    def _backward_bf16(self, gout: torch.Tensor) -> torch.Tensor:
+        from .runtime import cast_bf16, gemm_bf16_tn, transpose_bf16
+        rt = self.rt
+        xs, us = self._ctx["xs"], self._ctx["us"]
+        x0 = xs[0]
+        B, Di = x0.shape[0], self.D + self.front_pad
+        W = self.params["cross/W"]
+        G = gout.to(torch.bfloat16).contiguous()
+        if G.data_ptr() == gout.data_ptr():
+            G = G.clone()
+        dx0 = rt.zeros((B, Di))
+        for l in reversed(range(self.layer_num)):
+            du = rt.empty((B, Di), torch.bfloat16)
+            check(rt.lib.etr_cross_mat_bwd_elementwise_bf16(rt.ctx, G.data_ptr(), x0.data_ptr(), us[l].data_ptr(),
+                                                            B * Di, du.data_ptr(), dx0.data_ptr(), rt.stream))
+            # dW_l = dU^T X_l : A = dU^T [Di,B], B operand = X_l^T [Di,B]; fp32 result
+            dut = transpose_bf16(rt, du, B, Di)
+            xlt = transpose_bf16(rt, xs[l], B, Di)
+            gemm_bf16_tn(rt, dut, xlt, self.params.g("cross/W")[l], Di, Di, B)
+            check(rt.lib.etr_colsum_bf16(rt.ctx, du.data_ptr(), B, Di, Di, self.params.g("cross/b")[l].data_ptr(),
+                                         rt.stream))
+            # G_l = G_{l+1} + dU W_l : B operand [N=j, K=i] = W[i,j]  ->  W^T
+            Wt = cast_bf16(rt, W[l], transpose=True)
+            Gn = rt.empty((B, Di), torch.bfloat16)
+            check(rt.lib.etr_gemm_bf16_tn_residual(rt.ctx, B, Di, Di, du.data_ptr(), Di, Wt.data_ptr(), Wt.stride(0),
+                                                   G.data_ptr(), Di, Gn.data_ptr(), Di, rt.stream))
+            G = Gn
+        check(rt.lib.etr_add_bf16_into_f32(rt.ctx, G.data_ptr(), B * Di, dx0.data_ptr(), rt.stream))
+        return dx0
+
     def call(self, inputs, training: bool = False, out: Optional[torch.Tensor] = None):
         rt = self.rt
+        if self.precision == "bf16":
+            if self.D is None:
+                assert inputs.shape[1] % 8 == 0, "bf16 cross layer: width must be a multiple of 8"
+                self.build(inputs.shape[1])
+            x = inputs if (isinstance(inputs, torch.Tensor) and inputs.dtype == torch.bfloat16 and
+                           inputs.device == rt.device) else rt.to_device(inputs, torch.float32).to(torch.bfloat16)
+            return self._call_bf16(x.contiguous() if x.stride(1) != 1 else x, training, out)
         x = rt.to_device(inputs, torch.float32)
         if self.D is None:
             self.build(x.shape[1])
@@ -731,6 +796,8 @@ class MatrixCrossLayer(CrossLayer):
 
     def backward(self, gout: torch.Tensor) -> torch.Tensor:
         from .runtime import gemm_f32
+        if self._ctx.get("bf16"):
+            return self._backward_bf16(gout)
         rt = self.rt
         xs, us = self._ctx["xs"], self._ctx["us"]
         x0 = xs[0]
@@ -765,8 +832,11 @@ class DeepCrossNetworkLayer(_Layer):
                                              'itag3', 'itag4'],
                  continuous_features=['itag4_origin', 'itag4_square', 'itag4_cube'], feature_dims=160000,
                  embedding_dims=16, units=[64, 8], activation='relu', layer_num=3, reg_w=1e-4, reg_b=1e-4,
-                 type='vec', **kwargs):
+                 type='vec', precision="fp32", **kwargs):
         self._setup(kwargs)
+        # "bf16" (matrix type only): cross layers and the wide dense layers on the tensor cores
+        assert precision in ("fp32", "bf16") and not (precision == "bf16" and type == 'vec')
+        self.precision = precision
         self.categorical_features = list(categorical_features)
         self.continuous_features = list(continuous_features)
         self.feature_names = self.categorical_features
@@ -774,15 +844,17 @@ class DeepCrossNetworkLayer(_Layer):
         self.units, self.type = list(units), type
         C_, F, k = len(self.continuous_features), len(self.categorical_features), self.embedding_dims
         self.D = C_ + F * k
-        self.front_pad = (-C_) % 4
+        self.front_pad = (-C_) % (8 if precision == "bf16" else 4)
+        if precision == "bf16":
+            assert (F * k) % 8 == 0 and self.units[-1] % 8 == 0, "bf16 DCN: F*k and units[-1] must be multiples of 8"
         self.embedding_layer = self.table = EmbeddingTable(self.rt, self.feature_dims, k, self.table_dtype)
         self.table.init_uniform(-0.05, 0.05, self.gen)
         cls = CrossLayer if type == 'vec' else MatrixCrossLayer
-        self.cross_layer = cls(layer_num, reg_w, reg_b, device=self.rt.device)
+        self.cross_layer = cls(layer_num, reg_w, reg_b, precision=precision, device=self.rt.device)
         self.cross_layer.build(self.D, self.params, self.gen, front_pad=self.front_pad)
-        self.dense_layer = DenseLayer(self.units, activation, name="dense_layer")
+        self.dense_layer = DenseLayer(self.units, activation, name="dense_layer", precision=precision)
         self.dense_layer.build(self.D, self.params, self.gen, front_pad=self.front_pad)
-        self.output_layer = MLPLayer([1], 'sigmoid', name="output_layer")
+        self.output_layer = MLPLayer([1], 'sigmoid', name="output_layer", precision=precision)
         self.output_layer.build(self.D + self.units[-1], self.params, self.gen, front_pad=self.front_pad)
         self.params.finalize()
 
@@ -798,10 +870,11 @@ class DeepCrossNetworkLayer(_Layer):
         ids = self._ids(inputs, self.categorical_features)
         C_, k = len(self.continuous_features), self.embedding_dims
         Di = self.front_pad + self.D
-        x = rt.empty((ids.B, Di))                               # [pad | X_cont | Flatten(emb)]
+        dt = torch.bfloat16 if self.precision == "bf16" else torch.float32
+        x = rt.empty((ids.B, Di), dt)                           # [pad | X_cont | Flatten(emb)]
         cont = self._cont(inputs, self.continuous_features) if C_ else None
         gather_fm_forward(self.table, k, False, ids, flat=x, flat_col0=self.front_pad + C_, cont=cont)
-        comb = rt.empty((ids.B, Di + self.units[-1]))           # concat fused: [cross_output | dnn_output]
+        comb = rt.empty((ids.B, Di + self.units[-1]), dt)       # concat fused: [cross_output | dnn_output]
         self.cross_layer.call(x, training=training, out=comb[:, :Di])
         dnn = self.dense_layer(x, training=training)
         comb[:, Di:] = dnn
@@ -817,8 +890,8 @@ class DeepCrossNetworkLayer(_Layer):
         Di = self.front_pad + self.D
         dz = dlogit.reshape(-1, 1).clone()
         dcomb = self.output_layer.backward(dz, dy_is_preact=True)           # [B, Di + units[-1]]
-        dx = self.cross_layer.backward(dcomb[:, :Di])                       # [B, Di]
-        ddnn = dcomb[:, Di:].contiguous()
+        dx = self.cross_layer.backward(dcomb[:, :Di])                       # [B, Di] fp32
+        ddnn = dcomb[:, Di:].float().contiguous()
         self.dense_layer.backward(ddnn, accumulate_into=dx)
         bag = gather_fm_backward(self.table, self.embedding_dims, False, ids, dflat=dx,
                                  flat_col0=self.front_pad + len(self.continuous_features))

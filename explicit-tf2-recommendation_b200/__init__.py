@@ -12,9 +12,16 @@ from . import _lib  # noqa: F401
 from ._lib import EtrError, EtrIdRangeError  # noqa: F401
 
 
+_SUBMODULES = ("CustomLayers", "runtime", "dense", "sharded", "build")
+
+
 def __getattr__(name):
     # layers import torch + the runtime lazily so that `import etr_b200` stays cheap
     import importlib
+    if name in _SUBMODULES:
+        return importlib.import_module("." + name, __name__)
+    if name.startswith("__"):
+        raise AttributeError(name)
     mod = importlib.import_module(".CustomLayers", __name__)
     try:
         return getattr(mod, name)

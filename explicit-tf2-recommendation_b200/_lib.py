@@ -77,6 +77,10 @@ PROTOTYPES = {
     "etr_cross_mat_layer_f32": (C.c_int, [_vp, _vp, _vp, _i64, _i64, _i32, _vp, _vp, _vp, _i64, _vp, _i64, _vp]),
     "etr_cross_mat_layer_bf16": (C.c_int, [_vp, _vp, _vp, _i64, _i64, _i32, _vp, _i64, _vp, _vp, _i64, _vp, _i64, _vp]),
     "etr_gemm_bf16_tn": (C.c_int, [_vp, _i64, _i64, _i64, _vp, _i64, _vp, _i64, _vp, _i64, _i32, _vp, _i32, _vp]),
+    "etr_gemm_bf16_tn_residual": (C.c_int, [_vp, _i64, _i64, _i64, _vp, _i64, _vp, _i64, _vp, _i64, _vp, _i64, _vp]),
+    "etr_cross_mat_bwd_elementwise_bf16": (C.c_int, [_vp, _vp, _vp, _vp, _i64, _vp, _vp, _vp]),
+    "etr_add_bf16_into_f32": (C.c_int, [_vp, _vp, _i64, _vp, _vp]),
+    "etr_colsum_bf16": (C.c_int, [_vp, _vp, _i64, _i64, _i64, _vp, _vp]),
     "etr_cast_bf16": (C.c_int, [_vp, _vp, _i64, _i64, _i64, _vp, _i64, _i32, _vp]),
     "etr_transpose_bf16": (C.c_int, [_vp, _vp, _i64, _i64, _i64, _vp, _i64, _vp]),
     "etr_shard_partition": (C.c_int, [_vp, _vp, _i64, _i32, _i64, _vp, _vp, _vp, _vp, _vp]),

@@ -273,7 +273,7 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
           }
         }
       } else {   // EPI_CROSS: u = acc + b ; out = x0 * u + xl
-        const __nv_bfloat16* px0 = ep.x0 + row * ep.ldx + col0;
+        const __nv_bfloat16* px0 = ep.x0 ? ep.x0 + row * ep.ldx + col0 : nullptr;
         const __nv_bfloat16* pxl = ep.xl + row * ep.ldx + col0;
         __nv_bfloat16* po = ep.out + row * ep.ldo + col0;
         __nv_bfloat16* pu = ep.u ? ep.u + row * ep.ldu + col0 : nullptr;
@@ -282,7 +282,7 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
         if (vec) {
 #pragma unroll
           for (int i = 0; i < 32; i += 8) {
-            const uint4 a0 = *reinterpret_cast<const uint4*>(px0 + i);
+            const uint4 a0 = ep.x0 ? *reinterpret_cast<const uint4*>(px0 + i) : make_uint4(0x3f803f80u, 0x3f803f80u, 0x3f803f80u, 0x3f803f80u);
             const uint4 al = *reinterpret_cast<const uint4*>(pxl + i);
             const uint32_t w0[4] = {a0.x, a0.y, a0.z, a0.w};
             const uint32_t wl[4] = {al.x, al.y, al.z, al.w};
@@ -291,8 +291,8 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
             for (int j = 0; j < 4; ++j) {
               const float2 f0 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&w0[j]));
               const float2 fl = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&wl[j]));
-              const float ua = __uint_as_float(v[i + 2 * j]) + ep.bias[col0 + i + 2 * j];
-              const float ub = __uint_as_float(v[i + 2 * j + 1]) + ep.bias[col0 + i + 2 * j + 1];
+              const float ua = __uint_as_float(v[i + 2 * j]) + (ep.bias ? ep.bias[col0 + i + 2 * j] : 0.f);
+              const float ub = __uint_as_float(v[i + 2 * j + 1]) + (ep.bias ? ep.bias[col0 + i + 2 * j + 1] : 0.f);
               __nv_bfloat162 ho = __floats2bfloat162_rn(f0.x * ua + fl.x, f0.y * ub + fl.y);
               __nv_bfloat162 hu = __floats2bfloat162_rn(ua, ub);
               wo[j] = *reinterpret_cast<uint32_t*>(&ho);
@@ -305,8 +305,8 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
 #pragma unroll
           for (int i = 0; i < 32; ++i) {
             if (i < ncol) {
-              const float uu = __uint_as_float(v[i]) + ep.bias[col0 + i];
-              po[i] = __float2bfloat16_rn(__bfloat162float(px0[i]) * uu + __bfloat162float(pxl[i]));
+              const float uu = __uint_as_float(v[i]) + (ep.bias ? ep.bias[col0 + i] : 0.f);
+              po[i] = __float2bfloat16_rn((ep.x0 ? __bfloat162float(px0[i]) : 1.0f) * uu + __bfloat162float(pxl[i]));
               if (pu) pu[i] = __float2bfloat16_rn(uu);
             }
           }
@@ -366,20 +366,98 @@ __global__ void __launch_bounds__(256) cast_bf16_kernel(const float* src, long l
     }
   }
 }
-// bf16 [rows, cols] -> bf16 transposed [cols, ld_dst]
+// bf16 [rows, cols] -> bf16 transposed [cols, ld_dst]; 64x64 tiles, 4-byte (bf16x2)
+// global accesses on both sides (128 B per warp instruction), zero fill up to ld_dst.
 __global__ void __launch_bounds__(256) transpose_bf16_kernel(const __nv_bfloat16* src, long long rows, long long cols,
                                                              long long ld_src, __nv_bfloat16* dst, long long ld_dst) {
-  __shared__ __nv_bfloat16 tile[32][34];
-  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
-  const long long r0 = (long long)blockIdx.y * 32, c0 = (long long)blockIdx.x * 32;
-  for (int i = ty; i < 32; i += 8) {
-    const long long r = r0 + i, c = c0 + tx;
-    tile[i][tx] = (r < rows && c < cols) ? src[r * ld_src + c] : __float2bfloat16_rn(0.f);
+  __shared__ __nv_bfloat16 tile[64][66];
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;            // 32 x 8
+  const long long r0 = (long long)blockIdx.y * 64, c0 = (long long)blockIdx.x * 64;
+  const bool pair_ok = (ld_src % 2 == 0) && ((reinterpret_cast<uintptr_t>(src) & 3) == 0);
+  for (int i = ty; i < 64; i += 8) {
+    const long long r = r0 + i, c = c0 + 2 * tx;
+    __nv_bfloat16 a = __float2bfloat16_rn(0.f), b = a;
+    if (r < rows) {
+      if (pair_ok && c + 1 < cols) {
+        const __nv_bfloat162 v = *reinterpret_cast<const __nv_bfloat162*>(src + r * ld_src + c);
+        a = v.x; b = v.y;
+      } else {
+        if (c < cols) a = src[r * ld_src + c];
+        if (c + 1 < cols) b = src[r * ld_src + c + 1];
+      }
+    }
+    tile[i][2 * tx] = a;
+    tile[i][2 * tx + 1] = b;
   }
   __syncthreads();
-  for (int i = ty; i < 32; i += 8) {
-    const long long orow = c0 + i, ocol = r0 + tx;
-    if (orow < cols && ocol < ld_dst) dst[orow * ld_dst + ocol] = ocol < rows ? tile[tx][i] : __float2bfloat16_rn(0.f);
+  const bool opair_ok = (ld_dst % 2 == 0) && ((reinterpret_cast<uintptr_t>(dst) & 3) == 0);
+  for (int i = ty; i < 64; i += 8) {
+    const long long orow = c0 + i, ocol = r0 + 2 * tx;                // dst[c][r]
+    if (orow >= cols) continue;
+    __nv_bfloat162 v;
+    v.x = tile[2 * tx][i];
+    v.y = tile[2 * tx + 1][i];
+    if (ocol >= rows) v.x = __float2bfloat16_rn(0.f);
+    if (ocol + 1 >= rows) v.y = __float2bfloat16_rn(0.f);
+    if (opair_ok && ocol + 1 < ld_dst) {
+      *reinterpret_cast<__nv_bfloat162*>(dst + orow * ld_dst + ocol) = v;
+    } else {
+      if (ocol < ld_dst) dst[orow * ld_dst + ocol] = v.x;
+      if (ocol + 1 < ld_dst) dst[orow * ld_dst + ocol + 1] = v.y;
+    }
+  }
+}
+
+// bf16 elementwise pieces of the cross-matrix backward (SURVEY a'):
+//   du = G (.) x0 (bf16) ; dx0 += G (.) u (fp32 accumulate)
+__global__ void __launch_bounds__(256) cross_bwd_elem_bf16_kernel(const __nv_bfloat16* G, const __nv_bfloat16* x0,
+                                                                  const __nv_bfloat16* u, long long n2,
+                                                                  __nv_bfloat16* du, float* dx0) {
+  for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < n2; t += (long long)gridDim.x * blockDim.x) {
+    const float2 g = __bfloat1622float2(reinterpret_cast<const __nv_bfloat162*>(G)[t]);
+    const float2 a = __bfloat1622float2(reinterpret_cast<const __nv_bfloat162*>(x0)[t]);
+    const float2 b = __bfloat1622float2(reinterpret_cast<const __nv_bfloat162*>(u)[t]);
+    reinterpret_cast<__nv_bfloat162*>(du)[t] = __floats2bfloat162_rn(g.x * a.x, g.y * a.y);
+    float2 d = reinterpret_cast<float2*>(dx0)[t];
+    d.x += g.x * b.x; d.y += g.y * b.y;
+    reinterpret_cast<float2*>(dx0)[t] = d;
+  }
+}
+// y (fp32) += x (bf16)
+__global__ void __launch_bounds__(256) add_bf16_into_f32_kernel(const __nv_bfloat16* x, long long n2, float* y) {
+  for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < n2; t += (long long)gridDim.x * blockDim.x) {
+    const float2 a = __bfloat1622float2(reinterpret_cast<const __nv_bfloat162*>(x)[t]);
+    float2 d = reinterpret_cast<float2*>(y)[t];
+    d.x += a.x; d.y += a.y;
+    reinterpret_cast<float2*>(y)[t] = d;
+  }
+}
+// column sums of a bf16 matrix: stage 1 of the two-pass deterministic reduction
+__global__ void __launch_bounds__(256) colsum_bf16_stage1_kernel(const __nv_bfloat16* X, long long M, long long N, long long ldx,
+                                                                 float* partial) {
+  __shared__ float sm[8][33];
+  const int cx = threadIdx.x & 31, ry = threadIdx.x >> 5;
+  const long long n = (long long)blockIdx.x * 32 + cx;
+  const long long r0 = (long long)blockIdx.y * 2048;
+  long long r1 = r0 + 2048;
+  if (r1 > M) r1 = M;
+  float s = 0.f;
+  if (n < N)
+    for (long long r = r0 + ry; r < r1; r += 8) s += __bfloat162float(X[r * ldx + n]);
+  sm[ry][cx] = s;
+  __syncthreads();
+  if (ry == 0 && n < N) {
+    float t = 0.f;
+#pragma unroll
+    for (int q = 0; q < 8; ++q) t += sm[q][cx];
+    partial[(long long)blockIdx.y * N + n] = t;
+  }
+}
+__global__ void __launch_bounds__(256) colsum_stage2b_kernel(const float* partial, long long slabs, long long N, float* out) {
+  for (long long n = (long long)blockIdx.x * blockDim.x + threadIdx.x; n < N; n += (long long)gridDim.x * blockDim.x) {
+    float s = 0.f;
+    for (long long q = 0; q < slabs; ++q) s += partial[q * N + n];
+    out[n] = s;
   }
 }
 
@@ -523,6 +601,58 @@ int etr_cross_mat_layer_bf16(etr_ctx* ctx, const void* d_x0, const void* d_xl, i
   return tc::run_gemm(ctx, batch, D, D, d_xl, ldx, d_W, ldw, ep, 0, (cudaStream_t)stream, nullptr, 0, 1, nullptr, 0, 0.f);
 }
 
+int etr_gemm_bf16_tn_residual(etr_ctx* ctx, int64_t M, int64_t N, int64_t K, const void* d_A, int64_t lda,
+                              const void* d_B, int64_t ldb, const void* d_res, int64_t ldr, void* d_out, int64_t ldo,
+                              void* stream) {
+  ETR_CHECK_ARG(ctx && d_A && d_B && d_res && d_out, "NULL argument");
+  ETR_CHECK_ARG(M > 0 && N > 0 && K > 0, "empty GEMM");
+  tc::EpiParams ep;
+  memset(&ep, 0, sizeof(ep));
+  ep.mode = tc::EPI_CROSS;                  // x0 == NULL, bias == NULL: out = acc + res
+  ep.xl = (const __nv_bfloat16*)d_res; ep.ldx = ldr;
+  ep.out = (__nv_bfloat16*)d_out; ep.ldo = ldo;
+  return tc::run_gemm(ctx, M, N, K, d_A, lda, d_B, ldb, ep, 0, (cudaStream_t)stream, nullptr, 0, 1, nullptr, 0, 0.f);
+}
+
+int etr_cross_mat_bwd_elementwise_bf16(etr_ctx* ctx, const void* d_g, const void* d_x0, const void* d_u, int64_t n,
+                                       void* d_du, float* d_dx0_accum, void* stream) {
+  ETR_CHECK_ARG(ctx && d_g && d_x0 && d_u && d_du && d_dx0_accum, "NULL argument");
+  ETR_CHECK_ARG(n % 2 == 0, "n must be even (bf16x2 accesses)");
+  if (n <= 0) return ETR_OK;
+  tc::cross_bwd_elem_bf16_kernel<<<grid_for(n / 2, 256, ctx->sm_count, 8), 256, 0, (cudaStream_t)stream>>>(
+      (const __nv_bfloat16*)d_g, (const __nv_bfloat16*)d_x0, (const __nv_bfloat16*)d_u, n / 2, (__nv_bfloat16*)d_du,
+      d_dx0_accum);
+  ETR_LAUNCH_CHECK(ctx);
+  return ETR_OK;
+}
+
+int etr_add_bf16_into_f32(etr_ctx* ctx, const void* d_x, int64_t n, float* d_y, void* stream) {
+  ETR_CHECK_ARG(ctx && d_x && d_y, "NULL argument");
+  ETR_CHECK_ARG(n % 2 == 0, "n must be even");
+  if (n <= 0) return ETR_OK;
+  tc::add_bf16_into_f32_kernel<<<grid_for(n / 2, 256, ctx->sm_count, 8), 256, 0, (cudaStream_t)stream>>>(
+      (const __nv_bfloat16*)d_x, n / 2, d_y);
+  ETR_LAUNCH_CHECK(ctx);
+  return ETR_OK;
+}
+
+int etr_colsum_bf16(etr_ctx* ctx, const void* d_X, int64_t M, int64_t N, int64_t ldx, float* d_out, void* stream) {
+  ETR_CHECK_ARG(ctx && d_X && d_out, "NULL argument");
+  if (N <= 0) return ETR_OK;
+  cudaStream_t s = (cudaStream_t)stream;
+  if (M <= 0) { ETR_CUDA(cudaMemsetAsync(d_out, 0, sizeof(float) * N, s)); return ETR_OK; }
+  const long long slabs = ceil_div(M, 2048);
+  ETR_CHECK_ARG(slabs <= 65535, "M too large");
+  int st = etr_ws_reserve(ctx, sizeof(float) * (size_t)slabs * N);
+  if (st != ETR_OK) return st;
+  dim3 grid((unsigned)ceil_div(N, 32), (unsigned)slabs);
+  tc::colsum_bf16_stage1_kernel<<<grid, 256, 0, s>>>((const __nv_bfloat16*)d_X, M, N, ldx, (float*)ctx->d_ws);
+  ETR_LAUNCH_CHECK(ctx);
+  tc::colsum_stage2b_kernel<<<grid_for(N, 256, ctx->sm_count, 1), 256, 0, s>>>((const float*)ctx->d_ws, slabs, N, d_out);
+  ETR_LAUNCH_CHECK(ctx);
+  return ETR_OK;
+}
+
 int etr_cast_bf16(etr_ctx* ctx, const float* d_src, int64_t rows, int64_t cols, int64_t ld_src, void* d_dst,
                   int64_t ld_dst, int32_t transpose, void* stream) {
   ETR_CHECK_ARG(ctx && d_src && d_dst, "NULL argument");
@@ -544,7 +674,7 @@ int etr_transpose_bf16(etr_ctx* ctx, const void* d_src, int64_t rows, int64_t co
   ETR_CHECK_ARG(ctx && d_src && d_dst, "NULL argument");
   if (rows <= 0 || cols <= 0) return ETR_OK;
   const long long span_r = ld_dst > rows ? ld_dst : rows;
-  dim3 grid((unsigned)ceil_div(cols, 32), (unsigned)ceil_div(span_r, 32));
+  dim3 grid((unsigned)ceil_div(cols, 64), (unsigned)ceil_div(span_r, 64));
   tc::transpose_bf16_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>((const __nv_bfloat16*)d_src, rows, cols, ld_src,
                                                                    (__nv_bfloat16*)d_dst, ld_dst);
   ETR_LAUNCH_CHECK(ctx);

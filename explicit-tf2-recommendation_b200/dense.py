@@ -240,7 +240,9 @@ class MLPLayer:
                     # dx = d K^T : A = d (bf16) [B,out], B operand = K [in,out] as stored; bf16 result
                     db_ = cast_bf16(rt, d)
                     kb = cast_bf16(rt, k)
-                    dx = rt.empty((B, n_in), torch.bfloat16)
+                    # the model input's gradient goes to the gather backward (reads bf16); an
+                    # intermediate one feeds the next activation backward and stays fp32
+                    dx = rt.empty((B, n_in), torch.bfloat16 if i == 0 else torch.float32)
                     gemm_bf16_tn(rt, db_, kb, dx, B, n_in, n_out)
                 else:
                     dx = acc if acc is not None else rt.empty((B, n_in))

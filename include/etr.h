@@ -285,6 +285,18 @@ int etr_gemm_bf16_tn(etr_ctx* ctx, int64_t M, int64_t N, int64_t K,
                      const void* d_A, int64_t lda, const void* d_B, int64_t ldb,
                      void* d_C, int64_t ldc, int32_t c_dtype, const float* d_bias, int32_t act,
                      void* stream);
+/* Backward pieces of the bf16 cross-matrix layer (SURVEY a', cross-matrix):
+ *   etr_gemm_bf16_tn_residual : out = A B^T + res        (G_l = G_{l+1} + dU W_l; bf16 in/out, fp32 accumulate)
+ *   etr_cross_mat_bwd_elementwise_bf16 : du = g (.) x0 (bf16), dx0 += g (.) u (fp32), n elements
+ *   etr_add_bf16_into_f32 : y += x ;  etr_colsum_bf16 : out[n] = sum_m X[m,n] (db_l = colsum(dU)).   */
+int etr_gemm_bf16_tn_residual(etr_ctx* ctx, int64_t M, int64_t N, int64_t K, const void* d_A, int64_t lda,
+                              const void* d_B, int64_t ldb, const void* d_res, int64_t ldr,
+                              void* d_out, int64_t ldo, void* stream);
+int etr_cross_mat_bwd_elementwise_bf16(etr_ctx* ctx, const void* d_g, const void* d_x0, const void* d_u,
+                                       int64_t n, void* d_du, float* d_dx0_accum, void* stream);
+int etr_add_bf16_into_f32(etr_ctx* ctx, const void* d_x, int64_t n, float* d_y, void* stream);
+int etr_colsum_bf16(etr_ctx* ctx, const void* d_X, int64_t M, int64_t N, int64_t ldx, float* d_out,
+                    void* stream);
 /* fp32 [rows, cols] -> bf16 (optionally transposed) into a buffer with leading
  * dim ld_dst whose padding columns are written as zeros; bf16 -> bf16 transpose. */
 int etr_cast_bf16(etr_ctx* ctx, const float* d_src, int64_t rows, int64_t cols, int64_t ld_src,

@@ -143,3 +143,47 @@ def test_deepfm_bf16_mlp_matches_oracle(rt):
     y = torch.tensor((rng.random(B) < 0.3).astype(np.float32))
     losses = [float(tr.train_step(inputs, y).item()) for _ in range(6)]
     assert losses[-1] < losses[0]
+
+
+@pytest.mark.parametrize("B", [256, 1000])
+def test_dcn_matrix_bf16_forward_backward(rt, B):
+    """DeepCrossNetworkLayer(type='matrix', precision='bf16'): cross layers + wide dense layers on the
+    tensor cores; output and gradients vs the fp64 oracle within the bf16 tolerance (operands made
+    bf16-representable so ReLU masks agree, see test_deepfm_bf16_mlp_matches_oracle)."""
+    from etr_b200 import CustomLayers as L
+    from tests.util import assert_close, dense_table_grad_to_slices, oracle_dcn, table_slices, zipf_ids
+    rng = np.random.default_rng(B)
+    V = 5000
+    lay = L.DeepCrossNetworkLayer(feature_dims=V, type="matrix", precision="bf16", seed=7)
+    lay.table.data.copy_(lay.table.data.to(torch.bfloat16).float())
+    lay.params.value.copy_(lay.params.value.to(torch.bfloat16).float())
+    F, C = len(lay.categorical_features), len(lay.continuous_features)
+    X = zipf_ids(rng, [V // F] * F, B)
+    Xc = torch.tensor(rng.normal(size=(B, C)).astype(np.float32)).to(torch.bfloat16).float().numpy()
+    inputs = {n: torch.tensor(X[:, i]) for i, n in enumerate(lay.categorical_features)}
+    inputs.update({n: torch.tensor(Xc[:, i]) for i, n in enumerate(lay.continuous_features)})
+    out = lay(inputs, training=True)["output"]
+    orc = oracle_dcn(lay)
+    o_in = {n: torch.tensor(X[:, i]) for i, n in enumerate(lay.categorical_features)}
+    o_in.update({n: torch.tensor(Xc[:, i], dtype=torch.float64) for i, n in enumerate(lay.continuous_features)})
+    ref = orc.call(o_in)["output"]
+    assert_close(out.cpu().numpy(), ref.detach().numpy(), 1e-2, "DCN-matrix bf16 output")
+    dz = rng.normal(size=(B,)).astype(np.float32)
+    grads = lay.backward(torch.tensor(dz).cuda())
+    p = ref.squeeze(1)
+    z = torch.log(p) - torch.log1p(-p)
+    (z * torch.tensor(dz, dtype=torch.float64)).sum().backward()
+    ref_ids, ref_rows = dense_table_grad_to_slices(orc.embedding.grad)
+    ids, rows = table_slices(grads)
+    assert np.array_equal(ids, ref_ids)
+    assert_close(rows, ref_rows, 2e-2, "DCN bf16 embedding grads", grad=True)
+    p0 = lay.front_pad
+    for i in range(lay.cross_layer.layer_num):
+        gw = lay.params.g("cross/W")[i][p0:, p0:]
+        assert_close(gw.cpu().numpy(), orc.cross_layer.cross_weight[i].grad.numpy(), 2e-2, f"cross W{i}", grad=True)
+        gb = lay.params.g("cross/b")[i][p0:].unsqueeze(1)
+        assert_close(gb.cpu().numpy(), orc.cross_layer.cross_bias[i].grad.numpy(), 2e-2, f"cross b{i}", grad=True)
+    assert_close(lay.params.g("dense_layer/kernel_0").cpu().numpy(), orc.dense_layer.kernels[0].grad.numpy(), 2e-2,
+                 "dense k0", grad=True)
+    assert_close(lay.params.g("output_layer/kernel_0").cpu().numpy(), orc.output_layer.kernels[0].grad.numpy(), 2e-2,
+                 "output k0", grad=True)
