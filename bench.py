@@ -180,6 +180,100 @@ def workload_config(args, B, graph):
             "l2": "L2 flushed (512 MiB write) before every timed step", "cuda_graph": graph}
 
 
+def run_c3(args):
+    """BASELINE configs[2]: DCN-matrix (3 cross layers, k=64 -> D = 13 + 26*64 = 1677) + DenseLayer [64,8] +
+    Dense(1), bf16 tensor-core cross (tcgen05), batch 65 536, train step fwd+bwd+row-wise Adam."""
+    import torch
+    import etr_b200  # noqa: F401
+    from etr_b200 import CustomLayers as L
+    dev = torch.device("cuda", int(os.environ.get("LOCAL_RANK", "0")))
+    torch.cuda.set_device(dev)
+    B, K3, LAYERS = args.batch, 64, 3
+    V = int(sum(CRITEO_CARDS))
+    names = [f"C{i + 1}" for i in range(F)]
+    cont = [f"I{i + 1}" for i in range(C_DENSE)]
+    layer = L.DeepCrossNetworkLayer(names, cont, feature_dims=V, embedding_dims=K3, units=[64, 8], layer_num=LAYERS,
+                                    type="matrix", precision="bf16", check_ids=False, seed=1)
+    rt = layer.rt
+    host = make_batches(3, B, args.dist, seed=SEED + 1)
+    dev_batches = [(torch.from_numpy(np.ascontiguousarray(X.T)).to(dev),
+                    torch.from_numpy(np.ascontiguousarray(Xc.T)).to(dev), torch.from_numpy(y).to(dev))
+                   for X, Xc, y in host]
+    use_graph = not args.no_graph
+    trainer = L.Trainer(layer, lr=1e-3, graph=use_graph)
+    flush = torch.empty(512 << 20, dtype=torch.uint8, device=dev)
+
+    def stage(i):
+        ids, xc, y = dev_batches[i % 3]
+        return trainer.stage({**{n: ids[f] for f, n in enumerate(names)}, **{n: xc[c] for c, n in enumerate(cont)}}, y)
+
+    for i in range(max(args.warmup, 8 if use_graph else 3)):
+        trainer.train_step(stage(i))
+    torch.cuda.synchronize(dev)
+    clocks = ClockSampler(dev.index)
+    clocks.start()
+    l0 = rt.launches
+    ev = []
+    for i in range(args.steps):
+        b = stage(i)
+        flush.zero_()
+        torch.cuda.current_stream(dev).wait_event(b._slot.copy_done)
+        a, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        trainer.train_step(b)
+        e.record()
+        ev.append((a, e))
+    torch.cuda.synchronize(dev)
+    clk = clocks.stop()
+    ms = [a.elapsed_time(e) for a, e in ev]
+    total = sum(ms)
+    # one cross layer forward timed alone (the dominant tensor kernel)
+    import ctypes as C
+    from etr_b200._lib import check
+    from etr_b200.runtime import cast_bf16
+    Di = layer.front_pad + layer.D
+    x = (torch.randn(B, Di, device=dev) * 0.1).to(torch.bfloat16)
+    Wb = cast_bf16(rt, layer.params["cross/W"][0])
+    out = torch.empty_like(x)
+    u = torch.empty_like(x)
+    kt = []
+    for i in range(12):
+        flush.zero_()
+        a, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        check(rt.lib.etr_cross_mat_layer_bf16(rt.ctx, x.data_ptr(), x.data_ptr(), Di, B, Di, Wb.data_ptr(), Di,
+                                              layer.params["cross/b"][0].data_ptr(), out.data_ptr(), Di, u.data_ptr(),
+                                              Di, rt.stream))
+        e.record()
+        kt.append((a, e))
+    torch.cuda.synchronize(dev)
+    k_ms = statistics.mean(a.elapsed_time(e) for a, e in kt[2:])
+    D = layer.D
+    flops = 2.0 * B * D * D                                    # unpadded D = 1677 (SURVEY 8d)
+    peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json"))) if os.path.exists(
+        os.path.join(ROOT, "MEASURED_PEAKS.json")) else {"bf16_tflops": 1590.0}
+    peak = float(peaks["bf16_tflops"])                         # burst figure: the kernel is timed alone
+    ach = flops / (k_ms * 1e-3) / 1e12
+    step_flops = 3.0 * LAYERS * flops                          # fwd + dgrad + wgrad of the cross layers
+    line = {
+        "metric": "train samples/sec DCN-matrix (Criteo-shape)", "value": B * args.steps / (total * 1e-3),
+        "unit": "samples/s", "n_gpus": 1, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": total / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "bf16 tensor-core cross / dense GEMMs (fp32 accumulate), fp32 tables + Adam", "data": "synthetic",
+        "config": {"workload": "c3: DCN-matrix train step, 13 dense + 26 sparse (k=64, D=1677), 3 cross layers, "
+                               "DenseLayer [64,8], Dense(1); 33 762 577-row table", "global_batch": B,
+                   "id_distribution": args.dist, "cuda_graph": use_graph, "l2": "L2 flushed before every timed step",
+                   "apply_mode": "rowwise Adam"},
+        "clocks": clk, "gpu_launches": rt.launches - l0,
+        "roofline": {"bound": "tensor", "kernel": "gemm_bf16_tn_kernel<240,2> EPI_CROSS (one cross layer forward)",
+                     "achieved": ach, "peak": peak, "unit": "TFLOP/s", "frac": ach / peak, "traffic": None,
+                     "kernel_ms": k_ms, "peak_source": "MEASURED_PEAKS.json bf16_tflops (burst; kernel timed alone)"},
+        "cross_gemm_share_of_step_at_peak": step_flops / (float(peaks.get("bf16_tflops_sustained", peak)) * 1e12)
+        / (total / args.steps * 1e-3),
+    }
+    print(json.dumps(line))
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -193,10 +287,14 @@ def main():
                     help="first MLP layer: bf16 tcgen05 tensor cores (fp32 accumulate) or the fp32 SIMT exact-parity path")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-budget", type=float, default=12.0)
+    ap.add_argument("--config", default="c2", choices=["c2", "c3"],
+                    help="c2 = DeepFM (the headline, BASELINE configs[1]); c3 = DCN-matrix bf16 tensor-core cross")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
     if args.impl == "reference":
         return run_reference(args)
+    if args.config == "c3":
+        return run_c3(args)
 
     import torch
     import torch.distributed as dist

@@ -40,6 +40,11 @@ struct GatherParams {
   long long cont_sb, cont_sc;
   int cont_n;
   int fill_front;  // 1: this launch owns columns [0, flat_col0) of d_flat
+  // tiled kernels: the fused w column sits in its own chunk behind a power-of-two number of
+  // embedding chunks -> the lane group covers only the embedding and lane 0 fetches w with one
+  // extra 4-byte (2-byte for bf16) load, so no lane idles
+  int w_extra;
+  int esize;
   // backward only
   const float* dlogit;
   float* bag_grad;
@@ -324,9 +329,14 @@ __device__ __forceinline__ void emit_bag_grad(const GatherParams& p, long long b
 #pragma unroll
     for (int q = 0; q < VEC / 4; ++q) {
       const int gc = c * (VEC / 4) + q;
-      if (gc < grad_chunks)
+      if (gc < grad_chunks && (!p.w_extra || gc * 4 < p.k))
         stg_stream16(grow + gc * 4, make_float4(gout[4 * q], gout[4 * q + 1], gout[4 * q + 2], gout[4 * q + 3]));
     }
+  }
+  if (p.w_extra && gl == 0) {
+    // the w column's chunk (and any padding chunk behind it): [dlogit, 0, 0, 0]
+    for (int gc = p.k / 4; gc < grad_chunks; ++gc)
+      stg_stream16(grow + gc * 4, make_float4(gc * 4 == p.k ? dl * scale : 0.f, 0.f, 0.f, 0.f));
   }
 }
 
@@ -520,16 +530,24 @@ __global__ void __launch_bounds__(256, 3) gather_fm_fwd_tile_kernel(const Gather
         else reinterpret_cast<float*>(p.flat)[b * p.flat_ld + j] = v;
       }
     }
+    float wsum = 0.f;
     for (int f0 = 0; f0 < p.F; f0 += U) {
       Chunk<Elem> r[U];
+      float wv[U];
 #pragma unroll
       for (int u = 0; u < U; ++u) {
         bool ok = active && (f0 + u) < p.F;
         long long id = ok ? my[f0 + u] : 0;
         ok = ok && !(p.has_pad && id == p.pad);
         if (ok && (unsigned long long)id >= (unsigned long long)p.rows) { flag_bad_id(p.err, id); ok = false; }
-        if (ok && has_chunk) r[u].load(p.table + id * (long long)p.row_bytes + c * 16);
+        const char* rowp = p.table + id * (long long)p.row_bytes;
+        if (ok && has_chunk) r[u].load(rowp + c * 16);
         else r[u].zero();
+        wv[u] = 0.f;
+        if (p.w_extra && gl == 0 && ok) {
+          if (sizeof(Elem) == 4) wv[u] = __ldg(reinterpret_cast<const float*>(rowp) + p.k);
+          else wv[u] = __bfloat162float(reinterpret_cast<const __nv_bfloat16*>(rowp)[p.k]);
+        }
       }
 #pragma unroll
       for (int u = 0; u < U; ++u) {
@@ -540,12 +558,13 @@ __global__ void __launch_bounds__(256, 3) gather_fm_fwd_tile_kernel(const Gather
             S[i] += x;
             Q[i] += x * x;
           }
+          wsum += wv[u];
           if (p.flat && active) store_flat<Elem>(p, b, f0 + u, c * VEC, r[u].v);
         }
       }
     }
     if (want_fm) {
-      float second = 0.f, first = 0.f;
+      float second = 0.f, first = wsum;
 #pragma unroll
       for (int i = 0; i < VEC; ++i) {
         const int col = c * VEC + i;
@@ -717,6 +736,7 @@ static int fill_params(const char* fn, const etr_table* table, int k, int has_w,
   p->table = (const char*)table->d_data;
   p->rows = table->rows;
   p->row_bytes = table->stride * esize;
+  p->esize = esize;
   const int used = k + (has_w ? 1 : 0);
   p->nchunks = (used * esize + 15) / 16;
   p->k = k;
@@ -735,10 +755,30 @@ static int fill_params(const char* fn, const etr_table* table, int k, int has_w,
 }
 
 template <typename Elem, bool BWD>
-static int launch_gather(etr_ctx* ctx, const GatherParams& p, bool bag, cudaStream_t s) {
+static int launch_gather(etr_ctx* ctx, const GatherParams& p_in, bool bag, cudaStream_t s) {
+  GatherParams p = p_in;
+  auto lanes_for = [](int nchunks) {
+    int l = 1;
+    while (l < nchunks && l < 32) l <<= 1;
+    return l;
+  };
+  // single-hot + fused w in a chunk of its own behind a power-of-two number of embedding chunks:
+  // lane groups cover the embedding only (no idle lanes), lane 0 fetches w separately.  Only the
+  // tiled kernels implement this, so it is enabled only when they will be used.
+  {
+    const int emb_bytes = p.k * p.esize;
+    const int emb_chunks = emb_bytes / 16;
+    if (!bag && p.has_w && emb_bytes % 16 == 0 && emb_chunks >= 1 && emb_chunks <= 32 &&
+        (emb_chunks & (emb_chunks - 1)) == 0) {
+      const size_t smem = 2 * (size_t)(8 * (32 / emb_chunks)) * p.F * sizeof(long long);
+      if (smem <= 64 * 1024) {
+        p.w_extra = 1;
+        p.nchunks = emb_chunks;
+      }
+    }
+  }
   // lanes per row: smallest power of two covering the chunks, at most 32; then CPL
-  int lpr = 1;
-  while (lpr < p.nchunks && lpr < 32) lpr <<= 1;
+  const int lpr = lanes_for(p.nchunks);
   const int cpl = (p.nchunks + lpr - 1) / lpr;
   if (cpl > 4) {
     etr_set_error("gather: row of %d 16-byte chunks is wider than the kernels cover (2 KiB)", p.nchunks);

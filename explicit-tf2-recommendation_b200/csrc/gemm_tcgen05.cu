@@ -135,7 +135,7 @@ __device__ __forceinline__ float act_apply(float x, int act) {
 }
 
 template <int BLOCK_N, int STAGES>
-__global__ void __launch_bounds__(kThreads, 1)
+__global__ void __launch_bounds__(kThreads, 2)
 gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b, const EpiParams ep) {
   constexpr uint32_t A_BYTES = BLOCK_M * BLOCK_K * 2;        // 16 KiB
   constexpr uint32_t B_BYTES = BLOCK_N * BLOCK_K * 2;
@@ -206,11 +206,15 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
     }
   } else {
     // ===== epilogue warps 2..5 =====
+    // Each warp owns TMEM lanes [32q, 32q+32) = 32 output rows.  tcgen05.ld hands every lane
+    // 32 consecutive columns of ITS row; a 32x33 fp32 tile per warp (in the pipeline buffers,
+    // which are drained once tmem_full fires) transposes each 32x32 block so that every global
+    // load/store instruction touches ONE row's 32 consecutive elements (coalesced).
     const int q = warp & 3;                            // TMEM lane quarter this warp may read
     mbar_wait(smem_u32(tmem_full_bar), 0);
     fence_after();
-    const long long row = (long long)m_tile * BLOCK_M + q * 32 + lane;
-    const bool row_ok = row < ep.M;
+    float* T = reinterpret_cast<float*>(smem_a) + q * (32 * 33);
+    const long long row_base = (long long)m_tile * BLOCK_M + q * 32;
 #pragma unroll 1
     for (int c0 = 0; c0 < BLOCK_N; c0 += 32) {
       const long long col0 = (long long)n_tile * BLOCK_N + c0;
@@ -222,95 +226,63 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
 #pragma unroll
         for (int i = 0; i < 32; ++i) v[i] = 0u;
       }
-      if (!row_ok) continue;
       int ncol = (ep.N - col0) < 32 ? (int)(ep.N - col0) : 32;
       if (ncol > BLOCK_N - c0) ncol = BLOCK_N - c0;     // BLOCK_N = 240: the last chunk is 16 columns wide
+      const bool col_ok = lane < ncol;                  // this lane's column in the transposed accesses
+      float val[32];
+
+      // coalesced block read: rows row_base..+32, columns col0..col0+32 of a bf16 matrix, combined into
+      // dst (lane = row): MUL: dst[i] *= x ; ADD: dst[i] += x.  One 32-register array stays live.
+      auto combine_block = [&](const __nv_bfloat16* base, long long ld, float (&dst)[32], bool mul) {
+        __syncwarp();
+#pragma unroll
+        for (int r = 0; r < 32; ++r) {
+          const long long rr = row_base + r;
+          T[r * 33 + lane] = (rr < ep.M && col_ok) ? __bfloat162float(base[rr * ld + col0 + lane]) : 0.f;
+        }
+        __syncwarp();
+        if (mul) {
+#pragma unroll
+          for (int i = 0; i < 32; ++i) dst[i] *= T[lane * 33 + i];
+        } else {
+#pragma unroll
+          for (int i = 0; i < 32; ++i) dst[i] += T[lane * 33 + i];
+        }
+      };
+      // coalesced block store of val[] (lane = row) as fp32 or bf16
+      auto store_block = [&](void* base, long long ld, bool as_bf16, const float (&src)[32]) {
+        __syncwarp();
+#pragma unroll
+        for (int i = 0; i < 32; ++i) T[lane * 33 + i] = src[i];
+        __syncwarp();
+#pragma unroll
+        for (int r = 0; r < 32; ++r) {
+          const long long rr = row_base + r;
+          if (rr < ep.M && col_ok) {
+            const float x = T[r * 33 + lane];
+            if (as_bf16) reinterpret_cast<__nv_bfloat16*>(base)[rr * ld + col0 + lane] = __float2bfloat16_rn(x);
+            else reinterpret_cast<float*>(base)[rr * ld + col0 + lane] = x;
+          }
+        }
+      };
+
       if (ep.mode == EPI_PARTIAL) {
-        float* dst = ep.partial + ((long long)split * ep.M + row) * ep.N + col0;
+#pragma unroll
+        for (int i = 0; i < 32; ++i) val[i] = __uint_as_float(v[i]);
+        store_block(ep.partial + (long long)split * ep.M * ep.N, ep.N, false, val);
+      } else if (ep.mode == EPI_LINEAR) {
 #pragma unroll
         for (int i = 0; i < 32; ++i)
-          if (i < ncol) dst[i] = __uint_as_float(v[i]);
-      } else if (ep.mode == EPI_LINEAR) {
-        if (ep.c_bf16) {
-          __nv_bfloat16* dst = reinterpret_cast<__nv_bfloat16*>(ep.C) + row * ep.ldc + col0;
-          const bool vec = (ncol == 32) && ((reinterpret_cast<uintptr_t>(dst) & 15) == 0);
-          if (vec) {
+          val[i] = act_apply(__uint_as_float(v[i]) + ((ep.bias && i < ncol) ? ep.bias[col0 + i] : 0.f), ep.act);
+        store_block(ep.C, ep.ldc, ep.c_bf16 != 0, val);
+      } else {   // EPI_CROSS: u = acc + b ; out = x0 * u + xl   (x0 == NULL: out = u + xl)
 #pragma unroll
-            for (int i = 0; i < 32; i += 8) {
-              uint32_t w[4];
-#pragma unroll
-              for (int j = 0; j < 4; ++j) {
-                const float a = act_apply(__uint_as_float(v[i + 2 * j]) + (ep.bias ? ep.bias[col0 + i + 2 * j] : 0.f), ep.act);
-                const float b = act_apply(__uint_as_float(v[i + 2 * j + 1]) + (ep.bias ? ep.bias[col0 + i + 2 * j + 1] : 0.f), ep.act);
-                __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
-                w[j] = *reinterpret_cast<uint32_t*>(&h);
-              }
-              *reinterpret_cast<uint4*>(dst + i) = make_uint4(w[0], w[1], w[2], w[3]);
-            }
-          } else {
-#pragma unroll
-            for (int i = 0; i < 32; ++i)
-              if (i < ncol)
-                dst[i] = __float2bfloat16_rn(act_apply(__uint_as_float(v[i]) + (ep.bias ? ep.bias[col0 + i] : 0.f), ep.act));
-          }
-        } else {
-          float* dst = reinterpret_cast<float*>(ep.C) + row * ep.ldc + col0;
-          const bool vec = (ncol == 32) && ((reinterpret_cast<uintptr_t>(dst) & 15) == 0);
-          if (vec) {
-#pragma unroll
-            for (int i = 0; i < 32; i += 4) {
-              float4 o;
-              o.x = act_apply(__uint_as_float(v[i]) + (ep.bias ? ep.bias[col0 + i] : 0.f), ep.act);
-              o.y = act_apply(__uint_as_float(v[i + 1]) + (ep.bias ? ep.bias[col0 + i + 1] : 0.f), ep.act);
-              o.z = act_apply(__uint_as_float(v[i + 2]) + (ep.bias ? ep.bias[col0 + i + 2] : 0.f), ep.act);
-              o.w = act_apply(__uint_as_float(v[i + 3]) + (ep.bias ? ep.bias[col0 + i + 3] : 0.f), ep.act);
-              *reinterpret_cast<float4*>(dst + i) = o;
-            }
-          } else {
-#pragma unroll
-            for (int i = 0; i < 32; ++i)
-              if (i < ncol) dst[i] = act_apply(__uint_as_float(v[i]) + (ep.bias ? ep.bias[col0 + i] : 0.f), ep.act);
-          }
-        }
-      } else {   // EPI_CROSS: u = acc + b ; out = x0 * u + xl
-        const __nv_bfloat16* px0 = ep.x0 ? ep.x0 + row * ep.ldx + col0 : nullptr;
-        const __nv_bfloat16* pxl = ep.xl + row * ep.ldx + col0;
-        __nv_bfloat16* po = ep.out + row * ep.ldo + col0;
-        __nv_bfloat16* pu = ep.u ? ep.u + row * ep.ldu + col0 : nullptr;
-        const bool vec = (ncol == 32) && (((reinterpret_cast<uintptr_t>(px0) | reinterpret_cast<uintptr_t>(pxl) |
-                                            reinterpret_cast<uintptr_t>(po) | reinterpret_cast<uintptr_t>(pu)) & 15) == 0);
-        if (vec) {
-#pragma unroll
-          for (int i = 0; i < 32; i += 8) {
-            const uint4 a0 = ep.x0 ? *reinterpret_cast<const uint4*>(px0 + i) : make_uint4(0x3f803f80u, 0x3f803f80u, 0x3f803f80u, 0x3f803f80u);
-            const uint4 al = *reinterpret_cast<const uint4*>(pxl + i);
-            const uint32_t w0[4] = {a0.x, a0.y, a0.z, a0.w};
-            const uint32_t wl[4] = {al.x, al.y, al.z, al.w};
-            uint32_t wo[4], wu[4];
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {
-              const float2 f0 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&w0[j]));
-              const float2 fl = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&wl[j]));
-              const float ua = __uint_as_float(v[i + 2 * j]) + (ep.bias ? ep.bias[col0 + i + 2 * j] : 0.f);
-              const float ub = __uint_as_float(v[i + 2 * j + 1]) + (ep.bias ? ep.bias[col0 + i + 2 * j + 1] : 0.f);
-              __nv_bfloat162 ho = __floats2bfloat162_rn(f0.x * ua + fl.x, f0.y * ub + fl.y);
-              __nv_bfloat162 hu = __floats2bfloat162_rn(ua, ub);
-              wo[j] = *reinterpret_cast<uint32_t*>(&ho);
-              wu[j] = *reinterpret_cast<uint32_t*>(&hu);
-            }
-            *reinterpret_cast<uint4*>(po + i) = make_uint4(wo[0], wo[1], wo[2], wo[3]);
-            if (pu) *reinterpret_cast<uint4*>(pu + i) = make_uint4(wu[0], wu[1], wu[2], wu[3]);
-          }
-        } else {
-#pragma unroll
-          for (int i = 0; i < 32; ++i) {
-            if (i < ncol) {
-              const float uu = __uint_as_float(v[i]) + (ep.bias ? ep.bias[col0 + i] : 0.f);
-              po[i] = __float2bfloat16_rn((ep.x0 ? __bfloat162float(px0[i]) : 1.0f) * uu + __bfloat162float(pxl[i]));
-              if (pu) pu[i] = __float2bfloat16_rn(uu);
-            }
-          }
-        }
+        for (int i = 0; i < 32; ++i)
+          val[i] = __uint_as_float(v[i]) + ((ep.bias && i < ncol) ? ep.bias[col0 + i] : 0.f);
+        if (ep.u) store_block(ep.u, ep.ldu, true, val);
+        if (ep.x0) combine_block(ep.x0, ep.ldx, val, true);
+        combine_block(ep.xl, ep.ldx, val, false);
+        store_block(ep.out, ep.ldo, true, val);
       }
     }
   }

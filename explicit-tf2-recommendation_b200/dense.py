@@ -178,7 +178,8 @@ class MLPLayer:
         x = inputs if (isinstance(inputs, torch.Tensor) and inputs.dtype == torch.bfloat16 and
                        inputs.device == rt.device) else rt.to_device(inputs, torch.float32)
         assert x.dim() == 2 and x.shape[1] == self.front_pad + self.in_dim and x.stride(1) == 1
-        acts = [x]
+        acts = [x]          # layer outputs (fp32; acts[0] = the input): what the activation backward reads
+        ops = []            # the operand each layer's GEMM actually consumed (bf16 copy on the tensor-core path)
         for i, n_out in enumerate(self.units):
             k = self.params.full(f"{self.name}/kernel_{i}")
             b = self.params[f"{self.name}/bias_{i}"] if self.use_bias else None
@@ -186,17 +187,18 @@ class MLPLayer:
             if self._tc(i, x):
                 # tensor cores: Y = X K  ==  X [B,in] x (K^T)[out,in]^T ; K^T is a small bf16 copy made per call
                 xb = x if x.dtype == torch.bfloat16 else cast_bf16(rt, x)
-                acts[i] = xb
+                ops.append(xb)
                 kt = cast_bf16(rt, k, transpose=True)
                 gemm_bf16_tn(rt, xb, kt, y, x.shape[0], n_out, x.shape[1], bias=b, act=self.activation)
             else:
                 assert x.dtype == torch.float32
+                ops.append(x)
                 gemm_f32(rt, x, k, y, x.shape[0], n_out, x.shape[1], x.stride(0), n_out, n_out, bias=b,
                          act=self.activation)
             acts.append(y)
             x = y
         if training:
-            self._saved = acts
+            self._saved = (acts, ops)
         return x
 
     def _tc(self, i: int, x: torch.Tensor) -> bool:
@@ -210,12 +212,12 @@ class MLPLayer:
         dL/d(input) [B, front_pad+in_dim] (added into ``accumulate_into`` if given)."""
         assert self._saved is not None, "call with training=True first"
         rt = self.params.rt
-        acts = self._saved
+        acts, ops = self._saved
         d = dy
         assert d.is_contiguous()
         last = len(self.units) - 1
         for i in reversed(range(len(self.units))):
-            x, y = acts[i], acts[i + 1]
+            x, y = ops[i], acts[i + 1]
             B, n_in, n_out = x.shape[0], x.shape[1], self.units[i]
             if not (dy_is_preact and i == last):
                 check(rt.lib.etr_act_backward(rt.ctx, d.data_ptr(), y.data_ptr(), d.numel(),

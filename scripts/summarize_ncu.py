@@ -1,0 +1,70 @@
+#!/usr/bin/env python
+"""Turn the artefacts a GPU round brought back (gpurun_out/) into the tracked
+summaries under profiles/:  launches.csv -> per-kernel time shares of one eager
+step;  *.ncu-rep (ncu --set full) -> the key raw metrics per captured launch."""
+import csv
+import io
+import os
+import re
+import subprocess
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+OUT = os.path.join(ROOT, "gpurun_out")
+KEYS = ["gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum", "dram__throughput.avg.pct_of_peak_sustained_elapsed",
+        "gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed", "lts__t_bytes.sum", "sm__warps_active.avg.pct_of_peak_sustained_active",
+        "launch__registers_per_thread", "launch__grid_size", "launch__block_size", "launch__occupancy_limit_registers",
+        "sm__throughput.avg.pct_of_peak_sustained_elapsed", "sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active",
+        "sm__inst_executed_pipe_tensor.sum", "l1tex__t_sectors_pipe_lsu_mem_global_op_ld.sum", "smsp__warp_issue_stalled_long_scoreboard_per_warp_active.pct"]
+
+
+def launches(tag):
+    path = os.path.join(OUT, "launches.csv")
+    if not os.path.exists(path):
+        return
+    rows = list(csv.DictReader(l for l in open(path) if not l.startswith("==")))
+    names = [r["Kernel Name"] for r in rows]
+    starts = [i for i, n in enumerate(names) if "gather_fm_fwd" in n]
+    if len(starts) < 3:
+        return
+    a, b = starts[-3], starts[-2]
+    step = rows[a:b]
+    tot = sum(float(r["Metric Value"]) for r in step) / 1e3
+    with open(os.path.join(ROOT, "profiles", f"{tag}_launches_one_step.md"), "w") as fh:
+        fh.write(f"# {tag}: every kernel of ONE eager DeepFM (c2) train step, `ncu --metrics gpu__time_duration.sum "
+                 f"--clock-control none`\n\nCold-cache, serialised per-launch times: compare SHARES, not absolutes. "
+                 f"Sum = {tot:.1f} us over {len(step)} launches "
+                 f"(command: `python bench.py --steps 3 --warmup 3 --no-graph --no-cpu-baseline`).\n\n"
+                 f"| # | us | share | kernel |\n|---|---|---|---|\n")
+        for i, r in enumerate(step):
+            v = float(r["Metric Value"]) / 1e3
+            kname = r["Kernel Name"].split("(")[0][:110]
+            fh.write(f"| {i} | {v:.1f} | {100 * v / tot:.1f}% | `{kname}` |\n")
+
+
+def rep(name, tag):
+    path = os.path.join(OUT, name + ".ncu-rep")
+    if not os.path.exists(path):
+        return
+    raw = subprocess.run(["ncu", "-i", path, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+    rows = list(csv.reader(io.StringIO(raw)))
+    if len(rows) < 3:
+        return
+    hdr, units = rows[0], rows[1]
+    with open(os.path.join(ROOT, "profiles", f"{tag}_{name}.md"), "w") as fh:
+        fh.write(f"# {tag}: `ncu --set full --clock-control none --import-source on` -> {name}.ncu-rep\n\n")
+        for r in rows[2:]:
+            d = dict(zip(hdr, r))
+            fh.write(f"## {d.get('Kernel Name', '?')[:120]}  (launch id {d.get('ID')})\n\n| metric | value | unit |\n|---|---|---|\n")
+            for k in hdr:
+                if any(k == kk or k.startswith(kk) for kk in KEYS):
+                    fh.write(f"| {k} | {d[k]} | {units[hdr.index(k)]} |\n")
+            fh.write("\n")
+
+
+if __name__ == "__main__":
+    tag = sys.argv[1] if len(sys.argv) > 1 else "r01"
+    launches(tag)
+    for n in ("prof_gather_fwd", "prof_tcgemm", "prof_cross"):
+        rep(n, tag)
+    print(os.listdir(os.path.join(ROOT, "profiles")))
