@@ -178,7 +178,7 @@ __global__ void __launch_bounds__(256) gemm_skinny_rows_kernel(const GemmParams 
 // wgrad of the tail: C[M,N] = A^T B with M*N <= 256 and K = batch: each block
 // reduces a slab of kSkinnySlab batch rows (thread t owns output (t / N, t % N)),
 // slab partials are summed in fixed order by gemm_splitk_finish_kernel.
-constexpr int kSkinnySlab = 128;     // 65 536-row batch -> 512 CTAs
+constexpr int kSkinnySlab = 512;     // 65 536-row batch -> 128 CTAs, 128 partials per output
 __global__ void __launch_bounds__(256) gemm_skinny_wgrad_kernel(const GemmParams p) {
   __shared__ float As[32][65];     // [row in sub-slab][m]  (M <= 64)
   __shared__ float Bs[32][33];     // [row in sub-slab][n]  (N <= 32)
@@ -227,7 +227,7 @@ __global__ void __launch_bounds__(256) act_backward_kernel(float* dy, const floa
 
 // column sums: stage 1 -- each block sums a slab of rows for CB (power of two <= 32)
 // columns; the 256 threads are arranged as (256/CB) row lanes x CB columns.
-constexpr int kColRowsPerBlock = 2048;
+constexpr int kColRowsPerBlock = 512;
 __global__ void __launch_bounds__(256) colsum_stage1_kernel(const float* X, long long M, long long N, long long ldx,
                                                             int CB, float* partial /* [slabs, N] */) {
   __shared__ float sm[256];

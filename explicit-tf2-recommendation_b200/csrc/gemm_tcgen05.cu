@@ -213,7 +213,10 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
     const int q = warp & 3;                            // TMEM lane quarter this warp may read
     mbar_wait(smem_u32(tmem_full_bar), 0);
     fence_after();
-    float* T = reinterpret_cast<float*>(smem_a) + q * (32 * 33);
+    // per-warp tile, 32 rows x 36 floats: the 36-float stride keeps every 128-bit shared access
+    // 16-byte aligned and bank-conflict free in both directions (per quarter-warp)
+    constexpr int TS = 36;
+    float* T = reinterpret_cast<float*>(smem_a) + q * (32 * TS);
     const long long row_base = (long long)m_tile * BLOCK_M + q * 32;
 #pragma unroll 1
     for (int c0 = 0; c0 < BLOCK_N; c0 += 32) {
@@ -228,40 +231,105 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
       }
       int ncol = (ep.N - col0) < 32 ? (int)(ep.N - col0) : 32;
       if (ncol > BLOCK_N - c0) ncol = BLOCK_N - c0;     // BLOCK_N = 240: the last chunk is 16 columns wide
-      const bool col_ok = lane < ncol;                  // this lane's column in the transposed accesses
+      const bool col_ok = lane < ncol;                  // scalar fallback: this lane's column
+      const bool full = (ncol == 32);
       float val[32];
 
-      // coalesced block read: rows row_base..+32, columns col0..col0+32 of a bf16 matrix, combined into
-      // dst (lane = row): MUL: dst[i] *= x ; ADD: dst[i] += x.  One 32-register array stays live.
-      auto combine_block = [&](const __nv_bfloat16* base, long long ld, float (&dst)[32], bool mul) {
+      // own row (lane = row) <-> tile, 8 x 128-bit shared accesses
+      auto regs_to_tile = [&](const float (&src)[32]) {
         __syncwarp();
 #pragma unroll
-        for (int r = 0; r < 32; ++r) {
-          const long long rr = row_base + r;
-          T[r * 33 + lane] = (rr < ep.M && col_ok) ? __bfloat162float(base[rr * ld + col0 + lane]) : 0.f;
-        }
+        for (int i = 0; i < 32; i += 4)
+          *reinterpret_cast<float4*>(&T[lane * TS + i]) = make_float4(src[i], src[i + 1], src[i + 2], src[i + 3]);
         __syncwarp();
-        if (mul) {
+      };
+      // bf16 matrix block -> tile: 4 lanes x 16 bytes cover one row's 32 columns, 8 rows per instruction
+      auto bf16_block_to_tile = [&](const __nv_bfloat16* base, long long ld, bool vec) {
+        __syncwarp();
+        if (vec) {
+          const int g4 = lane & 3, r4 = lane >> 2;
 #pragma unroll
-          for (int i = 0; i < 32; ++i) dst[i] *= T[lane * 33 + i];
+          for (int j = 0; j < 4; ++j) {
+            const int r = r4 + 8 * j;
+            const long long rr = row_base + r;
+            uint4 w = make_uint4(0u, 0u, 0u, 0u);
+            if (rr < ep.M) w = *reinterpret_cast<const uint4*>(base + rr * ld + col0 + 8 * g4);
+            const uint32_t ww[4] = {w.x, w.y, w.z, w.w};
+            float f[8];
+#pragma unroll
+            for (int t = 0; t < 4; ++t) {
+              const float2 x = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&ww[t]));
+              f[2 * t] = x.x; f[2 * t + 1] = x.y;
+            }
+            *reinterpret_cast<float4*>(&T[r * TS + 8 * g4]) = make_float4(f[0], f[1], f[2], f[3]);
+            *reinterpret_cast<float4*>(&T[r * TS + 8 * g4 + 4]) = make_float4(f[4], f[5], f[6], f[7]);
+          }
         } else {
 #pragma unroll
-          for (int i = 0; i < 32; ++i) dst[i] += T[lane * 33 + i];
+          for (int r = 0; r < 32; ++r) {
+            const long long rr = row_base + r;
+            T[r * TS + lane] = (rr < ep.M && col_ok) ? __bfloat162float(base[rr * ld + col0 + lane]) : 0.f;
+          }
+        }
+        __syncwarp();
+      };
+      // dst (lane = row) combined with a bf16 matrix block: MUL: dst[i] *= x ; else dst[i] += x
+      auto combine_block = [&](const __nv_bfloat16* base, long long ld, float (&dst)[32], bool mul) {
+        const bool vec = full && ((ld & 7) == 0) && ((reinterpret_cast<uintptr_t>(base + col0) & 15) == 0);
+        bf16_block_to_tile(base, ld, vec);
+#pragma unroll
+        for (int i = 0; i < 32; i += 4) {
+          const float4 t = *reinterpret_cast<const float4*>(&T[lane * TS + i]);
+          if (mul) { dst[i] *= t.x; dst[i + 1] *= t.y; dst[i + 2] *= t.z; dst[i + 3] *= t.w; }
+          else { dst[i] += t.x; dst[i + 1] += t.y; dst[i + 2] += t.z; dst[i + 3] += t.w; }
         }
       };
-      // coalesced block store of val[] (lane = row) as fp32 or bf16
+      // coalesced block store of src[] (lane = row) as fp32 or bf16
       auto store_block = [&](void* base, long long ld, bool as_bf16, const float (&src)[32]) {
-        __syncwarp();
+        regs_to_tile(src);
+        if (as_bf16) {
+          __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(base);
+          const bool vec = full && ((ld & 7) == 0) && ((reinterpret_cast<uintptr_t>(o + col0) & 15) == 0);
+          if (vec) {                                   // 4 lanes x 16 bytes per row, 8 rows per instruction
+            const int g4 = lane & 3, r4 = lane >> 2;
 #pragma unroll
-        for (int i = 0; i < 32; ++i) T[lane * 33 + i] = src[i];
-        __syncwarp();
+            for (int j = 0; j < 4; ++j) {
+              const int r = r4 + 8 * j;
+              const long long rr = row_base + r;
+              const float4 a = *reinterpret_cast<const float4*>(&T[r * TS + 8 * g4]);
+              const float4 b = *reinterpret_cast<const float4*>(&T[r * TS + 8 * g4 + 4]);
+              __nv_bfloat162 h0 = __floats2bfloat162_rn(a.x, a.y), h1 = __floats2bfloat162_rn(a.z, a.w);
+              __nv_bfloat162 h2 = __floats2bfloat162_rn(b.x, b.y), h3 = __floats2bfloat162_rn(b.z, b.w);
+              if (rr < ep.M)
+                *reinterpret_cast<uint4*>(o + rr * ld + col0 + 8 * g4) =
+                    make_uint4(*reinterpret_cast<uint32_t*>(&h0), *reinterpret_cast<uint32_t*>(&h1),
+                               *reinterpret_cast<uint32_t*>(&h2), *reinterpret_cast<uint32_t*>(&h3));
+            }
+            return;
+          }
 #pragma unroll
-        for (int r = 0; r < 32; ++r) {
-          const long long rr = row_base + r;
-          if (rr < ep.M && col_ok) {
-            const float x = T[r * 33 + lane];
-            if (as_bf16) reinterpret_cast<__nv_bfloat16*>(base)[rr * ld + col0 + lane] = __float2bfloat16_rn(x);
-            else reinterpret_cast<float*>(base)[rr * ld + col0 + lane] = x;
+          for (int r = 0; r < 32; ++r) {
+            const long long rr = row_base + r;
+            if (rr < ep.M && col_ok) o[rr * ld + col0 + lane] = __float2bfloat16_rn(T[r * TS + lane]);
+          }
+        } else {
+          float* o = reinterpret_cast<float*>(base);
+          const bool vec = full && ((ld & 3) == 0) && ((reinterpret_cast<uintptr_t>(o + col0) & 15) == 0);
+          if (vec) {                                   // 8 lanes x 16 bytes per row, 4 rows per instruction
+            const int g8 = lane & 7, r8 = lane >> 3;
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              const int r = r8 + 4 * j;
+              const long long rr = row_base + r;
+              const float4 a = *reinterpret_cast<const float4*>(&T[r * TS + 4 * g8]);
+              if (rr < ep.M) *reinterpret_cast<float4*>(o + rr * ld + col0 + 4 * g8) = a;
+            }
+            return;
+          }
+#pragma unroll
+          for (int r = 0; r < 32; ++r) {
+            const long long rr = row_base + r;
+            if (rr < ep.M && col_ok) o[rr * ld + col0 + lane] = T[r * TS + lane];
           }
         }
       };

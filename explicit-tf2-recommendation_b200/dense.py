@@ -119,7 +119,7 @@ class MLPLayer:
     reference either and is ignored here."""
 
     # layers whose input is at least this wide run on the tensor cores when precision == "bf16"
-    TC_MIN_IN = 64
+    TC_MIN_IN = 129      # narrower layers take the exact fp32 thread-per-row kernels (K <= 128)
 
     def __init__(self, units, activation=None, use_bias=True, is_batch_norm=False, is_dropput=0,
                  kernel_initializer="glorot_uniform", bias_initializer="zeros", name="mlp", precision="fp32",
