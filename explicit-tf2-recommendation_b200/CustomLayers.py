@@ -22,7 +22,7 @@ import torch
 from . import _lib
 from ._lib import check
 from .dense import DenseLayer, DenseParams, MLPLayer, glorot_uniform, random_normal  # noqa: F401
-from .runtime import (EmbeddingTable, IdsBatch, Runtime, SparseGrad, SparsePlan, bce_forward_backward,
+from .runtime import (EmbeddingTable, FusedFMGrad, IdsBatch, Runtime, SparseGrad, SparsePlan, bce_forward_backward,
                       embedding_gather, gather_fm_backward, gather_fm_forward, lr_t, _p)
 
 _DT = {"float32": torch.float32, "bfloat16": torch.bfloat16, torch.float32: torch.float32,
@@ -48,6 +48,7 @@ class _Layer:
         self.pad_id = kwargs.pop("pad_id", None)
         self.pooling = kwargs.pop("pooling", "sum")
         self.check_ids = bool(kwargs.pop("check_ids", True))
+        self.fused_apply = bool(kwargs.pop("fused_apply", True))     # FM family: fused backward+reduce+Adam
         self.name = kwargs.pop("name", type(self).__name__)
         # row-sharded tables: shard=True (world/rank from torch.distributed) or shard=(world, rank)
         shard = kwargs.pop("shard", None)
@@ -190,11 +191,18 @@ class FMRankingLayer(_Layer):
         ids = self._ids(inputs, self.feature_names)
         prob = self.rt.empty((ids.B, 1))
         tab, vids, route = self._lookup(ids)
-        gather_fm_forward(tab, self.embedding_dims, True, vids, bias=self.bias, prob=prob)
+        sumv = self._sumv_buffer(training, tab, vids)
+        gather_fm_forward(tab, self.embedding_dims, True, vids, bias=self.bias, prob=prob, sumv=sumv)
         if training:
-            self._ctx = {"ids": vids, "table": tab, "route": route}
+            self._ctx = {"ids": vids, "table": tab, "route": route, "sumv": sumv}
         self._finish(training)
         return {"output": prob}
+
+    def _sumv_buffer(self, training: bool, tab, vids) -> Optional[torch.Tensor]:
+        """S = sum_f v_f [B,k], saved for the fused backward+apply (single-hot, fp32, unsharded)."""
+        if training and self.shard is None and self.fused_apply and FusedFMGrad.eligible(tab, vids, self.embedding_dims):
+            return self.rt.empty((vids.B, self.embedding_dims))
+        return None
 
     def _lookup(self, ids: IdsBatch):
         """(table, ids, route): the local table, or -- row-sharded -- the rows fetched over
@@ -213,9 +221,11 @@ class FMRankingLayer(_Layer):
         ``self.params.grad``; the table gradient is returned as a SparseGrad."""
         ids = self._ctx["ids"]
         dl = dlogit.reshape(-1)
-        bag = gather_fm_backward(self._ctx["table"], self.embedding_dims, True, ids, dlogit=dl)
         check(self.rt.lib.etr_colsum_f32(self.rt.ctx, dl.data_ptr(), ids.B, 1, 1, self.params.g("bias").data_ptr(),
                                          self.rt.stream))
+        if self._ctx.get("sumv") is not None:           # fused backward + segment reduction + Adam
+            return [FusedFMGrad(self.table, ids, self.embedding_dims, dl, self._ctx["sumv"])]
+        bag = gather_fm_backward(self._ctx["table"], self.embedding_dims, True, ids, dlogit=dl)
         return [self._table_grad(bag)]
 
 
@@ -266,13 +276,15 @@ class DeepFMRankingLayer(FMRankingLayer):
         cont = self._cont(inputs, self.continuous_features) if C_ else None
         fm_logit = rt.empty((ids.B,))
         tab, vids, route = self._lookup(ids)
-        gather_fm_forward(tab, k, True, vids, bias=self.bias, logit=fm_logit, flat=x, flat_col0=col0, cont=cont)
+        sumv = self._sumv_buffer(training, tab, vids)
+        gather_fm_forward(tab, k, True, vids, bias=self.bias, logit=fm_logit, sumv=sumv, flat=x, flat_col0=col0,
+                          cont=cont)
         dnn = self.MLP_layer2(self.MLP_layer1(x, training=training), training=training)      # [B,1]
         prob = rt.empty((ids.B, 1))
         check(rt.lib.etr_add_sigmoid(rt.ctx, fm_logit.data_ptr(), dnn.data_ptr(), ids.B, None, prob.data_ptr(),
                                      rt.stream))
         if training:
-            self._ctx = {"ids": vids, "table": tab, "route": route}
+            self._ctx = {"ids": vids, "table": tab, "route": route, "sumv": sumv}
         self._finish(training)
         return {"output": prob}
 
@@ -284,9 +296,11 @@ class DeepFMRankingLayer(FMRankingLayer):
         d_dnn = dl.clone().reshape(-1, 1)                    # d(fm+dnn)/d dnn = 1
         dh = self.MLP_layer2.backward(d_dnn)
         dx = self.MLP_layer1.backward(dh)                    # [B, pad + C + F*k]
+        check(rt.lib.etr_colsum_f32(rt.ctx, dl.data_ptr(), ids.B, 1, 1, self.params.g("bias").data_ptr(), rt.stream))
+        if self._ctx.get("sumv") is not None and col0 % 4 == 0 and dx.stride(0) % 4 == 0:
+            return [FusedFMGrad(self.table, ids, self.embedding_dims, dl, self._ctx["sumv"], dx, col0)]
         bag = gather_fm_backward(self._ctx["table"], self.embedding_dims, True, ids, dlogit=dl, dflat=dx,
                                  flat_col0=col0)
-        check(rt.lib.etr_colsum_f32(rt.ctx, dl.data_ptr(), ids.B, 1, 1, self.params.g("bias").data_ptr(), rt.stream))
         return [self._table_grad(bag)]
 
 
@@ -964,6 +978,9 @@ class Trainer:
         self.layer.params.adam_step(0.0, d_lr, self.b1, self.b2, self.eps)
         plans: Dict[tuple, SparsePlan] = {}
         for g in grads:
+            if isinstance(g, FusedFMGrad) and self.mode == _lib.ADAM_ROWWISE:
+                g.apply(d_lr, self.b1, self.b2, self.eps)
+                continue
             key = (id(g.ids), g.table.rows)
             g.reduce(plans.get(key))
             plans[key] = g.plan

@@ -1,0 +1,318 @@
+// K2+K8 fused for the FM family (single-hot ids, fp32 table with the fused w column):
+// backward of the gather/FM kernel + sorted-ID segment reduction + row-wise Adam in ONE pass
+// over the sorted occurrence list, without ever materialising per-occurrence (or per-bag)
+// gradient rows.
+//
+// For a table row r with occurrences (b,f) in its run (SURVEY a', FM / DeepFM):
+//   dL/dv_r[c] = sum_(b,f) [ g_b (S_b[c] - v_r[c]) + dflat[b, f*k + c] ]
+//              = sum g_b S_b[c]  +  sum dflat[b, f*k+c]  -  v_r[c] * sum g_b
+//   dL/dw_r    = sum g_b
+// so a run needs, per occurrence, only g_b (4 B), S_b (k floats, saved by the forward kernel)
+// and the MLP's input gradient slice -- all L2-resident (B*k*4 = 4 MB, B*F*k*2 = 56 MB at c2) --
+// and the row itself once, which the Adam update reads anyway.  Replaces
+// tape.gradient + Keras apply_gradients on IndexedSlices (2.FM/ModelManager.py:176-178).
+//
+// Runs <= 64 occurrences: one lane group (k/4 lanes, one float4 column chunk per lane), fully
+// fused.  Longer runs (hot ids): cut into 1024-occurrence chunks, each reduced by a whole CTA
+// into a partial row [P_0..P_{k-1}, sum_g] (fixed order), combined in chunk order and then
+// updated -- deterministic, no atomics on hot rows.
+#include "etr_common.cuh"
+
+namespace etr {
+
+constexpr int kFusedShortRun = 64;
+constexpr int kFusedChunk = 1024;
+
+struct FusedLong { int u; int base; int nchunks; int pad; };
+
+struct FusedParams {
+  float* table; float* m; float* v; int stride; int k;
+  int F; unsigned long long magic; int shift;       // b = (bag * magic) >> shift  ==  bag / F
+  const int* sorted_bag; const int* seg_start; const long long* unique_ids; const int* n_unique;
+  const float* dlogit; const float* sumv;
+  const void* dflat; int flat_bf16; long long flat_ld; int flat_col0;
+  float lr_t; const float* d_lr_t; float b1, b2, eps;
+  int apply;                  // 1: Adam update; 0: only export the gradient rows
+  float* unique_grad;         // optional [n_unique, stride]
+  int* counters; FusedLong* long_runs; int2* items; float* partials; int max_long, max_items;
+};
+
+__device__ __forceinline__ void bag_to_bf(const FusedParams& p, int bag, int& b, int& f) {
+  b = (int)(((unsigned long long)(unsigned)bag * p.magic) >> p.shift);
+  f = bag - b * p.F;
+}
+
+// accumulate occurrences [i0, i1) into acc (this lane's float4 column chunk) and sum_g
+__device__ __forceinline__ void fused_accumulate(const FusedParams& p, int i0, int i1, int gl, float4& acc, float& sum_g) {
+  int i = i0;
+  for (; i + 4 <= i1; i += 4) {
+    int b[4], f[4];
+    float g[4];
+    float4 s[4], d[4];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) bag_to_bf(p, __ldg(p.sorted_bag + i + q), b[q], f[q]);
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      g[q] = __ldg(p.dlogit + b[q]);
+      s[q] = *reinterpret_cast<const float4*>(p.sumv + (long long)b[q] * p.k + gl * 4);
+      d[q] = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (p.dflat) {
+        const long long e0 = (long long)b[q] * p.flat_ld + p.flat_col0 + (long long)f[q] * p.k + gl * 4;
+        if (p.flat_bf16) {
+          const uint2 w = *reinterpret_cast<const uint2*>(reinterpret_cast<const __nv_bfloat16*>(p.dflat) + e0);
+          const float2 lo = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&w.x));
+          const float2 hi = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&w.y));
+          d[q] = make_float4(lo.x, lo.y, hi.x, hi.y);
+        } else {
+          d[q] = *reinterpret_cast<const float4*>(reinterpret_cast<const float*>(p.dflat) + e0);
+        }
+      }
+    }
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      acc.x += g[q] * s[q].x + d[q].x; acc.y += g[q] * s[q].y + d[q].y;
+      acc.z += g[q] * s[q].z + d[q].z; acc.w += g[q] * s[q].w + d[q].w;
+      sum_g += g[q];
+    }
+  }
+  for (; i < i1; ++i) {
+    int b, f;
+    bag_to_bf(p, __ldg(p.sorted_bag + i), b, f);
+    const float g = __ldg(p.dlogit + b);
+    const float4 s = *reinterpret_cast<const float4*>(p.sumv + (long long)b * p.k + gl * 4);
+    float4 d = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (p.dflat) {
+      const long long e0 = (long long)b * p.flat_ld + p.flat_col0 + (long long)f * p.k + gl * 4;
+      if (p.flat_bf16) {
+        const uint2 w = *reinterpret_cast<const uint2*>(reinterpret_cast<const __nv_bfloat16*>(p.dflat) + e0);
+        const float2 lo = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&w.x));
+        const float2 hi = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&w.y));
+        d = make_float4(lo.x, lo.y, hi.x, hi.y);
+      } else {
+        d = *reinterpret_cast<const float4*>(reinterpret_cast<const float*>(p.dflat) + e0);
+      }
+    }
+    acc.x += g * s.x + d.x; acc.y += g * s.y + d.y; acc.z += g * s.z + d.z; acc.w += g * s.w + d.w;
+    sum_g += g;
+  }
+}
+
+__device__ __forceinline__ void adam_update4(float4& var, float4& m, float4& v, const float4 g, float lr_t, float b1,
+                                             float b2, float eps) {
+  float* pv = &var.x; float* pm = &m.x; float* pvv = &v.x; const float* pg = &g.x;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    pm[i] = b1 * pm[i] + (1.0f - b1) * pg[i];
+    pvv[i] = b2 * pvv[i] + (1.0f - b2) * pg[i] * pg[i];
+    pv[i] = pv[i] - lr_t * pm[i] / (sqrtf(pvv[i]) + eps);
+  }
+}
+
+// finish one row: grad = P - v_r * sum_g (embedding chunk gl), w chunk by lane 0; Adam and/or export
+__device__ __forceinline__ void fused_finish_row(const FusedParams& p, long long u, int gl, float4 P, float sum_g, float lr_t) {
+  const long long row = p.unique_ids[u];
+  float* prow = p.table + row * p.stride;
+  float4 var = *reinterpret_cast<const float4*>(prow + gl * 4);
+  const float4 g = make_float4(P.x - var.x * sum_g, P.y - var.y * sum_g, P.z - var.z * sum_g, P.w - var.w * sum_g);
+  if (p.unique_grad) *reinterpret_cast<float4*>(p.unique_grad + u * p.stride + gl * 4) = g;
+  if (p.apply) {
+    float4* pm = reinterpret_cast<float4*>(p.m + row * p.stride + gl * 4);
+    float4* pv = reinterpret_cast<float4*>(p.v + row * p.stride + gl * 4);
+    float4 m = *pm, v = *pv;
+    adam_update4(var, m, v, g, lr_t, p.b1, p.b2, p.eps);
+    *reinterpret_cast<float4*>(prow + gl * 4) = var; *pm = m; *pv = v;
+  }
+  if (gl == 0) {
+    // chunks behind the embedding: [w, 0, 0, 0] (+ zero padding chunks)
+    for (int c = p.k; c < p.stride; c += 4) {
+      const float4 gw = make_float4(c == p.k ? sum_g : 0.f, 0.f, 0.f, 0.f);
+      if (p.unique_grad) *reinterpret_cast<float4*>(p.unique_grad + u * p.stride + c) = gw;
+      if (p.apply && c == p.k) {
+        float4 wv = *reinterpret_cast<const float4*>(prow + c);
+        float4* pm = reinterpret_cast<float4*>(p.m + row * p.stride + c);
+        float4* pv = reinterpret_cast<float4*>(p.v + row * p.stride + c);
+        float4 m = *pm, v = *pv;
+        adam_update4(wv, m, v, gw, lr_t, p.b1, p.b2, p.eps);
+        *reinterpret_cast<float4*>(prow + c) = wv; *pm = m; *pv = v;
+      }
+    }
+  }
+}
+
+template <int LPR>
+__global__ void __launch_bounds__(256) fm_fused_short_kernel(const FusedParams p) {
+  constexpr int GPW = 32 / LPR;
+  const int lane = threadIdx.x & 31;
+  const int gl = lane % LPR, g = lane / LPR;
+  const int n_unique = *p.n_unique;
+  const float lr_t = p.d_lr_t ? *p.d_lr_t : p.lr_t;
+  const long long group_global = ((long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5)) * GPW + g;
+  const long long ngroups = (long long)gridDim.x * (blockDim.x >> 5) * GPW;
+  for (long long u = group_global; u < n_unique; u += ngroups) {
+    const int s0 = p.seg_start[u], s1 = p.seg_start[u + 1];
+    const int len = s1 - s0;
+    if (len > kFusedShortRun) {
+      if (gl == 0) {
+        const int nch = (len + kFusedChunk - 1) / kFusedChunk;
+        const int slot = atomicAdd(&p.counters[0], 1);
+        const int base = atomicAdd(&p.counters[1], nch);
+        if (slot < p.max_long && base + nch <= p.max_items) {
+          p.long_runs[slot] = FusedLong{(int)u, base, nch, 0};
+          for (int c = 0; c < nch; ++c) p.items[base + c] = make_int2(slot, c);
+        }
+      }
+      continue;
+    }
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    float sum_g = 0.f;
+    fused_accumulate(p, s0, s1, gl, acc, sum_g);
+    fused_finish_row(p, u, gl, acc, sum_g, lr_t);
+  }
+}
+
+// one CTA per chunk item: (256/LPR) lane groups each reduce a contiguous sub-range in order
+template <int LPR>
+__global__ void __launch_bounds__(256) fm_fused_chunk_kernel(const FusedParams p) {
+  constexpr int NG = 256 / LPR;
+  __shared__ float4 sm[NG][LPR];
+  __shared__ float sg[NG];
+  const int gl = threadIdx.x % LPR, g = threadIdx.x / LPR;
+  int n_items = p.counters[1];
+  if (n_items > p.max_items) n_items = p.max_items;
+  for (int it = blockIdx.x; it < n_items; it += gridDim.x) {
+    const int2 item = p.items[it];
+    const FusedLong lr = p.long_runs[item.x];
+    const int s0 = p.seg_start[lr.u] + item.y * kFusedChunk;
+    int s1 = p.seg_start[lr.u + 1];
+    if (s1 > s0 + kFusedChunk) s1 = s0 + kFusedChunk;
+    const int per = (s1 - s0 + NG - 1) / NG;
+    int a = s0 + g * per, b = a + per;
+    if (a > s1) a = s1;
+    if (b > s1) b = s1;
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    float sum_g = 0.f;
+    fused_accumulate(p, a, b, gl, acc, sum_g);
+    sm[g][gl] = acc;
+    if (gl == 0) sg[g] = sum_g;
+    __syncthreads();
+    if (g == 0) {
+      float4 t = sm[0][gl];
+      float ts = sg[0];
+      for (int q = 1; q < NG; ++q) {
+        const float4 r = sm[q][gl];
+        t.x += r.x; t.y += r.y; t.z += r.z; t.w += r.w;
+        ts += sg[q];
+      }
+      float* dst = p.partials + (long long)it * p.stride;
+      *reinterpret_cast<float4*>(dst + gl * 4) = t;
+      if (gl == 0) dst[p.k] = ts;
+    }
+    __syncthreads();
+  }
+}
+
+template <int LPR>
+__global__ void __launch_bounds__(256) fm_fused_combine_kernel(const FusedParams p) {
+  constexpr int GPW = 32 / LPR;
+  const int lane = threadIdx.x & 31;
+  const int gl = lane % LPR, g = lane / LPR;
+  const float lr_t = p.d_lr_t ? *p.d_lr_t : p.lr_t;
+  int n_long = p.counters[0];
+  if (n_long > p.max_long) n_long = p.max_long;
+  const long long group_global = ((long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5)) * GPW + g;
+  const long long ngroups = (long long)gridDim.x * (blockDim.x >> 5) * GPW;
+  for (long long r = group_global; r < n_long; r += ngroups) {
+    const FusedLong lr = p.long_runs[r];
+    float4 t = make_float4(0.f, 0.f, 0.f, 0.f);
+    float ts = 0.f;
+    for (int c = 0; c < lr.nchunks; ++c) {
+      const float* src = p.partials + (long long)(lr.base + c) * p.stride;
+      const float4 x = *reinterpret_cast<const float4*>(src + gl * 4);
+      t.x += x.x; t.y += x.y; t.z += x.z; t.w += x.w;
+      ts += src[p.k];
+    }
+    fused_finish_row(p, lr.u, gl, t, ts, lr_t);
+  }
+}
+
+}  // namespace etr
+
+using namespace etr;
+
+extern "C" {
+
+int etr_fm_fused_backward_apply(etr_ctx* ctx, const etr_table* table, float* d_m, float* d_v, int32_t k, int32_t fields,
+                                int64_t batch, const int32_t* d_sorted_bag, const int32_t* d_seg_start,
+                                const int64_t* d_unique_ids, const int32_t* d_n_unique, int64_t n_slots,
+                                const float* d_dlogit, const float* d_sumv, const void* d_dflat, int32_t flat_dtype,
+                                int64_t flat_ld, int32_t flat_col0, float lr_t, const float* d_lr_t, float beta1,
+                                float beta2, float eps, int32_t apply, float* d_unique_grad, void* stream) {
+  ETR_CHECK_ARG(ctx && table && table->d_data && d_sorted_bag && d_seg_start && d_unique_ids && d_n_unique && d_dlogit &&
+                    d_sumv, "NULL argument");
+  ETR_CHECK_ARG(!apply || (d_m && d_v), "Adam slots missing");
+  ETR_CHECK_ARG(apply || d_unique_grad, "nothing to do: apply == 0 and no gradient output");
+  if (table->dtype != ETR_F32) { etr_set_error("etr_fm_fused_backward_apply: fp32 tables only"); return ETR_EUNSUPPORTED; }
+  const int lpr = k / 4;
+  if (k % 4 != 0 || lpr < 1 || lpr > 32 || (lpr & (lpr - 1)) != 0 || table->width != k + 1 || table->stride % 4 != 0 ||
+      table->stride < k + 4) {
+    etr_set_error("etr_fm_fused_backward_apply: needs k in {4,8,16,32,64,128} and a [V, k+1] table with the w column "
+                  "in its own 16-byte chunk (k=%d width=%d stride=%d)", k, table->width, table->stride);
+    return ETR_EUNSUPPORTED;
+  }
+  ETR_CHECK_ARG(fields > 0 && batch >= 0 && (long long)fields * batch == n_slots, "n_slots must equal batch*fields (single-hot)");
+  if (d_dflat) {
+    const int osz = flat_dtype == ETR_BF16 ? 2 : 4;
+    ETR_CHECK_ARG((flat_col0 * osz) % (4 * osz) == 0 && (flat_ld * osz) % (4 * osz) == 0 && (k * osz) % (4 * osz) == 0 &&
+                      ((uintptr_t)d_dflat % (4 * osz)) == 0, "dflat must be aligned for 4-element vector loads");
+  }
+  if (n_slots == 0) return ETR_OK;
+  cudaStream_t s = (cudaStream_t)stream;
+  FusedParams p;
+  memset(&p, 0, sizeof(p));
+  p.table = (float*)table->d_data; p.m = d_m; p.v = d_v; p.stride = table->stride; p.k = k; p.F = fields;
+  // exact division of a 31-bit bag index by F: shift = 32 + ceil(log2 F), magic = ceil(2^shift / F)
+  int lg = 0;
+  while ((1 << lg) < fields) ++lg;
+  p.shift = 32 + lg;
+  p.magic = ((1ull << p.shift) + (unsigned long long)fields - 1) / (unsigned long long)fields;
+  p.sorted_bag = d_sorted_bag; p.seg_start = d_seg_start; p.unique_ids = (const long long*)d_unique_ids; p.n_unique = d_n_unique;
+  p.dlogit = d_dlogit; p.sumv = d_sumv; p.dflat = d_dflat; p.flat_bf16 = flat_dtype == ETR_BF16; p.flat_ld = flat_ld;
+  p.flat_col0 = flat_col0; p.lr_t = lr_t; p.d_lr_t = d_lr_t; p.b1 = beta1; p.b2 = beta2; p.eps = eps; p.apply = apply;
+  p.unique_grad = d_unique_grad;
+  p.max_long = (int)(n_slots / kFusedShortRun + 1);
+  p.max_items = (int)(n_slots / kFusedChunk + n_slots / kFusedShortRun + 2);
+  auto a256 = [](size_t x) { return (x + 255) & ~(size_t)255; };
+  const size_t b_cnt = 256, b_runs = a256(sizeof(FusedLong) * (size_t)p.max_long), b_items = a256(sizeof(int2) * (size_t)p.max_items),
+               b_part = a256(sizeof(float) * (size_t)p.max_items * p.stride);
+  int st = etr_ws_reserve(ctx, b_cnt + b_runs + b_items + b_part);
+  if (st != ETR_OK) return st;
+  char* ws = (char*)ctx->d_ws;
+  p.counters = (int*)ws;
+  p.long_runs = (FusedLong*)(ws + b_cnt);
+  p.items = (int2*)(ws + b_cnt + b_runs);
+  p.partials = (float*)(ws + b_cnt + b_runs + b_items);
+  ETR_CUDA(cudaMemsetAsync(p.counters, 0, 2 * sizeof(int), s));
+  const int gshort = grid_for(n_slots, 8 * (32 / lpr), ctx->sm_count, 8);
+  const int gchunk = ctx->sm_count * 4;
+#define ETR_FUSED(LPR)                                                      \
+  do {                                                                      \
+    fm_fused_short_kernel<LPR><<<gshort, 256, 0, s>>>(p);                   \
+    ETR_LAUNCH_CHECK(ctx);                                                  \
+    fm_fused_chunk_kernel<LPR><<<gchunk, 256, 0, s>>>(p);                   \
+    ETR_LAUNCH_CHECK(ctx);                                                  \
+    fm_fused_combine_kernel<LPR><<<ctx->sm_count, 256, 0, s>>>(p);          \
+    ETR_LAUNCH_CHECK(ctx);                                                  \
+  } while (0)
+  switch (lpr) {
+    case 1: ETR_FUSED(1); break;
+    case 2: ETR_FUSED(2); break;
+    case 4: ETR_FUSED(4); break;
+    case 8: ETR_FUSED(8); break;
+    case 16: ETR_FUSED(16); break;
+    default: ETR_FUSED(32); break;
+  }
+#undef ETR_FUSED
+  return ETR_OK;
+}
+
+}  // extern "C"

@@ -277,6 +277,55 @@ class SparseGrad:
         return self.plan.unique_ids[:u], self.unique_grad[:u, : self.table.width]
 
 
+class FusedFMGrad:
+    """Table gradient of the FM family in its un-materialised form: the plan's runs plus
+    (dlogit, sum_v, dflat).  ``apply`` runs backward + segment reduction + Adam in one pass
+    (etr_fm_fused_backward_apply); ``indexed_slices`` exports the deduplicated rows."""
+
+    def __init__(self, table: EmbeddingTable, ids: IdsBatch, k: int, dlogit: torch.Tensor, sumv: torch.Tensor,
+                 dflat: Optional[torch.Tensor] = None, flat_col0: int = 0):
+        self.table, self.ids, self.k = table, ids, k
+        self.dlogit, self.sumv, self.dflat, self.flat_col0 = dlogit, sumv, dflat, flat_col0
+        self.plan: Optional[SparsePlan] = None
+        self.unique_grad: Optional[torch.Tensor] = None
+
+    @staticmethod
+    def eligible(table: EmbeddingTable, ids: IdsBatch, k: int) -> bool:
+        lpr = k // 4
+        return (table.dtype == torch.float32 and not ids.is_bag and ids.pad_id is None and k % 4 == 0 and
+                1 <= lpr <= 32 and (lpr & (lpr - 1)) == 0 and table.width == k + 1)
+
+    def _run(self, apply: bool, lr_t: float, d_lr_t, b1: float, b2: float, eps: float, out):
+        rt, t = self.table.rt, self.table.desc()
+        if self.plan is None:
+            self.plan = SparsePlan(rt, self.ids, self.table.rows)
+        df = self.dflat
+        check(rt.lib.etr_fm_fused_backward_apply(
+            rt.ctx, C.byref(t), _p(self.table.m) if apply else None, _p(self.table.v) if apply else None, self.k,
+            self.ids.F, self.ids.B, self.plan.sorted_bag.data_ptr(), self.plan.seg_start.data_ptr(),
+            self.plan.unique_ids.data_ptr(), self.plan.counts.data_ptr(), self.plan.n_slots, self.dlogit.data_ptr(),
+            self.sumv.data_ptr(), _p(df), _TORCH2ETR[df.dtype] if df is not None else 0,
+            df.stride(0) if df is not None else 0, self.flat_col0, lr_t, _p(d_lr_t), b1, b2, eps, int(apply), _p(out),
+            rt.stream))
+
+    def apply(self, d_lr_t: torch.Tensor, b1: float, b2: float, eps: float) -> None:
+        self._run(True, 0.0, d_lr_t, b1, b2, eps, None)
+
+    def reduce(self, plan: Optional[SparsePlan] = None) -> "FusedFMGrad":
+        """materialise the deduplicated gradient rows (tests, export, the keras_dense apply)"""
+        rt = self.table.rt
+        self.plan = plan or self.plan or SparsePlan(rt, self.ids, self.table.rows)
+        self.unique_grad = rt.empty((max(self.plan.n_slots, 1), self.table.stride))
+        self._run(False, 0.0, None, 0.0, 0.0, 0.0, self.unique_grad)
+        return self
+
+    def indexed_slices(self):
+        if self.unique_grad is None:
+            self.reduce()
+        u = self.plan.n_unique
+        return self.plan.unique_ids[:u], self.unique_grad[:u, : self.table.width]
+
+
 # ---------------------------------------------------------------------------
 # thin op wrappers
 def gather_fm_forward(table: EmbeddingTable, k: int, has_w: bool, ids: IdsBatch, bias=None, logit=None, prob=None,

@@ -173,6 +173,24 @@ int etr_sparse_adam_apply(etr_ctx* ctx, const etr_table* table, float* d_m, floa
                           float lr_t, const float* d_lr_t, float beta1, float beta2, float eps, int32_t mode,
                           void* stream);
 
+/* FM family fast path (single-hot ids, fp32 [V, k+1] table): K2 + K8 fused.  Per
+ * unique row r of the plan, over its run of occurrences (b,f):
+ *   dv_r[c] = sum g_b*S_b[c] + sum dflat[b, col0+f*k+c] - v_r[c]*sum g_b ,  dw_r = sum g_b
+ * (g = d_dlogit, S = d_sumv saved by etr_gather_fm_forward, dflat = the MLP's input
+ * gradient, fp32 or bf16, may be NULL) followed by the row-wise Adam update -- no
+ * per-occurrence gradient rows are ever written.  Deterministic (runs <= 64 by one lane
+ * group; longer runs in 1024-occurrence chunks combined in order).  apply == 0 only
+ * exports the deduplicated gradient rows to d_unique_grad [n_unique, stride] (the
+ * IndexedSlices tape.gradient + Keras' dedup produce, 2.FM/ModelManager.py:176-178). */
+int etr_fm_fused_backward_apply(etr_ctx* ctx, const etr_table* table, float* d_m, float* d_v, int32_t k,
+                                int32_t fields, int64_t batch,
+                                const int32_t* d_sorted_bag, const int32_t* d_seg_start,
+                                const int64_t* d_unique_ids, const int32_t* d_n_unique, int64_t n_slots,
+                                const float* d_dlogit, const float* d_sumv,
+                                const void* d_dflat, int32_t flat_dtype, int64_t flat_ld, int32_t flat_col0,
+                                float lr_t, const float* d_lr_t, float beta1, float beta2, float eps,
+                                int32_t apply, float* d_unique_grad, void* stream);
+
 /* Dense Adam for the small replicated variables (bias, MLP, cross W/b).      */
 int etr_dense_adam_apply(etr_ctx* ctx, float* d_var, float* d_m, float* d_v, const float* d_grad,
                          int64_t n, float lr_t, const float* d_lr_t, float beta1, float beta2, float eps,

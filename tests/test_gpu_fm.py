@@ -166,12 +166,21 @@ def _fm_grad_check(L, lay, orc, X, rtol):
     assert_close(lay.params.g("bias").cpu().numpy(), orc.bias.grad.numpy(), rtol, "bias grad", grad=True)
 
 
-@pytest.mark.parametrize("B,F,k,V", [(16, 3, 16, 20), (4096, 26, 16, 160000), (300, 5, 8, 64), (128, 26, 64, 3000)])
-def test_fm_backward_matches_autograd(L, B, F, k, V):
+@pytest.mark.parametrize("fused", [True, False])
+@pytest.mark.parametrize("B,F,k,V", [(16, 3, 16, 20), (4096, 26, 16, 160000), (300, 5, 8, 64), (128, 26, 64, 3000),
+                                      (6000, 3, 16, 30)])
+def test_fm_backward_matches_autograd(L, B, F, k, V, fused):
+    """fused=True: backward + segment reduction in one pass over the sorted runs (no materialised row
+    gradients; (6000,3,16,30) has runs of thousands of occurrences -> the chunked long-run path);
+    fused=False: the generic per-bag gradient rows + segment reduction."""
     rng = np.random.default_rng(B)
-    lay = L.FMRankingLayer(_names(F), feature_dims=V, embedding_dims=k, seed=2)
+    lay = L.FMRankingLayer(_names(F), feature_dims=V, embedding_dims=k, seed=2, fused_apply=fused)
     X = zipf_ids(rng, [V // F] * F, B)
     _fm_grad_check(L, lay, oracle_fm(lay, torch.float64), X, FP32_RTOL)
+    from etr_b200.runtime import FusedFMGrad
+    lay(torch.tensor(X), training=True)
+    g = lay.backward(torch.zeros(B, device="cuda"))[0]
+    assert isinstance(g, FusedFMGrad) == fused
 
 
 def test_fm_backward_bags_mean(L):
@@ -315,6 +324,26 @@ def test_gemm_f32(L, M, N, K, ta, tb):
     ref = torch.relu((A.double().T if ta else A.double()) @ (Bm.double().T if tb else Bm.double()) + bias.double())
     err = (Cm.double() - ref).abs().max().item()
     assert err <= 1e-5 * ref.abs().max().item() * max(1.0, (K / 1000) ** 0.5), err
+
+
+def test_fused_and_generic_apply_agree(L):
+    """Two DeepFM replicas, one with the fused backward+reduce+Adam, one with materialised per-bag
+    gradient rows: same weights after training steps (up to fp32 summation order)."""
+    rng = np.random.default_rng(77)
+    B, F, k, V, C = 2048, 8, 16, 900, 3
+    names, cont = _names(F), [f"c{i}" for i in range(C)]
+    lays = [L.DeepFMRankingLayer(names, feature_dims=V, embedding_dims=k, continuous_features=cont, seed=4,
+                                 fused_apply=f) for f in (True, False)]
+    trs = [L.Trainer(l, lr=1e-2) for l in lays]
+    for step in range(3):
+        X = zipf_ids(rng, [V // F] * F, B)
+        d = {n: torch.tensor(X[:, i]) for i, n in enumerate(names)}
+        d.update({n: torch.tensor(rng.normal(size=B).astype(np.float32)) for n in cont})
+        y = torch.tensor((rng.random(B) < 0.3).astype(np.float32))
+        la, lb = trs[0].train_step(d, y), trs[1].train_step(d, y)
+        assert abs(float(la.item()) - float(lb.item())) < 1e-6
+    assert (lays[0].table.data - lays[1].table.data).abs().max().item() < 2e-5      # < 0.2% of one Adam step (lr 1e-2)
+    assert (lays[0].params.value - lays[1].params.value).abs().max().item() < 2e-5
 
 
 def test_graph_trainer_matches_eager(L):
