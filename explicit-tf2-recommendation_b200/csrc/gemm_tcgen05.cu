@@ -15,8 +15,10 @@
 // Two CTAs are resident per SM (shared memory and TMEM are budgeted for it), so
 // one CTA's epilogue overlaps the other's main loop.
 //
-// Warp roles (192 threads): warp 0 = TMA producer, warp 1 = TMEM allocator +
-// MMA issuer, warps 2..5 = epilogue (TMEM lane quarter = warp_id % 4).
+// Warp roles (320 threads): warp 0 = TMA producer, warp 1 = TMEM allocator +
+// MMA issuer, warps 2..9 = epilogue: TMEM lane quarter = warp_id % 4, and the two
+// warps of a quarter split the tile's 32-column chunks (even / odd) so that eight
+// latency-bound epilogue chains run per CTA instead of four.
 #include <cuda.h>
 
 #include "etr_common.cuh"
@@ -27,7 +29,7 @@ namespace tc {
 constexpr int BLOCK_M = 128;
 constexpr int BLOCK_K = 64;            // 64 bf16 = 128 bytes = one swizzle atom row
 constexpr int UMMA_K = 16;
-constexpr int kThreads = 192;
+constexpr int kThreads = 320;          // warp 0 TMA, warp 1 MMA/TMEM, warps 2..9 epilogue
 
 enum { EPI_LINEAR = 0, EPI_CROSS = 1, EPI_PARTIAL = 2 };
 
@@ -205,7 +207,7 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
       umma_commit(smem_u32(tmem_full_bar));            // accumulator complete
     }
   } else {
-    // ===== epilogue warps 2..5 =====
+    // ===== epilogue warps 2..9 =====
     // Each warp owns TMEM lanes [32q, 32q+32) = 32 output rows.  tcgen05.ld hands every lane
     // 32 consecutive columns of ITS row; a 32x33 fp32 tile per warp (in the pipeline buffers,
     // which are drained once tmem_full fires) transposes each 32x32 block so that every global
@@ -216,10 +218,11 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
     // per-warp tile, 32 rows x 36 floats: the 36-float stride keeps every 128-bit shared access
     // 16-byte aligned and bank-conflict free in both directions (per quarter-warp)
     constexpr int TS = 36;
-    float* T = reinterpret_cast<float*>(smem_a) + q * (32 * TS);
+    const int half = (warp - 2) >> 2;                  // 0: even 32-column chunks, 1: odd ones
+    float* T = reinterpret_cast<float*>(smem_a) + (warp - 2) * (32 * TS);
     const long long row_base = (long long)m_tile * BLOCK_M + q * 32;
 #pragma unroll 1
-    for (int c0 = 0; c0 < BLOCK_N; c0 += 32) {
+    for (int c0 = half * 32; c0 < BLOCK_N; c0 += 64) {
       const long long col0 = (long long)n_tile * BLOCK_N + c0;
       if (col0 >= ep.N) break;                         // warp-uniform
       uint32_t v[32];
