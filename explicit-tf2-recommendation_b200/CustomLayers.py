@@ -192,9 +192,10 @@ class FMRankingLayer(_Layer):
         prob = self.rt.empty((ids.B, 1))
         tab, vids, route = self._lookup(ids)
         sumv = self._sumv_buffer(training, tab, vids)
+        plan = SparsePlan(self.rt, vids, tab.rows, overlap=True) if sumv is not None else None   # sort || fwd/bwd
         gather_fm_forward(tab, self.embedding_dims, True, vids, bias=self.bias, prob=prob, sumv=sumv)
         if training:
-            self._ctx = {"ids": vids, "table": tab, "route": route, "sumv": sumv}
+            self._ctx = {"ids": vids, "table": tab, "route": route, "sumv": sumv, "plan": plan}
         self._finish(training)
         return {"output": prob}
 
@@ -213,7 +214,9 @@ class FMRankingLayer(_Layer):
 
     def _table_grad(self, bag: torch.Tensor) -> SparseGrad:
         if self.shard is None:
-            return SparseGrad(self.table, self._ctx["ids"], bag)
+            sg = SparseGrad(self.table, self._ctx["ids"], bag)
+            sg.plan = self._ctx.get("plan")          # an overlapped plan started at forward time, if any
+            return sg
         return self.shard.sparse_grad(self._ctx["route"], bag)
 
     def backward(self, dlogit: torch.Tensor) -> List[SparseGrad]:
@@ -224,7 +227,7 @@ class FMRankingLayer(_Layer):
         check(self.rt.lib.etr_colsum_f32(self.rt.ctx, dl.data_ptr(), ids.B, 1, 1, self.params.g("bias").data_ptr(),
                                          self.rt.stream))
         if self._ctx.get("sumv") is not None:           # fused backward + segment reduction + Adam
-            return [FusedFMGrad(self.table, ids, self.embedding_dims, dl, self._ctx["sumv"])]
+            return [FusedFMGrad(self.table, ids, self.embedding_dims, dl, self._ctx["sumv"], plan=self._ctx["plan"])]
         bag = gather_fm_backward(self._ctx["table"], self.embedding_dims, True, ids, dlogit=dl)
         return [self._table_grad(bag)]
 
@@ -277,6 +280,7 @@ class DeepFMRankingLayer(FMRankingLayer):
         fm_logit = rt.empty((ids.B,))
         tab, vids, route = self._lookup(ids)
         sumv = self._sumv_buffer(training, tab, vids)
+        plan = SparsePlan(rt, vids, tab.rows, overlap=True) if sumv is not None else None        # sort || fwd/bwd
         gather_fm_forward(tab, k, True, vids, bias=self.bias, logit=fm_logit, sumv=sumv, flat=x, flat_col0=col0,
                           cont=cont)
         dnn = self.MLP_layer2(self.MLP_layer1(x, training=training), training=training)      # [B,1]
@@ -284,7 +288,7 @@ class DeepFMRankingLayer(FMRankingLayer):
         check(rt.lib.etr_add_sigmoid(rt.ctx, fm_logit.data_ptr(), dnn.data_ptr(), ids.B, None, prob.data_ptr(),
                                      rt.stream))
         if training:
-            self._ctx = {"ids": vids, "table": tab, "route": route, "sumv": sumv}
+            self._ctx = {"ids": vids, "table": tab, "route": route, "sumv": sumv, "plan": plan}
         self._finish(training)
         return {"output": prob}
 
@@ -298,7 +302,8 @@ class DeepFMRankingLayer(FMRankingLayer):
         dx = self.MLP_layer1.backward(dh)                    # [B, pad + C + F*k]
         check(rt.lib.etr_colsum_f32(rt.ctx, dl.data_ptr(), ids.B, 1, 1, self.params.g("bias").data_ptr(), rt.stream))
         if self._ctx.get("sumv") is not None and col0 % 4 == 0 and dx.stride(0) % 4 == 0:
-            return [FusedFMGrad(self.table, ids, self.embedding_dims, dl, self._ctx["sumv"], dx, col0)]
+            return [FusedFMGrad(self.table, ids, self.embedding_dims, dl, self._ctx["sumv"], dx, col0,
+                                plan=self._ctx["plan"])]
         bag = gather_fm_backward(self._ctx["table"], self.embedding_dims, True, ids, dlogit=dl, dflat=dx,
                                  flat_col0=col0)
         return [self._table_grad(bag)]

@@ -175,40 +175,50 @@ __global__ void __launch_bounds__(256) gemm_skinny_rows_kernel(const GemmParams 
   }
 }
 
-// wgrad of the tail: C[M,N] = A^T B with M*N <= 256 and K = batch: each block
-// reduces a slab of kSkinnySlab batch rows (thread t owns output (t / N, t % N)),
-// slab partials are summed in fixed order by gemm_splitk_finish_kernel.
-constexpr int kSkinnySlab = 512;     // 65 536-row batch -> 128 CTAs, 128 partials per output
+// wgrad of the tail: C[M,N] = A^T B with M*N <= 256 and K = batch.  Each CTA stages a slab of
+// kSkinnySlab batch rows of A ([rows, M]) and B ([rows, N]) in shared memory (coalesced, no index
+// division) and thread t = (m, n) reduces it; the slab partials are then summed by one warp per
+// output in a fixed order (lane partition + xor tree) -- deterministic.
+constexpr int kSkinnySlab = 128;
 __global__ void __launch_bounds__(256) gemm_skinny_wgrad_kernel(const GemmParams p) {
-  __shared__ float As[32][65];     // [row in sub-slab][m]  (M <= 64)
-  __shared__ float Bs[32][33];     // [row in sub-slab][n]  (N <= 32)
+  extern __shared__ __align__(16) float sm_w[];          // As[slab][M] | Bs[slab][N]
   const int M = (int)p.M, N = (int)p.N;
-  const int t = threadIdx.x;
-  const int om = t / N, on = t % N;
-  const bool own = t < M * N;
+  float* As = sm_w;
+  float* Bs = sm_w + kSkinnySlab * M;
+  const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
   const long long r0 = (long long)blockIdx.x * kSkinnySlab;
-  long long r1 = r0 + kSkinnySlab;
-  if (r1 > p.K) r1 = p.K;
-  float acc = 0.f;
-  for (long long rb = r0; rb < r1; rb += 32) {
-    for (int e = t; e < 32 * M; e += 256) {
-      const int rr = e / M, mm = e % M;
-      const long long r = rb + rr;
-      As[rr][mm] = r < r1 ? p.A[mm * p.sam + r * p.sak] : 0.f;
-    }
-    for (int e = t; e < 32 * N; e += 256) {
-      const int rr = e / N, nn = e % N;
-      const long long r = rb + rr;
-      Bs[rr][nn] = r < r1 ? p.B[r * p.sbk + nn * p.sbn] : 0.f;
-    }
-    __syncthreads();
-    if (own) {
-#pragma unroll 8
-      for (int rr = 0; rr < 32; ++rr) acc = fmaf(As[rr][om], Bs[rr][on], acc);
-    }
-    __syncthreads();
+  int rows = kSkinnySlab;
+  if (r0 + rows > p.K) rows = (int)(p.K - r0);
+  for (int r = warp; r < kSkinnySlab; r += 8) {
+    const bool in = r < rows;
+    for (int mm = lane; mm < M; mm += 32) As[r * M + mm] = in ? p.A[mm * p.sam + (r0 + r) * p.sak] : 0.f;
+    for (int nn = lane; nn < N; nn += 32) Bs[r * N + nn] = in ? p.B[(r0 + r) * p.sbk + nn * p.sbn] : 0.f;
   }
-  if (own) p.partial[(long long)blockIdx.x * M * N + t] = acc;
+  __syncthreads();
+  if (t < M * N) {
+    const int om = t / N, on = t % N;
+    float acc = 0.f;
+#pragma unroll 8
+    for (int r = 0; r < kSkinnySlab; ++r) acc = fmaf(As[r * M + om], Bs[r * N + on], acc);
+    p.partial[(long long)blockIdx.x * M * N + t] = acc;
+  }
+}
+// one warp per output element: lane l sums partials l, l+32, ... in order, then a fixed xor tree
+__global__ void __launch_bounds__(256) skinny_finish_kernel(const GemmParams p) {
+  const int lane = threadIdx.x & 31;
+  const long long total = p.M * p.N;
+  const long long o = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (o >= total) return;
+  float s = 0.f;
+  for (int z = lane; z < p.splits; z += 32) s += p.partial[(long long)z * total + o];
+  s = group_sum<32>(s);
+  if (lane == 0) {
+    const long long gm = o / p.N, gn = o % p.N;
+    float x = p.alpha * s;
+    if (p.beta != 0.f) x += p.beta * p.C[gm * p.ldc + gn];
+    if (p.bias) x += p.bias[gn];
+    p.C[gm * p.ldc + gn] = apply_act(x, p.act);
+  }
 }
 
 __global__ void __launch_bounds__(256) act_backward_kernel(float* dy, const float* y, long long n, int act) {
@@ -337,9 +347,10 @@ static int gemm_dispatch(etr_ctx* ctx, GemmParams& p, cudaStream_t s) {
     int st = etr_ws_reserve(ctx, sizeof(float) * (size_t)p.splits * p.M * p.N);
     if (st != ETR_OK) return st;
     p.partial = (float*)ctx->d_ws;
-    gemm_skinny_wgrad_kernel<<<p.splits, 256, 0, s>>>(p);
+    const size_t smem = (size_t)kSkinnySlab * (p.M + p.N) * sizeof(float);
+    gemm_skinny_wgrad_kernel<<<p.splits, 256, smem, s>>>(p);
     ETR_LAUNCH_CHECK(ctx);
-    gemm_splitk_finish_kernel<<<1, 256, 0, s>>>(p);
+    skinny_finish_kernel<<<(unsigned)ceil_div(p.M * p.N, 8), 256, 0, s>>>(p);
     ETR_LAUNCH_CHECK(ctx);
     return ETR_OK;
   }

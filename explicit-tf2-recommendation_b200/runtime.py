@@ -47,19 +47,32 @@ class Runtime:
         h = C.c_void_p()
         check(self.lib.etr_ctx_create(index, C.byref(h)))
         self.ctx = h
+        # a second context (own workspace + error word) for work that runs CONCURRENTLY on the side
+        # stream: the sorted-id plan of a batch depends only on the ids, so it overlaps forward/backward
+        h2 = C.c_void_p()
+        check(self.lib.etr_ctx_create(index, C.byref(h2)))
+        self.side_ctx = h2
+        self._side_stream = None
 
     @property
     def stream(self) -> int:
         return torch.cuda.current_stream(self.device).cuda_stream
 
     @property
+    def side_stream(self) -> "torch.cuda.Stream":
+        if self._side_stream is None:
+            self._side_stream = torch.cuda.Stream(device=self.device)
+        return self._side_stream
+
+    @property
     def launches(self) -> int:
-        return int(self.lib.etr_ctx_launch_count(self.ctx))
+        return int(self.lib.etr_ctx_launch_count(self.ctx)) + int(self.lib.etr_ctx_launch_count(self.side_ctx))
 
     def poll_error(self) -> None:
         """Raise EtrIdRangeError if a kernel saw an out-of-range id (synchronises)."""
         bad = C.c_int64(0)
         check(self.lib.etr_ctx_poll_error(self.ctx, self.stream, C.byref(bad)))
+        check(self.lib.etr_ctx_poll_error(self.side_ctx, self.stream, C.byref(bad)))
 
     # ------------------------------------------------------------ tensors
     def to_device(self, x, dtype: torch.dtype) -> torch.Tensor:
@@ -233,17 +246,42 @@ class IdsBatch:
 class SparsePlan:
     """Sorted-ID plan of one batch (shared by every table indexed by the same ids)."""
 
-    def __init__(self, rt: Runtime, ids: IdsBatch, table_rows: int):
+    def __init__(self, rt: Runtime, ids: IdsBatch, table_rows: int, overlap: bool = False):
+        """``overlap=True``: the sort runs on the runtime's side stream (forked from the current
+        stream, using the side ctx's workspace) and overlaps whatever is enqueued next on the current
+        stream; consumers call ``join()`` first."""
         n = ids.n_slots
         self.n_slots = n
-        self.sorted_bag = rt.empty((max(n, 1),), torch.int32)
-        self.unique_ids = rt.empty((max(n, 1),), torch.int64)
-        self.seg_start = rt.empty((n + 1,), torch.int32)
-        self.counts = rt.zeros((2,), torch.int32)        # [n_unique, n_valid]
-        d = ids.desc()
-        check(rt.lib.etr_sparse_plan(rt.ctx, C.byref(d), ids.nnz or 0, table_rows, self.sorted_bag.data_ptr(),
-                                     self.unique_ids.data_ptr(), self.seg_start.data_ptr(),
-                                     self.counts[0:].data_ptr(), self.counts[1:].data_ptr(), rt.stream))
+        self.rt = rt
+        self._pending = None
+        cur = torch.cuda.current_stream(rt.device)
+        if overlap:
+            side = rt.side_stream
+            side.wait_stream(cur)                        # the ids are produced on the current stream
+            ctx_, stream_ctx = rt.side_ctx, torch.cuda.stream(side)
+        else:
+            ctx_, stream_ctx = rt.ctx, torch.cuda.stream(cur)
+        with stream_ctx:
+            self.sorted_bag = rt.empty((max(n, 1),), torch.int32)
+            self.unique_ids = rt.empty((max(n, 1),), torch.int64)
+            self.seg_start = rt.empty((n + 1,), torch.int32)
+            self.counts = rt.zeros((2,), torch.int32)        # [n_unique, n_valid]
+            d = ids.desc()
+            check(rt.lib.etr_sparse_plan(ctx_, C.byref(d), ids.nnz or 0, table_rows, self.sorted_bag.data_ptr(),
+                                         self.unique_ids.data_ptr(), self.seg_start.data_ptr(),
+                                         self.counts[0:].data_ptr(), self.counts[1:].data_ptr(),
+                                         torch.cuda.current_stream(rt.device).cuda_stream))
+        if overlap:
+            self._pending = rt.side_stream
+            for t in (self.sorted_bag, self.unique_ids, self.seg_start, self.counts):
+                t.record_stream(cur)                     # allocated on the side stream, consumed on the current one
+
+    def join(self) -> "SparsePlan":
+        """Make the current stream wait for an overlapped plan (no-op otherwise)."""
+        if self._pending is not None:
+            torch.cuda.current_stream(self.rt.device).wait_stream(self._pending)
+            self._pending = None
+        return self
 
     @property
     def n_unique(self) -> int:        # synchronises; tests / export only
@@ -261,7 +299,7 @@ class SparseGrad:
     def reduce(self, plan: Optional[SparsePlan] = None) -> "SparseGrad":
         """sort + segment-reduce -> (unique ids, summed rows) = deduplicated IndexedSlices."""
         rt = self.table.rt
-        self.plan = plan or SparsePlan(rt, self.ids, self.table.rows)
+        self.plan = (plan or self.plan or SparsePlan(rt, self.ids, self.table.rows)).join()
         ld = self.bag_grad.shape[1]
         self.unique_grad = rt.empty((max(self.plan.n_slots, 1), ld), torch.float32)
         check(rt.lib.etr_sparse_segment_reduce(rt.ctx, self.plan.sorted_bag.data_ptr(), self.plan.seg_start.data_ptr(),
@@ -283,10 +321,10 @@ class FusedFMGrad:
     (etr_fm_fused_backward_apply); ``indexed_slices`` exports the deduplicated rows."""
 
     def __init__(self, table: EmbeddingTable, ids: IdsBatch, k: int, dlogit: torch.Tensor, sumv: torch.Tensor,
-                 dflat: Optional[torch.Tensor] = None, flat_col0: int = 0):
+                 dflat: Optional[torch.Tensor] = None, flat_col0: int = 0, plan: Optional["SparsePlan"] = None):
         self.table, self.ids, self.k = table, ids, k
         self.dlogit, self.sumv, self.dflat, self.flat_col0 = dlogit, sumv, dflat, flat_col0
-        self.plan: Optional[SparsePlan] = None
+        self.plan: Optional[SparsePlan] = plan
         self.unique_grad: Optional[torch.Tensor] = None
 
     @staticmethod
@@ -299,6 +337,7 @@ class FusedFMGrad:
         rt, t = self.table.rt, self.table.desc()
         if self.plan is None:
             self.plan = SparsePlan(rt, self.ids, self.table.rows)
+        self.plan.join()
         df = self.dflat
         check(rt.lib.etr_fm_fused_backward_apply(
             rt.ctx, C.byref(t), _p(self.table.m) if apply else None, _p(self.table.v) if apply else None, self.k,
@@ -314,7 +353,7 @@ class FusedFMGrad:
     def reduce(self, plan: Optional[SparsePlan] = None) -> "FusedFMGrad":
         """materialise the deduplicated gradient rows (tests, export, the keras_dense apply)"""
         rt = self.table.rt
-        self.plan = plan or self.plan or SparsePlan(rt, self.ids, self.table.rows)
+        self.plan = (plan or self.plan or SparsePlan(rt, self.ids, self.table.rows)).join()
         self.unique_grad = rt.empty((max(self.plan.n_slots, 1), self.table.stride))
         self._run(False, 0.0, None, 0.0, 0.0, 0.0, self.unique_grad)
         return self
