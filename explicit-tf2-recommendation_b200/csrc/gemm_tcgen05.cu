@@ -213,6 +213,21 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
     // which are drained once tmem_full fires) transposes each 32x32 block so that every global
     // load/store instruction touches ONE row's 32 consecutive elements (coalesced).
     const int q = warp & 3;                            // TMEM lane quarter this warp may read
+    if (ep.mode == EPI_CROSS) {
+      // While the main loop runs, pull this tile's x0 / xl rows into L2: the epilogue's loads of them
+      // do not depend on the accumulator, so they should not pay DRAM latency after it is ready.
+      const int et = threadIdx.x - 64;                 // 0..255 over the 8 epilogue warps
+      const long long tile_col0 = (long long)n_tile * BLOCK_N;
+      const int lines = (BLOCK_N * 2 + 127) / 128;     // 128-byte lines per tile row (bf16)
+      for (int i = et; i < BLOCK_M * lines; i += 256) {
+        const long long rr = (long long)m_tile * BLOCK_M + i / lines;
+        const long long cc = tile_col0 + (long long)(i % lines) * 64;
+        if (rr < ep.M && cc < ep.N) {
+          if (ep.x0) asm volatile("prefetch.global.L2 [%0];" ::"l"(ep.x0 + rr * ep.ldx + cc));
+          asm volatile("prefetch.global.L2 [%0];" ::"l"(ep.xl + rr * ep.ldx + cc));
+        }
+      }
+    }
     mbar_wait(smem_u32(tmem_full_bar), 0);
     fence_after();
     // per-warp tile, 32 rows x 36 floats: the 36-float stride keeps every 128-bit shared access

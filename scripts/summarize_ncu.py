@@ -18,8 +18,9 @@ KEYS = ["gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum
         "sm__inst_executed_pipe_tensor.sum", "l1tex__t_sectors_pipe_lsu_mem_global_op_ld.sum", "smsp__warp_issue_stalled_long_scoreboard_per_warp_active.pct"]
 
 
-def launches(tag):
-    path = os.path.join(OUT, "launches.csv")
+def launches(tag, fname="launches.csv", out="launches_one_step", what="DeepFM (c2)", pick=(-3, -2),
+             cmd="python bench.py --steps 3 --warmup 3 --no-graph --no-cpu-baseline"):
+    path = os.path.join(OUT, fname)
     if not os.path.exists(path):
         return
     rows = list(csv.DictReader(l for l in open(path) if not l.startswith("==")))
@@ -27,14 +28,14 @@ def launches(tag):
     starts = [i for i, n in enumerate(names) if "gather_fm_fwd" in n]
     if len(starts) < 3:
         return
-    a, b = starts[-3], starts[-2]
+    a, b = starts[pick[0]], starts[pick[1]]
     step = rows[a:b]
     tot = sum(float(r["Metric Value"]) for r in step) / 1e3
-    with open(os.path.join(ROOT, "profiles", f"{tag}_launches_one_step.md"), "w") as fh:
-        fh.write(f"# {tag}: every kernel of ONE eager DeepFM (c2) train step, `ncu --metrics gpu__time_duration.sum "
+    with open(os.path.join(ROOT, "profiles", f"{tag}_{out}.md"), "w") as fh:
+        fh.write(f"# {tag}: every kernel of ONE eager {what} train step, `ncu --metrics gpu__time_duration.sum "
                  f"--clock-control none`\n\nCold-cache, serialised per-launch times: compare SHARES, not absolutes. "
                  f"Sum = {tot:.1f} us over {len(step)} launches "
-                 f"(command: `python bench.py --steps 3 --warmup 3 --no-graph --no-cpu-baseline`).\n\n"
+                 f"(command: `{cmd}`).\n\n"
                  f"| # | us | share | kernel |\n|---|---|---|---|\n")
         for i, r in enumerate(step):
             v = float(r["Metric Value"]) / 1e3
@@ -65,6 +66,8 @@ def rep(name, tag):
 if __name__ == "__main__":
     tag = sys.argv[1] if len(sys.argv) > 1 else "r01"
     launches(tag)
+    launches(tag, "launches_c3.csv", "launches_c3_step", "DCN-matrix bf16 (c3)", (-2, -1),
+             "python bench.py --config c3 --steps 1 --warmup 3 --no-graph")
     for n in ("prof_gather_fwd", "prof_tcgemm", "prof_cross"):
         rep(n, tag)
     print(os.listdir(os.path.join(ROOT, "profiles")))
