@@ -109,18 +109,32 @@ __device__ __forceinline__ void adam_update4(float4& var, float4& m, float4& v, 
 }
 
 // finish one row: grad = P - v_r * sum_g (embedding chunk gl), w chunk by lane 0; Adam and/or export
-__device__ __forceinline__ void fused_finish_row(const FusedParams& p, long long u, int gl, float4 P, float sum_g, float lr_t) {
-  const long long row = p.unique_ids[u];
+struct RowState { float4 var, m, v; };
+// issue the row's (var, m, v) loads; called BEFORE the occurrence loop so that their DRAM latency
+// overlaps the loop instead of following it
+__device__ __forceinline__ RowState fused_load_row(const FusedParams& p, long long row, int gl) {
+  RowState st;
+  st.var = *reinterpret_cast<const float4*>(p.table + row * p.stride + gl * 4);
+  st.m = st.v = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (p.apply) {
+    st.m = *reinterpret_cast<const float4*>(p.m + row * p.stride + gl * 4);
+    st.v = *reinterpret_cast<const float4*>(p.v + row * p.stride + gl * 4);
+  }
+  return st;
+}
+
+__device__ __forceinline__ void fused_finish_row(const FusedParams& p, long long u, long long row, int gl, RowState st,
+                                                 float4 P, float sum_g, float lr_t) {
   float* prow = p.table + row * p.stride;
-  float4 var = *reinterpret_cast<const float4*>(prow + gl * 4);
+  float4 var = st.var;
   const float4 g = make_float4(P.x - var.x * sum_g, P.y - var.y * sum_g, P.z - var.z * sum_g, P.w - var.w * sum_g);
   if (p.unique_grad) *reinterpret_cast<float4*>(p.unique_grad + u * p.stride + gl * 4) = g;
   if (p.apply) {
-    float4* pm = reinterpret_cast<float4*>(p.m + row * p.stride + gl * 4);
-    float4* pv = reinterpret_cast<float4*>(p.v + row * p.stride + gl * 4);
-    float4 m = *pm, v = *pv;
+    float4 m = st.m, v = st.v;
     adam_update4(var, m, v, g, lr_t, p.b1, p.b2, p.eps);
-    *reinterpret_cast<float4*>(prow + gl * 4) = var; *pm = m; *pv = v;
+    *reinterpret_cast<float4*>(prow + gl * 4) = var;
+    *reinterpret_cast<float4*>(p.m + row * p.stride + gl * 4) = m;
+    *reinterpret_cast<float4*>(p.v + row * p.stride + gl * 4) = v;
   }
   if (gl == 0) {
     // chunks behind the embedding: [w, 0, 0, 0] (+ zero padding chunks)
@@ -163,10 +177,12 @@ __global__ void __launch_bounds__(256) fm_fused_short_kernel(const FusedParams p
       }
       continue;
     }
+    const long long row = p.unique_ids[u];
+    const RowState st = fused_load_row(p, row, gl);
     float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
     float sum_g = 0.f;
     fused_accumulate(p, s0, s1, gl, acc, sum_g);
-    fused_finish_row(p, u, gl, acc, sum_g, lr_t);
+    fused_finish_row(p, u, row, gl, st, acc, sum_g, lr_t);
   }
 }
 
@@ -223,6 +239,8 @@ __global__ void __launch_bounds__(256) fm_fused_combine_kernel(const FusedParams
   const long long ngroups = (long long)gridDim.x * (blockDim.x >> 5) * GPW;
   for (long long r = group_global; r < n_long; r += ngroups) {
     const FusedLong lr = p.long_runs[r];
+    const long long row = p.unique_ids[lr.u];
+    const RowState st = fused_load_row(p, row, gl);
     float4 t = make_float4(0.f, 0.f, 0.f, 0.f);
     float ts = 0.f;
     for (int c = 0; c < lr.nchunks; ++c) {
@@ -231,7 +249,7 @@ __global__ void __launch_bounds__(256) fm_fused_combine_kernel(const FusedParams
       t.x += x.x; t.y += x.y; t.z += x.z; t.w += x.w;
       ts += src[p.k];
     }
-    fused_finish_row(p, lr.u, gl, t, ts, lr_t);
+    fused_finish_row(p, lr.u, row, gl, st, t, ts, lr_t);
   }
 }
 

@@ -23,9 +23,9 @@ echo "ncu exit $?"
 timeout 600 ncu --set full --clock-control none --import-source on -k regex:gather_fm_fwd_tile -s 4 -c 2 \
     -o gpurun_out/prof_gather_fwd python bench.py --steps 3 --warmup 3 --no-graph --no-cpu-baseline > gpurun_out/ncu_full1.log 2>&1
 echo "ncu full gather exit $?"
-timeout 600 ncu --set full --clock-control none --import-source on -k regex:gemm_bf16_tn -s 8 -c 3 \
-    -o gpurun_out/prof_tcgemm python bench.py --steps 3 --warmup 3 --no-graph --no-cpu-baseline > gpurun_out/ncu_full2.log 2>&1
-echo "ncu full tcgemm exit $?"
+timeout 600 ncu --set full --clock-control none --import-source on -k regex:fm_fused_short -s 3 -c 1 \
+    -o gpurun_out/prof_fused_short python bench.py --steps 3 --warmup 3 --no-graph --no-cpu-baseline > gpurun_out/ncu_full2.log 2>&1
+echo "ncu full fused exit $?"
 timeout 300 python bench.py --config c3 --steps 1 --warmup 3 --no-graph > gpurun_out/bench_c3_eager.json 2> gpurun_out/bench_c3_eager.err &&
 timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 900 --csv --log-file gpurun_out/launches_c3.csv \
     python bench.py --config c3 --steps 1 --warmup 3 --no-graph > gpurun_out/ncu_c3.log 2>&1

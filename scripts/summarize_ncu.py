@@ -68,6 +68,6 @@ if __name__ == "__main__":
     launches(tag)
     launches(tag, "launches_c3.csv", "launches_c3_step", "DCN-matrix bf16 (c3)", (-2, -1),
              "python bench.py --config c3 --steps 1 --warmup 3 --no-graph")
-    for n in ("prof_gather_fwd", "prof_tcgemm", "prof_cross"):
+    for n in ("prof_gather_fwd", "prof_tcgemm", "prof_cross", "prof_fused_short"):
         rep(n, tag)
     print(os.listdir(os.path.join(ROOT, "profiles")))
