@@ -257,12 +257,15 @@ __global__ void __launch_bounds__(256) colsum_stage1_kernel(const float* X, long
     partial[(long long)blockIdx.y * N + n] = t;
   }
 }
+// stage 2: one warp per column -- lane l sums slabs l, l+32, ... in order, then a fixed xor tree
 __global__ void __launch_bounds__(256) colsum_stage2_kernel(const float* partial, long long slabs, long long N, float* out) {
-  for (long long n = (long long)blockIdx.x * blockDim.x + threadIdx.x; n < N; n += (long long)gridDim.x * blockDim.x) {
-    float s = 0.f;
-    for (long long q = 0; q < slabs; ++q) s += partial[q * N + n];
-    out[n] = s;
-  }
+  const int lane = threadIdx.x & 31;
+  const long long n = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (n >= N) return;
+  float s = 0.f;
+  for (long long q = lane; q < slabs; q += 32) s += partial[q * N + n];
+  s = group_sum<32>(s);
+  if (lane == 0) out[n] = s;
 }
 
 // Keras BCE on probabilities + d/dz through the sigmoid.
@@ -429,7 +432,7 @@ int etr_colsum_f32(etr_ctx* ctx, const float* d_X, int64_t M, int64_t N, int64_t
   dim3 grid((unsigned)ceil_div(N, cb), (unsigned)slabs);
   colsum_stage1_kernel<<<grid, 256, 0, s>>>(d_X, M, N, ldx, cb, (float*)ctx->d_ws);
   ETR_LAUNCH_CHECK(ctx);
-  colsum_stage2_kernel<<<grid_for(N, 256, ctx->sm_count, 1), 256, 0, s>>>((const float*)ctx->d_ws, slabs, N, d_out);
+  colsum_stage2_kernel<<<(unsigned)ceil_div(N, 8), 256, 0, s>>>((const float*)ctx->d_ws, slabs, N, d_out);
   ETR_LAUNCH_CHECK(ctx);
   return ETR_OK;
 }

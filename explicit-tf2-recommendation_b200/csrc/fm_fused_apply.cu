@@ -42,17 +42,20 @@ __device__ __forceinline__ void bag_to_bf(const FusedParams& p, int bag, int& b,
   f = bag - b * p.F;
 }
 
-// accumulate occurrences [i0, i1) into acc (this lane's float4 column chunk) and sum_g
+// accumulate occurrences [i0, i1) into acc (this lane's float4 column chunk) and sum_g; UN
+// occurrences in flight (2 in the short-run kernel, where 83% of the runs have length 1 and
+// registers are better spent on occupancy; 4 in the chunk kernel)
+template <int UN>
 __device__ __forceinline__ void fused_accumulate(const FusedParams& p, int i0, int i1, int gl, float4& acc, float& sum_g) {
   int i = i0;
-  for (; i + 4 <= i1; i += 4) {
-    int b[4], f[4];
-    float g[4];
-    float4 s[4], d[4];
+  for (; i + UN <= i1; i += UN) {
+    int b[UN], f[UN];
+    float g[UN];
+    float4 s[UN], d[UN];
 #pragma unroll
-    for (int q = 0; q < 4; ++q) bag_to_bf(p, __ldg(p.sorted_bag + i + q), b[q], f[q]);
+    for (int q = 0; q < UN; ++q) bag_to_bf(p, __ldg(p.sorted_bag + i + q), b[q], f[q]);
 #pragma unroll
-    for (int q = 0; q < 4; ++q) {
+    for (int q = 0; q < UN; ++q) {
       g[q] = __ldg(p.dlogit + b[q]);
       s[q] = *reinterpret_cast<const float4*>(p.sumv + (long long)b[q] * p.k + gl * 4);
       d[q] = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -69,7 +72,7 @@ __device__ __forceinline__ void fused_accumulate(const FusedParams& p, int i0, i
       }
     }
 #pragma unroll
-    for (int q = 0; q < 4; ++q) {
+    for (int q = 0; q < UN; ++q) {
       acc.x += g[q] * s[q].x + d[q].x; acc.y += g[q] * s[q].y + d[q].y;
       acc.z += g[q] * s[q].z + d[q].z; acc.w += g[q] * s[q].w + d[q].w;
       sum_g += g[q];
@@ -154,7 +157,7 @@ __device__ __forceinline__ void fused_finish_row(const FusedParams& p, long long
 }
 
 template <int LPR>
-__global__ void __launch_bounds__(256) fm_fused_short_kernel(const FusedParams p) {
+__global__ void __launch_bounds__(256, 4) fm_fused_short_kernel(const FusedParams p) {
   constexpr int GPW = 32 / LPR;
   const int lane = threadIdx.x & 31;
   const int gl = lane % LPR, g = lane / LPR;
@@ -181,7 +184,7 @@ __global__ void __launch_bounds__(256) fm_fused_short_kernel(const FusedParams p
     const RowState st = fused_load_row(p, row, gl);
     float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
     float sum_g = 0.f;
-    fused_accumulate(p, s0, s1, gl, acc, sum_g);
+    fused_accumulate<2>(p, s0, s1, gl, acc, sum_g);
     fused_finish_row(p, u, row, gl, st, acc, sum_g, lr_t);
   }
 }
@@ -207,7 +210,7 @@ __global__ void __launch_bounds__(256) fm_fused_chunk_kernel(const FusedParams p
     if (b > s1) b = s1;
     float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
     float sum_g = 0.f;
-    fused_accumulate(p, a, b, gl, acc, sum_g);
+    fused_accumulate<4>(p, a, b, gl, acc, sum_g);
     sm[g][gl] = acc;
     if (gl == 0) sg[g] = sum_g;
     __syncthreads();
@@ -310,7 +313,7 @@ int etr_fm_fused_backward_apply(etr_ctx* ctx, const etr_table* table, float* d_m
   p.items = (int2*)(ws + b_cnt + b_runs);
   p.partials = (float*)(ws + b_cnt + b_runs + b_items);
   ETR_CUDA(cudaMemsetAsync(p.counters, 0, 2 * sizeof(int), s));
-  const int gshort = grid_for(n_slots, 8 * (32 / lpr), ctx->sm_count, 8);
+  const int gshort = grid_for(n_slots, 8 * (32 / lpr), ctx->sm_count, 16);
   const int gchunk = ctx->sm_count * 4;
 #define ETR_FUSED(LPR)                                                      \
   do {                                                                      \

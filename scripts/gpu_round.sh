@@ -30,6 +30,6 @@ timeout 300 python bench.py --config c3 --steps 1 --warmup 3 --no-graph > gpurun
 timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 900 --csv --log-file gpurun_out/launches_c3.csv \
     python bench.py --config c3 --steps 1 --warmup 3 --no-graph > gpurun_out/ncu_c3.log 2>&1
 echo "ncu c3 launches exit $?"
-timeout 600 ncu --set full --clock-control none --import-source on -k regex:gemm_bf16_tn_kernelILi240 -s 3 -c 2 \
+timeout 600 ncu --set full --clock-control none --import-source on -k regex:gemm_bf16_tn -s 0 -c 2 \
     -o gpurun_out/prof_cross python bench.py --config c3 --steps 1 --warmup 3 --no-graph > gpurun_out/ncu_full3.log 2>&1
 echo "ncu full cross exit $?"

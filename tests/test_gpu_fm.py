@@ -107,6 +107,17 @@ def test_fm_numpy_and_dlpack_inputs(L):
     assert torch.equal(torch.from_dlpack(a), a)                # output exports DLPack
 
 
+def test_device_resident_dict_uses_assemble_kernel(L):
+    """dict of CUDA int64 columns -> one etr_assemble_ids launch into the field-major [F,B] buffer."""
+    lay = L.FMRankingLayer(_names(70), feature_dims=500, embedding_dims=8)      # 70 fields: two launches of <= 64
+    X = np.random.default_rng(2).integers(0, 500, size=(33, 70))
+    host = lay({n: torch.tensor(X[:, i]) for i, n in enumerate(lay.feature_names)})["output"]
+    l0 = lay.rt.launches
+    dev = lay({n: torch.tensor(X[:, i]).cuda().reshape(-1, 1) for i, n in enumerate(lay.feature_names)})["output"]
+    assert lay.rt.launches - l0 >= 3                      # 2 assemble launches + the gather kernel
+    assert torch.equal(host, dev)
+
+
 def test_fm_bf16_table(L):
     rng = np.random.default_rng(11)
     lay = L.FMRankingLayer(_names(26), feature_dims=10000, embedding_dims=16, table_dtype="bfloat16")
