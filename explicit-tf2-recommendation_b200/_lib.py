@@ -85,6 +85,14 @@ PROTOTYPES = {
     "etr_colsum_bf16": (C.c_int, [_vp, _vp, _i64, _i64, _i64, _vp, _vp]),
     "etr_cast_bf16": (C.c_int, [_vp, _vp, _i64, _i64, _i64, _vp, _i64, _i32, _vp]),
     "etr_transpose_bf16": (C.c_int, [_vp, _vp, _i64, _i64, _i64, _vp, _i64, _vp]),
+    "etr_peer_alloc": (C.c_int, [_vp, _i64, C.POINTER(_vp), _vp]),
+    "etr_peer_open": (C.c_int, [_vp, _vp, C.POINTER(_vp)]),
+    "etr_peer_close": (C.c_int, [_vp, _vp]),
+    "etr_peer_free": (C.c_int, [_vp, _vp]),
+    "etr_shard_set_create": (C.c_int, [_vp, C.POINTER(_vp), _i32, _i32, _i64, C.POINTER(_i32)]),
+    "etr_shard_push": (C.c_int, [_vp, _vp, _vp, _i64, _vp, _i32, _i32, _i32, C.POINTER(_vp), C.POINTER(_vp),
+                                 C.POINTER(_vp), _vp, _vp]),
+    "etr_shard_mailbox_pad": (C.c_int, [_vp, _vp, _vp, _i32, _i32, _vp]),
     "etr_shard_partition": (C.c_int, [_vp, _vp, _i64, _i32, _i64, _vp, _vp, _vp, _vp, _vp]),
     "etr_cross_mat_bwd_elementwise": (C.c_int, [_vp, _vp, _vp, _vp, _i64, _vp, _vp, _vp]),
 }

@@ -61,6 +61,7 @@ int etr_ctx_create(int device, etr_ctx** out) {
   c->d_ws = nullptr;
   c->ws_bytes = 0;
   c->launches = 0;
+  c->n_shard_sets = 0;
   cudaError_t e = cudaMalloc(&c->d_err, 2 * sizeof(unsigned long long));
   if (e != cudaSuccess) {
     delete c;

@@ -8,9 +8,21 @@
 
 #include "../../include/etr.h"
 
+// A row-sharded table as seen from one rank: shard g (rows g, g+G, g+2G, ...) lives in GPU g's HBM
+// and is mapped here through CUDA IPC (NVLink peer memory); base[rank] is the local shard.
+struct EtrShardSet {
+  const char* base[16];
+  int world;
+  int rank;
+  long long rows_global;
+};
+constexpr int kMaxShardSets = 8;
+
 struct etr_ctx {
   int device;
   int sm_count;
+  EtrShardSet shard_sets[kMaxShardSets];
+  int n_shard_sets;
   // device error word: [0] flag, [1] first offending id (best effort)
   unsigned long long* d_err;
   // reusable workspace (CUB temp storage, long-segment lists, partial sums)

@@ -35,6 +35,7 @@ struct FusedParams {
   int apply;                  // 1: Adam update; 0: only export the gradient rows
   float* unique_grad;         // optional [n_unique, stride]
   int* counters; FusedLong* long_runs; int2* items; float* partials; int max_long, max_items;
+  const char* shard_base[16]; int world;     // peer-sharded table (export mode only): ids are global
 };
 
 __device__ __forceinline__ void bag_to_bf(const FusedParams& p, int bag, int& b, int& f) {
@@ -117,6 +118,13 @@ struct RowState { float4 var, m, v; };
 // overlaps the loop instead of following it
 __device__ __forceinline__ RowState fused_load_row(const FusedParams& p, long long row, int gl) {
   RowState st;
+  if (p.world > 1) {
+    const long long lrow = row / p.world;
+    st.var = *reinterpret_cast<const float4*>(reinterpret_cast<const float*>(p.shard_base[(int)(row - lrow * p.world)]) +
+                                              lrow * p.stride + gl * 4);
+    st.m = st.v = make_float4(0.f, 0.f, 0.f, 0.f);
+    return st;
+  }
   st.var = *reinterpret_cast<const float4*>(p.table + row * p.stride + gl * 4);
   st.m = st.v = make_float4(0.f, 0.f, 0.f, 0.f);
   if (p.apply) {
@@ -300,6 +308,14 @@ int etr_fm_fused_backward_apply(etr_ctx* ctx, const etr_table* table, float* d_m
   p.dlogit = d_dlogit; p.sumv = d_sumv; p.dflat = d_dflat; p.flat_bf16 = flat_dtype == ETR_BF16; p.flat_ld = flat_ld;
   p.flat_col0 = flat_col0; p.lr_t = lr_t; p.d_lr_t = d_lr_t; p.b1 = beta1; p.b2 = beta2; p.eps = eps; p.apply = apply;
   p.unique_grad = d_unique_grad;
+  p.world = 1;
+  if (table->reserved > 0) {
+    ETR_CHECK_ARG(table->reserved <= ctx->n_shard_sets, "unknown shard set");
+    ETR_CHECK_ARG(!apply, "a peer-sharded table is updated by its owner (push the exported rows, apply there)");
+    const EtrShardSet& ss = ctx->shard_sets[table->reserved - 1];
+    p.world = ss.world;
+    for (int g = 0; g < ss.world; ++g) p.shard_base[g] = ss.base[g];
+  }
   p.max_long = (int)(n_slots / kFusedShortRun + 1);
   p.max_items = (int)(n_slots / kFusedChunk + n_slots / kFusedShortRun + 2);
   auto a256 = [](size_t x) { return (x + 255) & ~(size_t)255; };

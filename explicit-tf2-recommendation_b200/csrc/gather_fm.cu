@@ -45,6 +45,9 @@ struct GatherParams {
   // extra 4-byte (2-byte for bf16) load, so no lane idles
   int w_extra;
   int esize;
+  // row-sharded table over peer memory (tiled forward kernel only): shard g holds rows g, g+G, ...
+  const char* shard_base[16];
+  int world;
   // backward only
   const float* dlogit;
   float* bag_grad;
@@ -541,6 +544,10 @@ __global__ void __launch_bounds__(256, 3) gather_fm_fwd_tile_kernel(const Gather
         ok = ok && !(p.has_pad && id == p.pad);
         if (ok && (unsigned long long)id >= (unsigned long long)p.rows) { flag_bad_id(p.err, id); ok = false; }
         const char* rowp = p.table + id * (long long)p.row_bytes;
+        if (p.world > 1) {                       // NVLink peer memory: the owner's shard, local row id / G
+          const long long lrow = id / p.world;
+          rowp = p.shard_base[(int)(id - lrow * p.world)] + lrow * (long long)p.row_bytes;
+        }
         if (ok && has_chunk) r[u].load(rowp + c * 16);
         else r[u].zero();
         wv[u] = 0.f;
@@ -751,6 +758,14 @@ static int fill_params(const char* fn, const etr_table* table, int k, int has_w,
   p->has_pad = ids->has_pad;
   p->mean = ids->pooling == ETR_POOL_MEAN;
   p->err = ctx->d_err;
+  p->world = 1;
+  if (table->reserved > 0) {
+    if (table->reserved > ctx->n_shard_sets) { etr_set_error("%s: unknown shard set %d", fn, table->reserved); return ETR_EINVAL; }
+    const EtrShardSet& ss = ctx->shard_sets[table->reserved - 1];
+    p->world = ss.world;
+    p->rows = ss.rows_global;                 // ids are GLOBAL; owner = id mod G, local row = id div G
+    for (int g = 0; g < ss.world; ++g) p->shard_base[g] = ss.base[g];
+  }
   return ETR_OK;
 }
 
@@ -788,6 +803,10 @@ static int launch_gather(etr_ctx* ctx, const GatherParams& p_in, bool bag, cudaS
   const int threads = 256;
   // tiled single-hot kernels: ids double-buffered in shared memory
   const size_t tile_smem = 2 * (size_t)(8 * gpw) * p.F * sizeof(long long);
+  if (p.world > 1 && (BWD || bag || cpl != 1 || tile_smem > 64 * 1024)) {
+    etr_set_error("gather: peer-sharded tables are served by the tiled single-hot forward kernel only");
+    return ETR_EUNSUPPORTED;
+  }
   if (!bag && cpl == 1 && tile_smem <= 64 * 1024) {
     const int tgrid = grid_for(p.B, 8 * gpw, ctx->sm_count, 3);
 #define ETR_TILE(LPR)                                                                                   \

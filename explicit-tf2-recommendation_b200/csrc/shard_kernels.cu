@@ -58,11 +58,162 @@ __global__ void __launch_bounds__(256) shard_finish_kernel(const long long* ids,
   }
 }
 
+// ---- peer-memory path: push deduplicated gradient rows into the owners' mailboxes
+struct PushParams {
+  const long long* unique_ids; const int* n_unique; const float* unique_grad; int ld;
+  int world; int cap;                    // slots per (owner, source) region
+  long long* ids_mb[16];                 // owner g: this source rank's id region (peer pointer)
+  float* grads_mb[16];                   // owner g: this source rank's gradient region
+  int* counts_mb[16];                    // owner g: &counts[source rank]
+  int* local_cnt;                        // [world] slots used so far per owner (this step)
+  unsigned long long* err;
+};
+
+template <int LPR>
+__global__ void __launch_bounds__(256) shard_push_kernel(const PushParams p) {
+  constexpr int GPW = 32 / LPR;
+  const int lane = threadIdx.x & 31;
+  const int gl = lane % LPR, g = lane / LPR;
+  const int nchunks = p.ld / 4;
+  const int n_unique = *p.n_unique;
+  const long long group_global = ((long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5)) * GPW + g;
+  const long long ngroups = (long long)gridDim.x * (blockDim.x >> 5) * GPW;
+  const unsigned gmask = (LPR == 32) ? 0xffffffffu : (((1u << LPR) - 1u) << (g * LPR));
+  for (long long u0 = group_global - g; u0 < n_unique; u0 += ngroups) {      // warp-uniform trip count
+    const long long u = u0 + g;
+    const bool active = u < n_unique;
+    int slot = 0, owner = 0;
+    long long lrow = 0;
+    if (active) {
+      const long long id = p.unique_ids[u];
+      owner = (int)(id % p.world);
+      lrow = id / p.world;
+      if (gl == 0) slot = atomicAdd(&p.local_cnt[owner], 1);
+    }
+    slot = __shfl_sync(gmask, slot, g * LPR);
+    if (!active) continue;
+    if (slot >= p.cap) {
+      if (gl == 0) flag_bad_id(p.err, -2);            // mailbox region overflow
+      continue;
+    }
+    if (gl == 0) p.ids_mb[owner][slot] = lrow;
+    for (int c = gl; c < nchunks; c += LPR)
+      *reinterpret_cast<float4*>(p.grads_mb[owner] + (long long)slot * p.ld + c * 4) =
+          *reinterpret_cast<const float4*>(p.unique_grad + u * p.ld + c * 4);
+  }
+}
+__global__ void shard_push_counts_kernel(const PushParams p) {
+  const int g = threadIdx.x;
+  if (g < p.world) {
+    int c = p.local_cnt[g];
+    if (c > p.cap) c = p.cap;
+    *p.counts_mb[g] = c;
+    p.local_cnt[g] = 0;                                // ready for the next step
+  }
+}
+// owner side: slots beyond each source's count become pads (id -1)
+__global__ void __launch_bounds__(256) shard_mailbox_pad_kernel(long long* ids, const int* counts, int world, int cap) {
+  const long long total = (long long)world * cap;
+  for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (long long)gridDim.x * blockDim.x) {
+    const int r = (int)(t / cap), s = (int)(t % cap);
+    if (s >= counts[r]) ids[t] = -1;
+  }
+}
+
 }  // namespace etr
 
 using namespace etr;
 
 extern "C" {
+
+int etr_peer_alloc(etr_ctx* ctx, int64_t bytes, void** d_ptr, void* handle64) {
+  ETR_CHECK_ARG(ctx && d_ptr && handle64 && bytes > 0, "bad argument");
+  ETR_CUDA(cudaMalloc(d_ptr, (size_t)bytes));
+  ETR_CUDA(cudaMemset(*d_ptr, 0, (size_t)bytes));
+  cudaIpcMemHandle_t h;
+  ETR_CUDA(cudaIpcGetMemHandle(&h, *d_ptr));
+  static_assert(sizeof(h) == 64, "cudaIpcMemHandle_t is 64 bytes");
+  memcpy(handle64, &h, 64);
+  return ETR_OK;
+}
+
+int etr_peer_open(etr_ctx* ctx, const void* handle64, void** d_ptr) {
+  ETR_CHECK_ARG(ctx && handle64 && d_ptr, "bad argument");
+  cudaIpcMemHandle_t h;
+  memcpy(&h, handle64, 64);
+  ETR_CUDA(cudaIpcOpenMemHandle(d_ptr, h, cudaIpcMemLazyEnablePeerAccess));
+  return ETR_OK;
+}
+
+int etr_peer_close(etr_ctx* ctx, void* d_ptr) {
+  ETR_CHECK_ARG(ctx, "bad argument");
+  if (d_ptr) ETR_CUDA(cudaIpcCloseMemHandle(d_ptr));
+  return ETR_OK;
+}
+
+int etr_peer_free(etr_ctx* ctx, void* d_ptr) {
+  ETR_CHECK_ARG(ctx, "bad argument");
+  if (d_ptr) ETR_CUDA(cudaFree(d_ptr));
+  return ETR_OK;
+}
+
+int etr_shard_set_create(etr_ctx* ctx, const void* const* h_shard_ptrs, int32_t world, int32_t rank,
+                         int64_t rows_global, int32_t* out_id) {
+  ETR_CHECK_ARG(ctx && h_shard_ptrs && out_id, "NULL argument");
+  ETR_CHECK_ARG(world >= 1 && world <= 16 && rank >= 0 && rank < world, "world must be in [1,16]");
+  ETR_CHECK_ARG(ctx->n_shard_sets < kMaxShardSets, "too many shard sets on this ctx");
+  EtrShardSet& ss = ctx->shard_sets[ctx->n_shard_sets];
+  for (int g = 0; g < world; ++g) {
+    ETR_CHECK_ARG(h_shard_ptrs[g] != nullptr, "NULL shard pointer");
+    ss.base[g] = (const char*)h_shard_ptrs[g];
+  }
+  ss.world = world; ss.rank = rank; ss.rows_global = rows_global;
+  *out_id = ++ctx->n_shard_sets;                        // ids start at 1; 0 in etr_table.reserved = not sharded
+  return ETR_OK;
+}
+
+int etr_shard_push(etr_ctx* ctx, const int64_t* d_unique_ids, const int32_t* d_n_unique, int64_t max_unique,
+                   const float* d_unique_grad, int32_t ld, int32_t world, int32_t cap,
+                   int64_t* const* h_ids_mb, float* const* h_grads_mb, int32_t* const* h_counts_mb,
+                   int32_t* d_local_cnt, void* stream) {
+  ETR_CHECK_ARG(ctx && d_unique_ids && d_n_unique && d_unique_grad && h_ids_mb && h_grads_mb && h_counts_mb && d_local_cnt,
+                "NULL argument");
+  ETR_CHECK_ARG(world >= 1 && world <= 16 && ld % 4 == 0 && ld / 4 <= 32 && cap > 0, "bad world / ld / cap");
+  PushParams p;
+  memset(&p, 0, sizeof(p));
+  p.unique_ids = (const long long*)d_unique_ids; p.n_unique = d_n_unique; p.unique_grad = d_unique_grad; p.ld = ld;
+  p.world = world; p.cap = cap; p.local_cnt = d_local_cnt; p.err = ctx->d_err;
+  for (int g = 0; g < world; ++g) {
+    p.ids_mb[g] = (long long*)h_ids_mb[g]; p.grads_mb[g] = h_grads_mb[g]; p.counts_mb[g] = h_counts_mb[g];
+  }
+  cudaStream_t s = (cudaStream_t)stream;
+  if (max_unique > 0) {
+    int lpr = 1;
+    while (lpr < ld / 4) lpr <<= 1;
+    const int grid = grid_for(max_unique, 8 * (32 / lpr), ctx->sm_count, 8);
+    switch (lpr) {
+      case 1: shard_push_kernel<1><<<grid, 256, 0, s>>>(p); break;
+      case 2: shard_push_kernel<2><<<grid, 256, 0, s>>>(p); break;
+      case 4: shard_push_kernel<4><<<grid, 256, 0, s>>>(p); break;
+      case 8: shard_push_kernel<8><<<grid, 256, 0, s>>>(p); break;
+      case 16: shard_push_kernel<16><<<grid, 256, 0, s>>>(p); break;
+      default: shard_push_kernel<32><<<grid, 256, 0, s>>>(p); break;
+    }
+    ETR_LAUNCH_CHECK(ctx);
+  }
+  shard_push_counts_kernel<<<1, 32, 0, s>>>(p);
+  ETR_LAUNCH_CHECK(ctx);
+  return ETR_OK;
+}
+
+int etr_shard_mailbox_pad(etr_ctx* ctx, int64_t* d_ids, const int32_t* d_counts, int32_t world, int32_t cap,
+                          void* stream) {
+  ETR_CHECK_ARG(ctx && d_ids && d_counts && world >= 1 && cap > 0, "bad argument");
+  shard_mailbox_pad_kernel<<<grid_for((long long)world * cap, 256, ctx->sm_count, 8), 256, 0, (cudaStream_t)stream>>>(
+      (long long*)d_ids, d_counts, world, cap);
+  ETR_LAUNCH_CHECK(ctx);
+  return ETR_OK;
+}
 
 int etr_shard_partition(etr_ctx* ctx, const int64_t* d_ids, int64_t n, int32_t world, int64_t rows_global,
                         int64_t* d_send_rows, int64_t* d_send_pos, int64_t* d_inv_pos, int32_t* d_counts,

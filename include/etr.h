@@ -340,6 +340,33 @@ int etr_shard_partition(etr_ctx* ctx, const int64_t* d_ids, int64_t n, int32_t w
                         int64_t* d_send_rows, int64_t* d_send_pos, int64_t* d_inv_pos, int32_t* d_counts,
                         void* stream);
 
+/* ---- peer-memory form of the sharded tables (NVLink / NVSwitch, CUDA IPC) ----
+ * Every rank allocates its shard (and its gradient mailbox) with etr_peer_alloc, ranks exchange
+ * the 64-byte IPC handles out of band and map each other's buffers with etr_peer_open.  A shard
+ * set (etr_shard_set_create) bundles the G mapped shard pointers; an etr_table whose ``reserved``
+ * field carries the shard-set id and whose ``rows`` is the GLOBAL row count is then consumed
+ * directly by etr_gather_fm_forward (single-hot) and by etr_fm_fused_backward_apply(apply = 0):
+ * the kernels fetch row ``id`` from shard ``id mod G`` at local row ``id div G`` with ordinary
+ * 128-bit loads over NVLink -- the gather and the exchange are ONE kernel, there is no
+ * all-to-all and nothing is read back to the host.
+ * Backward: etr_shard_push writes this rank's deduplicated gradient rows (and local row ids)
+ * into its own region of each owner's mailbox (plain peer stores; slots from local counters),
+ * then publishes the counts.  After a cross-rank barrier (the dense-gradient all-reduce), the
+ * owner pads the unused slots (etr_shard_mailbox_pad, id -1) and runs the ordinary
+ * etr_sparse_plan / segment-reduce / Adam over its mailbox.                                   */
+int etr_peer_alloc(etr_ctx* ctx, int64_t bytes, void** d_ptr, void* handle64);
+int etr_peer_open(etr_ctx* ctx, const void* handle64, void** d_ptr);
+int etr_peer_close(etr_ctx* ctx, void* d_ptr);
+int etr_peer_free(etr_ctx* ctx, void* d_ptr);
+int etr_shard_set_create(etr_ctx* ctx, const void* const* h_shard_ptrs, int32_t world, int32_t rank,
+                         int64_t rows_global, int32_t* out_id);
+int etr_shard_push(etr_ctx* ctx, const int64_t* d_unique_ids, const int32_t* d_n_unique, int64_t max_unique,
+                   const float* d_unique_grad, int32_t ld, int32_t world, int32_t cap,
+                   int64_t* const* h_ids_mb, float* const* h_grads_mb, int32_t* const* h_counts_mb,
+                   int32_t* d_local_cnt, void* stream);
+int etr_shard_mailbox_pad(etr_ctx* ctx, int64_t* d_ids, const int32_t* d_counts, int32_t world, int32_t cap,
+                          void* stream);
+
 #ifdef __cplusplus
 }
 #endif
