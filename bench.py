@@ -175,7 +175,10 @@ def workload_config(args, B, graph):
             "mlp": ("layer 1 on tcgen05 (bf16 operands, fp32 accumulate), tail layers fp32" if getattr(args, "mlp", "bf16") == "bf16"
                     else "fp32 SIMT"), "id_distribution": args.dist,
             "apply_mode": "rowwise Adam",
-            "parallelism": (f"dp{args.gpus} batch x row-sharded table (id mod {args.gpus}), NCCL all-to-all"
+            "parallelism": ((f"dp{args.gpus} batch x row-sharded table (id mod {args.gpus}), "
+                             + ("rows fetched by the gather kernel from NVLink peer memory, gradient rows pushed to the "
+                                "owners' mailboxes, device-side barriers (no NCCL in the step)"
+                                if getattr(args, "shard", "peer") == "peer" else "NCCL all-to-all"))
                             if args.gpus > 1 else "dp1"),
             "l2": "L2 flushed (512 MiB write) before every timed step", "cuda_graph": graph}
 
@@ -287,6 +290,8 @@ def main():
                     help="first MLP layer: bf16 tcgen05 tensor cores (fp32 accumulate) or the fp32 SIMT exact-parity path")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-budget", type=float, default=12.0)
+    ap.add_argument("--shard", default="peer", choices=["peer", "a2a"],
+                    help="N > 1: 'peer' = gather over NVLink peer memory (CUDA IPC), 'a2a' = NCCL all-to-all exchange")
     ap.add_argument("--config", default="c2", choices=["c2", "c3"],
                     help="c2 = DeepFM (the headline, BASELINE configs[1]); c3 = DCN-matrix bf16 tensor-core cross")
     args = ap.parse_args()
@@ -317,7 +322,8 @@ def main():
     # data-parallel (per-GPU batch fixed: weak scaling); ids and rows cross NVLink in two NCCL
     # all-to-alls per direction, dense gradients are all-reduced.
     layer = L.DeepFMRankingLayer(names, feature_dims=V, embedding_dims=K_EMB, continuous_features=cont,
-                                 seed=1, check_ids=False, mlp_precision=args.mlp, shard=(world > 1))
+                                 seed=1, check_ids=False, mlp_precision=args.mlp,
+                                 shard=(args.shard if world > 1 else None))
     rt = layer.rt
     n_batches = 6
     host = make_batches(n_batches, B, args.dist, seed=SEED + 17 * rank)
@@ -331,7 +337,8 @@ def main():
         ids = torch.from_numpy(np.ascontiguousarray(X.T)).to(dev)            # field-major [F,B]
         dev_batches.append((ids, torch.from_numpy(np.ascontiguousarray(Xc.T)).to(dev), torch.from_numpy(y).to(dev)))
 
-    use_graph = (not args.no_graph) and world == 1      # the sharded step syncs split sizes on the host
+    # the all-to-all sharded step syncs split sizes on the host (no graph); the peer-memory step does not
+    use_graph = (not args.no_graph) and (world == 1 or args.shard == "peer")
     trainer = L.Trainer(layer, lr=1e-3, apply_mode="rowwise", graph=use_graph)
     flush = torch.empty(512 << 20, dtype=torch.uint8, device=dev)
 
@@ -434,7 +441,7 @@ def main():
     id_batches = []
     for i in range(n_batches):
         ids_t = dev_batches[i][0]
-        if world > 1:
+        if world > 1 and args.shard != "peer":
             ids_t = ids_t // world                    # local rows of this rank's shard (kernel-only timing)
         id_batches.append(IdsBatch(rt, ids_t, B, F, 1, 1, B, 1))
     kt = []
@@ -483,7 +490,8 @@ def main():
                 "ms_per_step": e2e_ms / args.steps, "last_loss": last},
         "gpu_launches": launches_per_step * args.steps,
         "gpu_launches_per_step": launches_per_step,
-        "roofline": {"bound": "hbm", "kernel": "gather_fm_fwd_kernel (gather + FM terms + Flatten, one launch)",
+        "roofline": {"bound": "hbm", "kernel": "gather_fm_fwd_stream_kernel (gather + FM terms + Flatten, one launch)"
+                     + (f"; rows of the {world - 1} other shards come over NVLink" if world > 1 and args.shard == "peer" else ""),
                      "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                      "traffic": None, "peak_source": peak_src, "kernel_ms": k_ms,
                      "algorithmic_bytes_per_launch": (alg_fm + alg_flat) * B,

@@ -50,15 +50,24 @@ class _Layer:
         self.check_ids = bool(kwargs.pop("check_ids", True))
         self.fused_apply = bool(kwargs.pop("fused_apply", True))     # FM family: fused backward+reduce+Adam
         self.name = kwargs.pop("name", type(self).__name__)
-        # row-sharded tables: shard=True (world/rank from torch.distributed) or shard=(world, rank)
+        # row-sharded tables: shard=True | "a2a" (NCCL all-to-all exchange) | "peer" (rows fetched by the
+        # gather kernel itself from NVLink peer memory); world/rank from torch.distributed, or
+        # shard=(world, rank) / shard=("peer", world, rank)
         shard = kwargs.pop("shard", None)
-        self.shard_spec = None
+        self.shard_spec, self.shard_mode = None, None
         if shard:
+            mode = "a2a"
+            if isinstance(shard, str):
+                mode, shard = shard, True
+            elif isinstance(shard, (tuple, list)) and isinstance(shard[0], str):
+                mode, shard = shard[0], tuple(shard[1:])
+            assert mode in ("a2a", "peer"), mode
             if shard is True:
                 import torch.distributed as dist
                 shard = (dist.get_world_size(), dist.get_rank())
-            self.shard_spec = (int(shard[0]), int(shard[1]))
+            self.shard_spec, self.shard_mode = (int(shard[0]), int(shard[1])), mode
         self.shard = None
+        self.peer = None
         kwargs.pop("trainable", None)
         kwargs.pop("dtype", None)
         if kwargs:
@@ -144,10 +153,15 @@ class FMRankingLayer(_Layer):
         k = self.embedding_dims
         self.params.add("bias", glorot_uniform((1,), self.gen, self.rt.device))
         if self.shard_spec:
-            from .sharded import ShardedTable
-            self.shard = ShardedTable(self.rt, self.feature_dims, k + 1, self.shard_spec[0], self.shard_spec[1],
-                                      self.table_dtype)
-            self.table = self.shard.local                   # this rank's rows r, r+G, r+2G, ...
+            from .sharded import PeerShardedTable, ShardedTable
+            if self.shard_mode == "peer":
+                assert self.table_dtype == torch.float32, "peer-sharded tables are fp32 in this round"
+                self.peer = PeerShardedTable(self.rt, self.feature_dims, k + 1, self.shard_spec[0], self.shard_spec[1])
+                self.table = self.peer                      # kernels see the GLOBAL table; views are the local rows
+            else:
+                self.shard = ShardedTable(self.rt, self.feature_dims, k + 1, self.shard_spec[0], self.shard_spec[1],
+                                          self.table_dtype)
+                self.table = self.shard.local               # this rank's rows r, r+G, r+2G, ...
             shard_gen = torch.Generator(device=self.rt.device)
             shard_gen.manual_seed(self.seed * 1000003 + self.shard_spec[1])
             self.table.init_uniform(-0.05, 0.05, shard_gen)
@@ -212,6 +226,12 @@ class FMRankingLayer(_Layer):
             return self.table, ids, None
         return self.shard.lookup(ids)
 
+    def _fused_grad(self, fused: FusedFMGrad):
+        if self.peer is None:
+            return fused
+        from .sharded import PeerFMGrad
+        return PeerFMGrad(self.peer, fused)
+
     def _table_grad(self, bag: torch.Tensor) -> SparseGrad:
         if self.shard is None:
             sg = SparseGrad(self.table, self._ctx["ids"], bag)
@@ -227,7 +247,9 @@ class FMRankingLayer(_Layer):
         check(self.rt.lib.etr_colsum_f32(self.rt.ctx, dl.data_ptr(), ids.B, 1, 1, self.params.g("bias").data_ptr(),
                                          self.rt.stream))
         if self._ctx.get("sumv") is not None:           # fused backward + segment reduction + Adam
-            return [FusedFMGrad(self.table, ids, self.embedding_dims, dl, self._ctx["sumv"], plan=self._ctx["plan"])]
+            return [self._fused_grad(FusedFMGrad(self.table, ids, self.embedding_dims, dl, self._ctx["sumv"],
+                                                 plan=self._ctx["plan"]))]
+        assert self.peer is None, "peer-sharded tables need the fused FM gradient (single-hot ids, fp32, k % 4 == 0)"
         bag = gather_fm_backward(self._ctx["table"], self.embedding_dims, True, ids, dlogit=dl)
         return [self._table_grad(bag)]
 
@@ -302,8 +324,9 @@ class DeepFMRankingLayer(FMRankingLayer):
         dx = self.MLP_layer1.backward(dh)                    # [B, pad + C + F*k]
         check(rt.lib.etr_colsum_f32(rt.ctx, dl.data_ptr(), ids.B, 1, 1, self.params.g("bias").data_ptr(), rt.stream))
         if self._ctx.get("sumv") is not None and col0 % 4 == 0 and dx.stride(0) % 4 == 0:
-            return [FusedFMGrad(self.table, ids, self.embedding_dims, dl, self._ctx["sumv"], dx, col0,
-                                plan=self._ctx["plan"])]
+            return [self._fused_grad(FusedFMGrad(self.table, ids, self.embedding_dims, dl, self._ctx["sumv"], dx, col0,
+                                                 plan=self._ctx["plan"]))]
+        assert self.peer is None, "peer-sharded tables need the fused FM gradient (single-hot ids, fp32, k % 4 == 0)"
         bag = gather_fm_backward(self._ctx["table"], self.embedding_dims, True, ids, dlogit=dl, dflat=dx,
                                  flat_col0=col0)
         return [self._table_grad(bag)]
@@ -938,7 +961,9 @@ class Trainer:
         self.use_graph = graph
         # data parallel over the ranks of a sharded layer: local batches, global-mean loss
         self.dp_world = layer.shard_spec[0] if getattr(layer, "shard_spec", None) else 1
-        assert not (graph and self.dp_world > 1), "the sharded step syncs split sizes on the host: no CUDA graph"
+        self.peer = getattr(layer, "peer", None)      # peer-memory sharding: nothing syncs with the host
+        assert not (graph and self.dp_world > 1 and self.peer is None), \
+            "the all-to-all sharded step syncs split sizes on the host: no CUDA graph (use shard='peer')"
         self.depth = 2 if graph else 1
         self._graphs: Dict[tuple, list] = {}
         self._copy_stream = self._d2h_stream = None
@@ -967,10 +992,19 @@ class Trainer:
         if self.dp_world > 1:
             dlogit.mul_(1.0 / self.dp_world)          # the loss is the mean over the GLOBAL batch
         grads = self.layer.backward(dlogit)
-        if self.dp_world > 1:
+        if self.peer is not None:
+            # rows -> owners' mailboxes, dense grads -> every peer's slot; ONE device-side barrier
+            for g in grads:
+                g.push()
+            self.peer.allreduce_push(self.layer.params.grad)
+            self.peer.barrier()
+            self.peer.allreduce_sum(self.layer.params.grad)
+        elif self.dp_world > 1:
             import torch.distributed as dist
             dist.all_reduce(self.layer.params.grad)   # replicated dense variables: sum of the ranks' grads
         self.apply_gradients(grads)
+        if self.peer is not None:
+            self.peer.barrier()                       # owners have applied: shards and mailboxes are free again
         if sl is not None and not torch.cuda.is_current_stream_capturing():
             sl.used = True
             sl.compute_done.record(torch.cuda.current_stream(rt.device))
@@ -985,6 +1019,9 @@ class Trainer:
         for g in grads:
             if isinstance(g, FusedFMGrad) and self.mode == _lib.ADAM_ROWWISE:
                 g.apply(d_lr, self.b1, self.b2, self.eps)
+                continue
+            if hasattr(g, "push"):                    # PeerFMGrad: owner-side mailbox reduce + Adam
+                g.apply(d_lr, self.b1, self.b2, self.eps, self.mode)
                 continue
             key = (id(g.ids), g.table.rows)
             g.reduce(plans.get(key))
@@ -1092,7 +1129,7 @@ class Trainer:
             if sl.graph is None:
                 torch.cuda.synchronize(self.rt.device)
                 g = torch.cuda.CUDAGraph()
-                with torch.cuda.graph(g):
+                with torch.cuda.graph(g, capture_error_mode="thread_local"):
                     loss = self._eager_step(batch)
                     sl.loss.copy_(loss)
                 sl.graph = g                  # capture does not execute: the replay below runs the step

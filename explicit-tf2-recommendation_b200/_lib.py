@@ -93,6 +93,9 @@ PROTOTYPES = {
     "etr_shard_push": (C.c_int, [_vp, _vp, _vp, _i64, _vp, _i32, _i32, _i32, C.POINTER(_vp), C.POINTER(_vp),
                                  C.POINTER(_vp), _vp, _vp]),
     "etr_shard_mailbox_pad": (C.c_int, [_vp, _vp, _vp, _i32, _i32, _vp]),
+    "etr_peer_barrier": (C.c_int, [_vp, C.POINTER(_vp), _vp, _vp, _i32, _i32, _vp]),
+    "etr_peer_allreduce_push": (C.c_int, [_vp, _vp, _i64, C.POINTER(_vp), _i32, _i32, _vp]),
+    "etr_peer_allreduce_sum": (C.c_int, [_vp, _vp, _i64, _i32, _vp, _vp]),
     "etr_shard_partition": (C.c_int, [_vp, _vp, _i64, _i32, _i64, _vp, _vp, _vp, _vp, _vp]),
     "etr_cross_mat_bwd_elementwise": (C.c_int, [_vp, _vp, _vp, _vp, _i64, _vp, _vp, _vp]),
 }

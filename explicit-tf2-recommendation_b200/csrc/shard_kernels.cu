@@ -120,6 +120,63 @@ __global__ void __launch_bounds__(256) shard_mailbox_pad_kernel(long long* ids, 
   }
 }
 
+// ---- cross-rank barrier over peer memory: rank r stores the new epoch into flags[r] of every
+// peer (release, system scope) and waits until every peer's epoch has arrived in its own flags.
+// One warp; bounded spin (a missing peer flags error -3 instead of hanging the GPU).
+struct BarrierParams {
+  unsigned* peer_flags[16];
+  unsigned* my_flags;
+  unsigned* epoch;
+  int world, rank;
+  unsigned long long* err;
+};
+__global__ void peer_barrier_kernel(const BarrierParams p) {
+  const int g = threadIdx.x;
+  const unsigned e = *reinterpret_cast<volatile unsigned*>(p.epoch) + 1u;
+  __syncwarp();
+  if (g == 0) *p.epoch = e;
+  if (g < p.world) {
+    __threadfence_system();
+    asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p.peer_flags[g] + p.rank), "r"(e) : "memory");
+    const long long t0 = clock64();
+    for (;;) {
+      unsigned v;
+      asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p.my_flags + g) : "memory");
+      if ((int)(v - e) >= 0) break;
+      if (clock64() - t0 > 40000000000ll) {          // ~20 s: a peer never arrived
+        flag_bad_id(p.err, -3);
+        break;
+      }
+      __nanosleep(64);
+    }
+  }
+}
+
+// ---- small all-reduce over peer memory (replicated dense gradients): every rank stores its vector
+// into slot [rank] of every peer, barrier, then sums the G slots in rank order (deterministic, so
+// the replicas stay bit-identical).
+struct ArPushParams {
+  float* slots[16];          // peer g's slot buffer [world][n]
+  const float* src;
+  long long n;
+  int world, rank;
+};
+__global__ void __launch_bounds__(256) peer_allreduce_push_kernel(const ArPushParams p) {
+  const long long total = p.n * p.world;
+  for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (long long)gridDim.x * blockDim.x) {
+    const int g = (int)(t / p.n);
+    const long long i = t - (long long)g * p.n;
+    p.slots[g][(long long)p.rank * p.n + i] = p.src[i];
+  }
+}
+__global__ void __launch_bounds__(256) peer_allreduce_sum_kernel(const float* slots, long long n, int world, float* dst) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    float acc = slots[i];
+    for (int g = 1; g < world; ++g) acc += slots[(long long)g * n + i];
+    dst[i] = acc;
+  }
+}
+
 }  // namespace etr
 
 using namespace etr;
@@ -211,6 +268,45 @@ int etr_shard_mailbox_pad(etr_ctx* ctx, int64_t* d_ids, const int32_t* d_counts,
   ETR_CHECK_ARG(ctx && d_ids && d_counts && world >= 1 && cap > 0, "bad argument");
   shard_mailbox_pad_kernel<<<grid_for((long long)world * cap, 256, ctx->sm_count, 8), 256, 0, (cudaStream_t)stream>>>(
       (long long*)d_ids, d_counts, world, cap);
+  ETR_LAUNCH_CHECK(ctx);
+  return ETR_OK;
+}
+
+int etr_peer_barrier(etr_ctx* ctx, uint32_t* const* h_peer_flags, uint32_t* d_my_flags, uint32_t* d_epoch,
+                     int32_t world, int32_t rank, void* stream) {
+  ETR_CHECK_ARG(ctx && h_peer_flags && d_my_flags && d_epoch, "NULL argument");
+  ETR_CHECK_ARG(world >= 1 && world <= 16 && rank >= 0 && rank < world, "world must be in [1,16]");
+  BarrierParams p;
+  memset(&p, 0, sizeof(p));
+  for (int g = 0; g < world; ++g) {
+    ETR_CHECK_ARG(h_peer_flags[g] != nullptr, "NULL peer flag pointer");
+    p.peer_flags[g] = h_peer_flags[g];
+  }
+  p.my_flags = d_my_flags; p.epoch = d_epoch; p.world = world; p.rank = rank; p.err = ctx->d_err;
+  peer_barrier_kernel<<<1, 32, 0, (cudaStream_t)stream>>>(p);
+  ETR_LAUNCH_CHECK(ctx);
+  return ETR_OK;
+}
+
+int etr_peer_allreduce_push(etr_ctx* ctx, const float* d_src, int64_t n, float* const* h_peer_slots, int32_t world,
+                            int32_t rank, void* stream) {
+  ETR_CHECK_ARG(ctx && d_src && h_peer_slots && n > 0, "bad argument");
+  ETR_CHECK_ARG(world >= 1 && world <= 16 && rank >= 0 && rank < world, "world must be in [1,16]");
+  ArPushParams p;
+  memset(&p, 0, sizeof(p));
+  for (int g = 0; g < world; ++g) {
+    ETR_CHECK_ARG(h_peer_slots[g] != nullptr, "NULL peer slot pointer");
+    p.slots[g] = h_peer_slots[g];
+  }
+  p.src = d_src; p.n = n; p.world = world; p.rank = rank;
+  peer_allreduce_push_kernel<<<grid_for(n * world, 256, ctx->sm_count, 4), 256, 0, (cudaStream_t)stream>>>(p);
+  ETR_LAUNCH_CHECK(ctx);
+  return ETR_OK;
+}
+
+int etr_peer_allreduce_sum(etr_ctx* ctx, const float* d_slots, int64_t n, int32_t world, float* d_dst, void* stream) {
+  ETR_CHECK_ARG(ctx && d_slots && d_dst && n > 0 && world >= 1, "bad argument");
+  peer_allreduce_sum_kernel<<<grid_for(n, 256, ctx->sm_count, 4), 256, 0, (cudaStream_t)stream>>>(d_slots, n, world, d_dst);
   ETR_LAUNCH_CHECK(ctx);
   return ETR_OK;
 }

@@ -108,12 +108,21 @@ class EmbeddingTable:
     (2.FM/CustomLayers.py:129-134).  For the FM family the [V,1] ``w`` Embedding
     is fused in as column ``k`` (one DRAM burst serves v and w)."""
 
-    def __init__(self, rt: Runtime, rows: int, width: int, dtype: torch.dtype = torch.float32):
+    def __init__(self, rt: Runtime, rows: int, width: int, dtype: torch.dtype = torch.float32,
+                 data: Optional[torch.Tensor] = None, row_align: int = 16):
+        """``row_align`` (bytes, a multiple of 16): rows start on that boundary.  Random 64-byte
+        accesses are bound by DRAM activates, not bytes, so a row that straddles two 128-byte lines
+        (an 80-byte FM row at 80-byte stride does 37 % of the time) costs a second access: the FM
+        family pads its [v_0..v_15, w] rows to 128 bytes."""
         assert dtype in _TORCH2ETR
         self.rt, self.rows, self.width, self.dtype = rt, int(rows), int(width), dtype
-        epc = 16 // torch.empty((), dtype=dtype).element_size()       # elements per 16-byte chunk
+        esz = torch.empty((), dtype=dtype).element_size()
+        assert row_align % 16 == 0
+        epc = row_align // esz                                        # elements per alignment unit
         self.stride = ((self.width + epc - 1) // epc) * epc
-        self.data = rt.zeros((self.rows, self.stride), dtype)
+        if data is not None:          # caller-owned storage (e.g. a peer-mapped shard), already zeroed
+            assert data.shape == (self.rows, self.stride) and data.dtype == dtype and data.is_contiguous()
+        self.data = rt.zeros((self.rows, self.stride), dtype) if data is None else data
         self._m = self._v = None
 
     def desc(self) -> _lib.etr_table:

@@ -172,3 +172,204 @@ class ShardedTable:
             recv = pad
         lids = IdsBatch(self.rt, route.recv_rows, route.n_recv, 1, 1, 1, 1, 1)
         return SparseGrad(self.local, lids, recv)
+
+
+# ===========================================================================
+# Peer-memory form (NVLink / NVSwitch, CUDA IPC): no all-to-all at all.
+class _CudaArray:
+    """__cuda_array_interface__ shim: lets torch view a raw device pointer without a copy."""
+
+    def __init__(self, ptr: int, shape, typestr: str, owner=None):
+        self.__cuda_array_interface__ = {"data": (int(ptr), False), "shape": tuple(shape), "typestr": typestr,
+                                         "version": 2, "strides": None}
+        self._owner = owner
+
+
+class PeerBuffer:
+    """A cudaMalloc'ed, zero-initialised buffer of this rank, exported over CUDA IPC and mapped by
+    every rank of the group: ``peer[g]`` is rank g's buffer as seen from here (``peer[rank]`` = own)."""
+
+    def __init__(self, rt, nbytes: int, world: int, rank: int, group=None):
+        self.rt, self.nbytes, self.world, self.rank = rt, int(nbytes), world, rank
+        ptr, handle = C.c_void_p(), (C.c_char * 64)()
+        check(rt.lib.etr_peer_alloc(rt.ctx, self.nbytes, C.byref(ptr), handle))
+        self.ptr = int(ptr.value)
+        handles: List[Optional[bytes]] = [None] * world
+        if world > 1:
+            dist.all_gather_object(handles, bytes(handle.raw), group=group)
+        self.peer: List[int] = []
+        for g in range(world):
+            if g == rank:
+                self.peer.append(self.ptr)
+            else:
+                q = C.c_void_p()
+                check(rt.lib.etr_peer_open(rt.ctx, handles[g], C.byref(q)))
+                self.peer.append(int(q.value))
+
+    def tensor(self, shape, dtype: torch.dtype) -> torch.Tensor:
+        typestr = {torch.float32: "<f4", torch.int64: "<i8", torch.int32: "<i4", torch.uint8: "|u1"}[dtype]
+        return torch.as_tensor(_CudaArray(self.ptr, shape, typestr, self), device=self.rt.device)
+
+    def peer_array(self, byte_offset: int = 0):
+        return (C.c_void_p * self.world)(*[q + byte_offset for q in self.peer])
+
+
+class PeerShardedTable:
+    """A [rows_global, width] fp32 table row-sharded over the GPUs of one box (owner = id mod G,
+    local row = id div G) whose shards are mapped into every rank through CUDA IPC.
+
+    forward : the fused gather + FM kernel reads row ``id`` straight from its owner's HBM over
+              NVLink (etr_table.reserved = shard-set id) -- gather and exchange are ONE kernel;
+    backward: the fused backward exports this rank's de-duplicated gradient rows (re-reading the
+              rows the same way), ``etr_shard_push`` stores them into the owners' mailboxes;
+    apply   : after a device-side barrier each owner sorts / segment-reduces its mailbox and runs
+              Adam on its own shard; a second barrier closes the step.
+    Nothing is read back to the host, so the whole data-parallel step is one CUDA graph."""
+
+    def __init__(self, rt, rows_global: int, width: int, world: int, rank: int, group=None):
+        from .runtime import EmbeddingTable
+        assert world & (world - 1) == 0, "peer-sharded tables need a power-of-two number of ranks"
+        self.rt, self.world, self.rank, self.group = rt, world, rank, group
+        self.rows, self.width, self.dtype = int(rows_global), int(width), torch.float32
+        self.stride = (self.width + 3) // 4 * 4
+        self.local_rows_max = (self.rows + world - 1) // world          # same allocation on every rank
+        self.local_rows = (self.rows - rank + world - 1) // world
+        self._shard = PeerBuffer(rt, max(self.local_rows_max, 1) * self.stride * 4, world, rank, group)
+        data = self._shard.tensor((max(self.local_rows_max, 1), self.stride), torch.float32)
+        self.local = EmbeddingTable(rt, max(self.local_rows, 1), self.width, torch.float32,
+                                    data=data[: max(self.local_rows, 1)])
+        sid = C.c_int32(0)
+        check(rt.lib.etr_shard_set_create(rt.ctx, self._shard.peer_array(), world, rank, self.rows, C.byref(sid)))
+        self.shard_set = int(sid.value)
+        # barrier state + dense all-reduce slots + gradient mailbox (allocated on first use)
+        self._flags = PeerBuffer(rt, 64 * 4, world, rank, group)
+        self._epoch = rt.zeros((1,), torch.int32)
+        self._flag_ptrs = self._flags.peer_array()
+        self._ar = None
+        self._mb = None
+        self.cap = 0
+        if world > 1:
+            dist.barrier(group=group)
+
+    # -- EmbeddingTable-like surface for the kernels ------------------------
+    @property
+    def data(self) -> torch.Tensor:
+        return self.local.data
+
+    @property
+    def m(self):
+        return self.local.m
+
+    @property
+    def v(self):
+        return self.local.v
+
+    @property
+    def grad_ld(self) -> int:
+        return self.stride
+
+    def desc(self) -> _lib.etr_table:
+        return _lib.etr_table(self._shard.ptr, self.rows, self.width, self.stride, _lib.ETR_F32, self.shard_set)
+
+    def cols(self, c0: int, c1: int) -> torch.Tensor:
+        return self.local.data[:, c0:c1]
+
+    def init_uniform(self, lo, hi, gen, c0=0, c1=None):
+        self.local.init_uniform(lo, hi, gen, c0, c1)
+
+    def load_global(self, full: torch.Tensor, c0: int = 0):
+        mine = full[self.rank:: self.world].to(self.rt.device)
+        self.local.data[: mine.shape[0], c0:c0 + mine.shape[1]] = mine.to(torch.float32)
+
+    # -- collectives over peer memory ---------------------------------------
+    def barrier(self):
+        rt = self.rt
+        check(rt.lib.etr_peer_barrier(rt.ctx, self._flag_ptrs, self._flags.ptr, self._epoch.data_ptr(), self.world,
+                                      self.rank, rt.stream))
+
+    def _ensure_ar(self, n: int):
+        if self._ar is None or self._ar[1] < n:
+            torch.cuda.synchronize(self.rt.device)
+            buf = PeerBuffer(self.rt, self.world * n * 4, self.world, self.rank, self.group)
+            self._ar = (buf, n, buf.peer_array())
+            if self.world > 1:
+                dist.barrier(group=self.group)
+        return self._ar
+
+    def allreduce_push(self, vec: torch.Tensor):
+        """stage 1 of the dense-gradient all-reduce (before the mid-step barrier)"""
+        assert vec.dtype == torch.float32 and vec.is_contiguous()
+        buf, n, ptrs = self._ensure_ar(vec.numel())
+        assert n == vec.numel(), "the dense-gradient vector must keep its size"
+        rt = self.rt
+        check(rt.lib.etr_peer_allreduce_push(rt.ctx, vec.data_ptr(), n, ptrs, self.world, self.rank, rt.stream))
+
+    def allreduce_sum(self, vec: torch.Tensor):
+        """stage 2 (after the barrier): vec = sum over ranks, summed in rank order on every rank"""
+        buf, n, _ = self._ar
+        rt = self.rt
+        check(rt.lib.etr_peer_allreduce_sum(rt.ctx, buf.ptr, n, self.world, vec.data_ptr(), rt.stream))
+
+    # -- gradient mailbox -----------------------------------------------------
+    def ensure_mailbox(self, n_slots: int):
+        """[world][cap] regions per owner; cap = 1.5x the balanced share of a batch's slots (+1024).
+        Collective (every rank calls it with the same n_slots)."""
+        cap = (3 * n_slots // (2 * self.world) + 1024 + 63) // 64 * 64
+        if self._mb is not None and cap <= self.cap:
+            return
+        assert not torch.cuda.is_current_stream_capturing(), "size the mailbox with an eager step before capture"
+        torch.cuda.synchronize(self.rt.device)
+        W, ld, rt = self.world, self.stride, self.rt
+        ids = PeerBuffer(rt, W * cap * 8, W, self.rank, self.group)
+        grads = PeerBuffer(rt, W * cap * ld * 4, W, self.rank, self.group)
+        counts = PeerBuffer(rt, 64 * 4, W, self.rank, self.group)
+        self._mb = {
+            "ids": ids, "grads": grads, "counts": counts,
+            "ids_t": ids.tensor((W * cap,), torch.int64), "grads_t": grads.tensor((W * cap, ld), torch.float32),
+            "counts_t": counts.tensor((W,), torch.int32),
+            "ids_ptrs": ids.peer_array(self.rank * cap * 8), "grads_ptrs": grads.peer_array(self.rank * cap * ld * 4),
+            "counts_ptrs": counts.peer_array(self.rank * 4), "local_cnt": rt.zeros((W,), torch.int32),
+        }
+        self.cap = cap
+        if W > 1:
+            dist.barrier(group=self.group)
+
+    def push(self, unique_ids: torch.Tensor, n_unique: torch.Tensor, max_unique: int, unique_grad: torch.Tensor):
+        rt, mb = self.rt, self._mb
+        check(rt.lib.etr_shard_push(rt.ctx, unique_ids.data_ptr(), n_unique.data_ptr(), max_unique,
+                                    unique_grad.data_ptr(), unique_grad.shape[1], self.world, self.cap, mb["ids_ptrs"],
+                                    mb["grads_ptrs"], mb["counts_ptrs"], mb["local_cnt"].data_ptr(), rt.stream))
+
+    def apply_mailbox(self, d_lr_t: torch.Tensor, b1: float, b2: float, eps: float, mode: int):
+        """owner side: pad unused slots, sorted-ID plan over the mailbox, segment reduction, Adam"""
+        from .runtime import IdsBatch, SparsePlan
+        rt, mb, W, cap, ld = self.rt, self._mb, self.world, self.cap, self.stride
+        check(rt.lib.etr_shard_mailbox_pad(rt.ctx, mb["ids_t"].data_ptr(), mb["counts_t"].data_ptr(), W, cap, rt.stream))
+        lids = IdsBatch(rt, mb["ids_t"], W * cap, 1, 1, 1, 1, 1, pad_id=-1)
+        plan = SparsePlan(rt, lids, self.local.rows)
+        ug = rt.empty((W * cap, ld))
+        check(rt.lib.etr_sparse_segment_reduce(rt.ctx, plan.sorted_bag.data_ptr(), plan.seg_start.data_ptr(),
+                                               plan.counts.data_ptr(), plan.n_slots, mb["grads_t"].data_ptr(), ld,
+                                               ug.data_ptr(), rt.stream))
+        t = self.local.desc()
+        check(rt.lib.etr_sparse_adam_apply(rt.ctx, C.byref(t), self.local.m.data_ptr(), self.local.v.data_ptr(),
+                                           plan.unique_ids.data_ptr(), plan.counts.data_ptr(), plan.n_slots,
+                                           ug.data_ptr(), ld, 0.0, d_lr_t.data_ptr(), b1, b2, eps, mode, rt.stream))
+        self.last_plan, self.last_unique_grad = plan, ug
+
+
+class PeerFMGrad:
+    """FM-family table gradient of a peer-sharded table: ``push`` exports this rank's de-duplicated
+    rows (fused backward, apply = 0) into the owners' mailboxes; ``apply`` is the owner-side update."""
+
+    def __init__(self, table: PeerShardedTable, fused):
+        self.table, self.fused = table, fused            # fused: runtime.FusedFMGrad built on the sharded desc
+
+    def push(self):
+        f, T = self.fused, self.table
+        f.reduce()                                        # unique rows of this rank's batch (global ids)
+        T.ensure_mailbox(f.plan.n_slots)
+        T.push(f.plan.unique_ids, f.plan.counts, f.plan.n_slots, f.unique_grad)
+
+    def apply(self, d_lr_t, b1, b2, eps, mode=_lib.ADAM_ROWWISE):
+        self.table.apply_mailbox(d_lr_t, b1, b2, eps, mode)

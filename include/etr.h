@@ -366,6 +366,19 @@ int etr_shard_push(etr_ctx* ctx, const int64_t* d_unique_ids, const int32_t* d_n
                    int32_t* d_local_cnt, void* stream);
 int etr_shard_mailbox_pad(etr_ctx* ctx, int64_t* d_ids, const int32_t* d_counts, int32_t world, int32_t cap,
                           void* stream);
+/* Cross-rank barrier on the stream, over peer memory: every rank owns a flag array [world]
+ * (etr_peer_alloc, zero-initialised) and an epoch word; the kernel bumps the epoch, stores it into
+ * flags[rank] of every peer and waits (bounded: ~20 s, then error -3 is flagged) until all peers'
+ * epochs have arrived.  Graph-capturable; replaces a host-side or NCCL barrier in the step.    */
+int etr_peer_barrier(etr_ctx* ctx, uint32_t* const* h_peer_flags, uint32_t* d_my_flags, uint32_t* d_epoch,
+                     int32_t world, int32_t rank, void* stream);
+/* All-reduce (sum) of the small replicated dense-gradient vector over peer memory: push stores
+ * d_src into slot [rank] of every peer's slot buffer [world][n]; after an etr_peer_barrier,
+ * sum adds the G slots in rank order (deterministic: replicas stay bit-identical).  Replaces
+ * the per-variable all-reduce a MirroredStrategy would insert after 2.FM/ModelManager.py:176. */
+int etr_peer_allreduce_push(etr_ctx* ctx, const float* d_src, int64_t n, float* const* h_peer_slots, int32_t world,
+                            int32_t rank, void* stream);
+int etr_peer_allreduce_sum(etr_ctx* ctx, const float* d_slots, int64_t n, int32_t world, float* d_dst, void* stream);
 
 #ifdef __cplusplus
 }

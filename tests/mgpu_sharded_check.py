@@ -28,53 +28,66 @@ def main():
 
     F, k, V, C, B = 26, 16, 100003, 13, 4096
     names, cont = [f"f{i}" for i in range(F)], [f"c{i}" for i in range(C)]
-    sharded = L.DeepFMRankingLayer(names, V, k, continuous_features=cont, seed=3, shard=True, check_ids=False)
-    full = L.DeepFMRankingLayer(names, V, k, continuous_features=cont, seed=3, check_ids=False)
-    # identical global weights on every rank
-    g = torch.Generator(device="cuda").manual_seed(1234)
-    table = torch.empty(V, k + 1, device="cuda").uniform_(-0.05, 0.05, generator=g)
-    full.table.data[:, : k + 1] = table
-    sharded.shard.load_global(table)
-    sharded.params.value.copy_(full.params.value)
+    msgs = []
+    for mode, graph in (("a2a", False), ("peer", False), ("peer", True)):
+        sharded = L.DeepFMRankingLayer(names, V, k, continuous_features=cont, seed=3, shard=mode, check_ids=False)
+        full = L.DeepFMRankingLayer(names, V, k, continuous_features=cont, seed=3, check_ids=False)
+        # identical global weights on every rank
+        g = torch.Generator(device="cuda").manual_seed(1234)
+        table = torch.empty(V, k + 1, device="cuda").uniform_(-0.05, 0.05, generator=g)
+        full.table.data[:, : k + 1] = table
+        (sharded.peer if mode == "peer" else sharded.shard).load_global(table)
+        sharded.params.value.copy_(full.params.value)
+        torch.cuda.synchronize()
+        dist.barrier()                                  # every shard is loaded before anyone reads it
 
-    rng = np.random.default_rng(10 + rank)
-    def batch():
-        X = (rng.random((B, F)) ** 3 * V).astype(np.int64)
-        Xc = rng.normal(size=(B, C)).astype(np.float32)
-        y = (rng.random(B) < 0.3).astype(np.float32)
-        d = {n: torch.tensor(X[:, i]).cuda() for i, n in enumerate(names)}
-        d.update({n: torch.tensor(Xc[:, i]).cuda() for i, n in enumerate(cont)})
-        return d, torch.tensor(y).cuda()
+        rng = np.random.default_rng(10 + rank)
 
-    d, y = batch()
-    a = sharded(d)["output"]
-    b = full(d)["output"]
-    assert torch.equal(a, b), f"rank {rank}: sharded forward is not bit-exact ({(a - b).abs().max().item()})"
+        def batch():
+            X = (rng.random((B, F)) ** 3 * V).astype(np.int64)
+            Xc = rng.normal(size=(B, C)).astype(np.float32)
+            y = (rng.random(B) < 0.3).astype(np.float32)
+            d = {n: torch.tensor(X[:, i]).cuda() for i, n in enumerate(names)}
+            d.update({n: torch.tensor(Xc[:, i]).cuda() for i, n in enumerate(cont)})
+            return d, torch.tensor(y).cuda()
 
-    tr_s = L.Trainer(sharded, lr=1e-2)
-    tr_f = L.Trainer(full, lr=1e-2)
-    for step in range(3):
         d, y = batch()
-        ls = tr_s.train_step(d, y)
-        # the unsharded reference sees the global batch
-        gd = {}
-        for n, t in d.items():
-            parts = [torch.empty_like(t) for _ in range(world)]
-            dist.all_gather(parts, t)
-            gd[n] = torch.cat(parts)
-        ys = [torch.empty_like(y) for _ in range(world)]
-        dist.all_gather(ys, y)
-        lf = tr_f.train_step(gd, torch.cat(ys))
-        lsum = ls.clone()
-        dist.all_reduce(lsum)
-        assert abs(float(lsum.item()) / world - float(lf.item())) < 1e-5, (step, float(lsum.item()) / world, float(lf.item()))
-    mine = full.table.data[rank::world]
-    err_t = (sharded.table.data[: mine.shape[0]] - mine).abs().max().item()
-    err_d = (sharded.params.value - full.params.value).abs().max().item()
-    assert err_t < 2e-5 and err_d < 2e-5, (rank, err_t, err_d)       # lr 1e-2: < 0.2% of one Adam step
-    dist.barrier()
+        a = sharded(d)["output"]
+        b = full(d)["output"]
+        assert torch.equal(a, b), f"rank {rank} {mode}: sharded forward is not bit-exact ({(a - b).abs().max().item()})"
+
+        tr_s = L.Trainer(sharded, lr=1e-2, graph=graph)
+        tr_f = L.Trainer(full, lr=1e-2)
+        for step in range(6 if graph else 3):           # graph mode: 2 buffer sets x (2 eager + capture/replay)
+            d, y = batch()
+            ls = tr_s.train_step(d, y).clone()
+            # the unsharded reference sees the global batch
+            gd = {}
+            for n, t in d.items():
+                parts = [torch.empty_like(t) for _ in range(world)]
+                dist.all_gather(parts, t)
+                gd[n] = torch.cat(parts)
+            ys = [torch.empty_like(y) for _ in range(world)]
+            dist.all_gather(ys, y)
+            lf = tr_f.train_step(gd, torch.cat(ys))
+            lsum = ls.clone()
+            dist.all_reduce(lsum)
+            assert abs(float(lsum.item()) / world - float(lf.item())) < 1e-5, \
+                (mode, graph, step, float(lsum.item()) / world, float(lf.item()))
+        sharded.rt.poll_error()
+        mine = full.table.data[rank::world]
+        err_t = (sharded.table.data[: mine.shape[0]] - mine).abs().max().item()
+        err_d = (sharded.params.value - full.params.value).abs().max().item()
+        assert err_t < 2e-5 and err_d < 2e-5, (mode, graph, rank, err_t, err_d)   # lr 1e-2: < 0.2% of one Adam step
+        if mode == "peer":
+            # replicated dense variables must stay BIT-identical across ranks (deterministic rank-order sum)
+            ref = sharded.params.value.clone()
+            dist.broadcast(ref, 0)
+            assert torch.equal(ref, sharded.params.value), f"rank {rank}: dense replicas diverged"
+        dist.barrier()
+        msgs.append(f"{mode}{'+graph' if graph else ''}: table_err={err_t:.2e} dense_err={err_d:.2e}")
     if rank == 0:
-        print(f"MGPU_OK world={world} table_err={err_t:.2e} dense_err={err_d:.2e}")
+        print(f"MGPU_OK world={world} " + " | ".join(msgs))
     dist.destroy_process_group()
 
 

@@ -127,6 +127,49 @@ def test_fm_bf16_table(L):
     assert_close(out.cpu().numpy(), ref, FP32_RTOL, "bf16 rows, fp32 accumulate")
 
 
+# ----------------------------------------------- streaming single-hot kernel, every template shape
+@pytest.mark.parametrize("flat", [None, "float32", "bfloat16"])
+@pytest.mark.parametrize("dtype", ["float32", "bfloat16"])
+@pytest.mark.parametrize("B,F,k,has_w", [(1, 1, 8, True), (37, 26, 16, True), (1000, 39, 8, True), (513, 13, 32, True),
+                                         (130, 26, 64, False), (64, 3, 16, True), (2049, 9, 128, False)])
+def test_streaming_gather_every_shape(L, B, F, k, has_w, dtype, flat):
+    """gather_fm_fwd_stream_kernel<Elem, LPR, U, FLAT>: LPR in {2,4,8,16}, U in {8,13}, ragged tiles,
+    partial field batches, fp32 / bf16 rows, no / fp32 / bf16 flattened operand with front columns."""
+    from etr_b200.runtime import EmbeddingTable, IdsBatch, Runtime, gather_fm_forward
+    rt = Runtime.get()
+    tdt = torch.float32 if dtype == "float32" else torch.bfloat16
+    V = 4099
+    tab = EmbeddingTable(rt, V, k + (1 if has_w else 0), tdt)
+    g = torch.Generator(device=rt.device).manual_seed(5)
+    tab.init_uniform(-0.05, 0.05, g)
+    rng = np.random.default_rng(B * 131 + F)
+    X = torch.tensor(rng.integers(0, V, size=(B, F))).cuda()
+    ids = IdsBatch.from_matrix(rt, X)
+    C_ = 5
+    cont = torch.randn(B, C_, device=rt.device)
+    logit, prob, sumv = rt.empty((B,)), rt.empty((B, 1)), rt.empty((B, k))
+    fl = None
+    col0 = 8
+    if flat:
+        fl = torch.full((B, col0 + F * k), 7.0, device=rt.device, dtype=getattr(torch, flat))
+    bias = torch.tensor([0.125], device=rt.device)
+    gather_fm_forward(tab, k, has_w, ids, bias=bias, logit=logit, prob=prob, sumv=sumv, flat=fl, flat_col0=col0,
+                      cont=cont if flat else None)
+    rt.poll_error()
+    rows = tab.data[X].double()                              # [B,F,stride]
+    v = rows[..., :k]
+    S = v.sum(1)
+    z = 0.125 + 0.5 * ((S * S).sum(1) - (v * v).sum((1, 2)))
+    if has_w:
+        z = z + rows[..., k].sum(1)
+    assert_close(logit.cpu().numpy(), z.cpu().numpy(), FP32_RTOL, "logit")
+    assert_close(prob.cpu().numpy().ravel(), torch.sigmoid(z).cpu().numpy(), FP32_RTOL, "prob")
+    assert_close(sumv.cpu().numpy(), S.cpu().numpy(), FP32_RTOL, "sum_v")
+    if flat:
+        want = torch.cat([torch.zeros(B, col0 - C_, device=rt.device), cont, tab.data[X][..., :k].float().reshape(B, F * k)], 1)
+        assert torch.equal(fl, want.to(fl.dtype)), "flattened operand (front padding | dense | rows) must be exact"
+
+
 # --------------------------------------------------------------------- bags
 @pytest.mark.parametrize("pooling", ["sum", "mean"])
 @pytest.mark.parametrize("Lmax", [1, 5, 50])
