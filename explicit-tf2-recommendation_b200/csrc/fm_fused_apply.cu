@@ -119,10 +119,9 @@ struct RowState { float4 var, m, v; };
 __device__ __forceinline__ RowState fused_load_row(const FusedParams& p, long long row, int gl) {
   RowState st;
   if (p.world > 1) {
-    const long long lrow = row / p.world;
-    st.var = *reinterpret_cast<const float4*>(reinterpret_cast<const float*>(p.shard_base[(int)(row - lrow * p.world)]) +
-                                              lrow * p.stride + gl * 4);
-    st.m = st.v = make_float4(0.f, 0.f, 0.f, 0.f);
+    // peer-sharded table (export only): DEFERRED form -- the row is not read here at all (it may live
+    // in another GPU's HBM); the exported row is [P, sum_g] and the owner finishes dv = P - v * sum_g
+    st.var = st.m = st.v = make_float4(0.f, 0.f, 0.f, 0.f);
     return st;
   }
   st.var = *reinterpret_cast<const float4*>(p.table + row * p.stride + gl * 4);

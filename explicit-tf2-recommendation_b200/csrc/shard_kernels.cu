@@ -69,29 +69,40 @@ struct PushParams {
   unsigned long long* err;
 };
 
+// Slots are reserved per CTA: lane-group leaders count into shared-memory bins (one per owner), one
+// global atomicAdd per (CTA, owner) reserves the range.  (The first version did one global atomic
+// per row on G counters: 471 k same-address atomics = 232 us at N = 2.)  Slot order inside a source
+// region is arbitrary; nothing downstream depends on it (rows are unique within a source).
 template <int LPR>
 __global__ void __launch_bounds__(256) shard_push_kernel(const PushParams p) {
   constexpr int GPW = 32 / LPR;
+  constexpr int GPB = 8 * GPW;                          // lane groups (rows) per CTA iteration
+  __shared__ int bin[16], base[16];
   const int lane = threadIdx.x & 31;
   const int gl = lane % LPR, g = lane / LPR;
+  const int grp = (threadIdx.x >> 5) * GPW + g;
   const int nchunks = p.ld / 4;
   const int n_unique = *p.n_unique;
-  const long long group_global = ((long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5)) * GPW + g;
-  const long long ngroups = (long long)gridDim.x * (blockDim.x >> 5) * GPW;
-  const unsigned gmask = (LPR == 32) ? 0xffffffffu : (((1u << LPR) - 1u) << (g * LPR));
-  for (long long u0 = group_global - g; u0 < n_unique; u0 += ngroups) {      // warp-uniform trip count
-    const long long u = u0 + g;
+  for (long long u0 = (long long)blockIdx.x * GPB; u0 < n_unique; u0 += (long long)gridDim.x * GPB) {   // CTA-uniform
+    if (threadIdx.x < 16) bin[threadIdx.x] = 0;
+    __syncthreads();
+    const long long u = u0 + grp;
     const bool active = u < n_unique;
-    int slot = 0, owner = 0;
+    int owner = 0, off = 0;
     long long lrow = 0;
     if (active) {
       const long long id = p.unique_ids[u];
       owner = (int)(id % p.world);
       lrow = id / p.world;
-      if (gl == 0) slot = atomicAdd(&p.local_cnt[owner], 1);
+      if (gl == 0) off = atomicAdd(&bin[owner], 1);
     }
-    slot = __shfl_sync(gmask, slot, g * LPR);
+    __syncthreads();
+    if (threadIdx.x < p.world) base[threadIdx.x] = bin[threadIdx.x] ? atomicAdd(&p.local_cnt[threadIdx.x], bin[threadIdx.x]) : 0;
+    __syncthreads();
+    const unsigned gmask = (LPR == 32) ? 0xffffffffu : (((1u << LPR) - 1u) << (g * LPR));
+    off = __shfl_sync(gmask, off, g * LPR);
     if (!active) continue;
+    const int slot = base[owner] + off;
     if (slot >= p.cap) {
       if (gl == 0) flag_bad_id(p.err, -2);            // mailbox region overflow
       continue;
@@ -120,6 +131,110 @@ __global__ void __launch_bounds__(256) shard_mailbox_pad_kernel(long long* ids, 
   }
 }
 
+// ---- owner side without a sort: dense gradient accumulator + touched-row list
+// Source g's region holds rows that are unique within the region, so adding it into the accumulator
+// gacc[local_rows, ld] needs no atomics; the regions are added by G consecutive launches in rank
+// order (deterministic sum).  The LAST column of an accumulator row is its stamp: the first launch
+// of a step that meets the row (stamp != epoch) OVERWRITES it, stamps it and puts it on the touched
+// list (one global atomic per CTA iteration); later launches add.  So the accumulator is never
+// cleared and costs one read + one write request per (row, source).
+struct AccParams {
+  const long long* ids; const float* grads; const int* counts;   // one source region
+  int cap, ld;
+  float* gacc; const unsigned* epoch;
+  int* touched; int* n_touched; int max_touched;
+  unsigned long long* err;
+};
+template <int LPR>
+__global__ void __launch_bounds__(256) mailbox_accumulate_kernel(const AccParams p) {
+  constexpr int GPW = 32 / LPR;
+  constexpr int GPB = 8 * GPW;
+  __shared__ int wcount[8], wbase[8];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int gl = lane % LPR, g = lane / LPR;
+  const int nchunks = p.ld / 4;                       // LPR >= nchunks: one chunk per lane
+  const int stamp_lane = nchunks - 1;
+  int n = *p.counts;
+  if (n > p.cap) n = p.cap;
+  const unsigned epoch = *p.epoch;
+  const unsigned gmask = (LPR == 32) ? 0xffffffffu : (((1u << LPR) - 1u) << (g * LPR));
+  for (int s0 = blockIdx.x * GPB; s0 < n; s0 += gridDim.x * GPB) {            // CTA-uniform trip count
+    const int sl = s0 + warp * GPW + g;
+    const bool active = sl < n;
+    long long row = 0;
+    float4 a = make_float4(0.f, 0.f, 0.f, 0.f), x = a;
+    if (active) row = p.ids[sl];
+    const bool mine = active && gl < nchunks;
+    if (mine) {
+      a = *reinterpret_cast<const float4*>(p.gacc + row * p.ld + gl * 4);
+      x = *reinterpret_cast<const float4*>(p.grads + (long long)sl * p.ld + gl * 4);
+    }
+    const unsigned st = __shfl_sync(gmask, __float_as_uint(a.w), g * LPR + stamp_lane);
+    const bool fresh_row = active && st != epoch;
+    if (mine) {
+      if (fresh_row) a = x;
+      else { a.x += x.x; a.y += x.y; a.z += x.z; if (gl != stamp_lane) a.w += x.w; }
+      if (gl == stamp_lane) a.w = __uint_as_float(epoch);
+      *reinterpret_cast<float4*>(p.gacc + row * p.ld + gl * 4) = a;
+    }
+    const bool fresh = fresh_row && gl == 0;
+    const unsigned ball = __ballot_sync(0xffffffffu, fresh);
+    if (lane == 0) wcount[warp] = __popc(ball);
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      int tot = 0;
+      for (int w = 0; w < 8; ++w) { wbase[w] = tot; tot += wcount[w]; }
+      const int b0 = tot ? atomicAdd(p.n_touched, tot) : 0;
+      for (int w = 0; w < 8; ++w) wbase[w] += b0;
+    }
+    __syncthreads();
+    if (fresh) {
+      const int t = wbase[warp] + __popc(ball & ((1u << lane) - 1u));
+      if (t < p.max_touched) p.touched[t] = (int)row;
+      else flag_bad_id(p.err, -4);
+    }
+    __syncthreads();
+  }
+}
+
+// Adam on the touched rows; fm_k > 0: the pushed rows carry the DEFERRED FM gradient
+// [P_0..P_{k-1}, sum_g] with P = sum g S + sum dflat, and the owner finishes
+// dv = P - v * sum_g with its own copy of the row (so the exporting rank never reads it remotely).
+struct TouchedAdamParams {
+  float* table; float* m; float* v; int stride;
+  float* gacc; int ld; const int* touched; const int* n_touched; int max_touched;
+  int fm_k; const float* d_lr_t; float b1, b2, eps;
+};
+__global__ void __launch_bounds__(256) touched_adam_kernel(const TouchedAdamParams p) {
+  const int nch = p.ld / 4;
+  const float lr_t = *p.d_lr_t;
+  int n = *p.n_touched;
+  if (n > p.max_touched) n = p.max_touched;
+  const long long total = (long long)n * nch;
+  for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (long long)gridDim.x * blockDim.x) {
+    const long long i = t / nch;
+    const int c = (int)(t % nch);
+    const long long row = p.touched[i];
+    float4 g = *reinterpret_cast<const float4*>(p.gacc + row * p.ld + c * 4);
+    if (c == nch - 1) g.w = 0.f;                             // the stamp column is not a gradient
+    float4* pvar = reinterpret_cast<float4*>(p.table + row * p.stride + c * 4);
+    float4* pm = reinterpret_cast<float4*>(p.m + row * p.stride + c * 4);
+    float4* pv = reinterpret_cast<float4*>(p.v + row * p.stride + c * 4);
+    float4 var = *pvar, m = *pm, v = *pv;
+    if (p.fm_k > 0 && c * 4 < p.fm_k) {
+      const float sg = p.gacc[row * p.ld + p.fm_k];
+      g.x -= var.x * sg; g.y -= var.y * sg; g.z -= var.z * sg; g.w -= var.w * sg;
+    }
+    float* xv = &var.x; float* xm = &m.x; float* xvv = &v.x; const float* xg = &g.x;
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      xm[q] = p.b1 * xm[q] + (1.0f - p.b1) * xg[q];
+      xvv[q] = p.b2 * xvv[q] + (1.0f - p.b2) * xg[q] * xg[q];
+      xv[q] = xv[q] - lr_t * xm[q] / (sqrtf(xvv[q]) + p.eps);
+    }
+    *pvar = var; *pm = m; *pv = v;
+  }
+}
 // ---- cross-rank barrier over peer memory: rank r stores the new epoch into flags[r] of every
 // peer (release, system scope) and waits until every peer's epoch has arrived in its own flags.
 // One warp; bounded spin (a missing peer flags error -3 instead of hanging the GPU).
@@ -247,7 +362,7 @@ int etr_shard_push(etr_ctx* ctx, const int64_t* d_unique_ids, const int32_t* d_n
   if (max_unique > 0) {
     int lpr = 1;
     while (lpr < ld / 4) lpr <<= 1;
-    const int grid = grid_for(max_unique, 8 * (32 / lpr), ctx->sm_count, 8);
+    const int grid = grid_for(max_unique, 8 * (32 / lpr), ctx->sm_count, 6);
     switch (lpr) {
       case 1: shard_push_kernel<1><<<grid, 256, 0, s>>>(p); break;
       case 2: shard_push_kernel<2><<<grid, 256, 0, s>>>(p); break;
@@ -268,6 +383,52 @@ int etr_shard_mailbox_pad(etr_ctx* ctx, int64_t* d_ids, const int32_t* d_counts,
   ETR_CHECK_ARG(ctx && d_ids && d_counts && world >= 1 && cap > 0, "bad argument");
   shard_mailbox_pad_kernel<<<grid_for((long long)world * cap, 256, ctx->sm_count, 8), 256, 0, (cudaStream_t)stream>>>(
       (long long*)d_ids, d_counts, world, cap);
+  ETR_LAUNCH_CHECK(ctx);
+  return ETR_OK;
+}
+
+int etr_shard_mailbox_accumulate(etr_ctx* ctx, const int64_t* d_ids, const float* d_grads, const int32_t* d_counts,
+                                 int32_t world, int32_t cap, int32_t ld, float* d_gacc,
+                                 const uint32_t* d_epoch, int32_t* d_touched, int32_t* d_n_touched, int32_t max_touched,
+                                 void* stream) {
+  ETR_CHECK_ARG(ctx && d_ids && d_grads && d_counts && d_gacc && d_epoch && d_touched && d_n_touched,
+                "NULL argument");
+  ETR_CHECK_ARG(world >= 1 && world <= 16 && cap > 0 && ld % 4 == 0 && ld / 4 <= 32 && max_touched > 0, "bad world / cap / ld");
+  cudaStream_t s = (cudaStream_t)stream;
+  ETR_CUDA(cudaMemsetAsync(d_n_touched, 0, sizeof(int), s));
+  int lpr = 1;
+  while (lpr < ld / 4) lpr <<= 1;
+  const int grid = grid_for(cap, 8 * (32 / lpr), ctx->sm_count, 6);
+  for (int g = 0; g < world; ++g) {                    // rank order: the sum is deterministic
+    AccParams p;
+    p.ids = (const long long*)d_ids + (long long)g * cap; p.grads = d_grads + (long long)g * cap * ld; p.counts = d_counts + g;
+    p.cap = cap; p.ld = ld; p.gacc = d_gacc; p.epoch = d_epoch;
+    p.touched = d_touched; p.n_touched = d_n_touched; p.max_touched = max_touched; p.err = ctx->d_err;
+    switch (lpr) {
+      case 1: mailbox_accumulate_kernel<1><<<grid, 256, 0, s>>>(p); break;
+      case 2: mailbox_accumulate_kernel<2><<<grid, 256, 0, s>>>(p); break;
+      case 4: mailbox_accumulate_kernel<4><<<grid, 256, 0, s>>>(p); break;
+      case 8: mailbox_accumulate_kernel<8><<<grid, 256, 0, s>>>(p); break;
+      case 16: mailbox_accumulate_kernel<16><<<grid, 256, 0, s>>>(p); break;
+      default: mailbox_accumulate_kernel<32><<<grid, 256, 0, s>>>(p); break;
+    }
+    ETR_LAUNCH_CHECK(ctx);
+  }
+  return ETR_OK;
+}
+
+int etr_shard_touched_adam(etr_ctx* ctx, const etr_table* table, float* d_m, float* d_v, float* d_gacc, int32_t ld,
+                           const int32_t* d_touched, const int32_t* d_n_touched, int32_t max_touched, int32_t fm_k,
+                           const float* d_lr_t, float beta1, float beta2, float eps, void* stream) {
+  ETR_CHECK_ARG(ctx && table && table->d_data && d_m && d_v && d_gacc && d_touched && d_n_touched && d_lr_t, "NULL argument");
+  ETR_CHECK_ARG(table->dtype == ETR_F32 && ld % 4 == 0 && ld <= table->stride && max_touched > 0, "fp32 table, ld <= stride");
+  ETR_CHECK_ARG(fm_k == 0 || (fm_k % 4 == 0 && fm_k + 4 <= ld), "fm_k must be a multiple of 4 with a chunk behind it");
+  TouchedAdamParams p;
+  p.table = (float*)table->d_data; p.m = d_m; p.v = d_v; p.stride = table->stride; p.gacc = d_gacc; p.ld = ld;
+  p.touched = d_touched; p.n_touched = d_n_touched; p.max_touched = max_touched; p.fm_k = fm_k; p.d_lr_t = d_lr_t;
+  p.b1 = beta1; p.b2 = beta2; p.eps = eps;
+  const int grid = grid_for((long long)max_touched * (ld / 4), 256, ctx->sm_count, 8);
+  touched_adam_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(p);
   ETR_LAUNCH_CHECK(ctx);
   return ETR_OK;
 }

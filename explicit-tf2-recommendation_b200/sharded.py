@@ -220,10 +220,12 @@ class PeerShardedTable:
 
     forward : the fused gather + FM kernel reads row ``id`` straight from its owner's HBM over
               NVLink (etr_table.reserved = shard-set id) -- gather and exchange are ONE kernel;
-    backward: the fused backward exports this rank's de-duplicated gradient rows (re-reading the
-              rows the same way), ``etr_shard_push`` stores them into the owners' mailboxes;
-    apply   : after a device-side barrier each owner sorts / segment-reduces its mailbox and runs
-              Adam on its own shard; a second barrier closes the step.
+    backward: the fused backward exports this rank's de-duplicated gradient rows in DEFERRED form
+              [P, sum_g] (dv = P - v * sum_g is finished by the owner, so no row is re-read over
+              NVLink), ``etr_shard_push`` stores them into the owners' mailboxes;
+    apply   : after a device-side barrier each owner adds the G source regions of its mailbox into a
+              dense accumulator (rank order, no sort, no atomics) and runs Adam on the touched rows of
+              its own shard; a second barrier closes the step.
     Nothing is read back to the host, so the whole data-parallel step is one CUDA graph."""
 
     def __init__(self, rt, rows_global: int, width: int, world: int, rank: int, group=None):
@@ -247,6 +249,7 @@ class PeerShardedTable:
         self._flag_ptrs = self._flags.peer_array()
         self._ar = None
         self._mb = None
+        self._gacc = None
         self.cap = 0
         if world > 1:
             dist.barrier(group=group)
@@ -329,6 +332,7 @@ class PeerShardedTable:
             "counts_t": counts.tensor((W,), torch.int32),
             "ids_ptrs": ids.peer_array(self.rank * cap * 8), "grads_ptrs": grads.peer_array(self.rank * cap * ld * 4),
             "counts_ptrs": counts.peer_array(self.rank * 4), "local_cnt": rt.zeros((W,), torch.int32),
+            "touched": rt.empty((W * cap,), torch.int32), "n_touched": rt.zeros((1,), torch.int32),
         }
         self.cap = cap
         if W > 1:
@@ -341,21 +345,26 @@ class PeerShardedTable:
                                     mb["grads_ptrs"], mb["counts_ptrs"], mb["local_cnt"].data_ptr(), rt.stream))
 
     def apply_mailbox(self, d_lr_t: torch.Tensor, b1: float, b2: float, eps: float, mode: int):
-        """owner side: pad unused slots, sorted-ID plan over the mailbox, segment reduction, Adam"""
-        from .runtime import IdsBatch, SparsePlan
+        """owner side, no sort: the G source regions are added into the dense accumulator in rank order
+        (rows are unique within a region: no atomics, deterministic), first-touch rows go on a list, and
+        row-wise Adam runs over that list, finishing the deferred FM gradient dv = P - v * sum_g."""
+        if mode != _lib.ADAM_ROWWISE:
+            raise NotImplementedError("peer-sharded tables: row-wise Adam only (keras_dense decays every row of "
+                                      "every shard each step; use the all-to-all form for that parity mode)")
         rt, mb, W, cap, ld = self.rt, self._mb, self.world, self.cap, self.stride
-        check(rt.lib.etr_shard_mailbox_pad(rt.ctx, mb["ids_t"].data_ptr(), mb["counts_t"].data_ptr(), W, cap, rt.stream))
-        lids = IdsBatch(rt, mb["ids_t"], W * cap, 1, 1, 1, 1, 1, pad_id=-1)
-        plan = SparsePlan(rt, lids, self.local.rows)
-        ug = rt.empty((W * cap, ld))
-        check(rt.lib.etr_sparse_segment_reduce(rt.ctx, plan.sorted_bag.data_ptr(), plan.seg_start.data_ptr(),
-                                               plan.counts.data_ptr(), plan.n_slots, mb["grads_t"].data_ptr(), ld,
-                                               ug.data_ptr(), rt.stream))
+        if self._gacc is None:
+            assert not torch.cuda.is_current_stream_capturing()
+            assert ld >= self.width + 1, "the accumulator row needs a spare last column for its stamp"
+            self._gacc = rt.zeros((max(self.local_rows, 1), ld))
+        check(rt.lib.etr_shard_mailbox_accumulate(rt.ctx, mb["ids_t"].data_ptr(), mb["grads_t"].data_ptr(),
+                                                  mb["counts_t"].data_ptr(), W, cap, ld, self._gacc.data_ptr(),
+                                                  self._epoch.data_ptr(),
+                                                  mb["touched"].data_ptr(), mb["n_touched"].data_ptr(), W * cap, rt.stream))
         t = self.local.desc()
-        check(rt.lib.etr_sparse_adam_apply(rt.ctx, C.byref(t), self.local.m.data_ptr(), self.local.v.data_ptr(),
-                                           plan.unique_ids.data_ptr(), plan.counts.data_ptr(), plan.n_slots,
-                                           ug.data_ptr(), ld, 0.0, d_lr_t.data_ptr(), b1, b2, eps, mode, rt.stream))
-        self.last_plan, self.last_unique_grad = plan, ug
+        check(rt.lib.etr_shard_touched_adam(rt.ctx, C.byref(t), self.local.m.data_ptr(), self.local.v.data_ptr(),
+                                            self._gacc.data_ptr(), ld, mb["touched"].data_ptr(),
+                                            mb["n_touched"].data_ptr(), W * cap, self.width - 1, d_lr_t.data_ptr(),
+                                            b1, b2, eps, rt.stream))
 
 
 class PeerFMGrad:

@@ -366,6 +366,24 @@ int etr_shard_push(etr_ctx* ctx, const int64_t* d_unique_ids, const int32_t* d_n
                    int32_t* d_local_cnt, void* stream);
 int etr_shard_mailbox_pad(etr_ctx* ctx, int64_t* d_ids, const int32_t* d_counts, int32_t world, int32_t cap,
                           void* stream);
+/* Owner side of the peer-sharded apply WITHOUT a sort (replaces Unique + UnsortedSegmentSum +
+ * Adam._resource_apply_sparse of 2.FM/ModelManager.py:178 on the shard): the G source regions of
+ * the mailbox -- rows unique within a region -- are added into a dense accumulator
+ * d_gacc[local_rows, ld] by G launches in rank order, so the sum is
+ * deterministic and needs no atomics.  The last column of an accumulator row is its stamp (so the
+ * gradient must leave that column unused, as the FM row [v.., w, 0, 0, 0] does): the first region
+ * of a step that meets a row (stamp != *d_epoch, a value that changes every step) overwrites and
+ * stamps it and puts it on the touched list; the accumulator is never cleared.
+ * etr_shard_touched_adam then runs row-wise Adam on the touched rows.  fm_k > 0: the pushed rows are the DEFERRED FM gradient
+ * [P_0..P_{k-1}, sum_g, ...] (etr_fm_fused_backward_apply on a peer-sharded table, apply = 0) and
+ * the owner finishes dv = P - v * sum_g with its own copy of the row.                           */
+int etr_shard_mailbox_accumulate(etr_ctx* ctx, const int64_t* d_ids, const float* d_grads, const int32_t* d_counts,
+                                 int32_t world, int32_t cap, int32_t ld, float* d_gacc,
+                                 const uint32_t* d_epoch, int32_t* d_touched, int32_t* d_n_touched, int32_t max_touched,
+                                 void* stream);
+int etr_shard_touched_adam(etr_ctx* ctx, const etr_table* table, float* d_m, float* d_v, float* d_gacc, int32_t ld,
+                           const int32_t* d_touched, const int32_t* d_n_touched, int32_t max_touched, int32_t fm_k,
+                           const float* d_lr_t, float beta1, float beta2, float eps, void* stream);
 /* Cross-rank barrier on the stream, over peer memory: every rank owns a flag array [world]
  * (etr_peer_alloc, zero-initialised) and an epoch word; the kernel bumps the epoch, stores it into
  * flags[rank] of every peer and waits (bounded: ~20 s, then error -3 is flagged) until all peers'
