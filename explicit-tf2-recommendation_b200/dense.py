@@ -136,6 +136,7 @@ class MLPLayer:
         self.name = name
         assert precision in ("fp32", "bf16")
         self.precision = precision      # "bf16": wide layers use tcgen05 (bf16 operands, fp32 accumulate)
+        self.fused_skinny = bool(kwargs.pop("fused_skinny", True))   # K7b one-pass backward of a [wide -> 32] layer
         self.params: Optional[DenseParams] = None
         self.in_dim: Optional[int] = None
         self._saved = None
@@ -224,6 +225,16 @@ class MLPLayer:
                                               _lib.ACT[self.activation], rt.stream))
             gk = self.params.gfull(f"{self.name}/kernel_{i}")
             tc = x.dtype == torch.bfloat16
+            if (tc and self.fused_skinny and i == 0 and accumulate_into is None and n_out == 32 and n_in % 16 == 0 and
+                    n_in <= 512 and x.stride(0) % 8 == 0):
+                # wide-in / narrow-out first layer: dX, dK and db in one pass over the batch (K7b)
+                dx = rt.empty((B, n_in), torch.bfloat16) if need_input_grad else None
+                gb = self.params.g(f"{self.name}/bias_{i}") if self.use_bias else None
+                check(rt.lib.etr_mlp_skinny_backward(rt.ctx, x.data_ptr(), x.stride(0), d.data_ptr(),
+                                                     self.params.full(f"{self.name}/kernel_{i}").data_ptr(), B, n_in,
+                                                     n_out, _p(dx), n_in, gk.data_ptr(), _p(gb), rt.stream))
+                d = dx
+                continue
             if tc:
                 # dK = X^T d : [in,B] x [B,out]  ->  A = X^T (bf16 transpose), B operand = d^T; split-K over the batch
                 xt = transpose_bf16(rt, x, B, n_in)

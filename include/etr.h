@@ -317,6 +317,15 @@ int etr_colsum_bf16(etr_ctx* ctx, const void* d_X, int64_t M, int64_t N, int64_t
                     void* stream);
 /* fp32 [rows, cols] -> bf16 (optionally transposed) into a buffer with leading
  * dim ld_dst whose padding columns are written as zeros; bf16 -> bf16 transpose. */
+/* Backward of a wide-in / narrow-out dense layer in ONE pass over the batch (first MLP layer of
+ * DeepFM, [B,432] x [432,32]; MatMul + BiasAdd backward of 2.FM/CustomLayers.py:72-84 under
+ * tape.gradient, 2.FM/ModelManager.py:176):  dX = dy K^T (bf16, optional), dK = X^T dy (fp32),
+ * db = colsum(dy) (optional).  X bf16 [B, n_in] (row stride ldx), dy fp32 [B, n_out] contiguous,
+ * K fp32 [n_in, n_out] contiguous.  Needs n_out == 32 and n_in % 16 == 0, n_in <= 512; returns
+ * ETR_EUNSUPPORTED otherwise (callers fall back to the GEMM path).                           */
+int etr_mlp_skinny_backward(etr_ctx* ctx, const void* d_X, int64_t ldx, const float* d_dy, const float* d_K, int64_t B,
+                            int32_t n_in, int32_t n_out, void* d_dX, int64_t ld_dx, float* d_dK, float* d_db,
+                            void* stream);
 int etr_cast_bf16(etr_ctx* ctx, const float* d_src, int64_t rows, int64_t cols, int64_t ld_src,
                   void* d_dst, int64_t ld_dst, int32_t transpose, void* stream);
 int etr_transpose_bf16(etr_ctx* ctx, const void* d_src, int64_t rows, int64_t cols, int64_t ld_src,

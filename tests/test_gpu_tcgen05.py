@@ -187,3 +187,54 @@ def test_dcn_matrix_bf16_forward_backward(rt, B):
                  "dense k0", grad=True)
     assert_close(lay.params.g("output_layer/kernel_0").cpu().numpy(), orc.output_layer.kernels[0].grad.numpy(), 2e-2,
                  "output k0", grad=True)
+
+
+@pytest.mark.parametrize("B,n_in", [(1000, 432), (64, 16), (4097, 208), (130, 512)])
+def test_mlp_skinny_backward_one_pass(rt, B, n_in):
+    """K7b (etr_mlp_skinny_backward): dX, dK, db of a [n_in -> 32] layer in one pass == the same products
+    of the bf16-rounded operands in fp64 (dX is bf16: 2^-8 relative)."""
+    import ctypes as C
+    from etr_b200._lib import check
+    g = torch.Generator(device=rt.device)
+    g.manual_seed(B + n_in)
+    X = _rand_bf16(rt, (B, n_in), n_in, 3)
+    dy = torch.randn((B, 32), device=rt.device, generator=g) * 0.1
+    K = torch.randn((n_in, 32), device=rt.device, generator=g) * 0.2
+    dX = torch.full((B, n_in), 7.0, dtype=torch.bfloat16, device=rt.device)
+    dK = torch.full((n_in, 32), 7.0, device=rt.device)
+    db = torch.full((32,), 7.0, device=rt.device)
+    check(rt.lib.etr_mlp_skinny_backward(rt.ctx, X.data_ptr(), n_in, dy.data_ptr(), K.data_ptr(), B, n_in, 32,
+                                         dX.data_ptr(), n_in, dK.data_ptr(), db.data_ptr(), rt.stream))
+    torch.cuda.synchronize()
+    dyb, Kb = dy.to(torch.bfloat16).double(), K.to(torch.bfloat16).double()
+    ref_dX = dyb @ Kb.T
+    ref_dK = X.double().T @ dyb
+    ref_db = dy.double().sum(0)
+    assert (dX.double() - ref_dX).abs().max().item() <= 2.0 ** -7 * ref_dX.abs().max().item()
+    assert (dK.double() - ref_dK).abs().max().item() <= 1e-4 * max(ref_dK.abs().max().item(), 1.0)
+    assert (db.double() - ref_db).abs().max().item() <= 1e-5 * max(ref_db.abs().max().item(), 1.0)
+
+
+def test_mlp_backward_fused_skinny_matches_gemm_path(rt):
+    """MLPLayer(bf16) backward: the one-pass kernel and the transpose + tcgen05 GEMM path agree."""
+    from etr_b200.dense import DenseParams, MLPLayer
+    outs = []
+    for fused in (True, False):
+        params = DenseParams(rt)
+        gen = torch.Generator(device=rt.device)
+        gen.manual_seed(5)
+        mlp = MLPLayer(units=[32, 8], activation="relu", precision="bf16", fused_skinny=fused)
+        mlp.build(429, params, gen, front_pad=3)
+        params.finalize()
+        g = torch.Generator(device=rt.device)
+        g.manual_seed(9)
+        x = torch.zeros((777, 432), dtype=torch.bfloat16, device=rt.device)
+        x[:, 3:] = (torch.randn((777, 429), device=rt.device, generator=g) * 0.3).to(torch.bfloat16)
+        y = mlp(x, training=True)
+        dy = torch.randn(y.shape, device=rt.device, generator=g).contiguous()
+        dx = mlp.backward(dy)
+        torch.cuda.synchronize()
+        outs.append((dx.float().clone(), params.grad.clone()))
+    (dx1, g1), (dx0, g0) = outs
+    assert dx1.dtype == dx0.dtype and (dx1 - dx0).abs().max().item() <= 2.0 ** -6 * dx0.abs().max().item()
+    assert (g1 - g0).abs().max().item() <= 2e-3 * g0.abs().max().item()
