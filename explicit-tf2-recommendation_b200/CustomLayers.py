@@ -23,7 +23,7 @@ from . import _lib
 from ._lib import check
 from .dense import DenseLayer, DenseParams, MLPLayer, glorot_uniform, random_normal  # noqa: F401
 from .runtime import (EmbeddingTable, FusedFMGrad, IdsBatch, Runtime, SparseGrad, SparsePlan, bce_forward_backward,
-                      embedding_gather, gather_fm_backward, gather_fm_forward, lr_t, _p)
+                      cast_bf16, embedding_gather, gather_fm_backward, gather_fm_forward, gemm_bf16_tn, lr_t, _p)
 
 _DT = {"float32": torch.float32, "bfloat16": torch.bfloat16, torch.float32: torch.float32,
        torch.bfloat16: torch.bfloat16}
@@ -269,6 +269,7 @@ class DeepFMRankingLayer(FMRankingLayer):
         # "bf16": the wide first MLP layer runs on the tensor cores (bf16 operands, fp32 accumulate;
         # parity 1e-2); "fp32": exact-parity SIMT path (1e-5)
         self.mlp_precision = mlp_precision
+        self.fused_tail = bool(kwargs.pop("fused_tail", True))   # K7c: tower tail + loss fwd/bwd in one launch
         super().__init__(feature_names, feature_dims, embedding_dims, **kwargs)
 
     def _build_extra(self):
@@ -313,6 +314,52 @@ class DeepFMRankingLayer(FMRankingLayer):
             self._ctx = {"ids": vids, "table": tab, "route": route, "sumv": sumv, "plan": plan}
         self._finish(training)
         return {"output": prob}
+
+    # -- fused train step (K1 -> layer 1 on tcgen05 -> K7c tail+loss fwd/bwd -> K7b layer-1 backward) ------
+    def fused_train_ok(self) -> bool:
+        m1 = self.MLP_layer1
+        return (self.fused_tail and self.shard is None and self.mlp_precision == "bf16" and self.mlp_dims == [32, 8]
+                and m1.activation == "relu"
+                and m1.use_bias and self.MLP_layer2.use_bias and self.MLP_layer2.activation is None
+                and (self.front_pad + len(self.continuous_features) + len(self.feature_names) * self.embedding_dims) % 16 == 0)
+
+    def train_forward_backward(self, inputs, labels: torch.Tensor, grad_scale: float = 1.0):
+        """The whole reference train step up to apply_gradients (2.FM/ModelManager.py:172-176) for the default
+        DeepFM tower, in 6 launches: returns (loss [1], prob [B,1], table gradients) or None when this batch
+        is not eligible (the caller then takes the layer-by-layer path).  Dense grads land in params.grad."""
+        rt = self.rt
+        ids = self._ids(inputs, self.feature_names)
+        C_ = len(self.continuous_features)
+        k, F = self.embedding_dims, len(self.feature_names)
+        col0 = self.front_pad + C_
+        tab, vids, route = self._lookup(ids)
+        if route is not None or not FusedFMGrad.eligible(tab, vids, k) or not self.fused_apply or col0 % 4:
+            return None
+        B, n_in = ids.B, col0 + F * k
+        x = rt.empty((B, n_in), torch.bfloat16)                # [pad | X_cont | Flatten(emb)]
+        cont = self._cont(inputs, self.continuous_features) if C_ else None
+        fm_logit = rt.empty((B,))
+        sumv = rt.empty((B, k))
+        plan = SparsePlan(rt, vids, tab.rows, overlap=True)    # sort || everything below
+        gather_fm_forward(tab, k, True, vids, bias=self.bias, logit=fm_logit, sumv=sumv, flat=x, flat_col0=col0,
+                          cont=cont)
+        m1, m2, P = self.MLP_layer1, self.MLP_layer2, self.params
+        k0 = P.full(f"{m1.name}/kernel_0")
+        y1 = rt.empty((B, 32))
+        gemm_bf16_tn(rt, x, cast_bf16(rt, k0, transpose=True), y1, B, 32, n_in, bias=P[f"{m1.name}/bias_0"], act="relu")
+        prob, dlogit, d1, loss = rt.empty((B, 1)), rt.empty((B,)), rt.empty((B, 32)), rt.empty((1,))
+        check(rt.lib.etr_deepfm_tail_train(
+            rt.ctx, y1.data_ptr(), fm_logit.data_ptr(), labels.data_ptr(), B, P[f"{m1.name}/kernel_1"].data_ptr(),
+            P[f"{m1.name}/bias_1"].data_ptr(), P[f"{m2.name}/kernel_0"].data_ptr(), P[f"{m2.name}/bias_0"].data_ptr(),
+            float(grad_scale), prob.data_ptr(), dlogit.data_ptr(), d1.data_ptr(), loss.data_ptr(),
+            P.g("bias").data_ptr(), P.g(f"{m1.name}/kernel_1").data_ptr(), P.g(f"{m1.name}/bias_1").data_ptr(),
+            P.g(f"{m2.name}/kernel_0").data_ptr(), P.g(f"{m2.name}/bias_0").data_ptr(), rt.stream))
+        dx = rt.empty((B, n_in), torch.bfloat16)
+        check(rt.lib.etr_mlp_skinny_backward(rt.ctx, x.data_ptr(), n_in, d1.data_ptr(), k0.data_ptr(), B, n_in, 32,
+                                             dx.data_ptr(), n_in, P.gfull(f"{m1.name}/kernel_0").data_ptr(),
+                                             P.g(f"{m1.name}/bias_0").data_ptr(), rt.stream))
+        grads = [self._fused_grad(FusedFMGrad(self.table, vids, k, dlogit, sumv, dx, col0, plan=plan))]
+        return loss, prob, grads
 
     def backward(self, dlogit: torch.Tensor) -> List[SparseGrad]:
         rt = self.rt
@@ -986,12 +1033,18 @@ class Trainer:
         sl = getattr(inputs, "_slot", None)
         if sl is not None and not torch.cuda.is_current_stream_capturing():
             torch.cuda.current_stream(rt.device).wait_event(sl.copy_done)     # staged on the copy stream
-        out = self.layer(inputs, training=True)["output"]
         y = rt.to_device(labels, torch.float32).reshape(-1)
-        loss, dlogit = bce_forward_backward(rt, out.reshape(-1), y)
-        if self.dp_world > 1:
-            dlogit.mul_(1.0 / self.dp_world)          # the loss is the mean over the GLOBAL batch
-        grads = self.layer.backward(dlogit)
+        fused = None
+        if getattr(self.layer, "fused_train_ok", None) and self.layer.fused_train_ok():
+            fused = self.layer.train_forward_backward(inputs, y, 1.0 / self.dp_world)
+        if fused is not None:
+            loss, _, grads = fused
+        else:
+            out = self.layer(inputs, training=True)["output"]
+            loss, dlogit = bce_forward_backward(rt, out.reshape(-1), y)
+            if self.dp_world > 1:
+                dlogit.mul_(1.0 / self.dp_world)      # the loss is the mean over the GLOBAL batch
+            grads = self.layer.backward(dlogit)
         if self.peer is not None:
             # rows -> owners' mailboxes, dense grads -> every peer's slot; ONE device-side barrier
             for g in grads:

@@ -317,6 +317,17 @@ int etr_colsum_bf16(etr_ctx* ctx, const void* d_X, int64_t M, int64_t N, int64_t
                     void* stream);
 /* fp32 [rows, cols] -> bf16 (optionally transposed) into a buffer with leading
  * dim ld_dst whose padding columns are written as zeros; bf16 -> bf16 transpose. */
+/* The narrow tail of the DeepFM tower with the loss, forward and backward, in one launch (+ a
+ * finish): MLPLayer tail 32 -> 8 (relu) -> MLPLayer([1]) (2.FM/CustomLayers.py:255-256, 301-303),
+ * sigmoid(fm + dnn) (:305), Keras BinaryCrossentropy and tape.gradient through all of it
+ * (2.FM/ModelManager.py:175-176).  d_h1 [B,32] = relu output of the first MLP layer; outputs:
+ * prob [B], dlogit [B] (= dL/dz * grad_scale; the FM backward's input), d1 [B,32] (gradient of the
+ * first layer's pre-activation), loss (mean, unscaled), and the gradients of K2 [32,8], b2 [8],
+ * K3 [8], b3 [1] and the FM bias (sum of dlogit).                                              */
+int etr_deepfm_tail_train(etr_ctx* ctx, const float* d_h1, const float* d_fm_logit, const float* d_label, int64_t batch,
+                          const float* d_K2, const float* d_b2, const float* d_K3, const float* d_b3, float grad_scale,
+                          float* d_prob, float* d_dlogit, float* d_d1, float* d_loss, float* d_g_bias_fm, float* d_gK2,
+                          float* d_gb2, float* d_gK3, float* d_gb3, void* stream);
 /* Backward of a wide-in / narrow-out dense layer in ONE pass over the batch (first MLP layer of
  * DeepFM, [B,432] x [432,32]; MatMul + BiasAdd backward of 2.FM/CustomLayers.py:72-84 under
  * tape.gradient, 2.FM/ModelManager.py:176):  dX = dy K^T (bf16, optional), dK = X^T dy (fp32),

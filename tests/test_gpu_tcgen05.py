@@ -238,3 +238,29 @@ def test_mlp_backward_fused_skinny_matches_gemm_path(rt):
     (dx1, g1), (dx0, g0) = outs
     assert dx1.dtype == dx0.dtype and (dx1 - dx0).abs().max().item() <= 2.0 ** -6 * dx0.abs().max().item()
     assert (g1 - g0).abs().max().item() <= 2e-3 * g0.abs().max().item()
+
+
+def test_deepfm_fused_train_step_matches_layerwise(rt):
+    """Trainer on DeepFM(bf16 MLP): the fused step (K7c tail + loss, K7b layer-1 backward) and the layer-by-layer
+    step give the same losses and the same weights after 3 Adam steps (same bf16 products, fp32 sums reordered)."""
+    from etr_b200 import CustomLayers as L
+    F, k, V, C_, B = 26, 16, 5000, 13, 1000
+    names, cont = [f"f{i}" for i in range(F)], [f"c{i}" for i in range(C_)]
+    rng = np.random.default_rng(3)
+    batches = []
+    for _ in range(3):
+        d = {n: torch.tensor(rng.integers(0, V, size=B)) for n in names}
+        d.update({n: torch.tensor(rng.normal(size=B).astype(np.float32)) for n in cont})
+        batches.append((d, torch.tensor((rng.random(B) < 0.3).astype(np.float32))))
+    res = []
+    for fused in (True, False):
+        lay = L.DeepFMRankingLayer(names, V, k, continuous_features=cont, seed=4, mlp_precision="bf16", fused_tail=fused)
+        assert lay.fused_train_ok() == fused
+        tr = L.Trainer(lay, lr=1e-2)
+        losses = [float(tr.train_step(d, y).item()) for d, y in batches]
+        torch.cuda.synchronize()
+        res.append((losses, lay.params.value.clone(), lay.table.data.clone()))
+    (l1, p1, t1), (l0, p0, t0) = res
+    assert max(abs(a - b) for a, b in zip(l1, l0)) < 2e-5
+    assert (p1 - p0).abs().max().item() < 2e-3          # 3 Adam steps of lr 1e-2 (sign-like updates of tiny grads)
+    assert (t1 - t0).abs().max().item() < 2e-3
