@@ -33,6 +33,7 @@ CRITEO_CARDS = [1460, 583, 10131227, 2202608, 305, 24, 12517, 633, 3, 93145, 568
 F, K_EMB, C_DENSE = 26, 16, 13
 BATCH = 65536
 SEED = 20261          # 20260 + config index
+NCU_K1_DRAM_BYTES = 117.0e6   # dram read 105.6 MB + write 11.4 MB per launch (profiles/r01_prof_gather_fwd.md)
 
 
 def make_batches(n_batches: int, B: int, dist: str, seed: int = SEED):
@@ -327,10 +328,15 @@ def main():
     rt = layer.rt
     n_batches = 6
     host = make_batches(n_batches, B, args.dist, seed=SEED + 17 * rank)
+    # host side of the e2e path: the reference's dict of per-feature columns, living in pinned memory as the
+    # columns of one column-major block per dtype (what a data loader's pinned staging arena looks like); the
+    # Trainer recognises back-to-back columns and moves each block with one async copy
     pinned = []
     for X, Xc, y in host:
-        d = {n: torch.from_numpy(np.ascontiguousarray(X[:, i])).pin_memory() for i, n in enumerate(names)}
-        d.update({n: torch.from_numpy(np.ascontiguousarray(Xc[:, i])).pin_memory() for i, n in enumerate(cont)})
+        idb = torch.from_numpy(np.ascontiguousarray(X.T)).pin_memory()           # [F, B] int64
+        cb = torch.from_numpy(np.ascontiguousarray(Xc.T)).pin_memory()           # [C, B] fp32
+        d = {n: idb[i] for i, n in enumerate(names)}
+        d.update({n: cb[i] for i, n in enumerate(cont)})
         pinned.append((d, torch.from_numpy(y).pin_memory()))
     dev_batches = []
     for X, Xc, y in host:
@@ -462,6 +468,14 @@ def main():
     alg_flat = F * K_EMB * (2 if args.mlp == "bf16" else 4)
     achieved = (alg_fm + alg_flat) * B / (k_ms * 1e-3) / 1e9
     del ids0
+    # DRAM bytes of one launch of this kernel from the committed ncu --set full capture of this very
+    # command (dram__bytes_read.sum + dram__bytes_write.sum); only valid for the default workload
+    traffic, traffic_src = None, None
+    if world == 1 and args.dist == "zipf" and args.mlp == "bf16" and B == BATCH:
+        traffic = NCU_K1_DRAM_BYTES
+        traffic_src = ("profiles/r01_prof_gather_fwd.md (ncu --set full, per launch): below the algorithmic bytes because "
+                       "the Zipf head and the 16 small fields are L2 hits and the bf16 operand is still in L2 when the "
+                       "kernel ends")
 
     # ---- max over ranks
     t = torch.tensor([total_ms, e2e_ms], device=dev, dtype=torch.float64)
@@ -490,10 +504,12 @@ def main():
                 "ms_per_step": e2e_ms / args.steps, "last_loss": last},
         "gpu_launches": launches_per_step * args.steps,
         "gpu_launches_per_step": launches_per_step,
-        "roofline": {"bound": "hbm", "kernel": "gather_fm_fwd_stream_kernel (gather + FM terms + Flatten, one launch)"
-                     + (f"; rows of the {world - 1} other shards come over NVLink" if world > 1 and args.shard == "peer" else ""),
+        "roofline": {"bound": "hbm", "kernel": ("gather_fm_fwd_stream_kernel<float,4,13,2,true,true> (gather + FM terms + Flatten, "
+                                                f"one launch); rows of the {world - 1} other shards come over NVLink"
+                                                if world > 1 and args.shard == "peer" else
+                                                "gather_fm_fwd_tile_kernel<float,4> (gather + FM terms + Flatten, one launch)"),
                      "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                     "traffic": None, "peak_source": peak_src, "kernel_ms": k_ms,
+                     "traffic": traffic, "traffic_source": traffic_src, "peak_source": peak_src, "kernel_ms": k_ms,
                      "algorithmic_bytes_per_launch": (alg_fm + alg_flat) * B,
                      "note": "algorithmic bytes = B*(F*(4k+4+8)+4) FM terms + B*F*k*osize flattened operand written "
                              "for the MLP (osize 2 for the bf16 tensor-core MLP, 4 for fp32); timed alone with CUDA "

@@ -1155,13 +1155,35 @@ class Trainer:
         with torch.cuda.stream(self._copy_stream):
             if sl.used:
                 self._copy_stream.wait_event(sl.compute_done)      # the buffers' previous consumer has finished
-            for f, n in enumerate(names):
-                sl.ids_buf[f].copy_(torch.as_tensor(inputs[n]).reshape(-1), non_blocking=True)
-            for c, n in enumerate(cont_names):
-                sl.cont_buf[c].copy_(torch.as_tensor(inputs[n]).reshape(-1), non_blocking=True)
+            self._copy_columns(sl.ids_buf, [inputs[n] for n in names], torch.int64)
+            if cont_names:
+                self._copy_columns(sl.cont_buf, [inputs[n] for n in cont_names], torch.float32)
             sl.lab_buf.copy_(torch.as_tensor(labels).reshape(-1), non_blocking=True)
             sl.copy_done.record(self._copy_stream)
         return sl.batch
+
+    @staticmethod
+    def _copy_columns(dst: torch.Tensor, cols, dtype: torch.dtype) -> None:
+        """dst [n, B] <- n host/device columns.  Columns that sit back to back in one allocation (a
+        column-major block, e.g. a pinned staging arena or the columns of a contiguous [n, B] array) go in
+        ONE async copy per run instead of one per column: 40 cudaMemcpyAsync per step were host-bound."""
+        ts = [torch.as_tensor(c).reshape(-1) for c in cols]
+        i, n = 0, len(ts)
+        while i < n:
+            j = i + 1
+            t0 = ts[i]
+            if t0.dtype == dtype and t0.is_contiguous():
+                nbytes = t0.numel() * t0.element_size()
+                while (j < n and ts[j].dtype == dtype and ts[j].device == t0.device and ts[j].is_contiguous() and
+                       ts[j].numel() == t0.numel() and ts[j].data_ptr() == t0.data_ptr() + (j - i) * nbytes and
+                       ts[j].untyped_storage().data_ptr() == t0.untyped_storage().data_ptr()):
+                    j += 1
+            if j - i > 1:
+                block = torch.as_strided(t0, (j - i, t0.numel()), (t0.numel(), 1))
+                dst[i:j].copy_(block, non_blocking=True)
+            else:
+                dst[i].copy_(t0, non_blocking=True)
+            i = j
 
     def _graph_step(self, inputs, labels) -> torch.Tensor:
         """Per buffer set: calls 1-2 run eagerly on the static buffers (real training

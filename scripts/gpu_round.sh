@@ -20,7 +20,7 @@ timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --c
     python bench.py --steps 3 --warmup 3 --no-graph --no-cpu-baseline > gpurun_out/ncu.log 2>&1
 echo "ncu exit $?"
 # full ncu capture of the two headline kernels (after the same command exited 0 above)
-timeout 600 ncu --set full --clock-control none --import-source on -k regex:gather_fm_fwd_stream -s 4 -c 2 \
+timeout 600 ncu --set full --clock-control none --import-source on -k regex:gather_fm_fwd_tile -s 4 -c 2 \
     -o gpurun_out/prof_gather_fwd python bench.py --steps 3 --warmup 3 --no-graph --no-cpu-baseline > gpurun_out/ncu_full1.log 2>&1
 echo "ncu full gather exit $?"
 timeout 600 ncu --set full --clock-control none --import-source on -k regex:fm_fused_short -s 3 -c 1 \
