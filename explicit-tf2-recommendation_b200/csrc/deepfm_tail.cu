@@ -139,13 +139,26 @@ __global__ void __launch_bounds__(256) deepfm_tail_kernel(const Params p) {
   }
 }
 
-__global__ void __launch_bounds__(288) deepfm_tail_finish_kernel(const float* part, int nparts, long long B, float* loss,
+// a CTA owns 32 consecutive partial-sum slots; its 8 warps each add a contiguous range of the CTAs'
+// partials, combined in warp order (deterministic)
+__global__ void __launch_bounds__(256) deepfm_tail_finish_kernel(const float* part, int nparts, long long B, float* loss,
                                                                  float* g_bias_fm, float* gK3, float* gb3, float* gb2,
                                                                  float* gK2) {
-  const int e = threadIdx.x;
-  if (e >= NPART) return;
+  __shared__ float sm[8][32];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int e = blockIdx.x * 32 + lane;
+  const int per = (nparts + 7) / 8;
+  int c0 = warp * per, c1 = c0 + per;
+  if (c1 > nparts) c1 = nparts;
+  float t = 0.f;
+  if (e < NPART)
+    for (int c = c0; c < c1; ++c) t += part[(size_t)c * NPART + e];
+  sm[warp][lane] = t;
+  __syncthreads();
+  if (warp != 0 || e >= NPART) return;
   float s = 0.f;
-  for (int c = 0; c < nparts; ++c) s += part[(size_t)c * NPART + e];
+#pragma unroll
+  for (int w = 0; w < 8; ++w) s += sm[w][lane];
   if (e == 0) *loss = s / (float)B;
   else if (e == 1) { if (g_bias_fm) *g_bias_fm = s; }
   else if (e < 2 + H2) gK3[e - 2] = s;
@@ -178,7 +191,7 @@ int etr_deepfm_tail_train(etr_ctx* ctx, const float* d_h1, const float* d_fm_log
   p.prob = d_prob; p.dlogit = d_dlogit; p.d1 = d_d1; p.part = (float*)ctx->d_ws; p.B = batch; p.grad_scale = grad_scale;
   tail::deepfm_tail_kernel<<<grid, 256, 0, s>>>(p);
   ETR_LAUNCH_CHECK(ctx);
-  tail::deepfm_tail_finish_kernel<<<1, 288, 0, s>>>((const float*)ctx->d_ws, grid, batch, d_loss, d_g_bias_fm, d_gK3,
+  tail::deepfm_tail_finish_kernel<<<(tail::NPART + 31) / 32, 256, 0, s>>>((const float*)ctx->d_ws, grid, batch, d_loss, d_g_bias_fm, d_gK3,
                                                     d_gb3, d_gb2, d_gK2);
   ETR_LAUNCH_CHECK(ctx);
   return ETR_OK;

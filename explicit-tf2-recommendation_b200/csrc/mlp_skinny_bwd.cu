@@ -199,14 +199,27 @@ __global__ void __launch_bounds__(256, 2) mlp_skinny_bwd_kernel(const Params p) 
   if (tid < NOUT) out[(size_t)n_in * NOUT + tid] = db_acc;
 }
 
-// sum the per-CTA partials in CTA order
+// sum the per-CTA partials: a CTA owns 32 consecutive elements; its 8 warps each add a contiguous range
+// of the partials (coalesced 128-byte reads), the 8 sub-sums are combined in warp order (deterministic)
 __global__ void __launch_bounds__(256) mlp_skinny_bwd_finish_kernel(const float* part, int nparts, int n_elems, int n_k,
                                                                     float* dK, float* db) {
-  for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < n_elems; e += gridDim.x * blockDim.x) {
-    float s = 0.f;
-    for (int c = 0; c < nparts; ++c) s += part[(size_t)c * n_elems + e];
-    if (e < n_k) dK[e] = s;
-    else if (db) db[e - n_k] = s;
+  __shared__ float sm[8][32];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int e = blockIdx.x * 32 + lane;
+  const int per = (nparts + 7) / 8;
+  int c0 = warp * per, c1 = c0 + per;
+  if (c1 > nparts) c1 = nparts;
+  float s = 0.f;
+  if (e < n_elems)
+    for (int c = c0; c < c1; ++c) s += part[(size_t)c * n_elems + e];
+  sm[warp][lane] = s;
+  __syncthreads();
+  if (warp == 0 && e < n_elems) {
+    float t = 0.f;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) t += sm[w][lane];
+    if (e < n_k) dK[e] = t;
+    else if (db) db[e - n_k] = t;
   }
 }
 
@@ -259,7 +272,7 @@ int etr_mlp_skinny_backward(etr_ctx* ctx, const void* d_X, int64_t ldx, const fl
   }
 #undef ETR_SK
   ETR_LAUNCH_CHECK(ctx);
-  sk::mlp_skinny_bwd_finish_kernel<<<grid_for((long long)n_elems, 256, ctx->sm_count, 2), 256, 0, s>>>(
+  sk::mlp_skinny_bwd_finish_kernel<<<(int)((n_elems + 31) / 32), 256, 0, s>>>(
       (const float*)ctx->d_ws, (int)grid, (int)n_elems, n_in * sk::NOUT, d_dK, d_db);
   ETR_LAUNCH_CHECK(ctx);
   return ETR_OK;

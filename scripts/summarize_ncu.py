@@ -28,8 +28,13 @@ def launches(tag, fname="launches.csv", out="launches_one_step", what="DeepFM (c
     starts = [i for i, n in enumerate(names) if "gather_fm_fwd" in n]
     if len(starts) < 3:
         return
-    a, b = starts[pick[0]], starts[pick[1]]
-    step = rows[a:b]
+    # one train step = the longest run of launches between two consecutive gather launches (the roofline
+    # section of bench.py launches the gather kernel back to back: those windows have length 1)
+    wins = [(x, y) for x, y in zip(starts[:-1], starts[1:]) if y - x > 5]
+    if not wins:
+        return
+    a, b = wins[-1]                   # the last full step (the first one also zero-fills the Adam slots)
+    step = [r for r in rows[a:b] if "FillFunctor<unsigned char>" not in r["Kernel Name"]]     # bench.py's L2 flush
     tot = sum(float(r["Metric Value"]) for r in step) / 1e3
     with open(os.path.join(ROOT, "profiles", f"{tag}_{out}.md"), "w") as fh:
         fh.write(f"# {tag}: every kernel of ONE eager {what} train step, `ncu --metrics gpu__time_duration.sum "
