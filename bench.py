@@ -177,9 +177,12 @@ def workload_config(args, B, graph):
                     else "fp32 SIMT"), "id_distribution": args.dist,
             "apply_mode": "rowwise Adam",
             "parallelism": ((f"dp{args.gpus} batch x row-sharded table (id mod {args.gpus}), "
-                             + ("rows fetched by the gather kernel from NVLink peer memory, gradient rows pushed to the "
-                                "owners' mailboxes, device-side barriers (no NCCL in the step)"
-                                if getattr(args, "shard", "peer") == "peer" else "NCCL all-to-all"))
+                             + {"peer": "CUDA-IPC peer memory: unique ids requested from / rows served by the owners as "
+                                        "sequential peer stores, gradient rows returned through the same slots, "
+                                        "device-side barriers (no NCCL in the step)",
+                                "peer-pull": "rows pulled by the gather kernel from NVLink peer memory, gradient rows "
+                                             "pushed to the owners' mailboxes, device-side barriers (no NCCL in the step)",
+                                "a2a": "NCCL all-to-all"}[getattr(args, "shard", "peer")])
                             if args.gpus > 1 else "dp1"),
             "l2": "L2 flushed (512 MiB write) before every timed step", "cuda_graph": graph}
 
@@ -291,8 +294,9 @@ def main():
                     help="first MLP layer: bf16 tcgen05 tensor cores (fp32 accumulate) or the fp32 SIMT exact-parity path")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-budget", type=float, default=12.0)
-    ap.add_argument("--shard", default="peer", choices=["peer", "a2a"],
-                    help="N > 1: 'peer' = gather over NVLink peer memory (CUDA IPC), 'a2a' = NCCL all-to-all exchange")
+    ap.add_argument("--shard", default="peer", choices=["peer", "peer-pull", "a2a"],
+                    help="N > 1: 'peer' = CUDA-IPC peer memory, de-duplicated request/serve row exchange; 'peer-pull' = "
+                         "rows pulled by the gather kernel over NVLink; 'a2a' = NCCL all-to-all exchange")
     ap.add_argument("--config", default="c2", choices=["c2", "c3"],
                     help="c2 = DeepFM (the headline, BASELINE configs[1]); c3 = DCN-matrix bf16 tensor-core cross")
     args = ap.parse_args()
@@ -344,7 +348,7 @@ def main():
         dev_batches.append((ids, torch.from_numpy(np.ascontiguousarray(Xc.T)).to(dev), torch.from_numpy(y).to(dev)))
 
     # the all-to-all sharded step syncs split sizes on the host (no graph); the peer-memory step does not
-    use_graph = (not args.no_graph) and (world == 1 or args.shard == "peer")
+    use_graph = (not args.no_graph) and (world == 1 or args.shard != "a2a")
     trainer = L.Trainer(layer, lr=1e-3, apply_mode="rowwise", graph=use_graph)
     flush = torch.empty(512 << 20, dtype=torch.uint8, device=dev)
 
@@ -447,7 +451,7 @@ def main():
     id_batches = []
     for i in range(n_batches):
         ids_t = dev_batches[i][0]
-        if world > 1 and args.shard != "peer":
+        if world > 1 and args.shard == "a2a":
             ids_t = ids_t // world                    # local rows of this rank's shard (kernel-only timing)
         id_batches.append(IdsBatch(rt, ids_t, B, F, 1, 1, B, 1))
     kt = []
@@ -506,7 +510,7 @@ def main():
         "gpu_launches_per_step": launches_per_step,
         "roofline": {"bound": "hbm", "kernel": ("gather_fm_fwd_stream_kernel<float,4,13,2,true,true> (gather + FM terms + Flatten, "
                                                 f"one launch); rows of the {world - 1} other shards come over NVLink"
-                                                if world > 1 and args.shard == "peer" else
+                                                if world > 1 and args.shard != "a2a" else
                                                 "gather_fm_fwd_tile_kernel<float,4> (gather + FM terms + Flatten, one launch)"),
                      "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                      "traffic": traffic, "traffic_source": traffic_src, "peak_source": peak_src, "kernel_ms": k_ms,

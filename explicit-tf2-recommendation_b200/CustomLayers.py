@@ -50,8 +50,9 @@ class _Layer:
         self.check_ids = bool(kwargs.pop("check_ids", True))
         self.fused_apply = bool(kwargs.pop("fused_apply", True))     # FM family: fused backward+reduce+Adam
         self.name = kwargs.pop("name", type(self).__name__)
-        # row-sharded tables: shard=True | "a2a" (NCCL all-to-all exchange) | "peer" (rows fetched by the
-        # gather kernel itself from NVLink peer memory); world/rank from torch.distributed, or
+        # row-sharded tables: shard=True | "a2a" (NCCL all-to-all exchange) | "peer" (CUDA-IPC peer memory over
+        # NVLink: de-duplicated request/serve exchange in the fused train step, rows pulled by the gather kernel
+        # itself elsewhere) | "peer-pull" (always the fused pull); world/rank from torch.distributed, or
         # shard=(world, rank) / shard=("peer", world, rank)
         shard = kwargs.pop("shard", None)
         self.shard_spec, self.shard_mode = None, None
@@ -61,7 +62,7 @@ class _Layer:
                 mode, shard = shard, True
             elif isinstance(shard, (tuple, list)) and isinstance(shard[0], str):
                 mode, shard = shard[0], tuple(shard[1:])
-            assert mode in ("a2a", "peer"), mode
+            assert mode in ("a2a", "peer", "peer-pull"), mode
             if shard is True:
                 import torch.distributed as dist
                 shard = (dist.get_world_size(), dist.get_rank())
@@ -154,7 +155,7 @@ class FMRankingLayer(_Layer):
         self.params.add("bias", glorot_uniform((1,), self.gen, self.rt.device))
         if self.shard_spec:
             from .sharded import PeerShardedTable, ShardedTable
-            if self.shard_mode == "peer":
+            if self.shard_mode in ("peer", "peer-pull"):
                 assert self.table_dtype == torch.float32, "peer-sharded tables are fp32 in this round"
                 self.peer = PeerShardedTable(self.rt, self.feature_dims, k + 1, self.shard_spec[0], self.shard_spec[1])
                 self.table = self.peer                      # kernels see the GLOBAL table; views are the local rows
@@ -340,8 +341,16 @@ class DeepFMRankingLayer(FMRankingLayer):
         cont = self._cont(inputs, self.continuous_features) if C_ else None
         fm_logit = rt.empty((B,))
         sumv = rt.empty((B, k))
-        plan = SparsePlan(rt, vids, tab.rows, overlap=True)    # sort || everything below
-        gather_fm_forward(tab, k, True, vids, bias=self.bias, logit=fm_logit, sumv=sumv, flat=x, flat_col0=col0,
+        slot_of_u = None
+        if self.peer is not None and self.shard_mode == "peer":
+            # de-duplicated exchange: the sorted plan comes first, the owners write the unique rows into this rank's
+            # response buffer, and the gather below runs on that buffer (local HBM, mostly L2-resident)
+            plan = SparsePlan(rt, vids, tab.rows)
+            gtab, gids, slot_of_u = self.peer.exchange_forward(plan, B, F)
+        else:
+            plan = SparsePlan(rt, vids, tab.rows, overlap=True)    # sort || everything below
+            gtab, gids = tab, vids
+        gather_fm_forward(gtab, k, True, gids, bias=self.bias, logit=fm_logit, sumv=sumv, flat=x, flat_col0=col0,
                           cont=cont)
         m1, m2, P = self.MLP_layer1, self.MLP_layer2, self.params
         k0 = P.full(f"{m1.name}/kernel_0")
@@ -358,8 +367,11 @@ class DeepFMRankingLayer(FMRankingLayer):
         check(rt.lib.etr_mlp_skinny_backward(rt.ctx, x.data_ptr(), n_in, d1.data_ptr(), k0.data_ptr(), B, n_in, 32,
                                              dx.data_ptr(), n_in, P.gfull(f"{m1.name}/kernel_0").data_ptr(),
                                              P.g(f"{m1.name}/bias_0").data_ptr(), rt.stream))
-        grads = [self._fused_grad(FusedFMGrad(self.table, vids, k, dlogit, sumv, dx, col0, plan=plan))]
-        return loss, prob, grads
+        fused = FusedFMGrad(self.table, vids, k, dlogit, sumv, dx, col0, plan=plan)
+        if slot_of_u is not None:
+            from .sharded import PeerSlotGrad
+            return loss, prob, [PeerSlotGrad(self.peer, fused, slot_of_u)]
+        return loss, prob, [self._fused_grad(fused)]
 
     def backward(self, dlogit: torch.Tensor) -> List[SparseGrad]:
         rt = self.rt

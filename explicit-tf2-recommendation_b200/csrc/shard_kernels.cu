@@ -131,6 +131,128 @@ __global__ void __launch_bounds__(256) shard_mailbox_pad_kernel(long long* ids, 
   }
 }
 
+// ---- de-duplicated row exchange (peer form, forward): request -> serve -> virtual ids
+// request: every unique id of this rank's batch (sorted plan) is routed to its owner's request mailbox
+// (local row numbers; slots reserved per CTA) and remembers its (owner, slot); serve: the owner copies the
+// requested rows out of its shard into the requester's response buffer at the same (owner, slot) -- slots
+// of a region are consecutive, so the NVLink traffic is sequential full-line STORES instead of the
+// request-bound 80-byte remote loads of the fused pull (profiles/r01_mgpu.md); vid map: occurrence ->
+// response-buffer row, so the ordinary gather kernel runs on the response buffer as its table.
+struct RequestParams {
+  const long long* unique_ids; const int* n_unique;
+  int world, cap;
+  long long* req_mb[16];                 // owner g: this source's id region (peer pointer)
+  int* counts_mb[16];                    // owner g: &counts[source rank]
+  int* local_cnt;
+  int* slot_of_u;                        // [max_unique]: owner * cap + slot
+  unsigned long long* err;
+};
+__global__ void __launch_bounds__(256) shard_request_kernel(const RequestParams p) {
+  __shared__ int bin[16], base[16];
+  const int n_unique = *p.n_unique;
+  for (long long u0 = (long long)blockIdx.x * 256; u0 < n_unique; u0 += (long long)gridDim.x * 256) {      // CTA-uniform
+    if (threadIdx.x < 16) bin[threadIdx.x] = 0;
+    __syncthreads();
+    const long long u = u0 + threadIdx.x;
+    const bool active = u < n_unique;
+    int owner = 0, off = 0;
+    long long lrow = 0;
+    if (active) {
+      const long long id = p.unique_ids[u];
+      owner = (int)(id % p.world);
+      lrow = id / p.world;
+      off = atomicAdd(&bin[owner], 1);
+    }
+    __syncthreads();
+    if (threadIdx.x < p.world) base[threadIdx.x] = bin[threadIdx.x] ? atomicAdd(&p.local_cnt[threadIdx.x], bin[threadIdx.x]) : 0;
+    __syncthreads();
+    if (active) {
+      const int slot = base[owner] + off;
+      if (slot >= p.cap) {
+        flag_bad_id(p.err, -2);                       // mailbox region overflow
+        p.slot_of_u[u] = owner * p.cap;               // keep later kernels in range
+      } else {
+        p.req_mb[owner][slot] = lrow;
+        p.slot_of_u[u] = owner * p.cap + slot;
+      }
+    }
+    __syncthreads();
+  }
+}
+__global__ void shard_request_counts_kernel(const RequestParams p) {
+  const int g = threadIdx.x;
+  if (g < p.world) {
+    int c = p.local_cnt[g];
+    if (c > p.cap) c = p.cap;
+    *p.counts_mb[g] = c;
+    p.local_cnt[g] = 0;
+  }
+}
+
+struct ServeParams {
+  const float* table; int stride; long long rows;
+  const long long* req; const int* counts;   // own request mailbox [world][cap], counts[world]
+  int world, cap, ld, rank;
+  float* resp[16];                           // source g's response region for THIS owner: [cap][ld] (peer pointer)
+  unsigned long long* err;
+};
+template <int LPR>
+__global__ void __launch_bounds__(256) shard_serve_kernel(const ServeParams p) {
+  constexpr int GPW = 32 / LPR;
+  const int src = blockIdx.y;
+  const int lane = threadIdx.x & 31;
+  const int gl = lane % LPR, g = lane / LPR;
+  const int nchunks = p.ld / 4;
+  int n = p.counts[src];
+  if (n > p.cap) n = p.cap;
+  const long long* req = p.req + (long long)src * p.cap;
+  float* out = p.resp[src];
+  for (long long s = ((long long)blockIdx.x * 8 + (threadIdx.x >> 5)) * GPW + g; s < n; s += (long long)gridDim.x * 8 * GPW) {
+    long long row = req[s];
+    if ((unsigned long long)row >= (unsigned long long)p.rows) { flag_bad_id(p.err, row); row = 0; }
+    for (int c = gl; c < nchunks; c += LPR)
+      *reinterpret_cast<float4*>(out + s * p.ld + c * 4) = ldg_row16(p.table + row * p.stride + c * 4);
+  }
+}
+
+// vid[occurrence] = response-buffer row of the occurrence's id.  A thread per sorted position finds its
+// run by binary search over seg_start (n_unique + 1 entries, L2-resident).
+__global__ void __launch_bounds__(256) shard_vid_map_kernel(const int* sorted_bag, const int* seg_start, const int* n_unique,
+                                                            const int* slot_of_u, long long* vid) {
+  const int nu = *n_unique;
+  const int n_valid = seg_start[nu];
+  for (int pos = blockIdx.x * blockDim.x + threadIdx.x; pos < n_valid; pos += gridDim.x * blockDim.x) {
+    int lo = 0, hi = nu;                   // largest u with seg_start[u] <= pos
+    while (hi - lo > 1) {
+      const int mid = (lo + hi) >> 1;
+      if (seg_start[mid] <= pos) lo = mid; else hi = mid;
+    }
+    vid[sorted_bag[pos]] = slot_of_u[lo];
+  }
+}
+
+// gradient rows travel back through the SAME slots (the owner kept the request ids): no ids, no atomics
+struct PushSlotParams {
+  const float* unique_grad; const int* n_unique; const int* slot_of_u;
+  int cap, ld;
+  float* grads_mb[16];                       // owner g: this source's gradient region [cap][ld]
+};
+template <int LPR>
+__global__ void __launch_bounds__(256) shard_push_slots_kernel(const PushSlotParams p) {
+  constexpr int GPW = 32 / LPR;
+  const int lane = threadIdx.x & 31;
+  const int gl = lane % LPR, g = lane / LPR;
+  const int nchunks = p.ld / 4;
+  const int n = *p.n_unique;
+  for (long long u = ((long long)blockIdx.x * 8 + (threadIdx.x >> 5)) * GPW + g; u < n; u += (long long)gridDim.x * 8 * GPW) {
+    const int so = p.slot_of_u[u];
+    const int owner = so / p.cap, slot = so - owner * p.cap;
+    for (int c = gl; c < nchunks; c += LPR)
+      *reinterpret_cast<float4*>(p.grads_mb[owner] + (long long)slot * p.ld + c * 4) =
+          *reinterpret_cast<const float4*>(p.unique_grad + u * p.ld + c * 4);
+  }
+}
+
 // ---- owner side without a sort: dense gradient accumulator + touched-row list
 // Source g's region holds rows that are unique within the region, so adding it into the accumulator
 // gacc[local_rows, ld] needs no atomics; the regions are added by G consecutive launches in rank
@@ -383,6 +505,88 @@ int etr_shard_mailbox_pad(etr_ctx* ctx, int64_t* d_ids, const int32_t* d_counts,
   ETR_CHECK_ARG(ctx && d_ids && d_counts && world >= 1 && cap > 0, "bad argument");
   shard_mailbox_pad_kernel<<<grid_for((long long)world * cap, 256, ctx->sm_count, 8), 256, 0, (cudaStream_t)stream>>>(
       (long long*)d_ids, d_counts, world, cap);
+  ETR_LAUNCH_CHECK(ctx);
+  return ETR_OK;
+}
+
+int etr_shard_request(etr_ctx* ctx, const int64_t* d_unique_ids, const int32_t* d_n_unique, int64_t max_unique,
+                      int32_t world, int32_t cap, int64_t* const* h_req_mb, int32_t* const* h_counts_mb,
+                      int32_t* d_local_cnt, int32_t* d_slot_of_u, void* stream) {
+  ETR_CHECK_ARG(ctx && d_unique_ids && d_n_unique && h_req_mb && h_counts_mb && d_local_cnt && d_slot_of_u, "NULL argument");
+  ETR_CHECK_ARG(world >= 1 && world <= 16 && cap > 0 && (long long)world * cap < 0x7fffffffLL, "bad world / cap");
+  RequestParams p;
+  memset(&p, 0, sizeof(p));
+  p.unique_ids = (const long long*)d_unique_ids; p.n_unique = d_n_unique; p.world = world; p.cap = cap;
+  p.local_cnt = d_local_cnt; p.slot_of_u = d_slot_of_u; p.err = ctx->d_err;
+  for (int g = 0; g < world; ++g) { p.req_mb[g] = (long long*)h_req_mb[g]; p.counts_mb[g] = h_counts_mb[g]; }
+  cudaStream_t s = (cudaStream_t)stream;
+  if (max_unique > 0) {
+    shard_request_kernel<<<grid_for(max_unique, 256, ctx->sm_count, 4), 256, 0, s>>>(p);
+    ETR_LAUNCH_CHECK(ctx);
+  }
+  shard_request_counts_kernel<<<1, 32, 0, s>>>(p);
+  ETR_LAUNCH_CHECK(ctx);
+  return ETR_OK;
+}
+
+int etr_shard_serve(etr_ctx* ctx, const etr_table* table, const int64_t* d_req, const int32_t* d_counts, int32_t world,
+                    int32_t cap, float* const* h_resp, int32_t ld, void* stream) {
+  ETR_CHECK_ARG(ctx && table && table->d_data && d_req && d_counts && h_resp, "NULL argument");
+  ETR_CHECK_ARG(table->dtype == ETR_F32 && world >= 1 && world <= 16 && cap > 0 && ld % 4 == 0 && ld <= table->stride &&
+                    ld / 4 <= 32, "fp32 table, ld <= stride");
+  ServeParams p;
+  memset(&p, 0, sizeof(p));
+  p.table = (const float*)table->d_data; p.stride = table->stride; p.rows = table->rows; p.req = (const long long*)d_req;
+  p.counts = d_counts; p.world = world; p.cap = cap; p.ld = ld; p.err = ctx->d_err;
+  for (int g = 0; g < world; ++g) { ETR_CHECK_ARG(h_resp[g] != nullptr, "NULL response pointer"); p.resp[g] = h_resp[g]; }
+  int lpr = 1;
+  while (lpr < ld / 4) lpr <<= 1;
+  dim3 grid((unsigned)grid_for(cap, 8 * (32 / lpr), ctx->sm_count, 8 / (world < 8 ? world : 8) + 1), (unsigned)world);
+  cudaStream_t s = (cudaStream_t)stream;
+  switch (lpr) {
+    case 1: shard_serve_kernel<1><<<grid, 256, 0, s>>>(p); break;
+    case 2: shard_serve_kernel<2><<<grid, 256, 0, s>>>(p); break;
+    case 4: shard_serve_kernel<4><<<grid, 256, 0, s>>>(p); break;
+    case 8: shard_serve_kernel<8><<<grid, 256, 0, s>>>(p); break;
+    case 16: shard_serve_kernel<16><<<grid, 256, 0, s>>>(p); break;
+    default: shard_serve_kernel<32><<<grid, 256, 0, s>>>(p); break;
+  }
+  ETR_LAUNCH_CHECK(ctx);
+  return ETR_OK;
+}
+
+int etr_shard_vid_map(etr_ctx* ctx, const int32_t* d_sorted_bag, const int32_t* d_seg_start, const int32_t* d_n_unique,
+                      int64_t n_slots, const int32_t* d_slot_of_u, int64_t* d_vid, void* stream) {
+  ETR_CHECK_ARG(ctx && d_sorted_bag && d_seg_start && d_n_unique && d_slot_of_u && d_vid, "NULL argument");
+  if (n_slots <= 0) return ETR_OK;
+  shard_vid_map_kernel<<<grid_for(n_slots, 256, ctx->sm_count, 8), 256, 0, (cudaStream_t)stream>>>(
+      d_sorted_bag, d_seg_start, d_n_unique, d_slot_of_u, (long long*)d_vid);
+  ETR_LAUNCH_CHECK(ctx);
+  return ETR_OK;
+}
+
+int etr_shard_push_slots(etr_ctx* ctx, const float* d_unique_grad, const int32_t* d_n_unique, int64_t max_unique,
+                         const int32_t* d_slot_of_u, int32_t world, int32_t cap, int32_t ld, float* const* h_grads_mb,
+                         void* stream) {
+  ETR_CHECK_ARG(ctx && d_unique_grad && d_n_unique && d_slot_of_u && h_grads_mb, "NULL argument");
+  ETR_CHECK_ARG(world >= 1 && world <= 16 && cap > 0 && ld % 4 == 0 && ld / 4 <= 32, "bad world / cap / ld");
+  if (max_unique <= 0) return ETR_OK;
+  PushSlotParams p;
+  memset(&p, 0, sizeof(p));
+  p.unique_grad = d_unique_grad; p.n_unique = d_n_unique; p.slot_of_u = d_slot_of_u; p.cap = cap; p.ld = ld;
+  for (int g = 0; g < world; ++g) p.grads_mb[g] = h_grads_mb[g];
+  int lpr = 1;
+  while (lpr < ld / 4) lpr <<= 1;
+  const int grid = grid_for(max_unique, 8 * (32 / lpr), ctx->sm_count, 8);
+  cudaStream_t s = (cudaStream_t)stream;
+  switch (lpr) {
+    case 1: shard_push_slots_kernel<1><<<grid, 256, 0, s>>>(p); break;
+    case 2: shard_push_slots_kernel<2><<<grid, 256, 0, s>>>(p); break;
+    case 4: shard_push_slots_kernel<4><<<grid, 256, 0, s>>>(p); break;
+    case 8: shard_push_slots_kernel<8><<<grid, 256, 0, s>>>(p); break;
+    case 16: shard_push_slots_kernel<16><<<grid, 256, 0, s>>>(p); break;
+    default: shard_push_slots_kernel<32><<<grid, 256, 0, s>>>(p); break;
+  }
   ETR_LAUNCH_CHECK(ctx);
   return ETR_OK;
 }

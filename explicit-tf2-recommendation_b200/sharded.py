@@ -334,6 +334,12 @@ class PeerShardedTable:
             "counts_ptrs": counts.peer_array(self.rank * 4), "local_cnt": rt.zeros((W,), torch.int32),
             "touched": rt.empty((W * cap,), torch.int32), "n_touched": rt.zeros((1,), torch.int32),
         }
+        # response buffer of the de-duplicated forward exchange: [owner][cap][ld] on THIS rank; owner g writes its
+        # region through the pointer resp_ptrs[source] = source's buffer + g * cap * ld * 4
+        resp = PeerBuffer(rt, W * cap * ld * 4, W, self.rank, self.group)
+        self._mb["resp"] = resp
+        self._mb["resp_t"] = resp.tensor((W * cap, ld), torch.float32)
+        self._mb["resp_ptrs"] = resp.peer_array(self.rank * cap * ld * 4)
         self.cap = cap
         if W > 1:
             dist.barrier(group=self.group)
@@ -343,6 +349,36 @@ class PeerShardedTable:
         check(rt.lib.etr_shard_push(rt.ctx, unique_ids.data_ptr(), n_unique.data_ptr(), max_unique,
                                     unique_grad.data_ptr(), unique_grad.shape[1], self.world, self.cap, mb["ids_ptrs"],
                                     mb["grads_ptrs"], mb["counts_ptrs"], mb["local_cnt"].data_ptr(), rt.stream))
+
+    # -- de-duplicated forward exchange ------------------------------------------
+    def exchange_forward(self, plan, B: int, F: int):
+        """request -> barrier -> serve -> barrier -> virtual ids.  Returns (VirtualTable over the response buffer,
+        IdsBatch of response-buffer rows [B,F], slot_of_u) -- the fused gather kernel then runs on local memory."""
+        from .runtime import IdsBatch
+        rt, W = self.rt, self.world
+        self.ensure_mailbox(plan.n_slots)
+        mb, cap, ld = self._mb, self.cap, self.stride
+        slot_of_u = rt.empty((max(plan.n_slots, 1),), torch.int32)
+        check(rt.lib.etr_shard_request(rt.ctx, plan.unique_ids.data_ptr(), plan.counts.data_ptr(), plan.n_slots, W, cap,
+                                       mb["ids_ptrs"], mb["counts_ptrs"], mb["local_cnt"].data_ptr(),
+                                       slot_of_u.data_ptr(), rt.stream))
+        self.barrier()
+        t = self.local.desc()
+        check(rt.lib.etr_shard_serve(rt.ctx, C.byref(t), mb["ids_t"].data_ptr(), mb["counts_t"].data_ptr(), W, cap,
+                                     mb["resp_ptrs"], ld, rt.stream))
+        self.barrier()
+        vid = rt.empty((B * F,), torch.int64)
+        check(rt.lib.etr_shard_vid_map(rt.ctx, plan.sorted_bag.data_ptr(), plan.seg_start.data_ptr(),
+                                       plan.counts.data_ptr(), plan.n_slots, slot_of_u.data_ptr(), vid.data_ptr(),
+                                       rt.stream))
+        vt = VirtualTable(rt, mb["resp_t"], self.width)
+        return vt, IdsBatch(rt, vid, B, F, 1, F, 1, 1), slot_of_u
+
+    def push_slots(self, unique_grad: torch.Tensor, n_unique: torch.Tensor, max_unique: int, slot_of_u: torch.Tensor):
+        rt, mb = self.rt, self._mb
+        check(rt.lib.etr_shard_push_slots(rt.ctx, unique_grad.data_ptr(), n_unique.data_ptr(), max_unique,
+                                          slot_of_u.data_ptr(), self.world, self.cap, unique_grad.shape[1],
+                                          mb["grads_ptrs"], rt.stream))
 
     def apply_mailbox(self, d_lr_t: torch.Tensor, b1: float, b2: float, eps: float, mode: int):
         """owner side, no sort: the G source regions are added into the dense accumulator in rank order
@@ -382,3 +418,17 @@ class PeerFMGrad:
 
     def apply(self, d_lr_t, b1, b2, eps, mode=_lib.ADAM_ROWWISE):
         self.table.apply_mailbox(d_lr_t, b1, b2, eps, mode)
+
+
+class PeerSlotGrad(PeerFMGrad):
+    """Gradient of a peer-sharded table whose forward went through the de-duplicated exchange: the rows return
+    through the request slots (``slot_of_u``), no ids and no atomics."""
+
+    def __init__(self, table: PeerShardedTable, fused, slot_of_u: torch.Tensor):
+        super().__init__(table, fused)
+        self.slot_of_u = slot_of_u
+
+    def push(self):
+        f = self.fused
+        f.reduce()
+        self.table.push_slots(f.unique_grad, f.plan.counts, f.plan.n_slots, self.slot_of_u)

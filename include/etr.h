@@ -386,6 +386,26 @@ int etr_shard_push(etr_ctx* ctx, const int64_t* d_unique_ids, const int32_t* d_n
                    int32_t* d_local_cnt, void* stream);
 int etr_shard_mailbox_pad(etr_ctx* ctx, int64_t* d_ids, const int32_t* d_counts, int32_t world, int32_t cap,
                           void* stream);
+/* De-duplicated row exchange of the peer form (forward of a row-sharded Embedding gather,
+ * 2.FM/CustomLayers.py:146-147 across GPUs).  etr_shard_request routes every unique id of the
+ * rank's batch (etr_sparse_plan output) to its owner's request mailbox (local row numbers, region
+ * [source][cap], counts published like etr_shard_push) and records d_slot_of_u[u] = owner*cap+slot.
+ * After an etr_peer_barrier, etr_shard_serve makes the owner copy the requested rows of its shard
+ * into each requester's response buffer [world][cap][ld] at the same (owner, slot): NVLink carries
+ * sequential full-line stores instead of request-bound 80-byte remote loads.  After a second
+ * barrier etr_shard_vid_map turns every occurrence into its response-buffer row, so
+ * etr_gather_fm_forward runs on the response buffer as its table.  etr_shard_push_slots later
+ * returns the gradient rows through the same slots (the owner kept the request ids).          */
+int etr_shard_request(etr_ctx* ctx, const int64_t* d_unique_ids, const int32_t* d_n_unique, int64_t max_unique,
+                      int32_t world, int32_t cap, int64_t* const* h_req_mb, int32_t* const* h_counts_mb,
+                      int32_t* d_local_cnt, int32_t* d_slot_of_u, void* stream);
+int etr_shard_serve(etr_ctx* ctx, const etr_table* table, const int64_t* d_req, const int32_t* d_counts, int32_t world,
+                    int32_t cap, float* const* h_resp, int32_t ld, void* stream);
+int etr_shard_vid_map(etr_ctx* ctx, const int32_t* d_sorted_bag, const int32_t* d_seg_start, const int32_t* d_n_unique,
+                      int64_t n_slots, const int32_t* d_slot_of_u, int64_t* d_vid, void* stream);
+int etr_shard_push_slots(etr_ctx* ctx, const float* d_unique_grad, const int32_t* d_n_unique, int64_t max_unique,
+                         const int32_t* d_slot_of_u, int32_t world, int32_t cap, int32_t ld, float* const* h_grads_mb,
+                         void* stream);
 /* Owner side of the peer-sharded apply WITHOUT a sort (replaces Unique + UnsortedSegmentSum +
  * Adam._resource_apply_sparse of 2.FM/ModelManager.py:178 on the shard): the G source regions of
  * the mailbox -- rows unique within a region -- are added into a dense accumulator

@@ -1,4 +1,4 @@
-"""Phase timing of the peer-sharded DeepFM step (eager, CUDA events on the launch stream), under torchrun."""
+"""Phase timing of the peer-sharded DeepFM step (de-duplicated request/serve exchange) (eager, CUDA events on the launch stream), under torchrun."""
 import os
 import sys
 
@@ -43,34 +43,82 @@ def main():
         e.record()
         marks.append((name, e))
 
+    import ctypes as C
+    from etr_b200 import _lib
+    from etr_b200.runtime import FusedFMGrad, IdsBatch, SparsePlan, cast_bf16, gather_fm_forward, gemm_bf16_tn
+    from etr_b200.sharded import PeerSlotGrad, VirtualTable
+    names_c = cont
+
     def step(d, y):
+        """the fused train step of DeepFMRankingLayer.train_forward_backward + Trainer, phase by phase"""
         marks.clear()
+        lay, P = layer, layer.params
+        k, F = lay.embedding_dims, len(lay.feature_names)
         mark("start")
-        out = layer(d, training=True)["output"]
-        mark("forward (ids assemble + gather over NVLink + MLP)")
-        loss, dlogit = bce_forward_backward(rt, out.reshape(-1), y)
-        dlogit.mul_(1.0 / world)
-        grads = layer.backward(dlogit)
-        last["grads"] = grads
-        mark("bce + MLP backward")
-        for g in grads:
-            g.fused.reduce()
-        mark("fused backward export (deferred form, no remote reads)")
-        for g in grads:
-            peer.ensure_mailbox(g.fused.plan.n_slots)
-            peer.push(g.fused.plan.unique_ids, g.fused.plan.counts, g.fused.plan.n_slots, g.fused.unique_grad)
-        peer.allreduce_push(layer.params.grad)
-        mark("push rows + dense grads")
+        ids = lay._ids(d, lay.feature_names)
+        cont_m = lay._cont(d, names_c)
+        B = ids.B
+        col0 = lay.front_pad + len(names_c)
+        n_in = col0 + F * k
+        plan = SparsePlan(rt, ids, peer.rows)
+        mark("ids assemble + sorted plan (CUB sort + unique)")
+        peer.ensure_mailbox(plan.n_slots)
+        mb, cap, ld, W = peer._mb, peer.cap, peer.stride, world
+        slot_of_u = rt.empty((plan.n_slots,), torch.int32)
+        check(rt.lib.etr_shard_request(rt.ctx, plan.unique_ids.data_ptr(), plan.counts.data_ptr(), plan.n_slots, W, cap,
+                                       mb["ids_ptrs"], mb["counts_ptrs"], mb["local_cnt"].data_ptr(),
+                                       slot_of_u.data_ptr(), rt.stream))
+        mark("request: unique ids -> owners' mailboxes")
         peer.barrier()
-        mark("barrier 1")
-        peer.allreduce_sum(layer.params.grad)
+        mark("barrier")
+        t = peer.local.desc()
+        check(rt.lib.etr_shard_serve(rt.ctx, C.byref(t), mb["ids_t"].data_ptr(), mb["counts_t"].data_ptr(), W, cap,
+                                     mb["resp_ptrs"], ld, rt.stream))
+        mark("serve: owners write the rows into the requesters' buffers")
+        peer.barrier()
+        mark("barrier ")
+        vid = rt.empty((B * F,), torch.int64)
+        check(rt.lib.etr_shard_vid_map(rt.ctx, plan.sorted_bag.data_ptr(), plan.seg_start.data_ptr(),
+                                       plan.counts.data_ptr(), plan.n_slots, slot_of_u.data_ptr(), vid.data_ptr(), rt.stream))
+        mark("virtual ids (occurrence -> response row)")
+        x = rt.empty((B, n_in), torch.bfloat16)
+        fm_logit, sumv = rt.empty((B,)), rt.empty((B, k))
+        gather_fm_forward(VirtualTable(rt, mb["resp_t"], peer.width), k, True, IdsBatch(rt, vid, B, F, 1, F, 1, 1),
+                          bias=lay.bias, logit=fm_logit, sumv=sumv, flat=x, flat_col0=col0, cont=cont_m)
+        mark("K1 gather + FM on the response buffer")
+        m1, m2 = lay.MLP_layer1, lay.MLP_layer2
+        k0 = P.full(f"{m1.name}/kernel_0")
+        y1 = rt.empty((B, 32))
+        gemm_bf16_tn(rt, x, cast_bf16(rt, k0, transpose=True), y1, B, 32, n_in, bias=P[f"{m1.name}/bias_0"], act="relu")
+        prob, dlogit, d1, loss = rt.empty((B, 1)), rt.empty((B,)), rt.empty((B, 32)), rt.empty((1,))
+        check(rt.lib.etr_deepfm_tail_train(
+            rt.ctx, y1.data_ptr(), fm_logit.data_ptr(), y.data_ptr(), B, P[f"{m1.name}/kernel_1"].data_ptr(),
+            P[f"{m1.name}/bias_1"].data_ptr(), P[f"{m2.name}/kernel_0"].data_ptr(), P[f"{m2.name}/bias_0"].data_ptr(),
+            1.0 / world, prob.data_ptr(), dlogit.data_ptr(), d1.data_ptr(), loss.data_ptr(), P.g("bias").data_ptr(),
+            P.g(f"{m1.name}/kernel_1").data_ptr(), P.g(f"{m1.name}/bias_1").data_ptr(),
+            P.g(f"{m2.name}/kernel_0").data_ptr(), P.g(f"{m2.name}/bias_0").data_ptr(), rt.stream))
+        dx = rt.empty((B, n_in), torch.bfloat16)
+        check(rt.lib.etr_mlp_skinny_backward(rt.ctx, x.data_ptr(), n_in, d1.data_ptr(), k0.data_ptr(), B, n_in, 32,
+                                             dx.data_ptr(), n_in, P.gfull(f"{m1.name}/kernel_0").data_ptr(),
+                                             P.g(f"{m1.name}/bias_0").data_ptr(), rt.stream))
+        mark("MLP layer 1 (tcgen05) + tail/loss fwd+bwd (K7c) + layer-1 backward (K7b)")
+        g = PeerSlotGrad(peer, FusedFMGrad(lay.table, ids, k, dlogit, sumv, dx, col0, plan=plan), slot_of_u)
+        last["grads"] = [g]
+        g.fused.reduce()
+        mark("fused FM backward export (deferred form, no remote reads)")
+        peer.push_slots(g.fused.unique_grad, plan.counts, plan.n_slots, slot_of_u)
+        peer.allreduce_push(P.grad)
+        mark("gradient rows -> owners (same slots) + dense grads -> peers")
+        peer.barrier()
+        mark("barrier  ")
+        peer.allreduce_sum(P.grad)
         check(rt.lib.etr_adam_step_begin(rt.ctx, tr.state.data_ptr(), tr.lr, tr.b1, tr.b2, rt.stream))
-        layer.params.adam_step(0.0, tr.state[1:], tr.b1, tr.b2, tr.eps)
+        P.adam_step(0.0, tr.state[1:], tr.b1, tr.b2, tr.eps)
         mark("dense sum + adam")
         peer.apply_mailbox(tr.state[1:], tr.b1, tr.b2, tr.eps, 0)
         mark("owner: accumulate regions + touched-row adam")
         peer.barrier()
-        mark("barrier 2")
+        mark("barrier   ")
 
     for i in range(6):
         step(*batches[i % 4])

@@ -29,14 +29,17 @@ def main():
     F, k, V, C, B = 26, 16, 100003, 13, 4096
     names, cont = [f"f{i}" for i in range(F)], [f"c{i}" for i in range(C)]
     msgs = []
-    for mode, graph in (("a2a", False), ("peer", False), ("peer", True)):
-        sharded = L.DeepFMRankingLayer(names, V, k, continuous_features=cont, seed=3, shard=mode, check_ids=False)
-        full = L.DeepFMRankingLayer(names, V, k, continuous_features=cont, seed=3, check_ids=False)
+    for mode, graph, prec in (("a2a", False, "fp32"), ("peer-pull", False, "fp32"), ("peer-pull", True, "fp32"),
+                              ("peer", False, "bf16"), ("peer", True, "bf16")):
+        # "peer" + bf16 tower takes the fused train step with the de-duplicated request/serve exchange
+        sharded = L.DeepFMRankingLayer(names, V, k, continuous_features=cont, seed=3, shard=mode, check_ids=False,
+                                       mlp_precision=prec)
+        full = L.DeepFMRankingLayer(names, V, k, continuous_features=cont, seed=3, check_ids=False, mlp_precision=prec)
         # identical global weights on every rank
         g = torch.Generator(device="cuda").manual_seed(1234)
         table = torch.empty(V, k + 1, device="cuda").uniform_(-0.05, 0.05, generator=g)
         full.table.data[:, : k + 1] = table
-        (sharded.peer if mode == "peer" else sharded.shard).load_global(table)
+        (sharded.peer if mode.startswith("peer") else sharded.shard).load_global(table)
         sharded.params.value.copy_(full.params.value)
         torch.cuda.synchronize()
         dist.barrier()                                  # every shard is loaded before anyone reads it
@@ -72,20 +75,31 @@ def main():
             lf = tr_f.train_step(gd, torch.cat(ys))
             lsum = ls.clone()
             dist.all_reduce(lsum)
-            assert abs(float(lsum.item()) / world - float(lf.item())) < 1e-5, \
+            assert abs(float(lsum.item()) / world - float(lf.item())) < (1e-5 if prec == "fp32" else 1e-4), \
                 (mode, graph, step, float(lsum.item()) / world, float(lf.item()))
+            if step == 0:
+                # one step from identical weights: the sharded and the unsharded update agree to fp32 rounding in
+                # EVERY mode (later steps of the bf16 tower do not: a 1e-7 difference in an fp32 weight can flip its
+                # bf16 rounding, a 0.4 % change of that operand -- measured drift 1e-5 .. 6e-4 after 3-6 steps)
+                torch.cuda.synchronize()
+                mine0 = full.table.data[rank::world]
+                e_t = (sharded.table.data[: mine0.shape[0]] - mine0).abs().max().item()
+                e_d = (sharded.params.value - full.params.value).abs().max().item()
+                assert e_t < 2e-6 and e_d < 2e-6, (mode, graph, "first step", rank, e_t, e_d)
         sharded.rt.poll_error()
         mine = full.table.data[rank::world]
         err_t = (sharded.table.data[: mine.shape[0]] - mine).abs().max().item()
         err_d = (sharded.params.value - full.params.value).abs().max().item()
-        assert err_t < 2e-5 and err_d < 2e-5, (mode, graph, rank, err_t, err_d)   # lr 1e-2: < 0.2% of one Adam step
-        if mode == "peer":
+        # lr 1e-2: < 0.2% of one Adam step (fp32); bf16 tower: see the first-step check above
+        tol = 2e-5 if prec == "fp32" else 5e-3
+        assert err_t < tol and err_d < tol, (mode, graph, rank, err_t, err_d)
+        if mode.startswith("peer"):
             # replicated dense variables must stay BIT-identical across ranks (deterministic rank-order sum)
             ref = sharded.params.value.clone()
             dist.broadcast(ref, 0)
             assert torch.equal(ref, sharded.params.value), f"rank {rank}: dense replicas diverged"
         dist.barrier()
-        msgs.append(f"{mode}{'+graph' if graph else ''}: table_err={err_t:.2e} dense_err={err_d:.2e}")
+        msgs.append(f"{mode}{'+graph' if graph else ''}/{prec}: table_err={err_t:.2e} dense_err={err_d:.2e}")
     if rank == 0:
         print(f"MGPU_OK world={world} " + " | ".join(msgs))
     dist.destroy_process_group()
