@@ -34,6 +34,9 @@ struct FusedParams {
   float lr_t; const float* d_lr_t; float b1, b2, eps;
   int apply;                  // 1: Adam update; 0: only export the gradient rows
   float* unique_grad;         // optional [n_unique, stride]
+  // peer-sharded export straight into the owners' gradient mailboxes (NVLink peer stores): row u goes to
+  // slot_of_u[u] = owner * cap + slot of the request exchange; replaces unique_grad + a push kernel
+  const int* slot_of_u; int cap; float* grads_mb[16];
   int* counters; FusedLong* long_runs; int2* items; float* partials; int max_long, max_items;
   const char* shard_base[16]; int world;     // peer-sharded table (export mode only): ids are global
 };
@@ -138,7 +141,13 @@ __device__ __forceinline__ void fused_finish_row(const FusedParams& p, long long
   float* prow = p.table + row * p.stride;
   float4 var = st.var;
   const float4 g = make_float4(P.x - var.x * sum_g, P.y - var.y * sum_g, P.z - var.z * sum_g, P.w - var.w * sum_g);
-  if (p.unique_grad) *reinterpret_cast<float4*>(p.unique_grad + u * p.stride + gl * 4) = g;
+  float* gdst = p.unique_grad ? p.unique_grad + u * p.stride : nullptr;
+  if (p.slot_of_u) {
+    const int so = p.slot_of_u[u];
+    const int owner = so / p.cap;
+    gdst = p.grads_mb[owner] + (long long)(so - owner * p.cap) * p.stride;
+  }
+  if (gdst) *reinterpret_cast<float4*>(gdst + gl * 4) = g;
   if (p.apply) {
     float4 m = st.m, v = st.v;
     adam_update4(var, m, v, g, lr_t, p.b1, p.b2, p.eps);
@@ -150,7 +159,7 @@ __device__ __forceinline__ void fused_finish_row(const FusedParams& p, long long
     // chunks behind the embedding: [w, 0, 0, 0] (+ zero padding chunks)
     for (int c = p.k; c < p.stride; c += 4) {
       const float4 gw = make_float4(c == p.k ? sum_g : 0.f, 0.f, 0.f, 0.f);
-      if (p.unique_grad) *reinterpret_cast<float4*>(p.unique_grad + u * p.stride + c) = gw;
+      if (gdst) *reinterpret_cast<float4*>(gdst + c) = gw;
       if (p.apply && c == p.k) {
         float4 wv = *reinterpret_cast<const float4*>(prow + c);
         float4* pm = reinterpret_cast<float4*>(p.m + row * p.stride + c);
@@ -267,18 +276,19 @@ __global__ void __launch_bounds__(256) fm_fused_combine_kernel(const FusedParams
 
 using namespace etr;
 
-extern "C" {
 
-int etr_fm_fused_backward_apply(etr_ctx* ctx, const etr_table* table, float* d_m, float* d_v, int32_t k, int32_t fields,
-                                int64_t batch, const int32_t* d_sorted_bag, const int32_t* d_seg_start,
-                                const int64_t* d_unique_ids, const int32_t* d_n_unique, int64_t n_slots,
-                                const float* d_dlogit, const float* d_sumv, const void* d_dflat, int32_t flat_dtype,
-                                int64_t flat_ld, int32_t flat_col0, float lr_t, const float* d_lr_t, float beta1,
-                                float beta2, float eps, int32_t apply, float* d_unique_grad, void* stream) {
+
+static int fused_impl(etr_ctx* ctx, const etr_table* table, float* d_m, float* d_v, int32_t k, int32_t fields,
+                      int64_t batch, const int32_t* d_sorted_bag, const int32_t* d_seg_start,
+                      const int64_t* d_unique_ids, const int32_t* d_n_unique, int64_t n_slots,
+                      const float* d_dlogit, const float* d_sumv, const void* d_dflat, int32_t flat_dtype,
+                      int64_t flat_ld, int32_t flat_col0, float lr_t, const float* d_lr_t, float beta1,
+                      float beta2, float eps, int32_t apply, float* d_unique_grad, const int32_t* d_slot_of_u, int32_t cap,
+                      float* const* h_grads_mb, void* stream) {
   ETR_CHECK_ARG(ctx && table && table->d_data && d_sorted_bag && d_seg_start && d_unique_ids && d_n_unique && d_dlogit &&
                     d_sumv, "NULL argument");
   ETR_CHECK_ARG(!apply || (d_m && d_v), "Adam slots missing");
-  ETR_CHECK_ARG(apply || d_unique_grad, "nothing to do: apply == 0 and no gradient output");
+  ETR_CHECK_ARG(apply || d_unique_grad || d_slot_of_u, "nothing to do: apply == 0 and no gradient output");
   if (table->dtype != ETR_F32) { etr_set_error("etr_fm_fused_backward_apply: fp32 tables only"); return ETR_EUNSUPPORTED; }
   const int lpr = k / 4;
   if (k % 4 != 0 || lpr < 1 || lpr > 32 || (lpr & (lpr - 1)) != 0 || table->width != k + 1 || table->stride % 4 != 0 ||
@@ -307,6 +317,7 @@ int etr_fm_fused_backward_apply(etr_ctx* ctx, const etr_table* table, float* d_m
   p.dlogit = d_dlogit; p.sumv = d_sumv; p.dflat = d_dflat; p.flat_bf16 = flat_dtype == ETR_BF16; p.flat_ld = flat_ld;
   p.flat_col0 = flat_col0; p.lr_t = lr_t; p.d_lr_t = d_lr_t; p.b1 = beta1; p.b2 = beta2; p.eps = eps; p.apply = apply;
   p.unique_grad = d_unique_grad;
+  p.slot_of_u = d_slot_of_u; p.cap = cap;
   p.world = 1;
   if (table->reserved > 0) {
     ETR_CHECK_ARG(table->reserved <= ctx->n_shard_sets, "unknown shard set");
@@ -314,6 +325,10 @@ int etr_fm_fused_backward_apply(etr_ctx* ctx, const etr_table* table, float* d_m
     const EtrShardSet& ss = ctx->shard_sets[table->reserved - 1];
     p.world = ss.world;
     for (int g = 0; g < ss.world; ++g) p.shard_base[g] = ss.base[g];
+  }
+  if (d_slot_of_u) {
+    ETR_CHECK_ARG(h_grads_mb && cap > 0 && p.world > 1 && !apply, "mailbox export needs a peer-sharded table, apply == 0");
+    for (int g = 0; g < p.world; ++g) { ETR_CHECK_ARG(h_grads_mb[g] != nullptr, "NULL mailbox pointer"); p.grads_mb[g] = h_grads_mb[g]; }
   }
   p.max_long = (int)(n_slots / kFusedShortRun + 1);
   p.max_items = (int)(n_slots / kFusedChunk + n_slots / kFusedShortRun + 2);
@@ -349,6 +364,30 @@ int etr_fm_fused_backward_apply(etr_ctx* ctx, const etr_table* table, float* d_m
   }
 #undef ETR_FUSED
   return ETR_OK;
+}
+
+extern "C" {
+
+int etr_fm_fused_backward_apply(etr_ctx* ctx, const etr_table* table, float* d_m, float* d_v, int32_t k, int32_t fields,
+                                int64_t batch, const int32_t* d_sorted_bag, const int32_t* d_seg_start,
+                                const int64_t* d_unique_ids, const int32_t* d_n_unique, int64_t n_slots,
+                                const float* d_dlogit, const float* d_sumv, const void* d_dflat, int32_t flat_dtype,
+                                int64_t flat_ld, int32_t flat_col0, float lr_t, const float* d_lr_t, float beta1,
+                                float beta2, float eps, int32_t apply, float* d_unique_grad, void* stream) {
+  return fused_impl(ctx, table, d_m, d_v, k, fields, batch, d_sorted_bag, d_seg_start, d_unique_ids, d_n_unique, n_slots,
+                    d_dlogit, d_sumv, d_dflat, flat_dtype, flat_ld, flat_col0, lr_t, d_lr_t, beta1, beta2, eps, apply,
+                    d_unique_grad, nullptr, 0, nullptr, stream);
+}
+
+int etr_fm_fused_backward_push(etr_ctx* ctx, const etr_table* table, int32_t k, int32_t fields, int64_t batch,
+                               const int32_t* d_sorted_bag, const int32_t* d_seg_start, const int64_t* d_unique_ids,
+                               const int32_t* d_n_unique, int64_t n_slots, const float* d_dlogit, const float* d_sumv,
+                               const void* d_dflat, int32_t flat_dtype, int64_t flat_ld, int32_t flat_col0,
+                               const int32_t* d_slot_of_u, int32_t cap, float* const* h_grads_mb, void* stream) {
+  ETR_CHECK_ARG(d_slot_of_u && h_grads_mb, "NULL argument");
+  return fused_impl(ctx, table, nullptr, nullptr, k, fields, batch, d_sorted_bag, d_seg_start, d_unique_ids, d_n_unique,
+                    n_slots, d_dlogit, d_sumv, d_dflat, flat_dtype, flat_ld, flat_col0, 0.f, nullptr, 0.f, 0.f, 0.f, 0,
+                    nullptr, d_slot_of_u, cap, h_grads_mb, stream);
 }
 
 }  // extern "C"

@@ -219,15 +219,24 @@ __global__ void __launch_bounds__(256) shard_serve_kernel(const ServeParams p) {
 // run by binary search over seg_start (n_unique + 1 entries, L2-resident).
 __global__ void __launch_bounds__(256) shard_vid_map_kernel(const int* sorted_bag, const int* seg_start, const int* n_unique,
                                                             const int* slot_of_u, long long* vid) {
+  constexpr int PER = 8;                   // consecutive sorted positions per thread: one search, then a walk
   const int nu = *n_unique;
   const int n_valid = seg_start[nu];
-  for (int pos = blockIdx.x * blockDim.x + threadIdx.x; pos < n_valid; pos += gridDim.x * blockDim.x) {
-    int lo = 0, hi = nu;                   // largest u with seg_start[u] <= pos
+  for (long long p0 = ((long long)blockIdx.x * blockDim.x + threadIdx.x) * PER; p0 < n_valid;
+       p0 += (long long)gridDim.x * blockDim.x * PER) {
+    int lo = 0, hi = nu;                   // largest u with seg_start[u] <= p0
     while (hi - lo > 1) {
       const int mid = (lo + hi) >> 1;
-      if (seg_start[mid] <= pos) lo = mid; else hi = mid;
+      if (seg_start[mid] <= p0) lo = mid; else hi = mid;
     }
-    vid[sorted_bag[pos]] = slot_of_u[lo];
+    int next = seg_start[lo + 1];
+    int so = slot_of_u[lo];
+    for (int q = 0; q < PER; ++q) {
+      const int pos = (int)p0 + q;
+      if (pos >= n_valid) break;
+      while (pos >= next) { ++lo; next = seg_start[lo + 1]; so = slot_of_u[lo]; }
+      vid[sorted_bag[pos]] = so;
+    }
   }
 }
 
@@ -559,7 +568,7 @@ int etr_shard_vid_map(etr_ctx* ctx, const int32_t* d_sorted_bag, const int32_t* 
                       int64_t n_slots, const int32_t* d_slot_of_u, int64_t* d_vid, void* stream) {
   ETR_CHECK_ARG(ctx && d_sorted_bag && d_seg_start && d_n_unique && d_slot_of_u && d_vid, "NULL argument");
   if (n_slots <= 0) return ETR_OK;
-  shard_vid_map_kernel<<<grid_for(n_slots, 256, ctx->sm_count, 8), 256, 0, (cudaStream_t)stream>>>(
+  shard_vid_map_kernel<<<grid_for(n_slots, 256 * 8, ctx->sm_count, 8), 256, 0, (cudaStream_t)stream>>>(
       d_sorted_bag, d_seg_start, d_n_unique, d_slot_of_u, (long long*)d_vid);
   ETR_LAUNCH_CHECK(ctx);
   return ETR_OK;

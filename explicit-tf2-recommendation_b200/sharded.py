@@ -429,6 +429,12 @@ class PeerSlotGrad(PeerFMGrad):
         self.slot_of_u = slot_of_u
 
     def push(self):
-        f = self.fused
-        f.reduce()
-        self.table.push_slots(f.unique_grad, f.plan.counts, f.plan.n_slots, self.slot_of_u)
+        """fused FM backward (deferred form) writing every unique row straight into its owner's mailbox slot"""
+        from .runtime import _TORCH2ETR, _p
+        f, T = self.fused, self.table
+        rt, t, plan, df = T.rt, f.table.desc(), f.plan.join(), f.dflat
+        check(rt.lib.etr_fm_fused_backward_push(
+            rt.ctx, C.byref(t), f.k, f.ids.F, f.ids.B, plan.sorted_bag.data_ptr(), plan.seg_start.data_ptr(),
+            plan.unique_ids.data_ptr(), plan.counts.data_ptr(), plan.n_slots, f.dlogit.data_ptr(), f.sumv.data_ptr(),
+            _p(df), _TORCH2ETR[df.dtype] if df is not None else 0, df.stride(0) if df is not None else 0, f.flat_col0,
+            self.slot_of_u.data_ptr(), T.cap, T._mb["grads_ptrs"], rt.stream))

@@ -386,6 +386,14 @@ int etr_shard_push(etr_ctx* ctx, const int64_t* d_unique_ids, const int32_t* d_n
                    int32_t* d_local_cnt, void* stream);
 int etr_shard_mailbox_pad(etr_ctx* ctx, int64_t* d_ids, const int32_t* d_counts, int32_t world, int32_t cap,
                           void* stream);
+/* etr_fm_fused_backward_apply(apply = 0) on a peer-sharded table, writing every exported (deferred)
+ * gradient row straight into its owner's mailbox slot d_slot_of_u[u] = owner*cap + slot (peer
+ * stores over NVLink) instead of a local buffer + etr_shard_push_slots.                          */
+int etr_fm_fused_backward_push(etr_ctx* ctx, const etr_table* table, int32_t k, int32_t fields, int64_t batch,
+                               const int32_t* d_sorted_bag, const int32_t* d_seg_start, const int64_t* d_unique_ids,
+                               const int32_t* d_n_unique, int64_t n_slots, const float* d_dlogit, const float* d_sumv,
+                               const void* d_dflat, int32_t flat_dtype, int64_t flat_ld, int32_t flat_col0,
+                               const int32_t* d_slot_of_u, int32_t cap, float* const* h_grads_mb, void* stream);
 /* De-duplicated row exchange of the peer form (forward of a row-sharded Embedding gather,
  * 2.FM/CustomLayers.py:146-147 across GPUs).  etr_shard_request routes every unique id of the
  * rank's batch (etr_sparse_plan output) to its owner's request mailbox (local row numbers, region

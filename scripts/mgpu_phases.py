@@ -104,11 +104,10 @@ def main():
         mark("MLP layer 1 (tcgen05) + tail/loss fwd+bwd (K7c) + layer-1 backward (K7b)")
         g = PeerSlotGrad(peer, FusedFMGrad(lay.table, ids, k, dlogit, sumv, dx, col0, plan=plan), slot_of_u)
         last["grads"] = [g]
-        g.fused.reduce()
-        mark("fused FM backward export (deferred form, no remote reads)")
-        peer.push_slots(g.fused.unique_grad, plan.counts, plan.n_slots, slot_of_u)
+        g.push()
+        mark("fused FM backward, rows written straight into the owners' mailbox slots")
         peer.allreduce_push(P.grad)
-        mark("gradient rows -> owners (same slots) + dense grads -> peers")
+        mark("dense grads -> peers")
         peer.barrier()
         mark("barrier  ")
         peer.allreduce_sum(P.grad)
