@@ -449,10 +449,15 @@ def main():
     # latency of timing a single ~50 us launch is amortised
     GROUP = 4
     id_batches = []
+    # N > 1: the exchange forms run the gather on rows that are local when the kernel starts (response buffer /
+    # received rows): time it on this rank's shard with local row numbers; --shard peer-pull times the pull over NVLink
+    k1_table = layer.table
+    if world > 1 and args.shard == "peer":
+        k1_table = layer.peer.local
     for i in range(n_batches):
         ids_t = dev_batches[i][0]
-        if world > 1 and args.shard == "a2a":
-            ids_t = ids_t // world                    # local rows of this rank's shard (kernel-only timing)
+        if world > 1 and args.shard != "peer-pull":
+            ids_t = ids_t // world
         id_batches.append(IdsBatch(rt, ids_t, B, F, 1, 1, B, 1))
     kt = []
     for i in range(max(args.steps // 2, 8)):
@@ -460,7 +465,7 @@ def main():
         a, b_ = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         a.record()
         for j in range(GROUP):
-            gather_fm_forward(layer.table, K_EMB, True, id_batches[(i * GROUP + j) % n_batches], bias=layer.bias,
+            gather_fm_forward(k1_table, K_EMB, True, id_batches[(i * GROUP + j) % n_batches], bias=layer.bias,
                               logit=logit, flat=x, flat_col0=col0, cont=xc_dev)
         b_.record()
         kt.append((a, b_))
@@ -510,7 +515,7 @@ def main():
         "gpu_launches_per_step": launches_per_step,
         "roofline": {"bound": "hbm", "kernel": ("gather_fm_fwd_stream_kernel<float,4,13,2,true,true> (gather + FM terms + Flatten, "
                                                 f"one launch); rows of the {world - 1} other shards come over NVLink"
-                                                if world > 1 and args.shard != "a2a" else
+                                                if world > 1 and args.shard == "peer-pull" else
                                                 "gather_fm_fwd_tile_kernel<float,4> (gather + FM terms + Flatten, one launch)"),
                      "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                      "traffic": traffic, "traffic_source": traffic_src, "peak_source": peak_src, "kernel_ms": k_ms,

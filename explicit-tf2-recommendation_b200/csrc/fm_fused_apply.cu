@@ -39,6 +39,7 @@ struct FusedParams {
   const int* slot_of_u; int cap; float* grads_mb[16];
   int* counters; FusedLong* long_runs; int2* items; float* partials; int max_long, max_items;
   const char* shard_base[16]; int world;     // peer-sharded table (export mode only): ids are global
+  int sharded;                               // 1: deferred export (the owner finishes dv = P - v * sum_g), also at world 1
 };
 
 __device__ __forceinline__ void bag_to_bf(const FusedParams& p, int bag, int& b, int& f) {
@@ -121,7 +122,7 @@ struct RowState { float4 var, m, v; };
 // overlaps the loop instead of following it
 __device__ __forceinline__ RowState fused_load_row(const FusedParams& p, long long row, int gl) {
   RowState st;
-  if (p.world > 1) {
+  if (p.sharded) {
     // peer-sharded table (export only): DEFERRED form -- the row is not read here at all (it may live
     // in another GPU's HBM); the exported row is [P, sum_g] and the owner finishes dv = P - v * sum_g
     st.var = st.m = st.v = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -324,10 +325,11 @@ static int fused_impl(etr_ctx* ctx, const etr_table* table, float* d_m, float* d
     ETR_CHECK_ARG(!apply, "a peer-sharded table is updated by its owner (push the exported rows, apply there)");
     const EtrShardSet& ss = ctx->shard_sets[table->reserved - 1];
     p.world = ss.world;
+    p.sharded = 1;
     for (int g = 0; g < ss.world; ++g) p.shard_base[g] = ss.base[g];
   }
   if (d_slot_of_u) {
-    ETR_CHECK_ARG(h_grads_mb && cap > 0 && p.world > 1 && !apply, "mailbox export needs a peer-sharded table, apply == 0");
+    ETR_CHECK_ARG(h_grads_mb && cap > 0 && p.sharded && !apply, "mailbox export needs a peer-sharded table, apply == 0");
     for (int g = 0; g < p.world; ++g) { ETR_CHECK_ARG(h_grads_mb[g] != nullptr, "NULL mailbox pointer"); p.grads_mb[g] = h_grads_mb[g]; }
   }
   p.max_long = (int)(n_slots / kFusedShortRun + 1);
