@@ -36,10 +36,18 @@ SEED = 20261          # 20260 + config index
 NCU_K1_DRAM_BYTES = 117.0e6   # dram read 105.6 MB + write 11.4 MB per launch (profiles/r01_prof_gather_fwd.md)
 
 
-def make_batches(n_batches: int, B: int, dist: str, seed: int = SEED):
+def c5_cards(total: int = 100_000_000):
+    """BASELINE configs[4]: 26 fields, V = 1e8, cardinalities proportional to the Criteo list."""
+    base = np.asarray(CRITEO_CARDS, dtype=np.float64)
+    cards = np.maximum(np.floor(base * total / base.sum()), 1).astype(np.int64)
+    cards[int(np.argmax(cards))] += total - int(cards.sum())
+    return [int(c) for c in cards]
+
+
+def make_batches(n_batches: int, B: int, dist: str, seed: int = SEED, cards=None):
     """SURVEY 8d id space: field f owns [offset_f, offset_f + card_f)."""
     rng = np.random.Generator(np.random.PCG64(seed))
-    cards = np.asarray(CRITEO_CARDS, dtype=np.int64)
+    cards = np.asarray(CRITEO_CARDS if cards is None else cards, dtype=np.int64)
     offs = np.concatenate([[0], np.cumsum(cards)[:-1]])
     out = []
     for _ in range(n_batches):
@@ -169,9 +177,13 @@ def run_reference(args):
 
 
 def workload_config(args, B, graph):
-    return {"workload": "c2: DeepFM train step (fwd+bwd+Adam), Criteo shape: 13 dense + 26 sparse, one shared "
-                        "33 762 577-row table, k=16, MLP [429->32->8->1]",
-            "global_batch": B * max(args.gpus, 1), "per_gpu_batch": B, "table_rows": int(sum(CRITEO_CARDS)),
+    c5 = getattr(args, "config", "c2") == "c5"
+    return {"workload": ("c5: DeepFM train step (fwd+bwd+Adam), 13 dense + 26 sparse, one shared 100 000 000-row table "
+                         "(Criteo cardinalities rescaled) row-sharded over the ranks, k=16, MLP [429->32->8->1]" if c5 else
+                         "c2: DeepFM train step (fwd+bwd+Adam), Criteo shape: 13 dense + 26 sparse, one shared "
+                         "33 762 577-row table, k=16, MLP [429->32->8->1]"),
+            "global_batch": B * max(args.gpus, 1), "per_gpu_batch": B,
+            "table_rows": 100_000_000 if c5 else int(sum(CRITEO_CARDS)),
             "embedding_dims": K_EMB, "table_dtype": "f32",
             "mlp": ("layer 1 on tcgen05 (bf16 operands, fp32 accumulate), tail layers fp32" if getattr(args, "mlp", "bf16") == "bf16"
                     else "fp32 SIMT"), "id_distribution": args.dist,
@@ -297,8 +309,9 @@ def main():
     ap.add_argument("--shard", default="peer", choices=["peer", "peer-pull", "a2a"],
                     help="N > 1: 'peer' = CUDA-IPC peer memory, de-duplicated request/serve row exchange; 'peer-pull' = "
                          "rows pulled by the gather kernel over NVLink; 'a2a' = NCCL all-to-all exchange")
-    ap.add_argument("--config", default="c2", choices=["c2", "c3"],
-                    help="c2 = DeepFM (the headline, BASELINE configs[1]); c3 = DCN-matrix bf16 tensor-core cross")
+    ap.add_argument("--config", default="c2", choices=["c2", "c3", "c5"],
+                    help="c2 = DeepFM (the headline, BASELINE configs[1]); c3 = DCN-matrix bf16 tensor-core cross; "
+                         "c5 = DeepFM with a 1e8-row table row-sharded over the ranks, global batch 262 144")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
     if args.impl == "reference":
@@ -319,8 +332,11 @@ def main():
     from etr_b200.runtime import IdsBatch, gather_fm_forward
 
     dev = torch.device("cuda", local_rank)
+    cards = c5_cards() if args.config == "c5" else CRITEO_CARDS
+    if args.config == "c5" and args.batch == BATCH:
+        args.batch = 262144 // world                   # BASELINE configs[4]: global batch 256K
     B = args.batch
-    V = int(sum(CRITEO_CARDS))
+    V = int(sum(cards))
     names = [f"C{i + 1}" for i in range(F)]
     cont = [f"I{i + 1}" for i in range(C_DENSE)]
     # N > 1: the shared table is ROW-SHARDED over the ranks (owner = id mod N) and the batch is
@@ -331,7 +347,7 @@ def main():
                                  shard=(args.shard if world > 1 else None))
     rt = layer.rt
     n_batches = 6
-    host = make_batches(n_batches, B, args.dist, seed=SEED + 17 * rank)
+    host = make_batches(n_batches, B, args.dist, seed=SEED + 17 * rank, cards=cards)
     # host side of the e2e path: the reference's dict of per-feature columns, living in pinned memory as the
     # columns of one column-major block per dtype (what a data loader's pinned staging arena looks like); the
     # Trainer recognises back-to-back columns and moves each block with one async copy
@@ -480,7 +496,7 @@ def main():
     # DRAM bytes of one launch of this kernel from the committed ncu --set full capture of this very
     # command (dram__bytes_read.sum + dram__bytes_write.sum); only valid for the default workload
     traffic, traffic_src = None, None
-    if world == 1 and args.dist == "zipf" and args.mlp == "bf16" and B == BATCH:
+    if world == 1 and args.dist == "zipf" and args.mlp == "bf16" and B == BATCH and args.config == "c2":
         traffic = NCU_K1_DRAM_BYTES
         traffic_src = ("profiles/r01_prof_gather_fwd.md (ncu --set full, per launch): below the algorithmic bytes because "
                        "the Zipf head and the 16 small fields are L2 hits and the bf16 operand is still in L2 when the "

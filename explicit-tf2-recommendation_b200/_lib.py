@@ -97,11 +97,9 @@ PROTOTYPES = {
     "etr_shard_set_create": (C.c_int, [_vp, C.POINTER(_vp), _i32, _i32, _i64, C.POINTER(_i32)]),
     "etr_shard_push": (C.c_int, [_vp, _vp, _vp, _i64, _vp, _i32, _i32, _i32, C.POINTER(_vp), C.POINTER(_vp),
                                  C.POINTER(_vp), _vp, _vp]),
-    "etr_shard_mailbox_pad": (C.c_int, [_vp, _vp, _vp, _i32, _i32, _vp]),
     "etr_shard_request": (C.c_int, [_vp, _vp, _vp, _i64, _i32, _i32, C.POINTER(_vp), C.POINTER(_vp), _vp, _vp, _vp]),
     "etr_shard_serve": (C.c_int, [_vp, _T, _vp, _vp, _i32, _i32, C.POINTER(_vp), _i32, _vp]),
     "etr_shard_vid_map": (C.c_int, [_vp, _vp, _vp, _vp, _i64, _vp, _vp, _vp]),
-    "etr_shard_push_slots": (C.c_int, [_vp, _vp, _vp, _i64, _vp, _i32, _i32, _i32, C.POINTER(_vp), _vp]),
     "etr_shard_mailbox_accumulate": (C.c_int, [_vp, _vp, _vp, _vp, _i32, _i32, _i32, _vp, _vp, _vp, _vp, _i32, _vp]),
     "etr_shard_touched_adam": (C.c_int, [_vp, _T, _vp, _vp, _vp, _i32, _vp, _vp, _i32, _i32, _vp, _f32, _f32, _f32, _vp]),
     "etr_peer_barrier": (C.c_int, [_vp, C.POINTER(_vp), _vp, _vp, _i32, _i32, _vp]),

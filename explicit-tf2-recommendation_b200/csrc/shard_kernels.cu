@@ -122,15 +122,6 @@ __global__ void shard_push_counts_kernel(const PushParams p) {
     p.local_cnt[g] = 0;                                // ready for the next step
   }
 }
-// owner side: slots beyond each source's count become pads (id -1)
-__global__ void __launch_bounds__(256) shard_mailbox_pad_kernel(long long* ids, const int* counts, int world, int cap) {
-  const long long total = (long long)world * cap;
-  for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (long long)gridDim.x * blockDim.x) {
-    const int r = (int)(t / cap), s = (int)(t % cap);
-    if (s >= counts[r]) ids[t] = -1;
-  }
-}
-
 // ---- de-duplicated row exchange (peer form, forward): request -> serve -> virtual ids
 // request: every unique id of this rank's batch (sorted plan) is routed to its owner's request mailbox
 // (local row numbers; slots reserved per CTA) and remembers its (owner, slot); serve: the owner copies the
@@ -237,28 +228,6 @@ __global__ void __launch_bounds__(256) shard_vid_map_kernel(const int* sorted_ba
       while (pos >= next) { ++lo; next = seg_start[lo + 1]; so = slot_of_u[lo]; }
       vid[sorted_bag[pos]] = so;
     }
-  }
-}
-
-// gradient rows travel back through the SAME slots (the owner kept the request ids): no ids, no atomics
-struct PushSlotParams {
-  const float* unique_grad; const int* n_unique; const int* slot_of_u;
-  int cap, ld;
-  float* grads_mb[16];                       // owner g: this source's gradient region [cap][ld]
-};
-template <int LPR>
-__global__ void __launch_bounds__(256) shard_push_slots_kernel(const PushSlotParams p) {
-  constexpr int GPW = 32 / LPR;
-  const int lane = threadIdx.x & 31;
-  const int gl = lane % LPR, g = lane / LPR;
-  const int nchunks = p.ld / 4;
-  const int n = *p.n_unique;
-  for (long long u = ((long long)blockIdx.x * 8 + (threadIdx.x >> 5)) * GPW + g; u < n; u += (long long)gridDim.x * 8 * GPW) {
-    const int so = p.slot_of_u[u];
-    const int owner = so / p.cap, slot = so - owner * p.cap;
-    for (int c = gl; c < nchunks; c += LPR)
-      *reinterpret_cast<float4*>(p.grads_mb[owner] + (long long)slot * p.ld + c * 4) =
-          *reinterpret_cast<const float4*>(p.unique_grad + u * p.ld + c * 4);
   }
 }
 
@@ -509,15 +478,6 @@ int etr_shard_push(etr_ctx* ctx, const int64_t* d_unique_ids, const int32_t* d_n
   return ETR_OK;
 }
 
-int etr_shard_mailbox_pad(etr_ctx* ctx, int64_t* d_ids, const int32_t* d_counts, int32_t world, int32_t cap,
-                          void* stream) {
-  ETR_CHECK_ARG(ctx && d_ids && d_counts && world >= 1 && cap > 0, "bad argument");
-  shard_mailbox_pad_kernel<<<grid_for((long long)world * cap, 256, ctx->sm_count, 8), 256, 0, (cudaStream_t)stream>>>(
-      (long long*)d_ids, d_counts, world, cap);
-  ETR_LAUNCH_CHECK(ctx);
-  return ETR_OK;
-}
-
 int etr_shard_request(etr_ctx* ctx, const int64_t* d_unique_ids, const int32_t* d_n_unique, int64_t max_unique,
                       int32_t world, int32_t cap, int64_t* const* h_req_mb, int32_t* const* h_counts_mb,
                       int32_t* d_local_cnt, int32_t* d_slot_of_u, void* stream) {
@@ -570,32 +530,6 @@ int etr_shard_vid_map(etr_ctx* ctx, const int32_t* d_sorted_bag, const int32_t* 
   if (n_slots <= 0) return ETR_OK;
   shard_vid_map_kernel<<<grid_for(n_slots, 256 * 8, ctx->sm_count, 8), 256, 0, (cudaStream_t)stream>>>(
       d_sorted_bag, d_seg_start, d_n_unique, d_slot_of_u, (long long*)d_vid);
-  ETR_LAUNCH_CHECK(ctx);
-  return ETR_OK;
-}
-
-int etr_shard_push_slots(etr_ctx* ctx, const float* d_unique_grad, const int32_t* d_n_unique, int64_t max_unique,
-                         const int32_t* d_slot_of_u, int32_t world, int32_t cap, int32_t ld, float* const* h_grads_mb,
-                         void* stream) {
-  ETR_CHECK_ARG(ctx && d_unique_grad && d_n_unique && d_slot_of_u && h_grads_mb, "NULL argument");
-  ETR_CHECK_ARG(world >= 1 && world <= 16 && cap > 0 && ld % 4 == 0 && ld / 4 <= 32, "bad world / cap / ld");
-  if (max_unique <= 0) return ETR_OK;
-  PushSlotParams p;
-  memset(&p, 0, sizeof(p));
-  p.unique_grad = d_unique_grad; p.n_unique = d_n_unique; p.slot_of_u = d_slot_of_u; p.cap = cap; p.ld = ld;
-  for (int g = 0; g < world; ++g) p.grads_mb[g] = h_grads_mb[g];
-  int lpr = 1;
-  while (lpr < ld / 4) lpr <<= 1;
-  const int grid = grid_for(max_unique, 8 * (32 / lpr), ctx->sm_count, 8);
-  cudaStream_t s = (cudaStream_t)stream;
-  switch (lpr) {
-    case 1: shard_push_slots_kernel<1><<<grid, 256, 0, s>>>(p); break;
-    case 2: shard_push_slots_kernel<2><<<grid, 256, 0, s>>>(p); break;
-    case 4: shard_push_slots_kernel<4><<<grid, 256, 0, s>>>(p); break;
-    case 8: shard_push_slots_kernel<8><<<grid, 256, 0, s>>>(p); break;
-    case 16: shard_push_slots_kernel<16><<<grid, 256, 0, s>>>(p); break;
-    default: shard_push_slots_kernel<32><<<grid, 256, 0, s>>>(p); break;
-  }
   ETR_LAUNCH_CHECK(ctx);
   return ETR_OK;
 }

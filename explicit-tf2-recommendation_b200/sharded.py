@@ -374,12 +374,6 @@ class PeerShardedTable:
         vt = VirtualTable(rt, mb["resp_t"], self.width)
         return vt, IdsBatch(rt, vid, B, F, 1, F, 1, 1), slot_of_u
 
-    def push_slots(self, unique_grad: torch.Tensor, n_unique: torch.Tensor, max_unique: int, slot_of_u: torch.Tensor):
-        rt, mb = self.rt, self._mb
-        check(rt.lib.etr_shard_push_slots(rt.ctx, unique_grad.data_ptr(), n_unique.data_ptr(), max_unique,
-                                          slot_of_u.data_ptr(), self.world, self.cap, unique_grad.shape[1],
-                                          mb["grads_ptrs"], rt.stream))
-
     def apply_mailbox(self, d_lr_t: torch.Tensor, b1: float, b2: float, eps: float, mode: int):
         """owner side, no sort: the G source regions are added into the dense accumulator in rank order
         (rows are unique within a region: no atomics, deterministic), first-touch rows go on a list, and

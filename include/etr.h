@@ -371,9 +371,8 @@ int etr_shard_partition(etr_ctx* ctx, const int64_t* d_ids, int64_t n, int32_t w
  * all-to-all and nothing is read back to the host.
  * Backward: etr_shard_push writes this rank's deduplicated gradient rows (and local row ids)
  * into its own region of each owner's mailbox (plain peer stores; slots from local counters),
- * then publishes the counts.  After a cross-rank barrier (the dense-gradient all-reduce), the
- * owner pads the unused slots (etr_shard_mailbox_pad, id -1) and runs the ordinary
- * etr_sparse_plan / segment-reduce / Adam over its mailbox.                                   */
+ * then publishes the counts.  After etr_peer_barrier the owner applies its mailbox with
+ * etr_shard_mailbox_accumulate + etr_shard_touched_adam.                                      */
 int etr_peer_alloc(etr_ctx* ctx, int64_t bytes, void** d_ptr, void* handle64);
 int etr_peer_open(etr_ctx* ctx, const void* handle64, void** d_ptr);
 int etr_peer_close(etr_ctx* ctx, void* d_ptr);
@@ -384,11 +383,9 @@ int etr_shard_push(etr_ctx* ctx, const int64_t* d_unique_ids, const int32_t* d_n
                    const float* d_unique_grad, int32_t ld, int32_t world, int32_t cap,
                    int64_t* const* h_ids_mb, float* const* h_grads_mb, int32_t* const* h_counts_mb,
                    int32_t* d_local_cnt, void* stream);
-int etr_shard_mailbox_pad(etr_ctx* ctx, int64_t* d_ids, const int32_t* d_counts, int32_t world, int32_t cap,
-                          void* stream);
 /* etr_fm_fused_backward_apply(apply = 0) on a peer-sharded table, writing every exported (deferred)
  * gradient row straight into its owner's mailbox slot d_slot_of_u[u] = owner*cap + slot (peer
- * stores over NVLink) instead of a local buffer + etr_shard_push_slots.                          */
+ * stores over NVLink) instead of a local buffer and a separate push kernel.                    */
 int etr_fm_fused_backward_push(etr_ctx* ctx, const etr_table* table, int32_t k, int32_t fields, int64_t batch,
                                const int32_t* d_sorted_bag, const int32_t* d_seg_start, const int64_t* d_unique_ids,
                                const int32_t* d_n_unique, int64_t n_slots, const float* d_dlogit, const float* d_sumv,
@@ -402,8 +399,8 @@ int etr_fm_fused_backward_push(etr_ctx* ctx, const etr_table* table, int32_t k, 
  * into each requester's response buffer [world][cap][ld] at the same (owner, slot): NVLink carries
  * sequential full-line stores instead of request-bound 80-byte remote loads.  After a second
  * barrier etr_shard_vid_map turns every occurrence into its response-buffer row, so
- * etr_gather_fm_forward runs on the response buffer as its table.  etr_shard_push_slots later
- * returns the gradient rows through the same slots (the owner kept the request ids).          */
+ * etr_gather_fm_forward runs on the response buffer as its table.  etr_fm_fused_backward_push
+ * later returns the gradient rows through the same slots (the owner kept the request ids).    */
 int etr_shard_request(etr_ctx* ctx, const int64_t* d_unique_ids, const int32_t* d_n_unique, int64_t max_unique,
                       int32_t world, int32_t cap, int64_t* const* h_req_mb, int32_t* const* h_counts_mb,
                       int32_t* d_local_cnt, int32_t* d_slot_of_u, void* stream);
@@ -411,9 +408,6 @@ int etr_shard_serve(etr_ctx* ctx, const etr_table* table, const int64_t* d_req, 
                     int32_t cap, float* const* h_resp, int32_t ld, void* stream);
 int etr_shard_vid_map(etr_ctx* ctx, const int32_t* d_sorted_bag, const int32_t* d_seg_start, const int32_t* d_n_unique,
                       int64_t n_slots, const int32_t* d_slot_of_u, int64_t* d_vid, void* stream);
-int etr_shard_push_slots(etr_ctx* ctx, const float* d_unique_grad, const int32_t* d_n_unique, int64_t max_unique,
-                         const int32_t* d_slot_of_u, int32_t world, int32_t cap, int32_t ld, float* const* h_grads_mb,
-                         void* stream);
 /* Owner side of the peer-sharded apply WITHOUT a sort (replaces Unique + UnsortedSegmentSum +
  * Adam._resource_apply_sparse of 2.FM/ModelManager.py:178 on the shard): the G source regions of
  * the mailbox -- rows unique within a region -- are added into a dense accumulator

@@ -111,3 +111,35 @@ def test_c4_ffm_bags_full_size_properties():
     assert torch.allclose(ffm(Xr)["output"], out_ffm, rtol=1e-5, atol=1e-7)
     # batch-split invariance (bit-exact)
     assert torch.equal(torch.cat([ffm(Xd[:4096])["output"], ffm(Xd[4096:])["output"]]), out_ffm)
+
+
+def test_c2_fused_train_step_equals_layerwise_step():
+    """c2 at full size, bf16 tower: ONE train step through the fused path (K7c tail + loss, K7b layer-1 backward)
+    and one through the layer-by-layer path start from identical weights and must agree to fp32 rounding:
+    loss, every dense variable, and the touched table rows."""
+    from etr_b200 import CustomLayers as L
+    V, B, F, C_ = int(sum(CRITEO_CARDS)), 65536, 26, 13
+    rng = np.random.default_rng(20262)
+    cards = np.asarray(CRITEO_CARDS)
+    offs = np.concatenate([[0], np.cumsum(cards)[:-1]])
+    X = torch.tensor((offs[None, :] + np.floor(cards[None, :] * rng.random((B, F)) ** 3)).astype(np.int64)).cuda()
+    Xc = torch.tensor(rng.normal(size=(B, C_)).astype(np.float32)).cuda()
+    y = torch.tensor((rng.random(B) < 0.25).astype(np.float32)).cuda()
+    names, cont = [f"C{i}" for i in range(F)], [f"I{i}" for i in range(C_)]
+    d = {n: X[:, i].contiguous() for i, n in enumerate(names)}
+    d.update({n: Xc[:, i].contiguous() for i, n in enumerate(cont)})
+    res = []
+    for fused in (True, False):
+        lay = L.DeepFMRankingLayer(names, V, 16, continuous_features=cont, seed=1, check_ids=False, mlp_precision="bf16",
+                                   fused_tail=fused)
+        tr = L.Trainer(lay, lr=1e-3)
+        loss = float(tr.train_step(d, y).item())
+        torch.cuda.synchronize()
+        rows = lay.table.data[X[:2048].reshape(-1)].clone()
+        res.append((loss, lay.params.value.clone(), rows))
+        del lay, tr
+        torch.cuda.empty_cache()
+    (l1, p1, r1), (l0, p0, r0) = res
+    assert abs(l1 - l0) <= 1e-5 * abs(l0)
+    assert (p1 - p0).abs().max().item() < 2e-6
+    assert (r1 - r0).abs().max().item() < 2e-6
