@@ -117,46 +117,72 @@ __device__ __forceinline__ void adam_update4(float4& var, float4& m, float4& v, 
 }
 
 // finish one row: grad = P - v_r * sum_g (embedding chunk gl), w chunk by lane 0; Adam and/or export
-struct RowState { float4 var, m, v; };
+struct RowState { float4 var, m, v; float wx; };
 // issue the row's (var, m, v) loads; called BEFORE the occurrence loop so that their DRAM latency
-// overlaps the loop instead of following it
+// overlaps the loop instead of following it.  LPR >= 4: the w column's state is prefetched here too -- lane 1
+// of the group reads w, lane 2 its m, lane 3 its v (one scalar each) -- instead of three dependent 16-byte
+// loads by lane 0 after the loop (a second exposed DRAM round trip per row in the first version).
+template <int LPR>
 __device__ __forceinline__ RowState fused_load_row(const FusedParams& p, long long row, int gl) {
   RowState st;
-  if (p.sharded) {
-    // peer-sharded table (export only): DEFERRED form -- the row is not read here at all (it may live
-    // in another GPU's HBM); the exported row is [P, sum_g] and the owner finishes dv = P - v * sum_g
-    st.var = st.m = st.v = make_float4(0.f, 0.f, 0.f, 0.f);
-    return st;
-  }
+  st.var = st.m = st.v = make_float4(0.f, 0.f, 0.f, 0.f);
+  st.wx = 0.f;
+  // peer-sharded table (export only): DEFERRED form -- the row is not read here at all (it may live
+  // in another GPU's HBM); the exported row is [P, sum_g] and the owner finishes dv = P - v * sum_g
+  if (p.sharded) return st;
   st.var = *reinterpret_cast<const float4*>(p.table + row * p.stride + gl * 4);
-  st.m = st.v = make_float4(0.f, 0.f, 0.f, 0.f);
   if (p.apply) {
     st.m = *reinterpret_cast<const float4*>(p.m + row * p.stride + gl * 4);
     st.v = *reinterpret_cast<const float4*>(p.v + row * p.stride + gl * 4);
+    if (LPR >= 4 && gl >= 1 && gl <= 3) {
+      const float* src = gl == 1 ? p.table : (gl == 2 ? p.m : p.v);
+      st.wx = src[row * p.stride + p.k];
+    }
   }
   return st;
 }
 
-__device__ __forceinline__ void fused_finish_row(const FusedParams& p, long long u, long long row, int gl, RowState st,
-                                                 float4 P, float sum_g, float lr_t) {
+template <int LPR>
+__device__ __forceinline__ void fused_finish_row(const FusedParams& p, long long u, long long row, int gl, int g,
+                                                 RowState st, float4 P, float sum_g, float lr_t) {
   float* prow = p.table + row * p.stride;
   float4 var = st.var;
-  const float4 g = make_float4(P.x - var.x * sum_g, P.y - var.y * sum_g, P.z - var.z * sum_g, P.w - var.w * sum_g);
+  const float4 gr = make_float4(P.x - var.x * sum_g, P.y - var.y * sum_g, P.z - var.z * sum_g, P.w - var.w * sum_g);
   float* gdst = p.unique_grad ? p.unique_grad + u * p.stride : nullptr;
   if (p.slot_of_u) {
     const int so = p.slot_of_u[u];
     const int owner = so / p.cap;
     gdst = p.grads_mb[owner] + (long long)(so - owner * p.cap) * p.stride;
   }
-  if (gdst) *reinterpret_cast<float4*>(gdst + gl * 4) = g;
+  if (gdst) *reinterpret_cast<float4*>(gdst + gl * 4) = gr;
   if (p.apply) {
     float4 m = st.m, v = st.v;
-    adam_update4(var, m, v, g, lr_t, p.b1, p.b2, p.eps);
+    adam_update4(var, m, v, gr, lr_t, p.b1, p.b2, p.eps);
     *reinterpret_cast<float4*>(prow + gl * 4) = var;
     *reinterpret_cast<float4*>(p.m + row * p.stride + gl * 4) = m;
     *reinterpret_cast<float4*>(p.v + row * p.stride + gl * 4) = v;
   }
-  if (gl == 0) {
+  if (LPR >= 4) {
+    // the w column: state prefetched by lanes 1..3, one scalar Adam by lane 0 (the zero padding columns behind
+    // w have zero gradient and zero moments: Adam leaves them untouched, so skipping them is exact)
+    const unsigned gmask = (LPR == 32) ? 0xffffffffu : (((1u << LPR) - 1u) << (g * LPR));
+    float w = __shfl_sync(gmask, st.wx, g * LPR + 1);
+    float wm = __shfl_sync(gmask, st.wx, g * LPR + 2);
+    float wv = __shfl_sync(gmask, st.wx, g * LPR + 3);
+    if (gl == 0) {
+      if (gdst)
+        for (int c = p.k; c < p.stride; c += 4)
+          *reinterpret_cast<float4*>(gdst + c) = make_float4(c == p.k ? sum_g : 0.f, 0.f, 0.f, 0.f);
+      if (p.apply) {
+        wm = p.b1 * wm + (1.0f - p.b1) * sum_g;
+        wv = p.b2 * wv + (1.0f - p.b2) * sum_g * sum_g;
+        w = w - lr_t * wm / (sqrtf(wv) + p.eps);
+        prow[p.k] = w;
+        p.m[row * p.stride + p.k] = wm;
+        p.v[row * p.stride + p.k] = wv;
+      }
+    }
+  } else if (gl == 0) {
     // chunks behind the embedding: [w, 0, 0, 0] (+ zero padding chunks)
     for (int c = p.k; c < p.stride; c += 4) {
       const float4 gw = make_float4(c == p.k ? sum_g : 0.f, 0.f, 0.f, 0.f);
@@ -198,11 +224,11 @@ __global__ void __launch_bounds__(256, 4) fm_fused_short_kernel(const FusedParam
       continue;
     }
     const long long row = p.unique_ids[u];
-    const RowState st = fused_load_row(p, row, gl);
+    const RowState st = fused_load_row<LPR>(p, row, gl);
     float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
     float sum_g = 0.f;
     fused_accumulate<2>(p, s0, s1, gl, acc, sum_g);
-    fused_finish_row(p, u, row, gl, st, acc, sum_g, lr_t);
+    fused_finish_row<LPR>(p, u, row, gl, g, st, acc, sum_g, lr_t);
   }
 }
 
@@ -260,7 +286,7 @@ __global__ void __launch_bounds__(256) fm_fused_combine_kernel(const FusedParams
   for (long long r = group_global; r < n_long; r += ngroups) {
     const FusedLong lr = p.long_runs[r];
     const long long row = p.unique_ids[lr.u];
-    const RowState st = fused_load_row(p, row, gl);
+    const RowState st = fused_load_row<LPR>(p, row, gl);
     float4 t = make_float4(0.f, 0.f, 0.f, 0.f);
     float ts = 0.f;
     for (int c = 0; c < lr.nchunks; ++c) {
@@ -269,7 +295,7 @@ __global__ void __launch_bounds__(256) fm_fused_combine_kernel(const FusedParams
       t.x += x.x; t.y += x.y; t.z += x.z; t.w += x.w;
       ts += src[p.k];
     }
-    fused_finish_row(p, lr.u, row, gl, st, t, ts, lr_t);
+    fused_finish_row<LPR>(p, lr.u, row, gl, g, st, t, ts, lr_t);
   }
 }
 
