@@ -502,6 +502,36 @@ def main():
                        "the Zipf head and the 16 small fields are L2 hits and the bf16 operand is still in L2 when the "
                        "kernel ends")
 
+    # ---- second roofline: the largest kernel group of the step by time, the fused FM backward + segment
+    # reduction + Adam, timed alone (plan precomputed, L2 flushed); algorithmic bytes = 408 B per unique row
+    apply_roof = None
+    if world == 1:
+        from etr_b200.runtime import FusedFMGrad, SparsePlan
+        plans = [SparsePlan(rt, id_batches[i], V) for i in range(4)]
+        dl_ = torch.randn(B, device=dev) * 1e-7
+        sumv_ = torch.randn(B, K_EMB, device=dev) * 0.1
+        dx_ = (torch.randn(B, col0 + F * K_EMB, device=dev) * 1e-7).to(torch.bfloat16)
+        lr_ = torch.tensor([1e-3], device=dev)
+        at = []
+        for i in range(10):
+            g_ = FusedFMGrad(layer.table, id_batches[i % 4], K_EMB, dl_, sumv_, dx_, col0, plan=plans[i % 4])
+            flush.zero_()
+            a, b_ = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            g_.apply(lr_, 0.9, 0.999, 1e-7)
+            b_.record()
+            at.append((a, b_))
+        torch.cuda.synchronize(dev)
+        a_ms = statistics.median(a.elapsed_time(b_) for a, b_ in at[2:])
+        n_u = statistics.mean(p_.n_unique for p_ in plans)
+        a_bytes = n_u * 6 * (K_EMB + 1) * 4
+        apply_roof = {"bound": "hbm", "kernel": "fm_fused_short/chunk/combine_kernel<4> (FM backward + sorted-run reduction + "
+                      "row-wise Adam, 3 launches)", "achieved": a_bytes / (a_ms * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
+                      "frac": a_bytes / (a_ms * 1e-3) / 1e9 / peak, "kernel_ms": a_ms, "unique_rows_per_launch": n_u,
+                      "algorithmic_bytes_per_launch": a_bytes,
+                      "note": "408 B per unique row (3 reads + 3 writes of a 68-byte row, SURVEY 8d); request-bound, see "
+                              "profiles/r01_mb_apply.md"}
+
     # ---- max over ranks
     t = torch.tensor([total_ms, e2e_ms], device=dev, dtype=torch.float64)
     if world > 1:
@@ -542,6 +572,8 @@ def main():
                              "per event pair"},
         "step_ms_min_median_max": [min(step_ms), statistics.median(step_ms), max(step_ms)],
     }
+    if apply_roof:
+        line["roofline_apply"] = apply_roof
     if cpu:
         line["cpu_baseline"] = cpu
     print(json.dumps(line))
