@@ -917,183 +917,6 @@ __global__ void __launch_bounds__(128, 3) gather_fm_fwd_stream_kernel(const Gath
   if (any_bad) flag_bad_id(p.err, bad_id);
 }
 
-// ================================================================ staged single-hot forward (K1, v4)
-// Same contract as the streaming kernel, but the rows travel global -> shared memory with
-// cp.async (LDGSTS, L1 bypass) instead of through registers:
-//   * one LDGSTS instruction covers RPI = 32/RL whole rows, RL = the power of two >= the chunks of
-//     a row INCLUDING the w chunk, so a row is ONE request inside one line -- measured
-//     (profiles/r01_mb_gather.md): on a DRAM-resident table a random row costs ~30 us per million
-//     whether it is 32, 64 or 128 bytes, and every additional request to it costs the same again;
-//   * no data registers are tied up while the loads fly: a warp keeps a whole tile (GPW samples x F
-//     rows, e.g. 208 rows = 16.6 KB) in flight, ten warps per SM -> ~2 000 rows per SM, which is what
-//     ~34 G random rows/s at 2-3 us loaded latency needs (the register version topped out at 624);
-//   * the ids of the warp's next tile ride in the same cp.async group, so no row request ever waits
-//     on an id load.
-// Warps are independent: private shared-memory region, cp.async groups and __syncwarp only.
-__device__ __forceinline__ void cp_async16_cg(void* smem_dst, const void* gsrc) {
-  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((unsigned)__cvta_generic_to_shared(smem_dst)), "l"(gsrc)
-               : "memory");
-}
-__device__ __forceinline__ void cp_async16_ca(void* smem_dst, const void* gsrc) {
-  asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"((unsigned)__cvta_generic_to_shared(smem_dst)), "l"(gsrc)
-               : "memory");
-}
-constexpr int pow2_ceil(int x) { int r = 1; while (r < x) r <<= 1; return r; }
-
-template <typename Elem, int KCH, bool HAS_W, int FLAT, bool PEER>
-__global__ void __launch_bounds__(256) gather_fm_fwd_staged_kernel(const GatherParams p, const int wshift, const int ss,
-                                                                   const int warp_smem) {
-  constexpr int VEC = Chunk<Elem>::kElems;
-  constexpr int K = KCH * VEC;                      // embedding columns
-  constexpr int CL = KCH;                           // consumer lanes per sample
-  constexpr int GPW = 32 / CL;                      // samples per warp tile
-  constexpr int NCH = KCH + (HAS_W ? 1 : 0);        // chunks fetched per row
-  constexpr int RL = pow2_ceil(NCH);                // issuing lanes per row
-  constexpr int RPI = 32 / RL;                      // rows per LDGSTS instruction
-  constexpr int RB = NCH * 16;                      // bytes of a row in shared memory
-  constexpr int OSZ = FLAT == 2 ? 2 : 4;
-  extern __shared__ __align__(128) char smem_raw[];
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  char* rows_s = smem_raw + (size_t)warp * warp_smem;
-  const int nq = GPW * p.F;                         // rows of a tile
-  long long* ids_s = reinterpret_cast<long long*>(rows_s + GPW * ss);    // [2][nq]
-  const long long nwarps = (long long)gridDim.x * (blockDim.x >> 5);
-  long long tile = (long long)blockIdx.x * (blockDim.x >> 5) + warp;
-  const long long ntiles = (p.B + GPW - 1) / GPW;
-  const bool want_fm = (p.logit != nullptr) || (p.prob != nullptr) || (p.sumv != nullptr);
-  const unsigned row_bytes = (unsigned)p.row_bytes;
-  const int gl = lane % CL, g = lane / CL;
-  long long bad_id = 0;
-  bool any_bad = false;
-
-  auto stage_ids = [&](long long t, long long* dst) {
-    const long long b0 = t * GPW;
-    for (int e = lane; e < nq; e += 32) {
-      int s, f;
-      if (p.sb == 1) { s = e % GPW; f = e / GPW; } else { f = e % p.F; s = e / p.F; }
-      if (b0 + s < p.B) cp_async8(dst + s * p.F + f, p.ids + (b0 + s) * p.sb + (long long)f * p.sf);
-      else dst[s * p.F + f] = 0;                     // a sample past the batch reads row 0 (never stored)
-    }
-  };
-  auto issue_rows = [&](const long long* idsrc) {
-    const int c = lane % RL, slot = lane / RL;
-    if (c >= NCH) return;
-    int f = slot, s = 0;
-    while (f >= p.F) { f -= p.F; ++s; }
-    for (int q = slot; q < nq; q += RPI) {
-      long long id = idsrc[q];
-      const bool bad = (unsigned long long)id >= (unsigned long long)p.rows;
-      bad_id = bad ? id : bad_id;
-      any_bad = any_bad || bad;
-      const unsigned rid = bad ? 0u : (unsigned)id;
-      const char* src;
-      if constexpr (PEER) {
-        src = p.shard_base[rid & (unsigned)(p.world - 1)] + (unsigned long long)(rid >> wshift) * row_bytes + c * 16;
-        cp_async16_ca(rows_s + s * ss + f * RB + c * 16, src);     // peer rows skip the local L2: let L1 keep hot ones
-      } else {
-        src = p.table + (unsigned long long)rid * row_bytes + c * 16;
-        cp_async16_cg(rows_s + s * ss + f * RB + c * 16, src);
-      }
-      f += RPI;
-      while (f >= p.F) { f -= p.F; ++s; }
-    }
-  };
-
-  if (tile < ntiles) stage_ids(tile, ids_s);
-  cp_async_commit();
-  cp_async_wait_all();
-  __syncwarp();
-  int ib = 0;
-  for (; tile < ntiles; tile += nwarps) {
-    issue_rows(ids_s + ib * nq);
-    if (tile + nwarps < ntiles) stage_ids(tile + nwarps, ids_s + (ib ^ 1) * nq);
-    cp_async_commit();
-
-    const long long b = tile * GPW + g;
-    const bool active = b < p.B;
-    if (FLAT && p.fill_front && active) {             // dense columns while the rows are in flight
-      const int z = p.flat_col0 - p.cont_n;
-#pragma unroll 1
-      for (int j = gl; j < p.flat_col0; j += CL) {
-        const float v = (j < z) ? 0.f : __ldg(p.cont + b * p.cont_sb + (long long)(j - z) * p.cont_sc);
-        if (FLAT == 2) reinterpret_cast<__nv_bfloat16*>(p.flat)[b * p.flat_ld + j] = __float2bfloat16_rn(v);
-        else reinterpret_cast<float*>(p.flat)[b * p.flat_ld + j] = v;
-      }
-    }
-    char* fo = nullptr;                               // this lane's chunk of field 0 in the flat operand
-    if (FLAT) fo = reinterpret_cast<char*>(p.flat) + (b * p.flat_ld + p.flat_col0 + gl * VEC) * OSZ;
-    float S[VEC], Q[VEC];
-#pragma unroll
-    for (int i = 0; i < VEC; ++i) S[i] = Q[i] = 0.f;
-    float wsum = 0.f;
-
-    cp_async_wait_all();
-    __syncwarp();
-    const char* my = rows_s + g * ss + gl * 16;
-#pragma unroll 2
-    for (int f = 0; f < p.F; ++f) {
-      const float4 r = *reinterpret_cast<const float4*>(my + f * RB);
-      float x[VEC];
-      if constexpr (sizeof(Elem) == 4) {
-        x[0] = r.x; x[1] = r.y; x[2] = r.z; x[3] = r.w;
-      } else {
-        const uint32_t h[4] = {__float_as_uint(r.x), __float_as_uint(r.y), __float_as_uint(r.z), __float_as_uint(r.w)};
-#pragma unroll
-        for (int i = 0; i < 4; ++i) {
-          x[2 * i] = __uint_as_float(h[i] << 16);               // low half  = element 2i
-          x[2 * i + 1] = __uint_as_float(h[i] & 0xffff0000u);   // high half = element 2i+1
-        }
-      }
-      if (want_fm) {
-#pragma unroll
-        for (int i = 0; i < VEC; ++i) {
-          S[i] += x[i];
-          Q[i] += x[i] * x[i];
-        }
-        if (HAS_W && (f % CL) == gl) {                // the w chunk: lane (f mod CL) of the group takes it
-          const char* q = rows_s + g * ss + f * RB + KCH * 16;
-          if constexpr (sizeof(Elem) == 4) wsum += *reinterpret_cast<const float*>(q);
-          else wsum += __bfloat162float(*reinterpret_cast<const __nv_bfloat16*>(q));
-        }
-      }
-      if (FLAT && active) {
-        char* o = fo + (long long)f * (K * OSZ);
-        if constexpr (FLAT == 2 && sizeof(Elem) == 2) {
-          *reinterpret_cast<float4*>(o) = r;                            // bf16 row -> bf16 operand: raw copy
-        } else if constexpr (FLAT == 2) {
-          const __nv_bfloat162 h0 = __floats2bfloat162_rn(x[0], x[1]);
-          const __nv_bfloat162 h1 = __floats2bfloat162_rn(x[2], x[3]);
-          *reinterpret_cast<uint2*>(o) = make_uint2(*reinterpret_cast<const uint32_t*>(&h0),
-                                                    *reinterpret_cast<const uint32_t*>(&h1));
-        } else {
-#pragma unroll
-          for (int i = 0; i < VEC; i += 4) stg_stream16(o + i * 4, make_float4(x[i], x[i + 1], x[i + 2], x[i + 3]));
-        }
-      }
-    }
-    if (want_fm) {
-      float second = 0.f;
-#pragma unroll
-      for (int i = 0; i < VEC; ++i) second += S[i] * S[i] - Q[i];
-      if (p.sumv && active) {
-#pragma unroll
-        for (int i = 0; i < VEC; i += 4)
-          *reinterpret_cast<float4*>(p.sumv + b * K + gl * VEC + i) = make_float4(S[i], S[i + 1], S[i + 2], S[i + 3]);
-      }
-      second = group_sum<CL>(second);
-      const float first = group_sum<CL>(wsum);
-      if (gl == 0 && active) {
-        const float z = ((p.bias ? p.bias[0] : 0.f) + first) + 0.5f * second;
-        if (p.logit) p.logit[b] = z;
-        if (p.prob) p.prob[b] = sigmoidf_exact(z);
-      }
-    }
-    __syncwarp();                                     // every lane is done with the tile before it is overwritten
-    ib ^= 1;
-  }
-  if (any_bad) flag_bad_id(p.err, bad_id);
-}
-
 // ------------------------------------------------------------ K0 assemble
 struct ColPtrs {
   const long long* col[64];
@@ -1171,12 +994,7 @@ static int launch_stream_one(etr_ctx* ctx, const GatherParams& p_in, int wshift,
   const long long ntiles = (p.B + GPW - 1) / GPW;
   long long grid = (ntiles + 3) / 4;
   if (grid > (long long)ctx->sm_count * occ) grid = (long long)ctx->sm_count * occ;
-  if (const char* e = getenv("ETR_STREAM_CPS")) {            // experiments: CTAs per SM
-    const int c = atoi(e);
-    if (c > 0) grid = ctx->sm_count * c;
-  }
-  p.l1_alloc = 1;
-  if (const char* e = getenv("ETR_L1")) p.l1_alloc = atoi(e);
+  p.l1_alloc = 1;                          // measured: no difference on local tables; peer rows want L1
   kern<<<(int)grid, 128, 0, s>>>(p, wshift);
   ETR_LAUNCH_CHECK(ctx);
   return ETR_OK;
@@ -1227,92 +1045,18 @@ static int launch_stream(etr_ctx* ctx, const GatherParams& p, bool bag, cudaStre
   return -1;
 }
 
-template <typename Elem, int KCH, bool HAS_W, int FLAT, bool PEER>
-static int launch_staged_one(etr_ctx* ctx, const GatherParams& p, int wshift, cudaStream_t s) {
-  constexpr int CL = KCH, GPW = 32 / CL, NCH = KCH + (HAS_W ? 1 : 0), RB = NCH * 16;
-  int ss = p.F * RB;                                   // per-sample stride: quarter-warp LDS.128 conflict-free
-  if (CL < 8) while (ss % 128 != (CL * 16) % 128) ss += 16;
-  const int per_warp = (int)((GPW * (size_t)ss + 2 * (size_t)GPW * p.F * 8 + 127) / 128 * 128);
-  const int budget = 110 * 1024;                       // two CTAs per SM
-  if (per_warp > budget) return -1;
-  int wpb = budget / per_warp;
-  if (wpb > 8) wpb = 8;
-  if (const char* e = getenv("ETR_STAGED_WPB")) { const int w = atoi(e); if (w > 0 && w <= 8 && w * per_warp <= 220 * 1024) wpb = w; }
-  const int smem = wpb * per_warp;
-  auto kern = gather_fm_fwd_staged_kernel<Elem, KCH, HAS_W, FLAT, PEER>;
-  static int configured = 0;
-  if (configured < smem) {
-    ETR_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    configured = smem;
-  }
-  const long long ntiles = (p.B + GPW - 1) / GPW;
-  const int cps = smem <= budget ? 2 : 1;
-  long long grid = (ntiles + wpb - 1) / wpb;
-  if (grid > (long long)ctx->sm_count * cps) grid = (long long)ctx->sm_count * cps;
-  kern<<<(int)grid, wpb * 32, smem, s>>>(p, wshift, ss, per_warp);
-  ETR_LAUNCH_CHECK(ctx);
-  return ETR_OK;
-}
-
-// returns -1 when the shape is not one the staged kernel covers
-template <typename Elem>
-static int launch_staged(etr_ctx* ctx, const GatherParams& p, bool bag, cudaStream_t s) {
-  const int emb_bytes = p.k * p.esize;
-  const int kch = emb_bytes / 16;
-  if (bag || p.has_pad || emb_bytes % 16 != 0 || !(kch == 2 || kch == 4 || kch == 8 || kch == 16)) return -1;
-  if (p.rows >= (1ll << 32) || (p.flat && !p.flat_vec)) return -1;
-  if (p.has_w && p.row_bytes < (kch + 1) * 16) return -1;        // the w chunk must exist in the row
-  int wshift = 0;
-  if (p.world > 1) {
-    if ((p.world & (p.world - 1)) || !p.has_w || sizeof(Elem) != 4) return -1;
-    while ((1 << wshift) < p.world) ++wshift;
-  }
-  const int flat = !p.flat ? 0 : (p.flat_bf16 ? 2 : 1);
-#define ETR_STAGED_W(KCH, FL)                                                                          \
-  do {                                                                                                 \
-    if constexpr (sizeof(Elem) == 4) {                                                                 \
-      if (p.world > 1) return launch_staged_one<Elem, KCH, true, FL, true>(ctx, p, wshift, s);         \
-    }                                                                                                  \
-    return launch_staged_one<Elem, KCH, true, FL, false>(ctx, p, wshift, s);                           \
-  } while (0)
-#define ETR_STAGED_NOW(KCH, FL) return launch_staged_one<Elem, KCH, false, FL, false>(ctx, p, wshift, s)
-#define ETR_STAGED_FL(MACRO, KCH)                                                                      \
-  do {                                                                                                 \
-    if (flat == 0) { MACRO(KCH, 0); }                                                                  \
-    else if (flat == 1) { MACRO(KCH, 1); }                                                             \
-    else { MACRO(KCH, 2); }                                                                            \
-  } while (0)
-#define ETR_STAGED_K(MACRO)                                                                            \
-  switch (kch) {                                                                                       \
-    case 2: ETR_STAGED_FL(MACRO, 2); break;                                                            \
-    case 4: ETR_STAGED_FL(MACRO, 4); break;                                                            \
-    case 8: ETR_STAGED_FL(MACRO, 8); break;                                                            \
-    default: ETR_STAGED_FL(MACRO, 16); break;                                                          \
-  }
-  if (p.has_w) { ETR_STAGED_K(ETR_STAGED_W) } else { ETR_STAGED_K(ETR_STAGED_NOW) }
-#undef ETR_STAGED_W
-#undef ETR_STAGED_NOW
-#undef ETR_STAGED_FL
-#undef ETR_STAGED_K
-  return -1;
-}
-
 template <typename Elem, bool BWD>
 static int launch_gather(etr_ctx* ctx, const GatherParams& p_in, bool bag, cudaStream_t s) {
   GatherParams p = p_in;
   if (!BWD) {
-    // Measured on the c2 workload (scripts/mb_k1.py, profiles/r01_mb_gather.md): every variant is bound
-    // by the rows it keeps in flight per SM; with the fused w column the tiled kernel below (24 warps x
-    // 8 loads) wins (52 us vs 65 us streaming, 73 us staged), without it the streaming kernel does.
-    // Peer-sharded tables are served by the streaming kernel.  ETR_GATHER overrides (experiments).
+    // Measured on the c2 workload (scripts/mb_k1.py, profiles/r01_mb_gather.md): every variant is bound by the
+    // rows it keeps in flight per SM; with the fused w column the tiled kernel below (24 warps x 8 loads) wins
+    // (52 us vs 65 us streaming; a cp.async-staged variant reached 73 us and was dropped), without it the
+    // streaming kernel does.  Peer-sharded tables are served by the streaming kernel.  ETR_GATHER=stream|generic
+    // overrides the choice (micro-benchmarks).
     const char* which = getenv("ETR_GATHER");
-    const bool want_staged = which && strcmp(which, "staged") == 0;
     const bool want_stream = which ? strcmp(which, "stream") == 0 : (!p.has_w || p.world > 1);
-    if (want_staged) {
-      const int st = launch_staged<Elem>(ctx, p, bag, s);
-      if (st >= 0) return st;
-    }
-    if (want_stream || want_staged) {
+    if (want_stream) {
       const int st = launch_stream<Elem>(ctx, p, bag, s);
       if (st >= 0) return st;
     }
@@ -1323,7 +1067,6 @@ static int launch_gather(etr_ctx* ctx, const GatherParams& p_in, bool bag, cudaS
     return l;
   };
   p.l1_alloc = 0;
-  if (const char* e = getenv("ETR_L1")) p.l1_alloc = atoi(e);
   // single-hot + fused w in a chunk of its own behind a power-of-two number of embedding chunks:
   // lane groups cover the embedding only (no idle lanes), lane 0 fetches w separately.  Only the
   // tiled kernels implement this, so it is enabled only when they will be used.

@@ -58,7 +58,6 @@ __global__ void __launch_bounds__(256, 2) mlp_skinny_bwd_kernel(const Params p) 
   __nv_bfloat16* Ds = Xs + SB * XS;                                    // [SB][DS]
   __nv_bfloat16* Ks = Ds + SB * DS;                                    // [n_in][DS]
   __nv_bfloat16* St = Ks + (size_t)n_in * DS;                          // [8 warps][16][STG]
-  float* dbs = reinterpret_cast<float*>(St + 8 * 16 * STG);            // [NOUT] (block partial of db)
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int g = lane >> 2, t = lane & 3;
   const int mtiles = n_in / 16;
@@ -69,7 +68,6 @@ __global__ void __launch_bounds__(256, 2) mlp_skinny_bwd_kernel(const Params p) 
     const int j = e / NOUT, o = e % NOUT;
     Ks[j * DS + o] = __float2bfloat16_rn(p.K[e]);
   }
-  if (tid < NOUT) dbs[tid] = 0.f;
 
   float acc[MT][NOUT / 8][4];                                          // dK tiles of this warp, across all slabs
 #pragma unroll
@@ -244,7 +242,7 @@ int etr_mlp_skinny_backward(etr_ctx* ctx, const void* d_X, int64_t ldx, const fl
   if (B <= 0) return ETR_OK;
   cudaStream_t s = (cudaStream_t)stream;
   const int XS = n_in + 8;
-  const size_t smem = ((size_t)sk::SB * XS + (size_t)sk::SB * sk::DS + (size_t)n_in * sk::DS + 8 * 16 * sk::STG) * 2 + sk::NOUT * 4;
+  const size_t smem = ((size_t)sk::SB * XS + (size_t)sk::SB * sk::DS + (size_t)n_in * sk::DS + 8 * 16 * sk::STG) * 2;
   const long long nslabs = (B + sk::SB - 1) / sk::SB;
   long long grid = 2LL * ctx->sm_count;
   if (grid > nslabs) grid = nslabs;

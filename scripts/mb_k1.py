@@ -33,12 +33,9 @@ alg = B * (F * (K * 4 + 4 + 8) + 4) + B * F * K * 2
 
 
 def run(impl, l1, align, dist, extra=None):
+    # (the L1-policy / CTAs-per-SM knobs and the cp.async-staged variant of the r01 experiments were removed from the
+    # library after the measurements in profiles/r01_mb_gather.md; ETR_GATHER=stream|generic remains)
     os.environ["ETR_GATHER"] = impl
-    os.environ["ETR_L1"] = str(l1)
-    for k_ in ("ETR_STREAM_CPS", "ETR_STAGED_WPB"):
-        os.environ.pop(k_, None)
-    for k_, v_ in (extra or {}).items():
-        os.environ[k_] = str(v_)
     tab = tables[align]
     ts = []
     G = 4
@@ -58,9 +55,6 @@ def run(impl, l1, align, dist, extra=None):
 
 
 for dist in ("zipf", "uniform"):
-    for impl in ("generic", "stream", "staged"):
-        for l1 in ((0, 1) if impl != "staged" else (0,)):
-            for align in (16, 128):
-                run(impl, l1, align, dist)
-    for cps in (1, 2):
-        run("stream", 1, 128, dist, {"ETR_STREAM_CPS": cps})
+    for impl in ("generic", "stream"):
+        for align in (16, 128):
+            run(impl, 0, align, dist)
