@@ -82,7 +82,7 @@ class ClockSampler:
         try:
             self.fh = open(self.path, "w")
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.idx), f"--query-gpu={self.Q}",
-                                          "--format=csv,noheader,nounits", "-lms", "100"], stdout=self.fh,
+                                          "--format=csv,noheader,nounits", "-lms", "20"], stdout=self.fh,
                                          stderr=subprocess.DEVNULL)
         except Exception:
             self.proc = None
