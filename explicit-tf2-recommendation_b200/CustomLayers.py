@@ -1031,6 +1031,46 @@ class Trainer:
     def iterations(self) -> int:                     # synchronises
         return int(self.state[0].item())
 
+    # ------------------------------------------------------- checkpoint / resume
+    # The reference checkpoints the model and the optimizer with tf.train.Checkpoint(model=..., optimizer=...)
+    # (2.FM/ModelManager.py:112-119, variable names in 2.FM/ranking_model/checkpoint/ckpt-2.index: bias, embed, w,
+    # MLP_layer*/kernel_i, bias_i and the Adam slots m / v).  Here: one dict of host tensors, per rank for a
+    # row-sharded layer (the table entries are then this rank's shard).
+    def state_dict(self) -> Dict[str, torch.Tensor]:
+        torch.cuda.synchronize(self.rt.device)
+        P = self.layer.params
+        sd = {"optimizer/state": self.state.cpu().clone(), "dense/value": P.value.cpu().clone(),
+              "dense/m": P.m.cpu().clone(), "dense/v": P.v.cpu().clone()}
+        for name in P.names():
+            sd[f"var/{name}"] = P[name].cpu().clone()           # reference-shaped views, for inspection / export
+        for i, t in enumerate(self.layer.sparse_tables()):
+            t = getattr(t, "local", t)                          # a peer-sharded table checkpoints its own shard
+            sd[f"table{i}/data"] = t.data.cpu().clone()
+            sd[f"table{i}/m"] = t.m.cpu().clone()
+            sd[f"table{i}/v"] = t.v.cpu().clone()
+        return sd
+
+    def load_state_dict(self, sd: Dict[str, torch.Tensor]) -> None:
+        P, dev = self.layer.params, self.rt.device
+        assert sd["dense/value"].shape == P.value.shape, "checkpoint belongs to a different model configuration"
+        self.state.copy_(sd["optimizer/state"].to(dev))
+        P.value.copy_(sd["dense/value"].to(dev))
+        P.m.copy_(sd["dense/m"].to(dev))
+        P.v.copy_(sd["dense/v"].to(dev))
+        for i, t in enumerate(self.layer.sparse_tables()):
+            t = getattr(t, "local", t)
+            assert sd[f"table{i}/data"].shape == t.data.shape, "table shape mismatch (rows / sharding changed?)"
+            t.data.copy_(sd[f"table{i}/data"].to(dev))
+            t.m.copy_(sd[f"table{i}/m"].to(dev))
+            t.v.copy_(sd[f"table{i}/v"].to(dev))
+        torch.cuda.synchronize(dev)
+
+    def save(self, path: str) -> None:
+        torch.save(self.state_dict(), path)
+
+    def restore(self, path: str) -> None:
+        self.load_state_dict(torch.load(path, map_location="cpu"))
+
     # ------------------------------------------------------------ eager step
     def train_step(self, inputs, labels=None) -> torch.Tensor:
         """One step; returns the (device-resident, un-synchronised) scalar loss."""

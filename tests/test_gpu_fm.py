@@ -425,3 +425,35 @@ def test_graph_trainer_matches_eager(L):
     hs = [trs[1].train_step_async(d, torch.tensor(y)) for _ in range(3)]
     vals = [h.result() for h in hs]
     assert all(np.isfinite(v) for v in vals) and trs[1].iterations == 12
+
+
+# ------------------------------------------------------------ checkpoint / resume (tf.train.Checkpoint analogue)
+@pytest.mark.parametrize("graph", [False, True])
+def test_trainer_checkpoint_resume_is_bit_exact(L, graph, tmp_path):
+    F, k, V, C_, B = 26, 16, 20011, 13, 512
+    names, cont = _names(F), [f"c{i}" for i in range(C_)]
+    rng = np.random.default_rng(7)
+
+    def batch():
+        d = {n: torch.tensor(rng.integers(0, V, size=B)) for n in names}
+        d.update({n: torch.tensor(rng.normal(size=B).astype(np.float32)) for n in cont})
+        return d, torch.tensor((rng.random(B) < 0.3).astype(np.float32))
+
+    data = [batch() for _ in range(8)]
+    mk = lambda: L.DeepFMRankingLayer(names, V, k, continuous_features=cont, seed=5, mlp_precision="bf16")   # noqa: E731
+    lay = mk()
+    tr = L.Trainer(lay, lr=1e-2, graph=graph)
+    for d, y in data[:4]:
+        tr.train_step(d, y)
+    path = str(tmp_path / "ckpt.pt")
+    tr.save(path)
+    ref = [float(tr.train_step(d, y).item()) for d, y in data[4:]]
+    lay2 = mk()
+    tr2 = L.Trainer(lay2, lr=1e-2, graph=graph)
+    tr2.restore(path)
+    assert tr2.iterations == 4
+    got = [float(tr2.train_step(d, y).item()) for d, y in data[4:]]
+    assert got == ref                                                        # same losses, bit for bit
+    torch.cuda.synchronize()
+    assert torch.equal(lay2.table.data, lay.table.data) and torch.equal(lay2.params.value, lay.params.value)
+    assert torch.equal(lay2.table.m, lay.table.m) and torch.equal(lay2.params.v, lay.params.v)
