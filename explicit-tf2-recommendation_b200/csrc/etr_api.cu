@@ -69,6 +69,14 @@ int etr_ctx_create(int device, etr_ctx** out) {
     return ETR_ENOMEM;
   }
   cudaMemset(c->d_err, 0, 2 * sizeof(unsigned long long));
+  c->side = nullptr; c->ev_fork = nullptr; c->ev_join = nullptr;
+  if (cudaStreamCreateWithFlags(&c->side, cudaStreamNonBlocking) != cudaSuccess ||
+      cudaEventCreateWithFlags(&c->ev_fork, cudaEventDisableTiming) != cudaSuccess ||
+      cudaEventCreateWithFlags(&c->ev_join, cudaEventDisableTiming) != cudaSuccess) {
+    etr_set_error("etr_ctx_create: could not create the side stream / events");
+    etr_ctx_destroy(c);
+    return ETR_ECUDA;
+  }
   *out = c;
   return ETR_OK;
 }
@@ -78,6 +86,9 @@ int etr_ctx_destroy(etr_ctx* ctx) {
   cudaSetDevice(ctx->device);
   if (ctx->d_ws) cudaFree(ctx->d_ws);
   if (ctx->d_err) cudaFree(ctx->d_err);
+  if (ctx->ev_fork) cudaEventDestroy(ctx->ev_fork);
+  if (ctx->ev_join) cudaEventDestroy(ctx->ev_join);
+  if (ctx->side) cudaStreamDestroy(ctx->side);
   delete ctx;
   return ETR_OK;
 }

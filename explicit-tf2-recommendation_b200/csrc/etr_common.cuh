@@ -29,6 +29,10 @@ struct etr_ctx {
   void* d_ws;
   size_t ws_bytes;
   long long launches;
+  // fork / join inside one entry point (independent kernels of a call overlap; capturable: the side
+  // stream always joins back before the call returns)
+  cudaStream_t side;
+  cudaEvent_t ev_fork, ev_join;
 };
 
 void etr_set_error(const char* fmt, ...);

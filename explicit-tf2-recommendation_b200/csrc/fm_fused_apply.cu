@@ -199,6 +199,24 @@ __device__ __forceinline__ void fused_finish_row(const FusedParams& p, long long
   }
 }
 
+// runs longer than kFusedShortRun go on the long-run list (cut into chunk items); done BEFORE the short-run
+// kernel so that the chunk kernel (side stream) and the short-run kernel are independent and overlap
+__global__ void __launch_bounds__(256) fm_fused_classify_kernel(const FusedParams p) {
+  const int n_unique = *p.n_unique;
+  for (int u = blockIdx.x * blockDim.x + threadIdx.x; u < n_unique; u += gridDim.x * blockDim.x) {
+    const int len = p.seg_start[u + 1] - p.seg_start[u];
+    if (len > kFusedShortRun) {
+      const int nch = (len + kFusedChunk - 1) / kFusedChunk;
+      const int slot = atomicAdd(&p.counters[0], 1);
+      const int base = atomicAdd(&p.counters[1], nch);
+      if (slot < p.max_long && base + nch <= p.max_items) {
+        p.long_runs[slot] = FusedLong{u, base, nch, 0};
+        for (int c = 0; c < nch; ++c) p.items[base + c] = make_int2(slot, c);
+      }
+    }
+  }
+}
+
 template <int LPR>
 __global__ void __launch_bounds__(256, 4) fm_fused_short_kernel(const FusedParams p) {
   constexpr int GPW = 32 / LPR;
@@ -211,18 +229,7 @@ __global__ void __launch_bounds__(256, 4) fm_fused_short_kernel(const FusedParam
   for (long long u = group_global; u < n_unique; u += ngroups) {
     const int s0 = p.seg_start[u], s1 = p.seg_start[u + 1];
     const int len = s1 - s0;
-    if (len > kFusedShortRun) {
-      if (gl == 0) {
-        const int nch = (len + kFusedChunk - 1) / kFusedChunk;
-        const int slot = atomicAdd(&p.counters[0], 1);
-        const int base = atomicAdd(&p.counters[1], nch);
-        if (slot < p.max_long && base + nch <= p.max_items) {
-          p.long_runs[slot] = FusedLong{(int)u, base, nch, 0};
-          for (int c = 0; c < nch; ++c) p.items[base + c] = make_int2(slot, c);
-        }
-      }
-      continue;
-    }
+    if (len > kFusedShortRun) continue;             // on the long-run list (fm_fused_classify_kernel)
     const long long row = p.unique_ids[u];
     const RowState st = fused_load_row<LPR>(p, row, gl);
     float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -373,12 +380,19 @@ static int fused_impl(etr_ctx* ctx, const etr_table* table, float* d_m, float* d
   ETR_CUDA(cudaMemsetAsync(p.counters, 0, 2 * sizeof(int), s));
   const int gshort = grid_for(n_slots, 8 * (32 / lpr), ctx->sm_count, 16);
   const int gchunk = ctx->sm_count * 4;
+  // classify -> { short-run kernel on the caller's stream || chunk kernel on the ctx side stream } -> combine
+  fm_fused_classify_kernel<<<grid_for(n_slots, 256, ctx->sm_count, 4), 256, 0, s>>>(p);
+  ETR_LAUNCH_CHECK(ctx);
+  ETR_CUDA(cudaEventRecord(ctx->ev_fork, s));
+  ETR_CUDA(cudaStreamWaitEvent(ctx->side, ctx->ev_fork, 0));
 #define ETR_FUSED(LPR)                                                      \
   do {                                                                      \
+    fm_fused_chunk_kernel<LPR><<<gchunk, 256, 0, ctx->side>>>(p);           \
+    ETR_LAUNCH_CHECK(ctx);                                                  \
+    ETR_CUDA(cudaEventRecord(ctx->ev_join, ctx->side));                     \
     fm_fused_short_kernel<LPR><<<gshort, 256, 0, s>>>(p);                   \
     ETR_LAUNCH_CHECK(ctx);                                                  \
-    fm_fused_chunk_kernel<LPR><<<gchunk, 256, 0, s>>>(p);                   \
-    ETR_LAUNCH_CHECK(ctx);                                                  \
+    ETR_CUDA(cudaStreamWaitEvent(s, ctx->ev_join, 0));                      \
     fm_fused_combine_kernel<LPR><<<ctx->sm_count, 256, 0, s>>>(p);          \
     ETR_LAUNCH_CHECK(ctx);                                                  \
   } while (0)
