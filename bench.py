@@ -326,6 +326,9 @@ def main():
     world = int(os.environ.get("WORLD_SIZE", "1"))
     torch.cuda.set_device(local_rank)
     if world > 1:
+        # stdout carries exactly ONE JSON line: keep NCCL's version banner (NCCL_DEBUG=VERSION) off it
+        if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
+            os.environ["NCCL_DEBUG"] = "WARN"
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     import etr_b200  # noqa: F401
     from etr_b200 import CustomLayers as L
