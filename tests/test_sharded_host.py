@@ -88,3 +88,52 @@ def test_exchange_protocol_over_gloo_world2():
         assert ok_fwd and ok_bwd, (r, ok_fwd, ok_bwd)
         assert n_sent == 300
     assert sum(results[r][3] for r in range(world)) == 600
+
+
+# ------------------------------------------------------------------ peer form (request / serve / deferred gradient)
+def _peer_worker(rank, world, port, V, k, results):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from oracle.peer_exchange_cpu import PeerExchangeCpu
+        F, B = 5, 64
+        full = torch.randn(V, k + 1, dtype=torch.float64, generator=torch.Generator().manual_seed(3))
+        px = PeerExchangeCpu(world, rank, full[rank::world].clone(), k)
+        rng = np.random.default_rng(50 + rank)
+        ok = True
+        for step in range(3):                                              # 3 steps: the accumulator is never cleared
+            X = torch.tensor((rng.random((B, F)) ** 3 * V).astype(np.int64))
+            g = torch.tensor(rng.normal(size=B))
+            dflat = torch.tensor(rng.normal(size=(B, F, k)))
+            rows, st = px.exchange_forward(X)
+            ok &= torch.equal(rows, full[X])                               # gathered rows bit-exact
+            t, grad = px.push_and_apply(st, px.export_deferred(st, rows, g, dflat))
+            # reference: autograd on the GLOBAL batch through the unsharded FM expression
+            Xs, gs, ds = [torch.empty_like(X) for _ in range(world)], [torch.empty_like(g) for _ in range(world)], \
+                [torch.empty_like(dflat) for _ in range(world)]
+            dist.all_gather(Xs, X); dist.all_gather(gs, g); dist.all_gather(ds, dflat)
+            XA, gA, dA = torch.cat(Xs), torch.cat(gs), torch.cat(ds)
+            tab = full.clone().requires_grad_(True)
+            e = tab[XA]                                                    # [B*,F,k+1]
+            v, w = e[..., :k], e[..., k]
+            z = w.sum(1) + 0.5 * ((v.sum(1) ** 2).sum(1) - (v ** 2).sum((1, 2)))
+            ((gA * z).sum() + (dA * v).sum()).backward()
+            ref = tab.grad[rank::world]
+            mine = torch.zeros_like(ref)
+            mine[t] = grad
+            ok &= torch.allclose(mine, ref, atol=1e-10)
+            ok &= int((ref.abs().sum(1) > 0).sum()) == t.numel()           # touched list == rows with a gradient
+        results[rank] = bool(ok)
+    finally:
+        dist.destroy_process_group()
+
+
+def test_peer_exchange_protocol_over_gloo_world2():
+    """request / serve / virtual ids / deferred FM gradient / rank-ordered stamped accumulation, stated on CPU
+    (oracle/peer_exchange_cpu.py) and run with 2 gloo ranks against the unsharded FM expression under autograd."""
+    world = 2
+    mgr = mp.Manager()
+    results = mgr.dict()
+    mp.spawn(_peer_worker, args=(world, 29850 + os.getpid() % 100, 499, 4, results), nprocs=world, join=True)
+    assert dict(results) == {0: True, 1: True}
