@@ -1,6 +1,7 @@
 """The oracle against the known-answer vectors and its own
 internal consistency properties.  CPU only."""
 import numpy as np
+import pytest
 import torch
 
 from oracle import kats
@@ -125,3 +126,53 @@ def test_keras_bce_matches_definition():
     pc = np.clip(p.numpy().astype(np.float64), e, 1 - e)
     exp = np.mean(-(y.numpy() * np.log(pc + e) + (1 - y.numpy()) * np.log(1 - pc + e)))
     assert abs(got - exp) < 1e-5 * abs(exp)
+
+
+# ---------------------------------------------------------------- round 2: gradient / Adam / BCE KATs
+def test_kat6_fm_gradient():
+    import torch
+    from oracle import kats, reference_layers as R
+    embed, w, bias, X, dz, logit, g_embed, g_w, g_bias = kats.kat6_fm_gradient()
+    fm = R.FMRankingLayer(["a", "b"], 4, 2)
+    fm.bias = torch.tensor(bias, requires_grad=True)
+    fm.embed = torch.tensor(embed, requires_grad=True)
+    fm.w = torch.tensor(w, requires_grad=True)
+    z = fm.logit(torch.tensor(X))
+    assert np.array_equal(z.detach().numpy(), logit)
+    (z.squeeze(1) * torch.tensor(dz)).sum().backward()
+    assert np.array_equal(fm.embed.grad.numpy(), g_embed)
+    assert np.array_equal(fm.w.grad.numpy(), g_w)
+    assert np.array_equal(fm.bias.grad.numpy(), g_bias)
+
+
+def test_kat7_ffm_pair_gradient():
+    import torch
+    from oracle import kats, reference_layers as R
+    T, X, g = kats.kat7_ffm_pair_gradient()
+    Tt = torch.tensor(T, requires_grad=True)
+    R.field_aware_interaction(Tt, torch.tensor(X)).sum().backward()
+    assert np.array_equal(Tt.grad.numpy(), g)
+
+
+@pytest.mark.parametrize("mode", ["keras_dense", "rowwise"])
+def test_kat8_keras_adam(mode):
+    import torch
+    from oracle import kats, reference_layers as R
+    lr, steps, expect = kats.kat8_keras_adam()
+    var = torch.tensor([[1.0], [2.0]], dtype=torch.float64)
+    opt = R.KerasAdam(lr=lr, mode=mode)
+    for (idx, vals), (e_var, e_m, e_v) in zip(steps, expect[mode]):
+        uniq, summed = R.indexed_slices_dedup(idx, vals)
+        opt.apply_sparse(var, torch.tensor(uniq), torch.tensor(summed), opt.step_begin())
+        m, v = opt._slots(var)
+        np.testing.assert_allclose(var.numpy().ravel(), e_var, rtol=1e-13)
+        np.testing.assert_allclose(m.numpy().ravel(), e_m, rtol=1e-13, atol=1e-300)
+        np.testing.assert_allclose(v.numpy().ravel(), e_v, rtol=1e-13, atol=1e-300)
+
+
+def test_kat9_keras_bce():
+    import torch
+    from oracle import kats, reference_layers as R
+    p, y, expect = kats.kat9_keras_bce()
+    got = float(R.keras_bce(torch.tensor(y).reshape(-1, 1), torch.tensor(p).reshape(-1, 1)))
+    assert abs(got - expect) < 1e-13
