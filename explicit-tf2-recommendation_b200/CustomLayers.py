@@ -49,6 +49,7 @@ class _Layer:
         self.pooling = kwargs.pop("pooling", "sum")
         self.check_ids = bool(kwargs.pop("check_ids", True))
         self.fused_apply = bool(kwargs.pop("fused_apply", True))     # FM family: fused backward+reduce+Adam
+        self.record_layout = bool(kwargs.pop("record_layout", True))  # FM family, k=16: [var|m|v] in one 256-B record
         self.name = kwargs.pop("name", type(self).__name__)
         # row-sharded tables: shard=True | "a2a" (NCCL all-to-all exchange) | "peer" (CUDA-IPC peer memory over
         # NVLink: de-duplicated request/serve exchange in the fused train step, rows pulled by the gather kernel
@@ -167,7 +168,10 @@ class FMRankingLayer(_Layer):
             shard_gen.manual_seed(self.seed * 1000003 + self.shard_spec[1])
             self.table.init_uniform(-0.05, 0.05, shard_gen)
         else:
-            self.table = EmbeddingTable(self.rt, self.feature_dims, k + 1, self.table_dtype)
+            # k = 16, fp32: the row and its Adam slots share one 256-byte record (two full lines per row in the
+            # fused apply instead of twelve scattered chunks); ``record_layout=False`` keeps three plain arrays
+            rec = self.record_layout and self.table_dtype == torch.float32 and k == 16
+            self.table = EmbeddingTable(self.rt, self.feature_dims, k + 1, self.table_dtype, record=rec)
             self.table.init_uniform(-0.05, 0.05, self.gen)  # Keras Embedding default for embed and w
 
     def _build_extra(self):

@@ -17,6 +17,7 @@ ETR_F32, ETR_BF16 = 0, 1
 POOL_SUM, POOL_MEAN = 0, 1
 ACT = {None: 0, "linear": 0, "relu": 1, "sigmoid": 2, "tanh": 3}
 ADAM_ROWWISE, ADAM_KERAS_DENSE = 0, 1
+ETR_TABLE_RECORD = -1          # etr_table.reserved: [var | m | v] interleaved in one 256-byte record
 
 
 class EtrError(RuntimeError):

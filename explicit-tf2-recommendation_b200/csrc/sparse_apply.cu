@@ -306,29 +306,36 @@ __global__ void __launch_bounds__(256) sparse_adam_kernel(const AdamParams p) {
   }
 }
 
-// keras_dense passes over the whole table
-__global__ void __launch_bounds__(256) dense_decay_kernel(float* m, float* v, long long n4, float b1, float b2) {
+// keras_dense passes over the whole table: rows x (rc 16-byte chunks of meaningful columns); row stride in
+// floats (== 4*rc for a plain table: one flat pass; 64 for a RECORD table whose m / v sit inside the record)
+__global__ void __launch_bounds__(256) dense_decay_kernel(float* m, float* v, long long rows, int rc, int stride, float b1,
+                                                          float b2) {
+  const long long n4 = rows * rc;
   for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < n4; t += (long long)gridDim.x * blockDim.x) {
-    float4 a = reinterpret_cast<float4*>(m)[t], b = reinterpret_cast<float4*>(v)[t];
+    const long long off = (t / rc) * stride + (t % rc) * 4;
+    float4 a = *reinterpret_cast<float4*>(m + off), b = *reinterpret_cast<float4*>(v + off);
     a.x *= b1; a.y *= b1; a.z *= b1; a.w *= b1;
     b.x *= b2; b.y *= b2; b.z *= b2; b.w *= b2;
-    reinterpret_cast<float4*>(m)[t] = a; reinterpret_cast<float4*>(v)[t] = b;
+    *reinterpret_cast<float4*>(m + off) = a; *reinterpret_cast<float4*>(v + off) = b;
   }
 }
 __global__ void __launch_bounds__(256) dense_var_update_kernel(char* table, int bf16, const float* m, const float* v,
-                                                               long long n4, float lr_host, const float* d_lr_t,
-                                                               float eps) {
+                                                               long long rows, int rc, int stride, float lr_host,
+                                                               const float* d_lr_t, float eps) {
   const float lr_t = d_lr_t ? *d_lr_t : lr_host;
+  const long long n4 = rows * rc;
   for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < n4; t += (long long)gridDim.x * blockDim.x) {
-    const float4 a = reinterpret_cast<const float4*>(m)[t], b = reinterpret_cast<const float4*>(v)[t];
+    const long long off = (t / rc) * stride + (t % rc) * 4;
+    const float4 a = *reinterpret_cast<const float4*>(m + off), b = *reinterpret_cast<const float4*>(v + off);
     float d[4] = {lr_t * a.x / (sqrtf(b.x) + eps), lr_t * a.y / (sqrtf(b.y) + eps),
                   lr_t * a.z / (sqrtf(b.z) + eps), lr_t * a.w / (sqrtf(b.w) + eps)};
     if (!bf16) {
-      float4 x = reinterpret_cast<float4*>(table)[t];
+      float4* px = reinterpret_cast<float4*>(reinterpret_cast<float*>(table) + off);
+      float4 x = *px;
       x.x -= d[0]; x.y -= d[1]; x.z -= d[2]; x.w -= d[3];
-      reinterpret_cast<float4*>(table)[t] = x;
+      *px = x;
     } else {
-      __nv_bfloat162* px = reinterpret_cast<__nv_bfloat162*>(table) + 2 * t;
+      __nv_bfloat162* px = reinterpret_cast<__nv_bfloat162*>(reinterpret_cast<__nv_bfloat16*>(table) + off);
       float2 lo = __bfloat1622float2(px[0]), hi = __bfloat1622float2(px[1]);
       px[0] = __floats2bfloat162_rn(lo.x - d[0], lo.y - d[1]);
       px[1] = __floats2bfloat162_rn(hi.x - d[2], hi.y - d[3]);
@@ -497,18 +504,23 @@ int etr_sparse_adam_apply(etr_ctx* ctx, const etr_table* table, float* d_m, floa
                           float beta1, float beta2, float eps, int32_t mode, void* stream) {
   ETR_CHECK_ARG(ctx && table && table->d_data && d_m && d_v && d_unique_ids && d_n_unique && d_unique_grad,
                 "NULL argument");
-  ETR_CHECK_ARG(grad_ld == table->stride, "grad_ld must equal the table stride (gradient rows use the table layout)");
-  ETR_CHECK_ARG(grad_ld % 4 == 0, "stride must be a multiple of 4");
+  const bool record = table->reserved == ETR_TABLE_RECORD;
+  const int row_cols = record ? ETR_RECORD_ROW_FLOATS : table->stride;     // meaningful columns of a row, whole chunks
+  ETR_CHECK_ARG(grad_ld == row_cols, "grad_ld must equal the table stride (20 for a RECORD table): gradient rows use the table's column layout");
+  ETR_CHECK_ARG(grad_ld % 4 == 0 && table->stride % 4 == 0, "stride must be a multiple of 4");
+  ETR_CHECK_ARG(!record || (table->dtype == ETR_F32 && table->stride == 64 && d_m == (float*)table->d_data + 20 &&
+                            d_v == (float*)table->d_data + 40), "RECORD table: m / v must be the record's own slots");
   cudaStream_t s = (cudaStream_t)stream;
   AdamParams p;
   p.table = (char*)table->d_data; p.table_bf16 = table->dtype == ETR_BF16; p.stride = table->stride;
   p.m = d_m; p.v = d_v; p.unique_ids = (const long long*)d_unique_ids; p.n_unique = d_n_unique;
   p.grad = d_unique_grad; p.grad_ld = grad_ld; p.lr_t = lr_t; p.d_lr_t = d_lr_t; p.b1 = beta1; p.b2 = beta2; p.eps = eps;
   p.scatter_only = mode == ETR_ADAM_KERAS_DENSE;
-  const long long n4 = table->rows * (long long)table->stride / 4;
+  const int rc = row_cols / 4;
+  const long long n4 = table->rows * (long long)rc;
   const int gd = grid_for(n4, 256, ctx->sm_count, 8);
   if (mode == ETR_ADAM_KERAS_DENSE) {
-    dense_decay_kernel<<<gd, 256, 0, s>>>(d_m, d_v, n4, beta1, beta2);
+    dense_decay_kernel<<<gd, 256, 0, s>>>(d_m, d_v, table->rows, rc, table->stride, beta1, beta2);
     ETR_LAUNCH_CHECK(ctx);
   }
   if (max_unique > 0) {
@@ -517,7 +529,8 @@ int etr_sparse_adam_apply(etr_ctx* ctx, const etr_table* table, float* d_m, floa
     ETR_LAUNCH_CHECK(ctx);
   }
   if (mode == ETR_ADAM_KERAS_DENSE) {
-    dense_var_update_kernel<<<gd, 256, 0, s>>>((char*)table->d_data, p.table_bf16, d_m, d_v, n4, lr_t, d_lr_t, eps);
+    dense_var_update_kernel<<<gd, 256, 0, s>>>((char*)table->d_data, p.table_bf16, d_m, d_v, table->rows, rc, table->stride,
+                                               lr_t, d_lr_t, eps);
     ETR_LAUNCH_CHECK(ctx);
   }
   return ETR_OK;

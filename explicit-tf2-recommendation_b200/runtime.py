@@ -109,24 +109,40 @@ class EmbeddingTable:
     is fused in as column ``k`` (one DRAM burst serves v and w)."""
 
     def __init__(self, rt: Runtime, rows: int, width: int, dtype: torch.dtype = torch.float32,
-                 data: Optional[torch.Tensor] = None, row_align: int = 16):
-        """``row_align`` (bytes, a multiple of 16): rows start on that boundary.  Random 64-byte
-        accesses are bound by DRAM activates, not bytes, so a row that straddles two 128-byte lines
-        (an 80-byte FM row at 80-byte stride does 37 % of the time) costs a second access: the FM
-        family pads its [v_0..v_15, w] rows to 128 bytes."""
+                 data: Optional[torch.Tensor] = None, row_align: int = 16, record: bool = False):
+        """``row_align`` (bytes, a multiple of 16): rows start on that boundary.
+
+        ``record=True`` (fp32, width <= 20): the row and its two Adam slots are interleaved in ONE
+        256-byte, 256-byte-aligned record ``[var 0..19 | m 20..39 | v 40..59 | pad]``: ``data``, ``m`` and
+        ``v`` are column views of the same buffer with row stride 64, so every kernel that addresses them
+        through (pointer, stride) works unchanged, the gather still finds ``[v_0..v_15, w]`` inside one
+        128-byte line, and the fused apply moves a row's whole state as two full lines
+        (csrc/fm_fused_apply.cu: fm_fused_record_kernel)."""
         assert dtype in _TORCH2ETR
         self.rt, self.rows, self.width, self.dtype = rt, int(rows), int(width), dtype
         esz = torch.empty((), dtype=dtype).element_size()
         assert row_align % 16 == 0
         epc = row_align // esz                                        # elements per alignment unit
-        self.stride = ((self.width + epc - 1) // epc) * epc
+        self.row_width = ((self.width + epc - 1) // epc) * epc        # meaningful columns, whole 16-byte chunks
+        self.record = bool(record)
+        self._m = self._v = None
+        if self.record:
+            assert dtype == torch.float32 and data is None and self.row_width <= 20
+            self.row_width = 20
+            self.stride = 64
+            self.rec = rt.zeros((self.rows, 64), torch.float32)
+            assert self.rec.data_ptr() % 256 == 0
+            self.data = self.rec[:, 0:20]
+            self._m, self._v = self.rec[:, 20:40], self.rec[:, 40:60]
+            return
+        self.stride = self.row_width
         if data is not None:          # caller-owned storage (e.g. a peer-mapped shard), already zeroed
             assert data.shape == (self.rows, self.stride) and data.dtype == dtype and data.is_contiguous()
         self.data = rt.zeros((self.rows, self.stride), dtype) if data is None else data
-        self._m = self._v = None
 
     def desc(self) -> _lib.etr_table:
-        return _lib.etr_table(self.data.data_ptr(), self.rows, self.width, self.stride, _TORCH2ETR[self.dtype], 0)
+        return _lib.etr_table(self.data.data_ptr(), self.rows, self.width, self.stride, _TORCH2ETR[self.dtype],
+                              _lib.ETR_TABLE_RECORD if self.record else 0)
 
     def cols(self, c0: int, c1: int) -> torch.Tensor:
         """Strided view of columns [c0,c1) -- e.g. ``embed/embeddings`` = cols(0,k),
@@ -153,7 +169,7 @@ class EmbeddingTable:
 
     @property
     def grad_ld(self) -> int:
-        return self.stride            # gradient rows use the table row layout (fp32)
+        return self.row_width         # gradient rows use the table's column layout (fp32), densely packed
 
 
 # ---------------------------------------------------------------------------
@@ -363,7 +379,7 @@ class FusedFMGrad:
         """materialise the deduplicated gradient rows (tests, export, the keras_dense apply)"""
         rt = self.table.rt
         self.plan = (plan or self.plan or SparsePlan(rt, self.ids, self.table.rows)).join()
-        self.unique_grad = rt.empty((max(self.plan.n_slots, 1), self.table.stride))
+        self.unique_grad = rt.empty((max(self.plan.n_slots, 1), self.table.grad_ld))
         self._run(False, 0.0, None, 0.0, 0.0, 0.0, self.unique_grad)
         return self
 

@@ -61,8 +61,17 @@ typedef struct {
   int32_t width;
   int32_t stride;
   int32_t dtype;      /* etr_dtype */
-  int32_t reserved;
+  int32_t reserved;   /* 0 plain; > 0 shard-set id (etr_shard_set_create); ETR_TABLE_RECORD */
 } etr_table;
+
+/* RECORD layout (fp32, width <= 20, stride == 64, d_data 256-byte aligned): the row and its two Adam
+ * slots (the ``m`` / ``v`` slot variables of tf.keras.optimizers.Adam, 2.FM/ModelManager.py:103-104,
+ * names in 2.FM/ranking_model/checkpoint/ckpt-2.index) are interleaved in one 256-byte record
+ *   [ var 0..19 | m 20..39 | v 40..59 | pad 60..63 ]   (floats)
+ * so d_m == (float*)d_data + 20 and d_v == (float*)d_data + 40 with the same stride; gradient rows
+ * exported for such a table are 20 floats wide (grad_ld = 20), not ``stride``.                     */
+#define ETR_TABLE_RECORD (-1)
+#define ETR_RECORD_ROW_FLOATS 20
 
 /* The categorical input of one batch.  Replaces the dict -> X[B,F] assembly
  * (2.FM/CustomLayers.py:138-144).  Element strides make [B,F] row-major,
@@ -167,6 +176,7 @@ int etr_sparse_segment_reduce(etr_ctx* ctx, const int32_t* d_sorted_bag, const i
  * 2.FM/ModelManager.py:178).  table/m/v share rows/width/stride (fp32 slots).
  * ROWWISE touches only the unique rows; KERAS_DENSE restates Keras 2.8
  * _resource_apply_sparse (m,v decayed and var updated for ALL rows).         */
+/* grad_ld: any multiple of 4 with width <= grad_ld <= stride (the table stride, or 20 for a RECORD table). */
 int etr_sparse_adam_apply(etr_ctx* ctx, const etr_table* table, float* d_m, float* d_v,
                           const int64_t* d_unique_ids, const int32_t* d_n_unique, int64_t max_unique,
                           const float* d_unique_grad, int32_t grad_ld,
@@ -180,7 +190,8 @@ int etr_sparse_adam_apply(etr_ctx* ctx, const etr_table* table, float* d_m, floa
  * gradient, fp32 or bf16, may be NULL) followed by the row-wise Adam update -- no
  * per-occurrence gradient rows are ever written.  Deterministic (runs <= 64 by one lane
  * group; longer runs in 1024-occurrence chunks combined in order).  apply == 0 only
- * exports the deduplicated gradient rows to d_unique_grad [n_unique, stride] (the
+ * exports the deduplicated gradient rows to d_unique_grad [n_unique, ld], ld = stride (20 for a
+ * RECORD table) (the
  * IndexedSlices tape.gradient + Keras' dedup produce, 2.FM/ModelManager.py:176-178). */
 int etr_fm_fused_backward_apply(etr_ctx* ctx, const etr_table* table, float* d_m, float* d_v, int32_t k,
                                 int32_t fields, int64_t batch,
