@@ -1014,8 +1014,14 @@ class Trainer:
     (one async H2D copy per host column) and replays ONE captured CUDA graph of
     the whole step; the optimizer clock lives on the device for that reason."""
 
-    def __init__(self, layer, lr=1e-3, beta_1=0.9, beta_2=0.999, epsilon=1e-7, apply_mode="rowwise", graph=False):
+    def __init__(self, layer, lr=1e-3, beta_1=0.9, beta_2=0.999, epsilon=1e-7, apply_mode="rowwise", graph=False,
+                 poll_every: int = 64):
+        """``poll_every``: every that many steps the device error word (out-of-range id, mailbox / touched-list
+        overflow, peer-barrier timeout) is copied to pinned host memory WITHOUT stalling the loop and checked as soon
+        as the copy has landed (at the latest ``poll_every`` steps later, and always in ``state_dict()``); 0 = never.
+        The kernels clamp and carry on, so without this a bad id would train silently on the wrong row."""
         assert apply_mode in ("rowwise", "keras_dense")
+        self.poll_every, self._steps_since_poll = int(poll_every), 0
         self.layer, self.lr, self.b1, self.b2, self.eps = layer, lr, beta_1, beta_2, epsilon
         self.mode = _lib.ADAM_ROWWISE if apply_mode == "rowwise" else _lib.ADAM_KERAS_DENSE
         self.rt = layer.rt
@@ -1042,6 +1048,8 @@ class Trainer:
     # row-sharded layer (the table entries are then this rank's shard).
     def state_dict(self) -> Dict[str, torch.Tensor]:
         torch.cuda.synchronize(self.rt.device)
+        self.rt.check_peeked_error(wait=True)
+        self.rt.poll_error()                                    # never checkpoint a state trained on clamped ids
         P = self.layer.params
         sd = {"optimizer/state": self.state.cpu().clone(), "dense/value": P.value.cpu().clone(),
               "dense/m": P.m.cpu().clone(), "dense/v": P.v.cpu().clone()}
@@ -1078,9 +1086,19 @@ class Trainer:
     # ------------------------------------------------------------ eager step
     def train_step(self, inputs, labels=None) -> torch.Tensor:
         """One step; returns the (device-resident, un-synchronised) scalar loss."""
-        if self.use_graph:
-            return self._graph_step(inputs, labels)
-        return self._eager_step(inputs, labels)
+        loss = self._graph_step(inputs, labels) if self.use_graph else self._eager_step(inputs, labels)
+        self._poll()
+        return loss
+
+    def _poll(self) -> None:
+        if self.poll_every <= 0:
+            return
+        self.rt.check_peeked_error()                            # non-blocking: only if the last peek has landed
+        self._steps_since_poll += 1
+        if self._steps_since_poll >= self.poll_every:
+            self._steps_since_poll = 0
+            self.rt.check_peeked_error(wait=True)               # the previous peek is poll_every steps old: done long ago
+            self.rt.peek_error_async()
 
     def _eager_step(self, inputs, labels=None) -> torch.Tensor:
         rt = self.rt
@@ -1275,6 +1293,7 @@ class Trainer:
         returns immediately.  ``handle.result()`` blocks only until THIS step is done."""
         assert self.use_graph, "train_step_async needs graph=True"
         loss = self._graph_step(inputs, labels)
+        self._poll()
         batch_slot = None
         for slots, _ in self._graphs.values():
             for sl in slots:

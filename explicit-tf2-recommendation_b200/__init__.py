@@ -12,7 +12,7 @@ from . import _lib  # noqa: F401
 from ._lib import EtrError, EtrIdRangeError  # noqa: F401
 
 
-_SUBMODULES = ("CustomLayers", "runtime", "dense", "sharded", "build")
+_SUBMODULES = ("CustomLayers", "runtime", "dense", "sharded", "build", "autograd", "tf_adapter", "tf_checkpoint", "tfrecord")
 
 
 def __getattr__(name):

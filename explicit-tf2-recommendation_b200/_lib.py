@@ -12,7 +12,7 @@ from typing import Optional
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "libetr.so")
 
-ETR_OK, ETR_EINVAL, ETR_ERANGE, ETR_ECUDA, ETR_ENOMEM, ETR_EUNSUPPORTED = range(6)
+ETR_OK, ETR_EINVAL, ETR_ERANGE, ETR_ECUDA, ETR_ENOMEM, ETR_EUNSUPPORTED, ETR_EOVERFLOW, ETR_ETIMEOUT = range(8)
 ETR_F32, ETR_BF16 = 0, 1
 POOL_SUM, POOL_MEAN = 0, 1
 ACT = {None: 0, "linear": 0, "relu": 1, "sigmoid": 2, "tanh": 3}
@@ -28,6 +28,14 @@ class EtrError(RuntimeError):
 
 class EtrIdRangeError(EtrError, IndexError):
     """An embedding id was out of range (TF-CPU raises InvalidArgumentError)."""
+
+
+class EtrOverflowError(EtrError):
+    """A sharded step dropped rows: a mailbox region or the owner's touched list overflowed."""
+
+
+class EtrPeerTimeoutError(EtrError, TimeoutError):
+    """A device-side peer barrier timed out."""
 
 
 class etr_table(C.Structure):
@@ -53,12 +61,17 @@ PROTOTYPES = {
     "etr_ctx_destroy": (C.c_int, [_vp]),
     "etr_ctx_poll_error": (C.c_int, [_vp, _vp, C.POINTER(_i64)]),
     "etr_ctx_launch_count": (_i64, [_vp]),
+    "etr_ctx_peek_error_async": (C.c_int, [_vp, _vp, _vp]),
+    "etr_ctx_decode_error": (C.c_int, [_vp, _vp, _vp, C.POINTER(_i64)]),
     "etr_assemble_ids": (C.c_int, [_vp, C.POINTER(_vp), _i32, _i64, _vp, _vp]),
     "etr_gather_fm_forward": (C.c_int, [_vp, _T, _i32, _i32, _I, _vp, _vp, _vp, _vp, _vp, _i32, _i64, _i32, _vp, _i32, _i64, _i64, _vp]),
     "etr_embedding_gather": (C.c_int, [_vp, _T, _vp, _i64, _vp, _i64, _vp]),
     "etr_gather_fm_backward": (C.c_int, [_vp, _T, _i32, _i32, _I, _vp, _vp, _i32, _i64, _i32, _vp, _i32, _vp]),
     "etr_sparse_plan_slots": (_i64, [_I, _i64]),
     "etr_sparse_plan": (C.c_int, [_vp, _I, _i64, _i64, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "etr_sparse_plan_keys": (C.c_int, [_vp, _I, _i64, _i64, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "etr_fm_fused_flat_apply": (C.c_int, [_vp, _T, _i32, _i32, _i64, _vp, _vp, _i64, _vp, _vp, _vp, _i32, _i64, _i32, _f32, _vp,
+                                          _f32, _f32, _f32, _vp]),
     "etr_sparse_segment_reduce": (C.c_int, [_vp, _vp, _vp, _vp, _i64, _vp, _i32, _vp, _vp]),
     "etr_sparse_adam_apply": (C.c_int, [_vp, _T, _vp, _vp, _vp, _vp, _i64, _vp, _i32, _f32, _vp, _f32, _f32, _f32, _i32, _vp]),
     "etr_fm_fused_backward_apply": (C.c_int, [_vp, _T, _vp, _vp, _i32, _i32, _i64, _vp, _vp, _vp, _vp, _i64, _vp, _vp, _vp,
@@ -108,6 +121,8 @@ PROTOTYPES = {
     "etr_peer_allreduce_sum": (C.c_int, [_vp, _vp, _i64, _i32, _vp, _vp]),
     "etr_shard_partition": (C.c_int, [_vp, _vp, _i64, _i32, _i64, _vp, _vp, _vp, _vp, _vp]),
     "etr_cross_mat_bwd_elementwise": (C.c_int, [_vp, _vp, _vp, _vp, _i64, _vp, _vp, _vp]),
+    "etr_tfrecord_parse": (C.c_int, [_vp, _i64, _i32, C.POINTER(C.c_char_p), C.POINTER(_i32), C.POINTER(_i32), C.POINTER(_vp),
+                                     _i64, _i32, C.POINTER(_i64), C.POINTER(_i64)]),
 }
 
 _lib: Optional[C.CDLL] = None
@@ -138,4 +153,8 @@ def check(status: int) -> None:
     msg = load().etr_last_error().decode("utf-8", "replace")
     if status == ETR_ERANGE:
         raise EtrIdRangeError(status, msg)
+    if status == ETR_EOVERFLOW:
+        raise EtrOverflowError(status, msg)
+    if status == ETR_ETIMEOUT:
+        raise EtrPeerTimeoutError(status, msg)
     raise EtrError(status, msg)

@@ -93,20 +93,47 @@ int etr_ctx_destroy(etr_ctx* ctx) {
   return ETR_OK;
 }
 
+static int decode_error_word(const unsigned long long* h, int64_t* bad_id) {
+  if (h[0] == 0) return ETR_OK;
+  if (bad_id) *bad_id = (int64_t)h[1];
+  switch (h[0]) {
+    case 2:
+      etr_set_error("sharded step: a request / gradient mailbox region overflowed (ids skewed in id mod G beyond the "
+                    "mailbox capacity); rows of this step were dropped -- enlarge the capacity and redo the step");
+      return ETR_EOVERFLOW;
+    case 3:
+      etr_set_error("sharded step: a peer barrier timed out (a rank did not arrive within ~20 s)");
+      return ETR_ETIMEOUT;
+    case 4:
+      etr_set_error("sharded step: the owner's touched-row list overflowed; rows of this step were dropped");
+      return ETR_EOVERFLOW;
+    default:
+      etr_set_error("embedding id %lld out of range (TF-CPU raises InvalidArgumentError here)", (long long)h[1]);
+      return ETR_ERANGE;
+  }
+}
+
 int etr_ctx_poll_error(etr_ctx* ctx, void* stream, int64_t* bad_id) {
   ETR_CHECK_ARG(ctx != nullptr, "ctx is NULL");
   cudaStream_t s = (cudaStream_t)stream;
   unsigned long long h[2] = {0, 0};
   ETR_CUDA(cudaMemcpyAsync(h, ctx->d_err, sizeof(h), cudaMemcpyDeviceToHost, s));
   ETR_CUDA(cudaStreamSynchronize(s));
-  if (h[0] != 0) {
-    ETR_CUDA(cudaMemsetAsync(ctx->d_err, 0, sizeof(h), s));
-    if (bad_id) *bad_id = (int64_t)h[1];
-    etr_set_error("embedding id %lld out of range (TF-CPU raises InvalidArgumentError here)",
-                  (long long)h[1]);
-    return ETR_ERANGE;
-  }
+  if (h[0] != 0) ETR_CUDA(cudaMemsetAsync(ctx->d_err, 0, sizeof(h), s));
+  return decode_error_word(h, bad_id);
+}
+
+int etr_ctx_peek_error_async(etr_ctx* ctx, void* stream, uint64_t* h_pinned2) {
+  ETR_CHECK_ARG(ctx != nullptr && h_pinned2 != nullptr, "NULL argument");
+  ETR_CUDA(cudaMemcpyAsync(h_pinned2, ctx->d_err, 2 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, (cudaStream_t)stream));
   return ETR_OK;
+}
+
+int etr_ctx_decode_error(etr_ctx* ctx, const uint64_t* h_word2, void* stream, int64_t* bad_id) {
+  ETR_CHECK_ARG(ctx != nullptr && h_word2 != nullptr, "NULL argument");
+  const unsigned long long h[2] = {h_word2[0], h_word2[1]};
+  if (h[0] != 0) ETR_CUDA(cudaMemsetAsync(ctx->d_err, 0, sizeof(h), (cudaStream_t)stream));
+  return decode_error_word(h, bad_id);
 }
 
 int64_t etr_ctx_launch_count(etr_ctx* ctx) { return ctx ? ctx->launches : 0; }

@@ -120,9 +120,13 @@ struct Chunk<__nv_bfloat16> {
 
 __device__ __forceinline__ float sigmoidf_exact(float z) { return 1.0f / (1.0f + expf(-z)); }
 
-__device__ __forceinline__ void flag_bad_id(unsigned long long* err, long long id) {
-  if (atomicCAS(&err[0], 0ull, 1ull) == 0ull) err[1] = (unsigned long long)id;
+// device error word: err[0] = code of the FIRST error since the last poll (0 none, 1 embedding id out of range,
+// 2 mailbox region overflow, 3 peer-barrier timeout, 4 touched-list overflow), err[1] = its detail (the id)
+constexpr unsigned long long kErrBadId = 1, kErrMailbox = 2, kErrBarrier = 3, kErrTouched = 4;
+__device__ __forceinline__ void flag_error(unsigned long long* err, unsigned long long code, long long detail) {
+  if (atomicCAS(&err[0], 0ull, code) == 0ull) err[1] = (unsigned long long)detail;
 }
+__device__ __forceinline__ void flag_bad_id(unsigned long long* err, long long id) { flag_error(err, kErrBadId, id); }
 
 template <int W>
 __device__ __forceinline__ float group_sum(float x, unsigned mask = 0xffffffffu) {

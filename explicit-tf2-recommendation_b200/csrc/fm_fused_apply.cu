@@ -21,6 +21,7 @@
 #include <algorithm>
 
 #include "etr_common.cuh"
+#include "etr_async.cuh"
 
 namespace etr {
 
@@ -110,6 +111,49 @@ __device__ __forceinline__ void fused_accumulate(const FusedParams& p, int i0, i
   }
 }
 
+// occurrences i0, i0+step, ... < i1 into acc / sum_g (this lane's float4 column chunk), two in flight
+__device__ __forceinline__ void fused_accumulate_strided(const FusedParams& p, int i0, int i1, int step, int gl, float4& acc,
+                                                         float& sum_g) {
+  const __nv_bfloat16* dfl16 = reinterpret_cast<const __nv_bfloat16*>(p.dflat);
+  const float* dfl32 = reinterpret_cast<const float*>(p.dflat);
+  auto fetch = [&](int i, float& g, float4& s, float4& d) {
+    int b, f;
+    bag_to_bf(p, __ldg(p.sorted_bag + i), b, f);
+    g = __ldg(p.dlogit + b);
+    s = *reinterpret_cast<const float4*>(p.sumv + (long long)b * p.k + gl * 4);
+    d = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (p.dflat) {
+      const long long e0 = (long long)b * p.flat_ld + p.flat_col0 + (long long)f * p.k + gl * 4;
+      if (p.flat_bf16) {
+        const uint2 w = *reinterpret_cast<const uint2*>(dfl16 + e0);
+        const float2 lo = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&w.x));
+        const float2 hi = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&w.y));
+        d = make_float4(lo.x, lo.y, hi.x, hi.y);
+      } else {
+        d = *reinterpret_cast<const float4*>(dfl32 + e0);
+      }
+    }
+  };
+  int i = i0;
+  for (; i + step < i1; i += 2 * step) {
+    float g0, g1;
+    float4 s0, s1, d0, d1;
+    fetch(i, g0, s0, d0);
+    fetch(i + step, g1, s1, d1);
+    acc.x += g0 * s0.x + d0.x; acc.y += g0 * s0.y + d0.y; acc.z += g0 * s0.z + d0.z; acc.w += g0 * s0.w + d0.w;
+    sum_g += g0;
+    acc.x += g1 * s1.x + d1.x; acc.y += g1 * s1.y + d1.y; acc.z += g1 * s1.z + d1.z; acc.w += g1 * s1.w + d1.w;
+    sum_g += g1;
+  }
+  if (i < i1) {
+    float g0;
+    float4 s0, d0;
+    fetch(i, g0, s0, d0);
+    acc.x += g0 * s0.x + d0.x; acc.y += g0 * s0.y + d0.y; acc.z += g0 * s0.z + d0.z; acc.w += g0 * s0.w + d0.w;
+    sum_g += g0;
+  }
+}
+
 __device__ __forceinline__ void adam_update4(float4& var, float4& m, float4& v, const float4 g, float lr_t, float b1,
                                              float b2, float eps) {
   float* pv = &var.x; float* pm = &m.x; float* pvv = &v.x; const float* pg = &g.x;
@@ -117,7 +161,7 @@ __device__ __forceinline__ void adam_update4(float4& var, float4& m, float4& v, 
   for (int i = 0; i < 4; ++i) {
     pm[i] = b1 * pm[i] + (1.0f - b1) * pg[i];
     pvv[i] = b2 * pvv[i] + (1.0f - b2) * pg[i] * pg[i];
-    pv[i] = pv[i] - lr_t * pm[i] / (sqrtf(pvv[i]) + eps);
+    pv[i] = pv[i] - fast_div(lr_t * pm[i], fast_sqrt(pvv[i]) + eps);        // MUFU sqrt / rcp: <= 2 ulp each
   }
 }
 
@@ -181,7 +225,7 @@ __device__ __forceinline__ void fused_finish_row(const FusedParams& p, long long
       if (p.apply) {
         wm = p.b1 * wm + (1.0f - p.b1) * sum_g;
         wv = p.b2 * wv + (1.0f - p.b2) * sum_g * sum_g;
-        w = w - lr_t * wm / (sqrtf(wv) + p.eps);
+        w = w - fast_div(lr_t * wm, fast_sqrt(wv) + p.eps);
         prow[p.k] = w;
         p.m[row * p.stride + p.k] = wm;
         p.v[row * p.stride + p.k] = wv;
@@ -222,6 +266,8 @@ __global__ void __launch_bounds__(256) fm_fused_classify_kernel(const FusedParam
   }
 }
 
+constexpr int kFusedSolo = 8;      // runs up to this length: one lane group; kFusedSolo < len <= kFusedShortRun: the whole warp
+
 template <int LPR>
 __global__ void __launch_bounds__(256, 4) fm_fused_short_kernel(const FusedParams p) {
   constexpr int GPW = 32 / LPR;
@@ -229,266 +275,57 @@ __global__ void __launch_bounds__(256, 4) fm_fused_short_kernel(const FusedParam
   const int gl = lane % LPR, g = lane / LPR;
   const int n_unique = *p.n_unique;
   const float lr_t = p.d_lr_t ? *p.d_lr_t : p.lr_t;
-  const long long group_global = ((long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5)) * GPW + g;
-  const long long ngroups = (long long)gridDim.x * (blockDim.x >> 5) * GPW;
-  for (long long u = group_global; u < n_unique; u += ngroups) {
-    const int s0 = p.seg_start[u], s1 = p.seg_start[u + 1];
-    const int len = s1 - s0;
-    if (len > kFusedShortRun) continue;             // on the long-run list (fm_fused_classify_kernel)
-    const long long row = p.unique_ids[u];
-    const RowState st = fused_load_row<LPR>(p, row, gl);
-    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-    float sum_g = 0.f;
-    fused_accumulate<2>(p, s0, s1, gl, acc, sum_g);
-    fused_finish_row<LPR>(p, u, row, gl, g, st, acc, sum_g, lr_t);
-  }
-}
-
-// ------------------------------------------------------------------------------------------------
-// Record layout (round 2).  For k = 16 the FM row and its two Adam slots live interleaved in ONE
-// 256-byte, 256-byte-aligned record  [var 0..19 | m 20..39 | v 40..59 | pad 60..63]  (floats; var =
-// [v_0..v_15, w, 0, 0, 0] as before, so the gather kernel still finds v and w inside one 128-byte line).
-// A row's state is then two full lines instead of twelve scattered 16-byte chunks in three arrays, and it
-// is moved by the copy engine, not through registers:
-//   * every warp owns a ring of shared-memory slots; lane 4g of the warp issues ONE cp.async.bulk (1-D TMA,
-//     256 bytes, mbarrier complete_tx) per row of a warp-tile (8 rows), DEPTH warp-tiles ahead -- no register
-//     is held per in-flight row, 8 x DEPTH x 256 B are in flight per warp;
-//   * while the records fly, the warp reduces the tile's runs (g_b, S_b, dflat slices: L2 hits): runs <= 8 by
-//     their own 4-lane group, runs of 9..64 by the WHOLE warp (8 groups take every 8th occurrence, fixed
-//     shuffle tree) -- the middle tier that the 4-lane kernel serialised;
-//   * Adam reads var/m/v from the staged record (bank-conflict-free: 320-byte slot stride), writes the
-//     record back in place and returns it with ONE cp.async.bulk shared -> global per row (or, STORE == 0,
-//     with 128-bit global stores from registers).
-// sqrt / divide of the update are the approximate MUFU forms (<= 2 ulp each; parity tolerance is 1e-5).
-constexpr int kRecFloats = 64;
-constexpr int kRecBytes = 256;
-constexpr int kRecSlotBytes = 320;      // 80 words = 16 (mod 32): the two rows of a quarter-warp hit disjoint banks
-constexpr int kRecRows = 8;             // rows per warp-tile (4 lanes each)
-constexpr int kRecSolo = 8;             // longest run reduced by a single lane group
-
-__device__ __forceinline__ uint32_t rec_smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-__device__ __forceinline__ void rec_mbar_init(uint32_t bar, uint32_t count) {
-  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
-}
-__device__ __forceinline__ void rec_mbar_arrive_tx(uint32_t bar, uint32_t bytes) {
-  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ uint32_t rec_mbar_try_wait(uint32_t bar, uint32_t parity) {
-  uint32_t ok;
-  asm volatile(
-      "{\n"
-      ".reg .pred p;\n"
-      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
-      "selp.b32 %0, 1, 0, p;\n"
-      "}\n"
-      : "=r"(ok)
-      : "r"(bar), "r"(parity)
-      : "memory");
-  return ok;
-}
-__device__ __forceinline__ void rec_bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
-  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
-               "l"(src), "r"(bytes), "r"(bar)
-               : "memory");
-}
-__device__ __forceinline__ void rec_bulk_s2g(void* dst, uint32_t src, uint32_t bytes) {
-  asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst), "r"(src), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ float fast_sqrt(float x) {
-  float r;
-  asm("sqrt.approx.f32 %0, %1;" : "=f"(r) : "f"(x));
-  return r;
-}
-__device__ __forceinline__ float fast_div(float a, float b) {
-  float r;
-  asm("div.approx.f32 %0, %1, %2;" : "=f"(r) : "f"(a), "f"(b));
-  return r;
-}
-__device__ __forceinline__ void adam_update1_fast(float& var, float& m, float& v, const float g, float lr_t, float b1,
-                                                  float b2, float eps) {
-  m = b1 * m + (1.0f - b1) * g;
-  v = b2 * v + (1.0f - b2) * g * g;
-  var = var - fast_div(lr_t * m, fast_sqrt(v) + eps);
-}
-__device__ __forceinline__ void adam_update4_fast(float4& var, float4& m, float4& v, const float4 g, float lr_t, float b1,
-                                                  float b2, float eps) {
-  adam_update1_fast(var.x, m.x, v.x, g.x, lr_t, b1, b2, eps);
-  adam_update1_fast(var.y, m.y, v.y, g.y, lr_t, b1, b2, eps);
-  adam_update1_fast(var.z, m.z, v.z, g.z, lr_t, b1, b2, eps);
-  adam_update1_fast(var.w, m.w, v.w, g.w, lr_t, b1, b2, eps);
-}
-
-// occurrences i0, i0+step, ... < i1 into acc / sum_g (this lane's float4 column chunk), two in flight
-__device__ __forceinline__ void fused_accumulate_strided(const FusedParams& p, int i0, int i1, int step, int gl, float4& acc,
-                                                         float& sum_g) {
-  const __nv_bfloat16* dfl16 = reinterpret_cast<const __nv_bfloat16*>(p.dflat);
-  const float* dfl32 = reinterpret_cast<const float*>(p.dflat);
-  auto fetch = [&](int i, float& g, float4& s, float4& d) {
-    int b, f;
-    bag_to_bf(p, __ldg(p.sorted_bag + i), b, f);
-    g = __ldg(p.dlogit + b);
-    s = *reinterpret_cast<const float4*>(p.sumv + (long long)b * p.k + gl * 4);
-    d = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (p.dflat) {
-      const long long e0 = (long long)b * p.flat_ld + p.flat_col0 + (long long)f * p.k + gl * 4;
-      if (p.flat_bf16) {
-        const uint2 w = *reinterpret_cast<const uint2*>(dfl16 + e0);
-        const float2 lo = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&w.x));
-        const float2 hi = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&w.y));
-        d = make_float4(lo.x, lo.y, hi.x, hi.y);
-      } else {
-        d = *reinterpret_cast<const float4*>(dfl32 + e0);
-      }
-    }
-  };
-  int i = i0;
-  for (; i + step < i1; i += 2 * step) {
-    float g0, g1;
-    float4 s0, s1, d0, d1;
-    fetch(i, g0, s0, d0);
-    fetch(i + step, g1, s1, d1);
-    acc.x += g0 * s0.x + d0.x; acc.y += g0 * s0.y + d0.y; acc.z += g0 * s0.z + d0.z; acc.w += g0 * s0.w + d0.w;
-    sum_g += g0;
-    acc.x += g1 * s1.x + d1.x; acc.y += g1 * s1.y + d1.y; acc.z += g1 * s1.z + d1.z; acc.w += g1 * s1.w + d1.w;
-    sum_g += g1;
-  }
-  if (i < i1) {
-    float g0;
-    float4 s0, d0;
-    fetch(i, g0, s0, d0);
-    acc.x += g0 * s0.x + d0.x; acc.y += g0 * s0.y + d0.y; acc.z += g0 * s0.z + d0.z; acc.w += g0 * s0.w + d0.w;
-    sum_g += g0;
-  }
-}
-
-template <int DEPTH, int STORE>
-__global__ void __launch_bounds__(256) fm_fused_record_kernel(const FusedParams p) {
-  constexpr int SLOTS = DEPTH + (STORE ? 2 : 1);
-  constexpr int TILE_BYTES = kRecRows * kRecSlotBytes;
-  extern __shared__ __align__(128) unsigned char rec_smem[];
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int gl = lane & 3, g = lane >> 2;
-  const int warps_per_cta = blockDim.x >> 5;
-  unsigned char* my_ring = rec_smem + (size_t)warp * SLOTS * TILE_BYTES;
-  unsigned long long* bars = reinterpret_cast<unsigned long long*>(rec_smem + (size_t)warps_per_cta * SLOTS * TILE_BYTES) + warp * SLOTS;
-  if (lane == 0) {
-#pragma unroll
-    for (int s = 0; s < SLOTS; ++s) rec_mbar_init(rec_smem_u32(bars + s), 1);
-  }
-  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-  __syncthreads();
-
-  const int n_unique = *p.n_unique;
-  const float lr_t = p.d_lr_t ? *p.d_lr_t : p.lr_t;
-  const long long n_tiles = ((long long)n_unique + kRecRows - 1) / kRecRows;
-  const long long W = (long long)gridDim.x * warps_per_cta;
-  const long long w0 = (long long)blockIdx.x * warps_per_cta + warp;
-  char* const tbase = reinterpret_cast<char*>(p.table);
-
-  // issue the record loads of warp-tile T into ring slot `slot`
-  auto issue = [&](long long T, int slot) {
-    const long long u = T * kRecRows + g;
-    bool valid = false;
-    long long row = 0;
-    if (T < n_tiles && u < n_unique) {
-      const int len = __ldg(p.seg_start + u + 1) - __ldg(p.seg_start + u);
-      valid = len <= kFusedShortRun;            // longer runs: chunk + combine kernels
-      row = __ldg(p.unique_ids + u);
-    }
-    const unsigned vm = __ballot_sync(0xffffffffu, valid && gl == 0);
-    const uint32_t bar = rec_smem_u32(bars + slot);
-    if (lane == 0) rec_mbar_arrive_tx(bar, (uint32_t)__popc(vm) * kRecBytes);
-    __syncwarp();
-    if (valid && gl == 0)
-      rec_bulk_g2s(rec_smem_u32(my_ring + slot * TILE_BYTES + g * kRecSlotBytes), tbase + row * kRecBytes, kRecBytes, bar);
-  };
-
-#pragma unroll
-  for (int d = 0; d < DEPTH; ++d) issue(w0 + d * W, d);
-
-  long long it = 0;
-  for (long long T = w0; T < n_tiles; T += W, ++it) {
-    const int slot = (int)(it % SLOTS);
-    {
-      // the slot the next prefetch lands in was last used SLOTS - DEPTH iterations ago; its write-back
-      // (bulk store reading shared memory) must have drained first
-      if (STORE) {
-        asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
-        __syncwarp();
-      }
-      issue(T + (long long)DEPTH * W, (int)((it + DEPTH) % SLOTS));
-    }
-    // ---- reduce the runs of this tile while its records are in flight
-    const long long u = T * kRecRows + g;
+  const long long warp_global = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const long long nwarps = (long long)gridDim.x * (blockDim.x >> 5);
+  // warp-uniform trip count: the 9..64-occurrence tier below needs every lane of the warp
+  for (long long u0 = warp_global * GPW; u0 < n_unique; u0 += nwarps * GPW) {
+    const long long u = u0 + g;
     int s0 = 0, s1 = 0;
     long long row = 0;
+    RowState st;
+    st.var = st.m = st.v = make_float4(0.f, 0.f, 0.f, 0.f);
+    st.wx = 0.f;
     if (u < n_unique) {
-      s0 = __ldg(p.seg_start + u);
-      s1 = __ldg(p.seg_start + u + 1);
-      row = __ldg(p.unique_ids + u);
+      s0 = p.seg_start[u];
+      s1 = p.seg_start[u + 1];
+      if (s1 - s0 <= kFusedShortRun) {               // longer runs are on the long-run list (fm_fused_classify_kernel)
+        row = p.unique_ids[u];
+        st = fused_load_row<LPR>(p, row, gl);
+      }
     }
     const int len = s1 - s0;
-    const bool valid = len > 0 && len <= kFusedShortRun;
+    const bool mine = len > 0 && len <= kFusedShortRun;
     float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
     float sum_g = 0.f;
-    if (valid && len <= kRecSolo) fused_accumulate_strided(p, s0, s1, 1, gl, acc, sum_g);
-    unsigned coop = __ballot_sync(0xffffffffu, valid && len > kRecSolo && gl == 0);
+    if (mine && len <= kFusedSolo) fused_accumulate<2>(p, s0, s1, gl, acc, sum_g);
+    // middle tier: a run of 9..64 occurrences would hold the other GPW-1 groups of the warp up for len/2 dependent
+    // round trips; instead every group takes each GPW-th occurrence and a fixed shuffle tree combines them
+    unsigned coop = __ballot_sync(0xffffffffu, mine && len > kFusedSolo && gl == 0);
     while (coop) {
-      const int src = __ffs(coop) - 1;           // lane 4*gg of the owning group
+      const int src = __ffs(coop) - 1;               // lane LPR*gg of the owning group
       coop &= coop - 1;
       const int a = __shfl_sync(0xffffffffu, s0, src), b = __shfl_sync(0xffffffffu, s1, src);
       float4 t = make_float4(0.f, 0.f, 0.f, 0.f);
       float ts = 0.f;
-      fused_accumulate_strided(p, a + g, b, kRecRows, gl, t, ts);
+      fused_accumulate_strided(p, a + g, b, GPW, gl, t, ts);
 #pragma unroll
-      for (int o = 4; o < 32; o <<= 1) {         // fixed tree over the 8 groups (same gl)
+      for (int o = LPR; o < 32; o <<= 1) {
         t.x += __shfl_xor_sync(0xffffffffu, t.x, o); t.y += __shfl_xor_sync(0xffffffffu, t.y, o);
         t.z += __shfl_xor_sync(0xffffffffu, t.z, o); t.w += __shfl_xor_sync(0xffffffffu, t.w, o);
         ts += __shfl_xor_sync(0xffffffffu, ts, o);
       }
-      if ((src >> 2) == g) { acc = t; sum_g = ts; }
+      if (src / LPR == g) { acc = t; sum_g = ts; }
     }
-    // ---- wait for the records, Adam in shared memory
-    const uint32_t bar = rec_smem_u32(bars + slot);
-    const uint32_t parity = (uint32_t)((it / SLOTS) & 1);
-    while (!rec_mbar_try_wait(bar, parity)) {}
-    float* rec = reinterpret_cast<float*>(my_ring + slot * TILE_BYTES + g * kRecSlotBytes);
-    if (valid) {
-      float4 var = *reinterpret_cast<const float4*>(rec + gl * 4);
-      float4 m = *reinterpret_cast<const float4*>(rec + 20 + gl * 4);
-      float4 v = *reinterpret_cast<const float4*>(rec + 40 + gl * 4);
-      const float4 gr = make_float4(acc.x - var.x * sum_g, acc.y - var.y * sum_g, acc.z - var.z * sum_g, acc.w - var.w * sum_g);
-      adam_update4_fast(var, m, v, gr, lr_t, p.b1, p.b2, p.eps);
-      float wv = 0.f, wm = 0.f, wvv = 0.f;
-      if (gl == 0) {
-        wv = rec[16]; wm = rec[36]; wvv = rec[56];
-        adam_update1_fast(wv, wm, wvv, sum_g, lr_t, p.b1, p.b2, p.eps);
-      }
-      if (STORE) {
-        *reinterpret_cast<float4*>(rec + gl * 4) = var;
-        *reinterpret_cast<float4*>(rec + 20 + gl * 4) = m;
-        *reinterpret_cast<float4*>(rec + 40 + gl * 4) = v;
-        if (gl == 0) { rec[16] = wv; rec[36] = wm; rec[56] = wvv; }
-      } else {
-        float* grow = reinterpret_cast<float*>(tbase + row * kRecBytes);
-        *reinterpret_cast<float4*>(grow + gl * 4) = var;
-        *reinterpret_cast<float4*>(grow + 20 + gl * 4) = m;
-        *reinterpret_cast<float4*>(grow + 40 + gl * 4) = v;
-        if (gl == 0) { grow[16] = wv; grow[36] = wm; grow[56] = wvv; }
-      }
-    }
-    if (STORE) {
-      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-      __syncwarp();
-      if (valid && gl == 0) rec_bulk_s2g(tbase + row * kRecBytes, rec_smem_u32(rec), kRecBytes);
-      asm volatile("cp.async.bulk.commit_group;" ::: "memory");
-    } else {
-      __syncwarp();          // every lane has read its record before the slot is refilled
-    }
+    if (mine) fused_finish_row<LPR>(p, u, row, gl, g, st, acc, sum_g, lr_t);
   }
-  if (STORE) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
-  // drain prefetches issued past the end (they carry zero bytes: nothing to wait for)
 }
+
+// Record layout (round 2): for k = 16 the FM row and its two Adam slots live interleaved in ONE 256-byte record
+// [var 0..19 | m 20..39 | v 40..59 | pad] (include/etr.h, ETR_TABLE_RECORD).  The kernels of this file address var, m and
+// v through their own pointers with the record stride, so they run unchanged on either layout (the record layout alone
+// takes the c2 apply from 172 to 145 us: a row's state is two lines instead of twelve scattered chunks).  The
+// occurrence-parallel kernel that streams records through the copy engine is csrc/fm_fused_flat.cu; a row-parallel
+// copy-engine pipeline was measured at 200-290 us (profiles/r02_mb_apply.md) and dropped.
 
 // one CTA per chunk item: (256/LPR) lane groups each reduce a contiguous sub-range in order
 template <int LPR>
@@ -648,44 +485,6 @@ static int fused_impl(etr_ctx* ctx, const etr_table* table, float* d_m, float* d
     fm_fused_combine_kernel<LPR><<<ctx->sm_count, 256, 0, s>>>(p);          \
     ETR_LAUNCH_CHECK(ctx);                                                  \
   } while (0)
-  // record layout (k = 16: [var | m | v] interleaved in one 256-byte record, see fm_fused_record_kernel): the
-  // short-run kernel is replaced by the copy-engine pipeline; classify / chunk / combine stay as they are (they
-  // address var, m and v through their own pointers with the record stride)
-  const float* tb = (const float*)table->d_data;
-  static int rec_depth = -1, rec_store = 1;
-  if (rec_depth < 0) {
-    rec_depth = 3;
-    const char* e = getenv("ETR_FUSED_REC");          // "off" | "D<depth>S<0|1>"  (tuning / A-B runs)
-    if (e && !strcmp(e, "off")) rec_depth = 0;
-    else if (e && e[0] == 'D' && e[1] >= '2' && e[1] <= '4' && e[2] == 'S') { rec_depth = e[1] - '0'; rec_store = e[3] == '1'; }
-  }
-  const bool record = rec_depth > 0 && apply && table->reserved == ETR_TABLE_RECORD && !d_unique_grad && !d_slot_of_u && lpr == 4 &&
-                      table->stride == kRecFloats && d_m == tb + 20 && d_v == tb + 40 && ((uintptr_t)tb % kRecBytes) == 0;
-  if (record) {
-    fm_fused_chunk_kernel<4><<<gchunk, 256, 0, ctx->side>>>(p);
-    ETR_LAUNCH_CHECK(ctx);
-    ETR_CUDA(cudaEventRecord(ctx->ev_join, ctx->side));
-    const int slots = rec_depth + (rec_store ? 2 : 1);
-    const size_t smem = (size_t)8 * slots * kRecRows * kRecSlotBytes + (size_t)8 * slots * sizeof(unsigned long long);
-    const int per_sm = smem <= 113 * 1024 ? 2 : 1;
-    const int grec = (int)std::min<long long>((long long)ctx->sm_count * per_sm, (n_slots + 63) / 64 + 1);
-#define ETR_REC(D, S)                                                                                              \
-  do {                                                                                                             \
-    ETR_CUDA(cudaFuncSetAttribute(fm_fused_record_kernel<D, S>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
-    fm_fused_record_kernel<D, S><<<grec, 256, smem, s>>>(p);                                                       \
-  } while (0)
-    if (rec_store) {
-      if (rec_depth == 2) ETR_REC(2, 1); else if (rec_depth == 3) ETR_REC(3, 1); else ETR_REC(4, 1);
-    } else {
-      if (rec_depth == 2) ETR_REC(2, 0); else if (rec_depth == 3) ETR_REC(3, 0); else ETR_REC(4, 0);
-    }
-#undef ETR_REC
-    ETR_LAUNCH_CHECK(ctx);
-    ETR_CUDA(cudaStreamWaitEvent(s, ctx->ev_join, 0));
-    fm_fused_combine_kernel<4><<<ctx->sm_count, 256, 0, s>>>(p);
-    ETR_LAUNCH_CHECK(ctx);
-    return ETR_OK;
-  }
   switch (lpr) {
     case 1: ETR_FUSED(1); break;
     case 2: ETR_FUSED(2); break;

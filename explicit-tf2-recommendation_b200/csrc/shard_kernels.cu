@@ -104,7 +104,7 @@ __global__ void __launch_bounds__(256) shard_push_kernel(const PushParams p) {
     if (!active) continue;
     const int slot = base[owner] + off;
     if (slot >= p.cap) {
-      if (gl == 0) flag_bad_id(p.err, -2);            // mailbox region overflow
+      if (gl == 0) flag_error(p.err, kErrMailbox, 0);            // mailbox region overflow
       continue;
     }
     if (gl == 0) p.ids_mb[owner][slot] = lrow;
@@ -160,7 +160,7 @@ __global__ void __launch_bounds__(256) shard_request_kernel(const RequestParams 
     if (active) {
       const int slot = base[owner] + off;
       if (slot >= p.cap) {
-        flag_bad_id(p.err, -2);                       // mailbox region overflow
+        flag_error(p.err, kErrMailbox, 0);                       // mailbox region overflow
         p.slot_of_u[u] = owner * p.cap;               // keep later kernels in range
       } else {
         p.req_mb[owner][slot] = lrow;
@@ -291,7 +291,7 @@ __global__ void __launch_bounds__(256) mailbox_accumulate_kernel(const AccParams
     if (fresh) {
       const int t = wbase[warp] + __popc(ball & ((1u << lane) - 1u));
       if (t < p.max_touched) p.touched[t] = (int)row;
-      else flag_bad_id(p.err, -4);
+      else flag_error(p.err, kErrTouched, 0);
     }
     __syncthreads();
   }
@@ -359,7 +359,7 @@ __global__ void peer_barrier_kernel(const BarrierParams p) {
       asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p.my_flags + g) : "memory");
       if ((int)(v - e) >= 0) break;
       if (clock64() - t0 > 40000000000ll) {          // ~20 s: a peer never arrived
-        flag_bad_id(p.err, -3);
+        flag_error(p.err, kErrBarrier, 0);
         break;
       }
       __nanosleep(64);

@@ -386,6 +386,13 @@ int64_t etr_sparse_plan_slots(const etr_ids* ids, int64_t nnz_if_csr) {
 int etr_sparse_plan(etr_ctx* ctx, const etr_ids* ids, int64_t nnz_if_csr, int64_t table_rows,
                     int32_t* d_sorted_bag, int64_t* d_unique_ids, int32_t* d_seg_start,
                     int32_t* d_n_unique, int32_t* d_n_valid, void* stream) {
+  return etr_sparse_plan_keys(ctx, ids, nnz_if_csr, table_rows, d_sorted_bag, d_unique_ids, d_seg_start, d_n_unique,
+                              d_n_valid, nullptr, stream);
+}
+
+int etr_sparse_plan_keys(etr_ctx* ctx, const etr_ids* ids, int64_t nnz_if_csr, int64_t table_rows,
+                         int32_t* d_sorted_bag, int64_t* d_unique_ids, int32_t* d_seg_start,
+                         int32_t* d_n_unique, int32_t* d_n_valid, uint32_t* d_sorted_key, void* stream) {
   ETR_CHECK_ARG(ctx && ids && ids->d_ids && d_sorted_bag && d_unique_ids && d_seg_start && d_n_unique && d_n_valid,
                 "NULL argument");
   ETR_CHECK_ARG(table_rows > 0 && table_rows < 0xffffffffLL, "table_rows must fit 32 bits");
@@ -415,7 +422,7 @@ int etr_sparse_plan(etr_ctx* ctx, const etr_ids* ids, int64_t nnz_if_csr, int64_
   if (st != ETR_OK) return st;
   char* ws = (char*)ctx->d_ws;
   unsigned* keys_in = (unsigned*)ws;
-  unsigned* keys_out = (unsigned*)(ws + arr);
+  unsigned* keys_out = d_sorted_key ? d_sorted_key : (unsigned*)(ws + arr);   // the sorted ids themselves, kept for the caller
   int* bags_in = (int*)(ws + 2 * arr);
   int* n_runs = (int*)(ws + 3 * arr);
   void* tmp = ws + 3 * arr + 256;

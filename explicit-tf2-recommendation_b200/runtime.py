@@ -6,6 +6,7 @@ from __future__ import annotations
 
 import ctypes as C
 import math
+import os
 from typing import Dict, List, Optional, Sequence
 
 import numpy as np
@@ -73,6 +74,32 @@ class Runtime:
         bad = C.c_int64(0)
         check(self.lib.etr_ctx_poll_error(self.ctx, self.stream, C.byref(bad)))
         check(self.lib.etr_ctx_poll_error(self.side_ctx, self.stream, C.byref(bad)))
+
+    def peek_error_async(self) -> None:
+        """Enqueue a copy of both contexts' error words into pinned host memory (no synchronisation)."""
+        if getattr(self, "_err_host", None) is None:
+            self._err_host = torch.zeros(4, dtype=torch.int64).pin_memory()
+            self._err_event = torch.cuda.Event()
+            self._err_pending = False
+        check(self.lib.etr_ctx_peek_error_async(self.ctx, self.stream, self._err_host.data_ptr()))
+        check(self.lib.etr_ctx_peek_error_async(self.side_ctx, self.stream, self._err_host[2:].data_ptr()))
+        self._err_event.record(torch.cuda.current_stream(self.device))
+        self._err_pending = True
+
+    def check_peeked_error(self, wait: bool = False) -> None:
+        """Raise if the last peeked error word was set (EtrIdRangeError / EtrOverflowError / EtrPeerTimeoutError)."""
+        if not getattr(self, "_err_pending", False):
+            return
+        if wait:
+            self._err_event.synchronize()
+        elif not self._err_event.query():
+            return
+        self._err_pending = False
+        bad = C.c_int64(0)
+        for ctx_, off in ((self.ctx, 0), (self.side_ctx, 2)):
+            if int(self._err_host[off]) != 0:
+                word = (C.c_uint64 * 2)(int(self._err_host[off]) & (2 ** 64 - 1), int(self._err_host[off + 1]) & (2 ** 64 - 1))
+                check(self.lib.etr_ctx_decode_error(ctx_, word, self.stream, C.byref(bad)))
 
     # ------------------------------------------------------------ tensors
     def to_device(self, x, dtype: torch.dtype) -> torch.Tensor:
@@ -291,14 +318,16 @@ class SparsePlan:
             self.unique_ids = rt.empty((max(n, 1),), torch.int64)
             self.seg_start = rt.empty((n + 1,), torch.int32)
             self.counts = rt.zeros((2,), torch.int32)        # [n_unique, n_valid]
+            self.sorted_key = rt.empty((max(n, 1),), torch.int32)   # uint32 ids of the sorted occurrences
             d = ids.desc()
-            check(rt.lib.etr_sparse_plan(ctx_, C.byref(d), ids.nnz or 0, table_rows, self.sorted_bag.data_ptr(),
-                                         self.unique_ids.data_ptr(), self.seg_start.data_ptr(),
-                                         self.counts[0:].data_ptr(), self.counts[1:].data_ptr(),
-                                         torch.cuda.current_stream(rt.device).cuda_stream))
+            check(rt.lib.etr_sparse_plan_keys(ctx_, C.byref(d), ids.nnz or 0, table_rows, self.sorted_bag.data_ptr(),
+                                              self.unique_ids.data_ptr(), self.seg_start.data_ptr(),
+                                              self.counts[0:].data_ptr(), self.counts[1:].data_ptr(),
+                                              self.sorted_key.data_ptr(),
+                                              torch.cuda.current_stream(rt.device).cuda_stream))
         if overlap:
             self._pending = rt.side_stream
-            for t in (self.sorted_bag, self.unique_ids, self.seg_start, self.counts):
+            for t in (self.sorted_bag, self.unique_ids, self.seg_start, self.counts, self.sorted_key):
                 t.record_stream(cur)                     # allocated on the side stream, consumed on the current one
 
     def join(self) -> "SparsePlan":
@@ -372,7 +401,22 @@ class FusedFMGrad:
             df.stride(0) if df is not None else 0, self.flat_col0, lr_t, _p(d_lr_t), b1, b2, eps, int(apply), _p(out),
             rt.stream))
 
+    # "flat" = occurrence-parallel kernel (csrc/fm_fused_flat.cu; RECORD tables), "rows" = row-parallel kernels
+    apply_kernel = os.environ.get("ETR_FUSED_APPLY", "flat")
+
     def apply(self, d_lr_t: torch.Tensor, b1: float, b2: float, eps: float) -> None:
+        if self.table.record and self.k == 16 and FusedFMGrad.apply_kernel == "flat":
+            rt, t = self.table.rt, self.table.desc()
+            if self.plan is None:
+                self.plan = SparsePlan(rt, self.ids, self.table.rows)
+            self.plan.join()
+            df = self.dflat
+            check(rt.lib.etr_fm_fused_flat_apply(
+                rt.ctx, C.byref(t), self.k, self.ids.F, self.ids.B, self.plan.sorted_key.data_ptr(),
+                self.plan.sorted_bag.data_ptr(), self.plan.n_slots, self.dlogit.data_ptr(), self.sumv.data_ptr(), _p(df),
+                _TORCH2ETR[df.dtype] if df is not None else 0, df.stride(0) if df is not None else 0, self.flat_col0,
+                0.0, _p(d_lr_t), b1, b2, eps, rt.stream))
+            return
         self._run(True, 0.0, d_lr_t, b1, b2, eps, None)
 
     def reduce(self, plan: Optional[SparsePlan] = None) -> "FusedFMGrad":

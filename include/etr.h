@@ -40,7 +40,9 @@ typedef enum {
   ETR_ERANGE = 2,        /* an embedding id was < 0 or >= rows              */
   ETR_ECUDA = 3,         /* CUDA runtime error (see etr_last_error)         */
   ETR_ENOMEM = 4,        /* workspace allocation failed                     */
-  ETR_EUNSUPPORTED = 5   /* shape / dtype outside what the kernels cover    */
+  ETR_EUNSUPPORTED = 5,  /* shape / dtype outside what the kernels cover    */
+  ETR_EOVERFLOW = 6,     /* sharded step: a mailbox / touched list overflowed (rows were dropped) */
+  ETR_ETIMEOUT = 7       /* sharded step: a peer barrier timed out           */
 } etr_status;
 
 typedef enum { ETR_F32 = 0, ETR_BF16 = 1 } etr_dtype;
@@ -99,6 +101,13 @@ int etr_ctx_destroy(etr_ctx* ctx);
  * ETR_ERANGE (and the first offending id in *bad_id) if any kernel since the
  * last poll saw an out-of-range id.                                          */
 int etr_ctx_poll_error(etr_ctx* ctx, void* stream, int64_t* bad_id);
+/* The same check without stalling the training loop: peek enqueues a copy of the error word (2 x uint64) into
+ * caller-owned PINNED host memory on ``stream`` and returns at once; after the caller has seen that copy complete
+ * (event / later synchronisation) decode turns it into a status (ETR_ERANGE, ETR_EOVERFLOW, ETR_ETIMEOUT; message in
+ * etr_last_error) and clears the device word if it was set.  The reference's train loop gets the same guarantee
+ * from TF-CPU raising inside the step (2.FM/ModelManager.py:172-179).                                        */
+int etr_ctx_peek_error_async(etr_ctx* ctx, void* stream, uint64_t* h_pinned2);
+int etr_ctx_decode_error(etr_ctx* ctx, const uint64_t* h_word2, void* stream, int64_t* bad_id);
 /* number of kernels of THIS library launched through ctx since creation     */
 int64_t etr_ctx_launch_count(etr_ctx* ctx);
 
@@ -163,6 +172,14 @@ int etr_sparse_plan(etr_ctx* ctx, const etr_ids* ids, int64_t nnz_if_csr, int64_
                     int32_t* d_sorted_bag, int64_t* d_unique_ids, int32_t* d_seg_start,
                     int32_t* d_n_unique, int32_t* d_n_valid, void* stream);
 
+/* Same plan, and additionally the sorted ids themselves: d_sorted_key [n_slots] uint32, d_sorted_key[i] = id of
+ * sorted occurrence i (pad / out-of-range slots carry the sentinel ``table_rows`` and sort last).  With
+ * (d_sorted_key, d_sorted_bag) the occurrence list is self-describing, which is what the occurrence-parallel
+ * fused apply (etr_fm_fused_flat_apply) streams.                                                          */
+int etr_sparse_plan_keys(etr_ctx* ctx, const etr_ids* ids, int64_t nnz_if_csr, int64_t table_rows,
+                         int32_t* d_sorted_bag, int64_t* d_unique_ids, int32_t* d_seg_start,
+                         int32_t* d_n_unique, int32_t* d_n_valid, uint32_t* d_sorted_key, void* stream);
+
 /* Segment-reduce the bag gradients by id (deterministic: ascending occurrence
  * order inside a run; long runs are cut into fixed chunks combined in order)
  * into d_unique_grad[u, 0:grad_ld] -- the deduplicated IndexedSlices Keras'
@@ -201,6 +218,19 @@ int etr_fm_fused_backward_apply(etr_ctx* ctx, const etr_table* table, float* d_m
                                 const void* d_dflat, int32_t flat_dtype, int64_t flat_ld, int32_t flat_col0,
                                 float lr_t, const float* d_lr_t, float beta1, float beta2, float eps,
                                 int32_t apply, float* d_unique_grad, void* stream);
+
+/* The same computation as etr_fm_fused_backward_apply(apply = 1) for a RECORD table (k = 16), organised by
+ * OCCURRENCE instead of by row: every warp streams a contiguous range of the sorted occurrence list
+ * (d_sorted_key, d_sorted_bag from etr_sparse_plan_keys), 8 occurrences per step, gathers (g_b, S_b, dflat slice)
+ * for 32 occurrences at a time, reduces runs with a segmented scan in registers (any run length: no classify /
+ * chunk / combine passes, no dependent load chains), queues finished rows in shared memory where their 256-byte
+ * records arrive by cp.async.bulk, and applies Adam to 8 queued rows per warp at a time.  Runs that cross a range
+ * boundary are finished by a second small kernel in range order (deterministic).                          */
+int etr_fm_fused_flat_apply(etr_ctx* ctx, const etr_table* table, int32_t k, int32_t fields, int64_t batch,
+                            const uint32_t* d_sorted_key, const int32_t* d_sorted_bag, int64_t n_slots,
+                            const float* d_dlogit, const float* d_sumv,
+                            const void* d_dflat, int32_t flat_dtype, int64_t flat_ld, int32_t flat_col0,
+                            float lr_t, const float* d_lr_t, float beta1, float beta2, float eps, void* stream);
 
 /* Dense Adam for the small replicated variables (bias, MLP, cross W/b).      */
 int etr_dense_adam_apply(etr_ctx* ctx, float* d_var, float* d_m, float* d_v, const float* d_grad,
@@ -450,6 +480,19 @@ int etr_peer_barrier(etr_ctx* ctx, uint32_t* const* h_peer_flags, uint32_t* d_my
 int etr_peer_allreduce_push(etr_ctx* ctx, const float* d_src, int64_t n, float* const* h_peer_slots, int32_t world,
                             int32_t rank, void* stream);
 int etr_peer_allreduce_sum(etr_ctx* ctx, const float* d_slots, int64_t n, int32_t world, float* d_dst, void* stream);
+
+/* ------------------------------------------------ input side (host code, no kernel)
+ * TFRecord frames of serialized tf.train.Example -> column arrays; replaces tf.data.TFRecordDataset +
+ * tf.io.parse_single_example(FixedLenFeature) of 2.FM/ModelManager.py:122-153 for the files
+ * 2.FM/DataGenerator.py:104-124 writes.  Feature i (name names[i]) is an Int64List (kinds[i] = 0, column type int64)
+ * or a FloatList (kinds[i] = 1, float) of exactly widths[i] values; cols[i] is a HOST array [capacity, widths[i]]
+ * (pinned, so that the Trainer's staging copies stay asynchronous).  Parses whole frames from buf[0, len) until
+ * ``capacity`` rows are filled or a partial frame is met; *n_rows = rows written, *consumed = bytes used.  A missing
+ * feature, a wrong list type or length, a malformed message or (verify_crc) a bad checksum return ETR_EINVAL -- where
+ * TF raises InvalidArgumentError / DataLossError.                                                        */
+int etr_tfrecord_parse(const uint8_t* buf, int64_t len, int32_t n_feat, const char* const* names, const int32_t* kinds,
+                       const int32_t* widths, void* const* cols, int64_t capacity, int32_t verify_crc,
+                       int64_t* n_rows, int64_t* consumed);
 
 #ifdef __cplusplus
 }

@@ -24,13 +24,13 @@ for dist in dists:
     dx = (torch.randn(B, 16 + F * K, device=dev) * 1e-5).to(torch.bfloat16)
     lr = torch.tensor([1e-3], device=dev)
     ts = []
-    for i in range(14):
+    for i in range(int(os.environ.get("ETR_MB_ITERS", "14"))):
         g = FusedFMGrad(tab, ids[i % 4], K, dl, sumv, dx, 16, plan=plans[i % 4])
         flush.zero_()
         a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         a.record(); g.apply(lr, 0.9, 0.999, 1e-7); b.record(); ts.append((a, b))
     torch.cuda.synchronize()
     nu = plans[0].n_unique
-    us = statistics.median(a.elapsed_time(b) for a, b in ts[2:]) * 1e3
-    print(f"fused apply layout={layout} variant={os.environ.get('ETR_FUSED_REC', 'default')} ({dist}): {us:.1f} us; "
+    us = statistics.median(a.elapsed_time(b) for a, b in ts[min(2, len(ts) - 1):]) * 1e3
+    print(f"fused apply layout={layout} kernel={os.environ.get('ETR_FUSED_APPLY', 'flat')} rec={os.environ.get('ETR_FUSED_REC', 'default')} ({dist}): {us:.1f} us; "
           f"unique rows {nu}; {nu * 408 / us / 1e3:.0f} GB/s algorithmic (408 B per unique row)", flush=True)
