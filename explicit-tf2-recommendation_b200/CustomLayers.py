@@ -610,7 +610,7 @@ class InnerProductNetwork(_Layer):
         B, F, k = x.shape
         g = g.contiguous()
         dx = rt.zeros((B, F, k))
-        self.kernel_grad = torch.zeros_like(self.kernel) if self.kernel is not None else None
+        self.kernel_grad = torch.empty_like(self.kernel) if self.kernel is not None else None
         check(rt.lib.etr_pnn_backward(rt.ctx, x.data_ptr(), F * k, B, F, k, _PNN_TYPE[self.kernel_type],
                                       _p(self.kernel), g.data_ptr(), g.shape[1], dx.data_ptr(), F * k,
                                       _p(self.kernel_grad), rt.stream))
@@ -701,8 +701,7 @@ class PNNRankingLayer(_Layer):
         dcomb = self.MLP_layer1.backward(dh)                       # [B, F*k + P]
         dk = None
         if self.method == "outer":
-            dk = self.params.g("pn/kernel")
-            dk.zero_()
+            dk = self.params.g("pn/kernel")            # written by the deterministic batch reduction
         check(rt.lib.etr_pnn_backward(rt.ctx, comb.data_ptr(), F * k + P, ids.B, F, k, _PNN_TYPE[self.kernel_type],
                                       _p(self.pn_kernel), dcomb[:, F * k:].data_ptr(), F * k + P, dcomb.data_ptr(),
                                       F * k + P, _p(dk), rt.stream))
@@ -711,6 +710,193 @@ class PNNRankingLayer(_Layer):
 
 
 PNNLayer = PNNRankingLayer
+
+
+# ---------------------------------------------------------------------------
+# the other pairwise consumers of the same rows (dense [B,F,k] in, one kernel each way)
+class _PairDense(_Layer):
+    mode = 0
+
+    def _w(self):
+        return None, 0
+
+    def _fwd(self, x, training):
+        rt = self.rt
+        x = rt.to_device(x, torch.float32).contiguous()
+        B, F, k = x.shape
+        P = F * (F - 1) // 2
+        out = rt.empty((B, k)) if self.mode == 2 else rt.empty((B, P, k))
+        W, kind = self._w()
+        check(rt.lib.etr_pair_dense_forward(rt.ctx, x.data_ptr(), F * k, B, F, k, self.mode, kind, _p(W), out.data_ptr(),
+                                            k if self.mode == 2 else P * k, rt.stream))
+        if training:
+            self._ctx = {"x": x}
+        return out
+
+    def call(self, x, training: bool = False):
+        return self._fwd(x, training)
+
+    def backward(self, g: torch.Tensor) -> torch.Tensor:
+        """upstream gradient in the output layout -> dx [B,F,k]; a weight gradient lands in ``self.W_grad``."""
+        rt = self.rt
+        x = self._ctx["x"]
+        B, F, k = x.shape
+        g = g.to(torch.float32).contiguous()
+        dx = rt.zeros((B, F, k))
+        W, kind = self._w()
+        self.W_grad = torch.empty_like(W) if W is not None else None
+        check(rt.lib.etr_pair_dense_backward(rt.ctx, x.data_ptr(), F * k, B, F, k, self.mode, kind, _p(W), g.data_ptr(),
+                                             g.numel() // B, dx.data_ptr(), F * k, _p(self.W_grad), rt.stream))
+        return dx
+
+
+class InteractionLayer(_PairDense):
+    """AFM pair vectors: ``call(x[B,F,k]) -> [B,P,k]``, out[b,(i,j),:] = x_i * x_j, i<j in loop order
+    (3.DCN/CustomLayers.py:825-838)."""
+    mode = 0
+
+    def __init__(self, **kwargs):
+        self._setup(kwargs)
+        self.params.finalize()
+
+
+class BiInteractionPooling(_PairDense):
+    """NFM second-order pooling: ``call(x[B,F,k]) -> [B,k]`` = 0.5 ((sum_f x)^2 - sum_f x^2)
+    (inline in NFMLayer.call, 3.DCN/CustomLayers.py:499-501)."""
+    mode = 2
+
+    def __init__(self, **kwargs):
+        self._setup(kwargs)
+        self.params.finalize()
+
+
+class BilinearInteractionLayer(_PairDense):
+    """FiBiNet: ``call(x[B,F,k]) -> [B,P,k]``, out[b,(i,j),:] = (x_i W) * x_j; bilinear_type 'all' (one W [k,k]),
+    'each' (W_i per LEFT field, F-1 of them), 'interaction' (W_p per pair); glorot_normal init
+    (3.DCN/CustomLayers.py:977-1009).  Weights: ``self.W`` [n_w,k,k] (``W_list[i] == W[i]``)."""
+    mode = 1
+    _KIND = {"all": 0, "each": 1, "interaction": 2}
+
+    def __init__(self, bilinear_type='interaction', **kwargs):
+        if bilinear_type not in self._KIND:
+            raise NotImplementedError
+        self._setup(kwargs)
+        self.bilinear_type = bilinear_type
+        self.W = None
+        self.params.finalize()
+
+    def build(self, F: int, k: int):
+        n_w = {"all": 1, "each": F - 1, "interaction": F * (F - 1) // 2}[self.bilinear_type]
+        std = (2.0 / (k + k)) ** 0.5                     # glorot_normal: truncated normal, stddev sqrt(2/(fan_in+fan_out))
+        W = torch.empty((n_w, k, k), device=self.rt.device)
+        torch.nn.init.trunc_normal_(W, mean=0.0, std=std / 0.87962566103423978, a=-2 * std / 0.87962566103423978,
+                                    b=2 * std / 0.87962566103423978, generator=self.gen)
+        self.W = W
+        return self
+
+    @property
+    def W_list(self):
+        return [self.W[i] for i in range(self.W.shape[0])]
+
+    def _w(self):
+        return self.W, self._KIND[self.bilinear_type]
+
+    def call(self, x, training: bool = False):
+        if self.W is None:
+            self.build(x.shape[1], x.shape[2])
+        return self._fwd(x, training)
+
+
+class ParralledOnnLayer(_Layer):
+    """ONN (2.FM/CustomLayers.py:957-1006): ``interaction(inputs)`` = [Flatten(embedding_single(X)) | Flatten(pair
+    vectors of FieldAwareInteractionLayer(X))] (pair vectors summed over k when ``reduce``) -- one gather kernel + one
+    field-pair kernel.  The reference then applies ``make_mlp_layer(mlp_units, sigmoid_units=True)`` (Dense +
+    LayerNormalization + PReLU stacks, :868-888), which is not on the hot path: pass it as ``mlp_layer`` (any callable on
+    a [B, D] CUDA tensor, e.g. a torch module) or use ``interaction`` / ``interaction_backward`` directly.
+
+    Reference quirk fixed as for FFMLayer: the reference builds ``FieldAwareInteractionLayer(self.fields_cnt)`` without
+    forwarding feature_dims / embedding_dims (:982); here they are forwarded.  ``ONNLayer`` (the loop form, one table
+    pair per field pair, :891-955) computes the same function whenever the fields' id ranges are disjoint (the
+    DataGenerator id space): E1_ij[v] = T[v, j, :], E2_ij[v] = T[v, i, :]."""
+
+    def __init__(self, feature_names=['item_tag1', 'item_tag2', 'item_tag3', 'user_tag0'], feature_dims=20, embedding_dims=16,
+                 mlp_units=[40, 20], reduce=False, mlp_layer=None, **kwargs):
+        self._setup(kwargs)
+        self.feature_names = list(feature_names)
+        self.feature_dims, self.embedding_dims = int(feature_dims), int(embedding_dims)
+        self.fields_cnt = len(self.feature_names)
+        self.mlp_units, self.reduce, self.mlp_layer = list(mlp_units), bool(reduce), mlp_layer
+        self.table = EmbeddingTable(self.rt, self.feature_dims, self.embedding_dims, self.table_dtype)
+        self.table.init_uniform(-0.05, 0.05, self.gen)
+        self.fa_interaction_layer = FieldAwareInteractionLayer(self.fields_cnt, self.feature_dims, self.embedding_dims,
+                                                               device=self.rt.device, seed=self.seed + 1)
+        self.params.finalize()
+
+    @property
+    def embedding_single(self) -> torch.Tensor:
+        return self.table.cols(0, self.embedding_dims)
+
+    def sparse_tables(self):
+        return [self.table, self.fa_interaction_layer.table]
+
+    @property
+    def out_dim(self) -> int:
+        F, k = self.fields_cnt, self.embedding_dims
+        P = F * (F - 1) // 2
+        return F * k + (P if self.reduce else P * k)
+
+    def interaction(self, inputs, training: bool = False) -> torch.Tensor:
+        rt = self.rt
+        ids = self._ids(inputs, self.feature_names)
+        F, k = self.fields_cnt, self.embedding_dims
+        P = F * (F - 1) // 2
+        comb = rt.empty((ids.B, self.out_dim))
+        gather_fm_forward(self.table, k, False, ids, flat=comb, flat_col0=0)
+        fa = self.fa_interaction_layer
+        pooled = rt.empty((ids.B, F, F * k)) if training else None
+        t, d = fa.table.desc(), ids.desc()
+        if self.reduce:
+            pairdot = rt.empty((ids.B, P))
+            check(rt.lib.etr_field_pair_forward(rt.ctx, C.byref(t), k, 0, C.byref(d), None, None, None, None,
+                                                pairdot.data_ptr(), None, None, _p(pooled), rt.stream))
+            comb[:, F * k:] = pairdot
+        else:
+            pv = rt.empty((ids.B, P, k))
+            check(rt.lib.etr_field_pair_forward(rt.ctx, C.byref(t), k, 0, C.byref(d), None, None, None, pv.data_ptr(),
+                                                None, None, None, _p(pooled), rt.stream))
+            comb[:, F * k:] = pv.reshape(ids.B, P * k)
+        if training:
+            self._ctx = {"ids": ids, "pooled": pooled}
+        self._finish(training)
+        return comb
+
+    def interaction_backward(self, dcomb: torch.Tensor) -> List[SparseGrad]:
+        """d X_combined [B, out_dim] -> the two table gradients (embedding_single, pair table)."""
+        rt = self.rt
+        ids, pooled = self._ctx["ids"], self._ctx["pooled"]
+        F, k = self.fields_cnt, self.embedding_dims
+        P = F * (F - 1) // 2
+        dcomb = dcomb.to(torch.float32).contiguous()
+        bag1 = gather_fm_backward(self.table, k, False, ids, dflat=dcomb, flat_col0=0)
+        dpv = dcomb[:, F * k:]
+        if self.reduce:
+            dpv = dpv.unsqueeze(2).expand(ids.B, P, k)
+        dpv = dpv.reshape(ids.B, P, k).contiguous()
+        fa = self.fa_interaction_layer
+        bag2 = rt.empty((ids.B * ids.F, fa.table.grad_ld))
+        d = ids.desc()
+        check(rt.lib.etr_field_pair_backward(rt.ctx, k, 0, C.byref(d), pooled.data_ptr(), None, None, dpv.data_ptr(),
+                                             bag2.data_ptr(), fa.table.grad_ld, rt.stream))
+        return [SparseGrad(self.table, ids, bag1), SparseGrad(fa.table, ids, bag2)]
+
+    def call(self, inputs, training: bool = False):
+        if self.mlp_layer is None:
+            raise NotImplementedError("ParralledOnnLayer.call needs mlp_layer= (the reference's Dense + LayerNormalization + "
+                                      "PReLU tower is outside the hot path); interaction() is the kernel part")
+        return {"output": self.mlp_layer(self.interaction(inputs, training=training))}
+
+
+ONNLayer = ParralledOnnLayer
 
 
 # ---------------------------------------------------------------------------

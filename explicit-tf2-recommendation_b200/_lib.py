@@ -89,6 +89,9 @@ PROTOTYPES = {
     "etr_field_pair_backward": (C.c_int, [_vp, _i32, _i32, _I, _vp, _vp, _vp, _vp, _vp, _i32, _vp]),
     "etr_pnn_forward": (C.c_int, [_vp, _vp, _i64, _i64, _i32, _i32, _i32, _vp, _vp, _i64, _vp]),
     "etr_pnn_backward": (C.c_int, [_vp, _vp, _i64, _i64, _i32, _i32, _i32, _vp, _vp, _i64, _vp, _i64, _vp, _vp]),
+    "etr_pnn_kernel_grad": (C.c_int, [_vp, _vp, _i64, _i64, _i32, _i32, _i32, _vp, _i64, _vp, _vp]),
+    "etr_pair_dense_forward": (C.c_int, [_vp, _vp, _i64, _i64, _i32, _i32, _i32, _i32, _vp, _vp, _i64, _vp]),
+    "etr_pair_dense_backward": (C.c_int, [_vp, _vp, _i64, _i64, _i32, _i32, _i32, _i32, _vp, _vp, _i64, _vp, _i64, _vp, _vp]),
     "etr_cross_vec_forward": (C.c_int, [_vp, _vp, _i64, _i64, _i32, _i32, _vp, _vp, _vp, _i64, _vp]),
     "etr_cross_vec_backward": (C.c_int, [_vp, _vp, _i64, _i64, _i32, _i32, _vp, _vp, _vp, _i64, _vp, _i64, _vp, _vp]),
     "etr_cross_vec_finish": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _vp, _i32, _i32, _vp, _vp, _vp]),

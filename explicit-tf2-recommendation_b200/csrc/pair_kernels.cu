@@ -225,7 +225,8 @@ __global__ void __launch_bounds__(256) pnn_fwd_kernel(const PnnParams p) {
   }
 }
 
-// dx (accumulated into p.dx) and dK (atomicAdd over the batch; dK must be zeroed by the caller)
+// dx (accumulated into p.dx); the kernel gradient dK is reduced over the batch without atomics by pnn_dk_kernel
+// (pair_dense.cu: one CTA per (pair, batch slice), slices added in order -- deterministic)
 __global__ void __launch_bounds__(256) pnn_bwd_kernel(const PnnParams p) {
   extern __shared__ float sm[];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
@@ -262,26 +263,6 @@ __global__ void __launch_bounds__(256) pnn_bwd_kernel(const PnnParams p) {
           }
         }
         p.dx[b * p.lddx + t] += acc;
-      }
-      if (p.dkernel && p.type != 0) {
-        for (int pi = lane; pi < P; pi += 32) {
-          int i, j;
-          pair_from_index(pi, p.F, i, j);
-          const float G = gs[pi];
-          const float* xi = xs + i * p.k;
-          const float* xj = xs + j * p.k;
-          if (p.type == 3) {
-            float s = 0.f;
-            for (int d = 0; d < p.k; ++d) s += xi[d] * xj[d];
-            atomicAdd(p.dkernel + pi, G * s);
-          } else if (p.type == 2) {
-            for (int c = 0; c < p.k; ++c) atomicAdd(p.dkernel + (long long)pi * p.k + c, G * xi[c] * xj[c]);
-          } else {
-            for (int a = 0; a < p.k; ++a)
-              for (int c = 0; c < p.k; ++c)
-                atomicAdd(p.dkernel + ((long long)a * P + pi) * p.k + c, G * xi[c] * xj[a]);
-          }
-        }
       }
     }
     __syncwarp();
@@ -417,6 +398,8 @@ int etr_pnn_backward(etr_ctx* ctx, const float* d_x, int64_t ldx, int64_t batch,
   ETR_CUDA(cudaFuncSetAttribute(pnn_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   pnn_bwd_kernel<<<grid_for(batch, 8, ctx->sm_count, 4), 256, smem, (cudaStream_t)stream>>>(p);
   ETR_LAUNCH_CHECK(ctx);
+  if (d_dkernel && kernel_type != 0)
+    return etr_pnn_kernel_grad(ctx, d_x, ldx, batch, fields, k, kernel_type, d_g, ldg, d_dkernel, stream);
   return ETR_OK;
 }
 

@@ -297,10 +297,28 @@ int etr_field_pair_backward(etr_ctx* ctx, int32_t k, int32_t has_w, const etr_id
 int etr_pnn_forward(etr_ctx* ctx, const float* d_x, int64_t ldx, int64_t batch, int32_t fields, int32_t k,
                     int32_t kernel_type, const float* d_kernel, float* d_out, int64_t ldo, void* stream);
 /* d_dx[b,i,:] += sum_j G[b,p(i,j)] * dOut_p/dx_i (ACCUMULATES: pre-fill with the
- * Flatten gradient); d_dkernel += batch sum (caller zeroes it; fp32 atomics).  */
+ * Flatten gradient); d_dkernel (optional) is WRITTEN with the batch sum, reduced without atomics
+ * (etr_pnn_kernel_grad: one CTA per (pair, batch slice), slices added in order -- deterministic).  */
 int etr_pnn_backward(etr_ctx* ctx, const float* d_x, int64_t ldx, int64_t batch, int32_t fields, int32_t k,
                      int32_t kernel_type, const float* d_kernel, const float* d_g, int64_t ldg,
                      float* d_dx, int64_t lddx, float* d_dkernel, void* stream);
+
+int etr_pnn_kernel_grad(etr_ctx* ctx, const float* d_x, int64_t ldx, int64_t batch, int32_t fields, int32_t k,
+                        int32_t kernel_type, const float* d_g, int64_t ldg, float* d_dkernel, void* stream);
+
+/* --------------------- other pairwise consumers of the same rows, on x [B,F,k] fp32 (row b at d_x + b*ldx)
+ * mode 0: AFM InteractionLayer pair vectors  out[b,p,:] = x_i (.) x_j                       3.DCN/CustomLayers.py:825-838
+ * mode 1: FiBiNet BilinearInteractionLayer   out[b,p,:] = (x_i W) (.) x_j, w_kind 0 'all' W [k,k], 1 'each' W [F-1,k,k]
+ *         (W_i, i the left field), 2 'interaction' W [P,k,k]                               3.DCN/CustomLayers.py:977-1009
+ * mode 2: NFM bi-interaction pooling         out[b,:]   = 0.5 ((sum_f x_f)^2 - sum_f x_f^2)  3.DCN/CustomLayers.py:499-501
+ * pairs (i<j) in itertools.combinations order; out row b at d_out + b*ldo ([P*k] or [k] floats).  Backward: d_g is the
+ * upstream gradient in the output layout, d_dx is ACCUMULATED (pre-fill with zeros or another gradient of x), d_dW
+ * (mode 1, optional) is written with the deterministic batch sum.                                           */
+int etr_pair_dense_forward(etr_ctx* ctx, const float* d_x, int64_t ldx, int64_t batch, int32_t fields, int32_t k, int32_t mode,
+                           int32_t w_kind, const float* d_W, float* d_out, int64_t ldo, void* stream);
+int etr_pair_dense_backward(etr_ctx* ctx, const float* d_x, int64_t ldx, int64_t batch, int32_t fields, int32_t k, int32_t mode,
+                            int32_t w_kind, const float* d_W, const float* d_g, int64_t ldg, float* d_dx, int64_t lddx,
+                            float* d_dW, void* stream);
 
 /* ------------------------------------------ K5: DCN cross-vector layer (a12)
  * x_{l+1} = x0*(x_l . w_l) + b_l + x_l, l < layers <= 8; d_w, d_b are [layers, D]

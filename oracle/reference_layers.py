@@ -614,6 +614,65 @@ class DeepCrossNetworkLayer:
 
 
 # --------------------------------------------------------------------------
+# f2: the other pairwise consumers of the same rows
+# --------------------------------------------------------------------------
+def interaction_layer(x: Tensor) -> Tensor:
+    """AFM ``InteractionLayer.call`` (3.DCN/CustomLayers.py:825-838): the double loop i<j of
+    ``inputs[:,i,:] * inputs[:,j,:]``, stacked and transposed to [B,P,k]."""
+    F = x.shape[1]
+    result = []
+    for i in range(F - 1):
+        for j in range(i + 1, F):
+            result.append(x[:, i, :] * x[:, j, :])
+    return torch.stack(result, dim=0).permute(1, 0, 2)
+
+
+def bilinear_interaction(x: Tensor, W, bilinear_type: str = "interaction") -> Tensor:
+    """FiBiNet ``BilinearInteractionLayer.call`` (3.DCN/CustomLayers.py:996-1009): ``tensordot(field_i, W, axes=(-1,0))
+    * field_j`` over itertools.combinations; 'all': one W [k,k]; 'each': W_list[i] for the LEFT field i;
+    'interaction': W_list[p] per pair.  -> [B,P,k]."""
+    import itertools
+    F = x.shape[1]
+    pairs = list(itertools.combinations(range(F), 2))
+    out = []
+    for p, (i, j) in enumerate(pairs):
+        Wm = W if bilinear_type == "all" else (W[i] if bilinear_type == "each" else W[p])
+        out.append((x[:, i, :] @ Wm) * x[:, j, :])
+    return torch.stack(out, dim=1)
+
+
+def bi_interaction(x: Tensor) -> Tensor:
+    """NFM second-order pooling (3.DCN/CustomLayers.py:499-501): 0.5 * (square(sum_f x) - sum_f square(x)) -> [B,k]."""
+    return 0.5 * (torch.square(torch.sum(x, dim=1)) - torch.sum(torch.square(x), dim=1))
+
+
+def onn_combined(embed_single: Tensor, T: Tensor, X: Tensor, reduce: bool = False) -> Tensor:
+    """``ParralledOnnLayer.call`` up to the tower (2.FM/CustomLayers.py:989-1001): [Flatten(embedding_single(X)) |
+    Flatten(FieldAwareInteractionLayer(X))] with the pair vectors summed over k when ``reduce``."""
+    X_single = embedding_lookup(embed_single, X).reshape(X.shape[0], -1)
+    X_pair = field_aware_interaction(T, X)
+    if reduce:
+        X_pair = torch.sum(X_pair, dim=2)
+    return torch.cat([X_single, X_pair.reshape(X.shape[0], -1)], dim=1)
+
+
+def onn_loop_combined(embed_single: Tensor, pair_tables, X: Tensor, reduce: bool = False) -> Tensor:
+    """``ONNLayer.call`` up to the tower (2.FM/CustomLayers.py:936-953): per pair (i,j) its own two tables,
+    ``E1_ij[x_i] * E2_ij[x_j]``; ``pair_tables[(i,j)] = (E1, E2)``."""
+    F = X.shape[1]
+    X_single = embedding_lookup(embed_single, X).reshape(X.shape[0], -1)
+    prods = []
+    for i in range(F):
+        for j in range(i + 1, F):
+            e1, e2 = pair_tables[(i, j)]
+            prods.append(embedding_lookup(e1, X[:, i]) * embedding_lookup(e2, X[:, j]))
+    X_pair = torch.stack(prods, dim=1)
+    if reduce:
+        X_pair = torch.sum(X_pair, dim=2)
+    return torch.cat([X_single, X_pair.reshape(X.shape[0], -1)], dim=1)
+
+
+# --------------------------------------------------------------------------
 # a16: loss, backward, IndexedSlices dedup, Adam     2.FM/ModelManager.py:99-104,171-181
 # --------------------------------------------------------------------------
 KERAS_EPS = 1e-7

@@ -1,6 +1,6 @@
 #!/bin/bash
 mkdir -p gpurun_out
-timeout 600 python -m pytest tests/test_gpu_parity_r2.py tests/test_gpu_fm.py tests/test_gpu_autograd.py -m gpu -q --timeout 300 > gpurun_out/pytest_r2.log 2>&1; echo "pytest r2 exit $?" >> gpurun_out/pytest_r2.log
+timeout 900 python -m pytest tests -m gpu -q --timeout 300 > gpurun_out/pytest_r2.log 2>&1; echo "pytest r2 exit $?" >> gpurun_out/pytest_r2.log
 tail -30 gpurun_out/pytest_r2.log
 : > gpurun_out/mb_apply_r2e.txt
 ETR_FUSED_APPLY=flat timeout 120 python scripts/mb_apply_r2.py record zipf uniform >> gpurun_out/mb_apply_r2e.txt 2>&1

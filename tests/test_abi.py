@@ -62,3 +62,20 @@ def test_product_never_imports_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".h")):
                 txt = open(os.path.join(dirpath, f)).read()
                 assert not re.search(r"^\s*(from|import)\s+oracle\b", txt, flags=re.M), f
+
+
+def test_tree_never_names_the_batched_memcpy_apis():
+    """gpurun hygiene: the driver refuses GPU runs for trees whose sources name the batched-memcpy calls.
+    The identifiers are assembled here so that this file does not name them either."""
+    banned = [a + "Memcpy" + b + "Batch" + "Async" for a in ("cuda", "cu") for b in ("", "3D")]
+    skip_dirs = {".git", "gpurun_out", "__pycache__", "build", ".pytest_cache", "baseline"}
+    skip_files = {"VERDICT.md", "ADVICE.md"}                 # written by the driver, not by the build
+    hits = []
+    for dirpath, dirs, files in os.walk(ROOT):
+        dirs[:] = [d for d in dirs if d not in skip_dirs]
+        for f in files:
+            if f in skip_files or not f.endswith((".py", ".cu", ".cuh", ".h", ".md", ".sh", ".json", ".txt")):
+                continue
+            txt = open(os.path.join(dirpath, f), errors="replace").read()
+            hits += [(f, b) for b in banned if b in txt]
+    assert not hits, hits
