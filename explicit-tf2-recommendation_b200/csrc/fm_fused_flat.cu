@@ -330,23 +330,48 @@ __global__ void __launch_bounds__(256) fm_fused_flat_fixup_kernel(const FlatPara
   const FlatEntry* E = p.ent;
   if (E[2 * r0 + 1].state != 2u) return;
   const unsigned key = E[2 * r0 + 1].key;
-  // number of following pieces: ranges r0+1 .. r0+m, the last one has state 1
+  // number of following pieces: ranges r0+1 .. r0+m, the last one has state 1 (128 entries examined per round trip)
   long long m = 0;
   for (;;) {
-    const long long q = r0 + 1 + m + lane;
-    const unsigned st = q < p.n_ranges ? E[2 * q].state : 1u;
-    const unsigned stop = __ballot_sync(0xffffffffu, st != 2u);
-    if (stop) { m += __ffs(stop); break; }          // includes the final (state 1) piece
-    m += 32;
+    unsigned st4[4];
+#pragma unroll
+    for (int q4 = 0; q4 < 4; ++q4) {
+      const long long q = r0 + 1 + m + q4 * 32 + lane;
+      st4[q4] = q < p.n_ranges ? E[2 * q].state : 1u;
+    }
+    bool done = false;
+#pragma unroll
+    for (int q4 = 0; q4 < 4; ++q4) {
+      if (done) continue;
+      const unsigned stop = __ballot_sync(0xffffffffu, st4[q4] != 2u);
+      if (stop) { m += q4 * 32 + __ffs(stop); done = true; }      // includes the final (state 1) piece
+    }
+    if (done) break;
+    m += 128;
   }
   float4 t = make_float4(0.f, 0.f, 0.f, 0.f);
   float ts = 0.f;
-  for (long long j = g; j <= m; j += 8) {
-    const FlatEntry* e = j == 0 ? &E[2 * r0 + 1] : &E[2 * (r0 + j)];
-    if (j == 0 || (r0 + j < p.n_ranges && e->state != 0u && e->key == key)) {
-      const float4 x = *reinterpret_cast<const float4*>(e->v + gl * 4);
-      t.x += x.x; t.y += x.y; t.z += x.z; t.w += x.w;
-      ts += e->gs;
+  // pieces j = 0 (the head, entry 2 r0 + 1) .. m; group g takes j = g, g + 8, ...; four loads in flight per lane
+  for (long long j0 = g; j0 <= m; j0 += 32) {
+    float4 x4[4];
+    float s4[4];
+#pragma unroll
+    for (int q4 = 0; q4 < 4; ++q4) {
+      const long long j = j0 + 8 * q4;
+      x4[q4] = make_float4(0.f, 0.f, 0.f, 0.f);
+      s4[q4] = 0.f;
+      if (j <= m && r0 + j < p.n_ranges) {
+        const FlatEntry* e = j == 0 ? &E[2 * r0 + 1] : &E[2 * (r0 + j)];
+        if (j == 0 || (e->state != 0u && e->key == key)) {
+          x4[q4] = *reinterpret_cast<const float4*>(e->v + gl * 4);
+          s4[q4] = e->gs;
+        }
+      }
+    }
+#pragma unroll
+    for (int q4 = 0; q4 < 4; ++q4) {
+      t.x += x4[q4].x; t.y += x4[q4].y; t.z += x4[q4].z; t.w += x4[q4].w;
+      ts += s4[q4];
     }
   }
 #pragma unroll
