@@ -134,6 +134,56 @@ class Embedding(_Layer):
     def sparse_tables(self):
         return [self.table]
 
+    # -- masked / weighted pooling of looked-up rows ----------------------------------
+    def sequence_pool(self, ids, weights=None, mask=None, padding_index=None, reduce: bool = True, training: bool = False):
+        """``ids`` [B, L, C] (a padded behaviour series of C feature columns, as ``tf.stack(series, axis=2)`` in
+        7.SIM/CustomLayers.py:107) -> ``sum_l w[b,l] * [embed(ids[b,l,0]) | ... | embed(ids[b,l,C-1])]`` [B, C*k]
+        (``reduce=False``: the weighted rows themselves, [B, L, C*k]); ``w = weights * mask * (ids[b,l,0] != padding_index)``,
+        each factor optional (7.SIM/CustomLayers.py:88-95,116; 5.DIN/CustomLayers.py:258-283).  One fused kernel: the
+        [B, L, C*k] tensor of the reference is never written in reduce mode."""
+        rt = self.rt
+        t = rt.to_device(ids, torch.int64).contiguous()
+        assert t.dim() == 3, "ids must be [B, L, C]"
+        B, L, C_ = t.shape
+        k = self.output_dim
+        w = rt.to_device(weights, torch.float32).contiguous() if weights is not None else None
+        m = rt.to_device(mask, torch.uint8).contiguous() if mask is not None else None
+        out = rt.empty((B, C_ * k) if reduce else (B, L, C_ * k))
+        d = self.table.desc()
+        check(rt.lib.etr_sequence_pool_forward(rt.ctx, C.byref(d), k, t.data_ptr(), B, L, C_, _p(w), _p(m),
+                                               0 if padding_index is None else int(padding_index),
+                                               0 if padding_index is None else 1, int(reduce), out.data_ptr(), rt.stream))
+        if training:
+            self._ctx = {"ids": t, "w": w, "m": m, "pad": padding_index, "reduce": reduce}
+        self._finish(training)
+        return out
+
+    def sequence_pool_backward(self, dout: torch.Tensor, need_weight_grad: bool = True):
+        """-> (SparseGrad of the table, d weights [B, L] or None)"""
+        rt = self.rt
+        c = self._ctx
+        t = c["ids"]
+        B, L, C_ = t.shape
+        k = self.output_dim
+        dout = dout.to(torch.float32).contiguous()
+        occ = rt.empty((B * L * C_, self.table.grad_ld))
+        dw = rt.empty((B, L)) if need_weight_grad else None
+        d = self.table.desc()
+        check(rt.lib.etr_sequence_pool_backward(rt.ctx, C.byref(d), k, t.data_ptr(), B, L, C_, _p(c["w"]), _p(c["m"]),
+                                                0 if c["pad"] is None else int(c["pad"]), 0 if c["pad"] is None else 1,
+                                                int(c["reduce"]), dout.data_ptr(), occ.data_ptr(), self.table.grad_ld, _p(dw),
+                                                rt.stream))
+        flat = IdsBatch(rt, t.reshape(-1, 1), B * L * C_, 1, 1, 1, 1, 1, pad_id=c["pad"])
+        return SparseGrad(self.table, flat, occ), dw
+
+    def weighted_lookup(self, keys, values, training: bool = False):
+        """FiBiNet++ continuous-feature embedding: ``embed(keys)[B,F,k] * values[B,F,None]``
+        (11.FiBiNet++/CustomLayers.py:124-126), one kernel."""
+        keys = self.rt.to_device(keys, torch.int64)
+        B, F_ = keys.shape
+        out = self.sequence_pool(keys.reshape(B, F_, 1), weights=values, reduce=False, training=training)
+        return out.reshape(B, F_, self.output_dim)
+
 
 # ---------------------------------------------------------------------------
 class FMRankingLayer(_Layer):
@@ -1208,6 +1258,10 @@ class Trainer:
         The kernels clamp and carry on, so without this a bad id would train silently on the wrong row."""
         assert apply_mode in ("rowwise", "keras_dense")
         self.poll_every, self._steps_since_poll = int(poll_every), 0
+        # 5.DIN/ModelManager.py:175-190: L2 on the rows the batch used, factor * tf.nn.l2_loss(gather(embed, unique(ids)));
+        # set ``trainer.used_rows_l2 = factor`` (the table gradients are then materialised: no fused apply)
+        self.used_rows_l2 = 0.0
+        self.last_l2 = None
         self.layer, self.lr, self.b1, self.b2, self.eps = layer, lr, beta_1, beta_2, epsilon
         self.mode = _lib.ADAM_ROWWISE if apply_mode == "rowwise" else _lib.ADAM_KERAS_DENSE
         self.rt = layer.rt
@@ -1329,8 +1383,10 @@ class Trainer:
         d_lr = self.state[1:]
         self.layer.params.adam_step(0.0, d_lr, self.b1, self.b2, self.eps)
         plans: Dict[tuple, SparsePlan] = {}
+        if self.used_rows_l2:
+            self.last_l2 = rt.zeros((1,))
         for g in grads:
-            if isinstance(g, FusedFMGrad) and self.mode == _lib.ADAM_ROWWISE:
+            if isinstance(g, FusedFMGrad) and self.mode == _lib.ADAM_ROWWISE and not self.used_rows_l2:
                 g.apply(d_lr, self.b1, self.b2, self.eps)
                 continue
             if hasattr(g, "push"):                    # PeerFMGrad: owner-side mailbox reduce + Adam
@@ -1340,6 +1396,10 @@ class Trainer:
             g.reduce(plans.get(key))
             plans[key] = g.plan
             t = g.table.desc()
+            if self.used_rows_l2:
+                check(rt.lib.etr_used_rows_l2(rt.ctx, C.byref(t), g.plan.unique_ids.data_ptr(), g.plan.counts.data_ptr(),
+                                              g.plan.n_slots, float(self.used_rows_l2), g.unique_grad.data_ptr(),
+                                              g.unique_grad.shape[1], self.last_l2.data_ptr(), rt.stream))
             check(rt.lib.etr_sparse_adam_apply(rt.ctx, C.byref(t), g.table.m.data_ptr(), g.table.v.data_ptr(),
                                                g.plan.unique_ids.data_ptr(), g.plan.counts.data_ptr(),
                                                g.plan.n_slots, g.unique_grad.data_ptr(), g.unique_grad.shape[1],

@@ -124,6 +124,9 @@ PROTOTYPES = {
     "etr_peer_allreduce_sum": (C.c_int, [_vp, _vp, _i64, _i32, _vp, _vp]),
     "etr_shard_partition": (C.c_int, [_vp, _vp, _i64, _i32, _i64, _vp, _vp, _vp, _vp, _vp]),
     "etr_cross_mat_bwd_elementwise": (C.c_int, [_vp, _vp, _vp, _vp, _i64, _vp, _vp, _vp]),
+    "etr_used_rows_l2": (C.c_int, [_vp, _T, _vp, _vp, _i64, _f32, _vp, _i32, _vp, _vp]),
+    "etr_sequence_pool_forward": (C.c_int, [_vp, _T, _i32, _vp, _i64, _i32, _i32, _vp, _vp, _i64, _i32, _i32, _vp, _vp]),
+    "etr_sequence_pool_backward": (C.c_int, [_vp, _T, _i32, _vp, _i64, _i32, _i32, _vp, _vp, _i64, _i32, _i32, _vp, _vp, _i32, _vp, _vp]),
     "etr_tfrecord_parse": (C.c_int, [_vp, _i64, _i32, C.POINTER(C.c_char_p), C.POINTER(_i32), C.POINTER(_i32), C.POINTER(_vp),
                                      _i64, _i32, C.POINTER(_i64), C.POINTER(_i64)]),
 }

@@ -306,6 +306,37 @@ __global__ void __launch_bounds__(256) sparse_adam_kernel(const AdamParams p) {
   }
 }
 
+// used-rows L2 (5.DIN/ModelManager.py:175-190): l2 = factor * 0.5 * sum_{u in unique(batch ids)} |row_u|^2 ; grad_u += factor * row_u
+__global__ void __launch_bounds__(256) used_rows_l2_kernel(const char* table, int bf16, int stride, int width, const long long* unique_ids,
+                                                           const int* n_unique, float factor, float* grad, int grad_ld, float* rowsq) {
+  const int n = *n_unique;
+  for (int u = blockIdx.x * blockDim.x + threadIdx.x; u < n; u += gridDim.x * blockDim.x) {
+    const long long row = unique_ids[u];
+    float s = 0.f;
+    for (int c = 0; c < width; ++c) {
+      const float x = bf16 ? __bfloat162float(reinterpret_cast<const __nv_bfloat16*>(table)[row * stride + c])
+                           : reinterpret_cast<const float*>(table)[row * stride + c];
+      s += x * x;
+      grad[(long long)u * grad_ld + c] += factor * x;
+    }
+    rowsq[u] = s;
+  }
+}
+// fixed-order sum (one block, strided partials then a serial tail): deterministic
+__global__ void __launch_bounds__(1024) used_rows_l2_finish_kernel(const float* rowsq, const int* n_unique, float factor, float* loss_accum) {
+  __shared__ float part[1024];
+  const int n = *n_unique;
+  float s = 0.f;
+  for (int u = threadIdx.x; u < n; u += 1024) s += rowsq[u];
+  part[threadIdx.x] = s;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float t = 0.f;
+    for (int i = 0; i < 1024; ++i) t += part[i];
+    *loss_accum += 0.5f * factor * t;
+  }
+}
+
 // keras_dense passes over the whole table: rows x (rc 16-byte chunks of meaningful columns); row stride in
 // floats (== 4*rc for a plain table: one flat pass; 64 for a RECORD table whose m / v sit inside the record)
 __global__ void __launch_bounds__(256) dense_decay_kernel(float* m, float* v, long long rows, int rc, int stride, float b1,
@@ -540,6 +571,24 @@ int etr_sparse_adam_apply(etr_ctx* ctx, const etr_table* table, float* d_m, floa
                                                lr_t, d_lr_t, eps);
     ETR_LAUNCH_CHECK(ctx);
   }
+  return ETR_OK;
+}
+
+int etr_used_rows_l2(etr_ctx* ctx, const etr_table* table, const int64_t* d_unique_ids, const int32_t* d_n_unique,
+                     int64_t max_unique, float factor, float* d_unique_grad, int32_t grad_ld, float* d_loss_accum, void* stream) {
+  ETR_CHECK_ARG(ctx && table && table->d_data && d_unique_ids && d_n_unique && d_unique_grad && d_loss_accum, "NULL argument");
+  ETR_CHECK_ARG(grad_ld >= table->width, "grad_ld too small");
+  if (max_unique <= 0) return ETR_OK;
+  cudaStream_t s = (cudaStream_t)stream;
+  int st = etr_ws_reserve(ctx, (size_t)max_unique * sizeof(float));
+  if (st != ETR_OK) return st;
+  float* rowsq = (float*)ctx->d_ws;
+  used_rows_l2_kernel<<<grid_for(max_unique, 256, ctx->sm_count, 8), 256, 0, s>>>(
+      (const char*)table->d_data, table->dtype == ETR_BF16, table->stride, table->width, (const long long*)d_unique_ids, d_n_unique,
+      factor, d_unique_grad, grad_ld, rowsq);
+  ETR_LAUNCH_CHECK(ctx);
+  used_rows_l2_finish_kernel<<<1, 1024, 0, s>>>(rowsq, d_n_unique, factor, d_loss_accum);
+  ETR_LAUNCH_CHECK(ctx);
   return ETR_OK;
 }
 

@@ -232,6 +232,12 @@ int etr_fm_fused_flat_apply(etr_ctx* ctx, const etr_table* table, int32_t k, int
                             const void* d_dflat, int32_t flat_dtype, int64_t flat_ld, int32_t flat_col0,
                             float lr_t, const float* d_lr_t, float beta1, float beta2, float eps, void* stream);
 
+/* L2 on the rows a batch USED (5.DIN/ModelManager.py:175-190: tf.unique over every id of the batch, tf.gather,
+ * tf.nn.l2_loss * factor added to the loss): adds factor * row_u to the de-duplicated gradient row of every unique id and
+ * factor * 0.5 * sum_u |row_u|^2 to *d_loss_accum (fixed-order sum).  Falls out of the sorted-unique list of the plan.   */
+int etr_used_rows_l2(etr_ctx* ctx, const etr_table* table, const int64_t* d_unique_ids, const int32_t* d_n_unique,
+                     int64_t max_unique, float factor, float* d_unique_grad, int32_t grad_ld, float* d_loss_accum, void* stream);
+
 /* Dense Adam for the small replicated variables (bias, MLP, cross W/b).      */
 int etr_dense_adam_apply(etr_ctx* ctx, float* d_var, float* d_m, float* d_v, const float* d_grad,
                          int64_t n, float lr_t, const float* d_lr_t, float beta1, float beta2, float eps,
@@ -498,6 +504,22 @@ int etr_peer_barrier(etr_ctx* ctx, uint32_t* const* h_peer_flags, uint32_t* d_my
 int etr_peer_allreduce_push(etr_ctx* ctx, const float* d_src, int64_t n, float* const* h_peer_slots, int32_t world,
                             int32_t rank, void* stream);
 int etr_peer_allreduce_sum(etr_ctx* ctx, const float* d_slots, int64_t n, int32_t world, float* d_dst, void* stream);
+
+/* ------------------------- masked / weighted pooling behind the Embedding drop-in
+ * ids [B, L, C] int64 (a padded behaviour series of C feature columns; FiBiNet++'s weighted lookup is L = F, C = 1):
+ *   w[b,l]  = (d_weights ? d_weights[b,l] : 1) * (d_mask ? d_mask[b,l] != 0 : 1) * (has_pad ? ids[b,l,0] != pad_id : 1)
+ *   reduce != 0:  out[b, c*k ..]    = sum_l w[b,l] * table[ids[b,l,c], 0:k]     [B, C*k]     7.SIM/CustomLayers.py:88-95,107-118
+ *   reduce == 0:  out[b, l, c*k ..] =       w[b,l] * table[ids[b,l,c], 0:k]     [B, L, C*k]  11.FiBiNet++/CustomLayers.py:124-126
+ * rows are fetched once (128-bit loads), [B, L, C*k] is never materialised in reduce mode.  Backward: d_occ_grad
+ * [B*L*C, grad_ld] = w * dOut (one gradient row per looked-up id, table column layout) and d_dweights [B, L] =
+ * mask * sum_c <dOut, row> (the gradient of the attention scores); either may be NULL.                          */
+int etr_sequence_pool_forward(etr_ctx* ctx, const etr_table* table, int32_t k, const int64_t* d_ids, int64_t batch, int32_t L,
+                              int32_t C, const float* d_weights, const uint8_t* d_mask, int64_t pad_id, int32_t has_pad,
+                              int32_t reduce, float* d_out, void* stream);
+int etr_sequence_pool_backward(etr_ctx* ctx, const etr_table* table, int32_t k, const int64_t* d_ids, int64_t batch, int32_t L,
+                               int32_t C, const float* d_weights, const uint8_t* d_mask, int64_t pad_id, int32_t has_pad,
+                               int32_t reduce, const float* d_dout, float* d_occ_grad, int32_t grad_ld, float* d_dweights,
+                               void* stream);
 
 /* ------------------------------------------------ input side (host code, no kernel)
  * TFRecord frames of serialized tf.train.Example -> column arrays; replaces tf.data.TFRecordDataset +

@@ -673,6 +673,34 @@ def onn_loop_combined(embed_single: Tensor, pair_tables, X: Tensor, reduce: bool
 
 
 # --------------------------------------------------------------------------
+# f1: masked / weighted pooling of a padded behaviour series; f3: used-rows L2
+# --------------------------------------------------------------------------
+def sequence_pool(table: Tensor, ids: Tensor, weights: Optional[Tensor] = None, mask: Optional[Tensor] = None,
+                  padding_index: Optional[int] = None, reduce: bool = True) -> Tensor:
+    """7.SIM/CustomLayers.py:107-118 + :88-95: X_series = embed(reshape(ids, [B, L*C])) reshaped to [B, L, C*k];
+    valid_mask = ids[:, :, 0] != padding_index; pooled = einsum('bl,ble->be', scores * mask, X_series).
+    ``reduce=False`` returns the weighted [B, L, C*k] rows (FiBiNet++'s embed(keys) * values[..., None] is L = F, C = 1)."""
+    B, L, C = ids.shape
+    x = embedding_lookup(table, ids.reshape(B, L * C)).reshape(B, L, C * table.shape[1])
+    w = torch.ones((B, L), dtype=table.dtype)
+    if weights is not None:
+        w = w * weights
+    if mask is not None:
+        w = w * mask.to(table.dtype)
+    if padding_index is not None:
+        w = w * (ids[:, :, 0] != padding_index).to(table.dtype)
+    if reduce:
+        return torch.einsum("bl,ble->be", w, x)
+    return x * w.unsqueeze(-1)
+
+
+def used_rows_l2(table: Tensor, all_ids: Tensor, factor: float) -> Tensor:
+    """5.DIN/ModelManager.py:185-190: tf.unique over every id of the batch, gather, tf.nn.l2_loss (= sum(x^2)/2) * factor."""
+    uniq = torch.unique(all_ids.reshape(-1))
+    return factor * 0.5 * torch.sum(torch.square(table[uniq]))
+
+
+# --------------------------------------------------------------------------
 # a16: loss, backward, IndexedSlices dedup, Adam     2.FM/ModelManager.py:99-104,171-181
 # --------------------------------------------------------------------------
 KERAS_EPS = 1e-7

