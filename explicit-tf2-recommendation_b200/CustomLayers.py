@@ -99,6 +99,30 @@ class _Layer:
     def sparse_tables(self) -> List[EmbeddingTable]:
         return []
 
+    # -- row-sharded tables, all-to-all form: shared by every model layer ------------------
+    def _make_table(self, rows: int, width: int, record: bool = False) -> EmbeddingTable:
+        """the layer's embedding table: plain, or -- ``shard=`` -- this rank's rows r, r+G, r+2G, ... of it"""
+        if self.shard_spec and self.shard_mode == "a2a":
+            from .sharded import ShardedTable
+            self.shard = ShardedTable(self.rt, rows, width, self.shard_spec[0], self.shard_spec[1], self.table_dtype)
+            return self.shard.local
+        assert not self.shard_spec, f"{type(self).__name__}: row-sharded tables use the all-to-all form (shard='a2a')"
+        return EmbeddingTable(self.rt, rows, width, self.table_dtype, record=record)
+
+    def _lookup(self, ids: IdsBatch):
+        """(table, ids, route): the local table, or -- row-sharded -- the rows fetched over
+        the all-to-all presented as a virtual table indexed by the inverse permutation."""
+        if self.shard is None:
+            return self.table, ids, None
+        return self.shard.lookup(ids)
+
+    def _table_grad(self, bag: torch.Tensor) -> SparseGrad:
+        if self.shard is None:
+            sg = SparseGrad(self.table, self._ctx["ids"], bag)
+            sg.plan = self._ctx.get("plan")          # an overlapped plan started at forward time, if any
+            return sg
+        return self.shard.sparse_grad(self._ctx["route"], bag)
+
 
 def _cont_matrix(rt: Runtime, inputs, names: Sequence[str]) -> torch.Tensor:
     """continuous dict -> X_cont [B,C] fp32 (3.DCN/CustomLayers.py:248-254)."""
@@ -274,25 +298,11 @@ class FMRankingLayer(_Layer):
             return self.rt.empty((vids.B, self.embedding_dims))
         return None
 
-    def _lookup(self, ids: IdsBatch):
-        """(table, ids, route): the local table, or -- row-sharded -- the rows fetched over
-        the all-to-all presented as a virtual table indexed by the inverse permutation."""
-        if self.shard is None:
-            return self.table, ids, None
-        return self.shard.lookup(ids)
-
     def _fused_grad(self, fused: FusedFMGrad):
         if self.peer is None:
             return fused
         from .sharded import PeerFMGrad
         return PeerFMGrad(self.peer, fused)
-
-    def _table_grad(self, bag: torch.Tensor) -> SparseGrad:
-        if self.shard is None:
-            sg = SparseGrad(self.table, self._ctx["ids"], bag)
-            sg.plan = self._ctx.get("plan")          # an overlapped plan started at forward time, if any
-            return sg
-        return self.shard.sparse_grad(self._ctx["route"], bag)
 
     def backward(self, dlogit: torch.Tensor) -> List[SparseGrad]:
         """dlogit = dL/dz [B] (z the pre-sigmoid logit).  Dense grads land in
@@ -705,7 +715,7 @@ class PNNRankingLayer(_Layer):
         self.kernel_type = "inner" if method == "inner" else (kernel_type or "mat")
         F, k = self.fields_cnt, self.embedding_dims
         self.P = F * (F - 1) // 2
-        self.table = EmbeddingTable(self.rt, self.feature_dims, k, self.table_dtype)
+        self.table = self._make_table(self.feature_dims, k)
         self.table.init_uniform(-0.05, 0.05, self.gen)
         if method == "outer":
             shape = {"mat": (k, self.P, k), "vec": (self.P, k), "num": (self.P, 1)}[self.kernel_type]
@@ -732,12 +742,13 @@ class PNNRankingLayer(_Layer):
         ids = self._ids(inputs, self.feature_names)
         F, k, P = self.fields_cnt, self.embedding_dims, self.P
         comb = rt.empty((ids.B, F * k + P))                        # concat fused: [Flatten(emb) | product]
-        gather_fm_forward(self.table, k, False, ids, flat=comb, flat_col0=0)
+        tab, vids, route = self._lookup(ids)
+        gather_fm_forward(tab, k, False, vids, flat=comb, flat_col0=0)
         check(rt.lib.etr_pnn_forward(rt.ctx, comb.data_ptr(), F * k + P, ids.B, F, k, _PNN_TYPE[self.kernel_type],
                                      _p(self.pn_kernel), comb[:, F * k:].data_ptr(), F * k + P, rt.stream))
         out = self.MLP_layer2(self.MLP_layer1(comb, training=training), training=training)
         if training:
-            self._ctx = {"ids": ids, "comb": comb}
+            self._ctx = {"ids": vids, "comb": comb, "table": tab, "route": route}
         self._finish(training)
         return {"output": out}
 
@@ -755,8 +766,8 @@ class PNNRankingLayer(_Layer):
         check(rt.lib.etr_pnn_backward(rt.ctx, comb.data_ptr(), F * k + P, ids.B, F, k, _PNN_TYPE[self.kernel_type],
                                       _p(self.pn_kernel), dcomb[:, F * k:].data_ptr(), F * k + P, dcomb.data_ptr(),
                                       F * k + P, _p(dk), rt.stream))
-        bag = gather_fm_backward(self.table, k, False, ids, dflat=dcomb, flat_col0=0)
-        return [SparseGrad(self.table, ids, bag)]
+        bag = gather_fm_backward(self._ctx["table"], k, False, ids, dflat=dcomb, flat_col0=0)
+        return [self._table_grad(bag)]
 
 
 PNNLayer = PNNRankingLayer
@@ -1188,7 +1199,7 @@ class DeepCrossNetworkLayer(_Layer):
         self.front_pad = (-C_) % (8 if precision == "bf16" else 4)
         if precision == "bf16":
             assert (F * k) % 8 == 0 and self.units[-1] % 8 == 0, "bf16 DCN: F*k and units[-1] must be multiples of 8"
-        self.embedding_layer = self.table = EmbeddingTable(self.rt, self.feature_dims, k, self.table_dtype)
+        self.embedding_layer = self.table = self._make_table(self.feature_dims, k)
         self.table.init_uniform(-0.05, 0.05, self.gen)
         cls = CrossLayer if type == 'vec' else MatrixCrossLayer
         self.cross_layer = cls(layer_num, reg_w, reg_b, precision=precision, device=self.rt.device)
@@ -1214,14 +1225,15 @@ class DeepCrossNetworkLayer(_Layer):
         dt = torch.bfloat16 if self.precision == "bf16" else torch.float32
         x = rt.empty((ids.B, Di), dt)                           # [pad | X_cont | Flatten(emb)]
         cont = self._cont(inputs, self.continuous_features) if C_ else None
-        gather_fm_forward(self.table, k, False, ids, flat=x, flat_col0=self.front_pad + C_, cont=cont)
+        tab, vids, route = self._lookup(ids)
+        gather_fm_forward(tab, k, False, vids, flat=x, flat_col0=self.front_pad + C_, cont=cont)
         comb = rt.empty((ids.B, Di + self.units[-1]), dt)       # concat fused: [cross_output | dnn_output]
         self.cross_layer.call(x, training=training, out=comb[:, :Di])
         dnn = self.dense_layer(x, training=training)
         comb[:, Di:] = dnn
         out = self.output_layer(comb, training=training)
         if training:
-            self._ctx = {"ids": ids}
+            self._ctx = {"ids": vids, "table": tab, "route": route}
         self._finish(training)
         return {"output": out}
 
@@ -1234,9 +1246,9 @@ class DeepCrossNetworkLayer(_Layer):
         dx = self.cross_layer.backward(dcomb[:, :Di])                       # [B, Di] fp32
         ddnn = dcomb[:, Di:].float().contiguous()
         self.dense_layer.backward(ddnn, accumulate_into=dx)
-        bag = gather_fm_backward(self.table, self.embedding_dims, False, ids, dflat=dx,
+        bag = gather_fm_backward(self._ctx["table"], self.embedding_dims, False, ids, dflat=dx,
                                  flat_col0=self.front_pad + len(self.continuous_features))
-        return [SparseGrad(self.table, ids, bag)]
+        return [self._table_grad(bag)]
 
 
 # ---------------------------------------------------------------------------

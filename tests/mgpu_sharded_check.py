@@ -100,6 +100,53 @@ def main():
             assert torch.equal(ref, sharded.params.value), f"rank {rank}: dense replicas diverged"
         dist.barrier()
         msgs.append(f"{mode}{'+graph' if graph else ''}/{prec}: table_err={err_t:.2e} dense_err={err_d:.2e}")
+    # every other model family that gathers from one shared table: all-to-all form (DCN vector / matrix cross, PNN)
+    for model in ("dcn_vec", "dcn_matrix", "pnn"):
+        Fm, Vm, Bm = 10, 60013, 1024
+        nm, cm = [f"f{i}" for i in range(Fm)], [f"c{i}" for i in range(3)]
+
+        def make(shard):
+            if model == "pnn":
+                return L.PNNRankingLayer(nm, Vm, k, seed=4, shard=shard, check_ids=False)
+            return L.DeepCrossNetworkLayer(nm, cm, feature_dims=Vm, embedding_dims=k, type="vec" if model == "dcn_vec" else "matrix",
+                                           seed=4, shard=shard, check_ids=False)
+
+        sharded, full = make("a2a"), make(None)
+        g = torch.Generator(device="cuda").manual_seed(77)
+        table = torch.empty(Vm, k, device="cuda").uniform_(-0.05, 0.05, generator=g)
+        full.table.data[:, :k] = table
+        sharded.shard.load_global(table)
+        sharded.params.value.copy_(full.params.value)
+        torch.cuda.synchronize()
+        dist.barrier()
+        rng = np.random.default_rng(20 + rank)
+        tr_s, tr_f = L.Trainer(sharded, lr=1e-2), L.Trainer(full, lr=1e-2)
+        for step in range(3):
+            X = (rng.random((Bm, Fm)) ** 3 * Vm).astype(np.int64)
+            Xc = rng.normal(size=(Bm, 3)).astype(np.float32)
+            y = torch.tensor((rng.random(Bm) < 0.3).astype(np.float32)).cuda()
+            d = {n: torch.tensor(X[:, i]).cuda() for i, n in enumerate(nm)}
+            if model != "pnn":
+                d.update({n: torch.tensor(Xc[:, i]).cuda() for i, n in enumerate(cm)})
+            if step == 0:
+                assert torch.equal(sharded(d)["output"], full(d)["output"]), f"rank {rank} {model}: forward not bit-exact"
+            ls = tr_s.train_step(d, y).clone()
+            gd = {}
+            for n, t in d.items():
+                parts = [torch.empty_like(t) for _ in range(world)]
+                dist.all_gather(parts, t)
+                gd[n] = torch.cat(parts)
+            ys = [torch.empty_like(y) for _ in range(world)]
+            dist.all_gather(ys, y)
+            lf = tr_f.train_step(gd, torch.cat(ys))
+            dist.all_reduce(ls)
+            assert abs(float(ls.item()) / world - float(lf.item())) < 1e-5, (model, step)
+        mine = full.table.data[rank::world, :k]
+        err_t = (sharded.table.data[: mine.shape[0], :k] - mine).abs().max().item()
+        err_d = (sharded.params.value - full.params.value).abs().max().item()
+        assert err_t < 2e-5 and err_d < 2e-5, (model, rank, err_t, err_d)
+        dist.barrier()
+        msgs.append(f"{model}/a2a: table_err={err_t:.2e} dense_err={err_d:.2e}")
     if rank == 0:
         print(f"MGPU_OK world={world} " + " | ".join(msgs))
     dist.destroy_process_group()

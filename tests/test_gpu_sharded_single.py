@@ -73,3 +73,37 @@ def test_peer_barrier_and_allreduce_world1(L):
         T.allreduce_sum(v)
     rt.poll_error()
     assert torch.equal(v, ref) and int(T._epoch.item()) == 3
+
+
+@pytest.mark.parametrize("model", ["dcn_vec", "dcn_matrix", "pnn", "fm"])
+def test_a2a_sharded_world1_equals_unsharded(L, model):
+    """row-sharded tables (all-to-all form) for every model family that gathers from one table: at world 1 the route is
+    the identity, so forward is bit-exact and 3 train steps give the same weights as the unsharded layer."""
+    F, k, V, C_, B = 10, 16, 6007, 3, 512
+    names, cont = [f"f{i}" for i in range(F)], [f"c{i}" for i in range(C_)]
+
+    def make(shard):
+        if model.startswith("dcn"):
+            return L.DeepCrossNetworkLayer(names, cont, feature_dims=V, embedding_dims=k, type="vec" if model == "dcn_vec" else "matrix",
+                                           seed=5, shard=shard, check_ids=False)
+        if model == "pnn":
+            return L.PNNRankingLayer(names, V, k, seed=5, shard=shard, check_ids=False)
+        return L.FMRankingLayer(names, V, k, seed=5, shard=shard, check_ids=False)
+
+    sh, full = make((1, 0)), make(None)
+    assert sh.shard is not None and full.shard is None
+    sh.shard.load_global(full.table.data[:, : full.table.width])
+    sh.params.value.copy_(full.params.value)
+    tr_s, tr_f = L.Trainer(sh, lr=1e-2), L.Trainer(full, lr=1e-2)
+    for step, (X, Xc, y) in enumerate(_batches(3, B, F, C_, V, 5)):
+        d = {n: torch.tensor(X[:, i]).cuda() for i, n in enumerate(names)}
+        if model.startswith("dcn"):
+            d.update({n: torch.tensor(Xc[:, i]).cuda() for i, n in enumerate(cont)})
+        if step == 0:
+            assert torch.equal(sh(d)["output"], full(d)["output"])
+        ls = float(tr_s.train_step(d, torch.tensor(y).cuda()).item())
+        lf = float(tr_f.train_step(d, torch.tensor(y).cuda()).item())
+        assert abs(ls - lf) < 1e-5, (step, ls, lf)
+    w = full.table.width
+    assert (sh.table.data[:V, :w] - full.table.data[:, :w]).abs().max().item() < 2e-5
+    assert (sh.params.value - full.params.value).abs().max().item() < 2e-5
