@@ -264,24 +264,37 @@ def run_c3(args):
     """BASELINE configs[2]: DCN-matrix (3 cross layers, k=64 -> D = 13 + 26*64 = 1677) + DenseLayer [64,8] +
     Dense(1), bf16 tensor-core cross (tcgen05), batch 65 536, train step fwd+bwd+row-wise Adam."""
     import torch
-    import etr_b200  # noqa: F401
-    from etr_b200 import CustomLayers as L
+    import torch.distributed as dist
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
     dev = torch.device("cuda", int(os.environ.get("LOCAL_RANK", "0")))
     torch.cuda.set_device(dev)
+    if world > 1:
+        if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION", "WARN"):
+            os.environ["NCCL_DEBUG"] = "NONE"
+        dist.init_process_group("nccl", device_id=dev)
+    import etr_b200  # noqa: F401
+    from etr_b200 import CustomLayers as L
     B, K3, LAYERS = args.batch, 64, 3
     V = int(sum(CRITEO_CARDS))
     names = [f"C{i + 1}" for i in range(F)]
     cont = [f"I{i + 1}" for i in range(C_DENSE)]
+    # N > 1 (BASELINE configs[2] is 1/2/4/8 x B200): batch data-parallel (weak scaling, 65 536 samples per GPU), the table
+    # row-sharded with the NCCL all-to-all exchange (ids out, rows back; gradient rows to the owners), cross / tower
+    # weights replicated and all-reduced -- the cross GEMMs are per-sample work and do not communicate
     layer = L.DeepCrossNetworkLayer(names, cont, feature_dims=V, embedding_dims=K3, units=[64, 8], layer_num=LAYERS,
-                                    type="matrix", precision="bf16", check_ids=False, seed=1)
+                                    type="matrix", precision="bf16", check_ids=False, seed=1,
+                                    shard=("a2a" if world > 1 else None))
     rt = layer.rt
-    host = make_batches(3, B, args.dist, seed=SEED + 1)
+    host = make_batches(3, B, args.dist, seed=SEED + 1 + 17 * rank)
     dev_batches = [(torch.from_numpy(np.ascontiguousarray(X.T)).to(dev),
                     torch.from_numpy(np.ascontiguousarray(Xc.T)).to(dev), torch.from_numpy(y).to(dev))
                    for X, Xc, y in host]
-    use_graph = not args.no_graph
+    use_graph = (not args.no_graph) and world == 1          # the all-to-all exchange reads split sizes on the host
     trainer = L.Trainer(layer, lr=1e-3, graph=use_graph)
     flush = torch.empty(512 << 20, dtype=torch.uint8, device=dev)
+    clocks = ClockSampler(dev.index, getattr(torch.cuda.get_device_properties(dev), "uuid", None))
+    clocks.start()
 
     def stage(i):
         ids, xc, y = dev_batches[i % 3]
@@ -290,8 +303,9 @@ def run_c3(args):
     for i in range(max(args.warmup, 8 if use_graph else 3)):
         trainer.train_step(stage(i))
     torch.cuda.synchronize(dev)
-    clocks = ClockSampler(dev.index)
-    clocks.start()
+    if world > 1:
+        dist.barrier()
+    clocks.busy(True)
     l0 = rt.launches
     ev = []
     for i in range(args.steps):
@@ -304,9 +318,13 @@ def run_c3(args):
         e.record()
         ev.append((a, e))
     torch.cuda.synchronize(dev)
-    clk = clocks.stop()
+    clocks.busy(False)
     ms = [a.elapsed_time(e) for a, e in ev]
     total = sum(ms)
+    if world > 1:
+        t_ = torch.tensor([total], device=dev, dtype=torch.float64)
+        dist.all_reduce(t_, op=dist.ReduceOp.MAX)
+        total = float(t_[0])
     # one cross layer forward timed alone (the dominant tensor kernel)
     import ctypes as C
     from etr_b200._lib import check
@@ -328,6 +346,10 @@ def run_c3(args):
         kt.append((a, e))
     torch.cuda.synchronize(dev)
     k_ms = statistics.mean(a.elapsed_time(e) for a, e in kt[2:])
+    clk = clocks.stop()
+    if rank != 0:
+        dist.destroy_process_group()
+        return
     D = layer.D
     flops = 2.0 * B * D * D                                    # unpadded D = 1677
     peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json"))) if os.path.exists(
@@ -336,12 +358,14 @@ def run_c3(args):
     ach = flops / (k_ms * 1e-3) / 1e12
     step_flops = 3.0 * LAYERS * flops                          # fwd + dgrad + wgrad of the cross layers
     line = {
-        "metric": "train samples/sec DCN-matrix (Criteo-shape)", "value": B * args.steps / (total * 1e-3),
-        "unit": "samples/s", "n_gpus": 1, "steps": args.steps, "warmup": args.warmup,
+        "metric": "train samples/sec DCN-matrix (Criteo-shape)", "value": B * world * args.steps / (total * 1e-3),
+        "unit": "samples/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": total / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "bf16 tensor-core cross / dense GEMMs (fp32 accumulate), fp32 tables + Adam", "data": "synthetic",
         "config": {"workload": "c3: DCN-matrix train step, 13 dense + 26 sparse (k=64, D=1677), 3 cross layers, "
-                               "DenseLayer [64,8], Dense(1); 33 762 577-row table", "global_batch": B,
+                               "DenseLayer [64,8], Dense(1); 33 762 577-row table", "global_batch": B * world, "per_gpu_batch": B,
+                   "parallelism": "dp1" if world == 1 else f"dp{world} batch x row-sharded table (id mod {world}), NCCL all-to-all exchange; "
+                                  "cross / tower weights replicated, gradients all-reduced",
                    "id_distribution": args.dist, "cuda_graph": use_graph, "l2": "L2 flushed before every timed step",
                    "apply_mode": "rowwise Adam"},
         "clocks": clk, "gpu_launches": rt.launches - l0,
@@ -553,6 +577,8 @@ def run_c4(args):
                               "algorithmic_bytes_per_launch": alg,
                               "note": "F*k*4 + 8 = 1 256 B per looked-up id (SURVEY 8d) x the valid ids of one batch + 4 B/sample out"}})
     print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
 
 
 def ncu_traffic(kernel_substr: str):

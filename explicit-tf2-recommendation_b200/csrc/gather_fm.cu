@@ -619,6 +619,108 @@ __global__ void __launch_bounds__(256, 3) gather_fm_fwd_tile_kernel(const Gather
   }
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// Lean form of the tiled forward kernel for the FM family's hot configuration (round 2): fp32 rows, k = 16 with the
+// fused w column at 16, single-hot ids, no padding, local table.  The generic tiled kernel above re-evaluates every
+// option of GatherParams per row (ncu, r01_prof_gather_fwd: 26.4 M warp instructions for 1.70 M rows = 15.5 per row,
+// of which IMAD 20.8 %, ISETP 19.2 %, BRA 8.4 % and only LDG 2.8 %, FADD + FFMA 7.7 %: it is ISSUE-bound at 45 % of
+// the issue slots with 6 warps per scheduler, not memory-bound).  Here everything that does not depend on the row is
+// a template parameter or hoisted out of the field loop: per row a thread executes one shared-memory id read, a range
+// check, one 64-bit multiply-add, one 128-bit load (lane 0: + the 4-byte w), 4 FADD + 4 FFMA, and (FLAT) two packs + one
+// 8-byte store.  FLAT: 0 no flattened operand, 1 bf16, 2 fp32.
+template <int FLAT, int OCC>
+__global__ void __launch_bounds__(256, OCC) gather_fm_fwd_lean_kernel(const GatherParams p) {
+  constexpr int SPB = 64, U = 8;
+  extern __shared__ __align__(16) long long ids_s[];          // [2][SPB * F]
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int c = lane & 3, g = lane >> 2;
+  const int sl = warp * 8 + g;
+  const int F = p.F;
+  const long long ntiles = (p.B + SPB - 1) / SPB;
+  const unsigned long long rows = (unsigned long long)p.rows;
+  const long long row_bytes = p.row_bytes;
+  const char* const tbase = p.table + c * 16;
+  const float bias = p.bias ? p.bias[0] : 0.f;
+  int buf = 0;
+  long long tile = blockIdx.x;
+  if (tile < ntiles) stage_ids_tile<SPB>(p, tile, ids_s);
+  cp_async_commit();
+  cp_async_wait_all();
+  __syncthreads();
+  for (; tile < ntiles; tile += gridDim.x) {
+    const long long next = tile + gridDim.x;
+    if (next < ntiles) stage_ids_tile<SPB>(p, next, ids_s + (buf ^ 1) * SPB * F);
+    cp_async_commit();
+
+    const long long b = tile * SPB + sl;
+    const bool active = b < p.B;
+    const long long* my = ids_s + buf * SPB * F + sl * F;
+    float4 S = make_float4(0.f, 0.f, 0.f, 0.f), Q = make_float4(0.f, 0.f, 0.f, 0.f);
+    float wsum = 0.f;
+    if (active) {
+      if (p.fill_front) {
+        const int z = p.flat_col0 - p.cont_n;
+        for (int j = c; j < p.flat_col0; j += 4) {
+          const float v = (j < z) ? 0.f : p.cont[b * p.cont_sb + (long long)(j - z) * p.cont_sc];
+          if (FLAT == 1) reinterpret_cast<__nv_bfloat16*>(p.flat)[b * p.flat_ld + j] = __float2bfloat16_rn(v);
+          else if (FLAT == 2) reinterpret_cast<float*>(p.flat)[b * p.flat_ld + j] = v;
+        }
+      }
+      // this lane's 4 columns of field 0 in the flattened operand; field f is 16 elements further
+      char* const obase = FLAT == 1 ? reinterpret_cast<char*>(reinterpret_cast<__nv_bfloat16*>(p.flat) + b * p.flat_ld + p.flat_col0 + c * 4)
+                                    : reinterpret_cast<char*>(reinterpret_cast<float*>(p.flat) + b * p.flat_ld + p.flat_col0 + c * 4);
+      for (int f0 = 0; f0 < F; f0 += U) {
+        float4 r[U];
+        float wv[U];
+        const int nu = F - f0 < U ? F - f0 : U;
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+          r[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+          wv[u] = 0.f;
+          if (u < nu) {
+            const unsigned long long id = (unsigned long long)my[f0 + u];
+            if (id < rows) {
+              const char* rp = tbase + id * row_bytes;
+              r[u] = ldg_row16(rp);
+              if (c == 0) wv[u] = __ldg(reinterpret_cast<const float*>(rp) + 16);
+            } else {
+              flag_bad_id(p.err, (long long)id);
+            }
+          }
+        }
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+          if (u < nu) {
+            S.x += r[u].x; S.y += r[u].y; S.z += r[u].z; S.w += r[u].w;
+            Q.x += r[u].x * r[u].x; Q.y += r[u].y * r[u].y; Q.z += r[u].z * r[u].z; Q.w += r[u].w * r[u].w;
+            wsum += wv[u];
+            if (FLAT == 1) {
+              const __nv_bfloat162 lo = __floats2bfloat162_rn(r[u].x, r[u].y), hi = __floats2bfloat162_rn(r[u].z, r[u].w);
+              uint2 w2;
+              w2.x = *reinterpret_cast<const uint32_t*>(&lo);
+              w2.y = *reinterpret_cast<const uint32_t*>(&hi);
+              *reinterpret_cast<uint2*>(obase + (f0 + u) * 32) = w2;
+            } else if (FLAT == 2) {
+              stg_stream16(obase + (f0 + u) * 64, r[u]);
+            }
+          }
+        }
+      }
+      if (p.sumv) *reinterpret_cast<float4*>(p.sumv + b * 16 + c * 4) = S;
+    }
+    float second = (S.x * S.x - Q.x) + (S.y * S.y - Q.y) + (S.z * S.z - Q.z) + (S.w * S.w - Q.w);
+    second = group_sum<4>(second);
+    if (c == 0 && active) {
+      const float z = (bias + wsum) + 0.5f * second;
+      if (p.logit) p.logit[b] = z;
+      if (p.prob) p.prob[b] = sigmoidf_exact(z);
+    }
+    cp_async_wait_all();
+    __syncthreads();
+    buf ^= 1;
+  }
+}
+
 template <typename Elem, int LPR>
 __global__ void __launch_bounds__(256, 3) gather_fm_bwd_tile_kernel(const GatherParams p) {
   constexpr int VEC = Chunk<Elem>::kElems;
@@ -1099,6 +1201,27 @@ static int launch_gather(etr_ctx* ctx, const GatherParams& p_in, bool bag, cudaS
   }
   if (!bag && cpl == 1 && tile_smem <= 64 * 1024) {
     const int tgrid = grid_for(p.B, 8 * gpw, ctx->sm_count, 3);
+    // the FM family's hot configuration takes the lean kernel (ETR_GATHER=generic keeps the generic tiled one)
+    const char* which_k = getenv("ETR_GATHER");
+    const bool flat_ok = !p.flat || (p.flat_vec && p.flat_col0 % 4 == 0 && p.flat_ld % 4 == 0);
+    if (!BWD && sizeof(Elem) == 4 && p.k == 16 && p.has_w && p.w_extra && lpr == 4 && !p.has_pad && p.world <= 1 &&
+        flat_ok && p.row_bytes >= 68 && !(which_k && strcmp(which_k, "generic") == 0)) {
+      static int occ = 0;
+      if (!occ) { const char* e = getenv("ETR_K1_OCC"); occ = (e && e[0] == '3') ? 3 : 4; }
+      const int lgrid = grid_for(p.B, 64, ctx->sm_count, occ);
+#define ETR_LEAN(FL, OC)                                                                                               \
+  do {                                                                                                                 \
+    if (tile_smem > 48 * 1024)                                                                                         \
+      cudaFuncSetAttribute(gather_fm_fwd_lean_kernel<FL, OC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tile_smem); \
+    gather_fm_fwd_lean_kernel<FL, OC><<<lgrid, threads, tile_smem, s>>>(p);                                           \
+  } while (0)
+      const int fl = !p.flat ? 0 : (p.flat_bf16 ? 1 : 2);
+      if (occ == 3) { if (fl == 0) ETR_LEAN(0, 3); else if (fl == 1) ETR_LEAN(1, 3); else ETR_LEAN(2, 3); }
+      else { if (fl == 0) ETR_LEAN(0, 4); else if (fl == 1) ETR_LEAN(1, 4); else ETR_LEAN(2, 4); }
+#undef ETR_LEAN
+      ETR_LAUNCH_CHECK(ctx);
+      return ETR_OK;
+    }
 #define ETR_TILE(LPR)                                                                                   \
   do {                                                                                                  \
     if (BWD) {                                                                                          \

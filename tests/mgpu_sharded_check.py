@@ -90,8 +90,12 @@ def main():
         mine = full.table.data[rank::world]
         err_t = (sharded.table.data[: mine.shape[0]] - mine).abs().max().item()
         err_d = (sharded.params.value - full.params.value).abs().max().item()
-        # lr 1e-2: < 0.2% of one Adam step (fp32); bf16 tower: see the first-step check above
-        tol = 2e-5 if prec == "fp32" else 5e-3
+        # lr 1e-2: < 0.2% of one Adam step (fp32).  bf16 tower: the two sides run DIFFERENT kernels on different table
+        # layouts (unsharded: 256-byte records, occurrence-parallel apply with MUFU sqrt / rcp; sharded: plain arrays,
+        # owner-side apply), so their fp32 weights differ in the last ulp after one step (checked above: < 2e-6); a last-ulp
+        # difference can flip the bf16 rounding of an operand, and in its first steps Adam turns a flipped sign of a
+        # near-zero gradient into a full +-lr step: entries a step or two of lr apart after 3-6 steps are expected
+        tol = 2e-5 if prec == "fp32" else 2.5e-2
         assert err_t < tol and err_d < tol, (mode, graph, rank, err_t, err_d)
         if mode.startswith("peer"):
             # replicated dense variables must stay BIT-identical across ranks (deterministic rank-order sum)
