@@ -967,6 +967,10 @@ def main():
     if world == 1:
         from etr_b200.runtime import FusedFMGrad, SparsePlan
         plans = [SparsePlan(rt, id_batches[i], V) for i in range(4)]
+        tiled = layer.table.record and K_EMB == 16 and FusedFMGrad.apply_kernel == "tile"
+        if tiled:
+            for p_ in plans:
+                p_.prepare_fm()          # row descriptors + long-run items: part of the plan (ids only)
         dl_ = torch.randn(B, device=dev) * 1e-7
         sumv_ = torch.randn(B, K_EMB, device=dev) * 0.1
         dx_ = (torch.randn(B, col0 + F * K_EMB, device=dev) * 1e-7).to(torch.bfloat16)
@@ -986,10 +990,11 @@ def main():
         a_ms = statistics.median(a.elapsed_time(b_) for a, b_ in at[2:])
         n_u = statistics.mean(p_.n_unique for p_ in plans)
         a_bytes = n_u * 6 * (K_EMB + 1) * 4
-        tr_ = ncu_traffic("fm_fused_") if (args.dist == "zipf" and B == BATCH and args.config == "c2") else None
-        roof_apply = {"bound": "hbm", "kernel": "fm_fused_{classify,short|record,chunk,combine}_kernel (FM backward + sorted-run "
-                      "reduction + row-wise Adam; table layout: " + ("256-byte [var|m|v] records" if layer.table.record else
-                                                                      "three plain arrays") + ")",
+        tr_ = ncu_traffic("fm_tile_kernel" if tiled else "fm_fused_") if (args.dist == "zipf" and B == BATCH and args.config == "c2") else None
+        roof_apply = {"bound": "hbm", "kernel": ("fm_tile_kernel<1,7> (ONE launch: " if tiled else
+                                                 "fm_fused_{classify,short|record,chunk,combine}_kernel (") +
+                      "FM backward + sorted-run reduction + row-wise Adam; table layout: " +
+                      ("256-byte [var|m|v] records" if layer.table.record else "three plain arrays") + ")",
                       "achieved": a_bytes / (a_ms * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
                       "frac": a_bytes / (a_ms * 1e-3) / 1e9 / peak, "traffic": tr_[0] if tr_ else None,
                       "traffic_source": tr_[1] if tr_ else None, "peak_source": peak_src, "kernel_ms": a_ms,

@@ -286,11 +286,17 @@ class FMRankingLayer(_Layer):
         tab, vids, route = self._lookup(ids)
         sumv = self._sumv_buffer(training, tab, vids)
         plan = SparsePlan(self.rt, vids, tab.rows, overlap=True) if sumv is not None else None   # sort || fwd/bwd
+        self._prepare_plan(plan, tab)
         gather_fm_forward(tab, self.embedding_dims, True, vids, bias=self.bias, prob=prob, sumv=sumv)
         if training:
             self._ctx = {"ids": vids, "table": tab, "route": route, "sumv": sumv, "plan": plan}
         self._finish(training)
         return {"output": prob}
+
+    def _prepare_plan(self, plan, tab) -> None:
+        """Row descriptors / long-run items of the tiled fused apply: built behind the sort, off the critical path."""
+        if plan is not None and getattr(tab, "record", False) and self.embedding_dims == 16 and FusedFMGrad.apply_kernel == "tile":
+            plan.prepare_fm()
 
     def _sumv_buffer(self, training: bool, tab, vids) -> Optional[torch.Tensor]:
         """S = sum_f v_f [B,k], saved for the fused backward+apply (single-hot, fp32, unsharded)."""
@@ -369,6 +375,7 @@ class DeepFMRankingLayer(FMRankingLayer):
         tab, vids, route = self._lookup(ids)
         sumv = self._sumv_buffer(training, tab, vids)
         plan = SparsePlan(rt, vids, tab.rows, overlap=True) if sumv is not None else None        # sort || fwd/bwd
+        self._prepare_plan(plan, tab)
         gather_fm_forward(tab, k, True, vids, bias=self.bias, logit=fm_logit, sumv=sumv, flat=x, flat_col0=col0,
                           cont=cont)
         dnn = self.MLP_layer2(self.MLP_layer1(x, training=training), training=training)      # [B,1]
@@ -413,6 +420,7 @@ class DeepFMRankingLayer(FMRankingLayer):
             gtab, gids, slot_of_u = self.peer.exchange_forward(plan, B, F)
         else:
             plan = SparsePlan(rt, vids, tab.rows, overlap=True)    # sort || everything below
+            self._prepare_plan(plan, tab)
             gtab, gids = tab, vids
         gather_fm_forward(gtab, k, True, gids, bias=self.bias, logit=fm_logit, sumv=sumv, flat=x, flat_col0=col0,
                           cont=cont)

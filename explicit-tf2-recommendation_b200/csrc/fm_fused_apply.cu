@@ -22,6 +22,7 @@
 
 #include "etr_common.cuh"
 #include "etr_async.cuh"
+#include "fm_fused_tile.cuh"
 
 namespace etr {
 
@@ -406,7 +407,7 @@ static int fused_impl(etr_ctx* ctx, const etr_table* table, float* d_m, float* d
                       const float* d_dlogit, const float* d_sumv, const void* d_dflat, int32_t flat_dtype,
                       int64_t flat_ld, int32_t flat_col0, float lr_t, const float* d_lr_t, float beta1,
                       float beta2, float eps, int32_t apply, float* d_unique_grad, const int32_t* d_slot_of_u, int32_t cap,
-                      float* const* h_grads_mb, void* stream) {
+                      float* const* h_grads_mb, const void* d_prep, void* stream) {
   ETR_CHECK_ARG(ctx && table && table->d_data && d_sorted_bag && d_seg_start && d_unique_ids && d_n_unique && d_dlogit &&
                     d_sumv, "NULL argument");
   ETR_CHECK_ARG(!apply || (d_m && d_v), "Adam slots missing");
@@ -453,6 +454,26 @@ static int fused_impl(etr_ctx* ctx, const etr_table* table, float* d_m, float* d
   if (d_slot_of_u) {
     ETR_CHECK_ARG(h_grads_mb && cap > 0 && p.sharded && !apply, "mailbox export needs a peer-sharded table, apply == 0");
     for (int g = 0; g < p.world; ++g) { ETR_CHECK_ARG(h_grads_mb[g] != nullptr, "NULL mailbox pointer"); p.grads_mb[g] = h_grads_mb[g]; }
+  }
+  // hot configuration (Adam apply on a local RECORD table, k = 16, no / bf16 dflat) -> tiled kernels (csrc/fm_fused_tile.cu);
+  // ETR_FUSED_APPLY=rows keeps the row-parallel kernels below
+  {
+    static int use_tile = -1;
+    if (use_tile < 0) { const char* e = getenv("ETR_FUSED_APPLY"); use_tile = !(e && strcmp(e, "rows") == 0); }
+    const bool rec_tab = table->reserved == ETR_TABLE_RECORD && table->stride == 64 && d_m == (float*)table->d_data + 20 &&
+                         d_v == (float*)table->d_data + 40;
+    const bool df_ok = !d_dflat || (flat_dtype == ETR_BF16 && flat_col0 % 4 == 0 && flat_ld % 4 == 0);
+    if (use_tile && apply && rec_tab && lpr == 4 && !d_unique_grad && !d_slot_of_u && !p.sharded && df_ok &&
+        batch * 16 < 0x7fffffffLL && n_slots < 0x7fffffffLL) {
+      TileArgs a;
+      a.table = p.table; a.sorted_bag = p.sorted_bag; a.seg_start = p.seg_start; a.unique_ids = p.unique_ids; a.n_unique = p.n_unique;
+      a.dlogit = p.dlogit; a.sumv = p.sumv;
+      a.dflat = d_dflat ? reinterpret_cast<const __nv_bfloat16*>(d_dflat) + flat_col0 : nullptr;
+      a.flat_ld = flat_ld; a.F = p.F; a.magic = p.magic; a.shift = p.shift;
+      a.lr_t = lr_t; a.d_lr_t = d_lr_t; a.b1 = beta1; a.b2 = beta2; a.eps = eps; a.n_slots = n_slots;
+      return fused_tile_launch(ctx, a, d_prep, s);
+    }
+    if (d_prep) { etr_set_error("etr_fm_fused_backward_apply_prepared: needs an Adam apply on a local RECORD table (k = 16, bf16 dflat)"); return ETR_EUNSUPPORTED; }
   }
   p.max_long = (int)(n_slots / kFusedShortRun + 1);
   p.max_items = (int)(n_slots / kFusedChunk + n_slots / kFusedShortRun + 2);
@@ -507,7 +528,31 @@ int etr_fm_fused_backward_apply(etr_ctx* ctx, const etr_table* table, float* d_m
                                 float beta2, float eps, int32_t apply, float* d_unique_grad, void* stream) {
   return fused_impl(ctx, table, d_m, d_v, k, fields, batch, d_sorted_bag, d_seg_start, d_unique_ids, d_n_unique, n_slots,
                     d_dlogit, d_sumv, d_dflat, flat_dtype, flat_ld, flat_col0, lr_t, d_lr_t, beta1, beta2, eps, apply,
-                    d_unique_grad, nullptr, 0, nullptr, stream);
+                    d_unique_grad, nullptr, 0, nullptr, nullptr, stream);
+}
+
+int64_t etr_fm_fused_prepare_bytes(int64_t n_slots) { return n_slots > 0 ? (int64_t)fused_tile_prep_bytes(n_slots) : 256; }
+
+int etr_fm_fused_prepare(etr_ctx* ctx, const int32_t* d_seg_start, const int64_t* d_unique_ids, const int32_t* d_n_unique,
+                         int64_t n_slots, void* d_prep, int64_t prep_bytes, void* stream) {
+  ETR_CHECK_ARG(ctx && d_seg_start && d_unique_ids && d_n_unique && d_prep, "NULL argument");
+  ETR_CHECK_ARG(n_slots >= 0 && n_slots < 0x7fffffffLL, "n_slots out of range");
+  ETR_CHECK_ARG(prep_bytes >= etr_fm_fused_prepare_bytes(n_slots) && ((uintptr_t)d_prep & 255) == 0,
+                "d_prep must hold etr_fm_fused_prepare_bytes(n_slots) bytes, 256-byte aligned");
+  if (n_slots == 0) return ETR_OK;
+  return fused_tile_prepare(ctx, d_seg_start, (const long long*)d_unique_ids, d_n_unique, n_slots, d_prep, (cudaStream_t)stream);
+}
+
+int etr_fm_fused_backward_apply_prepared(etr_ctx* ctx, const etr_table* table, float* d_m, float* d_v, int32_t k, int32_t fields,
+                                         int64_t batch, const int32_t* d_sorted_bag, const int32_t* d_seg_start,
+                                         const int64_t* d_unique_ids, const int32_t* d_n_unique, int64_t n_slots,
+                                         const float* d_dlogit, const float* d_sumv, const void* d_dflat, int32_t flat_dtype,
+                                         int64_t flat_ld, int32_t flat_col0, float lr_t, const float* d_lr_t, float beta1,
+                                         float beta2, float eps, const void* d_prep, int64_t prep_bytes, void* stream) {
+  ETR_CHECK_ARG(d_prep && prep_bytes >= etr_fm_fused_prepare_bytes(n_slots), "d_prep missing or too small");
+  return fused_impl(ctx, table, d_m, d_v, k, fields, batch, d_sorted_bag, d_seg_start, d_unique_ids, d_n_unique, n_slots,
+                    d_dlogit, d_sumv, d_dflat, flat_dtype, flat_ld, flat_col0, lr_t, d_lr_t, beta1, beta2, eps, 1,
+                    nullptr, nullptr, 0, nullptr, d_prep, stream);
 }
 
 int etr_fm_fused_backward_push(etr_ctx* ctx, const etr_table* table, int32_t k, int32_t fields, int64_t batch,
@@ -518,7 +563,7 @@ int etr_fm_fused_backward_push(etr_ctx* ctx, const etr_table* table, int32_t k, 
   ETR_CHECK_ARG(d_slot_of_u && h_grads_mb, "NULL argument");
   return fused_impl(ctx, table, nullptr, nullptr, k, fields, batch, d_sorted_bag, d_seg_start, d_unique_ids, d_n_unique,
                     n_slots, d_dlogit, d_sumv, d_dflat, flat_dtype, flat_ld, flat_col0, 0.f, nullptr, 0.f, 0.f, 0.f, 0,
-                    nullptr, d_slot_of_u, cap, h_grads_mb, stream);
+                    nullptr, d_slot_of_u, cap, h_grads_mb, nullptr, stream);
 }
 
 }  // extern "C"

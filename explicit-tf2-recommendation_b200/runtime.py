@@ -6,6 +6,7 @@ from __future__ import annotations
 
 import ctypes as C
 import math
+import contextlib
 import os
 from typing import Dict, List, Optional, Sequence
 
@@ -306,6 +307,7 @@ class SparsePlan:
         self.n_slots = n
         self.rt = rt
         self._pending = None
+        self.fm_prep = None
         cur = torch.cuda.current_stream(rt.device)
         if overlap:
             side = rt.side_stream
@@ -329,6 +331,24 @@ class SparsePlan:
             self._pending = rt.side_stream
             for t in (self.sorted_bag, self.unique_ids, self.seg_start, self.counts, self.sorted_key):
                 t.record_stream(cur)                     # allocated on the side stream, consumed on the current one
+
+    def prepare_fm(self) -> "SparsePlan":
+        """Row descriptors + long-run items for the tiled fused FM apply (etr_fm_fused_prepare): depend on the ids only,
+        so they are built once per plan -- right behind the sort, on the stream the plan was built on."""
+        if getattr(self, "fm_prep", None) is not None:
+            return self
+        rt = self.rt
+        side = self._pending
+        with (torch.cuda.stream(side) if side is not None else contextlib.nullcontext()):
+            nbytes = int(rt.lib.etr_fm_fused_prepare_bytes(self.n_slots))
+            self.fm_prep = rt.empty((nbytes,), torch.uint8)
+            assert self.fm_prep.data_ptr() % 256 == 0
+            check(rt.lib.etr_fm_fused_prepare(rt.side_ctx if side is not None else rt.ctx, self.seg_start.data_ptr(),
+                                              self.unique_ids.data_ptr(), self.counts.data_ptr(), self.n_slots,
+                                              self.fm_prep.data_ptr(), nbytes, torch.cuda.current_stream(rt.device).cuda_stream))
+        if side is not None:
+            self.fm_prep.record_stream(torch.cuda.current_stream(rt.device))
+        return self
 
     def join(self) -> "SparsePlan":
         """Make the current stream wait for an overlapped plan (no-op otherwise)."""
@@ -401,8 +421,9 @@ class FusedFMGrad:
             df.stride(0) if df is not None else 0, self.flat_col0, lr_t, _p(d_lr_t), b1, b2, eps, int(apply), _p(out),
             rt.stream))
 
+    # "tile" (default) = tiled kernels (csrc/fm_fused_tile.cu; RECORD tables, picked inside etr_fm_fused_backward_apply),
     # "flat" = occurrence-parallel kernel (csrc/fm_fused_flat.cu; RECORD tables), "rows" = row-parallel kernels
-    apply_kernel = os.environ.get("ETR_FUSED_APPLY", "flat")
+    apply_kernel = os.environ.get("ETR_FUSED_APPLY", "tile")
 
     def apply(self, d_lr_t: torch.Tensor, b1: float, b2: float, eps: float) -> None:
         if self.table.record and self.k == 16 and FusedFMGrad.apply_kernel == "flat":
@@ -416,6 +437,20 @@ class FusedFMGrad:
                 self.plan.sorted_bag.data_ptr(), self.plan.n_slots, self.dlogit.data_ptr(), self.sumv.data_ptr(), _p(df),
                 _TORCH2ETR[df.dtype] if df is not None else 0, df.stride(0) if df is not None else 0, self.flat_col0,
                 0.0, _p(d_lr_t), b1, b2, eps, rt.stream))
+            return
+        if self.table.record and self.k == 16 and FusedFMGrad.apply_kernel == "tile" and \
+                (self.dflat is None or self.dflat.dtype == torch.bfloat16):
+            rt, t = self.table.rt, self.table.desc()
+            if self.plan is None:
+                self.plan = SparsePlan(rt, self.ids, self.table.rows)
+            self.plan.prepare_fm().join()
+            df, pl = self.dflat, self.plan
+            check(rt.lib.etr_fm_fused_backward_apply_prepared(
+                rt.ctx, C.byref(t), _p(self.table.m), _p(self.table.v), self.k, self.ids.F, self.ids.B,
+                pl.sorted_bag.data_ptr(), pl.seg_start.data_ptr(), pl.unique_ids.data_ptr(), pl.counts.data_ptr(), pl.n_slots,
+                self.dlogit.data_ptr(), self.sumv.data_ptr(), _p(df), _TORCH2ETR[df.dtype] if df is not None else 0,
+                df.stride(0) if df is not None else 0, self.flat_col0, 0.0, _p(d_lr_t), b1, b2, eps,
+                pl.fm_prep.data_ptr(), pl.fm_prep.numel(), rt.stream))
             return
         self._run(True, 0.0, d_lr_t, b1, b2, eps, None)
 

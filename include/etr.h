@@ -219,6 +219,28 @@ int etr_fm_fused_backward_apply(etr_ctx* ctx, const etr_table* table, float* d_m
                                 float lr_t, const float* d_lr_t, float beta1, float beta2, float eps,
                                 int32_t apply, float* d_unique_grad, void* stream);
 
+/* Hot configuration of etr_fm_fused_backward_apply (apply = 1, local RECORD table, k = 16, dflat NULL or bf16): the tiled
+ * kernel of csrc/fm_fused_tile.cu.  It works from per-row descriptors and a list of long-run items that depend on the
+ * plan only (not on the gradients), so they can be prepared ONCE per plan, off the critical path (e.g. on the side
+ * stream that sorts the ids, 2.FM/ModelManager.py:172-178 runs the whole of this inside apply_gradients):
+ *   etr_fm_fused_prepare_bytes(n_slots)  size of the caller-owned buffer (256-byte aligned)
+ *   etr_fm_fused_prepare(...)            fills it from the plan (one launch)
+ *   etr_fm_fused_backward_apply_prepared(...)  ONE launch: runs longer than 32 occurrences as 256-occurrence items
+ *       (deterministic last-arriver combine), all other rows in tiles of 8 with records, bag indices and descriptors
+ *       prefetched by cp.async.  etr_fm_fused_backward_apply without a prepared buffer builds the lists in the
+ *       ctx workspace first (one more launch) and is otherwise identical.                                        */
+int64_t etr_fm_fused_prepare_bytes(int64_t n_slots);
+int etr_fm_fused_prepare(etr_ctx* ctx, const int32_t* d_seg_start, const int64_t* d_unique_ids, const int32_t* d_n_unique,
+                         int64_t n_slots, void* d_prep, int64_t prep_bytes, void* stream);
+int etr_fm_fused_backward_apply_prepared(etr_ctx* ctx, const etr_table* table, float* d_m, float* d_v, int32_t k,
+                                         int32_t fields, int64_t batch,
+                                         const int32_t* d_sorted_bag, const int32_t* d_seg_start,
+                                         const int64_t* d_unique_ids, const int32_t* d_n_unique, int64_t n_slots,
+                                         const float* d_dlogit, const float* d_sumv,
+                                         const void* d_dflat, int32_t flat_dtype, int64_t flat_ld, int32_t flat_col0,
+                                         float lr_t, const float* d_lr_t, float beta1, float beta2, float eps,
+                                         const void* d_prep, int64_t prep_bytes, void* stream);
+
 /* The same computation as etr_fm_fused_backward_apply(apply = 1) for a RECORD table (k = 16), organised by
  * OCCURRENCE instead of by row: every warp streams a contiguous range of the sorted occurrence list
  * (d_sorted_key, d_sorted_bag from etr_sparse_plan_keys), 8 occurrences per step, gathers (g_b, S_b, dflat slice)

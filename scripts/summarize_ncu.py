@@ -15,7 +15,15 @@ KEYS = ["gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum
         "gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed", "lts__t_bytes.sum", "sm__warps_active.avg.pct_of_peak_sustained_active",
         "launch__registers_per_thread", "launch__grid_size", "launch__block_size", "launch__occupancy_limit_registers",
         "sm__throughput.avg.pct_of_peak_sustained_elapsed", "sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active",
-        "sm__inst_executed_pipe_tensor.sum", "l1tex__t_sectors_pipe_lsu_mem_global_op_ld.sum", "smsp__warp_issue_stalled_long_scoreboard_per_warp_active.pct"]
+        "sm__inst_executed_pipe_tensor.sum", "l1tex__t_sectors_pipe_lsu_mem_global_op_ld.sum", "smsp__warp_issue_stalled_long_scoreboard_per_warp_active.pct",
+        "smsp__inst_executed.sum", "smsp__issue_active.avg.pct_of_peak_sustained_active", "lts__t_requests_srcunit_tex.sum",
+        "lts__t_sectors_srcunit_tex_op_read_lookup_hit.sum", "lts__t_sectors_srcunit_tex_op_read_lookup_miss.sum", "lts__t_sector_hit_rate.pct",
+        "l1tex__t_sector_hit_rate.pct", "l1tex__m_xbar2l1tex_read_sectors.sum", "smsp__average_warps_issue_stalled_long_scoreboard_per_issue_active.ratio",
+        "smsp__average_warps_issue_stalled_short_scoreboard_per_issue_active.ratio", "smsp__average_warps_issue_stalled_wait_per_issue_active.ratio",
+        "smsp__average_warps_issue_stalled_barrier_per_issue_active.ratio", "smsp__average_warps_issue_stalled_not_selected_per_issue_active.ratio",
+        "smsp__average_warps_issue_stalled_mio_throttle_per_issue_active.ratio", "smsp__average_warps_issue_stalled_math_pipe_throttle_per_issue_active.ratio",
+        "smsp__average_warps_issue_stalled_lg_throttle_per_issue_active.ratio", "smsp__average_warps_issue_stalled_branch_resolving_per_issue_active.ratio",
+        "sm__cycles_active.avg"]
 
 
 def launches(tag, fname="launches.csv", out="launches_one_step", what="DeepFM (c2)", pick=(-3, -2),
@@ -57,7 +65,8 @@ def rep(name, tag):
     if len(rows) < 3:
         return
     hdr, units = rows[0], rows[1]
-    with open(os.path.join(ROOT, "profiles", f"{tag}_{name}.md"), "w") as fh:
+    out_name = name if name.startswith(tag) else f"{tag}_{name}"
+    with open(os.path.join(ROOT, "profiles", f"{out_name}.md"), "w") as fh:
         fh.write(f"# {tag}: `ncu --set full --clock-control none --import-source on` -> {name}.ncu-rep\n\n")
         for r in rows[2:]:
             d = dict(zip(hdr, r))
@@ -73,6 +82,7 @@ if __name__ == "__main__":
     launches(tag)
     launches(tag, "launches_c3.csv", "launches_c3_step", "DCN-matrix bf16 (c3)", (-2, -1),
              "python bench.py --config c3 --steps 1 --warmup 3 --no-graph")
-    for n in ("prof_gather_fwd", "prof_tcgemm", "prof_cross", "prof_fused_short"):
+    names = sys.argv[2:] or ["prof_gather_fwd", "prof_tcgemm", "prof_cross", "prof_fused_short"]
+    for n in names:
         rep(n, tag)
     print(os.listdir(os.path.join(ROOT, "profiles")))
