@@ -395,7 +395,7 @@ class DeepFMRankingLayer(FMRankingLayer):
                 and m1.use_bias and self.MLP_layer2.use_bias and self.MLP_layer2.activation is None
                 and (self.front_pad + len(self.continuous_features) + len(self.feature_names) * self.embedding_dims) % 16 == 0)
 
-    def train_forward_backward(self, inputs, labels: torch.Tensor, grad_scale: float = 1.0):
+    def train_forward_backward(self, inputs, labels: torch.Tensor, grad_scale: float = 1.0, plan: Optional[SparsePlan] = None):
         """The whole reference train step up to apply_gradients (2.FM/ModelManager.py:172-176) for the default
         DeepFM tower, in 6 launches: returns (loss [1], prob [B,1], table gradients) or None when this batch
         is not eligible (the caller then takes the layer-by-layer path).  Dense grads land in params.grad."""
@@ -416,7 +416,8 @@ class DeepFMRankingLayer(FMRankingLayer):
         if self.peer is not None and self.shard_mode == "peer":
             # de-duplicated exchange: the sorted plan comes first, the owners write the unique rows into this rank's
             # response buffer, and the gather below runs on that buffer (local HBM, mostly L2-resident)
-            plan = SparsePlan(rt, vids, tab.rows)
+            # ``plan``: this batch's plan, sorted ahead of time during the previous step (Trainer next_batch=)
+            plan = plan.join() if plan is not None else SparsePlan(rt, vids, tab.rows)
             gtab, gids, slot_of_u = self.peer.exchange_forward(plan, B, F)
         else:
             plan = SparsePlan(rt, vids, tab.rows, overlap=True)    # sort || everything below
@@ -1293,7 +1294,9 @@ class Trainer:
         self.peer = getattr(layer, "peer", None)      # peer-memory sharding: nothing syncs with the host
         assert not (graph and self.dp_world > 1 and self.peer is None), \
             "the all-to-all sharded step syncs split sizes on the host: no CUDA graph (use shard='peer')"
-        self.depth = 2 if graph else 1
+        # static buffer sets: 2 = stage step i+1 while step i runs; 3 for the plan-ahead of peer-sharded layers (step i
+        # already reads the ids of step i+1, so those are staged while step i-1 runs)
+        self.depth = (3 if self.peer is not None else 2) if graph else 1
         self._graphs: Dict[tuple, list] = {}
         self._copy_stream = self._d2h_stream = None
 
@@ -1344,9 +1347,14 @@ class Trainer:
         self.load_state_dict(torch.load(path, map_location="cpu"))
 
     # ------------------------------------------------------------ eager step
-    def train_step(self, inputs, labels=None) -> torch.Tensor:
-        """One step; returns the (device-resident, un-synchronised) scalar loss."""
-        loss = self._graph_step(inputs, labels) if self.use_graph else self._eager_step(inputs, labels)
+    def train_step(self, inputs, labels=None, next_batch=None) -> torch.Tensor:
+        """One step; returns the (device-resident, un-synchronised) scalar loss.
+
+        ``next_batch`` (peer-sharded layers; a DeviceBatch from ``stage()`` that is already staged): the sorted plan of
+        the NEXT batch is built on the side stream while this step runs, so that the next step can send its requests
+        at once -- at N > 1 the plan is otherwise the first thing on the critical path (nothing of the table side can
+        start before the unique ids are known)."""
+        loss = self._graph_step(inputs, labels, next_batch) if self.use_graph else self._eager_step(inputs, labels, next_batch)
         self._poll()
         return loss
 
@@ -1360,7 +1368,7 @@ class Trainer:
             self.rt.check_peeked_error(wait=True)               # the previous peek is poll_every steps old: done long ago
             self.rt.peek_error_async()
 
-    def _eager_step(self, inputs, labels=None) -> torch.Tensor:
+    def _eager_step(self, inputs, labels=None, next_batch=None) -> torch.Tensor:
         rt = self.rt
         if labels is None and isinstance(inputs, DeviceBatch):
             labels = inputs.labels
@@ -1368,9 +1376,23 @@ class Trainer:
         if sl is not None and not torch.cuda.is_current_stream_capturing():
             torch.cuda.current_stream(rt.device).wait_event(sl.copy_done)     # staged on the copy stream
         y = rt.to_device(labels, torch.float32).reshape(-1)
+        # plan-ahead (peer-sharded): this batch's plan was sorted during the previous step; the next batch's starts now
+        pre, nsl = None, getattr(next_batch, "_slot", None)
+        if self.peer is not None and sl is not None and sl.plan_ready:
+            pre, sl.plan_ready = sl.plan, False
+        if self.peer is not None and nsl is not None and nsl is not sl:
+            rows = self.layer.sparse_tables()[0].rows
+            if nsl.plan is None:
+                assert not torch.cuda.is_current_stream_capturing()
+                nsl.plan = SparsePlan(rt, nsl.batch.ids, rows, overlap=True)
+                if getattr(self.layer, "embedding_dims", 0) == 16 and FusedFMGrad.apply_kernel == "tile":
+                    nsl.plan.prepare_fm()             # row descriptors / long-run items of the tiled push kernel
+            else:
+                nsl.plan.rebuild(nsl.batch.ids, rows)
         fused = None
         if getattr(self.layer, "fused_train_ok", None) and self.layer.fused_train_ok():
-            fused = self.layer.train_forward_backward(inputs, y, 1.0 / self.dp_world)
+            fused = self.layer.train_forward_backward(inputs, y, 1.0 / self.dp_world, plan=pre) if pre is not None else \
+                self.layer.train_forward_backward(inputs, y, 1.0 / self.dp_world)
         if fused is not None:
             loss, _, grads = fused
         else:
@@ -1392,6 +1414,10 @@ class Trainer:
         self.apply_gradients(grads)
         if self.peer is not None:
             self.peer.barrier()                       # owners have applied: shards and mailboxes are free again
+        if self.peer is not None and nsl is not None and nsl is not sl:
+            nsl.plan.join()                           # the look-ahead sort belongs to THIS step (timed with it)
+            nsl.plan._pending = None
+            nsl.plan_ready = True
         if sl is not None and not torch.cuda.is_current_stream_capturing():
             sl.used = True
             sl.compute_done.record(torch.cuda.current_stream(rt.device))
@@ -1435,8 +1461,9 @@ class Trainer:
     class _Slot:
         def __init__(self):
             self.batch = self.ids_buf = self.cont_buf = self.lab_buf = None
-            self.graph = self.loss = None
-            self.eager_steps = 0
+            self.loss = None
+            self.graphs, self.eager = {}, {}          # per step variant (plan ready?, look-ahead?): captured graph, eager runs
+            self.plan, self.plan_ready = None, False  # plan-ahead (peer-sharded layers): this slot's sorted plan, static buffers
             self.copy_done = torch.cuda.Event()
             self.compute_done = torch.cuda.Event()
             self.used = False
@@ -1492,6 +1519,7 @@ class Trainer:
         cols = [inputs[n] for n in names] + [inputs[n] for n in cont_names] + [labels]
         if any(isinstance(c, torch.Tensor) and c.is_cuda for c in cols):
             self._copy_stream.wait_stream(cur)            # device-resident inputs: order after their producer
+        sl.plan_ready = False                             # the ids are about to change: a plan sorted for the old ones is stale
         with torch.cuda.stream(self._copy_stream):
             if sl.used:
                 self._copy_stream.wait_event(sl.compute_done)      # the buffers' previous consumer has finished
@@ -1525,8 +1553,8 @@ class Trainer:
                 dst[i].copy_(t0, non_blocking=True)
             i = j
 
-    def _graph_step(self, inputs, labels) -> torch.Tensor:
-        """Per buffer set: calls 1-2 run eagerly on the static buffers (real training
+    def _graph_step(self, inputs, labels, next_batch=None) -> torch.Tensor:
+        """Per buffer set and step variant: calls 1-2 run eagerly on the static buffers (real training
         steps; they size the workspace), call 3 captures the step into a CUDA graph,
         every later call is one graph replay."""
         batch = inputs if isinstance(inputs, DeviceBatch) else self.stage(inputs, labels)
@@ -1534,31 +1562,47 @@ class Trainer:
         assert sl is not None, "graph mode needs the static DeviceBatch returned by stage()"
         cur = torch.cuda.current_stream(self.rt.device)
         cur.wait_event(sl.copy_done)
-        if sl.graph is None and sl.eager_steps < 2:
-            sl.eager_steps += 1
-            loss = self._eager_step(batch)
+        nsl = getattr(next_batch, "_slot", None) if self.peer is not None else None
+        if nsl is sl:
+            nsl = next_batch = None
+        if nsl is not None:
+            cur.wait_event(nsl.copy_done)     # its ids are sorted inside this step
+        else:
+            next_batch = None
+        key = (self.peer is not None and sl.plan_ready, nsl is not None)
+        if key not in sl.graphs and sl.eager.get(key, 0) < 2:
+            sl.eager[key] = sl.eager.get(key, 0) + 1
+            loss = self._eager_step(batch, None, next_batch)
             if sl.loss is None:
                 sl.loss = self.rt.empty((1,))
             sl.loss.copy_(loss)
         else:
-            if sl.graph is None:
+            if key not in sl.graphs:
                 torch.cuda.synchronize(self.rt.device)
+                ready = (sl.plan_ready, nsl.plan_ready if nsl is not None else False)
                 g = torch.cuda.CUDAGraph()
                 with torch.cuda.graph(g, capture_error_mode="thread_local"):
-                    loss = self._eager_step(batch)
+                    loss = self._eager_step(batch, None, next_batch)
                     sl.loss.copy_(loss)
-                sl.graph = g                  # capture does not execute: the replay below runs the step
+                sl.graphs[key] = g            # capture does not execute: the replay below runs the step
+                sl.plan_ready = ready[0]      # ... so the flags the captured step flipped are restored first
+                if nsl is not None:
+                    nsl.plan_ready = ready[1]
                 cur = torch.cuda.current_stream(self.rt.device)
-            sl.graph.replay()
+            sl.graphs[key].replay()
+            if self.peer is not None:         # what the replayed step did to the plan flags
+                sl.plan_ready = False
+                if nsl is not None:
+                    nsl.plan_ready = True
         sl.used = True
         sl.compute_done.record(cur)
         return sl.loss
 
-    def train_step_async(self, inputs, labels=None) -> "Trainer.LossHandle":
+    def train_step_async(self, inputs, labels=None, next_batch=None) -> "Trainer.LossHandle":
         """Graph mode: enqueue the step and an asynchronous read-back of its loss;
         returns immediately.  ``handle.result()`` blocks only until THIS step is done."""
         assert self.use_graph, "train_step_async needs graph=True"
-        loss = self._graph_step(inputs, labels)
+        loss = self._graph_step(inputs, labels, next_batch)
         self._poll()
         batch_slot = None
         for slots, _ in self._graphs.values():

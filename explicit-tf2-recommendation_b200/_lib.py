@@ -81,7 +81,7 @@ PROTOTYPES = {
     "etr_fm_fused_backward_apply_prepared": (C.c_int, [_vp, _T, _vp, _vp, _i32, _i32, _i64, _vp, _vp, _vp, _vp, _i64, _vp, _vp, _vp,
                                                        _i32, _i64, _i32, _f32, _vp, _f32, _f32, _f32, _vp, _i64, _vp]),
     "etr_fm_fused_backward_push": (C.c_int, [_vp, _T, _i32, _i32, _i64, _vp, _vp, _vp, _vp, _i64, _vp, _vp, _vp, _i32, _i64, _i32,
-                                             _vp, _i32, C.POINTER(_vp), _vp]),
+                                             _vp, _i32, C.POINTER(_vp), _vp, _i64, _vp]),
     "etr_dense_adam_apply": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _i64, _f32, _vp, _f32, _f32, _f32, _vp]),
     "etr_adam_step_begin": (C.c_int, [_vp, _vp, _f32, _f32, _f32, _vp]),
     "etr_bce_forward_backward": (C.c_int, [_vp, _vp, _vp, _i64, _vp, _vp, _vp]),

@@ -463,17 +463,23 @@ static int fused_impl(etr_ctx* ctx, const etr_table* table, float* d_m, float* d
     const bool rec_tab = table->reserved == ETR_TABLE_RECORD && table->stride == 64 && d_m == (float*)table->d_data + 20 &&
                          d_v == (float*)table->d_data + 40;
     const bool df_ok = !d_dflat || (flat_dtype == ETR_BF16 && flat_col0 % 4 == 0 && flat_ld % 4 == 0);
-    if (use_tile && apply && rec_tab && lpr == 4 && !d_unique_grad && !d_slot_of_u && !p.sharded && df_ok &&
-        batch * 16 < 0x7fffffffLL && n_slots < 0x7fffffffLL) {
+    const bool tile_apply = apply && rec_tab && !d_unique_grad && !d_slot_of_u && !p.sharded;
+    const bool tile_push = !apply && d_slot_of_u && p.sharded && !d_unique_grad && p.gld == 20;
+    if (use_tile && (tile_apply || tile_push) && lpr == 4 && df_ok && batch * 16 < 0x7fffffffLL && n_slots < 0x7fffffffLL) {
       TileArgs a;
+      memset(&a, 0, sizeof(a));
       a.table = p.table; a.sorted_bag = p.sorted_bag; a.seg_start = p.seg_start; a.unique_ids = p.unique_ids; a.n_unique = p.n_unique;
       a.dlogit = p.dlogit; a.sumv = p.sumv;
       a.dflat = d_dflat ? reinterpret_cast<const __nv_bfloat16*>(d_dflat) + flat_col0 : nullptr;
       a.flat_ld = flat_ld; a.F = p.F; a.magic = p.magic; a.shift = p.shift;
       a.lr_t = lr_t; a.d_lr_t = d_lr_t; a.b1 = beta1; a.b2 = beta2; a.eps = eps; a.n_slots = n_slots;
+      if (tile_push) {
+        a.slot_of_u = d_slot_of_u; a.cap = cap; a.gld = p.gld;
+        for (int g = 0; g < p.world; ++g) a.grads_mb[g] = p.grads_mb[g];
+      }
       return fused_tile_launch(ctx, a, d_prep, s);
     }
-    if (d_prep) { etr_set_error("etr_fm_fused_backward_apply_prepared: needs an Adam apply on a local RECORD table (k = 16, bf16 dflat)"); return ETR_EUNSUPPORTED; }
+    if (d_prep && apply) { etr_set_error("etr_fm_fused_backward_apply_prepared: needs an Adam apply on a local RECORD table (k = 16, bf16 dflat)"); return ETR_EUNSUPPORTED; }
   }
   p.max_long = (int)(n_slots / kFusedShortRun + 1);
   p.max_items = (int)(n_slots / kFusedChunk + n_slots / kFusedShortRun + 2);
@@ -559,11 +565,13 @@ int etr_fm_fused_backward_push(etr_ctx* ctx, const etr_table* table, int32_t k, 
                                const int32_t* d_sorted_bag, const int32_t* d_seg_start, const int64_t* d_unique_ids,
                                const int32_t* d_n_unique, int64_t n_slots, const float* d_dlogit, const float* d_sumv,
                                const void* d_dflat, int32_t flat_dtype, int64_t flat_ld, int32_t flat_col0,
-                               const int32_t* d_slot_of_u, int32_t cap, float* const* h_grads_mb, void* stream) {
+                               const int32_t* d_slot_of_u, int32_t cap, float* const* h_grads_mb, const void* d_prep,
+                               int64_t prep_bytes, void* stream) {
   ETR_CHECK_ARG(d_slot_of_u && h_grads_mb, "NULL argument");
+  ETR_CHECK_ARG(!d_prep || prep_bytes >= etr_fm_fused_prepare_bytes(n_slots), "d_prep too small");
   return fused_impl(ctx, table, nullptr, nullptr, k, fields, batch, d_sorted_bag, d_seg_start, d_unique_ids, d_n_unique,
                     n_slots, d_dlogit, d_sumv, d_dflat, flat_dtype, flat_ld, flat_col0, 0.f, nullptr, 0.f, 0.f, 0.f, 0,
-                    nullptr, d_slot_of_u, cap, h_grads_mb, nullptr, stream);
+                    nullptr, d_slot_of_u, cap, h_grads_mb, d_prep, stream);
 }
 
 }  // extern "C"

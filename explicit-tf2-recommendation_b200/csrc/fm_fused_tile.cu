@@ -91,6 +91,14 @@ __device__ __forceinline__ void rec_finish(float* rec, int gl, RecState& st, flo
   }
 }
 
+// push mode: the finished row goes to its owner's mailbox slot
+__device__ __forceinline__ void row_push(const TileArgs& a, int so, int gl, float4 P, float sum_g) {
+  const int owner = so / a.cap;
+  float* dst = a.grads_mb[owner] + (long long)(so - owner * a.cap) * a.gld;
+  *reinterpret_cast<float4*>(dst + gl * 4) = P;
+  if (gl == 0) *reinterpret_cast<float4*>(dst + 16) = make_float4(sum_g, 0.f, 0.f, 0.f);
+}
+
 // one thread per unique row (and per pad row of the last tile): descriptor + the items of a long run.
 // items[i] = (run u, first sorted position, length, slot), slot = -1 for a single-item run, else the index of its
 // (base, nchunks) entry and arrival counter
@@ -128,18 +136,18 @@ __device__ __forceinline__ void tree8(float4& t, float& ts) {     // fixed combi
   }
 }
 
-template <int DF>
+template <int DF, int PUSH>
 __device__ __forceinline__ void tile_item(const TileParams& p, int it, int lane, float lr_t) {
   const TileArgs& a = p.a;
   const unsigned full = 0xffffffffu;
   const int gl = lane & 3, g = lane >> 2;
   const int4 item = p.items[it];
   const int lo = item.y, n_it = item.z, slot = item.w;
-  float* rec = a.table + __ldg(a.unique_ids + item.x) * 64;
+  float* rec = PUSH ? a.table : a.table + __ldg(a.unique_ids + item.x) * 64;
   RecState st;
   st.var = st.m = st.v = make_float4(0.f, 0.f, 0.f, 0.f);
   st.wx = 0.f;
-  if (slot < 0 && lane < 4) rec_load(rec, gl, st);       // single-item run: the record travels during the gather
+  if (!PUSH && slot < 0 && lane < 4) rec_load(rec, gl, st);       // single-item run: the record travels during the gather
   float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
   float sum_g = 0.f;
   for (int pos = 0; pos < n_it; pos += 128) {
@@ -169,6 +177,10 @@ __device__ __forceinline__ void tile_item(const TileParams& p, int it, int lane,
   }
   tree8(acc, sum_g);
   if (slot < 0) {
+    if (PUSH) {
+      if (lane < 4) row_push(a, __ldg(a.slot_of_u + item.x), gl, acc, sum_g);
+      return;
+    }
     const float w = __shfl_sync(full, st.wx, 1), wm = __shfl_sync(full, st.wx, 2), wv = __shfl_sync(full, st.wx, 3);
     if (lane < 4) rec_finish(rec, gl, st, acc, sum_g, w, wm, wv, a, lr_t);
     return;
@@ -187,7 +199,7 @@ __device__ __forceinline__ void tile_item(const TileParams& p, int it, int lane,
   if (old == run.nchunks - 1) {                          // last item of the run to finish: combine in item order
     __threadfence();
     if (lane == 0) p.arrived[slot] = 0;                  // self-cleaning: the lists are reused by every apply of this plan
-    if (lane < 4) rec_load(rec, gl, st);
+    if (!PUSH && lane < 4) rec_load(rec, gl, st);
     float4 t = make_float4(0.f, 0.f, 0.f, 0.f);
     float ts = 0.f;
     for (int c = g; c < run.nchunks; c += 8) {
@@ -197,6 +209,10 @@ __device__ __forceinline__ void tile_item(const TileParams& p, int it, int lane,
       ts += __ldcg(src + 16);
     }
     tree8(t, ts);
+    if (PUSH) {
+      if (lane < 4) row_push(a, __ldg(a.slot_of_u + item.x), gl, t, ts);
+      return;
+    }
     const float w = __shfl_sync(full, st.wx, 1), wm = __shfl_sync(full, st.wx, 2), wv = __shfl_sync(full, st.wx, 3);
     if (lane < 4) rec_finish(rec, gl, st, t, ts, w, wm, wv, a, lr_t);
   }
@@ -222,7 +238,7 @@ __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commi
 template <int N>
 __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 
-template <int DF, int OCC>
+template <int DF, int OCC, int PUSH>
 __global__ void __launch_bounds__(128, OCC) fm_tile_kernel(const TileParams p) {
   __shared__ WarpSmem smem[4];
   const TileArgs& a = p.a;
@@ -237,22 +253,26 @@ __global__ void __launch_bounds__(128, OCC) fm_tile_kernel(const TileParams p) {
   if (n_items > p.max_items || p.counters[0] > p.max_runs) n_items = 0;      // cannot happen (the bounds are exact)
   const int W = gridDim.x * 4;
   int idx = blockIdx.x * 4 + wid;
-  for (; idx < n_items; idx += W) tile_item<DF>(p, idx, lane, lr_t);
+  for (; idx < n_items; idx += W) tile_item<DF, PUSH>(p, idx, lane, lr_t);
   int tile = idx - n_items;
   if (tile >= n_tiles) return;
 
   // records + bag indices of the tile whose descriptors sit in sm.hdr[hb] -> buffers `nb`.  Unconditional: a pad or
   // long row fetches a record nobody reads, bag indices past the span are clamped to a valid slot.
-  auto issue_rec_bags = [&](int hb, int nb, int4& h, int& S0, int& S1) {
+  auto issue_rec_bags = [&](int t, int hb, int nb, int4& h, int& S0, int& S1) {
     h = sm.hdr[hb][g];
     const int4 first = sm.hdr[hb][0], last = sm.hdr[hb][7];
     S0 = first.x; S1 = last.x + abs(last.y);
-    const long long uid = ((long long)h.w << 32) | (unsigned)h.z;
-    const float* rec = a.table + uid * 64;
-    cp_async16(&sm.var[nb][lane], rec + gl * 4);
-    cp_async16(&sm.m[nb][lane], rec + 20 + gl * 4);
-    cp_async16(&sm.v[nb][lane], rec + 40 + gl * 4);
-    cp_async4(&sm.w[nb][lane], rec + (gl ? 20 * gl - 4 : 16));
+    if (!PUSH) {
+      const long long uid = ((long long)h.w << 32) | (unsigned)h.z;
+      const float* rec = a.table + uid * 64;
+      cp_async16(&sm.var[nb][lane], rec + gl * 4);
+      cp_async16(&sm.m[nb][lane], rec + 20 + gl * 4);
+      cp_async16(&sm.v[nb][lane], rec + 40 + gl * 4);
+      cp_async4(&sm.w[nb][lane], rec + (gl ? 20 * gl - 4 : 16));
+    } else if (lane >= 16 && lane < 24) {                  // push mode: the 8 mailbox slots instead of the 8 records
+      cp_async4(&sm.w[nb][lane - 16], a.slot_of_u + min(t * 8 + lane - 16, last_slot));
+    }
     if (lane < 16) cp_async4(&sm.bag[nb][lane], a.sorted_bag + min(S0 + lane, last_slot));
   };
   auto issue_hdr = [&](int t, int hb) {
@@ -265,7 +285,7 @@ __global__ void __launch_bounds__(128, OCC) fm_tile_kernel(const TileParams p) {
   __syncwarp();
   int4 hc;
   int S0c, S1c;
-  issue_rec_bags(0, 0, hc, S0c, S1c);
+  issue_rec_bags(tile, 0, 0, hc, S0c, S1c);
   issue_hdr(tile + W, 1);
   cp_async_commit();
   int buf = 0, hb = 1;
@@ -275,7 +295,7 @@ __global__ void __launch_bounds__(128, OCC) fm_tile_kernel(const TileParams p) {
     int4 hn = make_int4(0, 0, 0, 0);
     int S0n = 0, S1n = 0;
     if (tile + W < n_tiles) {
-      issue_rec_bags(hb, buf ^ 1, hn, S0n, S1n);
+      issue_rec_bags(tile + W, hb, buf ^ 1, hn, S0n, S1n);
       issue_hdr(tile + 2 * W, hb ^ 1);
     }
     cp_async_commit();
@@ -328,7 +348,9 @@ __global__ void __launch_bounds__(128, OCC) fm_tile_kernel(const TileParams p) {
         bag0 = nb0; bag1 = nb1;
       }
     }
-    if (len > 0) {
+    if (PUSH) {
+      if (len > 0) row_push(a, __float_as_int(sm.w[buf][g]), gl, acc, sum_g);
+    } else if (len > 0) {
       const long long uid = ((long long)hc.w << 32) | (unsigned)hc.z;
       float* rec = a.table + uid * 64;
       RecState st;
@@ -413,8 +435,9 @@ int fused_tile_launch(etr_ctx* ctx, const TileArgs& a, const void* d_prep, cudaS
   }
   const int OCC = g_OCC;
   const int grid = grid_for(a.n_slots, 32, ctx->sm_count, OCC);
-#define ETR_TILE(DF) do { if (OCC <= 5) fm_tile_kernel<DF, 5><<<grid, 128, 0, s>>>(p); else if (OCC == 6) fm_tile_kernel<DF, 6><<<grid, 128, 0, s>>>(p); \
-    else if (OCC == 7) fm_tile_kernel<DF, 7><<<grid, 128, 0, s>>>(p); else fm_tile_kernel<DF, 8><<<grid, 128, 0, s>>>(p); } while (0)
+#define ETR_TILE(DF) do { if (a.slot_of_u) fm_tile_kernel<DF, 7, 1><<<grid, 128, 0, s>>>(p); \
+    else if (OCC <= 5) fm_tile_kernel<DF, 5, 0><<<grid, 128, 0, s>>>(p); else if (OCC == 6) fm_tile_kernel<DF, 6, 0><<<grid, 128, 0, s>>>(p); \
+    else if (OCC == 7) fm_tile_kernel<DF, 7, 0><<<grid, 128, 0, s>>>(p); else fm_tile_kernel<DF, 8, 0><<<grid, 128, 0, s>>>(p); } while (0)
   if (a.dflat) ETR_TILE(1); else ETR_TILE(0);
 #undef ETR_TILE
   ETR_LAUNCH_CHECK(ctx);

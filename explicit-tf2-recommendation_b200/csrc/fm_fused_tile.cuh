@@ -14,6 +14,9 @@ struct TileArgs {
   int F; unsigned long long magic; int shift;       // b = (bag * magic) >> shift == bag / F
   float lr_t; const float* d_lr_t; float b1, b2, eps;
   long long n_slots;
+  // push mode (peer-sharded table, deferred export): instead of the Adam update, row u = [P_0..P_15, sum_g, 0, 0, 0] is
+  // stored into the owner's gradient mailbox, slot_of_u[u] = owner * cap + slot (NVLink peer stores)
+  const int* slot_of_u; int cap; int gld; float* grads_mb[16];
 };
 
 // row descriptors + long-run items of a plan (depend on the ids only): prepared once per plan into a caller-owned

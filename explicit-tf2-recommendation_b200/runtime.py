@@ -332,10 +332,30 @@ class SparsePlan:
             for t in (self.sorted_bag, self.unique_ids, self.seg_start, self.counts, self.sorted_key):
                 t.record_stream(cur)                     # allocated on the side stream, consumed on the current one
 
+    def rebuild(self, ids: IdsBatch, table_rows: int) -> "SparsePlan":
+        """Plan another batch of the same shape INTO THE SAME BUFFERS, on the side stream (forked from the current one):
+        the plan of the NEXT batch is sorted while the current step runs (Trainer ``next_batch=``); consumers ``join()``."""
+        assert ids.n_slots == self.n_slots
+        rt = self.rt
+        cur = torch.cuda.current_stream(rt.device)
+        side = rt.side_stream
+        side.wait_stream(cur)
+        with torch.cuda.stream(side):
+            self.counts.zero_()
+            d = ids.desc()
+            check(rt.lib.etr_sparse_plan_keys(rt.side_ctx, C.byref(d), ids.nnz or 0, table_rows, self.sorted_bag.data_ptr(),
+                                              self.unique_ids.data_ptr(), self.seg_start.data_ptr(),
+                                              self.counts[0:].data_ptr(), self.counts[1:].data_ptr(),
+                                              self.sorted_key.data_ptr(), side.cuda_stream))
+            if self.fm_prep is not None:
+                self._run_prepare(side)
+        self._pending = side
+        return self
+
     def prepare_fm(self) -> "SparsePlan":
-        """Row descriptors + long-run items for the tiled fused FM apply (etr_fm_fused_prepare): depend on the ids only,
-        so they are built once per plan -- right behind the sort, on the stream the plan was built on."""
-        if getattr(self, "fm_prep", None) is not None:
+        """Row descriptors + long-run items for the tiled fused FM apply / push (etr_fm_fused_prepare): depend on the ids
+        only, so they are built once per plan -- right behind the sort, on the stream the plan was built on."""
+        if self.fm_prep is not None:
             return self
         rt = self.rt
         side = self._pending
@@ -343,12 +363,17 @@ class SparsePlan:
             nbytes = int(rt.lib.etr_fm_fused_prepare_bytes(self.n_slots))
             self.fm_prep = rt.empty((nbytes,), torch.uint8)
             assert self.fm_prep.data_ptr() % 256 == 0
-            check(rt.lib.etr_fm_fused_prepare(rt.side_ctx if side is not None else rt.ctx, self.seg_start.data_ptr(),
-                                              self.unique_ids.data_ptr(), self.counts.data_ptr(), self.n_slots,
-                                              self.fm_prep.data_ptr(), nbytes, torch.cuda.current_stream(rt.device).cuda_stream))
+            self._run_prepare(side)
         if side is not None:
             self.fm_prep.record_stream(torch.cuda.current_stream(rt.device))
         return self
+
+    def _run_prepare(self, side) -> None:
+        rt = self.rt
+        check(rt.lib.etr_fm_fused_prepare(rt.side_ctx if side is not None else rt.ctx, self.seg_start.data_ptr(),
+                                          self.unique_ids.data_ptr(), self.counts.data_ptr(), self.n_slots,
+                                          self.fm_prep.data_ptr(), self.fm_prep.numel(),
+                                          torch.cuda.current_stream(rt.device).cuda_stream))
 
     def join(self) -> "SparsePlan":
         """Make the current stream wait for an overlapped plan (no-op otherwise)."""

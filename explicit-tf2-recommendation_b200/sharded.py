@@ -427,8 +427,10 @@ class PeerSlotGrad(PeerFMGrad):
         from .runtime import _TORCH2ETR, _p
         f, T = self.fused, self.table
         rt, t, plan, df = T.rt, f.table.desc(), f.plan.join(), f.dflat
+        prep = getattr(plan, "fm_prep", None)             # row descriptors / long-run items built with the plan, if any
         check(rt.lib.etr_fm_fused_backward_push(
             rt.ctx, C.byref(t), f.k, f.ids.F, f.ids.B, plan.sorted_bag.data_ptr(), plan.seg_start.data_ptr(),
             plan.unique_ids.data_ptr(), plan.counts.data_ptr(), plan.n_slots, f.dlogit.data_ptr(), f.sumv.data_ptr(),
             _p(df), _TORCH2ETR[df.dtype] if df is not None else 0, df.stride(0) if df is not None else 0, f.flat_col0,
-            self.slot_of_u.data_ptr(), T.cap, T._mb["grads_ptrs"], rt.stream))
+            self.slot_of_u.data_ptr(), T.cap, T._mb["grads_ptrs"], prep.data_ptr() if prep is not None else None,
+            prep.numel() if prep is not None else 0, rt.stream))

@@ -477,7 +477,10 @@ int etr_fm_fused_backward_push(etr_ctx* ctx, const etr_table* table, int32_t k, 
                                const int32_t* d_sorted_bag, const int32_t* d_seg_start, const int64_t* d_unique_ids,
                                const int32_t* d_n_unique, int64_t n_slots, const float* d_dlogit, const float* d_sumv,
                                const void* d_dflat, int32_t flat_dtype, int64_t flat_ld, int32_t flat_col0,
-                               const int32_t* d_slot_of_u, int32_t cap, float* const* h_grads_mb, void* stream);
+                               const int32_t* d_slot_of_u, int32_t cap, float* const* h_grads_mb,
+                               const void* d_prep, int64_t prep_bytes, void* stream);
+/* (d_prep: the plan's prepared lists from etr_fm_fused_prepare, or NULL -- k = 16 with a bf16 / no dflat then takes the
+ * tiled kernel either way and builds the lists in the ctx workspace first.)                                     */
 /* De-duplicated row exchange of the peer form (forward of a row-sharded Embedding gather,
  * 2.FM/CustomLayers.py:146-147 across GPUs).  etr_shard_request routes every unique id of the
  * rank's batch (etr_sparse_plan output) to its owner's request mailbox (local row numbers, region

@@ -29,8 +29,10 @@ def main():
     F, k, V, C, B = 26, 16, 100003, 13, 4096
     names, cont = [f"f{i}" for i in range(F)], [f"c{i}" for i in range(C)]
     msgs = []
-    for mode, graph, prec in (("a2a", False, "fp32"), ("peer-pull", False, "fp32"), ("peer-pull", True, "fp32"),
-                              ("peer", False, "bf16"), ("peer", True, "bf16")):
+    # ahead: Trainer next_batch= (the plan of step i+1 is sorted on the side stream during step i; 3 buffer sets)
+    for mode, graph, prec, ahead in (("a2a", False, "fp32", False), ("peer-pull", False, "fp32", False),
+                                     ("peer-pull", True, "fp32", False), ("peer", False, "bf16", False),
+                                     ("peer", True, "bf16", False), ("peer", True, "bf16", True)):
         # "peer" + bf16 tower takes the fused train step with the de-duplicated request/serve exchange
         sharded = L.DeepFMRankingLayer(names, V, k, continuous_features=cont, seed=3, shard=mode, check_ids=False,
                                        mlp_precision=prec)
@@ -61,9 +63,17 @@ def main():
 
         tr_s = L.Trainer(sharded, lr=1e-2, graph=graph)
         tr_f = L.Trainer(full, lr=1e-2)
-        for step in range(6 if graph else 3):           # graph mode: 2 buffer sets x (2 eager + capture/replay)
-            d, y = batch()
-            ls = tr_s.train_step(d, y).clone()
+        n_steps = (13 if ahead else 6) if graph else 3  # graph mode: 2 (3) buffer sets x (2 eager + capture/replay)
+        feed = [batch() for _ in range(n_steps + 1)]
+        staged = tr_s.stage(*feed[0]) if ahead and graph else None
+        for step in range(n_steps):
+            d, y = feed[step]
+            if ahead and graph:
+                nxt = tr_s.stage(*feed[step + 1])
+                ls = tr_s.train_step(staged, None, nxt).clone()
+                staged = nxt
+            else:
+                ls = tr_s.train_step(d, y).clone()
             # the unsharded reference sees the global batch
             gd = {}
             for n, t in d.items():
@@ -103,7 +113,7 @@ def main():
             dist.broadcast(ref, 0)
             assert torch.equal(ref, sharded.params.value), f"rank {rank}: dense replicas diverged"
         dist.barrier()
-        msgs.append(f"{mode}{'+graph' if graph else ''}/{prec}: table_err={err_t:.2e} dense_err={err_d:.2e}")
+        msgs.append(f"{mode}{'+graph' if graph else ''}{'+ahead' if ahead else ''}/{prec}: table_err={err_t:.2e} dense_err={err_d:.2e}")
     # every other model family that gathers from one shared table: all-to-all form (DCN vector / matrix cross, PNN)
     for model in ("dcn_vec", "dcn_matrix", "pnn"):
         Fm, Vm, Bm = 10, 60013, 1024
