@@ -1297,6 +1297,8 @@ class Trainer:
         # static buffer sets: 2 = stage step i+1 while step i runs; 3 for the plan-ahead of peer-sharded layers (step i
         # already reads the ids of step i+1, so those are staged while step i-1 runs)
         self.depth = (3 if self.peer is not None else 2) if graph else 1
+        if self.peer is not None:
+            self.peer.n_req_sets = max(self.peer.n_req_sets, self.depth)      # one request-mailbox set per buffer set
         self._graphs: Dict[tuple, list] = {}
         self._copy_stream = self._d2h_stream = None
 
@@ -1389,6 +1391,11 @@ class Trainer:
                     nsl.plan.prepare_fm()             # row descriptors / long-run items of the tiled push kernel
             else:
                 nsl.plan.rebuild(nsl.batch.ids, rows)
+            if getattr(self.layer, "shard_mode", None) == "peer":
+                # ... and its requests go to the owners' mailbox set of that buffer set (the barrier that closes this
+                # step orders them before the next step's serve)
+                with torch.cuda.stream(rt.side_stream):
+                    self.peer.request(nsl.plan, nsl.batch.ids.B, nsl.batch.ids.F, nsl.index, rt.side_stream.cuda_stream)
         fused = None
         if getattr(self.layer, "fused_train_ok", None) and self.layer.fused_train_ok():
             fused = self.layer.train_forward_backward(inputs, y, 1.0 / self.dp_world, plan=pre) if pre is not None else \
@@ -1412,12 +1419,12 @@ class Trainer:
             import torch.distributed as dist
             dist.all_reduce(self.layer.params.grad)   # replicated dense variables: sum of the ranks' grads
         self.apply_gradients(grads)
-        if self.peer is not None:
-            self.peer.barrier()                       # owners have applied: shards and mailboxes are free again
         if self.peer is not None and nsl is not None and nsl is not sl:
-            nsl.plan.join()                           # the look-ahead sort belongs to THIS step (timed with it)
+            nsl.plan.join()                           # the look-ahead sort + requests belong to THIS step (timed with it)
             nsl.plan._pending = None
             nsl.plan_ready = True
+        if self.peer is not None:
+            self.peer.barrier()                       # owners have applied: shards and mailboxes are free again
         if sl is not None and not torch.cuda.is_current_stream_capturing():
             sl.used = True
             sl.compute_done.record(torch.cuda.current_stream(rt.device))
@@ -1489,8 +1496,9 @@ class Trainer:
             names = getattr(lay, "feature_names", None) or lay.categorical_features
             cont_names = list(getattr(lay, "continuous_features", []))
             slots = []
-            for _ in range(self.depth):
+            for q in range(self.depth):
                 sl = Trainer._Slot()
+                sl.index = q
                 sl.ids_buf = rt.empty((len(names), B), torch.int64)
                 sl.cont_buf = rt.empty((max(len(cont_names), 1), B), torch.float32)
                 sl.lab_buf = rt.empty((B,), torch.float32)

@@ -251,6 +251,9 @@ class PeerShardedTable:
         self._mb = None
         self._gacc = None
         self.cap = 0
+        # request mailboxes (ids + counts) come in ``n_req_sets`` sets: set 0 serves requests made inside the step, the
+        # Trainer's plan-ahead sends the requests of the batch staged in buffer set s into set s one step early
+        self.n_req_sets, self._mb_sets, self._cur_set = 1, 0, 0
         if world > 1:
             dist.barrier(group=group)
 
@@ -318,22 +321,27 @@ class PeerShardedTable:
         """[world][cap] regions per owner; cap = 1.5x the balanced share of a batch's slots (+1024).
         Collective (every rank calls it with the same n_slots)."""
         cap = (3 * n_slots // (2 * self.world) + 1024 + 63) // 64 * 64
-        if self._mb is not None and cap <= self.cap:
+        if self._mb is not None and cap <= self.cap and self._mb_sets >= self.n_req_sets:
             return
+        cap = max(cap, self.cap)
         assert not torch.cuda.is_current_stream_capturing(), "size the mailbox with an eager step before capture"
         torch.cuda.synchronize(self.rt.device)
-        W, ld, rt = self.world, self.stride, self.rt
-        ids = PeerBuffer(rt, W * cap * 8, W, self.rank, self.group)
+        W, ld, rt, S = self.world, self.stride, self.rt, self.n_req_sets
+        ids = PeerBuffer(rt, S * W * cap * 8, W, self.rank, self.group)
         grads = PeerBuffer(rt, W * cap * ld * 4, W, self.rank, self.group)
-        counts = PeerBuffer(rt, 64 * 4, W, self.rank, self.group)
+        counts = PeerBuffer(rt, S * 64 * 4, W, self.rank, self.group)
+        ids_all, counts_all = ids.tensor((S, W * cap), torch.int64), counts.tensor((S, 64), torch.int32)
         self._mb = {
             "ids": ids, "grads": grads, "counts": counts,
-            "ids_t": ids.tensor((W * cap,), torch.int64), "grads_t": grads.tensor((W * cap, ld), torch.float32),
-            "counts_t": counts.tensor((W,), torch.int32),
-            "ids_ptrs": ids.peer_array(self.rank * cap * 8), "grads_ptrs": grads.peer_array(self.rank * cap * ld * 4),
-            "counts_ptrs": counts.peer_array(self.rank * 4), "local_cnt": rt.zeros((W,), torch.int32),
+            "ids_t": [ids_all[q] for q in range(S)], "grads_t": grads.tensor((W * cap, ld), torch.float32),
+            "counts_t": [counts_all[q, :W] for q in range(S)],
+            "ids_ptrs": [ids.peer_array((q * W + self.rank) * cap * 8) for q in range(S)],
+            "grads_ptrs": grads.peer_array(self.rank * cap * ld * 4),
+            "counts_ptrs": [counts.peer_array((q * 64 + self.rank) * 4) for q in range(S)],
+            "local_cnt": [rt.zeros((W,), torch.int32) for _ in range(S)],
             "touched": rt.empty((W * cap,), torch.int32), "n_touched": rt.zeros((1,), torch.int32),
         }
+        self._mb_sets = S
         # response buffer of the de-duplicated forward exchange: [owner][cap][ld] on THIS rank; owner g writes its
         # region through the pointer resp_ptrs[source] = source's buffer + g * cap * ld * 4
         resp = PeerBuffer(rt, W * cap * ld * 4, W, self.rank, self.group)
@@ -346,33 +354,48 @@ class PeerShardedTable:
 
     def push(self, unique_ids: torch.Tensor, n_unique: torch.Tensor, max_unique: int, unique_grad: torch.Tensor):
         rt, mb = self.rt, self._mb
+        self._cur_set = 0
         check(rt.lib.etr_shard_push(rt.ctx, unique_ids.data_ptr(), n_unique.data_ptr(), max_unique,
-                                    unique_grad.data_ptr(), unique_grad.shape[1], self.world, self.cap, mb["ids_ptrs"],
-                                    mb["grads_ptrs"], mb["counts_ptrs"], mb["local_cnt"].data_ptr(), rt.stream))
+                                    unique_grad.data_ptr(), unique_grad.shape[1], self.world, self.cap, mb["ids_ptrs"][0],
+                                    mb["grads_ptrs"], mb["counts_ptrs"][0], mb["local_cnt"][0].data_ptr(), rt.stream))
 
     # -- de-duplicated forward exchange ------------------------------------------
-    def exchange_forward(self, plan, B: int, F: int):
-        """request -> barrier -> serve -> barrier -> virtual ids.  Returns (VirtualTable over the response buffer,
-        IdsBatch of response-buffer rows [B,F], slot_of_u) -- the fused gather kernel then runs on local memory."""
-        from .runtime import IdsBatch
+    def request(self, plan, B: int, F: int, req_set: int = 0, stream=None):
+        """unique ids -> the owners' request mailboxes (set ``req_set``), and the occurrence -> response-row map.  Both
+        depend on the plan only, so the Trainer's plan-ahead runs them one step early (``stream`` = its side stream)."""
         rt, W = self.rt, self.world
         self.ensure_mailbox(plan.n_slots)
-        mb, cap, ld = self._mb, self.cap, self.stride
-        slot_of_u = rt.empty((max(plan.n_slots, 1),), torch.int32)
+        mb, cap = self._mb, self.cap
+        if getattr(plan, "slot_of_u", None) is None:
+            plan.slot_of_u = rt.empty((max(plan.n_slots, 1),), torch.int32)
+            plan.vid = rt.empty((B * F,), torch.int64)
+        st = stream if stream is not None else rt.stream
         check(rt.lib.etr_shard_request(rt.ctx, plan.unique_ids.data_ptr(), plan.counts.data_ptr(), plan.n_slots, W, cap,
-                                       mb["ids_ptrs"], mb["counts_ptrs"], mb["local_cnt"].data_ptr(),
-                                       slot_of_u.data_ptr(), rt.stream))
-        self.barrier()
+                                       mb["ids_ptrs"][req_set], mb["counts_ptrs"][req_set], mb["local_cnt"][req_set].data_ptr(),
+                                       plan.slot_of_u.data_ptr(), st))
+        check(rt.lib.etr_shard_vid_map(rt.ctx, plan.sorted_bag.data_ptr(), plan.seg_start.data_ptr(),
+                                       plan.counts.data_ptr(), plan.n_slots, plan.slot_of_u.data_ptr(), plan.vid.data_ptr(), st))
+        plan.req_set = req_set
+
+    def exchange_forward(self, plan, B: int, F: int):
+        """[request -> virtual ids -> barrier ->] serve -> barrier.  Returns (VirtualTable over the response buffer,
+        IdsBatch of response-buffer rows [B,F], slot_of_u) -- the fused gather kernel then runs on local memory.  The
+        bracketed part is skipped when the plan's requests were sent ahead of time (``request``; the barrier that closed
+        the previous step has ordered them)."""
+        from .runtime import IdsBatch
+        rt, W = self.rt, self.world
+        if getattr(plan, "req_set", None) is None:
+            self.request(plan, B, F, 0)
+            self.barrier()
+        q, plan.req_set = plan.req_set, None
+        self._cur_set = q
+        mb, cap, ld = self._mb, self.cap, self.stride
         t = self.local.desc()
-        check(rt.lib.etr_shard_serve(rt.ctx, C.byref(t), mb["ids_t"].data_ptr(), mb["counts_t"].data_ptr(), W, cap,
+        check(rt.lib.etr_shard_serve(rt.ctx, C.byref(t), mb["ids_t"][q].data_ptr(), mb["counts_t"][q].data_ptr(), W, cap,
                                      mb["resp_ptrs"], ld, rt.stream))
         self.barrier()
-        vid = rt.empty((B * F,), torch.int64)
-        check(rt.lib.etr_shard_vid_map(rt.ctx, plan.sorted_bag.data_ptr(), plan.seg_start.data_ptr(),
-                                       plan.counts.data_ptr(), plan.n_slots, slot_of_u.data_ptr(), vid.data_ptr(),
-                                       rt.stream))
         vt = VirtualTable(rt, mb["resp_t"], self.width)
-        return vt, IdsBatch(rt, vid, B, F, 1, F, 1, 1), slot_of_u
+        return vt, IdsBatch(rt, plan.vid, B, F, 1, F, 1, 1), plan.slot_of_u
 
     def apply_mailbox(self, d_lr_t: torch.Tensor, b1: float, b2: float, eps: float, mode: int):
         """owner side, no sort: the G source regions are added into the dense accumulator in rank order
@@ -386,8 +409,9 @@ class PeerShardedTable:
             assert not torch.cuda.is_current_stream_capturing()
             assert ld >= self.width + 1, "the accumulator row needs a spare last column for its stamp"
             self._gacc = rt.zeros((max(self.local_rows, 1), ld))
-        check(rt.lib.etr_shard_mailbox_accumulate(rt.ctx, mb["ids_t"].data_ptr(), mb["grads_t"].data_ptr(),
-                                                  mb["counts_t"].data_ptr(), W, cap, ld, self._gacc.data_ptr(),
+        q = self._cur_set                                 # the request set of the step being applied (the owner kept the ids)
+        check(rt.lib.etr_shard_mailbox_accumulate(rt.ctx, mb["ids_t"][q].data_ptr(), mb["grads_t"].data_ptr(),
+                                                  mb["counts_t"][q].data_ptr(), W, cap, ld, self._gacc.data_ptr(),
                                                   self._epoch.data_ptr(),
                                                   mb["touched"].data_ptr(), mb["n_touched"].data_ptr(), W * cap, rt.stream))
         t = self.local.desc()

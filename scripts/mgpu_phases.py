@@ -63,16 +63,17 @@ def main():
         plan = SparsePlan(rt, ids, peer.rows)
         mark("ids assemble + sorted plan (CUB sort + unique)")
         peer.ensure_mailbox(plan.n_slots)
+        peer._cur_set = 0
         mb, cap, ld, W = peer._mb, peer.cap, peer.stride, world
         slot_of_u = rt.empty((plan.n_slots,), torch.int32)
         check(rt.lib.etr_shard_request(rt.ctx, plan.unique_ids.data_ptr(), plan.counts.data_ptr(), plan.n_slots, W, cap,
-                                       mb["ids_ptrs"], mb["counts_ptrs"], mb["local_cnt"].data_ptr(),
+                                       mb["ids_ptrs"][0], mb["counts_ptrs"][0], mb["local_cnt"][0].data_ptr(),
                                        slot_of_u.data_ptr(), rt.stream))
         mark("request: unique ids -> owners' mailboxes")
         peer.barrier()
         mark("barrier")
         t = peer.local.desc()
-        check(rt.lib.etr_shard_serve(rt.ctx, C.byref(t), mb["ids_t"].data_ptr(), mb["counts_t"].data_ptr(), W, cap,
+        check(rt.lib.etr_shard_serve(rt.ctx, C.byref(t), mb["ids_t"][0].data_ptr(), mb["counts_t"][0].data_ptr(), W, cap,
                                      mb["resp_ptrs"], ld, rt.stream))
         mark("serve: owners write the rows into the requesters' buffers")
         peer.barrier()
