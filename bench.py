@@ -257,7 +257,8 @@ def workload_config(args, B, graph):
                                              "pushed to the owners' mailboxes, device-side barriers (no NCCL in the step)",
                                 "a2a": "NCCL all-to-all"}[getattr(args, "shard", "peer")])
                             if args.gpus > 1 else "dp1"),
-            "l2": "L2 flushed (512 MiB write) before every timed step", "cuda_graph": graph}
+            "l2": "L2 flushed (512 MiB write, then 256 MiB read so that the cache holds clean lines) before every timed step",
+            "cuda_graph": graph}
 
 
 def run_c3(args):
@@ -769,7 +770,17 @@ def main():
 
     # the all-to-all sharded step syncs split sizes on the host (no graph); the peer-memory step does not
     use_graph = (not args.no_graph) and (world == 1 or args.shard != "a2a")
-    flush = torch.empty(512 << 20, dtype=torch.uint8, device=dev)
+    flush_wr = torch.empty(512 << 20, dtype=torch.uint8, device=dev)
+    flush_rd = torch.ones(64 << 20, dtype=torch.float32, device=dev)
+
+    class flush:
+        """L2 flush between timed iterations: a 512 MiB WRITE evicts everything, then a 256 MiB READ replaces the dirty
+        flush lines by clean ones -- otherwise the timed kernel pays the write-back of up to 126 MB of flush data
+        (measured: +8 us on the 110 us apply kernel, profiles/r02_mb_apply.md)."""
+        @staticmethod
+        def zero_():
+            flush_wr.zero_()
+            flush_rd.sum()
 
     def barrier():
         if world > 1:

@@ -1093,31 +1093,31 @@ class MatrixCrossLayer(CrossLayer):
         return xl
 
     def _backward_bf16(self, gout: torch.Tensor) -> torch.Tensor:
-        from .runtime import cast_bf16, gemm_bf16_tn, transpose_bf16
+        from .runtime import cast_bf16, gemm_bf16_wgrad
         rt = self.rt
         xs, us = self._ctx["xs"], self._ctx["us"]
         x0 = xs[0]
         B, Di = x0.shape[0], self.D + self.front_pad
         W = self.params["cross/W"]
-        G = gout.to(torch.bfloat16).contiguous()
-        if G.data_ptr() == gout.data_ptr():
-            G = G.clone()
-        dx0 = rt.zeros((B, Di))
+        # G starts as the caller's gradient (possibly a column slice of a wider bf16 matrix: read through its row pitch)
+        G = gout if (gout.dtype == torch.bfloat16 and gout.stride(1) == 1 and gout.stride(0) % 2 == 0) else \
+            gout.to(torch.bfloat16).contiguous()
+        dx0 = rt.empty((B, Di))
+        assert x0.stride(0) == Di
         for l in reversed(range(self.layer_num)):
             du = rt.empty((B, Di), torch.bfloat16)
-            check(rt.lib.etr_cross_mat_bwd_elementwise_bf16(rt.ctx, G.data_ptr(), x0.data_ptr(), us[l].data_ptr(),
-                                                            B * Di, du.data_ptr(), dx0.data_ptr(), rt.stream))
-            # dW_l = dU^T X_l : A = dU^T [Di,B], B operand = X_l^T [Di,B]; fp32 result
-            dut = transpose_bf16(rt, du, B, Di)
-            xlt = transpose_bf16(rt, xs[l], B, Di)
-            gemm_bf16_tn(rt, dut, xlt, self.params.g("cross/W")[l], Di, Di, B)
+            check(rt.lib.etr_cross_mat_bwd_elementwise_bf16(rt.ctx, G.data_ptr(), G.stride(0), x0.data_ptr(), us[l].data_ptr(),
+                                                            B, Di, du.data_ptr(), dx0.data_ptr(),
+                                                            int(l == self.layer_num - 1), rt.stream))
+            # dW_l = dU^T X_l : both operands as stored ([B, Di], MN-major UMMA operands), split-K over the batch; fp32 result
+            gemm_bf16_wgrad(rt, du, xs[l], self.params.g("cross/W")[l], Di, Di, B)
             check(rt.lib.etr_colsum_bf16(rt.ctx, du.data_ptr(), B, Di, Di, self.params.g("cross/b")[l].data_ptr(),
                                          rt.stream))
             # G_l = G_{l+1} + dU W_l : B operand [N=j, K=i] = W[i,j]  ->  W^T
             Wt = cast_bf16(rt, W[l], transpose=True)
             Gn = rt.empty((B, Di), torch.bfloat16)
             check(rt.lib.etr_gemm_bf16_tn_residual(rt.ctx, B, Di, Di, du.data_ptr(), Di, Wt.data_ptr(), Wt.stride(0),
-                                                   G.data_ptr(), Di, Gn.data_ptr(), Di, rt.stream))
+                                                   G.data_ptr(), G.stride(0), Gn.data_ptr(), Di, rt.stream))
             G = Gn
         check(rt.lib.etr_add_bf16_into_f32(rt.ctx, G.data_ptr(), B * Di, dx0.data_ptr(), rt.stream))
         return dx0

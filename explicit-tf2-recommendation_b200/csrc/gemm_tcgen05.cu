@@ -38,6 +38,7 @@ struct EpiParams {
   long long M, N;
   void* C; long long ldc; int c_bf16;            // LINEAR: output
   const float* bias; int act;
+  int accumulate;                                // LINEAR, fp32 C: C += act(acc + bias)
   const __nv_bfloat16* x0; const __nv_bfloat16* xl; long long ldx;   // CROSS inputs
   __nv_bfloat16* out; long long ldo;             // CROSS: x_{l+1}
   __nv_bfloat16* u; long long ldu;               // CROSS: optional U = xl W^T + b
@@ -121,10 +122,25 @@ __device__ __forceinline__ uint64_t make_kmajor_sw128_desc(uint32_t smem_addr) {
   return d;
 }
 
+// MN-major, 128-byte-swizzled operand (the operand's M / N extent is the contiguous one in memory): the tile is a row of
+// [64 mn x BLOCK_K k] boxes (one TMA box each, 8 KiB, rows of 128 bytes = 64 mn elements, one row per k), i.e. the
+// canonical layout ((8,n),(8,k)) : ((1,LBO),(8,SBO)) in 16-byte units (cute/atom/mma_traits_sm100.hpp):
+// LBO = byte distance between 64-element mn blocks = 8192, SBO = byte distance between groups of 8 k rows = 1024.
+__device__ __forceinline__ uint64_t make_mnmajor_sw128_desc(uint32_t smem_addr) {
+  uint64_t d = 0;
+  d |= (uint64_t)((smem_addr & 0x3FFFF) >> 4);
+  d |= (uint64_t)(8192 >> 4) << 16;
+  d |= (uint64_t)(1024 >> 4) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)2 << 61;
+  return d;
+}
+
 // kind::f16 instruction descriptor: D = F32 (bits 4-5 = 1), A = B = BF16 (bits 7-9,
 // 10-12 = 1), both K-major (bits 15, 16 = 0), N >> 3 in bits [17,23), M >> 4 in [24,29).
-__device__ __forceinline__ uint32_t make_idesc(int umma_m, int umma_n) {
-  return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(umma_n >> 3) << 17) | ((uint32_t)(umma_m >> 4) << 24);
+__device__ __forceinline__ uint32_t make_idesc(int umma_m, int umma_n, bool mn_major = false) {
+  return (1u << 4) | (1u << 7) | (1u << 10) | (mn_major ? (3u << 15) : 0u) | ((uint32_t)(umma_n >> 3) << 17) |
+         ((uint32_t)(umma_m >> 4) << 24);
 }
 
 __device__ __forceinline__ float act_apply(float x, int act) {
@@ -136,11 +152,14 @@ __device__ __forceinline__ float act_apply(float x, int act) {
   }
 }
 
-template <int BLOCK_N, int STAGES>
+// MN = false: A [M,K], B [N,K] (K contiguous, "TN").  MN = true: A [K,M], B [K,N] (M / N contiguous): C = A^T B, the
+// weight-gradient shape dW = dY^T X with K = batch -- both operands are read as they are stored, no transposes.
+template <int BLOCK_N, int STAGES, bool MN = false>
 __global__ void __launch_bounds__(kThreads, 2)
 gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b, const EpiParams ep) {
   constexpr uint32_t A_BYTES = BLOCK_M * BLOCK_K * 2;        // 16 KiB
-  constexpr uint32_t B_BYTES = BLOCK_N * BLOCK_K * 2;
+  constexpr int NB_BOX = (BLOCK_N + 63) / 64;                // MN: 64-column boxes of the B tile
+  constexpr uint32_t B_BYTES = MN ? NB_BOX * 64 * BLOCK_K * 2 : BLOCK_N * BLOCK_K * 2;
   constexpr uint32_t TMEM_COLS = BLOCK_N <= 32 ? 32 : (BLOCK_N <= 64 ? 64 : (BLOCK_N <= 128 ? 128 : 256));
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   // 1024-byte alignment is required by the 128B swizzle atoms
@@ -182,25 +201,36 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
         mbar_wait(smem_u32(&empty_bar[s]), ph ^ 1);
         mbar_expect_tx(smem_u32(&full_bar[s]), A_BYTES + B_BYTES);
         const int k0 = (kb_begin + i) * BLOCK_K;
-        tma_load_2d(smem_u32(smem_a + s * A_BYTES), &map_a, smem_u32(&full_bar[s]), k0, m_tile * BLOCK_M);
-        tma_load_2d(smem_u32(smem_b + s * B_BYTES), &map_b, smem_u32(&full_bar[s]), k0, n_tile * BLOCK_N);
+        if (MN) {
+#pragma unroll
+          for (int b = 0; b < BLOCK_M / 64; ++b)
+            tma_load_2d(smem_u32(smem_a + s * A_BYTES + b * 8192), &map_a, smem_u32(&full_bar[s]), m_tile * BLOCK_M + b * 64, k0);
+#pragma unroll
+          for (int b = 0; b < NB_BOX; ++b)
+            tma_load_2d(smem_u32(smem_b + s * B_BYTES + b * 8192), &map_b, smem_u32(&full_bar[s]), n_tile * BLOCK_N + b * 64, k0);
+        } else {
+          tma_load_2d(smem_u32(smem_a + s * A_BYTES), &map_a, smem_u32(&full_bar[s]), k0, m_tile * BLOCK_M);
+          tma_load_2d(smem_u32(smem_b + s * B_BYTES), &map_b, smem_u32(&full_bar[s]), k0, n_tile * BLOCK_N);
+        }
       }
     }
   } else if (warp == 1) {
     // ===== MMA issuer =====
     if (lane == 0) {
-      const uint32_t idesc = make_idesc(BLOCK_M, BLOCK_N);
+      const uint32_t idesc = make_idesc(BLOCK_M, BLOCK_N, MN);
       for (int i = 0; i < nkb; ++i) {
         const int s = i % STAGES;
         const uint32_t ph = (i / STAGES) & 1;
         mbar_wait(smem_u32(&full_bar[s]), ph);
         fence_after();
-        const uint64_t da = make_kmajor_sw128_desc(smem_u32(smem_a + s * A_BYTES));
-        const uint64_t db = make_kmajor_sw128_desc(smem_u32(smem_b + s * B_BYTES));
+        const uint64_t da = MN ? make_mnmajor_sw128_desc(smem_u32(smem_a + s * A_BYTES)) : make_kmajor_sw128_desc(smem_u32(smem_a + s * A_BYTES));
+        const uint64_t db = MN ? make_mnmajor_sw128_desc(smem_u32(smem_b + s * B_BYTES)) : make_kmajor_sw128_desc(smem_u32(smem_b + s * B_BYTES));
 #pragma unroll
         for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
-          // advance 16 bf16 = 32 bytes inside the swizzle atom: +2 in the (>>4) address field
-          umma_f16(tmem_base, da + (uint64_t)(k * 2), db + (uint64_t)(k * 2), idesc, (i | k) != 0 ? 1u : 0u);
+          // K-major: advance 16 bf16 = 32 bytes inside the swizzle atom: +2 in the (>>4) address field;
+          // MN-major: advance 16 k rows of 128 bytes = 2048 bytes: +128
+          const uint64_t adv = MN ? (uint64_t)(k * 128) : (uint64_t)(k * 2);
+          umma_f16(tmem_base, da + adv, db + adv, idesc, (i | k) != 0 ? 1u : 0u);
         }
         umma_commit(smem_u32(&empty_bar[s]));        // frees the smem stage once these MMAs retire
       }
@@ -360,6 +390,34 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
 #pragma unroll
         for (int i = 0; i < 32; ++i)
           val[i] = act_apply(__uint_as_float(v[i]) + ((ep.bias && i < ncol) ? ep.bias[col0 + i] : 0.f), ep.act);
+        if (ep.accumulate && !ep.c_bf16) {             // C += ... : this block of C -> tile (coalesced) -> own row
+          const float* cbase = reinterpret_cast<const float*>(ep.C);
+          const bool vec = full && ((ep.ldc & 3) == 0) && ((reinterpret_cast<uintptr_t>(cbase + col0) & 15) == 0);
+          __syncwarp();
+          if (vec) {
+            const int g8 = lane & 7, r8 = lane >> 3;
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              const int r = r8 + 4 * j;
+              const long long rr = row_base + r;
+              float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
+              if (rr < ep.M) a = *reinterpret_cast<const float4*>(cbase + rr * ep.ldc + col0 + 4 * g8);
+              *reinterpret_cast<float4*>(&T[r * TS + 4 * g8]) = a;
+            }
+          } else {
+#pragma unroll
+            for (int r = 0; r < 32; ++r) {
+              const long long rr = row_base + r;
+              T[r * TS + lane] = (rr < ep.M && col_ok) ? cbase[rr * ep.ldc + col0 + lane] : 0.f;
+            }
+          }
+          __syncwarp();
+#pragma unroll
+          for (int i = 0; i < 32; i += 4) {
+            const float4 t = *reinterpret_cast<const float4*>(&T[lane * TS + i]);
+            val[i] += t.x; val[i + 1] += t.y; val[i + 2] += t.z; val[i + 3] += t.w;
+          }
+        }
         store_block(ep.C, ep.ldc, ep.c_bf16 != 0, val);
       } else {   // EPI_CROSS: u = acc + b ; out = x0 * u + xl   (x0 == NULL: out = u + xl)
 #pragma unroll
@@ -468,15 +526,18 @@ __global__ void __launch_bounds__(256) transpose_bf16_kernel(const __nv_bfloat16
 
 // bf16 elementwise pieces of the cross-matrix backward (SURVEY a'):
 //   du = G (.) x0 (bf16) ; dx0 += G (.) u (fp32 accumulate)
-__global__ void __launch_bounds__(256) cross_bwd_elem_bf16_kernel(const __nv_bfloat16* G, const __nv_bfloat16* x0,
-                                                                  const __nv_bfloat16* u, long long n2,
-                                                                  __nv_bfloat16* du, float* dx0) {
+__global__ void __launch_bounds__(256) cross_bwd_elem_bf16_kernel(const __nv_bfloat16* G, long long cols2, long long ldg2,
+                                                                  const __nv_bfloat16* x0, const __nv_bfloat16* u, long long n2,
+                                                                  __nv_bfloat16* du, float* dx0, int init) {
+  // G may be a column slice of a wider matrix (row pitch ldg2 bf16x2 pairs); x0, u, du, dx0 are dense [rows, cols]
   for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < n2; t += (long long)gridDim.x * blockDim.x) {
-    const float2 g = __bfloat1622float2(reinterpret_cast<const __nv_bfloat162*>(G)[t]);
+    const long long tg = (ldg2 == cols2) ? t : (t / cols2) * ldg2 + t % cols2;
+    const float2 g = __bfloat1622float2(reinterpret_cast<const __nv_bfloat162*>(G)[tg]);
     const float2 a = __bfloat1622float2(reinterpret_cast<const __nv_bfloat162*>(x0)[t]);
     const float2 b = __bfloat1622float2(reinterpret_cast<const __nv_bfloat162*>(u)[t]);
     reinterpret_cast<__nv_bfloat162*>(du)[t] = __floats2bfloat162_rn(g.x * a.x, g.y * a.y);
-    float2 d = reinterpret_cast<float2*>(dx0)[t];
+    float2 d = make_float2(0.f, 0.f);
+    if (!init) d = reinterpret_cast<float2*>(dx0)[t];
     d.x += g.x * b.x; d.y += g.y * b.y;
     reinterpret_cast<float2*>(dx0)[t] = d;
   }
@@ -555,16 +616,33 @@ static int make_map(CUtensorMap* map, const void* base, long long rows, long lon
   return ETR_OK;
 }
 
-template <int BLOCK_N, int STAGES>
+// MN-major operand [k_rows, mn_cols] (mn contiguous, leading dimension ld): box = [BLOCK_K k rows, 64 mn columns]
+static int make_map_mn(CUtensorMap* map, const void* base, long long k_rows, long long mn_cols, long long ld) {
+  EncodeTiledFn enc = get_encode();
+  if (!enc) { etr_set_error("cuTensorMapEncodeTiled is not available from the driver"); return ETR_ECUDA; }
+  if (((uintptr_t)base & 15) || (ld * 2) % 16 != 0) {
+    etr_set_error("tcgen05 GEMM operands need 16-byte aligned base and row pitch (ld %% 8 == 0)");
+    return ETR_EINVAL;
+  }
+  cuuint64_t gdim[2] = {(cuuint64_t)mn_cols, (cuuint64_t)k_rows};
+  cuuint64_t gstride[1] = {(cuuint64_t)ld * 2};
+  cuuint32_t box[2] = {64u, (cuuint32_t)BLOCK_K};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), gdim, gstride, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) { etr_set_error("cuTensorMapEncodeTiled failed with CUresult %d", (int)r); return ETR_ECUDA; }
+  return ETR_OK;
+}
+
+template <int BLOCK_N, int STAGES, bool MN = false>
 static int launch_tile(etr_ctx* ctx, const CUtensorMap& ma, const CUtensorMap& mb, const EpiParams& ep, dim3 grid,
                        cudaStream_t s) {
-  constexpr size_t smem = (size_t)STAGES * (BLOCK_M * BLOCK_K * 2 + BLOCK_N * BLOCK_K * 2) + (2 * STAGES + 2) * 8 + 1024;
-  static bool attr_done = false;
-  if (!attr_done) {
-    ETR_CUDA(cudaFuncSetAttribute(gemm_bf16_tn_kernel<BLOCK_N, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    attr_done = true;
-  }
-  gemm_bf16_tn_kernel<BLOCK_N, STAGES><<<grid, kThreads, smem, s>>>(ma, mb, ep);
+  constexpr size_t b_bytes = MN ? (size_t)((BLOCK_N + 63) / 64) * 64 * BLOCK_K * 2 : (size_t)BLOCK_N * BLOCK_K * 2;
+  constexpr size_t smem = (size_t)STAGES * (BLOCK_M * BLOCK_K * 2 + b_bytes) + (2 * STAGES + 2) * 8 + 1024;
+  // the opt-in is per device: set it on every call (one process may drive several GPUs)
+  ETR_CUDA(cudaFuncSetAttribute(gemm_bf16_tn_kernel<BLOCK_N, STAGES, MN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  gemm_bf16_tn_kernel<BLOCK_N, STAGES, MN><<<grid, kThreads, smem, s>>>(ma, mb, ep);
   ETR_LAUNCH_CHECK(ctx);
   return ETR_OK;
 }
@@ -582,12 +660,13 @@ static int pick_block_n(long long N) {
 
 static int run_gemm(etr_ctx* ctx, long long M, long long N, long long K, const void* A, long long lda, const void* B,
                     long long ldb, EpiParams ep, int allow_split, cudaStream_t s, void* C, long long ldc, int c_bf16,
-                    const float* bias, int act, float beta) {
-  const int bn = pick_block_n(N);
+                    const float* bias, int act, float beta, bool mn = false) {
+  int bn = pick_block_n(N);
+  if (mn && bn < 64) bn = 64;                        // MN-major tiles are built from 64-column boxes
   CUtensorMap ma, mb;
-  int st = make_map(&ma, A, M, K, lda, BLOCK_M);
+  int st = mn ? make_map_mn(&ma, A, K, M, lda) : make_map(&ma, A, M, K, lda, BLOCK_M);
   if (st != ETR_OK) return st;
-  st = make_map(&mb, B, N, K, ldb, bn);
+  st = mn ? make_map_mn(&mb, B, K, N, ldb) : make_map(&mb, B, N, K, ldb, bn);
   if (st != ETR_OK) return st;
   const long long mt = ceil_div(M, BLOCK_M), nt = ceil_div(N, bn);
   const int kbt = (int)ceil_div(K, BLOCK_K);
@@ -609,12 +688,21 @@ static int run_gemm(etr_ctx* ctx, long long M, long long N, long long K, const v
   }
   if (mt > 65535 || nt > 65535) { etr_set_error("tcgen05 GEMM: too many tiles"); return ETR_EUNSUPPORTED; }
   dim3 grid((unsigned)nt, (unsigned)mt, (unsigned)splits);
-  switch (bn) {
-    case 32: st = launch_tile<32, 4>(ctx, ma, mb, ep, grid, s); break;
-    case 64: st = launch_tile<64, 4>(ctx, ma, mb, ep, grid, s); break;
-    case 128: st = launch_tile<128, 3>(ctx, ma, mb, ep, grid, s); break;
-    case 240: st = launch_tile<240, 2>(ctx, ma, mb, ep, grid, s); break;
-    default: st = launch_tile<256, 2>(ctx, ma, mb, ep, grid, s); break;
+  if (mn) {
+    switch (bn) {
+      case 64: st = launch_tile<64, 4, true>(ctx, ma, mb, ep, grid, s); break;
+      case 128: st = launch_tile<128, 3, true>(ctx, ma, mb, ep, grid, s); break;
+      case 240: st = launch_tile<240, 2, true>(ctx, ma, mb, ep, grid, s); break;
+      default: st = launch_tile<256, 2, true>(ctx, ma, mb, ep, grid, s); break;
+    }
+  } else {
+    switch (bn) {
+      case 32: st = launch_tile<32, 4>(ctx, ma, mb, ep, grid, s); break;
+      case 64: st = launch_tile<64, 4>(ctx, ma, mb, ep, grid, s); break;
+      case 128: st = launch_tile<128, 3>(ctx, ma, mb, ep, grid, s); break;
+      case 240: st = launch_tile<240, 2>(ctx, ma, mb, ep, grid, s); break;
+      default: st = launch_tile<256, 2>(ctx, ma, mb, ep, grid, s); break;
+    }
   }
   if (st != ETR_OK) return st;
   if (splits > 1) {
@@ -642,6 +730,28 @@ int etr_gemm_bf16_tn(etr_ctx* ctx, int64_t M, int64_t N, int64_t K, const void* 
   ep.mode = tc::EPI_LINEAR;
   ep.C = d_C; ep.ldc = ldc; ep.c_bf16 = c_dtype == ETR_BF16; ep.bias = d_bias; ep.act = act;
   return tc::run_gemm(ctx, M, N, K, d_A, lda, d_B, ldb, ep, 1, (cudaStream_t)stream, d_C, ldc, ep.c_bf16, d_bias, act, 0.f);
+}
+
+int etr_gemm_bf16_nn_wgrad(etr_ctx* ctx, int64_t M, int64_t N, int64_t K, const void* d_A, int64_t lda, const void* d_B,
+                           int64_t ldb, float* d_C, int64_t ldc, void* stream) {
+  ETR_CHECK_ARG(ctx && d_A && d_B && d_C, "NULL argument");
+  ETR_CHECK_ARG(M > 0 && N > 0 && K > 0, "empty GEMM");
+  tc::EpiParams ep;
+  memset(&ep, 0, sizeof(ep));
+  ep.mode = tc::EPI_LINEAR;
+  ep.C = d_C; ep.ldc = ldc; ep.c_bf16 = 0;
+  return tc::run_gemm(ctx, M, N, K, d_A, lda, d_B, ldb, ep, 1, (cudaStream_t)stream, d_C, ldc, 0, nullptr, 0, 0.f, true);
+}
+
+int etr_gemm_bf16_tn_accumulate(etr_ctx* ctx, int64_t M, int64_t N, int64_t K, const void* d_A, int64_t lda, const void* d_B,
+                                int64_t ldb, float* d_C, int64_t ldc, void* stream) {
+  ETR_CHECK_ARG(ctx && d_A && d_B && d_C, "NULL argument");
+  ETR_CHECK_ARG(M > 0 && N > 0 && K > 0, "empty GEMM");
+  tc::EpiParams ep;
+  memset(&ep, 0, sizeof(ep));
+  ep.mode = tc::EPI_LINEAR;
+  ep.C = d_C; ep.ldc = ldc; ep.c_bf16 = 0; ep.accumulate = 1;
+  return tc::run_gemm(ctx, M, N, K, d_A, lda, d_B, ldb, ep, 0, (cudaStream_t)stream, d_C, ldc, 0, nullptr, 0, 0.f);
 }
 
 int etr_cross_mat_layer_bf16(etr_ctx* ctx, const void* d_x0, const void* d_xl, int64_t ldx, int64_t batch, int32_t D,
@@ -672,14 +782,15 @@ int etr_gemm_bf16_tn_residual(etr_ctx* ctx, int64_t M, int64_t N, int64_t K, con
   return tc::run_gemm(ctx, M, N, K, d_A, lda, d_B, ldb, ep, 0, (cudaStream_t)stream, nullptr, 0, 1, nullptr, 0, 0.f);
 }
 
-int etr_cross_mat_bwd_elementwise_bf16(etr_ctx* ctx, const void* d_g, const void* d_x0, const void* d_u, int64_t n,
-                                       void* d_du, float* d_dx0_accum, void* stream) {
+int etr_cross_mat_bwd_elementwise_bf16(etr_ctx* ctx, const void* d_g, int64_t ldg, const void* d_x0, const void* d_u,
+                                       int64_t rows, int64_t cols, void* d_du, float* d_dx0_accum, int32_t init, void* stream) {
   ETR_CHECK_ARG(ctx && d_g && d_x0 && d_u && d_du && d_dx0_accum, "NULL argument");
-  ETR_CHECK_ARG(n % 2 == 0, "n must be even (bf16x2 accesses)");
+  ETR_CHECK_ARG(cols % 2 == 0 && ldg % 2 == 0 && ldg >= cols && ((uintptr_t)d_g & 3) == 0, "cols / ldg must be even (bf16x2 accesses)");
+  const int64_t n = rows * cols;
   if (n <= 0) return ETR_OK;
   tc::cross_bwd_elem_bf16_kernel<<<grid_for(n / 2, 256, ctx->sm_count, 8), 256, 0, (cudaStream_t)stream>>>(
-      (const __nv_bfloat16*)d_g, (const __nv_bfloat16*)d_x0, (const __nv_bfloat16*)d_u, n / 2, (__nv_bfloat16*)d_du,
-      d_dx0_accum);
+      (const __nv_bfloat16*)d_g, cols / 2, ldg / 2, (const __nv_bfloat16*)d_x0, (const __nv_bfloat16*)d_u, n / 2,
+      (__nv_bfloat16*)d_du, d_dx0_accum, init);
   ETR_LAUNCH_CHECK(ctx);
   return ETR_OK;
 }

@@ -13,7 +13,7 @@ import torch
 
 from . import _lib
 from ._lib import check
-from .runtime import Runtime, cast_bf16, gemm_bf16_tn, gemm_f32, transpose_bf16, _p
+from .runtime import Runtime, cast_bf16, gemm_bf16_tn, gemm_bf16_tn_accumulate, gemm_bf16_wgrad, gemm_f32, _p
 
 
 class DenseParams:
@@ -236,10 +236,8 @@ class MLPLayer:
                 d = dx
                 continue
             if tc:
-                # dK = X^T d : [in,B] x [B,out]  ->  A = X^T (bf16 transpose), B operand = d^T; split-K over the batch
-                xt = transpose_bf16(rt, x, B, n_in)
-                dt = cast_bf16(rt, d, transpose=True)
-                gemm_bf16_tn(rt, xt, dt, gk, n_in, n_out, B)
+                # dK = X^T d : X [B,in] and d [B,out] as stored (MN-major UMMA operands); split-K over the batch
+                gemm_bf16_wgrad(rt, x, cast_bf16(rt, d), gk, n_in, n_out, B)
             else:
                 # dK = x^T d : A stored [K=B, M=n_in] -> trans_a
                 gemm_f32(rt, x, d, gk, n_in, n_out, B, x.stride(0), n_out, n_out, trans_a=True)
@@ -257,6 +255,10 @@ class MLPLayer:
                     # intermediate one feeds the next activation backward and stays fp32
                     dx = rt.empty((B, n_in), torch.bfloat16 if i == 0 else torch.float32)
                     gemm_bf16_tn(rt, db_, kb, dx, B, n_in, n_out)
+                elif tc and acc.dtype == torch.float32 and acc.stride(1) == 1:
+                    # the same product accumulated into the gradient another branch already wrote for this input
+                    gemm_bf16_tn_accumulate(rt, cast_bf16(rt, d), cast_bf16(rt, k), acc, B, n_in, n_out)
+                    dx = acc
                 else:
                     dx = acc if acc is not None else rt.empty((B, n_in))
                     # dx = d K^T : B(k,n) = K[n,k] -> trans_b

@@ -569,6 +569,22 @@ def gemm_bf16_tn(rt: Runtime, A: torch.Tensor, B: torch.Tensor, C_out: torch.Ten
                                   rt.stream))
 
 
+def gemm_bf16_wgrad(rt: Runtime, A: torch.Tensor, B: torch.Tensor, C_out: torch.Tensor, M: int, N: int, K: int):
+    """C[M,N] (fp32) = A^T B: A [K,M], B [K,N] bf16 row-major (K = batch) -- dW = dY^T X without transposing either."""
+    assert A.dtype == torch.bfloat16 and B.dtype == torch.bfloat16 and A.stride(1) == 1 and B.stride(1) == 1
+    assert C_out.dtype == torch.float32 and C_out.stride(1) == 1
+    check(rt.lib.etr_gemm_bf16_nn_wgrad(rt.ctx, M, N, K, A.data_ptr(), A.stride(0), B.data_ptr(), B.stride(0),
+                                        C_out.data_ptr(), C_out.stride(0), rt.stream))
+
+
+def gemm_bf16_tn_accumulate(rt: Runtime, A: torch.Tensor, B: torch.Tensor, C_io: torch.Tensor, M: int, N: int, K: int):
+    """C[M,N] (fp32) += A[M,K] B[N,K]^T (bf16 operands, fp32 accumulate)."""
+    assert A.dtype == torch.bfloat16 and B.dtype == torch.bfloat16 and A.stride(1) == 1 and B.stride(1) == 1
+    assert C_io.dtype == torch.float32 and C_io.stride(1) == 1
+    check(rt.lib.etr_gemm_bf16_tn_accumulate(rt.ctx, M, N, K, A.data_ptr(), A.stride(0), B.data_ptr(), B.stride(0),
+                                             C_io.data_ptr(), C_io.stride(0), rt.stream))
+
+
 def cast_bf16(rt: Runtime, src: torch.Tensor, transpose: bool = False, ld_dst: Optional[int] = None) -> torch.Tensor:
     """fp32 [rows, cols] -> bf16 [rows, ld] (or [cols, ld] transposed), ld rounded up to 8, zero padded."""
     assert src.dtype == torch.float32 and src.dim() == 2 and src.stride(1) == 1

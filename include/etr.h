@@ -392,13 +392,24 @@ int etr_gemm_bf16_tn(etr_ctx* ctx, int64_t M, int64_t N, int64_t K,
                      void* stream);
 /* Backward pieces of the bf16 cross-matrix layer (SURVEY a', cross-matrix):
  *   etr_gemm_bf16_tn_residual : out = A B^T + res        (G_l = G_{l+1} + dU W_l; bf16 in/out, fp32 accumulate)
- *   etr_cross_mat_bwd_elementwise_bf16 : du = g (.) x0 (bf16), dx0 += g (.) u (fp32), n elements
+ *   etr_cross_mat_bwd_elementwise_bf16 : du = g (.) x0 (bf16), dx0 (+)= g (.) u (fp32) on [rows, cols]; g may be a column
+ *       slice of a wider matrix (row pitch ldg); init != 0 writes dx0 instead of accumulating into it
  *   etr_add_bf16_into_f32 : y += x ;  etr_colsum_bf16 : out[n] = sum_m X[m,n] (db_l = colsum(dU)).   */
 int etr_gemm_bf16_tn_residual(etr_ctx* ctx, int64_t M, int64_t N, int64_t K, const void* d_A, int64_t lda,
                               const void* d_B, int64_t ldb, const void* d_res, int64_t ldr,
                               void* d_out, int64_t ldo, void* stream);
-int etr_cross_mat_bwd_elementwise_bf16(etr_ctx* ctx, const void* d_g, const void* d_x0, const void* d_u,
-                                       int64_t n, void* d_du, float* d_dx0_accum, void* stream);
+/* Weight-gradient shape on the tensor cores without transposes: C[M,N] (fp32) = A^T B with A [K,M] and B [K,N] row-major
+ * bf16 (K = batch): dW = dY^T X of tf.GradientTape for a Dense / cross kernel (2.FM/ModelManager.py:172-176).  Both
+ * operands are MN-major UMMA operands (TMA boxes of 64 columns x 64 rows, 128-byte swizzle); split-K over the batch,
+ * fixed-order finish.                                                                                           */
+int etr_gemm_bf16_nn_wgrad(etr_ctx* ctx, int64_t M, int64_t N, int64_t K, const void* d_A, int64_t lda, const void* d_B,
+                           int64_t ldb, float* d_C, int64_t ldc, void* stream);
+/* C[M,N] (fp32) += A[M,K] B[N,K]^T: the input gradient of the first Dense layer accumulated into the gradient that the
+ * cross layers already wrote for the same input (3.DCN/CustomLayers.py: x feeds both branches).                 */
+int etr_gemm_bf16_tn_accumulate(etr_ctx* ctx, int64_t M, int64_t N, int64_t K, const void* d_A, int64_t lda, const void* d_B,
+                                int64_t ldb, float* d_C, int64_t ldc, void* stream);
+int etr_cross_mat_bwd_elementwise_bf16(etr_ctx* ctx, const void* d_g, int64_t ldg, const void* d_x0, const void* d_u,
+                                       int64_t rows, int64_t cols, void* d_du, float* d_dx0_accum, int32_t init, void* stream);
 int etr_add_bf16_into_f32(etr_ctx* ctx, const void* d_x, int64_t n, float* d_y, void* stream);
 int etr_colsum_bf16(etr_ctx* ctx, const void* d_X, int64_t M, int64_t N, int64_t ldx, float* d_out,
                     void* stream);

@@ -63,6 +63,44 @@ def test_gemm_bf16_split_k_wgrad_shape(rt):
     assert torch.equal(C, C2)                            # deterministic
 
 
+@pytest.mark.parametrize("M,N,K", [(128, 64, 64), (200, 100, 1000), (1680, 1680, 4096), (432, 8, 65536), (1677 + 3, 240, 777),
+                                    (64, 1, 300)])
+def test_gemm_bf16_wgrad_mn_major(rt, M, N, K):
+    """C = A^T B with A [K,M], B [K,N] as stored (MN-major UMMA operands: no transposes); ragged M / N / K tails."""
+    from etr_b200.runtime import gemm_bf16_wgrad
+    ldm, ldn = (M + 7) // 8 * 8, (N + 7) // 8 * 8
+    A = _rand_bf16(rt, (K, M), ldm, 5, scale=0.1)
+    B = _rand_bf16(rt, (K, N), ldn, 6, scale=0.1)
+    C = torch.full((M, ldn), 7.0, device=rt.device)
+    gemm_bf16_wgrad(rt, A, B, C, M, N, K)
+    C2 = torch.full((M, ldn), 7.0, device=rt.device)
+    gemm_bf16_wgrad(rt, A, B, C2, M, N, K)
+    torch.cuda.synchronize()
+    ref = A[:, :M].double().T @ B[:, :N].double()
+    err = (C[:, :N].double() - ref).abs().max().item()
+    assert err <= 2e-3 * max(ref.abs().max().item(), 1e-6), err
+    assert torch.equal(C, C2)                            # deterministic
+    if ldn > N:
+        assert torch.all(C[:, N:] == 7.0)               # nothing written past the N columns
+
+
+@pytest.mark.parametrize("M,N,K", [(1000, 1680, 64), (257, 240, 40), (128, 33, 8)])
+def test_gemm_bf16_tn_accumulate(rt, M, N, K):
+    from etr_b200.runtime import gemm_bf16_tn_accumulate
+    ldk = (K + 7) // 8 * 8
+    A = _rand_bf16(rt, (M, K), ldk, 7)
+    B = _rand_bf16(rt, (N, K), ldk, 8)
+    ldc = (N + 3) // 4 * 4 + 4
+    C0 = torch.randn((M, ldc), device=rt.device)
+    C = C0.clone()
+    gemm_bf16_tn_accumulate(rt, A, B, C, M, N, K)
+    torch.cuda.synchronize()
+    ref = C0[:, :N].double() + A[:, :K].double() @ B[:, :K].double().T
+    err = (C[:, :N].double() - ref).abs().max().item()
+    assert err <= 1e-4 * max(ref.abs().max().item(), 1.0), err
+    assert torch.equal(C[:, N:], C0[:, N:])
+
+
 def test_cast_and_transpose_bf16(rt):
     from etr_b200.runtime import cast_bf16, transpose_bf16
     x = torch.randn(37, 13, device=rt.device)
