@@ -578,8 +578,6 @@ def run_c4(args):
                               "algorithmic_bytes_per_launch": alg,
                               "note": "F*k*4 + 8 = 1 256 B per looked-up id (SURVEY 8d) x the valid ids of one batch + 4 B/sample out"}})
     print(json.dumps(line))
-    if world > 1:
-        dist.destroy_process_group()
 
 
 def ncu_traffic(kernel_substr: str):
