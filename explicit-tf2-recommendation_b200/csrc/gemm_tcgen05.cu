@@ -152,6 +152,175 @@ __device__ __forceinline__ float act_apply(float x, int act) {
   }
 }
 
+__device__ __forceinline__ void unpack_bf16x8(const uint4& w, float (&f)[8]) {
+  const uint32_t ww[4] = {w.x, w.y, w.z, w.w};
+#pragma unroll
+  for (int t = 0; t < 4; ++t) {
+    const float2 x = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&ww[t]));
+    f[2 * t] = x.x; f[2 * t + 1] = x.y;
+  }
+}
+__device__ __forceinline__ uint4 pack_bf16x8(const float (&f)[8]) {
+  __nv_bfloat162 h0 = __floats2bfloat162_rn(f[0], f[1]), h1 = __floats2bfloat162_rn(f[2], f[3]);
+  __nv_bfloat162 h2 = __floats2bfloat162_rn(f[4], f[5]), h3 = __floats2bfloat162_rn(f[6], f[7]);
+  return make_uint4(*reinterpret_cast<uint32_t*>(&h0), *reinterpret_cast<uint32_t*>(&h1), *reinterpret_cast<uint32_t*>(&h2),
+                    *reinterpret_cast<uint32_t*>(&h3));
+}
+__device__ __noinline__ float act_slow(float x, int act) { return act_apply(x, act); }
+template <int N>
+__device__ __forceinline__ void act_vec(float (&a)[N], int act) {      // act is warp-uniform: one branch per vector
+  if (act == ETR_ACT_RELU) {
+#pragma unroll
+    for (int i = 0; i < N; ++i) a[i] = a[i] > 0.f ? a[i] : 0.f;
+  } else if (act == ETR_ACT_SIGMOID || act == ETR_ACT_TANH) {
+#pragma unroll 1
+    for (int i = 0; i < N; ++i) a[i] = act_slow(a[i], act);
+  }
+}
+__device__ __forceinline__ bool al16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
+// 8 consecutive bf16 / N consecutive fp32 of one row: one 16-byte access when the piece is whole and aligned,
+// element by element (first nv only) on ragged column tails and odd pitches
+__device__ __forceinline__ void load_bf16x8(const __nv_bfloat16* p, bool vec, int nv, float (&f)[8]) {
+  if (vec) {
+    unpack_bf16x8(*reinterpret_cast<const uint4*>(p), f);
+  } else {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) f[i] = i < nv ? __bfloat162float(p[i]) : 0.f;
+  }
+}
+__device__ __forceinline__ void store_bf16x8(__nv_bfloat16* p, bool vec, int nv, const float (&f)[8]) {
+  if (vec) {
+    *reinterpret_cast<uint4*>(p) = pack_bf16x8(f);
+  } else {
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+      if (i < nv) p[i] = __float2bfloat16_rn(f[i]);
+  }
+}
+
+// One 32-row x (<= 32)-column block of the accumulator (fp32 bits in v[], lane = row row_base + lane, columns
+// col0 .. col0 + ncol) through the fused epilogue; shared by the per-tile and the persistent kernel.  The block is
+// transposed ONCE through the warp's private 32 x 36 fp32 tile T (lane = row  ->  4 or 8 lanes per row); everything
+// after that is elementwise in the coalesced layout: bias, activation, the cross combine with x0 / xl (loaded
+// straight into that layout, or preloaded by epi_preload: px0 / pxl, only for whole aligned blocks), 16-byte stores.
+// Ragged column tails (BLOCK_N = 240: the last block of a tile is 16 wide; N = 1677: 13) and pitches that are not
+// 16-byte multiples take the same path with per-element accesses.
+__device__ __forceinline__ bool epi_vec_ok(const __nv_bfloat16* base, long long ld, long long col0, int ncol) {
+  return ncol == 32 && ((ld & 7) == 0) && al16(base + col0);
+}
+__device__ __forceinline__ void epi_preload(const __nv_bfloat16* base, long long ld, long long row_base, long long col0,
+                                            long long M, int lane, uint4 (&w)[4]) {
+  const int g4 = lane & 3, r4 = lane >> 2;
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const long long rr = row_base + r4 + 8 * j;
+    w[j] = make_uint4(0u, 0u, 0u, 0u);
+    if (rr < M) w[j] = *reinterpret_cast<const uint4*>(base + rr * ld + col0 + 8 * g4);
+  }
+}
+__device__ __forceinline__ void epi_block(const EpiParams& ep, float* T, int lane, long long row_base, long long col0, int ncol,
+                                          const uint32_t (&v)[32], int split, bool pre, const uint4 (&px0)[4],
+                                          const uint4 (&pxl)[4]) {
+  constexpr int TS = 36;
+  __syncwarp();
+#pragma unroll
+  for (int i = 0; i < 32; i += 4)
+    *reinterpret_cast<uint4*>(&T[lane * TS + i]) = make_uint4(v[i], v[i + 1], v[i + 2], v[i + 3]);
+  __syncwarp();
+  if (ep.mode == EPI_PARTIAL || (ep.mode == EPI_LINEAR && !ep.c_bf16)) {
+    // fp32 out: 8 lanes x 16 bytes per row, 4 rows per instruction
+    const int g8 = lane & 7, r8 = lane >> 3;
+    const int nv = ncol - 4 * g8;                    // valid columns of this lane's piece (<= 0: none)
+    if (nv <= 0) return;
+    const bool linear = ep.mode == EPI_LINEAR;
+    float* obase = linear ? reinterpret_cast<float*>(ep.C) : ep.partial + (long long)split * ep.M * ep.N;
+    const long long ld = linear ? ep.ldc : ep.N;
+    const long long off = col0 + 4 * g8;
+    const bool vec = nv >= 4 && (ld & 3) == 0 && al16(obase + off);
+    float b4[4] = {0.f, 0.f, 0.f, 0.f};
+    if (linear && ep.bias) {
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+        if (i < nv) b4[i] = ep.bias[off + i];
+    }
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const int r = r8 + 4 * j;
+      const long long rr = row_base + r;
+      const float4 t = *reinterpret_cast<const float4*>(&T[r * TS + 4 * g8]);
+      float a[4] = {t.x + b4[0], t.y + b4[1], t.z + b4[2], t.w + b4[3]};
+      if (linear) act_vec<4>(a, ep.act);
+      if (rr >= ep.M) continue;
+      float* o = obase + rr * ld + off;
+      if (vec) {
+        if (linear && ep.accumulate) {
+          const float4 c = *reinterpret_cast<const float4*>(o);
+          a[0] += c.x; a[1] += c.y; a[2] += c.z; a[3] += c.w;
+        }
+        *reinterpret_cast<float4*>(o) = make_float4(a[0], a[1], a[2], a[3]);
+      } else {
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+          if (i < nv) o[i] = (linear && ep.accumulate) ? o[i] + a[i] : a[i];
+      }
+    }
+    return;
+  }
+  // bf16 out: 4 lanes x 16 bytes per row, 8 rows per instruction
+  const int g4 = lane & 3, r4 = lane >> 2;
+  const int nv = ncol - 8 * g4;
+  if (nv <= 0) return;
+  const long long off = col0 + 8 * g4;
+  const bool whole = nv >= 8;
+  float b8[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+  if (ep.bias) {
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+      if (i < nv) b8[i] = ep.bias[off + i];
+  }
+  if (ep.mode == EPI_LINEAR) {
+    __nv_bfloat16* C = reinterpret_cast<__nv_bfloat16*>(ep.C);
+    const bool vc = whole && (ep.ldc & 7) == 0 && al16(C + off);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int r = r4 + 8 * j;
+      const long long rr = row_base + r;
+      const float4 t0 = *reinterpret_cast<const float4*>(&T[r * TS + 8 * g4]);
+      const float4 t1 = *reinterpret_cast<const float4*>(&T[r * TS + 8 * g4 + 4]);
+      float a[8] = {t0.x + b8[0], t0.y + b8[1], t0.z + b8[2], t0.w + b8[3], t1.x + b8[4], t1.y + b8[5], t1.z + b8[6], t1.w + b8[7]};
+      act_vec<8>(a, ep.act);
+      if (rr < ep.M) store_bf16x8(C + rr * ep.ldc + off, vc, nv, a);
+    }
+    return;
+  }
+  // EPI_CROSS: u = acc + b ; out = x0 * u + xl   (x0 == NULL: out = u + xl)
+  const bool vx = whole && (ep.ldx & 7) == 0 && al16(ep.xl + off) && (!ep.x0 || al16(ep.x0 + off));
+  const bool vo = whole && (ep.ldo & 7) == 0 && al16(ep.out + off);
+  const bool vu = whole && ep.u && (ep.ldu & 7) == 0 && al16(ep.u + off);
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const int r = r4 + 8 * j;
+    const long long rr = row_base + r;
+    const float4 t0 = *reinterpret_cast<const float4*>(&T[r * TS + 8 * g4]);
+    const float4 t1 = *reinterpret_cast<const float4*>(&T[r * TS + 8 * g4 + 4]);
+    float a[8] = {t0.x + b8[0], t0.y + b8[1], t0.z + b8[2], t0.w + b8[3], t1.x + b8[4], t1.y + b8[5], t1.z + b8[6], t1.w + b8[7]};
+    if (rr >= ep.M) continue;
+    if (ep.u) store_bf16x8(ep.u + rr * ep.ldu + off, vu, nv, a);
+    float x[8];
+    if (ep.x0) {
+      if (pre) unpack_bf16x8(px0[j], x);
+      else load_bf16x8(ep.x0 + rr * ep.ldx + off, vx, nv, x);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) a[i] *= x[i];
+    }
+    if (pre) unpack_bf16x8(pxl[j], x);
+    else load_bf16x8(ep.xl + rr * ep.ldx + off, vx, nv, x);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) a[i] += x[i];
+    store_bf16x8(ep.out + rr * ep.ldo + off, vo, nv, a);
+  }
+}
+
 // MN = false: A [M,K], B [N,K] (K contiguous, "TN").  MN = true: A [K,M], B [K,N] (M / N contiguous): C = A^T B, the
 // weight-gradient shape dW = dY^T X with K = batch -- both operands are read as they are stored, no transposes.
 template <int BLOCK_N, int STAGES, bool MN = false>
@@ -279,155 +448,8 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
       }
       int ncol = (ep.N - col0) < 32 ? (int)(ep.N - col0) : 32;
       if (ncol > BLOCK_N - c0) ncol = BLOCK_N - c0;     // BLOCK_N = 240: the last chunk is 16 columns wide
-      const bool col_ok = lane < ncol;                  // scalar fallback: this lane's column
-      const bool full = (ncol == 32);
-      float val[32];
-
-      // own row (lane = row) <-> tile, 8 x 128-bit shared accesses
-      auto regs_to_tile = [&](const float (&src)[32]) {
-        __syncwarp();
-#pragma unroll
-        for (int i = 0; i < 32; i += 4)
-          *reinterpret_cast<float4*>(&T[lane * TS + i]) = make_float4(src[i], src[i + 1], src[i + 2], src[i + 3]);
-        __syncwarp();
-      };
-      // bf16 matrix block -> tile: 4 lanes x 16 bytes cover one row's 32 columns, 8 rows per instruction
-      auto bf16_block_to_tile = [&](const __nv_bfloat16* base, long long ld, bool vec) {
-        __syncwarp();
-        if (vec) {
-          const int g4 = lane & 3, r4 = lane >> 2;
-#pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            const int r = r4 + 8 * j;
-            const long long rr = row_base + r;
-            uint4 w = make_uint4(0u, 0u, 0u, 0u);
-            if (rr < ep.M) w = *reinterpret_cast<const uint4*>(base + rr * ld + col0 + 8 * g4);
-            const uint32_t ww[4] = {w.x, w.y, w.z, w.w};
-            float f[8];
-#pragma unroll
-            for (int t = 0; t < 4; ++t) {
-              const float2 x = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&ww[t]));
-              f[2 * t] = x.x; f[2 * t + 1] = x.y;
-            }
-            *reinterpret_cast<float4*>(&T[r * TS + 8 * g4]) = make_float4(f[0], f[1], f[2], f[3]);
-            *reinterpret_cast<float4*>(&T[r * TS + 8 * g4 + 4]) = make_float4(f[4], f[5], f[6], f[7]);
-          }
-        } else {
-#pragma unroll
-          for (int r = 0; r < 32; ++r) {
-            const long long rr = row_base + r;
-            T[r * TS + lane] = (rr < ep.M && col_ok) ? __bfloat162float(base[rr * ld + col0 + lane]) : 0.f;
-          }
-        }
-        __syncwarp();
-      };
-      // dst (lane = row) combined with a bf16 matrix block: MUL: dst[i] *= x ; else dst[i] += x
-      auto combine_block = [&](const __nv_bfloat16* base, long long ld, float (&dst)[32], bool mul) {
-        const bool vec = full && ((ld & 7) == 0) && ((reinterpret_cast<uintptr_t>(base + col0) & 15) == 0);
-        bf16_block_to_tile(base, ld, vec);
-#pragma unroll
-        for (int i = 0; i < 32; i += 4) {
-          const float4 t = *reinterpret_cast<const float4*>(&T[lane * TS + i]);
-          if (mul) { dst[i] *= t.x; dst[i + 1] *= t.y; dst[i + 2] *= t.z; dst[i + 3] *= t.w; }
-          else { dst[i] += t.x; dst[i + 1] += t.y; dst[i + 2] += t.z; dst[i + 3] += t.w; }
-        }
-      };
-      // coalesced block store of src[] (lane = row) as fp32 or bf16
-      auto store_block = [&](void* base, long long ld, bool as_bf16, const float (&src)[32]) {
-        regs_to_tile(src);
-        if (as_bf16) {
-          __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(base);
-          const bool vec = full && ((ld & 7) == 0) && ((reinterpret_cast<uintptr_t>(o + col0) & 15) == 0);
-          if (vec) {                                   // 4 lanes x 16 bytes per row, 8 rows per instruction
-            const int g4 = lane & 3, r4 = lane >> 2;
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {
-              const int r = r4 + 8 * j;
-              const long long rr = row_base + r;
-              const float4 a = *reinterpret_cast<const float4*>(&T[r * TS + 8 * g4]);
-              const float4 b = *reinterpret_cast<const float4*>(&T[r * TS + 8 * g4 + 4]);
-              __nv_bfloat162 h0 = __floats2bfloat162_rn(a.x, a.y), h1 = __floats2bfloat162_rn(a.z, a.w);
-              __nv_bfloat162 h2 = __floats2bfloat162_rn(b.x, b.y), h3 = __floats2bfloat162_rn(b.z, b.w);
-              if (rr < ep.M)
-                *reinterpret_cast<uint4*>(o + rr * ld + col0 + 8 * g4) =
-                    make_uint4(*reinterpret_cast<uint32_t*>(&h0), *reinterpret_cast<uint32_t*>(&h1),
-                               *reinterpret_cast<uint32_t*>(&h2), *reinterpret_cast<uint32_t*>(&h3));
-            }
-            return;
-          }
-#pragma unroll
-          for (int r = 0; r < 32; ++r) {
-            const long long rr = row_base + r;
-            if (rr < ep.M && col_ok) o[rr * ld + col0 + lane] = __float2bfloat16_rn(T[r * TS + lane]);
-          }
-        } else {
-          float* o = reinterpret_cast<float*>(base);
-          const bool vec = full && ((ld & 3) == 0) && ((reinterpret_cast<uintptr_t>(o + col0) & 15) == 0);
-          if (vec) {                                   // 8 lanes x 16 bytes per row, 4 rows per instruction
-            const int g8 = lane & 7, r8 = lane >> 3;
-#pragma unroll
-            for (int j = 0; j < 8; ++j) {
-              const int r = r8 + 4 * j;
-              const long long rr = row_base + r;
-              const float4 a = *reinterpret_cast<const float4*>(&T[r * TS + 4 * g8]);
-              if (rr < ep.M) *reinterpret_cast<float4*>(o + rr * ld + col0 + 4 * g8) = a;
-            }
-            return;
-          }
-#pragma unroll
-          for (int r = 0; r < 32; ++r) {
-            const long long rr = row_base + r;
-            if (rr < ep.M && col_ok) o[rr * ld + col0 + lane] = T[r * TS + lane];
-          }
-        }
-      };
-
-      if (ep.mode == EPI_PARTIAL) {
-#pragma unroll
-        for (int i = 0; i < 32; ++i) val[i] = __uint_as_float(v[i]);
-        store_block(ep.partial + (long long)split * ep.M * ep.N, ep.N, false, val);
-      } else if (ep.mode == EPI_LINEAR) {
-#pragma unroll
-        for (int i = 0; i < 32; ++i)
-          val[i] = act_apply(__uint_as_float(v[i]) + ((ep.bias && i < ncol) ? ep.bias[col0 + i] : 0.f), ep.act);
-        if (ep.accumulate && !ep.c_bf16) {             // C += ... : this block of C -> tile (coalesced) -> own row
-          const float* cbase = reinterpret_cast<const float*>(ep.C);
-          const bool vec = full && ((ep.ldc & 3) == 0) && ((reinterpret_cast<uintptr_t>(cbase + col0) & 15) == 0);
-          __syncwarp();
-          if (vec) {
-            const int g8 = lane & 7, r8 = lane >> 3;
-#pragma unroll
-            for (int j = 0; j < 8; ++j) {
-              const int r = r8 + 4 * j;
-              const long long rr = row_base + r;
-              float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
-              if (rr < ep.M) a = *reinterpret_cast<const float4*>(cbase + rr * ep.ldc + col0 + 4 * g8);
-              *reinterpret_cast<float4*>(&T[r * TS + 4 * g8]) = a;
-            }
-          } else {
-#pragma unroll
-            for (int r = 0; r < 32; ++r) {
-              const long long rr = row_base + r;
-              T[r * TS + lane] = (rr < ep.M && col_ok) ? cbase[rr * ep.ldc + col0 + lane] : 0.f;
-            }
-          }
-          __syncwarp();
-#pragma unroll
-          for (int i = 0; i < 32; i += 4) {
-            const float4 t = *reinterpret_cast<const float4*>(&T[lane * TS + i]);
-            val[i] += t.x; val[i + 1] += t.y; val[i + 2] += t.z; val[i + 3] += t.w;
-          }
-        }
-        store_block(ep.C, ep.ldc, ep.c_bf16 != 0, val);
-      } else {   // EPI_CROSS: u = acc + b ; out = x0 * u + xl   (x0 == NULL: out = u + xl)
-#pragma unroll
-        for (int i = 0; i < 32; ++i)
-          val[i] = __uint_as_float(v[i]) + ((ep.bias && i < ncol) ? ep.bias[col0 + i] : 0.f);
-        if (ep.u) store_block(ep.u, ep.ldu, true, val);
-        if (ep.x0) combine_block(ep.x0, ep.ldx, val, true);
-        combine_block(ep.xl, ep.ldx, val, false);
-        store_block(ep.out, ep.ldo, true, val);
-      }
+      const uint4 nopre[4] = {};
+      epi_block(ep, T, lane, row_base, col0, ncol, v, split, false, nopre, nopre);
     }
   }
   fence_before();
@@ -435,6 +457,255 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
   if (warp == 1) {
     fence_after();
     tmem_dealloc(tmem_base, TMEM_COLS);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// Persistent form for the big K-major ("TN") products of the cross network (3.DCN/CustomLayers.py:300-303 and
+// its backward): M = batch, N = K = D.  One CTA per SM walks a static list of output tiles; the accumulator is
+// DOUBLE-BUFFERED in TMEM (2 x 256 columns), so the eight epilogue warps drain tile i (x0 / xl blocks preloaded
+// into registers before the accumulator is waited for) while the MMA warp is already accumulating tile i + 1, and
+// the smem ring never drains between tiles.  CG = 2 pairs two SMs (cluster of 2, tcgen05 cta_group::2): the pair
+// owns a 256 x BLOCK_N tile, each CTA stages its own 128 rows of A and HALF of the B tile (BLOCK_N / 2 rows), the
+// leader CTA issues UMMA 256 x BLOCK_N x 16 for both, and every B byte is fetched from L2 once per pair instead
+// of once per CTA (the 128 x 240 one-CTA tile is shared-memory-fill-bound: TMA writes + MMA operand reads).
+//   barriers: full[s]   (leader CTA only; tx bytes of BOTH CTAs' loads, armed by the leader's producer)
+//             empty[s]  (per CTA; tcgen05.commit, multicast to both CTAs when CG = 2)
+//             tmem_full[a]  (per CTA; commit after a tile's last k-block, multicast when CG = 2)
+//             tmem_empty[a] (leader; one arrival per epilogue warp of the whole pair)
+// Tile order: n fastest, so the clusters that run side by side read the same A rows (L2 hits).
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ uint32_t mapa_shared(uint32_t addr, uint32_t rank) {
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(addr), "r"(rank));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
+  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_local(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_wait_cluster(uint32_t bar, uint32_t parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred P1;\n"
+      "LAB_WAIT:\n"
+      "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 P1, [%0], %1;\n"
+      "@P1 bra DONE;\n"
+      "bra LAB_WAIT;\n"
+      "DONE:\n"
+      "}\n" ::"r"(bar),
+      "r"(parity)
+      : "memory");
+}
+template <int CG>
+__device__ __forceinline__ void tma_load_2d_cg(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c_inner, int c_outer) {
+  if (CG == 2) {
+    // the mbarrier may live in the peer (leader) CTA: shared::cluster address
+    asm volatile(
+        "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(dst),
+        "l"(reinterpret_cast<uint64_t>(map)), "r"(bar), "r"(c_inner), "r"(c_outer)
+        : "memory");
+  } else {
+    tma_load_2d(dst, map, bar, c_inner, c_outer);
+  }
+}
+template <int CG>
+__device__ __forceinline__ void umma_f16_cg(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
+  if (CG == 2) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "setp.ne.b32 p, %4, 0;\n"
+        "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n"
+        "}\n" ::"r"(tmem_d),
+        "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+        : "memory");
+  } else {
+    umma_f16(tmem_d, desc_a, desc_b, idesc, accumulate);
+  }
+}
+template <int CG>
+__device__ __forceinline__ void umma_commit_cg(uint32_t bar) {
+  if (CG == 2) {
+    asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(bar),
+                 "h"((uint16_t)3)
+                 : "memory");
+  } else {
+    umma_commit(bar);
+  }
+}
+
+constexpr int kEpiWarps = 8;
+constexpr int kEpiTileBytes = kEpiWarps * 32 * 36 * 4;       // the epilogue warps' private transpose tiles
+
+template <int BLOCK_N, int STAGES, int CG>
+__global__ void __launch_bounds__(kThreads, 1)
+gemm_bf16_persist_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b, const EpiParams ep,
+                         int num_tiles, int n_tiles) {
+  static_assert(BLOCK_N % 16 == 0 && (BLOCK_N / CG) % 8 == 0 && BLOCK_N <= 256, "UMMA N");
+  constexpr int B_ROWS = BLOCK_N / CG;                        // rows of the B tile this CTA stages
+  constexpr uint32_t A_BYTES = BLOCK_M * BLOCK_K * 2;         // 16 KiB
+  constexpr uint32_t B_TX = B_ROWS * BLOCK_K * 2;
+  constexpr uint32_t B_BYTES = (B_TX + 1023) & ~1023u;        // keep every stage 1024-byte aligned
+  constexpr uint32_t ACC_COLS = 256;                          // column pitch of the two accumulators
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint8_t* smem_a = smem;
+  uint8_t* smem_b = smem + STAGES * A_BYTES;
+  float* smem_t = reinterpret_cast<float*>(smem_b + STAGES * B_BYTES);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(reinterpret_cast<uint8_t*>(smem_t) + kEpiTileBytes);
+  uint64_t* full_bar = bars;                  // [STAGES]
+  uint64_t* empty_bar = bars + STAGES;        // [STAGES]
+  uint64_t* tmem_full_bar = bars + 2 * STAGES;       // [2]
+  uint64_t* tmem_empty_bar = bars + 2 * STAGES + 2;  // [2]
+  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 4);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t rank = CG == 2 ? cluster_ctarank() : 0u;
+  const int cluster_id = blockIdx.x / CG, num_clusters = gridDim.x / CG;
+  const int nkb = ep.k_blocks_total;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < STAGES; ++s) { mbar_init(smem_u32(&full_bar[s]), 1); mbar_init(smem_u32(&empty_bar[s]), 1); }
+    for (int a = 0; a < 2; ++a) { mbar_init(smem_u32(&tmem_full_bar[a]), 1); mbar_init(smem_u32(&tmem_empty_bar[a]), CG * kEpiWarps); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&map_a)) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&map_b)) : "memory");
+  }
+  if (warp == 1) {
+    if (CG == 2) {
+      asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_ptr_smem)), "r"(512) : "memory");
+      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+    } else {
+      tmem_alloc(smem_u32(tmem_ptr_smem), 512);
+    }
+  }
+  fence_before();
+  __syncthreads();
+  if (CG == 2) cluster_sync_all();            // the peer's barriers and TMEM exist before anything signals them
+  fence_after();
+  const uint32_t tmem_base = *tmem_ptr_smem;
+
+  if (warp == 0) {
+    // ===== TMA producer (both CTAs of a pair: each stages its own A rows and its half of the B tile) =====
+    if (lane == 0) {
+      uint32_t it = 0;
+      for (int t = cluster_id; t < num_tiles; t += num_clusters) {
+        const int m_blk = t / n_tiles, n_blk = t % n_tiles;
+        const int a_row = (m_blk * CG + (int)rank) * BLOCK_M;
+        const int b_row = n_blk * BLOCK_N + (int)rank * B_ROWS;
+        for (int kb = 0; kb < nkb; ++kb, ++it) {
+          const int s = it % STAGES;
+          const uint32_t ph = (it / STAGES) & 1;
+          mbar_wait(smem_u32(&empty_bar[s]), ph ^ 1);
+          uint32_t fb = smem_u32(&full_bar[s]);
+          if (rank == 0) mbar_expect_tx(fb, CG * (A_BYTES + B_TX));
+          if (CG == 2) fb = mapa_shared(fb, 0);
+          tma_load_2d_cg<CG>(smem_u32(smem_a + s * A_BYTES), &map_a, fb, kb * BLOCK_K, a_row);
+          tma_load_2d_cg<CG>(smem_u32(smem_b + s * B_BYTES), &map_b, fb, kb * BLOCK_K, b_row);
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===== MMA issuer: one thread of the leader CTA =====
+    if (lane == 0 && rank == 0) {
+      const uint32_t idesc = make_idesc(BLOCK_M * CG, BLOCK_N);
+      uint32_t it = 0;
+      int tl = 0;
+      for (int t = cluster_id; t < num_tiles; t += num_clusters, ++tl) {
+        const int acc = tl & 1;
+        const uint32_t accph = (tl >> 1) & 1;
+        mbar_wait_cluster(smem_u32(&tmem_empty_bar[acc]), accph ^ 1);     // the epilogue has drained this accumulator
+        fence_after();
+        const uint32_t d_tmem = tmem_base + (uint32_t)acc * ACC_COLS;
+        for (int kb = 0; kb < nkb; ++kb, ++it) {
+          const int s = it % STAGES;
+          const uint32_t ph = (it / STAGES) & 1;
+          mbar_wait(smem_u32(&full_bar[s]), ph);
+          fence_after();
+          const uint64_t da = make_kmajor_sw128_desc(smem_u32(smem_a + s * A_BYTES));
+          const uint64_t db = make_kmajor_sw128_desc(smem_u32(smem_b + s * B_BYTES));
+#pragma unroll
+          for (int k = 0; k < BLOCK_K / UMMA_K; ++k)
+            umma_f16_cg<CG>(d_tmem, da + (uint64_t)(k * 2), db + (uint64_t)(k * 2), idesc, (kb | k) != 0 ? 1u : 0u);
+          umma_commit_cg<CG>(smem_u32(&empty_bar[s]));
+        }
+        umma_commit_cg<CG>(smem_u32(&tmem_full_bar[acc]));
+      }
+    }
+  } else {
+    // ===== epilogue warps 2..9 =====
+    const int q = warp & 3;
+    const int half = (warp - 2) >> 2;
+    float* T = smem_t + (warp - 2) * (32 * 36);
+    const uint32_t empty_addr0 = CG == 2 ? mapa_shared(smem_u32(&tmem_empty_bar[0]), 0) : smem_u32(&tmem_empty_bar[0]);
+    const bool cross = ep.mode == EPI_CROSS;
+    int tl = 0;
+    for (int t = cluster_id; t < num_tiles; t += num_clusters, ++tl) {
+      const int m_blk = t / n_tiles, n_blk = t % n_tiles;
+      const int acc = tl & 1;
+      const uint32_t accph = (tl >> 1) & 1;
+      const long long row_base = ((long long)m_blk * CG + rank) * BLOCK_M + q * 32;
+      const long long tile_col0 = (long long)n_blk * BLOCK_N;
+      uint4 nx0[4] = {}, nxl[4] = {};
+      bool npre = false;
+      auto chunk_cols = [&](int c0) {
+        int ncol = (ep.N - (tile_col0 + c0)) < 32 ? (int)(ep.N - (tile_col0 + c0)) : 32;
+        if (ncol > BLOCK_N - c0) ncol = BLOCK_N - c0;
+        return ncol;
+      };
+      auto preload = [&](int c0) {
+        npre = false;
+        if (!cross || c0 >= BLOCK_N || tile_col0 + c0 >= ep.N) return;
+        const long long col0 = tile_col0 + c0;
+        const int ncol = chunk_cols(c0);
+        if (!epi_vec_ok(ep.xl, ep.ldx, col0, ncol) || (ep.x0 && !epi_vec_ok(ep.x0, ep.ldx, col0, ncol))) return;
+        if (ep.x0) epi_preload(ep.x0, ep.ldx, row_base, col0, ep.M, lane, nx0);
+        epi_preload(ep.xl, ep.ldx, row_base, col0, ep.M, lane, nxl);
+        npre = true;
+      };
+      preload(half * 32);                                   // in flight while the accumulator is still being computed
+      mbar_wait(smem_u32(&tmem_full_bar[acc]), accph);
+      fence_after();
+#pragma unroll 1
+      for (int c0 = half * 32; c0 < BLOCK_N; c0 += 64) {
+        const long long col0 = tile_col0 + c0;
+        if (col0 >= ep.N) break;                            // warp-uniform
+        uint4 cx0[4], cxl[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) { cx0[j] = nx0[j]; cxl[j] = nxl[j]; }
+        const bool cpre = npre;
+        uint32_t v[32];
+        tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)acc * ACC_COLS + (uint32_t)c0, v);
+        preload(c0 + 64);                                   // the next block's operands fly during this block's work
+        epi_block(ep, T, lane, row_base, col0, chunk_cols(c0), v, 0, cpre, cx0, cxl);
+      }
+      // every tcgen05.ld of this warp has completed (tmem_ld32 waits): hand the accumulator back to the MMA warp
+      fence_before();
+      __syncwarp();
+      if (lane == 0) {
+        if (CG == 2) mbar_arrive_cluster(empty_addr0 + (uint32_t)acc * 8u);
+        else mbar_arrive_local(empty_addr0 + (uint32_t)acc * 8u);
+      }
+    }
+  }
+  fence_before();
+  __syncthreads();
+  if (CG == 2) cluster_sync_all();            // the peer may still be read by the leader's MMAs / signalled by its commits
+  if (warp == 1) {
+    fence_after();
+    if (CG == 2) asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512) : "memory");
+    else tmem_dealloc(tmem_base, 512);
   }
 }
 
@@ -647,6 +918,41 @@ static int launch_tile(etr_ctx* ctx, const CUtensorMap& ma, const CUtensorMap& m
   return ETR_OK;
 }
 
+template <int BLOCK_N, int STAGES, int CG>
+static int launch_persist(etr_ctx* ctx, const CUtensorMap& ma, const CUtensorMap& mb, const EpiParams& ep, int num_tiles,
+                          int n_tiles, cudaStream_t s) {
+  constexpr size_t b_bytes = ((size_t)(BLOCK_N / CG) * BLOCK_K * 2 + 1023) & ~(size_t)1023;
+  constexpr size_t smem = (size_t)STAGES * (BLOCK_M * BLOCK_K * 2 + b_bytes) + kEpiTileBytes + (2 * STAGES + 4) * 8 + 16 + 1024;
+  static_assert(smem <= 232448, "shared memory budget of one SM");
+  auto kern = gemm_bf16_persist_kernel<BLOCK_N, STAGES, CG>;
+  ETR_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  int clusters = ctx->sm_count / CG;
+  if (clusters > num_tiles) clusters = num_tiles;
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = dim3((unsigned)(clusters * CG));
+  cfg.blockDim = dim3(kThreads);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = s;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = CG;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  ETR_CUDA(cudaLaunchKernelEx(&cfg, kern, ma, mb, ep, num_tiles, n_tiles));
+  ETR_LAUNCH_CHECK(ctx);
+  return ETR_OK;
+}
+
+// ETR_GEMM_PERSIST: 0 = per-tile kernel only, 1 = persistent one-CTA form, 2 (default) = persistent CTA-pair form
+static int persist_mode() {
+  const char* e = getenv("ETR_GEMM_PERSIST");      // read per call: tests switch it within one process
+  const int mode = e ? atoi(e) : 2;
+  return (mode < 0 || mode > 2) ? 2 : mode;
+}
+
 // BLOCK_N choice: widest tile that does not waste more than ~7% of the N extent.
 static int pick_block_n(long long N) {
   if (N <= 32) return 32;
@@ -664,6 +970,35 @@ static int run_gemm(etr_ctx* ctx, long long M, long long N, long long K, const v
   int bn = pick_block_n(N);
   if (mn && bn < 64) bn = 64;                        // MN-major tiles are built from 64-column boxes
   CUtensorMap ma, mb;
+  // big K-major products without split-K (cross layers forward / dgrad): persistent kernel, TMEM double-buffered
+  const int pm = persist_mode();
+  if (pm > 0 && !mn && bn >= 128 && (ep.mode == EPI_LINEAR || ep.mode == EPI_CROSS) &&
+      ceil_div(M, BLOCK_M) * ceil_div(N, bn) >= 2LL * ctx->sm_count) {
+    const int cg = pm;
+    int st = make_map(&ma, A, M, K, lda, BLOCK_M);
+    if (st != ETR_OK) return st;
+    st = make_map(&mb, B, N, K, ldb, bn / cg);
+    if (st != ETR_OK) return st;
+    const long long mt2 = ceil_div(M, (long long)BLOCK_M * cg), nt2 = ceil_div(N, bn);
+    if (mt2 * nt2 < (1LL << 30)) {
+      ep.M = M; ep.N = N;
+      ep.k_blocks_total = (int)ceil_div(K, BLOCK_K);
+      ep.k_blocks_per_split = ep.k_blocks_total;
+      const int tiles = (int)(mt2 * nt2), ntl = (int)nt2;
+      if (cg == 2) {
+        switch (bn) {
+          case 128: return launch_persist<128, 5, 2>(ctx, ma, mb, ep, tiles, ntl, s);
+          case 240: return launch_persist<240, 5, 2>(ctx, ma, mb, ep, tiles, ntl, s);
+          default: return launch_persist<256, 5, 2>(ctx, ma, mb, ep, tiles, ntl, s);
+        }
+      }
+      switch (bn) {
+        case 128: return launch_persist<128, 5, 1>(ctx, ma, mb, ep, tiles, ntl, s);
+        case 240: return launch_persist<240, 4, 1>(ctx, ma, mb, ep, tiles, ntl, s);
+        default: return launch_persist<256, 3, 1>(ctx, ma, mb, ep, tiles, ntl, s);
+      }
+    }
+  }
   int st = mn ? make_map_mn(&ma, A, K, M, lda) : make_map(&ma, A, M, K, lda, BLOCK_M);
   if (st != ETR_OK) return st;
   st = mn ? make_map_mn(&mb, B, K, N, ldb) : make_map(&mb, B, N, K, ldb, bn);

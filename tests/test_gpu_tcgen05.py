@@ -302,3 +302,89 @@ def test_deepfm_fused_train_step_matches_layerwise(rt):
     assert max(abs(a - b) for a, b in zip(l1, l0)) < 2e-5
     assert (p1 - p0).abs().max().item() < 2e-3          # 3 Adam steps of lr 1e-2 (sign-like updates of tiny grads)
     assert (t1 - t0).abs().max().item() < 2e-3
+
+
+# ---- persistent forms of the big K-major products (TMEM double-buffered; ETR_GEMM_PERSIST = 1: one CTA per tile row
+# block, 2: CTA pairs with tcgen05 cta_group::2).  Same operands through the per-tile kernel (mode 0) must agree: the
+# k order of the fp32 accumulation is the same, so the results are compared bit for bit as well as with fp64.
+_PERSIST_MODES = [int(x) for x in __import__("os").environ.get("ETR_TEST_PERSIST_MODES", "1,2").split(",")]
+
+
+@pytest.fixture
+def persist_env():
+    import os
+    old = os.environ.get("ETR_GEMM_PERSIST")
+    yield lambda m: os.environ.__setitem__("ETR_GEMM_PERSIST", str(m))
+    if old is None:
+        os.environ.pop("ETR_GEMM_PERSIST", None)
+    else:
+        os.environ["ETR_GEMM_PERSIST"] = old
+
+
+@pytest.mark.parametrize("mode", _PERSIST_MODES)
+@pytest.mark.parametrize("B,D", [(40000, 1677), (38400 + 130, 512), (50000, 384), (65536, 256)])
+def test_cross_mat_layer_bf16_persistent(rt, persist_env, mode, B, D):
+    from etr_b200._lib import check
+    ld = (D + 7) // 8 * 8
+    x0 = _rand_bf16(rt, (B, D), ld, 15)
+    xl = _rand_bf16(rt, (B, D), ld, 16)
+    W = _rand_bf16(rt, (D, D), ld, 17, scale=0.05)
+    b = torch.randn(ld, device=rt.device) * 0.1
+    b[D:] = 0
+    res = {}
+    for m in (0, mode):
+        persist_env(m)
+        out = torch.full((B, ld), 3.0, dtype=torch.bfloat16, device=rt.device)
+        u = torch.full((B, ld), 3.0, dtype=torch.bfloat16, device=rt.device)
+        check(rt.lib.etr_cross_mat_layer_bf16(rt.ctx, x0.data_ptr(), xl.data_ptr(), ld, B, D, W.data_ptr(), ld,
+                                              b.data_ptr(), out.data_ptr(), ld, u.data_ptr(), ld, rt.stream))
+        torch.cuda.synchronize()
+        res[m] = (out, u)
+    ref_u = xl[:, :D].double() @ W[:, :D].double().T + b[:D].double()
+    ref = x0[:, :D].double() * ref_u + xl[:, :D].double()
+    out, u = res[mode]
+    eu = (u[:, :D].double() - ref_u).abs().max().item()
+    eo = (out[:, :D].double() - ref).abs().max().item()
+    assert eu <= 1e-2 * max(1.0, ref_u.abs().max().item()), eu
+    assert eo <= 1e-2 * max(1.0, ref.abs().max().item()), eo
+    if ld > D:
+        assert torch.all(out[:, D:] == 3.0) and torch.all(u[:, D:] == 3.0)       # padding columns untouched
+    assert torch.equal(out, res[0][0]) and torch.equal(u, res[0][1])
+
+
+@pytest.mark.parametrize("mode", _PERSIST_MODES)
+@pytest.mark.parametrize("out_dtype", [torch.float32, torch.bfloat16])
+def test_gemm_bf16_tn_persistent(rt, persist_env, mode, out_dtype):
+    from etr_b200.runtime import gemm_bf16_tn, gemm_bf16_tn_accumulate
+    M, N, K = 40000 + 77, 1677, 200
+    ldk = (K + 7) // 8 * 8
+    A = _rand_bf16(rt, (M, K), ldk, 21)
+    B = _rand_bf16(rt, (N, K), ldk, 22)
+    bias = torch.randn(N, device=rt.device)
+    ldc = (N + 7) // 8 * 8
+    outs = {}
+    for m in (0, mode):
+        persist_env(m)
+        C = torch.full((M, ldc), 7.0, dtype=out_dtype, device=rt.device)
+        gemm_bf16_tn(rt, A, B, C, M, N, K, bias=bias, act="relu")
+        torch.cuda.synchronize()
+        outs[m] = C
+    ref = torch.relu(A[:, :K].double() @ B[:, :K].double().T + bias.double())
+    tol = 2e-3 if out_dtype == torch.float32 else 1e-2
+    err = (outs[mode][:, :N].double() - ref).abs().max().item()
+    assert err <= tol * max(1.0, ref.abs().max().item()), err
+    assert torch.all(outs[mode][:, N:] == 7.0)
+    assert torch.equal(outs[mode], outs[0])
+    if out_dtype == torch.float32:                       # C += A B^T (the shared-input gradient of the cross backward)
+        C0 = torch.randn((M, ldc), device=rt.device)
+        acc = {}
+        for m in (0, mode):
+            persist_env(m)
+            C = C0.clone()
+            gemm_bf16_tn_accumulate(rt, A, B, C, M, N, K)
+            torch.cuda.synchronize()
+            acc[m] = C
+        ref2 = C0[:, :N].double() + A[:, :K].double() @ B[:, :K].double().T
+        err2 = (acc[mode][:, :N].double() - ref2).abs().max().item()
+        assert err2 <= 1e-4 * max(ref2.abs().max().item(), 1.0), err2
+        assert torch.equal(acc[mode], acc[0])
