@@ -95,7 +95,7 @@ __device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t desc_a, uint6
       "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
       : "memory");
 }
-__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
+__device__ __forceinline__ void tmem_ld32_issue(uint32_t taddr, uint32_t (&v)[32]) {
   asm volatile(
       "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
       "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
@@ -106,7 +106,11 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
         "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
       : "r"(taddr)
       : "memory");
-  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
+  tmem_ld32_issue(taddr, v);
+  tmem_ld_wait();
 }
 
 // K-major, 128-byte-swizzled shared-memory operand descriptor (sm_100 UMMA):
@@ -180,9 +184,22 @@ __device__ __forceinline__ void act_vec(float (&a)[N], int act) {      // act is
 __device__ __forceinline__ bool al16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
 // 8 consecutive bf16 / N consecutive fp32 of one row: one 16-byte access when the piece is whole and aligned,
 // element by element (first nv only) on ragged column tails and odd pitches
+__device__ __forceinline__ uint4 ldg_u4(const void* p) {          // the epilogue operands are global: spare the generic path
+  uint4 w;
+  asm volatile("ld.global.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(w.x), "=r"(w.y), "=r"(w.z), "=r"(w.w) : "l"(p));
+  return w;
+}
+__device__ __forceinline__ float4 ldg_f4(const float* p) {
+  float4 w;
+  asm volatile("ld.global.nc.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(w.x), "=f"(w.y), "=f"(w.z), "=f"(w.w) : "l"(p));
+  return w;
+}
+__device__ __forceinline__ void stg_u4(void* p, const uint4& w) {
+  asm volatile("st.global.v4.u32 [%0], {%1, %2, %3, %4};" ::"l"(p), "r"(w.x), "r"(w.y), "r"(w.z), "r"(w.w) : "memory");
+}
 __device__ __forceinline__ void load_bf16x8(const __nv_bfloat16* p, bool vec, int nv, float (&f)[8]) {
   if (vec) {
-    unpack_bf16x8(*reinterpret_cast<const uint4*>(p), f);
+    unpack_bf16x8(ldg_u4(p), f);
   } else {
 #pragma unroll
     for (int i = 0; i < 8; ++i) f[i] = i < nv ? __bfloat162float(p[i]) : 0.f;
@@ -190,11 +207,41 @@ __device__ __forceinline__ void load_bf16x8(const __nv_bfloat16* p, bool vec, in
 }
 __device__ __forceinline__ void store_bf16x8(__nv_bfloat16* p, bool vec, int nv, const float (&f)[8]) {
   if (vec) {
-    *reinterpret_cast<uint4*>(p) = pack_bf16x8(f);
+    stg_u4(p, pack_bf16x8(f));
   } else {
 #pragma unroll
     for (int i = 0; i < 8; ++i)
       if (i < nv) p[i] = __float2bfloat16_rn(f[i]);
+  }
+}
+
+// The hot form of the cross epilogue: a whole 32 x 32 block, every pointer 16-byte aligned, all 32 rows inside M, x0 / xl
+// preloaded -- straight-line code, no per-row or per-element predicates.  (__fmul_rn / __fadd_rn here and in the general
+// form: no FMA contraction, so both give the same bits.)
+template <bool HAS_U, bool HAS_X0>
+__device__ __forceinline__ void epi_cross_lean(const EpiParams& ep, const float* Tl, const float (&b8)[8], long long r0,
+                                               long long off, const uint4 (&px0)[4], const uint4 (&pxl)[4]) {
+  constexpr int TS = 36;
+  __nv_bfloat16* po = ep.out + r0 * ep.ldo + off;
+  __nv_bfloat16* pu = HAS_U ? ep.u + r0 * ep.ldu + off : nullptr;
+  const long long so = 8 * ep.ldo, su = 8 * ep.ldu;
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const float4 t0 = *reinterpret_cast<const float4*>(Tl + 8 * j * TS);
+    const float4 t1 = *reinterpret_cast<const float4*>(Tl + 8 * j * TS + 4);
+    float a[8] = {__fadd_rn(t0.x, b8[0]), __fadd_rn(t0.y, b8[1]), __fadd_rn(t0.z, b8[2]), __fadd_rn(t0.w, b8[3]),
+                  __fadd_rn(t1.x, b8[4]), __fadd_rn(t1.y, b8[5]), __fadd_rn(t1.z, b8[6]), __fadd_rn(t1.w, b8[7])};
+    if (HAS_U) stg_u4(pu + j * su, pack_bf16x8(a));
+    float x[8];
+    if (HAS_X0) {
+      unpack_bf16x8(px0[j], x);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) a[i] = __fmul_rn(a[i], x[i]);
+    }
+    unpack_bf16x8(pxl[j], x);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) a[i] = __fadd_rn(a[i], x[i]);
+    stg_u4(po + j * so, pack_bf16x8(a));
   }
 }
 
@@ -215,7 +262,7 @@ __device__ __forceinline__ void epi_preload(const __nv_bfloat16* base, long long
   for (int j = 0; j < 4; ++j) {
     const long long rr = row_base + r4 + 8 * j;
     w[j] = make_uint4(0u, 0u, 0u, 0u);
-    if (rr < M) w[j] = *reinterpret_cast<const uint4*>(base + rr * ld + col0 + 8 * g4);
+    if (rr < M) w[j] = ldg_u4(base + rr * ld + col0 + 8 * g4);
   }
 }
 __device__ __forceinline__ void epi_block(const EpiParams& ep, float* T, int lane, long long row_base, long long col0, int ncol,
@@ -274,50 +321,73 @@ __device__ __forceinline__ void epi_block(const EpiParams& ep, float* T, int lan
   const bool whole = nv >= 8;
   float b8[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
   if (ep.bias) {
+    if (whole && al16(ep.bias + off)) {
+      const float4 p = ldg_f4(ep.bias + off), q = ldg_f4(ep.bias + off + 4);
+      b8[0] = p.x; b8[1] = p.y; b8[2] = p.z; b8[3] = p.w; b8[4] = q.x; b8[5] = q.y; b8[6] = q.z; b8[7] = q.w;
+    } else {
 #pragma unroll
-    for (int i = 0; i < 8; ++i)
-      if (i < nv) b8[i] = ep.bias[off + i];
+      for (int i = 0; i < 8; ++i)
+        if (i < nv) b8[i] = ep.bias[off + i];
+    }
   }
+  const long long r0 = row_base + r4;                // this lane's rows: r0 + 8 j
+  const float* Tl = T + r4 * TS + 8 * g4;
   if (ep.mode == EPI_LINEAR) {
-    __nv_bfloat16* C = reinterpret_cast<__nv_bfloat16*>(ep.C);
-    const bool vc = whole && (ep.ldc & 7) == 0 && al16(C + off);
+    __nv_bfloat16* pc = reinterpret_cast<__nv_bfloat16*>(ep.C) + r0 * ep.ldc + off;
+    const bool vc = whole && (ep.ldc & 7) == 0 && al16(pc);
 #pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      const int r = r4 + 8 * j;
-      const long long rr = row_base + r;
-      const float4 t0 = *reinterpret_cast<const float4*>(&T[r * TS + 8 * g4]);
-      const float4 t1 = *reinterpret_cast<const float4*>(&T[r * TS + 8 * g4 + 4]);
+    for (int j = 0; j < 4; ++j, pc += 8 * ep.ldc) {
+      const float4 t0 = *reinterpret_cast<const float4*>(Tl + 8 * j * TS);
+      const float4 t1 = *reinterpret_cast<const float4*>(Tl + 8 * j * TS + 4);
       float a[8] = {t0.x + b8[0], t0.y + b8[1], t0.z + b8[2], t0.w + b8[3], t1.x + b8[4], t1.y + b8[5], t1.z + b8[6], t1.w + b8[7]};
       act_vec<8>(a, ep.act);
-      if (rr < ep.M) store_bf16x8(C + rr * ep.ldc + off, vc, nv, a);
+      if (r0 + 8 * j < ep.M) store_bf16x8(pc, vc, nv, a);
     }
     return;
   }
   // EPI_CROSS: u = acc + b ; out = x0 * u + xl   (x0 == NULL: out = u + xl)
-  const bool vx = whole && (ep.ldx & 7) == 0 && al16(ep.xl + off) && (!ep.x0 || al16(ep.x0 + off));
-  const bool vo = whole && (ep.ldo & 7) == 0 && al16(ep.out + off);
-  const bool vu = whole && ep.u && (ep.ldu & 7) == 0 && al16(ep.u + off);
+  const __nv_bfloat16* pxl_g = ep.xl + r0 * ep.ldx + off;
+  const __nv_bfloat16* px0_g = ep.x0 ? ep.x0 + r0 * ep.ldx + off : nullptr;
+  __nv_bfloat16* po = ep.out + r0 * ep.ldo + off;
+  __nv_bfloat16* pu = ep.u ? ep.u + r0 * ep.ldu + off : nullptr;
+  const bool vx = whole && (ep.ldx & 7) == 0 && al16(pxl_g) && (!px0_g || al16(px0_g));
+  const bool vo = whole && (ep.ldo & 7) == 0 && al16(po);
+  const bool vu = whole && pu && (ep.ldu & 7) == 0 && al16(pu);
+  if (pre && ncol == 32 && vx && vo && (!pu || vu) && row_base + 32 <= ep.M) {
+    if (pu) {
+      if (px0_g) epi_cross_lean<true, true>(ep, Tl, b8, r0, off, px0, pxl);
+      else epi_cross_lean<true, false>(ep, Tl, b8, r0, off, px0, pxl);
+    } else {
+      if (px0_g) epi_cross_lean<false, true>(ep, Tl, b8, r0, off, px0, pxl);
+      else epi_cross_lean<false, false>(ep, Tl, b8, r0, off, px0, pxl);
+    }
+    return;
+  }
 #pragma unroll
   for (int j = 0; j < 4; ++j) {
-    const int r = r4 + 8 * j;
-    const long long rr = row_base + r;
-    const float4 t0 = *reinterpret_cast<const float4*>(&T[r * TS + 8 * g4]);
-    const float4 t1 = *reinterpret_cast<const float4*>(&T[r * TS + 8 * g4 + 4]);
-    float a[8] = {t0.x + b8[0], t0.y + b8[1], t0.z + b8[2], t0.w + b8[3], t1.x + b8[4], t1.y + b8[5], t1.z + b8[6], t1.w + b8[7]};
-    if (rr >= ep.M) continue;
-    if (ep.u) store_bf16x8(ep.u + rr * ep.ldu + off, vu, nv, a);
-    float x[8];
-    if (ep.x0) {
-      if (pre) unpack_bf16x8(px0[j], x);
-      else load_bf16x8(ep.x0 + rr * ep.ldx + off, vx, nv, x);
+    const float4 t0 = *reinterpret_cast<const float4*>(Tl + 8 * j * TS);
+    const float4 t1 = *reinterpret_cast<const float4*>(Tl + 8 * j * TS + 4);
+    float a[8] = {__fadd_rn(t0.x, b8[0]), __fadd_rn(t0.y, b8[1]), __fadd_rn(t0.z, b8[2]), __fadd_rn(t0.w, b8[3]),
+                  __fadd_rn(t1.x, b8[4]), __fadd_rn(t1.y, b8[5]), __fadd_rn(t1.z, b8[6]), __fadd_rn(t1.w, b8[7])};
+    if (r0 + 8 * j < ep.M) {
+      if (pu) store_bf16x8(pu, vu, nv, a);
+      float x[8];
+      if (px0_g) {
+        if (pre) unpack_bf16x8(px0[j], x);
+        else load_bf16x8(px0_g, vx, nv, x);
 #pragma unroll
-      for (int i = 0; i < 8; ++i) a[i] *= x[i];
+        for (int i = 0; i < 8; ++i) a[i] = __fmul_rn(a[i], x[i]);
+      }
+      if (pre) unpack_bf16x8(pxl[j], x);
+      else load_bf16x8(pxl_g, vx, nv, x);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) a[i] = __fadd_rn(a[i], x[i]);
+      store_bf16x8(po, vo, nv, a);
     }
-    if (pre) unpack_bf16x8(pxl[j], x);
-    else load_bf16x8(ep.xl + rr * ep.ldx + off, vx, nv, x);
-#pragma unroll
-    for (int i = 0; i < 8; ++i) a[i] += x[i];
-    store_bf16x8(ep.out + rr * ep.ldo + off, vo, nv, a);
+    pxl_g += 8 * ep.ldx;
+    if (px0_g) px0_g += 8 * ep.ldx;
+    po += 8 * ep.ldo;
+    if (pu) pu += 8 * ep.ldu;
   }
 }
 
@@ -489,7 +559,7 @@ __device__ __forceinline__ void cluster_sync_all() {
   asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
 }
 __device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
-  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+  asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
 }
 __device__ __forceinline__ void mbar_arrive_local(uint32_t bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
@@ -548,7 +618,7 @@ __device__ __forceinline__ void umma_commit_cg(uint32_t bar) {
 constexpr int kEpiWarps = 8;
 constexpr int kEpiTileBytes = kEpiWarps * 32 * 36 * 4;       // the epilogue warps' private transpose tiles
 
-template <int BLOCK_N, int STAGES, int CG>
+template <int BLOCK_N, int STAGES, int CG, bool PIPE>
 __global__ void __launch_bounds__(kThreads, 1)
 gemm_bf16_persist_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b, const EpiParams ep,
                          int num_tiles, int n_tiles) {
@@ -677,26 +747,45 @@ gemm_bf16_persist_kernel(const __grid_constant__ CUtensorMap map_a, const __grid
       preload(half * 32);                                   // in flight while the accumulator is still being computed
       mbar_wait(smem_u32(&tmem_full_bar[acc]), accph);
       fence_after();
+      const uint32_t t_acc = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)acc * ACC_COLS;
+      uint32_t vn[32];
+      if (PIPE && tile_col0 + half * 32 < ep.N) {
+        tmem_ld32_issue(t_acc + (uint32_t)(half * 32), vn);
+        tmem_ld_wait();
+      }
+      bool released = false;
+      auto release = [&]() {                                // all of this warp's reads of the accumulator are done
+        released = true;
+        fence_before();
+        __syncwarp();
+        if (lane == 0) {
+          if (CG == 2) mbar_arrive_cluster(empty_addr0 + (uint32_t)acc * 8u);
+          else mbar_arrive_local(empty_addr0 + (uint32_t)acc * 8u);
+        }
+      };
 #pragma unroll 1
       for (int c0 = half * 32; c0 < BLOCK_N; c0 += 64) {
         const long long col0 = tile_col0 + c0;
         if (col0 >= ep.N) break;                            // warp-uniform
         uint4 cx0[4], cxl[4];
+        uint32_t v[32];
 #pragma unroll
         for (int j = 0; j < 4; ++j) { cx0[j] = nx0[j]; cxl[j] = nxl[j]; }
         const bool cpre = npre;
-        uint32_t v[32];
-        tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)acc * ACC_COLS + (uint32_t)c0, v);
-        preload(c0 + 64);                                   // the next block's operands fly during this block's work
+        const bool more = c0 + 64 < BLOCK_N && col0 + 64 < ep.N;
+        if (PIPE) {
+#pragma unroll
+          for (int i = 0; i < 32; ++i) v[i] = vn[i];
+          if (more) tmem_ld32_issue(t_acc + (uint32_t)(c0 + 64), vn);    // next block: TMEM -> registers under this block's work
+        } else {
+          tmem_ld32(t_acc + (uint32_t)c0, v);
+        }
+        if (!more) release();                               // (the last block is already in registers)
+        preload(c0 + 64);                                   // the next block's x0 / xl fly during this block's work too
         epi_block(ep, T, lane, row_base, col0, chunk_cols(c0), v, 0, cpre, cx0, cxl);
+        if (PIPE && more) tmem_ld_wait();
       }
-      // every tcgen05.ld of this warp has completed (tmem_ld32 waits): hand the accumulator back to the MMA warp
-      fence_before();
-      __syncwarp();
-      if (lane == 0) {
-        if (CG == 2) mbar_arrive_cluster(empty_addr0 + (uint32_t)acc * 8u);
-        else mbar_arrive_local(empty_addr0 + (uint32_t)acc * 8u);
-      }
+      if (!released) release();
     }
   }
   fence_before();
@@ -918,13 +1007,13 @@ static int launch_tile(etr_ctx* ctx, const CUtensorMap& ma, const CUtensorMap& m
   return ETR_OK;
 }
 
-template <int BLOCK_N, int STAGES, int CG>
-static int launch_persist(etr_ctx* ctx, const CUtensorMap& ma, const CUtensorMap& mb, const EpiParams& ep, int num_tiles,
+template <int BLOCK_N, int STAGES, int CG, bool PIPE>
+static int launch_persist2(etr_ctx* ctx, const CUtensorMap& ma, const CUtensorMap& mb, const EpiParams& ep, int num_tiles,
                           int n_tiles, cudaStream_t s) {
   constexpr size_t b_bytes = ((size_t)(BLOCK_N / CG) * BLOCK_K * 2 + 1023) & ~(size_t)1023;
   constexpr size_t smem = (size_t)STAGES * (BLOCK_M * BLOCK_K * 2 + b_bytes) + kEpiTileBytes + (2 * STAGES + 4) * 8 + 16 + 1024;
   static_assert(smem <= 232448, "shared memory budget of one SM");
-  auto kern = gemm_bf16_persist_kernel<BLOCK_N, STAGES, CG>;
+  auto kern = gemm_bf16_persist_kernel<BLOCK_N, STAGES, CG, PIPE>;
   ETR_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   int clusters = ctx->sm_count / CG;
   if (clusters > num_tiles) clusters = num_tiles;
@@ -944,6 +1033,14 @@ static int launch_persist(etr_ctx* ctx, const CUtensorMap& ma, const CUtensorMap
   ETR_CUDA(cudaLaunchKernelEx(&cfg, kern, ma, mb, ep, num_tiles, n_tiles));
   ETR_LAUNCH_CHECK(ctx);
   return ETR_OK;
+}
+
+template <int BLOCK_N, int STAGES, int CG>
+static int launch_persist(etr_ctx* ctx, const CUtensorMap& ma, const CUtensorMap& mb, const EpiParams& ep, int num_tiles,
+                          int n_tiles, cudaStream_t s) {
+  const char* e = getenv("ETR_GEMM_EPI_PIPE");        // 1: the next block's tcgen05.ld is issued under the current block's work
+  if (e && atoi(e) == 1) return launch_persist2<BLOCK_N, STAGES, CG, true>(ctx, ma, mb, ep, num_tiles, n_tiles, s);
+  return launch_persist2<BLOCK_N, STAGES, CG, false>(ctx, ma, mb, ep, num_tiles, n_tiles, s);
 }
 
 // ETR_GEMM_PERSIST: 0 = per-tile kernel only, 1 = persistent one-CTA form, 2 (default) = persistent CTA-pair form
