@@ -370,8 +370,12 @@ def run_c3(args):
                    "id_distribution": args.dist, "cuda_graph": use_graph, "l2": "L2 flushed before every timed step",
                    "apply_mode": "rowwise Adam"},
         "clocks": clk, "gpu_launches": rt.launches - l0,
-        "roofline": {"bound": "tensor", "kernel": "gemm_bf16_tn_kernel<240,2> EPI_CROSS (one cross layer forward)",
-                     "achieved": ach, "peak": peak, "unit": "TFLOP/s", "frac": ach / peak, "traffic": None,
+        "roofline": {"bound": "tensor", "kernel": {"0": "gemm_bf16_tn_kernel<240,2> (one tile per CTA)",
+                                                   "1": "gemm_bf16_persist_kernel<240,4,1> (persistent, TMEM double-buffered)"}.get(
+                         os.environ.get("ETR_GEMM_PERSIST", "2"), "gemm_bf16_persist_kernel<240,5,2> (persistent CTA pairs, "
+                         "tcgen05 cta_group::2, TMEM double-buffered)") + " EPI_CROSS: one cross layer forward, x_{l+1} = x0 (.) (W x_l + b) + x_l",
+                     "achieved": ach, "peak": peak, "unit": "TFLOP/s", "frac": ach / peak,
+                     "traffic": (ncu_traffic("gemm_bf16_persist") or [None])[0],
                      "kernel_ms": k_ms, "peak_source": "MEASURED_PEAKS.json bf16_tflops (burst; kernel timed alone)"},
         "cross_gemm_share_of_step_at_peak": step_flops / (float(peaks.get("bf16_tflops_sustained", peak)) * 1e12)
         / (total / args.steps * 1e-3),

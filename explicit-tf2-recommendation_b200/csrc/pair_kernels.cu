@@ -42,45 +42,106 @@ __device__ __forceinline__ int bag_count(const PairParams& p, long long b, int f
 
 // CPL: 16-byte chunks per lane (row of up to 32*CPL chunks)
 template <int CPL>
-__global__ void __launch_bounds__(256) field_pair_fwd_kernel(const PairParams p) {
+__global__ void __launch_bounds__(256, 3) field_pair_fwd_kernel(const PairParams p) {
   extern __shared__ __align__(16) float E[];          // [F][es]
   __shared__ float red[8];
+  __shared__ int bag_ctr;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
   const int P = p.F * (p.F - 1) / 2;
   const int Fk = p.F * p.k;
+  if (threadIdx.x == 0) bag_ctr = 0;
+  __syncthreads();
   for (long long b = blockIdx.x; b < p.B; b += gridDim.x) {
     // ---- phase 1: pool every field's bag into E[a][:]
-    for (int a = warp; a < p.F; a += nwarps) {
-      const long long* base; long long step; int n;
+    // The ids of a bag are read 64 slots at a time by the whole warp (two per lane), pads / out-of-range ids drop out
+    // in a ballot, and the surviving ids are handed out four at a time by shuffles: the row loads of a bag are issued
+    // back to back (12 x 128-bit per lane in flight) instead of waiting for each group's ids, and padded slots cost
+    // nothing.  The ids of the warp's NEXT bag are fetched before this bag's rows, so that latency is hidden too.
+    // Accumulation order = slot order of the valid ids (unchanged: bit-identical sums).
+    auto bag_desc = [&](int a, const long long*& base, long long& step, int& n) {
       if (p.csr) { const int o0 = p.csr[b * p.F + a]; n = p.csr[b * p.F + a + 1] - o0; base = p.ids + o0; step = 1; }
       else { base = p.ids + b * p.sb + (long long)a * p.sf; step = p.sl; n = p.L; }
+    };
+    auto load_ids = [&](const long long* base, long long step, int n, int s0, long long& i0, long long& i1, bool& k0, bool& k1) {
+      const int s = s0 + lane;
+      i0 = 0; i1 = 0; k0 = false; k1 = false;
+      if (s < n) {
+        i0 = __ldg(base + (long long)s * step);
+        k0 = !(p.has_pad && i0 == p.pad);
+        if (k0 && (unsigned long long)i0 >= (unsigned long long)p.rows) { flag_bad_id(p.err, i0); k0 = false; }
+      }
+      if (s + 32 < n) {
+        i1 = __ldg(base + (long long)(s + 32) * step);
+        k1 = !(p.has_pad && i1 == p.pad);
+        if (k1 && (unsigned long long)i1 >= (unsigned long long)p.rows) { flag_bad_id(p.err, i1); k1 = false; }
+      }
+    };
+    // bags are claimed dynamically (their lengths differ: a static split leaves warps idle at the barrier below)
+    auto claim = [&]() {
+      int x = 0;
+      if (lane == 0) x = atomicAdd(&bag_ctr, 1);
+      return __shfl_sync(0xffffffffu, x, 0);
+    };
+    long long ni0 = 0, ni1 = 0; bool nk0 = false, nk1 = false;
+    int a = claim();
+    if (a < p.F) {
+      const long long* base; long long step; int n;
+      bag_desc(a, base, step, n);
+      load_ids(base, step, n, 0, ni0, ni1, nk0, nk1);
+    }
+    while (a < p.F) {
+      const int a_next = claim();
+      const long long* base; long long step; int n;
+      bag_desc(a, base, step, n);
       float4 acc[CPL];
 #pragma unroll
       for (int j = 0; j < CPL; ++j) acc[j] = make_float4(0.f, 0.f, 0.f, 0.f);
       int cnt = 0;
-      for (int l0 = 0; l0 < n; l0 += 4) {
-        long long id[4]; bool ok[4];
-#pragma unroll
-        for (int u = 0; u < 4; ++u) {
-          const bool in = (l0 + u) < n;
-          id[u] = in ? __ldg(base + (long long)(l0 + u) * step) : 0;
-          ok[u] = in && !(p.has_pad && id[u] == p.pad);
-          if (ok[u] && (unsigned long long)id[u] >= (unsigned long long)p.rows) { flag_bad_id(p.err, id[u]); ok[u] = false; }
+      for (int s0 = 0; s0 < n || s0 == 0; s0 += 64) {
+        long long i0, i1; bool k0, k1;
+        if (s0 == 0) { i0 = ni0; i1 = ni1; k0 = nk0; k1 = nk1; }
+        else load_ids(base, step, n, s0, i0, i1, k0, k1);
+        if (s0 == 0 && a_next < p.F) {                 // the next bag's first 64 ids: in flight during this bag's rows
+          const long long* nb; long long ns; int nn;
+          bag_desc(a_next, nb, ns, nn);
+          load_ids(nb, ns, nn, 0, ni0, ni1, nk0, nk1);
         }
-        float4 r[4][CPL];
+        unsigned m0 = __ballot_sync(0xffffffffu, k0), m1 = __ballot_sync(0xffffffffu, k1);
+        cnt += __popc(m0) + __popc(m1);
+        // two-stage pipeline over pairs of rows: the loads of pair g + 1 are issued before pair g is accumulated
+        auto issue = [&](float4 (&r)[2][CPL]) {        // pops up to two valid ids (slot order) and issues their row loads
 #pragma unroll
-        for (int u = 0; u < 4; ++u)
+          for (int u = 0; u < 2; ++u) {
+            const bool ok = (m0 | m1) != 0;
+            int src = 0; bool hi = false;
+            if (m0) { src = __ffs(m0) - 1; m0 &= m0 - 1; }
+            else if (m1) { src = __ffs(m1) - 1; m1 &= m1 - 1; hi = true; }
+            const long long x0 = __shfl_sync(0xffffffffu, i0, src), x1 = __shfl_sync(0xffffffffu, i1, src);
+            const char* row = p.table + (hi ? x1 : x0) * (long long)p.row_bytes;
 #pragma unroll
-          for (int j = 0; j < CPL; ++j) {
-            const int c = lane + j * 32;
-            r[u][j] = (ok[u] && c < p.nchunks) ? ldg_row16(p.table + id[u] * (long long)p.row_bytes + c * 16)
-                                               : make_float4(0.f, 0.f, 0.f, 0.f);
+            for (int j = 0; j < CPL; ++j) {
+              const int c = lane + j * 32;
+              r[u][j] = (ok && c < p.nchunks) ? ldg_row16(row + c * 16) : make_float4(0.f, 0.f, 0.f, 0.f);
+            }
           }
+        };
+        auto add = [&](const float4 (&r)[2][CPL]) {
 #pragma unroll
-        for (int u = 0; u < 4; ++u) {
-          cnt += ok[u] ? 1 : 0;
+          for (int u = 0; u < 2; ++u)
 #pragma unroll
-          for (int j = 0; j < CPL; ++j) { acc[j].x += r[u][j].x; acc[j].y += r[u][j].y; acc[j].z += r[u][j].z; acc[j].w += r[u][j].w; }
+            for (int j = 0; j < CPL; ++j) { acc[j].x += r[u][j].x; acc[j].y += r[u][j].y; acc[j].z += r[u][j].z; acc[j].w += r[u][j].w; }
+        };
+        if (m0 | m1) {                                 // warp-uniform control flow throughout
+          float4 rA[2][CPL], rB[2][CPL];
+          issue(rA);
+          while (true) {
+            if (!(m0 | m1)) { add(rA); break; }
+            issue(rB);
+            add(rA);
+            if (!(m0 | m1)) { add(rB); break; }
+            issue(rA);
+            add(rB);
+          }
         }
       }
       const float inv = (p.mean && cnt > 1) ? 1.0f / (float)cnt : 1.0f;
@@ -99,8 +160,10 @@ __global__ void __launch_bounds__(256) field_pair_fwd_kernel(const PairParams p)
           }
         }
       }
+      a = a_next;
     }
     __syncthreads();
+    if (threadIdx.x == 0) bag_ctr = 0;                 // (visible to the next sample through the barrier that ends phase 2)
     // ---- phase 2: pairs
     float part = 0.f;
     for (int pi = threadIdx.x; pi < P; pi += blockDim.x) {
