@@ -15,6 +15,7 @@ Extra, build-defined kwargs (all optional, defaults reproduce the reference):
 from __future__ import annotations
 
 import ctypes as C
+import os
 from typing import Dict, List, Optional, Sequence
 
 import torch
@@ -1104,22 +1105,41 @@ class MatrixCrossLayer(CrossLayer):
             gout.to(torch.bfloat16).contiguous()
         dx0 = rt.empty((B, Di))
         assert x0.stride(0) == Di
+        # one-pass form (round 2): du + db in one kernel per layer, dx0 = sum_l G_{l+1} (.) u_l + G_0 written once at the end
+        # (needs 16-byte aligned rows everywhere; otherwise the per-layer read-modify-write form below)
+        one_pass = (Di % 8 == 0 and G.stride(0) % 8 == 0 and G.data_ptr() % 16 == 0 and self.layer_num <= 8
+                    and os.environ.get("ETR_CROSS_BWD_ONEPASS", "1") != "0")
+        Gs = [None] * (self.layer_num + 1)
+        Gs[self.layer_num] = G
         for l in reversed(range(self.layer_num)):
             du = rt.empty((B, Di), torch.bfloat16)
-            check(rt.lib.etr_cross_mat_bwd_elementwise_bf16(rt.ctx, G.data_ptr(), G.stride(0), x0.data_ptr(), us[l].data_ptr(),
-                                                            B, Di, du.data_ptr(), dx0.data_ptr(),
-                                                            int(l == self.layer_num - 1), rt.stream))
+            if one_pass:
+                check(rt.lib.etr_cross_mat_bwd_du_colsum_bf16(rt.ctx, G.data_ptr(), G.stride(0), x0.data_ptr(), B, Di, du.data_ptr(),
+                                                              self.params.g("cross/b")[l].data_ptr(), rt.stream))
+            else:
+                check(rt.lib.etr_cross_mat_bwd_elementwise_bf16(rt.ctx, G.data_ptr(), G.stride(0), x0.data_ptr(), us[l].data_ptr(),
+                                                                B, Di, du.data_ptr(), dx0.data_ptr(),
+                                                                int(l == self.layer_num - 1), rt.stream))
             # dW_l = dU^T X_l : both operands as stored ([B, Di], MN-major UMMA operands), split-K over the batch; fp32 result
             gemm_bf16_wgrad(rt, du, xs[l], self.params.g("cross/W")[l], Di, Di, B)
-            check(rt.lib.etr_colsum_bf16(rt.ctx, du.data_ptr(), B, Di, Di, self.params.g("cross/b")[l].data_ptr(),
-                                         rt.stream))
+            if not one_pass:
+                check(rt.lib.etr_colsum_bf16(rt.ctx, du.data_ptr(), B, Di, Di, self.params.g("cross/b")[l].data_ptr(),
+                                             rt.stream))
             # G_l = G_{l+1} + dU W_l : B operand [N=j, K=i] = W[i,j]  ->  W^T
             Wt = cast_bf16(rt, W[l], transpose=True)
             Gn = rt.empty((B, Di), torch.bfloat16)
             check(rt.lib.etr_gemm_bf16_tn_residual(rt.ctx, B, Di, Di, du.data_ptr(), Di, Wt.data_ptr(), Wt.stride(0),
                                                    G.data_ptr(), G.stride(0), Gn.data_ptr(), Di, rt.stream))
             G = Gn
-        check(rt.lib.etr_add_bf16_into_f32(rt.ctx, G.data_ptr(), B * Di, dx0.data_ptr(), rt.stream))
+            Gs[l] = G
+        if one_pass:
+            L_ = self.layer_num
+            gp = (C.c_void_p * (L_ + 1))(*[g.data_ptr() for g in Gs])
+            gl = (C.c_int64 * (L_ + 1))(*[g.stride(0) for g in Gs])
+            up = (C.c_void_p * L_)(*[u.data_ptr() for u in us])
+            check(rt.lib.etr_cross_mat_bwd_dx0_bf16(rt.ctx, L_, gp, gl, up, B, Di, dx0.data_ptr(), rt.stream))
+        else:
+            check(rt.lib.etr_add_bf16_into_f32(rt.ctx, G.data_ptr(), B * Di, dx0.data_ptr(), rt.stream))
         return dx0
 
     def call(self, inputs, training: bool = False, out: Optional[torch.Tensor] = None):

@@ -902,6 +902,75 @@ __global__ void __launch_bounds__(256) cross_bwd_elem_bf16_kernel(const __nv_bfl
     reinterpret_cast<float2*>(dx0)[t] = d;
   }
 }
+// ---- one-pass forms of the elementwise half of the cross-matrix backward (round 2) ----------------------------
+// (a) du = G (.) x0 (bf16) AND the column sums of du (db_l) in the same pass: a thread owns 8 consecutive columns
+//     (16-byte accesses), the 8 warps of a CTA walk a 512-row slab, per-slab partial sums are combined in slab order.
+constexpr int kDuSlab = 512;
+__global__ void __launch_bounds__(256) cross_bwd_du_colsum_kernel(const __nv_bfloat16* G, long long ldg, const __nv_bfloat16* x0,
+                                                                  long long rows, int cols, __nv_bfloat16* du, float* partial) {
+  __shared__ float sm[8][32][9];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int c = blockIdx.x * 32 + lane;              // 8-column chunk
+  const bool on = c * 8 < cols;
+  const long long r0 = (long long)blockIdx.y * kDuSlab;
+  float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+#pragma unroll 4
+  for (int i = 0; i < kDuSlab / 8; ++i) {
+    const long long r = r0 + warp + 8 * i;
+    if (on && r < rows) {
+      float g[8], a[8];
+      unpack_bf16x8(ldg_u4(G + r * ldg + c * 8), g);
+      unpack_bf16x8(ldg_u4(x0 + r * cols + c * 8), a);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) g[j] *= a[j];
+      const uint4 w = pack_bf16x8(g);
+      stg_u4(du + r * cols + c * 8, w);
+      unpack_bf16x8(w, a);                           // db sums du AS STORED (bf16-rounded), like colsum(du) did
+#pragma unroll
+      for (int j = 0; j < 8; ++j) acc[j] += a[j];
+    }
+  }
+#pragma unroll
+  for (int j = 0; j < 8; ++j) sm[warp][lane][j] = acc[j];
+  __syncthreads();
+  if (warp == 0 && on) {
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      float t = 0.f;
+#pragma unroll
+      for (int w = 0; w < 8; ++w) t += sm[w][lane][j];
+      partial[(long long)blockIdx.y * cols + c * 8 + j] = t;
+    }
+  }
+}
+// (b) dx0 = sum_l G_{l+1} (.) u_l  (l = L-1 .. 0, that order)  + G_0, fp32, written ONCE: replaces the fp32 read-modify-write of
+//     dx0 in every layer's elementwise kernel and the final bf16 -> fp32 add.
+struct Dx0Params {
+  const __nv_bfloat16* G[9]; long long ldg[9];       // G[l + 1] pairs with u[l]; G[0] is the gradient that reaches x0 through x_0
+  const __nv_bfloat16* u[8];
+  int layers; long long rows; int cols; float* dx0;
+};
+__global__ void __launch_bounds__(256) cross_bwd_dx0_kernel(const Dx0Params p) {
+  const int nch = p.cols / 8;
+  const long long total = p.rows * nch;
+  for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (long long)gridDim.x * blockDim.x) {
+    const long long r = t / nch;
+    const int c = (int)(t % nch);
+    float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    for (int l = p.layers - 1; l >= 0; --l) {
+      float g[8], u[8];
+      unpack_bf16x8(ldg_u4(p.G[l + 1] + r * p.ldg[l + 1] + c * 8), g);
+      unpack_bf16x8(ldg_u4(p.u[l] + r * p.cols + c * 8), u);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) acc[j] = (l == p.layers - 1) ? g[j] * u[j] : acc[j] + g[j] * u[j];
+    }
+    float g0[8];
+    unpack_bf16x8(ldg_u4(p.G[0] + r * p.ldg[0] + c * 8), g0);
+    float* o = p.dx0 + r * p.cols + c * 8;
+    *reinterpret_cast<float4*>(o) = make_float4(acc[0] + g0[0], acc[1] + g0[1], acc[2] + g0[2], acc[3] + g0[3]);
+    *reinterpret_cast<float4*>(o + 4) = make_float4(acc[4] + g0[4], acc[5] + g0[5], acc[6] + g0[6], acc[7] + g0[7]);
+  }
+}
 // y (fp32) += x (bf16)
 __global__ void __launch_bounds__(256) add_bf16_into_f32_kernel(const __nv_bfloat16* x, long long n2, float* y) {
   for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < n2; t += (long long)gridDim.x * blockDim.x) {
@@ -1223,6 +1292,49 @@ int etr_cross_mat_bwd_elementwise_bf16(etr_ctx* ctx, const void* d_g, int64_t ld
   tc::cross_bwd_elem_bf16_kernel<<<grid_for(n / 2, 256, ctx->sm_count, 8), 256, 0, (cudaStream_t)stream>>>(
       (const __nv_bfloat16*)d_g, cols / 2, ldg / 2, (const __nv_bfloat16*)d_x0, (const __nv_bfloat16*)d_u, n / 2,
       (__nv_bfloat16*)d_du, d_dx0_accum, init);
+  ETR_LAUNCH_CHECK(ctx);
+  return ETR_OK;
+}
+
+int etr_cross_mat_bwd_du_colsum_bf16(etr_ctx* ctx, const void* d_g, int64_t ldg, const void* d_x0, int64_t rows, int64_t cols,
+                                     void* d_du, float* d_db, void* stream) {
+  ETR_CHECK_ARG(ctx && d_g && d_x0 && d_du && d_db, "NULL argument");
+  ETR_CHECK_ARG(cols % 8 == 0 && ldg % 8 == 0 && ldg >= cols && ((uintptr_t)d_g & 15) == 0 && ((uintptr_t)d_x0 & 15) == 0 &&
+                    ((uintptr_t)d_du & 15) == 0, "cols / ldg must be multiples of 8 and the matrices 16-byte aligned");
+  cudaStream_t s = (cudaStream_t)stream;
+  if (cols <= 0) return ETR_OK;
+  if (rows <= 0) { ETR_CUDA(cudaMemsetAsync(d_db, 0, sizeof(float) * cols, s)); return ETR_OK; }
+  const long long slabs = ceil_div(rows, tc::kDuSlab);
+  ETR_CHECK_ARG(slabs <= 65535, "too many rows");
+  int st = etr_ws_reserve(ctx, sizeof(float) * (size_t)slabs * cols);
+  if (st != ETR_OK) return st;
+  dim3 grid((unsigned)ceil_div(cols / 8, 32), (unsigned)slabs);
+  tc::cross_bwd_du_colsum_kernel<<<grid, 256, 0, s>>>((const __nv_bfloat16*)d_g, ldg, (const __nv_bfloat16*)d_x0, rows, (int)cols,
+                                                      (__nv_bfloat16*)d_du, (float*)ctx->d_ws);
+  ETR_LAUNCH_CHECK(ctx);
+  tc::colsum_stage2b_kernel<<<grid_for(cols, 256, ctx->sm_count, 1), 256, 0, s>>>((const float*)ctx->d_ws, slabs, cols, d_db);
+  ETR_LAUNCH_CHECK(ctx);
+  return ETR_OK;
+}
+
+int etr_cross_mat_bwd_dx0_bf16(etr_ctx* ctx, int32_t layers, const void* const* h_G, const int64_t* h_ldg, const void* const* h_u,
+                               int64_t rows, int64_t cols, float* d_dx0, void* stream) {
+  ETR_CHECK_ARG(ctx && h_G && h_ldg && h_u && d_dx0, "NULL argument");
+  ETR_CHECK_ARG(layers >= 1 && layers <= 8, "1..8 cross layers");
+  ETR_CHECK_ARG(cols % 8 == 0 && ((uintptr_t)d_dx0 & 15) == 0, "cols must be a multiple of 8");
+  if (rows <= 0 || cols <= 0) return ETR_OK;
+  tc::Dx0Params p;
+  memset(&p, 0, sizeof(p));
+  for (int l = 0; l <= layers; ++l) {
+    ETR_CHECK_ARG(h_G[l] && h_ldg[l] % 8 == 0 && h_ldg[l] >= cols && ((uintptr_t)h_G[l] & 15) == 0, "G[l]: 16-byte aligned rows");
+    p.G[l] = (const __nv_bfloat16*)h_G[l]; p.ldg[l] = h_ldg[l];
+  }
+  for (int l = 0; l < layers; ++l) {
+    ETR_CHECK_ARG(h_u[l] && ((uintptr_t)h_u[l] & 15) == 0, "u[l]: 16-byte aligned");
+    p.u[l] = (const __nv_bfloat16*)h_u[l];
+  }
+  p.layers = layers; p.rows = rows; p.cols = (int)cols; p.dx0 = d_dx0;
+  tc::cross_bwd_dx0_kernel<<<grid_for(rows * (cols / 8), 256, ctx->sm_count, 8), 256, 0, (cudaStream_t)stream>>>(p);
   ETR_LAUNCH_CHECK(ctx);
   return ETR_OK;
 }

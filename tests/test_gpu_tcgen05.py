@@ -388,3 +388,46 @@ def test_gemm_bf16_tn_persistent(rt, persist_env, mode, out_dtype):
         err2 = (acc[mode][:, :N].double() - ref2).abs().max().item()
         assert err2 <= 1e-4 * max(ref2.abs().max().item(), 1.0), err2
         assert torch.equal(acc[mode], acc[0])
+
+
+@pytest.mark.parametrize("B,D,slice_off", [(1000, 1680, 0), (513, 64, 8), (2048 + 3, 168, 0)])
+def test_cross_backward_one_pass_kernels(rt, B, D, slice_off):
+    """du = G (.) x0 with db = colsum(du) in one pass, and dx0 = sum_l G_{l+1} (.) u_l + G_0 written once, against the
+    per-layer read-modify-write kernels they replace (same arithmetic order: dx0 bit-identical, du bit-identical, db to
+    summation-order rounding) and against fp64."""
+    import ctypes as C
+    from etr_b200._lib import check
+    L_ = 3
+    wide = _rand_bf16(rt, (B, D + slice_off + 8), D + slice_off + 8, 31)
+    Gs = [_rand_bf16(rt, (B, D), D, 40 + l) for l in range(L_)] + [wide[:, slice_off:slice_off + D]]   # G_L = a column slice
+    us = [_rand_bf16(rt, (B, D), D, 50 + l) for l in range(L_)]
+    x0 = _rand_bf16(rt, (B, D), D, 60)
+    # (a) du + db
+    G = Gs[L_]
+    du = torch.empty((B, D), dtype=torch.bfloat16, device=rt.device)
+    db = torch.empty((D,), device=rt.device)
+    check(rt.lib.etr_cross_mat_bwd_du_colsum_bf16(rt.ctx, G.data_ptr(), G.stride(0), x0.data_ptr(), B, D, du.data_ptr(),
+                                                  db.data_ptr(), rt.stream))
+    du_ref = torch.empty_like(du)
+    dx0_old = torch.empty((B, D), device=rt.device)
+    check(rt.lib.etr_cross_mat_bwd_elementwise_bf16(rt.ctx, G.data_ptr(), G.stride(0), x0.data_ptr(), us[L_ - 1].data_ptr(), B, D,
+                                                    du_ref.data_ptr(), dx0_old.data_ptr(), 1, rt.stream))
+    torch.cuda.synchronize()
+    assert torch.equal(du, du_ref)
+    ref_db = du.double().sum(0)
+    assert (db.double() - ref_db).abs().max().item() <= 1e-5 * max(1.0, ref_db.abs().max().item())
+    # (b) dx0 in one pass == the layer-by-layer accumulation
+    for l in reversed(range(L_ - 1)):
+        tmp = torch.empty_like(du)
+        check(rt.lib.etr_cross_mat_bwd_elementwise_bf16(rt.ctx, Gs[l + 1].data_ptr(), Gs[l + 1].stride(0), x0.data_ptr(),
+                                                        us[l].data_ptr(), B, D, tmp.data_ptr(), dx0_old.data_ptr(), 0, rt.stream))
+    check(rt.lib.etr_add_bf16_into_f32(rt.ctx, Gs[0].data_ptr(), B * D, dx0_old.data_ptr(), rt.stream))
+    dx0 = torch.empty((B, D), device=rt.device)
+    gp = (C.c_void_p * (L_ + 1))(*[g.data_ptr() for g in Gs])
+    gl = (C.c_int64 * (L_ + 1))(*[g.stride(0) for g in Gs])
+    up = (C.c_void_p * L_)(*[u.data_ptr() for u in us])
+    check(rt.lib.etr_cross_mat_bwd_dx0_bf16(rt.ctx, L_, gp, gl, up, B, D, dx0.data_ptr(), rt.stream))
+    torch.cuda.synchronize()
+    ref = sum(Gs[l + 1].double() * us[l].double() for l in range(L_)) + Gs[0].double()
+    assert (dx0.double() - ref).abs().max().item() <= 1e-5 * max(1.0, ref.abs().max().item())
+    assert torch.equal(dx0, dx0_old)
