@@ -948,6 +948,7 @@ __global__ void __launch_bounds__(256) cross_bwd_du_colsum_kernel(const __nv_bfl
 struct Dx0Params {
   const __nv_bfloat16* G[9]; long long ldg[9];       // G[l + 1] pairs with u[l]; G[0] is the gradient that reaches x0 through x_0
   const __nv_bfloat16* u[8];
+  const __nv_bfloat16* extra; long long ld_extra;    // optional: one more bf16 term (the other branch's gradient for the same input)
   int layers; long long rows; int cols; float* dx0;
 };
 __global__ void __launch_bounds__(256) cross_bwd_dx0_kernel(const Dx0Params p) {
@@ -966,6 +967,14 @@ __global__ void __launch_bounds__(256) cross_bwd_dx0_kernel(const Dx0Params p) {
     }
     float g0[8];
     unpack_bf16x8(ldg_u4(p.G[0] + r * p.ldg[0] + c * 8), g0);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[j] += g0[j];
+    if (p.extra) {
+      unpack_bf16x8(ldg_u4(p.extra + r * p.ld_extra + c * 8), g0);
+    } else {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) g0[j] = 0.f;
+    }
     float* o = p.dx0 + r * p.cols + c * 8;
     *reinterpret_cast<float4*>(o) = make_float4(acc[0] + g0[0], acc[1] + g0[1], acc[2] + g0[2], acc[3] + g0[3]);
     *reinterpret_cast<float4*>(o + 4) = make_float4(acc[4] + g0[4], acc[5] + g0[5], acc[6] + g0[6], acc[7] + g0[7]);
@@ -1318,7 +1327,7 @@ int etr_cross_mat_bwd_du_colsum_bf16(etr_ctx* ctx, const void* d_g, int64_t ldg,
 }
 
 int etr_cross_mat_bwd_dx0_bf16(etr_ctx* ctx, int32_t layers, const void* const* h_G, const int64_t* h_ldg, const void* const* h_u,
-                               int64_t rows, int64_t cols, float* d_dx0, void* stream) {
+                               const void* d_extra, int64_t ld_extra, int64_t rows, int64_t cols, float* d_dx0, void* stream) {
   ETR_CHECK_ARG(ctx && h_G && h_ldg && h_u && d_dx0, "NULL argument");
   ETR_CHECK_ARG(layers >= 1 && layers <= 8, "1..8 cross layers");
   ETR_CHECK_ARG(cols % 8 == 0 && ((uintptr_t)d_dx0 & 15) == 0, "cols must be a multiple of 8");
@@ -1333,6 +1342,8 @@ int etr_cross_mat_bwd_dx0_bf16(etr_ctx* ctx, int32_t layers, const void* const* 
     ETR_CHECK_ARG(h_u[l] && ((uintptr_t)h_u[l] & 15) == 0, "u[l]: 16-byte aligned");
     p.u[l] = (const __nv_bfloat16*)h_u[l];
   }
+  ETR_CHECK_ARG(!d_extra || (ld_extra % 8 == 0 && ld_extra >= cols && ((uintptr_t)d_extra & 15) == 0), "extra: 16-byte aligned rows");
+  p.extra = (const __nv_bfloat16*)d_extra; p.ld_extra = ld_extra;
   p.layers = layers; p.rows = rows; p.cols = (int)cols; p.dx0 = d_dx0;
   tc::cross_bwd_dx0_kernel<<<grid_for(rows * (cols / 8), 256, ctx->sm_count, 8), 256, 0, (cudaStream_t)stream>>>(p);
   ETR_LAUNCH_CHECK(ctx);

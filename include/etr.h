@@ -413,11 +413,13 @@ int etr_cross_mat_bwd_elementwise_bf16(etr_ctx* ctx, const void* d_g, int64_t ld
 /* One-pass forms of the same backward (tape.gradient through 3.DCN/CustomLayers.py:300-303 for all layers):
  *   etr_cross_mat_bwd_du_colsum_bf16 : du = g (.) x0 (bf16) and db_l[n] = sum_m du[m,n] (of the stored, bf16-rounded du) in ONE pass
  *   etr_cross_mat_bwd_dx0_bf16 : dx0 = sum_{l = L-1..0} G_{l+1} (.) u_l + G_0, fp32, written once (host arrays of L+1 gradient
- *       pointers / row pitches and L saved-u pointers; every matrix [rows, cols], cols % 8 == 0, rows 16-byte aligned).   */
+ *       pointers / row pitches and L saved-u pointers; every matrix [rows, cols], cols % 8 == 0, rows 16-byte aligned);
+ *       d_extra (may be NULL): one more bf16 [rows, cols] term added last -- the gradient the Dense branch of
+ *       DeepCrossNetworkLayer computes for the same input x (3.DCN/CustomLayers.py:259-262: x feeds both branches).      */
 int etr_cross_mat_bwd_du_colsum_bf16(etr_ctx* ctx, const void* d_g, int64_t ldg, const void* d_x0, int64_t rows, int64_t cols,
                                      void* d_du, float* d_db, void* stream);
 int etr_cross_mat_bwd_dx0_bf16(etr_ctx* ctx, int32_t layers, const void* const* h_G, const int64_t* h_ldg, const void* const* h_u,
-                               int64_t rows, int64_t cols, float* d_dx0, void* stream);
+                               const void* d_extra, int64_t ld_extra, int64_t rows, int64_t cols, float* d_dx0, void* stream);
 int etr_add_bf16_into_f32(etr_ctx* ctx, const void* d_x, int64_t n, float* d_y, void* stream);
 int etr_colsum_bf16(etr_ctx* ctx, const void* d_X, int64_t M, int64_t N, int64_t ldx, float* d_out,
                     void* stream);

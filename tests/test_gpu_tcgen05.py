@@ -426,8 +426,13 @@ def test_cross_backward_one_pass_kernels(rt, B, D, slice_off):
     gp = (C.c_void_p * (L_ + 1))(*[g.data_ptr() for g in Gs])
     gl = (C.c_int64 * (L_ + 1))(*[g.stride(0) for g in Gs])
     up = (C.c_void_p * L_)(*[u.data_ptr() for u in us])
-    check(rt.lib.etr_cross_mat_bwd_dx0_bf16(rt.ctx, L_, gp, gl, up, B, D, dx0.data_ptr(), rt.stream))
+    check(rt.lib.etr_cross_mat_bwd_dx0_bf16(rt.ctx, L_, gp, gl, up, None, 0, B, D, dx0.data_ptr(), rt.stream))
     torch.cuda.synchronize()
     ref = sum(Gs[l + 1].double() * us[l].double() for l in range(L_)) + Gs[0].double()
     assert (dx0.double() - ref).abs().max().item() <= 1e-5 * max(1.0, ref.abs().max().item())
     assert torch.equal(dx0, dx0_old)
+    ex = _rand_bf16(rt, (B, D), D, 70)
+    dx1 = torch.empty_like(dx0)
+    check(rt.lib.etr_cross_mat_bwd_dx0_bf16(rt.ctx, L_, gp, gl, up, ex.data_ptr(), D, B, D, dx1.data_ptr(), rt.stream))
+    torch.cuda.synchronize()
+    assert torch.equal(dx1, dx0 + ex.float())
