@@ -108,6 +108,7 @@ PROTOTYPES = {
     "etr_cross_mat_bwd_elementwise_bf16": (C.c_int, [_vp, _vp, _i64, _vp, _vp, _i64, _i64, _vp, _vp, _i32, _vp]),
     "etr_cross_mat_bwd_du_colsum_bf16": (C.c_int, [_vp, _vp, _i64, _vp, _i64, _i64, _vp, _vp, _vp]),
     "etr_cross_mat_bwd_dx0_bf16": (C.c_int, [_vp, _i32, _vp, _vp, _vp, _vp, _i64, _i64, _i64, _vp, _vp]),
+    "etr_outer_bf16": (C.c_int, [_vp, _vp, _vp, _i64, _i64, _vp, _i64, _vp]),
     "etr_add_bf16_into_f32": (C.c_int, [_vp, _vp, _i64, _vp, _vp]),
     "etr_colsum_bf16": (C.c_int, [_vp, _vp, _i64, _i64, _i64, _vp, _vp]),
     "etr_deepfm_tail_train": (C.c_int, [_vp, _vp, _vp, _vp, _i64, _vp, _vp, _vp, _vp, _f32, _vp, _vp, _vp, _vp, _vp, _vp, _vp,

@@ -175,7 +175,7 @@ __global__ void __launch_bounds__(256) gemm_skinny_rows_kernel(const GemmParams 
   }
 }
 
-// wgrad of the tail: C[M,N] = A^T B with M*N <= 256 and K = batch.  Each CTA stages a slab of
+// wgrad of the tail: C[M,N] = A^T B with M*N <= 1024 (M + N <= 88: the slab fits 48 KB) and K = batch.  Each CTA stages a slab of
 // kSkinnySlab batch rows of A ([rows, M]) and B ([rows, N]) in shared memory (coalesced, no index
 // division) and thread t = (m, n) reduces it; the slab partials are then summed by one warp per
 // output in a fixed order (lane partition + xor tree) -- deterministic.
@@ -195,12 +195,12 @@ __global__ void __launch_bounds__(256) gemm_skinny_wgrad_kernel(const GemmParams
     for (int nn = lane; nn < N; nn += 32) Bs[r * N + nn] = in ? p.B[(r0 + r) * p.sbk + nn * p.sbn] : 0.f;
   }
   __syncthreads();
-  if (t < M * N) {
-    const int om = t / N, on = t % N;
+  for (int o = t; o < M * N; o += 256) {               // up to 4 outputs per thread (M*N <= 1024)
+    const int om = o / N, on = o % N;
     float acc = 0.f;
 #pragma unroll 8
     for (int r = 0; r < kSkinnySlab; ++r) acc = fmaf(As[r * M + om], Bs[r * N + on], acc);
-    p.partial[(long long)blockIdx.x * M * N + t] = acc;
+    p.partial[(long long)blockIdx.x * M * N + o] = acc;
   }
 }
 // one warp per output element: lane l sums partials l, l+32, ... in order, then a fixed xor tree
@@ -345,7 +345,7 @@ static int gemm_dispatch(etr_ctx* ctx, GemmParams& p, cudaStream_t s) {
     return ETR_OK;
   }
   // wgrad of the tail: tiny output, reduction over the batch
-  if (p.M * p.N <= 256 && p.M <= 64 && p.N <= 32 && p.K >= 4096) {
+  if (p.M * p.N <= 1024 && p.M <= 64 && p.N <= 32 && p.M + p.N <= 88 && p.K >= 4096) {
     p.splits = (int)ceil_div(p.K, kSkinnySlab);
     int st = etr_ws_reserve(ctx, sizeof(float) * (size_t)p.splits * p.M * p.N);
     if (st != ETR_OK) return st;

@@ -980,6 +980,26 @@ __global__ void __launch_bounds__(256) cross_bwd_dx0_kernel(const Dx0Params p) {
     *reinterpret_cast<float4*>(o + 4) = make_float4(acc[4] + g0[4], acc[5] + g0[5], acc[6] + g0[6], acc[7] + g0[7]);
   }
 }
+// out[b, n] = bf16(d[b] * k[n]): the input gradient of a Dense(1) layer (dz K^T is a rank-1 product: no GEMM needed)
+__global__ void __launch_bounds__(256) outer_bf16_kernel(const float* d, const float* k, long long rows, int cols, __nv_bfloat16* out,
+                                                         long long ldo) {
+  const int nch = (cols + 7) / 8;
+  const long long total = rows * nch;
+  for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (long long)gridDim.x * blockDim.x) {
+    const long long r = t / nch;
+    const int c = (int)(t % nch) * 8;
+    const float dv = d[r];
+    float a[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) a[j] = (c + j < cols) ? dv * __ldg(k + c + j) : 0.f;
+    __nv_bfloat16* o = out + r * ldo + c;
+    if (c + 8 <= ldo && ((reinterpret_cast<uintptr_t>(o) & 15) == 0)) {
+      stg_u4(o, pack_bf16x8(a));
+    } else {
+      for (int j = 0; j < 8 && c + j < cols; ++j) o[j] = __float2bfloat16_rn(a[j]);
+    }
+  }
+}
 // y (fp32) += x (bf16)
 __global__ void __launch_bounds__(256) add_bf16_into_f32_kernel(const __nv_bfloat16* x, long long n2, float* y) {
   for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < n2; t += (long long)gridDim.x * blockDim.x) {
@@ -1346,6 +1366,16 @@ int etr_cross_mat_bwd_dx0_bf16(etr_ctx* ctx, int32_t layers, const void* const* 
   p.extra = (const __nv_bfloat16*)d_extra; p.ld_extra = ld_extra;
   p.layers = layers; p.rows = rows; p.cols = (int)cols; p.dx0 = d_dx0;
   tc::cross_bwd_dx0_kernel<<<grid_for(rows * (cols / 8), 256, ctx->sm_count, 8), 256, 0, (cudaStream_t)stream>>>(p);
+  ETR_LAUNCH_CHECK(ctx);
+  return ETR_OK;
+}
+
+int etr_outer_bf16(etr_ctx* ctx, const float* d_d, const float* d_k, int64_t rows, int64_t cols, void* d_out, int64_t ldo, void* stream) {
+  ETR_CHECK_ARG(ctx && d_d && d_k && d_out, "NULL argument");
+  ETR_CHECK_ARG(ldo >= cols, "ldo < cols");
+  if (rows <= 0 || cols <= 0) return ETR_OK;
+  tc::outer_bf16_kernel<<<grid_for(rows * ((cols + 7) / 8), 256, ctx->sm_count, 8), 256, 0, (cudaStream_t)stream>>>(
+      d_d, d_k, rows, (int)cols, (__nv_bfloat16*)d_out, ldo);
   ETR_LAUNCH_CHECK(ctx);
   return ETR_OK;
 }

@@ -247,7 +247,11 @@ class MLPLayer:
             if i > 0 or need_input_grad:
                 k = self.params.full(f"{self.name}/kernel_{i}")
                 acc = accumulate_into if (i == 0 and accumulate_into is not None) else None
-                if tc and acc is None:
+                if tc and acc is None and n_out == 1 and i == 0 and k.is_contiguous():
+                    # Dense(1): dx = dz k^T is a rank-1 product -- one elementwise pass instead of a K = 1 GEMM
+                    dx = rt.empty((B, n_in), torch.bfloat16)
+                    check(rt.lib.etr_outer_bf16(rt.ctx, d.data_ptr(), k.data_ptr(), B, n_in, dx.data_ptr(), n_in, rt.stream))
+                elif tc and acc is None:
                     # dx = d K^T : A = d (bf16) [B,out], B operand = K [in,out] as stored; bf16 result
                     db_ = cast_bf16(rt, d)
                     kb = cast_bf16(rt, k)

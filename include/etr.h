@@ -420,6 +420,9 @@ int etr_cross_mat_bwd_du_colsum_bf16(etr_ctx* ctx, const void* d_g, int64_t ldg,
                                      void* d_du, float* d_db, void* stream);
 int etr_cross_mat_bwd_dx0_bf16(etr_ctx* ctx, int32_t layers, const void* const* h_G, const int64_t* h_ldg, const void* const* h_u,
                                const void* d_extra, int64_t ld_extra, int64_t rows, int64_t cols, float* d_dx0, void* stream);
+/* out[b, n] = bf16(d[b] * k[n]) on [rows, cols] (row pitch ldo): dL/dx of a Dense(1) layer, e.g. the DCN output layer
+ * (3.DCN/CustomLayers.py:263-264) -- dz K^T is a rank-1 product, written at HBM speed instead of through a K = 1 GEMM.   */
+int etr_outer_bf16(etr_ctx* ctx, const float* d_d, const float* d_k, int64_t rows, int64_t cols, void* d_out, int64_t ldo, void* stream);
 int etr_add_bf16_into_f32(etr_ctx* ctx, const void* d_x, int64_t n, float* d_y, void* stream);
 int etr_colsum_bf16(etr_ctx* ctx, const void* d_X, int64_t M, int64_t N, int64_t ldx, float* d_out,
                     void* stream);

@@ -362,7 +362,8 @@ def test_train_steps_match_oracle_adam(L, mode, model):
 # --------------------------------------------------------------------- GEMM
 @pytest.mark.parametrize("M,N,K,ta,tb", [(513, 32, 429, 0, 0), (1000, 8, 32, 0, 0), (777, 1, 8, 0, 0),
                                            (429, 32, 20000, 1, 0), (300, 429, 32, 0, 1), (130, 70, 50, 1, 1),
-                                           (64, 1677, 1677, 0, 1)])
+                                           (64, 1677, 1677, 0, 1), (64, 8, 65536, 1, 0), (32, 8, 8192, 1, 0),
+                                           (56, 32, 5000, 1, 0)])
 def test_gemm_f32(L, M, N, K, ta, tb):
     from etr_b200 import Runtime
     from etr_b200.runtime import gemm_f32
