@@ -197,27 +197,37 @@ __global__ void __launch_bounds__(256, 2) mlp_skinny_bwd_kernel(const Params p) 
   if (tid < NOUT) out[(size_t)n_in * NOUT + tid] = db_acc;
 }
 
-// sum the per-CTA partials: a CTA owns 32 consecutive elements; its 8 warps each add a contiguous range
-// of the partials (coalesced 128-byte reads), the 8 sub-sums are combined in warp order (deterministic)
+// sum the per-CTA partials: a CTA owns 128 consecutive elements (one float4 per lane); its 8 warps each add a contiguous
+// range of the partials (512-byte coalesced reads, 8 independent loads in flight), the 8 sub-sums are combined in warp
+// order (deterministic; same per-element order as a scalar walk)
 __global__ void __launch_bounds__(256) mlp_skinny_bwd_finish_kernel(const float* part, int nparts, int n_elems, int n_k,
                                                                     float* dK, float* db) {
-  __shared__ float sm[8][32];
+  __shared__ float4 sm[8][32];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const int e = blockIdx.x * 32 + lane;
+  const int e = (blockIdx.x * 32 + lane) * 4;          // n_elems % 4 == 0 (n_in * 32 + 32)
   const int per = (nparts + 7) / 8;
   int c0 = warp * per, c1 = c0 + per;
   if (c1 > nparts) c1 = nparts;
-  float s = 0.f;
-  if (e < n_elems)
-    for (int c = c0; c < c1; ++c) s += part[(size_t)c * n_elems + e];
+  float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (e < n_elems) {
+#pragma unroll 8
+    for (int c = c0; c < c1; ++c) {
+      const float4 v = __ldg(reinterpret_cast<const float4*>(part + (size_t)c * n_elems + e));
+      s.x += v.x; s.y += v.y; s.z += v.z; s.w += v.w;
+    }
+  }
   sm[warp][lane] = s;
   __syncthreads();
   if (warp == 0 && e < n_elems) {
-    float t = 0.f;
+    float4 t = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
-    for (int w = 0; w < 8; ++w) t += sm[w][lane];
-    if (e < n_k) dK[e] = t;
-    else if (db) db[e - n_k] = t;
+    for (int w = 0; w < 8; ++w) { t.x += sm[w][lane].x; t.y += sm[w][lane].y; t.z += sm[w][lane].z; t.w += sm[w][lane].w; }
+    const float tv[4] = {t.x, t.y, t.z, t.w};
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      if (e + i < n_k) dK[e + i] = tv[i];
+      else if (db) db[e + i - n_k] = tv[i];
+    }
   }
 }
 
@@ -270,7 +280,7 @@ int etr_mlp_skinny_backward(etr_ctx* ctx, const void* d_X, int64_t ldx, const fl
   }
 #undef ETR_SK
   ETR_LAUNCH_CHECK(ctx);
-  sk::mlp_skinny_bwd_finish_kernel<<<(int)((n_elems + 31) / 32), 256, 0, s>>>(
+  sk::mlp_skinny_bwd_finish_kernel<<<(int)((n_elems + 127) / 128), 256, 0, s>>>(
       (const float*)ctx->d_ws, (int)grid, (int)n_elems, n_in * sk::NOUT, d_dK, d_db);
   ETR_LAUNCH_CHECK(ctx);
   return ETR_OK;
