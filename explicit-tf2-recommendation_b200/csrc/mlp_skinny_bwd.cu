@@ -49,10 +49,12 @@ struct Params {
 };
 
 // MT: feature m-tiles (16 rows of dK) owned per warp = ceil(n_in / 16 / 8)
-template <int MT>
+// NIN: n_in as a compile-time constant for the hot shape (0 = run-time): the index divisions of the staging loops and
+// the tile bounds fold away (15.1 M warp instructions per c2 launch with run-time n_in, issue-bound at 16 warps / SM)
+template <int MT, int NIN = 0>
 __global__ void __launch_bounds__(256, 2) mlp_skinny_bwd_kernel(const Params p) {
   extern __shared__ __align__(16) unsigned char smem[];
-  const int n_in = p.n_in;
+  const int n_in = NIN ? NIN : p.n_in;
   const int XS = n_in + 8;                                            // smem row stride of an X row (bf16)
   __nv_bfloat16* Xs = reinterpret_cast<__nv_bfloat16*>(smem);         // [SB][XS]
   __nv_bfloat16* Ds = Xs + SB * XS;                                    // [SB][DS]
@@ -272,6 +274,14 @@ int etr_mlp_skinny_backward(etr_ctx* ctx, const void* d_X, int64_t ldx, const fl
     }                                                                                                                 \
     sk::mlp_skinny_bwd_kernel<MT><<<(int)grid, 256, smem, s>>>(p);                                                   \
   } while (0)
+  if (n_in == 432) {                                  // DeepFM c2: 13 dense + 26 x 16 (+3 pad) inputs
+    static size_t configured432 = 0;
+    if (configured432 < smem) {
+      ETR_CUDA(cudaFuncSetAttribute(sk::mlp_skinny_bwd_kernel<4, 432>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      configured432 = smem;
+    }
+    sk::mlp_skinny_bwd_kernel<4, 432><<<(int)grid, 256, smem, s>>>(p);
+  } else
   switch (mt) {
     case 1: ETR_SK(1); break;
     case 2: ETR_SK(2); break;
