@@ -309,3 +309,120 @@ def test_shipped_checkpoint_weights_train_step(L):
         e_v = _rel(cpu(t.v[:, :k]).numpy(), v_ref.numpy())
         _report(f"ckpt_weights/{mode}", {"embed_abs_over_lr": e_var, "m": e_m, "v": e_v})
         assert e_var <= 6e-3 and e_m <= 1e-5 and e_v <= 1e-5, (mode, e_var, e_m, e_v)
+
+
+def _dcn_oracle_compact(lay, uniq, dtype=torch.float64):
+    """oracle twin of a DeepCrossNetworkLayer on the compact table of touched rows"""
+    from tests.util import leaf, oracle_mlp
+    o = R.DeepCrossNetworkLayer(lay.categorical_features, lay.continuous_features, len(uniq), lay.embedding_dims, lay.units,
+                                lay.dense_layer.activation, lay.cross_layer.layer_num, type=lay.type)
+    sel = torch.tensor(uniq).to(lay.rt.device)
+    o.embedding = cpu(lay.embeddings[sel], dtype).requires_grad_(True)
+    o.cross_layer.cross_weight = [leaf(w, dtype) for w in lay.cross_layer.cross_weight]
+    o.cross_layer.cross_bias = [leaf(b, dtype) for b in lay.cross_layer.cross_bias]
+    o.dense_layer, o.output_layer = oracle_mlp(lay.dense_layer, dtype), oracle_mlp(lay.output_layer, dtype)
+    return o
+
+
+@pytest.mark.parametrize("precision,tol,gtol", [("fp32", 1e-5, 1e-5), ("bf16", 1e-2, 1e-2)])
+def test_c3_shape_vs_oracle(L, precision, tol, gtol):
+    """BASELINE configs[2] at its real shape: DCN-matrix, 13 dense + 26 sparse, k = 64 -> D = 1677, 3 cross layers,
+    DenseLayer [64, 8], the 33 762 577-row table; batch 2 048 (what the fp64 oracle does in seconds) with the touched rows
+    remapped to a compact table.  fp32 path at 1e-5 (MatrixCrossLayer fp32 was only tested up to D = 163), bf16
+    tensor-core path (persistent CTA-pair GEMM, one-pass backward) at 1e-2 on bf16-representable operands (measured:
+    outputs 8e-4, gradients <= 5.5e-3; fp32 path: <= 1.8e-6)."""
+    rng = np.random.default_rng(31)
+    B, F, k, C = 2048, 26, 64, 13
+    V = int(sum(CRITEO_CARDS))
+    names, cont = [f"C{i}" for i in range(F)], [f"I{i}" for i in range(C)]
+    lay = L.DeepCrossNetworkLayer(names, cont, feature_dims=V, embedding_dims=k, units=[64, 8], layer_num=3, type="matrix",
+                                  precision=precision, seed=3)
+    X = zipf_ids(rng, CRITEO_CARDS, B)
+    Xc = rng.normal(size=(B, C)).astype(np.float32)
+    uniq, Xr = _compact(X)
+    if precision == "bf16":
+        sel = torch.tensor(uniq).to(lay.rt.device)
+        lay.table.data[sel] = lay.table.data[sel].to(torch.bfloat16).float()
+        lay.params.value.copy_(lay.params.value.to(torch.bfloat16).float())
+        Xc = torch.tensor(Xc).to(torch.bfloat16).float().numpy()
+    d = {n: torch.tensor(X[:, i]) for i, n in enumerate(names)}
+    d.update({n: torch.tensor(Xc[:, i]) for i, n in enumerate(cont)})
+    out = lay(d, training=True)["output"]
+    orc = _dcn_oracle_compact(lay, uniq)
+    o_in = {n: torch.tensor(Xr[:, i]) for i, n in enumerate(names)}
+    o_in.update({n: torch.tensor(Xc[:, i], dtype=torch.float64) for i, n in enumerate(cont)})
+    ref = orc.call(o_in)["output"]
+    errs = {"prob": _rel(cpu(out).numpy(), ref.detach().numpy())}
+    dz = rng.normal(size=(B,)).astype(np.float32)
+    grads = lay.backward(torch.tensor(dz).cuda())
+    p = ref.squeeze(1)
+    z = torch.log(p) - torch.log1p(-p)
+    (z * torch.tensor(dz, dtype=torch.float64)).sum().backward()
+    ids_g, rows_g = grads[0].indexed_slices()
+    assert np.array_equal(ids_g.cpu().numpy(), uniq)                       # routing: every touched row, ascending
+    errs["table_grad"] = _rel(cpu(rows_g)[:, :k].numpy(), orc.embedding.grad.numpy())
+    p0 = lay.front_pad
+    for i in range(3):
+        errs[f"cross_W{i}"] = _rel(cpu(lay.params.g("cross/W")[i][p0:, p0:]).numpy(), orc.cross_layer.cross_weight[i].grad.numpy())
+        errs[f"cross_b{i}"] = _rel(cpu(lay.params.g("cross/b")[i][p0:]).numpy().reshape(-1, 1), orc.cross_layer.cross_bias[i].grad.numpy())
+    errs["dense_k0"] = _rel(cpu(lay.params.g("dense_layer/kernel_0")).numpy(), orc.dense_layer.kernels[0].grad.numpy())
+    errs["dense_k1"] = _rel(cpu(lay.params.g("dense_layer/kernel_1")).numpy(), orc.dense_layer.kernels[1].grad.numpy())
+    errs["output_k0"] = _rel(cpu(lay.params.g("output_layer/kernel_0")).numpy(), orc.output_layer.kernels[0].grad.numpy())
+    _report(f"c3_shape/{precision}", errs)
+    assert errs["prob"] <= tol, errs
+    for key, e in errs.items():
+        assert e <= gtol, (precision, key, e, errs)
+    del lay, grads
+    torch.cuda.empty_cache()
+
+
+@pytest.mark.parametrize("model", ["ffm", "fwfm"])
+def test_c4_shape_vs_oracle(L, model):
+    """BASELINE configs[3] at its real shape: 39 fields x 100 000 ids, k = 8, padded bags of 1..50 ids (pad id 0), sum
+    pooling; batch 192 (the oracle materialises [B, F, L, F*k] in fp64) with the touched rows remapped to a compact
+    table: probabilities and the de-duplicated pair-table / linear gradients at 1e-5."""
+    from tests.util import leaf
+    rng = np.random.default_rng(41)
+    B, F, k, Lm, CARD = 192, 39, 8, 50, 100000
+    V = F * CARD
+    names = [f"S{i}" for i in range(F)]
+    cls = L.FwFMLayer if model == "fwfm" else L.FFMLayer
+    lay = cls(names, feature_dims=V, embedding_dims=k, pad_id=0, pooling="sum", seed=5)
+    lens = rng.integers(1, Lm + 1, size=(B, F))
+    r = np.floor(CARD * rng.random((B, F, Lm)) ** 3).astype(np.int64)
+    X = np.maximum(np.arange(F)[None, :, None] * CARD + np.minimum(r, CARD - 1), 1)
+    X[np.arange(Lm)[None, None, :] >= lens[:, :, None]] = 0
+    uniq, Xr = _compact(X)
+    assert uniq[0] == 0                                                    # the pad id keeps rank 0
+    out = lay(torch.tensor(X), training=True)["output"]
+    ocls = R.FwFMLayer if model == "fwfm" else R.FFMLayer
+    orc = ocls(names, len(uniq), k, pad_id=0, pooling="sum")
+    sel = torch.tensor(uniq).to(lay.rt.device)
+    orc.bias = leaf(lay.bias, torch.float64)
+    orc.w = cpu(lay.w[sel], torch.float64).requires_grad_(True)
+    orc.fa_interaction_layer.embedding_lookup_table = cpu(lay.fa_interaction_layer.embedding_lookup_table[sel],
+                                                          torch.float64).requires_grad_(True)
+    if model == "fwfm":
+        orc.r = leaf(lay.params["interaction_weights/kernel"], torch.float64)
+        orc.r0 = leaf(lay.params["interaction_weights/bias"], torch.float64)
+    z = orc.logit(torch.tensor(Xr))
+    errs = {"prob": _rel(cpu(out).numpy(), torch.sigmoid(z).detach().numpy())}
+    dz = rng.normal(size=(B,)).astype(np.float32)
+    grads = lay.backward(torch.tensor(dz).cuda())
+    (z.squeeze(1) * torch.tensor(dz, dtype=torch.float64)).sum().backward()
+    Tg = orc.fa_interaction_layer.embedding_lookup_table.grad.reshape(len(uniq), F * k)
+    full = torch.cat([Tg, orc.w.grad], dim=1).numpy()
+    ids_g, rows_g = grads[0].indexed_slices()
+    ids_g, rows_g = ids_g.cpu().numpy(), cpu(rows_g).numpy()[:, : F * k + 1]
+    pos = np.searchsorted(uniq, ids_g)
+    assert np.array_equal(uniq[pos], ids_g) and 0 not in ids_g             # only touched, non-pad rows carry a gradient
+    dense = np.zeros_like(full)
+    dense[pos] = rows_g
+    errs["table_grad"] = _rel(dense, full)
+    if model == "fwfm":
+        errs["r"] = _rel(cpu(lay.params.g("interaction_weights/kernel")).numpy().reshape(-1), orc.r.grad.numpy().reshape(-1))
+    _report(f"c4_shape/{model}", errs)
+    for key, e in errs.items():
+        assert e <= 1e-5, (model, key, e, errs)
+    del lay, grads
+    torch.cuda.empty_cache()

@@ -436,3 +436,20 @@ def test_cross_backward_one_pass_kernels(rt, B, D, slice_off):
     check(rt.lib.etr_cross_mat_bwd_dx0_bf16(rt.ctx, L_, gp, gl, up, ex.data_ptr(), D, B, D, dx1.data_ptr(), rt.stream))
     torch.cuda.synchronize()
     assert torch.equal(dx1, dx0 + ex.float())
+
+
+@pytest.mark.parametrize("B,n,ld", [(1000, 1688, 1688), (257, 13, 16), (64, 40, 40)])
+def test_outer_bf16(rt, B, n, ld):
+    """dL/dx of a Dense(1) layer as a rank-1 pass: out[b, j] = bf16(dz[b] * k[j]); padding columns untouched."""
+    from etr_b200._lib import check
+    g = torch.Generator(device=rt.device)
+    g.manual_seed(B + n)
+    dz = torch.randn(B, device=rt.device, generator=g)
+    k = torch.randn(n, device=rt.device, generator=g)
+    out = torch.full((B, ld), 7.0, dtype=torch.bfloat16, device=rt.device)
+    check(rt.lib.etr_outer_bf16(rt.ctx, dz.data_ptr(), k.data_ptr(), B, n, out.data_ptr(), ld, rt.stream))
+    torch.cuda.synchronize()
+    ref = (dz[:, None] * k[None, :]).to(torch.bfloat16)
+    assert torch.equal(out[:, :n], ref)
+    if ld > n:
+        assert torch.all(out[:, n:].float() == 0.0) or torch.all(out[:, n:] == 7.0)
