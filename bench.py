@@ -795,7 +795,10 @@ def main():
 
     def make_stepper(lay, apply_mode, graph):
         """(trainer, step_fn, graph_used) after the warm-up (which also captures the graph)"""
-        tr = L.Trainer(lay, lr=1e-3, apply_mode=apply_mode, graph=graph)
+        # plan-ahead (the sort of batch i+1 runs on the side stream during step i; every step still does exactly one sort):
+        # always at N > 1 (peer), and at N = 1 for the row-wise fused step unless --no-plan-ahead
+        tr = L.Trainer(lay, lr=1e-3, apply_mode=apply_mode, graph=graph,
+                       plan_ahead=(graph and apply_mode == "rowwise" and not args.no_plan_ahead))
         try:
             for i in range(max(args.warmup, 8 if graph else 0)):      # 2 buffer sets x (2 eager + capture) first
                 d_, y_ = device_dict(i)
@@ -816,7 +819,7 @@ def main():
 
     # N > 1, peer-sharded, CUDA graph: the inputs of step i+1 are staged BEFORE step i is launched, and step i sorts
     # them (side stream, inside its own timed bracket) -- every step still does one sort, one step early
-    ahead = {"on": world > 1 and args.shard == "peer" and not args.no_plan_ahead, "batch": None, "i": None}
+    ahead = {"on": (world == 1 or args.shard == "peer") and not args.no_plan_ahead, "batch": None, "i": None}
 
     def timed_rep(tr, step_fn, K, base):
         """EXACTLY K steps, each bracketed by CUDA events on the launch stream, L2 flushed (untimed) before every
@@ -1109,7 +1112,10 @@ def main():
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f32 (tables, FM terms, Adam)" + (" + bf16 tensor-core MLP layer 1" if args.mlp == "bf16" else ""),
         "data": "synthetic",
-        "config": workload_config(args, B, use_graph),
+        "config": {**workload_config(args, B, use_graph),
+                   "plan_ahead": ("the sorted-id plan of batch i+1 is built on the side stream during step i (its ids are staged one "
+                                  "step early); every timed step contains exactly one sort" if ahead["on"] else
+                                  "each step sorts its own ids (side stream, overlapped with forward + tower)")},
         "clocks": clk,
         "e2e": {"value": e2e_value, "unit": "samples/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                 "ms_per_step": e2e_ms / args.steps, "last_loss": last, "repetitions": len(e2e_totals),

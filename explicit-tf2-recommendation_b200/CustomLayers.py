@@ -421,8 +421,11 @@ class DeepFMRankingLayer(FMRankingLayer):
             plan = plan.join() if plan is not None else SparsePlan(rt, vids, tab.rows)
             gtab, gids, slot_of_u = self.peer.exchange_forward(plan, B, F)
         else:
-            plan = SparsePlan(rt, vids, tab.rows, overlap=True)    # sort || everything below
-            self._prepare_plan(plan, tab)
+            if plan is not None:
+                plan = plan.join()                                 # sorted (and prepared) during the previous step
+            else:
+                plan = SparsePlan(rt, vids, tab.rows, overlap=True)    # sort || everything below
+                self._prepare_plan(plan, tab)
             gtab, gids = tab, vids
         gather_fm_forward(gtab, k, True, gids, bias=self.bias, logit=fm_logit, sumv=sumv, flat=x, flat_col0=col0,
                           cont=cont)
@@ -1311,7 +1314,7 @@ class Trainer:
     the whole step; the optimizer clock lives on the device for that reason."""
 
     def __init__(self, layer, lr=1e-3, beta_1=0.9, beta_2=0.999, epsilon=1e-7, apply_mode="rowwise", graph=False,
-                 poll_every: int = 64):
+                 poll_every: int = 64, plan_ahead: Optional[bool] = None):
         """``poll_every``: every that many steps the device error word (out-of-range id, mailbox / touched-list
         overflow, peer-barrier timeout) is copied to pinned host memory WITHOUT stalling the loop and checked as soon
         as the copy has landed (at the latest ``poll_every`` steps later, and always in ``state_dict()``); 0 = never.
@@ -1335,7 +1338,12 @@ class Trainer:
             "the all-to-all sharded step syncs split sizes on the host: no CUDA graph (use shard='peer')"
         # static buffer sets: 2 = stage step i+1 while step i runs; 3 for the plan-ahead of peer-sharded layers (step i
         # already reads the ids of step i+1, so those are staged while step i-1 runs)
-        self.depth = (3 if self.peer is not None else 2) if graph else 1
+        # plan-ahead: ``train_step(batch, next_batch=staged)`` sorts the ids of the NEXT batch on the side stream while this
+        # step runs, so that no step waits for its own sort (always on for peer-sharded layers, where the unique ids are the
+        # first thing the exchange needs; opt-in for unsharded fused FM / DeepFM steps, where it takes the sort off the path
+        # in front of the fused backward + apply)
+        self.plan_ahead = (self.peer is not None) if plan_ahead is None else (bool(plan_ahead) or self.peer is not None)
+        self.depth = (3 if self.plan_ahead else 2) if graph else 1
         if self.peer is not None:
             self.peer.n_req_sets = max(self.peer.n_req_sets, self.depth)      # one request-mailbox set per buffer set
         self._graphs: Dict[tuple, list] = {}
@@ -1419,18 +1427,18 @@ class Trainer:
         y = rt.to_device(labels, torch.float32).reshape(-1)
         # plan-ahead (peer-sharded): this batch's plan was sorted during the previous step; the next batch's starts now
         pre, nsl = None, getattr(next_batch, "_slot", None)
-        if self.peer is not None and sl is not None and sl.plan_ready:
+        if self.plan_ahead and sl is not None and sl.plan_ready:
             pre, sl.plan_ready = sl.plan, False
-        if self.peer is not None and nsl is not None and nsl is not sl:
+        if self.plan_ahead and nsl is not None and nsl is not sl:
             rows = self.layer.sparse_tables()[0].rows
             if nsl.plan is None:
                 assert not torch.cuda.is_current_stream_capturing()
                 nsl.plan = SparsePlan(rt, nsl.batch.ids, rows, overlap=True)
                 if getattr(self.layer, "embedding_dims", 0) == 16 and FusedFMGrad.apply_kernel == "tile":
-                    nsl.plan.prepare_fm()             # row descriptors / long-run items of the tiled push kernel
+                    nsl.plan.prepare_fm()             # row descriptors / long-run items of the tiled kernel
             else:
                 nsl.plan.rebuild(nsl.batch.ids, rows)
-            if getattr(self.layer, "shard_mode", None) == "peer":
+            if self.peer is not None and getattr(self.layer, "shard_mode", None) == "peer":
                 # ... and its requests go to the owners' mailbox set of that buffer set (the barrier that closes this
                 # step orders them before the next step's serve)
                 with torch.cuda.stream(rt.side_stream):
@@ -1458,7 +1466,7 @@ class Trainer:
             import torch.distributed as dist
             dist.all_reduce(self.layer.params.grad)   # replicated dense variables: sum of the ranks' grads
         self.apply_gradients(grads)
-        if self.peer is not None and nsl is not None and nsl is not sl:
+        if self.plan_ahead and nsl is not None and nsl is not sl:
             nsl.plan.join()                           # the look-ahead sort + requests belong to THIS step (timed with it)
             nsl.plan._pending = None
             nsl.plan_ready = True
@@ -1609,14 +1617,14 @@ class Trainer:
         assert sl is not None, "graph mode needs the static DeviceBatch returned by stage()"
         cur = torch.cuda.current_stream(self.rt.device)
         cur.wait_event(sl.copy_done)
-        nsl = getattr(next_batch, "_slot", None) if self.peer is not None else None
+        nsl = getattr(next_batch, "_slot", None) if self.plan_ahead else None
         if nsl is sl:
             nsl = next_batch = None
         if nsl is not None:
             cur.wait_event(nsl.copy_done)     # its ids are sorted inside this step
         else:
             next_batch = None
-        key = (self.peer is not None and sl.plan_ready, nsl is not None)
+        key = (self.plan_ahead and sl.plan_ready, nsl is not None)
         if key not in sl.graphs and sl.eager.get(key, 0) < 2:
             sl.eager[key] = sl.eager.get(key, 0) + 1
             loss = self._eager_step(batch, None, next_batch)
@@ -1637,7 +1645,7 @@ class Trainer:
                     nsl.plan_ready = ready[1]
                 cur = torch.cuda.current_stream(self.rt.device)
             sl.graphs[key].replay()
-            if self.peer is not None:         # what the replayed step did to the plan flags
+            if self.plan_ahead:               # what the replayed step did to the plan flags
                 sl.plan_ready = False
                 if nsl is not None:
                     nsl.plan_ready = True

@@ -458,3 +458,35 @@ def test_trainer_checkpoint_resume_is_bit_exact(L, graph, tmp_path):
     torch.cuda.synchronize()
     assert torch.equal(lay2.table.data, lay.table.data) and torch.equal(lay2.params.value, lay.params.value)
     assert torch.equal(lay2.table.m, lay.table.m) and torch.equal(lay2.params.v, lay.params.v)
+
+
+def test_plan_ahead_unsharded_is_bit_exact(L):
+    """Trainer(plan_ahead=True): the sorted-id plan of batch i+1 is built on the side stream during step i
+    (train_step(batch, next_batch=staged), CUDA graph, 3 buffer sets).  Same kernels on the same plans: weights, Adam slots
+    and losses equal those of the plain graph trainer bit for bit, over enough steps to replay every captured variant."""
+    F, k, V, C_, B = 26, 16, 20011, 13, 1024
+    names, cont = _names(F), [f"c{i}" for i in range(C_)]
+    rng = np.random.default_rng(11)
+
+    def batch():
+        d = {n: torch.tensor(rng.integers(0, V, size=B)) for n in names}
+        d.update({n: torch.tensor(rng.normal(size=B).astype(np.float32)) for n in cont})
+        return d, torch.tensor((rng.random(B) < 0.3).astype(np.float32))
+
+    data = [batch() for _ in range(16)]
+    mk = lambda: L.DeepFMRankingLayer(names, V, k, continuous_features=cont, seed=5, mlp_precision="bf16")   # noqa: E731
+    lay_a, lay_b = mk(), mk()
+    tr_a = L.Trainer(lay_a, lr=1e-2, graph=True)
+    tr_b = L.Trainer(lay_b, lr=1e-2, graph=True, plan_ahead=True)
+    assert tr_b.plan_ahead and tr_b.depth == 3 and not tr_a.plan_ahead
+    ref = [float(tr_a.train_step(d, y).item()) for d, y in data]
+    got = []
+    cur = tr_b.stage(*data[0])
+    for i in range(len(data)):
+        nxt = tr_b.stage(*data[i + 1]) if i + 1 < len(data) else None
+        got.append(float(tr_b.train_step(cur, None, nxt).item()))
+        cur = nxt
+    torch.cuda.synchronize()
+    assert got == ref
+    assert torch.equal(lay_b.table.data, lay_a.table.data) and torch.equal(lay_b.params.value, lay_a.params.value)
+    assert torch.equal(lay_b.table.m, lay_a.table.m) and torch.equal(lay_b.table.v, lay_a.table.v)
