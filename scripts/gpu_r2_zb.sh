@@ -1,6 +1,6 @@
 #!/bin/bash
 mkdir -p gpurun_out
-timeout 600 python -m pytest tests -m gpu -q --timeout 300 -x -k "plan_ahead or graph_trainer or checkpoint_resume" > gpurun_out/pytest_gpu.log 2>&1; echo "pytest all exit $?"
+timeout 600 python -m pytest tests -m gpu -q --timeout 300 -x > gpurun_out/pytest_gpu.log 2>&1; echo "pytest all exit $?"
 tail -2 gpurun_out/pytest_gpu.log
 for v in ""; do
 timeout 600 python bench.py --no-cpu-baseline --no-extras $v > gpurun_out/bench_c2_pa.json 2> gpurun_out/bench_c2_pa.err; echo "bench c2 [$v] exit $?"
