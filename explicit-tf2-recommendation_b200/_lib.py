@@ -128,6 +128,9 @@ PROTOTYPES = {
     "etr_shard_vid_map": (C.c_int, [_vp, _vp, _vp, _vp, _i64, _vp, _vp, _vp]),
     "etr_shard_mailbox_accumulate": (C.c_int, [_vp, _vp, _vp, _vp, _i32, _i32, _i32, _vp, _vp, _vp, _vp, _i32, _vp]),
     "etr_shard_touched_adam": (C.c_int, [_vp, _T, _vp, _vp, _vp, _i32, _vp, _vp, _i32, _i32, _vp, _f32, _f32, _f32, _vp]),
+    "etr_shard_owner_prep": (C.c_int, [_vp, _vp, _vp, _i32, _i32, _i64, _vp, _vp, _vp, _vp, _vp]),
+    "etr_shard_owner_apply": (C.c_int, [_vp, _T, _vp, _vp, _vp, _vp, _vp, _i32, _i32, _i32, _vp, _vp, _i32, _vp, _f32, _f32,
+                                        _f32, _vp]),
     "etr_peer_barrier": (C.c_int, [_vp, C.POINTER(_vp), _vp, _vp, _i32, _i32, _vp]),
     "etr_peer_allreduce_push": (C.c_int, [_vp, _vp, _i64, C.POINTER(_vp), _i32, _i32, _vp]),
     "etr_peer_allreduce_sum": (C.c_int, [_vp, _vp, _i64, _i32, _vp, _vp]),

@@ -440,7 +440,10 @@ static int fused_impl(etr_ctx* ctx, const etr_table* table, float* d_m, float* d
   p.dlogit = d_dlogit; p.sumv = d_sumv; p.dflat = d_dflat; p.flat_bf16 = flat_dtype == ETR_BF16; p.flat_ld = flat_ld;
   p.flat_col0 = flat_col0; p.lr_t = lr_t; p.d_lr_t = d_lr_t; p.b1 = beta1; p.b2 = beta2; p.eps = eps; p.apply = apply;
   p.unique_grad = d_unique_grad;
-  p.gld = table->reserved == ETR_TABLE_RECORD ? ETR_RECORD_ROW_FLOATS : table->stride;
+  // gradient rows are densely packed (20 floats) whenever the table rows are 256-byte records -- a local record
+  // table, or a peer-sharded one whose shards hold records (stride 64)
+  p.gld = (table->reserved == ETR_TABLE_RECORD || (table->reserved > 0 && table->stride == 64 && table->width <= 20))
+              ? ETR_RECORD_ROW_FLOATS : table->stride;
   p.slot_of_u = d_slot_of_u; p.cap = cap;
   p.world = 1;
   if (table->reserved > 0) {

@@ -335,6 +335,126 @@ __global__ void __launch_bounds__(256) touched_adam_kernel(const TouchedAdamPara
     *pvar = var; *pm = m; *pv = v;
   }
 }
+// ---- owner side, round 2: who-contributes-to-which-row is known from the REQUESTS (the gradient rows return
+// through the request slots), so it is worked out off the critical path while the forward runs:
+//   owner_prep  : every request entry e = src * cap + s claims its row in a dense map (64-bit CAS of
+//                 (step << 32) | e); the winner is the row's LEADER (bit 31 of mask[e]); the others record their
+//                 slot at the leader (others[leader][src]) and OR their source bit into mask[leader];
+//   owner_apply : after the gradient barrier, ONE pass over the entries: a leader adds its own mailbox row and
+//                 the recorded ones in ascending source order (the same order as the region-by-region
+//                 accumulation: bit-identical), finishes the deferred FM gradient and runs Adam on the row --
+//                 no dense accumulator, no touched list, one read + one write of the row's state.  The pass
+//                 clears mask[e] behind itself, so prep needs no memset.
+struct OwnerPrepParams {
+  const long long* req; const int* counts;       // [world][cap], [world]
+  int world, cap; long long rows;
+  unsigned long long* map;                       // [local rows]
+  unsigned* step;                                // bumped by owner_step_kernel before the prep launch
+  unsigned* mask; int* others;                   // [world * cap], [world * cap][world]
+  unsigned long long* err;
+};
+__global__ void owner_step_kernel(unsigned* step) { *step += 1u; }
+__global__ void __launch_bounds__(256) owner_prep_kernel(const OwnerPrepParams p) {
+  const int src = blockIdx.y;
+  int n = p.counts[src];
+  if (n > p.cap) n = p.cap;
+  const unsigned long long ep = (unsigned long long)(*p.step) << 32;
+  for (int s = blockIdx.x * 256 + threadIdx.x; s < n; s += gridDim.x * 256) {
+    const unsigned e = (unsigned)src * (unsigned)p.cap + (unsigned)s;
+    const long long row = p.req[e];
+    if ((unsigned long long)row >= (unsigned long long)p.rows) continue;       // the serve kernel has flagged it
+    unsigned long long* slot = p.map + row;
+    unsigned long long cur = *reinterpret_cast<volatile unsigned long long*>(slot);
+    unsigned leader = e;
+    for (;;) {
+      if ((cur >> 32 << 32) == ep) { leader = (unsigned)cur; break; }
+      const unsigned long long old = atomicCAS(slot, cur, ep | e);
+      if (old == cur) break;
+      cur = old;
+    }
+    if (leader == e) {
+      atomicOr(p.mask + e, 0x80000000u | (1u << src));
+    } else {
+      p.others[(long long)leader * p.world + src] = s;
+      atomicOr(p.mask + leader, 1u << src);
+    }
+  }
+}
+
+struct OwnerApplyParams {
+  const long long* req; const int* counts; const float* grads;
+  int world, cap, ld;
+  unsigned* mask; const int* others;
+  float* table; float* m; float* v; int stride; long long rows;
+  int fm_k; const float* d_lr_t; float b1, b2, eps;
+};
+template <int LPR>
+__global__ void __launch_bounds__(256) owner_apply_kernel(const OwnerApplyParams p) {
+  constexpr int GPW = 32 / LPR;
+  const int src = blockIdx.y;
+  const int lane = threadIdx.x & 31;
+  const int gl = lane % LPR, g = lane / LPR;
+  const int nch = p.ld / 4;
+  const unsigned gmask = (LPR == 32) ? 0xffffffffu : (((1u << LPR) - 1u) << (g * LPR));
+  int n = p.counts[src];
+  if (n > p.cap) n = p.cap;
+  const float lr_t = *p.d_lr_t;
+  const bool mine = gl < nch;
+  const int sg_lane = g * LPR + p.fm_k / 4;
+  // trip count uniform per lane group (the shuffles are group-wide)
+  for (int s = (blockIdx.x * 8 + (threadIdx.x >> 5)) * GPW + g; s < n; s += gridDim.x * 8 * GPW) {
+    const long long e = (long long)src * p.cap + s;
+    const unsigned mk = p.mask[e];
+    const long long row = p.req[e];
+    __syncwarp(gmask);
+    if (mk == 0u) continue;                                 // out-of-range row (never claimed)
+    if (gl == 0) p.mask[e] = 0u;                            // self-cleaning
+    if (!(mk & 0x80000000u)) continue;                      // a leader elsewhere sums this row
+    float4 var = make_float4(0.f, 0.f, 0.f, 0.f), mm = var, vv = var, acc = var;
+    float* prow = p.table + row * p.stride + gl * 4;
+    float* pm = p.m + row * p.stride + gl * 4;
+    float* pv = p.v + row * p.stride + gl * 4;
+    if (mine) {
+      var = *reinterpret_cast<const float4*>(prow);
+      mm = *reinterpret_cast<const float4*>(pm);
+      vv = *reinterpret_cast<const float4*>(pv);
+    }
+    unsigned srcs = mk & 0xffffu;
+    if (srcs == (1u << src)) {                              // the common case: one contributor
+      if (mine) acc = __ldcs(reinterpret_cast<const float4*>(p.grads + e * p.ld + gl * 4));
+    } else {
+      bool first = true;
+      while (srcs) {
+        const int q = __ffs(srcs) - 1;
+        srcs &= srcs - 1;
+        const long long eq = (q == src) ? e : (long long)q * p.cap + p.others[e * p.world + q];
+        if (mine) {
+          const float4 x = __ldcs(reinterpret_cast<const float4*>(p.grads + eq * p.ld + gl * 4));
+          if (first) acc = x;
+          else { acc.x += x.x; acc.y += x.y; acc.z += x.z; acc.w += x.w; }
+        }
+        first = false;
+      }
+    }
+    if (p.fm_k > 0) {
+      const float sg = __shfl_sync(gmask, acc.x, sg_lane);
+      if (gl * 4 < p.fm_k) { acc.x -= var.x * sg; acc.y -= var.y * sg; acc.z -= var.z * sg; acc.w -= var.w * sg; }
+    }
+    if (mine) {
+      float* xv = &var.x; float* xm = &mm.x; float* xvv = &vv.x; const float* xg = &acc.x;
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        xm[q] = p.b1 * xm[q] + (1.0f - p.b1) * xg[q];
+        xvv[q] = p.b2 * xvv[q] + (1.0f - p.b2) * xg[q] * xg[q];
+        xv[q] = xv[q] - lr_t * xm[q] / (sqrtf(xvv[q]) + p.eps);
+      }
+      *reinterpret_cast<float4*>(prow) = var;
+      *reinterpret_cast<float4*>(pm) = mm;
+      *reinterpret_cast<float4*>(pv) = vv;
+    }
+  }
+}
+
 // ---- cross-rank barrier over peer memory: rank r stores the new epoch into flags[r] of every
 // peer (release, system scope) and waits until every peer's epoch has arrived in its own flags.
 // One warp; bounded spin (a missing peer flags error -3 instead of hanging the GPU).
@@ -576,6 +696,53 @@ int etr_shard_touched_adam(etr_ctx* ctx, const etr_table* table, float* d_m, flo
   p.b1 = beta1; p.b2 = beta2; p.eps = eps;
   const int grid = grid_for((long long)max_touched * (ld / 4), 256, ctx->sm_count, 8);
   touched_adam_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(p);
+  ETR_LAUNCH_CHECK(ctx);
+  return ETR_OK;
+}
+
+int etr_shard_owner_prep(etr_ctx* ctx, const int64_t* d_req, const int32_t* d_counts, int32_t world, int32_t cap,
+                         int64_t local_rows, uint64_t* d_map, uint32_t* d_step, uint32_t* d_mask, int32_t* d_others,
+                         void* stream) {
+  ETR_CHECK_ARG(ctx && d_req && d_counts && d_map && d_step && d_mask && d_others, "NULL argument");
+  ETR_CHECK_ARG(world >= 1 && world <= 16 && cap > 0 && local_rows > 0 && (long long)world * cap < 0x7fffffffLL,
+                "bad world / cap / rows");
+  OwnerPrepParams p;
+  p.req = (const long long*)d_req; p.counts = d_counts; p.world = world; p.cap = cap; p.rows = local_rows;
+  p.map = (unsigned long long*)d_map; p.step = d_step; p.mask = d_mask; p.others = d_others; p.err = ctx->d_err;
+  cudaStream_t s = (cudaStream_t)stream;
+  owner_step_kernel<<<1, 1, 0, s>>>(d_step);
+  ETR_LAUNCH_CHECK(ctx);
+  dim3 grid((unsigned)grid_for(cap, 256, ctx->sm_count, 8 / (world < 8 ? world : 8) + 1), (unsigned)world);
+  owner_prep_kernel<<<grid, 256, 0, s>>>(p);
+  ETR_LAUNCH_CHECK(ctx);
+  return ETR_OK;
+}
+
+int etr_shard_owner_apply(etr_ctx* ctx, const etr_table* table, float* d_m, float* d_v, const int64_t* d_req,
+                          const int32_t* d_counts, const float* d_grads, int32_t world, int32_t cap, int32_t ld,
+                          uint32_t* d_mask, const int32_t* d_others, int32_t fm_k, const float* d_lr_t, float beta1,
+                          float beta2, float eps, void* stream) {
+  ETR_CHECK_ARG(ctx && table && table->d_data && d_m && d_v && d_req && d_counts && d_grads && d_mask && d_others && d_lr_t,
+                "NULL argument");
+  ETR_CHECK_ARG(table->dtype == ETR_F32 && world >= 1 && world <= 16 && cap > 0 && ld % 4 == 0 && ld <= table->stride &&
+                    ld / 4 <= 32, "fp32 table, ld <= stride");
+  ETR_CHECK_ARG(fm_k == 0 || (fm_k % 4 == 0 && fm_k + 4 <= ld), "fm_k must be a multiple of 4 with a chunk behind it");
+  OwnerApplyParams p;
+  p.req = (const long long*)d_req; p.counts = d_counts; p.grads = d_grads; p.world = world; p.cap = cap; p.ld = ld;
+  p.mask = d_mask; p.others = d_others; p.table = (float*)table->d_data; p.m = d_m; p.v = d_v; p.stride = table->stride;
+  p.rows = table->rows; p.fm_k = fm_k; p.d_lr_t = d_lr_t; p.b1 = beta1; p.b2 = beta2; p.eps = eps;
+  int lpr = 1;
+  while (lpr < ld / 4) lpr <<= 1;
+  dim3 grid((unsigned)grid_for(cap, 8 * (32 / lpr), ctx->sm_count, 16 / (world < 8 ? world : 8) + 1), (unsigned)world);
+  cudaStream_t s = (cudaStream_t)stream;
+  switch (lpr) {
+    case 1: owner_apply_kernel<1><<<grid, 256, 0, s>>>(p); break;
+    case 2: owner_apply_kernel<2><<<grid, 256, 0, s>>>(p); break;
+    case 4: owner_apply_kernel<4><<<grid, 256, 0, s>>>(p); break;
+    case 8: owner_apply_kernel<8><<<grid, 256, 0, s>>>(p); break;
+    case 16: owner_apply_kernel<16><<<grid, 256, 0, s>>>(p); break;
+    default: owner_apply_kernel<32><<<grid, 256, 0, s>>>(p); break;
+  }
   ETR_LAUNCH_CHECK(ctx);
   return ETR_OK;
 }

@@ -137,7 +137,8 @@ class EmbeddingTable:
     is fused in as column ``k`` (one DRAM burst serves v and w)."""
 
     def __init__(self, rt: Runtime, rows: int, width: int, dtype: torch.dtype = torch.float32,
-                 data: Optional[torch.Tensor] = None, row_align: int = 16, record: bool = False):
+                 data: Optional[torch.Tensor] = None, row_align: int = 16, record: bool = False,
+                 rec: Optional[torch.Tensor] = None):
         """``row_align`` (bytes, a multiple of 16): rows start on that boundary.
 
         ``record=True`` (fp32, width <= 20): the row and its two Adam slots are interleaved in ONE
@@ -158,7 +159,9 @@ class EmbeddingTable:
             assert dtype == torch.float32 and data is None and self.row_width <= 20
             self.row_width = 20
             self.stride = 64
-            self.rec = rt.zeros((self.rows, 64), torch.float32)
+            if rec is not None:       # caller-owned record storage (a peer-mapped shard), already zeroed
+                assert rec.shape == (self.rows, 64) and rec.dtype == torch.float32 and rec.is_contiguous()
+            self.rec = rt.zeros((self.rows, 64), torch.float32) if rec is None else rec
             assert self.rec.data_ptr() % 256 == 0
             self.data = self.rec[:, 0:20]
             self._m, self._v = self.rec[:, 20:40], self.rec[:, 40:60]

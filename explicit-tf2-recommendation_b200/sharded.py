@@ -19,6 +19,7 @@ very same protocol over gloo without a GPU).
 from __future__ import annotations
 
 import ctypes as C
+import os
 from typing import List, Optional
 
 import torch
@@ -228,18 +229,29 @@ class PeerShardedTable:
               its own shard; a second barrier closes the step.
     Nothing is read back to the host, so the whole data-parallel step is one CUDA graph."""
 
-    def __init__(self, rt, rows_global: int, width: int, world: int, rank: int, group=None):
+    def __init__(self, rt, rows_global: int, width: int, world: int, rank: int, group=None, record: Optional[bool] = None):
+        """``record`` (default: whenever a row is 17..20 floats, the FM table of k = 16): the shard holds 256-byte records [var | m | v | pad] like the
+        unsharded FM table (runtime.EmbeddingTable record=True), so the owner's apply moves a row's whole state as two
+        full lines; mailbox / response rows stay densely packed (``ld`` floats)."""
         from .runtime import EmbeddingTable
         assert world & (world - 1) == 0, "peer-sharded tables need a power-of-two number of ranks"
         self.rt, self.world, self.rank, self.group = rt, world, rank, group
         self.rows, self.width, self.dtype = int(rows_global), int(width), torch.float32
-        self.stride = (self.width + 3) // 4 * 4
+        self.ld = (self.width + 3) // 4 * 4                             # mailbox / response / gradient row
+        self.record = (self.ld == 20 and os.environ.get("ETR_PEER_RECORD", "1") != "0") if record is None else bool(record)
+        self.stride = 64 if self.record else self.ld
+        if self.record:
+            self.ld = 20
         self.local_rows_max = (self.rows + world - 1) // world          # same allocation on every rank
         self.local_rows = (self.rows - rank + world - 1) // world
         self._shard = PeerBuffer(rt, max(self.local_rows_max, 1) * self.stride * 4, world, rank, group)
         data = self._shard.tensor((max(self.local_rows_max, 1), self.stride), torch.float32)
-        self.local = EmbeddingTable(rt, max(self.local_rows, 1), self.width, torch.float32,
-                                    data=data[: max(self.local_rows, 1)])
+        if self.record:
+            self.local = EmbeddingTable(rt, max(self.local_rows, 1), self.width, torch.float32, record=True,
+                                        rec=data[: max(self.local_rows, 1)])
+        else:
+            self.local = EmbeddingTable(rt, max(self.local_rows, 1), self.width, torch.float32,
+                                        data=data[: max(self.local_rows, 1)])
         sid = C.c_int32(0)
         check(rt.lib.etr_shard_set_create(rt.ctx, self._shard.peer_array(), world, rank, self.rows, C.byref(sid)))
         self.shard_set = int(sid.value)
@@ -250,6 +262,10 @@ class PeerShardedTable:
         self._ar = None
         self._mb = None
         self._gacc = None
+        self._own = None                                  # owner-side prep state (map, step, mask, others)
+        self._prep_stream = None
+        self._prep_done = None                            # event of the prep that the next apply_mailbox consumes
+        self.owner_prep = os.environ.get("ETR_PEER_OWNER_PREP", "1") != "0"
         self.cap = 0
         # request mailboxes (ids + counts) come in ``n_req_sets`` sets: set 0 serves requests made inside the step, the
         # Trainer's plan-ahead sends the requests of the batch staged in buffer set s into set s one step early
@@ -272,7 +288,7 @@ class PeerShardedTable:
 
     @property
     def grad_ld(self) -> int:
-        return self.stride
+        return self.ld
 
     def desc(self) -> _lib.etr_table:
         return _lib.etr_table(self._shard.ptr, self.rows, self.width, self.stride, _lib.ETR_F32, self.shard_set)
@@ -326,7 +342,7 @@ class PeerShardedTable:
         cap = max(cap, self.cap)
         assert not torch.cuda.is_current_stream_capturing(), "size the mailbox with an eager step before capture"
         torch.cuda.synchronize(self.rt.device)
-        W, ld, rt, S = self.world, self.stride, self.rt, self.n_req_sets
+        W, ld, rt, S = self.world, self.ld, self.rt, self.n_req_sets
         ids = PeerBuffer(rt, S * W * cap * 8, W, self.rank, self.group)
         grads = PeerBuffer(rt, W * cap * ld * 4, W, self.rank, self.group)
         counts = PeerBuffer(rt, S * 64 * 4, W, self.rank, self.group)
@@ -342,6 +358,7 @@ class PeerShardedTable:
             "touched": rt.empty((W * cap,), torch.int32), "n_touched": rt.zeros((1,), torch.int32),
         }
         self._mb_sets = S
+        self._own, self._prep_done = None, None           # sized by cap: rebuilt on the next prep
         # response buffer of the de-duplicated forward exchange: [owner][cap][ld] on THIS rank; owner g writes its
         # region through the pointer resp_ptrs[source] = source's buffer + g * cap * ld * 4
         resp = PeerBuffer(rt, W * cap * ld * 4, W, self.rank, self.group)
@@ -389,13 +406,38 @@ class PeerShardedTable:
             self.barrier()
         q, plan.req_set = plan.req_set, None
         self._cur_set = q
-        mb, cap, ld = self._mb, self.cap, self.stride
+        mb, cap, ld = self._mb, self.cap, self.ld
+        if self.owner_prep:
+            self._launch_owner_prep(q)
         t = self.local.desc()
         check(rt.lib.etr_shard_serve(rt.ctx, C.byref(t), mb["ids_t"][q].data_ptr(), mb["counts_t"][q].data_ptr(), W, cap,
                                      mb["resp_ptrs"], ld, rt.stream))
         self.barrier()
         vt = VirtualTable(rt, mb["resp_t"], self.width)
         return vt, IdsBatch(rt, plan.vid, B, F, 1, F, 1, 1), plan.slot_of_u
+
+    def _launch_owner_prep(self, q: int):
+        """The requests of set ``q`` have arrived (a barrier has ordered them): on a side stream, while the forward
+        runs, every entry claims its row (etr_shard_owner_prep) so that the apply after the gradient barrier is one pass."""
+        rt, mb, W, cap = self.rt, self._mb, self.world, self.cap
+        if self._own is None:
+            assert not torch.cuda.is_current_stream_capturing(), "run one eager step before capture (owner-prep buffers)"
+            self._own = {"map": rt.zeros((max(self.local_rows, 1),), torch.int64), "step": rt.zeros((1,), torch.int32),
+                         "mask": rt.zeros((W * cap,), torch.int32), "others": rt.empty((W * cap, W), torch.int32)}
+        own = self._own
+        if self._prep_stream is None:
+            self._prep_stream = torch.cuda.Stream(device=rt.device)
+        cur = torch.cuda.current_stream(rt.device)
+        if self._prep_done is not None:                   # a prep that no apply consumed: its claims are stale
+            cur.wait_event(self._prep_done)
+            own["mask"].zero_()
+        ps = self._prep_stream
+        ps.wait_stream(cur)                               # after the previous apply (mask / map free) and the requests' barrier
+        check(rt.lib.etr_shard_owner_prep(rt.ctx, mb["ids_t"][q].data_ptr(), mb["counts_t"][q].data_ptr(), W, cap,
+                                          max(self.local_rows, 1), own["map"].data_ptr(), own["step"].data_ptr(),
+                                          own["mask"].data_ptr(), own["others"].data_ptr(), ps.cuda_stream))
+        self._prep_done = torch.cuda.Event()
+        self._prep_done.record(ps)
 
     def apply_mailbox(self, d_lr_t: torch.Tensor, b1: float, b2: float, eps: float, mode: int):
         """owner side, no sort: the G source regions are added into the dense accumulator in rank order
@@ -404,7 +446,18 @@ class PeerShardedTable:
         if mode != _lib.ADAM_ROWWISE:
             raise NotImplementedError("peer-sharded tables: row-wise Adam only (keras_dense decays every row of "
                                       "every shard each step; use the all-to-all form for that parity mode)")
-        rt, mb, W, cap, ld = self.rt, self._mb, self.world, self.cap, self.stride
+        rt, mb, W, cap, ld = self.rt, self._mb, self.world, self.cap, self.ld
+        if self._prep_done is not None:
+            # the rows came back through the request slots and the prep pass has paired them up: one pass
+            torch.cuda.current_stream(rt.device).wait_event(self._prep_done)
+            self._prep_done = None
+            q, own, t = self._cur_set, self._own, self.local.desc()
+            check(rt.lib.etr_shard_owner_apply(rt.ctx, C.byref(t), self.local.m.data_ptr(), self.local.v.data_ptr(),
+                                               mb["ids_t"][q].data_ptr(), mb["counts_t"][q].data_ptr(),
+                                               mb["grads_t"].data_ptr(), W, cap, ld, own["mask"].data_ptr(),
+                                               own["others"].data_ptr(), self.width - 1, d_lr_t.data_ptr(), b1, b2, eps,
+                                               rt.stream))
+            return
         if self._gacc is None:
             assert not torch.cuda.is_current_stream_capturing()
             assert ld >= self.width + 1, "the accumulator row needs a spare last column for its stamp"

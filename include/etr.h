@@ -540,6 +540,25 @@ int etr_shard_mailbox_accumulate(etr_ctx* ctx, const int64_t* d_ids, const float
 int etr_shard_touched_adam(etr_ctx* ctx, const etr_table* table, float* d_m, float* d_v, float* d_gacc, int32_t ld,
                            const int32_t* d_touched, const int32_t* d_n_touched, int32_t max_touched, int32_t fm_k,
                            const float* d_lr_t, float beta1, float beta2, float eps, void* stream);
+/* Owner side of the peer-sharded apply when the gradient rows return through the REQUEST slots
+ * (etr_shard_request / etr_fm_fused_backward_push): which entries meet on which row is known from the
+ * requests alone, so etr_shard_owner_prep works it out off the critical path (a side stream, while the
+ * forward runs): every entry e = source * cap + slot claims its local row in d_map[local_rows] with a
+ * 64-bit CAS of (step << 32 | e) (*d_step is bumped by the call); the winner becomes the row's leader
+ * (bit 31 of d_mask[e]), the others record their slot in d_others[leader * world + source] and OR their
+ * source bit into d_mask[leader].  d_mask [world * cap] must be zero on the first call; the apply pass
+ * clears what it reads.  etr_shard_owner_apply is then ONE pass after the gradient barrier: each leader
+ * sums its row's mailbox rows in ascending source order (the order of the region-by-region
+ * accumulation above: bit-identical), finishes the deferred FM gradient (fm_k > 0) and runs row-wise
+ * Adam on the row -- no dense accumulator, no touched list.  Replaces Unique + UnsortedSegmentSum +
+ * Adam._resource_apply_sparse of 2.FM/ModelManager.py:178 on the shard.                            */
+int etr_shard_owner_prep(etr_ctx* ctx, const int64_t* d_req, const int32_t* d_counts, int32_t world, int32_t cap,
+                         int64_t local_rows, uint64_t* d_map, uint32_t* d_step, uint32_t* d_mask, int32_t* d_others,
+                         void* stream);
+int etr_shard_owner_apply(etr_ctx* ctx, const etr_table* table, float* d_m, float* d_v, const int64_t* d_req,
+                          const int32_t* d_counts, const float* d_grads, int32_t world, int32_t cap, int32_t ld,
+                          uint32_t* d_mask, const int32_t* d_others, int32_t fm_k, const float* d_lr_t, float beta1,
+                          float beta2, float eps, void* stream);
 /* Cross-rank barrier on the stream, over peer memory: every rank owns a flag array [world]
  * (etr_peer_alloc, zero-initialised) and an epoch word; the kernel bumps the epoch, stores it into
  * flags[rank] of every peer and waits (bounded: ~20 s, then error -3 is flagged) until all peers'

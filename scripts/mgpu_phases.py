@@ -64,7 +64,7 @@ def main():
         mark("ids assemble + sorted plan (CUB sort + unique)")
         peer.ensure_mailbox(plan.n_slots)
         peer._cur_set = 0
-        mb, cap, ld, W = peer._mb, peer.cap, peer.stride, world
+        mb, cap, ld, W = peer._mb, peer.cap, peer.ld, world
         slot_of_u = rt.empty((plan.n_slots,), torch.int32)
         check(rt.lib.etr_shard_request(rt.ctx, plan.unique_ids.data_ptr(), plan.counts.data_ptr(), plan.n_slots, W, cap,
                                        mb["ids_ptrs"][0], mb["counts_ptrs"][0], mb["local_cnt"][0].data_ptr(),
@@ -72,6 +72,8 @@ def main():
         mark("request: unique ids -> owners' mailboxes")
         peer.barrier()
         mark("barrier")
+        if peer.owner_prep:
+            peer._launch_owner_prep(0)                # side stream: pairs up the entries per row while the forward runs
         t = peer.local.desc()
         check(rt.lib.etr_shard_serve(rt.ctx, C.byref(t), mb["ids_t"][0].data_ptr(), mb["counts_t"][0].data_ptr(), W, cap,
                                      mb["resp_ptrs"], ld, rt.stream))
@@ -116,7 +118,7 @@ def main():
         P.adam_step(0.0, tr.state[1:], tr.b1, tr.b2, tr.eps)
         mark("dense sum + adam")
         peer.apply_mailbox(tr.state[1:], tr.b1, tr.b2, tr.eps, 0)
-        mark("owner: accumulate regions + touched-row adam")
+        mark("owner apply (one pass over the request entries; ETR_PEER_OWNER_PREP=0: accumulate regions + touched-row adam)")
         peer.barrier()
         mark("barrier   ")
 

@@ -107,3 +107,84 @@ def test_a2a_sharded_world1_equals_unsharded(L, model):
     w = full.table.width
     assert (sh.table.data[:V, :w] - full.table.data[:, :w]).abs().max().item() < 2e-5
     assert (sh.params.value - full.params.value).abs().max().item() < 2e-5
+
+
+@pytest.mark.parametrize("record", [True, False])
+def test_owner_prep_apply_equals_region_accumulation(L, record):
+    """Owner side of the peer step on ONE GPU with a synthetic 4-source mailbox whose regions overlap heavily: the
+    request-driven form (etr_shard_owner_prep on the requests, then the one-pass etr_shard_owner_apply) must be
+    BIT-identical to the region-by-region stamped accumulator + touched-row Adam, and match a torch statement of
+    'sum the sources in rank order, finish dv = P - v * sum_g, row-wise Adam' -- two steps (the pass cleans its masks)."""
+    import ctypes as C
+    from etr_b200 import _lib
+    from etr_b200._lib import check
+    from etr_b200.runtime import Runtime, EmbeddingTable
+    rt = Runtime.get()
+    W, cap, rows, ld, k = 4, 512, 1000, 20, 16
+    g = torch.Generator(device="cpu").manual_seed(5)
+
+    def table():
+        if record:
+            t = EmbeddingTable(rt, rows, k + 1, record=True)
+        else:
+            t = EmbeddingTable(rt, rows, k + 1)
+            assert t.stride == 20
+        return t
+
+    A, Bt = table(), table()
+    init = torch.rand((rows, k + 1), generator=g) * 0.1 - 0.05
+    for t in (A, Bt):
+        t.data[:, : k + 1] = init.cuda()
+        _ = t.m, t.v
+    own = {"map": rt.zeros((rows,), torch.int64), "step": rt.zeros((1,), torch.int32),
+           "mask": rt.zeros((W * cap,), torch.int32), "others": rt.empty((W * cap, W), torch.int32)}
+    gacc, epoch = rt.zeros((rows, ld)), rt.zeros((1,), torch.int32)
+    touched, n_touched = rt.empty((W * cap,), torch.int32), rt.zeros((1,), torch.int32)
+    lr_t = torch.tensor([1e-2], device=rt.device)
+    ref_var, ref_m, ref_v = init.double().clone(), torch.zeros(rows, k + 1).double(), torch.zeros(rows, k + 1).double()
+    for step in range(2):
+        req = torch.zeros((W, cap), dtype=torch.int64)
+        grads = torch.zeros((W, cap, ld))
+        counts = torch.tensor([300, 0, 512, 170][::1 if step == 0 else -1], dtype=torch.int32)
+        for s in range(W):
+            n = int(counts[s])
+            req[s, :n] = torch.randperm(rows, generator=g)[:n]
+            grads[s, :n, : k + 1] = torch.randn((n, k + 1), generator=g) * 0.1
+        req_d, grads_d, counts_d = req.cuda(), grads.cuda(), counts.cuda()
+        epoch += 1
+        # A: the request-driven form
+        check(rt.lib.etr_shard_owner_prep(rt.ctx, req_d.data_ptr(), counts_d.data_ptr(), W, cap, rows, own["map"].data_ptr(),
+                                          own["step"].data_ptr(), own["mask"].data_ptr(), own["others"].data_ptr(), rt.stream))
+        ta = A.desc()
+        check(rt.lib.etr_shard_owner_apply(rt.ctx, C.byref(ta), A.m.data_ptr(), A.v.data_ptr(), req_d.data_ptr(),
+                                           counts_d.data_ptr(), grads_d.data_ptr(), W, cap, ld, own["mask"].data_ptr(),
+                                           own["others"].data_ptr(), k, lr_t.data_ptr(), 0.9, 0.999, 1e-7, rt.stream))
+        # B: region-by-region accumulation + touched-row Adam
+        tb = Bt.desc()
+        check(rt.lib.etr_shard_mailbox_accumulate(rt.ctx, req_d.data_ptr(), grads_d.data_ptr(), counts_d.data_ptr(), W, cap, ld,
+                                                  gacc.data_ptr(), epoch.data_ptr(), touched.data_ptr(), n_touched.data_ptr(),
+                                                  W * cap, rt.stream))
+        check(rt.lib.etr_shard_touched_adam(rt.ctx, C.byref(tb), Bt.m.data_ptr(), Bt.v.data_ptr(), gacc.data_ptr(), ld,
+                                            touched.data_ptr(), n_touched.data_ptr(), W * cap, k, lr_t.data_ptr(), 0.9, 0.999,
+                                            1e-7, rt.stream))
+        torch.cuda.synchronize()
+        rt.poll_error()
+        assert int(own["mask"].abs().sum().item()) == 0                 # the pass cleaned up behind itself
+        for a, b in ((A.data, Bt.data), (A.m, Bt.m), (A.v, Bt.v)):
+            assert torch.equal(a[:, : k + 1], b[:, : k + 1])
+        # torch statement (fp64)
+        acc = torch.zeros(rows, ld).double()
+        hit = torch.zeros(rows, dtype=torch.bool)
+        for s in range(W):
+            n = int(counts[s])
+            acc.index_add_(0, req[s, :n], grads[s, :n].double())
+            hit[req[s, :n]] = True
+        gr = acc[:, : k + 1].clone()
+        gr[:, :k] -= ref_var[:, :k] * acc[:, k: k + 1]
+        m2 = 0.9 * ref_m + 0.1 * gr
+        v2 = 0.999 * ref_v + 0.001 * gr * gr
+        var2 = ref_var - 1e-2 * m2 / (v2.sqrt() + 1e-7)
+        ref_m, ref_v, ref_var = torch.where(hit[:, None], m2, ref_m), torch.where(hit[:, None], v2, ref_v), \
+            torch.where(hit[:, None], var2, ref_var)
+        assert (A.data[:, : k + 1].cpu().double() - ref_var).abs().max().item() < 1e-5
+        assert (A.m[:, : k + 1].cpu().double() - ref_m).abs().max().item() < 1e-6
