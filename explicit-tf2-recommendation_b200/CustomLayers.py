@@ -1456,16 +1456,22 @@ class Trainer:
                 dlogit.mul_(1.0 / self.dp_world)      # the loss is the mean over the GLOBAL batch
             grads = self.layer.backward(dlogit)
         if self.peer is not None:
-            # rows -> owners' mailboxes, dense grads -> every peer's slot; ONE device-side barrier
+            # rows -> owners' mailboxes, dense grads -> every peer's slot (on the dense stream, under the row push);
+            # ONE device-side barrier; then the owner's row apply with the dense sum + dense Adam beside it
+            cur, ds = torch.cuda.current_stream(rt.device), self._dense_stream_get()
+            ds.wait_stream(cur)
+            with torch.cuda.stream(ds):
+                self.peer.allreduce_push(self.layer.params.grad)
             for g in grads:
                 g.push()
-            self.peer.allreduce_push(self.layer.params.grad)
+            cur.wait_stream(ds)
             self.peer.barrier()
-            self.peer.allreduce_sum(self.layer.params.grad)
-        elif self.dp_world > 1:
-            import torch.distributed as dist
-            dist.all_reduce(self.layer.params.grad)   # replicated dense variables: sum of the ranks' grads
-        self.apply_gradients(grads)
+            self._apply_peer(grads, cur, ds)
+        else:
+            if self.dp_world > 1:
+                import torch.distributed as dist
+                dist.all_reduce(self.layer.params.grad)   # replicated dense variables: sum of the ranks' grads
+            self.apply_gradients(grads)
         if self.plan_ahead and nsl is not None and nsl is not sl:
             nsl.plan.join()                           # the look-ahead sort + requests belong to THIS step (timed with it)
             nsl.plan._pending = None
@@ -1476,6 +1482,27 @@ class Trainer:
             sl.used = True
             sl.compute_done.record(torch.cuda.current_stream(rt.device))
         return loss
+
+    def _dense_stream_get(self) -> "torch.cuda.Stream":
+        if getattr(self, "_dense_stream", None) is None:
+            self._dense_stream = torch.cuda.Stream(device=self.rt.device)
+        return self._dense_stream
+
+    def _apply_peer(self, grads, cur, ds) -> None:
+        """after the gradient barrier of a peer-sharded step: the owner's row apply on the main stream, the rank-ordered
+        sum of the dense-gradient slots + dense Adam beside it on the dense stream (they share only the step's lr_t)"""
+        rt = self.rt
+        assert not self.used_rows_l2, "used-rows L2 is not wired into the peer-sharded apply"
+        check(rt.lib.etr_adam_step_begin(rt.ctx, self.state.data_ptr(), self.lr, self.b1, self.b2, rt.stream))
+        d_lr = self.state[1:]
+        ds.wait_stream(cur)
+        with torch.cuda.stream(ds):
+            self.peer.allreduce_sum(self.layer.params.grad)
+            self.layer.params.adam_step(0.0, d_lr, self.b1, self.b2, self.eps)
+        for g in grads:
+            g.apply(d_lr, self.b1, self.b2, self.eps, self.mode)
+        cur.wait_stream(ds)
+        self.last_grads = grads
 
     def apply_gradients(self, grads: List[SparseGrad]) -> None:
         rt = self.rt

@@ -9,6 +9,7 @@
 #include <cub/device/device_radix_sort.cuh>
 
 #include "etr_common.cuh"
+#include "etr_async.cuh"
 
 namespace etr {
 
@@ -328,9 +329,7 @@ __global__ void __launch_bounds__(256) touched_adam_kernel(const TouchedAdamPara
     float* xv = &var.x; float* xm = &m.x; float* xvv = &v.x; const float* xg = &g.x;
 #pragma unroll
     for (int q = 0; q < 4; ++q) {
-      xm[q] = p.b1 * xm[q] + (1.0f - p.b1) * xg[q];
-      xvv[q] = p.b2 * xvv[q] + (1.0f - p.b2) * xg[q] * xg[q];
-      xv[q] = xv[q] - lr_t * xm[q] / (sqrtf(xvv[q]) + p.eps);
+      adam_update1_fast(xv[q], xm[q], xvv[q], xg[q], lr_t, p.b1, p.b2, p.eps);   // the fused single-GPU apply's expression
     }
     *pvar = var; *pm = m; *pv = v;
   }
@@ -388,7 +387,7 @@ struct OwnerApplyParams {
   float* table; float* m; float* v; int stride; long long rows;
   int fm_k; const float* d_lr_t; float b1, b2, eps;
 };
-template <int LPR>
+template <int LPR, int U>                                   // U: entries in flight per lane group
 __global__ void __launch_bounds__(256) owner_apply_kernel(const OwnerApplyParams p) {
   constexpr int GPW = 32 / LPR;
   const int src = blockIdx.y;
@@ -401,56 +400,70 @@ __global__ void __launch_bounds__(256) owner_apply_kernel(const OwnerApplyParams
   const float lr_t = *p.d_lr_t;
   const bool mine = gl < nch;
   const int sg_lane = g * LPR + p.fm_k / 4;
-  // trip count uniform per lane group (the shuffles are group-wide)
-  for (int s = (blockIdx.x * 8 + (threadIdx.x >> 5)) * GPW + g; s < n; s += gridDim.x * 8 * GPW) {
-    const long long e = (long long)src * p.cap + s;
-    const unsigned mk = p.mask[e];
-    const long long row = p.req[e];
-    __syncwarp(gmask);
-    if (mk == 0u) continue;                                 // out-of-range row (never claimed)
-    if (gl == 0) p.mask[e] = 0u;                            // self-cleaning
-    if (!(mk & 0x80000000u)) continue;                      // a leader elsewhere sums this row
-    float4 var = make_float4(0.f, 0.f, 0.f, 0.f), mm = var, vv = var, acc = var;
-    float* prow = p.table + row * p.stride + gl * 4;
-    float* pm = p.m + row * p.stride + gl * 4;
-    float* pv = p.v + row * p.stride + gl * 4;
-    if (mine) {
-      var = *reinterpret_cast<const float4*>(prow);
-      mm = *reinterpret_cast<const float4*>(pm);
-      vv = *reinterpret_cast<const float4*>(pv);
+  const int step = gridDim.x * 8 * GPW;
+  // every condition below is uniform per lane group (the shuffles are group-wide)
+  for (int s0 = (blockIdx.x * 8 + (threadIdx.x >> 5)) * GPW + g; s0 < n; s0 += U * step) {
+    unsigned mk[U];
+    long long e[U], row[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const int s = s0 + u * step;
+      e[u] = (long long)src * p.cap + s;
+      mk[u] = 0u; row[u] = 0;
+      if (s < n) { mk[u] = p.mask[e[u]]; row[u] = p.req[e[u]]; }
     }
-    unsigned srcs = mk & 0xffffu;
-    if (srcs == (1u << src)) {                              // the common case: one contributor
-      if (mine) acc = __ldcs(reinterpret_cast<const float4*>(p.grads + e * p.ld + gl * 4));
-    } else {
+    __syncwarp(gmask);
+    float4 var[U], mm[U], vv[U], acc[U];
+    bool lead[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      lead[u] = (mk[u] & 0x80000000u) != 0u;                // else: a leader elsewhere sums this row (or never claimed)
+      if (mk[u] != 0u && gl == 0) p.mask[e[u]] = 0u;        // self-cleaning
+      var[u] = mm[u] = vv[u] = acc[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (lead[u] && mine) {
+        const long long off = row[u] * p.stride + gl * 4;
+        var[u] = *reinterpret_cast<const float4*>(p.table + off);
+        mm[u] = *reinterpret_cast<const float4*>(p.m + off);
+        vv[u] = *reinterpret_cast<const float4*>(p.v + off);
+        if ((mk[u] & 0xffffu) == (1u << src))               // the common case: one contributor
+          acc[u] = __ldcs(reinterpret_cast<const float4*>(p.grads + e[u] * p.ld + gl * 4));
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      unsigned srcs = mk[u] & 0xffffu;
+      if (!lead[u] || srcs == (1u << src)) continue;
       bool first = true;
-      while (srcs) {
+      while (srcs) {                                        // ascending source order = the region-by-region order
         const int q = __ffs(srcs) - 1;
         srcs &= srcs - 1;
-        const long long eq = (q == src) ? e : (long long)q * p.cap + p.others[e * p.world + q];
+        const long long eq = (q == src) ? e[u] : (long long)q * p.cap + p.others[e[u] * p.world + q];
         if (mine) {
           const float4 x = __ldcs(reinterpret_cast<const float4*>(p.grads + eq * p.ld + gl * 4));
-          if (first) acc = x;
-          else { acc.x += x.x; acc.y += x.y; acc.z += x.z; acc.w += x.w; }
+          if (first) acc[u] = x;
+          else { acc[u].x += x.x; acc[u].y += x.y; acc[u].z += x.z; acc[u].w += x.w; }
         }
         first = false;
       }
     }
-    if (p.fm_k > 0) {
-      const float sg = __shfl_sync(gmask, acc.x, sg_lane);
-      if (gl * 4 < p.fm_k) { acc.x -= var.x * sg; acc.y -= var.y * sg; acc.z -= var.z * sg; acc.w -= var.w * sg; }
-    }
-    if (mine) {
-      float* xv = &var.x; float* xm = &mm.x; float* xvv = &vv.x; const float* xg = &acc.x;
 #pragma unroll
-      for (int q = 0; q < 4; ++q) {
-        xm[q] = p.b1 * xm[q] + (1.0f - p.b1) * xg[q];
-        xvv[q] = p.b2 * xvv[q] + (1.0f - p.b2) * xg[q] * xg[q];
-        xv[q] = xv[q] - lr_t * xm[q] / (sqrtf(xvv[q]) + p.eps);
+    for (int u = 0; u < U; ++u) {
+      if (!lead[u]) continue;
+      if (p.fm_k > 0) {
+        const float sg = __shfl_sync(gmask, acc[u].x, sg_lane);
+        if (gl * 4 < p.fm_k) { acc[u].x -= var[u].x * sg; acc[u].y -= var[u].y * sg; acc[u].z -= var[u].z * sg; acc[u].w -= var[u].w * sg; }
       }
-      *reinterpret_cast<float4*>(prow) = var;
-      *reinterpret_cast<float4*>(pm) = mm;
-      *reinterpret_cast<float4*>(pv) = vv;
+      if (mine) {
+        float* xv = &var[u].x; float* xm = &mm[u].x; float* xvv = &vv[u].x; const float* xg = &acc[u].x;
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          adam_update1_fast(xv[q], xm[q], xvv[q], xg[q], lr_t, p.b1, p.b2, p.eps);
+        }
+        const long long off = row[u] * p.stride + gl * 4;
+        *reinterpret_cast<float4*>(p.table + off) = var[u];
+        *reinterpret_cast<float4*>(p.m + off) = mm[u];
+        *reinterpret_cast<float4*>(p.v + off) = vv[u];
+      }
     }
   }
 }
@@ -733,15 +746,22 @@ int etr_shard_owner_apply(etr_ctx* ctx, const etr_table* table, float* d_m, floa
   p.rows = table->rows; p.fm_k = fm_k; p.d_lr_t = d_lr_t; p.b1 = beta1; p.b2 = beta2; p.eps = eps;
   int lpr = 1;
   while (lpr < ld / 4) lpr <<= 1;
-  dim3 grid((unsigned)grid_for(cap, 8 * (32 / lpr), ctx->sm_count, 16 / (world < 8 ? world : 8) + 1), (unsigned)world);
+  static int bps = -1, unroll = 1;                          // ETR_OWNER_BPS / ETR_OWNER_U: measurement knobs
+  if (bps < 0) {
+    const char* e = getenv("ETR_OWNER_BPS"); bps = e ? atoi(e) : 0;
+    const char* u = getenv("ETR_OWNER_U"); unroll = (u && atoi(u) == 2) ? 2 : 1;
+  }
+  const int per_sm = bps > 0 ? bps : 16 / (world < 8 ? world : 8) + 1;
+  dim3 grid((unsigned)grid_for(cap, 8 * (32 / lpr) * unroll, ctx->sm_count, per_sm), (unsigned)world);
   cudaStream_t s = (cudaStream_t)stream;
-  switch (lpr) {
-    case 1: owner_apply_kernel<1><<<grid, 256, 0, s>>>(p); break;
-    case 2: owner_apply_kernel<2><<<grid, 256, 0, s>>>(p); break;
-    case 4: owner_apply_kernel<4><<<grid, 256, 0, s>>>(p); break;
-    case 8: owner_apply_kernel<8><<<grid, 256, 0, s>>>(p); break;
-    case 16: owner_apply_kernel<16><<<grid, 256, 0, s>>>(p); break;
-    default: owner_apply_kernel<32><<<grid, 256, 0, s>>>(p); break;
+  if (lpr == 8 && unroll == 2) owner_apply_kernel<8, 2><<<grid, 256, 0, s>>>(p);
+  else switch (lpr) {
+    case 1: owner_apply_kernel<1, 1><<<grid, 256, 0, s>>>(p); break;
+    case 2: owner_apply_kernel<2, 1><<<grid, 256, 0, s>>>(p); break;
+    case 4: owner_apply_kernel<4, 1><<<grid, 256, 0, s>>>(p); break;
+    case 8: owner_apply_kernel<8, 1><<<grid, 256, 0, s>>>(p); break;
+    case 16: owner_apply_kernel<16, 1><<<grid, 256, 0, s>>>(p); break;
+    default: owner_apply_kernel<32, 1><<<grid, 256, 0, s>>>(p); break;
   }
   ETR_LAUNCH_CHECK(ctx);
   return ETR_OK;
