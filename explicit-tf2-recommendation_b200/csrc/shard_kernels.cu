@@ -206,6 +206,33 @@ __global__ void __launch_bounds__(256) shard_serve_kernel(const ServeParams p) {
       *reinterpret_cast<float4*>(out + s * p.ld + c * 4) = ldg_row16(p.table + row * p.stride + c * 4);
   }
 }
+// The same copy with the response region addressed as a flat array of 16-byte chunks: thread t of a CTA iteration moves
+// chunk t of a 256-slot span (slot = chunk / chunks-per-row), so every warp store is 512 contiguous, line-aligned bytes
+// (cap is a multiple of 64 slots and the span starts on a multiple of 256 slots: 256 * ld * 4 bytes is a whole number of
+// lines).  The row-per-lane-group form above ends most warp stores inside a 32-byte sector (80-byte rows): partial
+// writes that NVLink carries as separate, masked packets.
+__global__ void __launch_bounds__(256) shard_serve_flat_kernel(const ServeParams p) {
+  const int src = blockIdx.y;
+  const int nchunks = p.ld / 4;
+  int n = p.counts[src];
+  if (n > p.cap) n = p.cap;
+  const long long* req = p.req + (long long)src * p.cap;
+  float4* out = reinterpret_cast<float4*>(p.resp[src]);
+  const long long total = (long long)n * nchunks;
+  for (long long q0 = (long long)blockIdx.x * (256 * nchunks); q0 < total; q0 += (long long)gridDim.x * (256 * nchunks)) {
+#pragma unroll 5
+    for (int it = 0; it < nchunks; ++it) {
+      const long long q = q0 + it * 256 + threadIdx.x;
+      if (q < total) {
+        const long long s = q / nchunks;
+        const int c = (int)(q - s * nchunks);
+        long long row = req[s];
+        if ((unsigned long long)row >= (unsigned long long)p.rows) { flag_bad_id(p.err, row); row = 0; }
+        out[q] = ldg_row16(p.table + row * p.stride + c * 4);
+      }
+    }
+  }
+}
 
 // vid[occurrence] = response-buffer row of the occurrence's id.  A thread per sorted position finds its
 // run by binary search over seg_start (n_unique + 1 entries, L2-resident).
@@ -645,6 +672,14 @@ int etr_shard_serve(etr_ctx* ctx, const etr_table* table, const int64_t* d_req, 
   while (lpr < ld / 4) lpr <<= 1;
   dim3 grid((unsigned)grid_for(cap, 8 * (32 / lpr), ctx->sm_count, 8 / (world < 8 ? world : 8) + 1), (unsigned)world);
   cudaStream_t s = (cudaStream_t)stream;
+  static int flat = -1;
+  if (flat < 0) { const char* e = getenv("ETR_SERVE_FLAT"); flat = !(e && atoi(e) == 0); }
+  if (flat) {
+    dim3 fgrid((unsigned)grid_for(cap, 256, ctx->sm_count, 8 / (world < 8 ? world : 8) + 1), (unsigned)world);
+    shard_serve_flat_kernel<<<fgrid, 256, 0, s>>>(p);
+    ETR_LAUNCH_CHECK(ctx);
+    return ETR_OK;
+  }
   switch (lpr) {
     case 1: shard_serve_kernel<1><<<grid, 256, 0, s>>>(p); break;
     case 2: shard_serve_kernel<2><<<grid, 256, 0, s>>>(p); break;
