@@ -17,7 +17,7 @@ namespace etr {
 
 namespace sk {
 
-constexpr int SB = 64;                 // samples per slab
+constexpr int SB = 32;                 // samples per slab (two X slabs in flight: the next one lands while this one is used)
 constexpr int NOUT = 32;               // narrow side
 constexpr int DS = NOUT + 8;           // smem row stride (bf16) of d and K rows: 80 B -> conflict-free ldmatrix
 constexpr int STG = 32 + 8;            // staging row stride (bf16) of a 16 x 32 dX fragment block
@@ -51,19 +51,24 @@ struct Params {
 // MT: feature m-tiles (16 rows of dK) owned per warp = ceil(n_in / 16 / 8)
 // NIN: n_in as a compile-time constant for the hot shape (0 = run-time): the index divisions of the staging loops and
 // the tile bounds fold away (15.1 M warp instructions per c2 launch with run-time n_in, issue-bound at 16 warps / SM)
+// Pipeline (end of round 2): 32-sample slabs, the X slab of the NEXT iteration is in flight (cp.async into the other
+// buffer) and its d rows sit in registers while this slab's two products run; the one-stage form stalled on every slab
+// (issue active 35 %, 16 warps / SM: profiles/r02_prof_c2_tower.md).
 template <int MT, int NIN = 0>
 __global__ void __launch_bounds__(256, 2) mlp_skinny_bwd_kernel(const Params p) {
   extern __shared__ __align__(16) unsigned char smem[];
   const int n_in = NIN ? NIN : p.n_in;
   const int XS = n_in + 8;                                            // smem row stride of an X row (bf16)
-  __nv_bfloat16* Xs = reinterpret_cast<__nv_bfloat16*>(smem);         // [SB][XS]
-  __nv_bfloat16* Ds = Xs + SB * XS;                                    // [SB][DS]
+  __nv_bfloat16* Xs = reinterpret_cast<__nv_bfloat16*>(smem);         // [2][SB][XS]
+  __nv_bfloat16* Ds = Xs + 2 * SB * XS;                                // [SB][DS]
   __nv_bfloat16* Ks = Ds + SB * DS;                                    // [n_in][DS]
   __nv_bfloat16* St = Ks + (size_t)n_in * DS;                          // [8 warps][16][STG]
+  float* dbs = reinterpret_cast<float*>(St + 8 * 16 * STG);            // [8 warps][NOUT] column sums of d (4 rows each)
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int g = lane >> 2, t = lane & 3;
   const int mtiles = n_in / 16;
   const int ntiles_x = n_in / 8;                                       // n-tiles of the dX product
+  const int chunks_per_row = n_in / 8;
 
   // K -> bf16 in shared memory, once per CTA
   for (int e = tid; e < n_in * NOUT; e += 256) {
@@ -81,43 +86,63 @@ __global__ void __launch_bounds__(256, 2) mlp_skinny_bwd_kernel(const Params p) 
   float db_acc = 0.f;                                                  // thread tid < NOUT: column tid of d
 
   const long long nslabs = (p.B + SB - 1) / SB;
-  for (long long slab = blockIdx.x; slab < nslabs; slab += gridDim.x) {
+  const int dr = tid >> 3, dc = tid & 7;                               // this thread's float4 of a d slab: row dr, columns 4 dc..
+  auto stage_x = [&](long long slab, int buf) {                        // cp.async, 16 B per request
     const long long b0 = slab * SB;
-    __syncthreads();                                                   // the previous slab is fully consumed
-    // ---- stage X slab (cp.async, 16 B per request) and d slab (fp32 -> bf16)
-    const int chunks_per_row = n_in / 8;
+    __nv_bfloat16* dst = Xs + buf * SB * XS;
     for (int e = tid; e < SB * chunks_per_row; e += 256) {
       const int r = e / chunks_per_row, c = e % chunks_per_row;
-      if (b0 + r < p.B) cp16(Xs + r * XS + c * 8, p.X + (b0 + r) * p.ldx + c * 8);
-      else *reinterpret_cast<uint4*>(Xs + r * XS + c * 8) = make_uint4(0, 0, 0, 0);
+      if (b0 + r < p.B) cp16(dst + r * XS + c * 8, p.X + (b0 + r) * p.ldx + c * 8);
+      else *reinterpret_cast<uint4*>(dst + r * XS + c * 8) = make_uint4(0, 0, 0, 0);
     }
     asm volatile("cp.async.commit_group;" ::: "memory");
-    for (int e = tid; e < SB * NOUT / 4; e += 256) {
-      const int r = e / (NOUT / 4), c = e % (NOUT / 4);
-      float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-      if (b0 + r < p.B) v = *reinterpret_cast<const float4*>(p.d + (b0 + r) * NOUT + c * 4);
-      const __nv_bfloat162 lo = __floats2bfloat162_rn(v.x, v.y), hi = __floats2bfloat162_rn(v.z, v.w);
-      *reinterpret_cast<uint2*>(Ds + r * DS + c * 4) =
+  };
+  auto load_d = [&](long long slab) {
+    const long long b = slab * SB + dr;
+    return b < p.B ? *reinterpret_cast<const float4*>(p.d + b * NOUT + dc * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
+  };
+  float4 dreg = make_float4(0.f, 0.f, 0.f, 0.f);
+  if ((long long)blockIdx.x < nslabs) { stage_x(blockIdx.x, 0); dreg = load_d(blockIdx.x); }
+  int buf = 0;
+  for (long long slab = blockIdx.x; slab < nslabs; slab += gridDim.x, buf ^= 1) {
+    const long long b0 = slab * SB;
+    __syncthreads();                                                   // the previous slab is fully consumed
+    // ---- this slab's d: registers -> bf16 rows in shared memory, column sums (fixed shuffle tree, then warp order)
+    {
+      const __nv_bfloat162 lo = __floats2bfloat162_rn(dreg.x, dreg.y), hi = __floats2bfloat162_rn(dreg.z, dreg.w);
+      *reinterpret_cast<uint2*>(Ds + dr * DS + dc * 4) =
           make_uint2(*reinterpret_cast<const unsigned*>(&lo), *reinterpret_cast<const unsigned*>(&hi));
+      float4 s4 = dreg;                                                // lanes l, l^8, l^16, l^24: rows 4 warp .. 4 warp + 3
+      s4.x += __shfl_xor_sync(0xffffffffu, s4.x, 8); s4.y += __shfl_xor_sync(0xffffffffu, s4.y, 8);
+      s4.z += __shfl_xor_sync(0xffffffffu, s4.z, 8); s4.w += __shfl_xor_sync(0xffffffffu, s4.w, 8);
+      s4.x += __shfl_xor_sync(0xffffffffu, s4.x, 16); s4.y += __shfl_xor_sync(0xffffffffu, s4.y, 16);
+      s4.z += __shfl_xor_sync(0xffffffffu, s4.z, 16); s4.w += __shfl_xor_sync(0xffffffffu, s4.w, 16);
+      if (lane < 8) *reinterpret_cast<float4*>(dbs + warp * NOUT + lane * 4) = s4;
     }
-    if (tid < NOUT) {                                                  // db: fixed order over the slab's rows
+    // ---- the next slab: X into the other buffer, d into registers
+    const long long nxt = slab + gridDim.x;
+    if (nxt < nslabs) { stage_x(nxt, buf ^ 1); dreg = load_d(nxt); }
+    else asm volatile("cp.async.commit_group;" ::: "memory");
+    asm volatile("cp.async.wait_group 1;" ::: "memory");               // this slab's X has landed
+    __syncthreads();
+    if (tid < NOUT) {
       float s = 0.f;
-      const int rows = (int)((p.B - b0) < SB ? (p.B - b0) : SB);
-      for (int r = 0; r < rows; ++r) s += p.d[(b0 + r) * NOUT + tid];
+#pragma unroll
+      for (int w = 0; w < 8; ++w) s += dbs[w * NOUT + tid];
       db_acc += s;
     }
-    asm volatile("cp.async.wait_group 0;" ::: "memory");
-    __syncthreads();
+    const __nv_bfloat16* Xb = Xs + buf * SB * XS;
 
-    // ---- (I) dX slab = d (SB x 32) * K^T: warp -> sample tile (warp & 3), half of the n-tiles (warp >> 2)
+    // ---- (I) dX slab = d (SB x 32) * K^T: warp -> sample tile (warp & 1), a quarter of the n-tiles (warp >> 1)
     if (p.dX) {
-      const int st = warp & 3, half = warp >> 2;
+      const int st = warp & 1, quarter = warp >> 1;
       unsigned a[NOUT / 16][4];
 #pragma unroll
       for (int ks = 0; ks < NOUT / 16; ++ks)
         ldsm_x4(a[ks], Ds + (st * 16 + (lane & 7) + 8 * ((lane >> 3) & 1)) * DS + ks * 16 + 8 * (lane >> 4));
-      const int nt0 = half * ((ntiles_x + 1) / 2);
-      int nt1 = nt0 + (ntiles_x + 1) / 2;
+      const int per = ((ntiles_x + 3) / 4 + 1) & ~1;                   // n-tiles per quarter, whole pairs
+      const int nt0 = quarter * per;
+      int nt1 = nt0 + per;
       if (nt1 > ntiles_x) nt1 = ntiles_x;
       __nv_bfloat16* stg = St + warp * 16 * STG;
       for (int nb = nt0; nb < nt1; nb += 4) {                         // blocks of 4 n-tiles = 32 columns
@@ -169,7 +194,7 @@ __global__ void __launch_bounds__(256, 2) mlp_skinny_bwd_kernel(const Params p) 
         for (int ks = 0; ks < SB / 16; ++ks) {
           unsigned a[4], b0r[4], b1r[4];
           // A = X^T tile: stored [k = sample][m = feature]; matrices q: k-off 8*(q/2), m-off 8*(q%2)
-          ldsm_x4_t(a, Xs + (ks * 16 + (lane & 7) + 8 * (lane >> 4)) * XS + mt * 16 + 8 * ((lane >> 3) & 1));
+          ldsm_x4_t(a, Xb + (ks * 16 + (lane & 7) + 8 * (lane >> 4)) * XS + mt * 16 + 8 * ((lane >> 3) & 1));
           // B = d: stored [k = sample][n = o]; matrices q: k-off 8*(q%2), n-off 8*(q/2)
           ldsm_x4_t(b0r, Ds + (ks * 16 + (lane & 7) + 8 * ((lane >> 3) & 1)) * DS + 0 + 8 * (lane >> 4));
           ldsm_x4_t(b1r, Ds + (ks * 16 + (lane & 7) + 8 * ((lane >> 3) & 1)) * DS + 16 + 8 * (lane >> 4));
@@ -181,6 +206,7 @@ __global__ void __launch_bounds__(256, 2) mlp_skinny_bwd_kernel(const Params p) 
       }
     }
   }
+  asm volatile("cp.async.wait_group 0;" ::: "memory");
 
   // ---- per-CTA partials: dK [n_in][NOUT] then db [NOUT]
   float* out = p.part + (size_t)blockIdx.x * ((size_t)n_in * NOUT + NOUT);
@@ -199,37 +225,31 @@ __global__ void __launch_bounds__(256, 2) mlp_skinny_bwd_kernel(const Params p) 
   if (tid < NOUT) out[(size_t)n_in * NOUT + tid] = db_acc;
 }
 
-// sum the per-CTA partials: a CTA owns 128 consecutive elements (one float4 per lane); its 8 warps each add a contiguous
-// range of the partials (512-byte coalesced reads, 8 independent loads in flight), the 8 sub-sums are combined in warp
-// order (deterministic; same per-element order as a scalar walk)
+// sum the per-CTA partials: a CTA owns 32 consecutive elements (one float per lane: 433 CTAs for the c2 layer instead of
+// 109 with a float4 per lane, which left a quarter of the SMs idle and every warp with 37 dependent-latency rounds); its
+// 8 warps each add a contiguous range of the partials (8 independent loads in flight), the 8 sub-sums are combined in
+// warp order (deterministic; the per-element order is unchanged)
 __global__ void __launch_bounds__(256) mlp_skinny_bwd_finish_kernel(const float* part, int nparts, int n_elems, int n_k,
                                                                     float* dK, float* db) {
-  __shared__ float4 sm[8][32];
+  __shared__ float sm[8][32];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const int e = (blockIdx.x * 32 + lane) * 4;          // n_elems % 4 == 0 (n_in * 32 + 32)
+  const int e = blockIdx.x * 32 + lane;
   const int per = (nparts + 7) / 8;
   int c0 = warp * per, c1 = c0 + per;
   if (c1 > nparts) c1 = nparts;
-  float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
+  float s = 0.f;
   if (e < n_elems) {
 #pragma unroll 8
-    for (int c = c0; c < c1; ++c) {
-      const float4 v = __ldg(reinterpret_cast<const float4*>(part + (size_t)c * n_elems + e));
-      s.x += v.x; s.y += v.y; s.z += v.z; s.w += v.w;
-    }
+    for (int c = c0; c < c1; ++c) s += __ldg(part + (size_t)c * n_elems + e);
   }
   sm[warp][lane] = s;
   __syncthreads();
   if (warp == 0 && e < n_elems) {
-    float4 t = make_float4(0.f, 0.f, 0.f, 0.f);
+    float t = 0.f;
 #pragma unroll
-    for (int w = 0; w < 8; ++w) { t.x += sm[w][lane].x; t.y += sm[w][lane].y; t.z += sm[w][lane].z; t.w += sm[w][lane].w; }
-    const float tv[4] = {t.x, t.y, t.z, t.w};
-#pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      if (e + i < n_k) dK[e + i] = tv[i];
-      else if (db) db[e + i - n_k] = tv[i];
-    }
+    for (int w = 0; w < 8; ++w) t += sm[w][lane];
+    if (e < n_k) dK[e] = t;
+    else if (db) db[e - n_k] = t;
   }
 }
 
@@ -254,7 +274,8 @@ int etr_mlp_skinny_backward(etr_ctx* ctx, const void* d_X, int64_t ldx, const fl
   if (B <= 0) return ETR_OK;
   cudaStream_t s = (cudaStream_t)stream;
   const int XS = n_in + 8;
-  const size_t smem = ((size_t)sk::SB * XS + (size_t)sk::SB * sk::DS + (size_t)n_in * sk::DS + 8 * 16 * sk::STG) * 2;
+  const size_t smem = ((size_t)2 * sk::SB * XS + (size_t)sk::SB * sk::DS + (size_t)n_in * sk::DS + 8 * 16 * sk::STG) * 2 +
+                      8 * sk::NOUT * sizeof(float);
   const long long nslabs = (B + sk::SB - 1) / sk::SB;
   long long grid = 2LL * ctx->sm_count;
   if (grid > nslabs) grid = nslabs;
@@ -290,7 +311,7 @@ int etr_mlp_skinny_backward(etr_ctx* ctx, const void* d_X, int64_t ldx, const fl
   }
 #undef ETR_SK
   ETR_LAUNCH_CHECK(ctx);
-  sk::mlp_skinny_bwd_finish_kernel<<<(int)((n_elems + 127) / 128), 256, 0, s>>>(
+  sk::mlp_skinny_bwd_finish_kernel<<<(int)((n_elems + 31) / 32), 256, 0, s>>>(
       (const float*)ctx->d_ws, (int)grid, (int)n_elems, n_in * sk::NOUT, d_dK, d_db);
   ETR_LAUNCH_CHECK(ctx);
   return ETR_OK;
