@@ -220,12 +220,12 @@ __device__ __forceinline__ void tile_item(const TileParams& p, int it, int lane,
 
 // per-warp shared memory; every array is indexed by `lane` (= 4 * group + gl) or by a sorted position
 struct WarpSmem {
-  float4 P[64];                       // [j * 4 + gl]: g*S + dflat of the 16 occurrences of a round, sorted order
-  float G[16];
+  float4 P[128];                      // [j * 4 + gl]: g*S + dflat of the (up to 32) occurrences of a round, sorted order
+  float G[32];
   float4 var[2][32], m[2][32], v[2][32];      // two tiles of records (cp.async destinations)
   float w[2][32];                     // [.][4 * g + (0 | 1 | 2 | 3)] = (w, w, its m, its v)
   int4 hdr[2][8];                     // row descriptors of a tile
-  int bag[2][16];                     // bag indices of a tile's first 16 occurrences
+  int bag[2][32];                     // bag indices of a tile's first 32 occurrences
 };
 
 __device__ __forceinline__ void cp_async16(void* dst, const void* src) {
@@ -238,8 +238,11 @@ __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commi
 template <int N>
 __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 
-template <int DF, int OCC, int PUSH>
+// RPG: occurrences per lane group and round (2: rounds of 16, 4: rounds of 32 -- a typical c2 tile, 29 occurrences, is then
+// ONE exposed operand round trip instead of two, at 14 more registers)
+template <int DF, int OCC, int PUSH, int RPG = 2>
 __global__ void __launch_bounds__(128, OCC) fm_tile_kernel(const TileParams p) {
+  constexpr int RND = 8 * RPG;
   __shared__ WarpSmem smem[4];
   const TileArgs& a = p.a;
   const unsigned full = 0xffffffffu;
@@ -273,7 +276,7 @@ __global__ void __launch_bounds__(128, OCC) fm_tile_kernel(const TileParams p) {
     } else if (lane >= 16 && lane < 24) {                  // push mode: the 8 mailbox slots instead of the 8 records
       cp_async4(&sm.w[nb][lane - 16], a.slot_of_u + min(t * 8 + lane - 16, last_slot));
     }
-    if (lane < 16) cp_async4(&sm.bag[nb][lane], a.sorted_bag + min(S0 + lane, last_slot));
+    if (lane < RND) cp_async4(&sm.bag[nb][lane], a.sorted_bag + min(S0 + lane, last_slot));
   };
   auto issue_hdr = [&](int t, int hb) {
     if (t < n_tiles && lane < 8) cp_async16(&sm.hdr[hb][lane], p.rowinfo + t * 8 + lane);
@@ -309,43 +312,50 @@ __global__ void __launch_bounds__(128, OCC) fm_tile_kernel(const TileParams p) {
     const int nspan = any_long ? 8 : 1;
     for (int q = 0; q < nspan; ++q) {
       int lo = S0c, hi = S1c;
-      int bag0 = 0, bag1 = 0;
+      int bag[RPG];
+#pragma unroll
+      for (int r = 0; r < RPG; ++r) bag[r] = 0;
       if (any_long) {
         lo = __shfl_sync(full, s0, q * 4);
         const int l = __shfl_sync(full, len, q * 4);
         if (l <= 0) continue;
         hi = lo + l;
-        if (lo + g < hi) bag0 = __ldg(a.sorted_bag + lo + g);
-        if (lo + 8 + g < hi) bag1 = __ldg(a.sorted_bag + lo + 8 + g);
+#pragma unroll
+        for (int r = 0; r < RPG; ++r)
+          if (lo + r * 8 + g < hi) bag[r] = __ldg(a.sorted_bag + lo + r * 8 + g);
       } else {
-        bag0 = sm.bag[buf][g];
-        bag1 = sm.bag[buf][8 + g];
+#pragma unroll
+        for (int r = 0; r < RPG; ++r) bag[r] = sm.bag[buf][r * 8 + g];
       }
-      for (int pos = lo; pos < hi; pos += 16) {           // a round: 16 occurrences, two per lane group
-        const int n = hi - pos;                            // (>= 16: a full round)
-        int nb0 = 0, nb1 = 0;                              // the next round's bag indices travel during this one
-        if (pos + 16 + g < hi) nb0 = __ldg(a.sorted_bag + pos + 16 + g);
-        if (pos + 24 + g < hi) nb1 = __ldg(a.sorted_bag + pos + 24 + g);
-        Occ o0, o1;
-        if (g < n) occ_load<DF>(a, bag0, gl, o0);
-        if (8 + g < n) occ_load<DF>(a, bag1, gl, o1);
-        if (g < n) {
-          sm.P[lane] = occ_value(o0);
-          if (gl == 0) sm.G[g] = o0.g;
+      for (int pos = lo; pos < hi; pos += RND) {          // a round: RND occurrences, RPG per lane group
+        const int n = hi - pos;                            // (>= RND: a full round)
+        int nbag[RPG];                                     // the next round's bag indices travel during this one
+#pragma unroll
+        for (int r = 0; r < RPG; ++r) {
+          nbag[r] = 0;
+          if (pos + RND + r * 8 + g < hi) nbag[r] = __ldg(a.sorted_bag + pos + RND + r * 8 + g);
         }
-        if (8 + g < n) {
-          sm.P[32 + lane] = occ_value(o1);
-          if (gl == 0) sm.G[8 + g] = o1.g;
+        Occ o[RPG];
+#pragma unroll
+        for (int r = 0; r < RPG; ++r)
+          if (r * 8 + g < n) occ_load<DF>(a, bag[r], gl, o[r]);
+#pragma unroll
+        for (int r = 0; r < RPG; ++r) {
+          if (r * 8 + g < n) {
+            sm.P[r * 32 + lane] = occ_value(o[r]);
+            if (gl == 0) sm.G[r * 8 + g] = o[r].g;
+          }
         }
         __syncwarp();
-        const int ja = max(s0, pos) - pos, je = min(min(s1, hi), pos + 16) - pos;      // empty unless len > 0
+        const int ja = max(s0, pos) - pos, je = min(min(s1, hi), pos + RND) - pos;     // empty unless len > 0
         for (int j = ja; j < je; ++j) {
           const float4 t = sm.P[j * 4 + gl];
           acc.x += t.x; acc.y += t.y; acc.z += t.z; acc.w += t.w;
           sum_g += sm.G[j];
         }
         __syncwarp();
-        bag0 = nb0; bag1 = nb1;
+#pragma unroll
+        for (int r = 0; r < RPG; ++r) bag[r] = nbag[r];
       }
     }
     if (PUSH) {
@@ -376,7 +386,7 @@ static int g_T = -1, g_ITEM, g_OCC;
 static void tile_knobs() {
   if (g_T >= 0) return;
   g_ITEM = env_int("ETR_TILE_ITEM", 256);
-  g_OCC = env_int("ETR_TILE_OCC", 7);
+  g_OCC = env_int("ETR_TILE_OCC", 6);     // with rounds of 32 (ETR_TILE_RPG=4, the default): 80 registers, 6 CTAs / SM
   int t = env_int("ETR_TILE_T", 32);
   if (t < 1) t = 1;
   if (g_ITEM < t + 1) g_ITEM = t + 1;
@@ -433,9 +443,15 @@ int fused_tile_launch(etr_ctx* ctx, const TileArgs& a, const void* d_prep, cudaS
     if (st != ETR_OK) return st;
     tile_layout(a.n_slots, (char*)ctx->d_ws, p);
   }
-  const int OCC = g_OCC;
+  const int OCC = a.slot_of_u ? 7 : g_OCC;          // the push form is compiled for 7 CTAs / SM only
   const int grid = grid_for(a.n_slots, 32, ctx->sm_count, OCC);
-#define ETR_TILE(DF) do { if (a.slot_of_u) fm_tile_kernel<DF, 7, 1><<<grid, 128, 0, s>>>(p); \
+  static int rpg = -1;
+  if (rpg < 0) rpg = env_int("ETR_TILE_RPG", 4) == 2 ? 2 : 4;   // apply mode; the mailbox-push form keeps rounds of 16
+#define ETR_TILE(DF) do { \
+    if (rpg == 4 && !a.slot_of_u) { \
+      if (OCC <= 5) fm_tile_kernel<DF, 5, 0, 4><<<grid, 128, 0, s>>>(p); else if (OCC == 6) fm_tile_kernel<DF, 6, 0, 4><<<grid, 128, 0, s>>>(p); \
+      else fm_tile_kernel<DF, 7, 0, 4><<<grid, 128, 0, s>>>(p); \
+    } else if (a.slot_of_u) fm_tile_kernel<DF, 7, 1><<<grid, 128, 0, s>>>(p); \
     else if (OCC <= 5) fm_tile_kernel<DF, 5, 0><<<grid, 128, 0, s>>>(p); else if (OCC == 6) fm_tile_kernel<DF, 6, 0><<<grid, 128, 0, s>>>(p); \
     else if (OCC == 7) fm_tile_kernel<DF, 7, 0><<<grid, 128, 0, s>>>(p); else fm_tile_kernel<DF, 8, 0><<<grid, 128, 0, s>>>(p); } while (0)
   if (a.dflat) ETR_TILE(1); else ETR_TILE(0);

@@ -286,21 +286,14 @@ int etr_mlp_skinny_backward(etr_ctx* ctx, const void* d_X, int64_t ldx, const fl
   p.X = (const __nv_bfloat16*)d_X; p.ldx = ldx; p.d = d_dy; p.K = d_K; p.dX = (__nv_bfloat16*)d_dX; p.ld_dx = ld_dx;
   p.part = (float*)ctx->d_ws; p.B = B; p.n_in = n_in;
   const int mt = (n_in / 16 + 7) / 8;
+  // the attribute is per device: set it on every call (as the other files do), not once per process
 #define ETR_SK(MT)                                                                                                    \
   do {                                                                                                                \
-    static size_t configured = 0;                                                                                     \
-    if (configured < smem) {                                                                                          \
-      ETR_CUDA(cudaFuncSetAttribute(sk::mlp_skinny_bwd_kernel<MT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
-      configured = smem;                                                                                              \
-    }                                                                                                                 \
+    ETR_CUDA(cudaFuncSetAttribute(sk::mlp_skinny_bwd_kernel<MT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
     sk::mlp_skinny_bwd_kernel<MT><<<(int)grid, 256, smem, s>>>(p);                                                   \
   } while (0)
   if (n_in == 432) {                                  // DeepFM c2: 13 dense + 26 x 16 (+3 pad) inputs
-    static size_t configured432 = 0;
-    if (configured432 < smem) {
-      ETR_CUDA(cudaFuncSetAttribute(sk::mlp_skinny_bwd_kernel<4, 432>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-      configured432 = smem;
-    }
+    ETR_CUDA(cudaFuncSetAttribute(sk::mlp_skinny_bwd_kernel<4, 432>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     sk::mlp_skinny_bwd_kernel<4, 432><<<(int)grid, 256, smem, s>>>(p);
   } else
   switch (mt) {
