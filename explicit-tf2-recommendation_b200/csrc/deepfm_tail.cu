@@ -151,8 +151,10 @@ __global__ void __launch_bounds__(256) deepfm_tail_finish_kernel(const float* pa
   int c0 = warp * per, c1 = c0 + per;
   if (c1 > nparts) c1 = nparts;
   float t = 0.f;
-  if (e < NPART)
-    for (int c = c0; c < c1; ++c) t += part[(size_t)c * NPART + e];
+  if (e < NPART) {
+#pragma unroll 8
+    for (int c = c0; c < c1; ++c) t += __ldg(part + (size_t)c * NPART + e);      // independent loads, ordered adds
+  }
   sm[warp][lane] = t;
   __syncthreads();
   if (warp != 0 || e >= NPART) return;

@@ -10,6 +10,9 @@ world_size 2 on CPU against the unsharded oracle:
   export    etr_fm_fused_backward_push   per unique row the DEFERRED gradient [P, sum_g], P = sum g S + sum dflat
   apply     etr_shard_mailbox_accumulate the G source regions are added in rank order into an accumulator whose rows
             + etr_shard_touched_adam     carry a stamp (first touch of a step overwrites), then dv = P - v * sum_g
+  apply'    etr_shard_owner_prep         the same sums from the REQUESTS alone: every entry claims its row (any one entry
+            + etr_shard_owner_apply      wins = the leader, the others register their slot with it); after the gradient
+                                         barrier each leader adds its row's entries in ascending source order
 """
 from typing import List, Tuple
 
@@ -95,3 +98,36 @@ class PeerExchangeCpu:
         grad[:, :k] = acc[:, :k] - self.shard[t, :k] * acc[:, k:k + 1]    # the owner finishes the FM gradient
         grad[:, k] = acc[:, k]
         return t, grad
+
+    # -- the request-driven form of the same apply (etr_shard_owner_prep / etr_shard_owner_apply) ---------------------
+    @staticmethod
+    def owner_pairing(regions: List[torch.Tensor], rng=None):
+        """From the request regions alone: leader[(src, slot)] -> {src': slot'} of the other entries of the same row.
+        WHICH entry of a row leads is decided by a race on the device (a 64-bit CAS); ``rng`` picks an arbitrary one here --
+        the sums below must not depend on it."""
+        by_row = {}
+        for src, reg in enumerate(regions):
+            for slot, lr in enumerate(reg.tolist()):
+                by_row.setdefault(lr, []).append((src, slot))
+        leaders = {}
+        for lr, ents in by_row.items():
+            lead = ents[int(rng.integers(len(ents)))] if rng is not None else ents[0]
+            leaders[lead] = (lr, {s: q for s, q in ents})
+        return leaders
+
+    def push_and_apply_paired(self, st: dict, deferred: torch.Tensor, rng=None) -> Tuple[torch.Tensor, torch.Tensor]:
+        """``push_and_apply`` without the accumulator: one pass over the leaders, contributors added in ascending source
+        order (the order of the region-by-region accumulation, so the sums are bit-identical to it)."""
+        G, k = self.world, self.k
+        sent = [deferred[st["owner"] == g_] for g_ in range(G)]
+        recv = _a2a(sent, deferred, self.group)
+        rows, grads = [], []
+        for (src, slot), (lr, ents) in self.owner_pairing(st["regions"], rng).items():
+            acc = None
+            for s in sorted(ents):                                         # ascending source order
+                acc = recv[s][ents[s]].clone() if acc is None else acc + recv[s][ents[s]]
+            gr = acc.clone()
+            gr[:k] = acc[:k] - self.shard[lr, :k] * acc[k]
+            rows.append(lr)
+            grads.append(gr)
+        return torch.tensor(rows, dtype=torch.int64), torch.stack(grads) if grads else deferred.new_empty((0, k + 1))

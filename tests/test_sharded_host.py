@@ -108,7 +108,12 @@ def _peer_worker(rank, world, port, V, k, results):
             dflat = torch.tensor(rng.normal(size=(B, F, k)))
             rows, st = px.exchange_forward(X)
             ok &= torch.equal(rows, full[X])                               # gathered rows bit-exact
-            t, grad = px.push_and_apply(st, px.export_deferred(st, rows, g, dflat))
+            deferred = px.export_deferred(st, rows, g, dflat)
+            t, grad = px.push_and_apply(st, deferred)
+            # the request-driven owner pass (leaders picked at random, as the device race would) gives the SAME bits
+            t2, grad2 = px.push_and_apply_paired(st, deferred, rng)
+            o1, o2 = torch.argsort(t), torch.argsort(t2)
+            ok &= torch.equal(t[o1], t2[o2]) and torch.equal(grad[o1], grad2[o2])
             # reference: autograd on the GLOBAL batch through the unsharded FM expression
             Xs, gs, ds = [torch.empty_like(X) for _ in range(world)], [torch.empty_like(g) for _ in range(world)], \
                 [torch.empty_like(dflat) for _ in range(world)]
