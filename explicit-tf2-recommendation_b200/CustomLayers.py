@@ -24,7 +24,7 @@ from . import _lib
 from ._lib import check
 from .dense import DenseLayer, DenseParams, MLPLayer, glorot_uniform, random_normal  # noqa: F401
 from .runtime import (EmbeddingTable, FusedFMGrad, IdsBatch, Runtime, SparseGrad, SparsePlan, bce_forward_backward,
-                      cast_bf16, embedding_gather, gather_fm_backward, gather_fm_forward, gemm_bf16_tn, lr_t, _p)
+                      cast_bf16, embedding_gather, gather_fm_backward, FlatSparseGrad, gather_fm_forward, gemm_bf16_tn, lr_t, _p)
 
 _DT = {"float32": torch.float32, "bfloat16": torch.bfloat16, torch.float32: torch.float32,
        torch.bfloat16: torch.bfloat16}
@@ -1297,8 +1297,13 @@ class DeepCrossNetworkLayer(_Layer):
         else:
             dx = self.cross_layer.backward(dcomb[:, :Di])                   # [B, Di] fp32
             self.dense_layer.backward(ddnn, accumulate_into=dx)
-        bag = gather_fm_backward(self._ctx["table"], self.embedding_dims, False, ids, dflat=dx,
-                                 flat_col0=self.front_pad + len(self.continuous_features))
+        col0 = self.front_pad + len(self.continuous_features)
+        if self.shard is None and FlatSparseGrad.eligible(self._ctx["table"], ids, dx, col0, self.embedding_dims):
+            # the rows' gradients ARE the embedding block of dx: the segment reduction reads them in place
+            sg = FlatSparseGrad(self._ctx["table"], ids, dx, col0, self.embedding_dims)
+            sg.plan = self._ctx.get("plan")
+            return [sg]
+        bag = gather_fm_backward(self._ctx["table"], self.embedding_dims, False, ids, dflat=dx, flat_col0=col0)
         return [self._table_grad(bag)]
 
 

@@ -73,6 +73,7 @@ PROTOTYPES = {
     "etr_fm_fused_flat_apply": (C.c_int, [_vp, _T, _i32, _i32, _i64, _vp, _vp, _i64, _vp, _vp, _vp, _i32, _i64, _i32, _f32, _vp,
                                           _f32, _f32, _f32, _vp]),
     "etr_sparse_segment_reduce": (C.c_int, [_vp, _vp, _vp, _vp, _i64, _vp, _i32, _vp, _vp]),
+    "etr_sparse_segment_reduce_flat": (C.c_int, [_vp, _vp, _vp, _vp, _i64, _vp, _i64, _i32, _i32, _i32, _vp, _vp]),
     "etr_sparse_adam_apply": (C.c_int, [_vp, _T, _vp, _vp, _vp, _vp, _i64, _vp, _i32, _f32, _vp, _f32, _f32, _f32, _i32, _vp]),
     "etr_fm_fused_backward_apply": (C.c_int, [_vp, _T, _vp, _vp, _i32, _i32, _i64, _vp, _vp, _vp, _vp, _i64, _vp, _vp, _vp,
                                               _i32, _i64, _i32, _f32, _vp, _f32, _f32, _f32, _i32, _vp, _vp]),

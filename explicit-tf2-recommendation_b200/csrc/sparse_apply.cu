@@ -96,6 +96,10 @@ struct SegParams {
   const int* n_unique;
   const float* bag_grad;
   int grad_ld;        // floats, multiple of 4
+  // src_fields > 0: the per-occurrence rows are NOT materialised -- occurrence bg = b * F + f (single-hot ids in
+  // (b, f) order) is the slice [src_col0 + f * grad_ld, + grad_ld) of row b of a [B, src_ld] matrix (the gradient
+  // of the Flatten(embeddings) block of a dense layer's input: 3.DCN/CustomLayers.py:1096-1100 backward)
+  int src_fields, src_col0; long long src_ld;
   float* unique_grad; // [max_unique, grad_ld]
   // long-run work lists (workspace)
   int* counters;      // [0] #long runs, [1] #chunk items
@@ -104,6 +108,12 @@ struct SegParams {
   float* partials;    // [items, grad_ld]
   int max_long, max_items;
 };
+
+__device__ __forceinline__ const float* grad_row(const SegParams& p, int bg) {
+  if (p.src_fields == 0) return p.bag_grad + (long long)bg * p.grad_ld;
+  const int b = bg / p.src_fields, f = bg - b * p.src_fields;
+  return p.bag_grad + (long long)b * p.src_ld + p.src_col0 + f * p.grad_ld;
+}
 
 // Sums gradient rows sorted_bag[i0..i1) into acc[CPL] (lane gl of an LPR-lane
 // group owns 16-byte chunks gl, gl+LPR, ...), 4 rows in flight.
@@ -114,6 +124,9 @@ __device__ __forceinline__ void sum_rows(const SegParams& p, int i0, int i1, int
     int bg[4];
 #pragma unroll
     for (int q = 0; q < 4; ++q) bg[q] = __ldg(p.sorted_bag + i + q);
+    const float* rp[4];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) rp[q] = grad_row(p, bg[q]);
 #pragma unroll
     for (int j = 0; j < CPL; ++j) {
       const int c = gl + j * LPR;
@@ -121,19 +134,19 @@ __device__ __forceinline__ void sum_rows(const SegParams& p, int i0, int i1, int
         float4 r[4];
 #pragma unroll
         for (int q = 0; q < 4; ++q)
-          r[q] = *reinterpret_cast<const float4*>(p.bag_grad + (long long)bg[q] * p.grad_ld + c * 4);
+          r[q] = *reinterpret_cast<const float4*>(rp[q] + c * 4);
 #pragma unroll
         for (int q = 0; q < 4; ++q) { acc[j].x += r[q].x; acc[j].y += r[q].y; acc[j].z += r[q].z; acc[j].w += r[q].w; }
       }
     }
   }
   for (; i < i1; ++i) {
-    const long long row = (long long)__ldg(p.sorted_bag + i) * p.grad_ld;
+    const float* rp = grad_row(p, __ldg(p.sorted_bag + i));
 #pragma unroll
     for (int j = 0; j < CPL; ++j) {
       const int c = gl + j * LPR;
       if (c < nchunks) {
-        const float4 r = *reinterpret_cast<const float4*>(p.bag_grad + row + c * 4);
+        const float4 r = *reinterpret_cast<const float4*>(rp + c * 4);
         acc[j].x += r.x; acc[j].y += r.y; acc[j].z += r.z; acc[j].w += r.w;
       }
     }
@@ -477,9 +490,33 @@ int etr_sparse_plan_keys(etr_ctx* ctx, const etr_ids* ids, int64_t nnz_if_csr, i
   return ETR_OK;
 }
 
+static int segment_reduce_impl(etr_ctx* ctx, const int32_t* d_sorted_bag, const int32_t* d_seg_start,
+                               const int32_t* d_n_unique, int64_t n_slots, const float* d_bag_grad,
+                               int32_t grad_ld, int32_t src_fields, int64_t src_ld, int32_t src_col0,
+                               float* d_unique_grad, void* stream);
+
 int etr_sparse_segment_reduce(etr_ctx* ctx, const int32_t* d_sorted_bag, const int32_t* d_seg_start,
                               const int32_t* d_n_unique, int64_t n_slots, const float* d_bag_grad,
                               int32_t grad_ld, float* d_unique_grad, void* stream) {
+  return segment_reduce_impl(ctx, d_sorted_bag, d_seg_start, d_n_unique, n_slots, d_bag_grad, grad_ld, 0, 0, 0,
+                             d_unique_grad, stream);
+}
+
+int etr_sparse_segment_reduce_flat(etr_ctx* ctx, const int32_t* d_sorted_bag, const int32_t* d_seg_start,
+                                   const int32_t* d_n_unique, int64_t n_slots, const float* d_flat, int64_t flat_ld,
+                                   int32_t flat_col0, int32_t fields, int32_t grad_ld, float* d_unique_grad,
+                                   void* stream) {
+  ETR_CHECK_ARG(fields > 0 && flat_ld % 4 == 0 && flat_col0 % 4 == 0 && flat_col0 >= 0 &&
+                    (int64_t)flat_col0 + (int64_t)fields * grad_ld <= flat_ld,
+                "flat source: 16-byte aligned slices inside a row");
+  return segment_reduce_impl(ctx, d_sorted_bag, d_seg_start, d_n_unique, n_slots, d_flat, grad_ld, fields, flat_ld,
+                             flat_col0, d_unique_grad, stream);
+}
+
+static int segment_reduce_impl(etr_ctx* ctx, const int32_t* d_sorted_bag, const int32_t* d_seg_start,
+                               const int32_t* d_n_unique, int64_t n_slots, const float* d_bag_grad,
+                               int32_t grad_ld, int32_t src_fields, int64_t src_ld, int32_t src_col0,
+                               float* d_unique_grad, void* stream) {
   ETR_CHECK_ARG(ctx && d_sorted_bag && d_seg_start && d_n_unique && d_bag_grad && d_unique_grad, "NULL argument");
   ETR_CHECK_ARG(grad_ld > 0 && grad_ld % 4 == 0, "grad_ld must be a positive multiple of 4");
   ETR_CHECK_ARG((((uintptr_t)d_bag_grad | (uintptr_t)d_unique_grad) & 15) == 0, "gradients must be 16-byte aligned");
@@ -488,6 +525,7 @@ int etr_sparse_segment_reduce(etr_ctx* ctx, const int32_t* d_sorted_bag, const i
   SegParams p;
   p.sorted_bag = d_sorted_bag; p.seg_start = d_seg_start; p.n_unique = d_n_unique;
   p.bag_grad = d_bag_grad; p.grad_ld = grad_ld; p.unique_grad = d_unique_grad;
+  p.src_fields = src_fields; p.src_ld = src_ld; p.src_col0 = src_col0;
   p.max_long = (int)(n_slots / kShortRun + 1);
   p.max_items = (int)(n_slots / kChunk + n_slots / kShortRun + 2);
   const size_t b_cnt = 256, b_runs = align256(sizeof(LongRun) * (size_t)p.max_long),

@@ -417,6 +417,34 @@ class SparseGrad:
         return self.plan.unique_ids[:u], self.unique_grad[:u, : self.table.width]
 
 
+class FlatSparseGrad(SparseGrad):
+    """SparseGrad whose per-occurrence rows are slices of a dense fp32 matrix ``flat`` [B, ld] (occurrence (b, f) =
+    flat[b, col0 + f*k : col0 + (f+1)*k], single-hot ids): the segment reduction reads them in place
+    (etr_sparse_segment_reduce_flat) instead of a [B*F, k] re-layout -- the table gradient of DCN / PNN-style models,
+    whose only use of the rows is Flatten(embeddings) (3.DCN/CustomLayers.py:1096-1100)."""
+
+    def __init__(self, table: EmbeddingTable, ids: IdsBatch, flat: torch.Tensor, col0: int, k: int):
+        assert flat.dtype == torch.float32 and flat.stride(1) == 1 and not ids.is_bag and table.grad_ld == k
+        super().__init__(table, ids, None)
+        self.flat, self.col0, self.k = flat, int(col0), int(k)
+
+    @staticmethod
+    def eligible(table, ids: IdsBatch, flat: torch.Tensor, col0: int, k: int) -> bool:
+        return (isinstance(table, EmbeddingTable) and flat.dtype == torch.float32 and flat.stride(1) == 1 and not ids.is_bag
+                and table.grad_ld == k and k % 4 == 0 and col0 % 4 == 0 and flat.stride(0) % 4 == 0
+                and flat.data_ptr() % 16 == 0 and os.environ.get("ETR_FLAT_SEGRED", "1") != "0")
+
+    def reduce(self, plan: Optional[SparsePlan] = None) -> "SparseGrad":
+        rt = self.table.rt
+        self.plan = (plan or self.plan or SparsePlan(rt, self.ids, self.table.rows)).join()
+        self.unique_grad = rt.empty((max(self.plan.n_slots, 1), self.k), torch.float32)
+        check(rt.lib.etr_sparse_segment_reduce_flat(rt.ctx, self.plan.sorted_bag.data_ptr(), self.plan.seg_start.data_ptr(),
+                                                    self.plan.counts.data_ptr(), self.plan.n_slots, self.flat.data_ptr(),
+                                                    self.flat.stride(0), self.col0, self.ids.F, self.k,
+                                                    self.unique_grad.data_ptr(), rt.stream))
+        return self
+
+
 class FusedFMGrad:
     """Table gradient of the FM family in its un-materialised form: the plan's runs plus
     (dlogit, sum_v, dflat).  ``apply`` runs backward + segment reduction + Adam in one pass

@@ -188,6 +188,15 @@ int etr_sparse_segment_reduce(etr_ctx* ctx, const int32_t* d_sorted_bag, const i
                               const int32_t* d_n_unique, int64_t n_slots,
                               const float* d_bag_grad, int32_t grad_ld,
                               float* d_unique_grad, void* stream);
+/* The same reduction when the per-occurrence rows are slices of a dense matrix and need not be
+ * materialised: ids are single-hot in (b, f) order (occurrence b * fields + f) and its gradient row is
+ * d_flat[b, flat_col0 + f * grad_ld .. + grad_ld) -- the gradient of the Flatten(embeddings) block of
+ * a dense layer's input (3.DCN/CustomLayers.py:1096-1100 under tape.gradient).  Saves the
+ * [B * fields, grad_ld] re-layout of etr_gather_fm_backward for models without an FM term.        */
+int etr_sparse_segment_reduce_flat(etr_ctx* ctx, const int32_t* d_sorted_bag, const int32_t* d_seg_start,
+                                   const int32_t* d_n_unique, int64_t n_slots, const float* d_flat, int64_t flat_ld,
+                                   int32_t flat_col0, int32_t fields, int32_t grad_ld, float* d_unique_grad,
+                                   void* stream);
 
 /* Adam on the unique rows (replaces opt.apply_gradients for IndexedSlices,
  * 2.FM/ModelManager.py:178).  table/m/v share rows/width/stride (fp32 slots).
