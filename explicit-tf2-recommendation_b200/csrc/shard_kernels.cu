@@ -429,7 +429,9 @@ __global__ void __launch_bounds__(256) owner_apply_kernel(const OwnerApplyParams
   const int sg_lane = g * LPR + p.fm_k / 4;
   const int step = gridDim.x * 8 * GPW;
   // every condition below is uniform per lane group (the shuffles are group-wide)
-  for (int s0 = (blockIdx.x * 8 + (threadIdx.x >> 5)) * GPW + g; s0 < n; s0 += U * step) {
+  // (LPR = 5, the 20-float FM row: six entries per warp, lanes 30 and 31 idle -- the pass is issue-bound, and the
+  // power-of-two grouping spent 3 of 8 lanes on nothing)
+  for (int s0 = g < GPW ? (blockIdx.x * 8 + (threadIdx.x >> 5)) * GPW + g : n; s0 < n; s0 += U * step) {
     unsigned mk[U];
     long long e[U], row[U];
 #pragma unroll
@@ -787,8 +789,16 @@ int etr_shard_owner_apply(etr_ctx* ctx, const etr_table* table, float* d_m, floa
     const char* u = getenv("ETR_OWNER_U"); unroll = (u && atoi(u) == 2) ? 2 : 1;
   }
   const int per_sm = bps > 0 ? bps : 16 / (world < 8 ? world : 8) + 1;
-  dim3 grid((unsigned)grid_for(cap, 8 * (32 / lpr) * unroll, ctx->sm_count, per_sm), (unsigned)world);
   cudaStream_t s = (cudaStream_t)stream;
+  static int five = -1;
+  if (five < 0) { const char* e = getenv("ETR_OWNER_LPR5"); five = !(e && atoi(e) == 0); }
+  if (five && ld == 20 && unroll == 1) {
+    dim3 g5((unsigned)grid_for(cap, 8 * 6, ctx->sm_count, per_sm), (unsigned)world);
+    owner_apply_kernel<5, 1><<<g5, 256, 0, s>>>(p);
+    ETR_LAUNCH_CHECK(ctx);
+    return ETR_OK;
+  }
+  dim3 grid((unsigned)grid_for(cap, 8 * (32 / lpr) * unroll, ctx->sm_count, per_sm), (unsigned)world);
   if (lpr == 8 && unroll == 2) owner_apply_kernel<8, 2><<<grid, 256, 0, s>>>(p);
   else switch (lpr) {
     case 1: owner_apply_kernel<1, 1><<<grid, 256, 0, s>>>(p); break;
