@@ -800,7 +800,9 @@ def main():
         tr = L.Trainer(lay, lr=1e-3, apply_mode=apply_mode, graph=graph,
                        plan_ahead=(graph and apply_mode == "rowwise" and not args.no_plan_ahead))
         try:
-            for i in range(max(args.warmup, 8 if graph else 0)):      # 2 buffer sets x (2 eager + capture) first
+            # every buffer set (2, or 3 with plan-ahead) needs 2 eager steps + its capture before anything is timed: with 8
+            # warm-ups and 3 sets the last capture fell into the timed steps of value_fp32 (4.45 instead of 1.06 ms per step)
+            for i in range(max(args.warmup, 3 * tr.depth + 2 if graph else 0)):
                 d_, y_ = device_dict(i)
                 tr.train_step(tr.stage(d_, y_))
             torch.cuda.synchronize(dev)
@@ -1082,7 +1084,7 @@ def main():
                 tr32, fn32, g32 = make_stepper(lay32, "rowwise", use_graph)
                 ms32 = timed_rep(tr32, fn32, K2, args.warmup)
                 extras["value_fp32"] = {"value": B * K2 / (sum(ms32) * 1e-3), "unit": "samples/s", "ms_per_step": sum(ms32) / K2,
-                                        "steps": K2, "cuda_graph": g32,
+                                        "steps": K2, "cuda_graph": g32, "ms_each": [round(x, 3) for x in ms32],
                                         "what": "same step with the first MLP layer on the fp32 SIMT path (1e-5 parity)"}
                 del tr32, fn32, lay32
                 torch.cuda.empty_cache()
@@ -1090,6 +1092,7 @@ def main():
             msd = timed_rep(trd, fnd, min(K2, 5), args.warmup)
             extras["value_keras_dense"] = {"value": B * len(msd) / (sum(msd) * 1e-3), "unit": "samples/s",
                                            "ms_per_step": sum(msd) / len(msd), "steps": len(msd), "cuda_graph": gd_,
+                                           "ms_each": [round(x, 3) for x in msd],
                                            "what": "same step with apply_mode='keras_dense': Keras-2.8 Adam on IndexedSlices "
                                                    "decays m, v and updates var for ALL V rows every step (13.8 GB of "
                                                    "table traffic per step at c2)"}

@@ -359,7 +359,33 @@ __global__ void __launch_bounds__(128, OCC) fm_tile_kernel(const TileParams p) {
       }
     }
     if (PUSH) {
-      if (len > 0) row_push(a, __float_as_int(sm.w[buf][g]), gl, acc, sum_g);
+      // the 8 finished rows go out as ONE 80-byte request each: staged in shared memory (the park buffer is free), then
+      // five adjacent lanes store the five 16-byte chunks of a row (40 chunks: two warp stores) -- half the peer write
+      // requests of the direct form (row_push: 64 bytes by the row's four lanes + a separate 16-byte store for sum_g).
+      // Measured at N = 4: 132.9 -> 134.1 us, i.e. no difference; the growth of the push with N is not the request
+      // count (profiles/r02_mgpu.md).  Kept: one request per row is the cleaner traffic pattern.
+      float4* stg = sm.P;                                  // [8 rows][5 chunks]
+      int* sslot = reinterpret_cast<int*>(sm.G);           // [8]
+      stg[g * 5 + gl] = acc;
+      if (gl == 0) {
+        stg[g * 5 + 4] = make_float4(sum_g, 0.f, 0.f, 0.f);
+        sslot[g] = len > 0 ? __float_as_int(sm.w[buf][g]) : -1;
+      }
+      __syncwarp();
+#pragma unroll
+      for (int rr = 0; rr < 2; ++rr) {
+        const int idx = rr * 32 + lane;
+        if (idx < 40) {
+          const int r = idx / 5, c = idx - r * 5;
+          const int so = sslot[r];
+          if (so >= 0) {
+            const int owner = so / a.cap;
+            float* dst = a.grads_mb[owner] + (long long)(so - owner * a.cap) * a.gld;
+            *reinterpret_cast<float4*>(dst + c * 4) = stg[idx];
+          }
+        }
+      }
+      __syncwarp();
     } else if (len > 0) {
       const long long uid = ((long long)hc.w << 32) | (unsigned)hc.z;
       float* rec = a.table + uid * 64;

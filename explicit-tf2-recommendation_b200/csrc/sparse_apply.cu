@@ -12,6 +12,7 @@
 #include <cub/iterator/counting_input_iterator.cuh>
 
 #include "etr_common.cuh"
+#include "etr_async.cuh"
 
 namespace etr {
 
@@ -363,6 +364,15 @@ __global__ void __launch_bounds__(256) dense_decay_kernel(float* m, float* v, lo
     *reinterpret_cast<float4*>(m + off) = a; *reinterpret_cast<float4*>(v + off) = b;
   }
 }
+// The quotient uses the MUFU forms (sqrt.approx / div.approx, <= 2 ulp each, as the fused row-wise apply does), NOT the
+// IEEE ones.  Under keras_dense every row's m decays by 0.9 per step, so ~700 steps after its last touch a row's m is a
+// SUBNORMAL float for ~150 steps before it reaches zero, and IEEE division / square root have data-dependent slow
+// paths.  Measured (end of round 2): value_keras_dense of the full default bench, i.e. after ~2 500 training steps on
+// the table, 27.5 ms per step with the IEEE form, 5.67 ms with this one (5.7 ms on a fresh table either way; an
+// all-subnormal m alone costs the IEEE form only +0.5 ms, scripts/dbg_extras.py, so the subnormal window is not the
+// whole story -- the branch-free form is what removed the dependence on the table's history).  IEEE = true keeps the
+// old form for an A/B (ETR_DENSE_IEEE=1).
+template <bool IEEE>
 __global__ void __launch_bounds__(256) dense_var_update_kernel(char* table, int bf16, const float* m, const float* v,
                                                                long long rows, int rc, int stride, float lr_host,
                                                                const float* d_lr_t, float eps) {
@@ -371,8 +381,14 @@ __global__ void __launch_bounds__(256) dense_var_update_kernel(char* table, int 
   for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < n4; t += (long long)gridDim.x * blockDim.x) {
     const long long off = (t / rc) * stride + (t % rc) * 4;
     const float4 a = *reinterpret_cast<const float4*>(m + off), b = *reinterpret_cast<const float4*>(v + off);
-    float d[4] = {lr_t * a.x / (sqrtf(b.x) + eps), lr_t * a.y / (sqrtf(b.y) + eps),
-                  lr_t * a.z / (sqrtf(b.z) + eps), lr_t * a.w / (sqrtf(b.w) + eps)};
+    float d[4];
+    if (IEEE) {
+      d[0] = lr_t * a.x / (sqrtf(b.x) + eps); d[1] = lr_t * a.y / (sqrtf(b.y) + eps);
+      d[2] = lr_t * a.z / (sqrtf(b.z) + eps); d[3] = lr_t * a.w / (sqrtf(b.w) + eps);
+    } else {
+      d[0] = fast_div(lr_t * a.x, fast_sqrt(b.x) + eps); d[1] = fast_div(lr_t * a.y, fast_sqrt(b.y) + eps);
+      d[2] = fast_div(lr_t * a.z, fast_sqrt(b.z) + eps); d[3] = fast_div(lr_t * a.w, fast_sqrt(b.w) + eps);
+    }
     if (!bf16) {
       float4* px = reinterpret_cast<float4*>(reinterpret_cast<float*>(table) + off);
       float4 x = *px;
@@ -605,7 +621,11 @@ int etr_sparse_adam_apply(etr_ctx* ctx, const etr_table* table, float* d_m, floa
     ETR_LAUNCH_CHECK(ctx);
   }
   if (mode == ETR_ADAM_KERAS_DENSE) {
-    dense_var_update_kernel<<<gd, 256, 0, s>>>((char*)table->d_data, p.table_bf16, d_m, d_v, table->rows, rc, table->stride,
+    static int ieee = -1;
+    if (ieee < 0) { const char* e = getenv("ETR_DENSE_IEEE"); ieee = (e && atoi(e) == 1) ? 1 : 0; }
+    if (ieee) dense_var_update_kernel<true><<<gd, 256, 0, s>>>((char*)table->d_data, p.table_bf16, d_m, d_v, table->rows, rc, table->stride,
+                                               lr_t, d_lr_t, eps);
+    else dense_var_update_kernel<false><<<gd, 256, 0, s>>>((char*)table->d_data, p.table_bf16, d_m, d_v, table->rows, rc, table->stride,
                                                lr_t, d_lr_t, eps);
     ETR_LAUNCH_CHECK(ctx);
   }
