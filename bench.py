@@ -1060,7 +1060,7 @@ def main():
         n_u = statistics.mean(p_.n_unique for p_ in plans)
         a_bytes = n_u * 6 * (K_EMB + 1) * 4
         tr_ = ncu_traffic("fm_tile_kernel" if tiled else "fm_fused_") if (args.dist == "zipf" and B == BATCH and args.config == "c2") else None
-        roof_apply = {"bound": "hbm", "kernel": ("fm_tile_kernel<1,7> (ONE launch: " if tiled else
+        roof_apply = {"bound": "hbm", "kernel": ("fm_tile_kernel<1,6,0,4> (ONE launch: " if tiled else
                                                  "fm_fused_{classify,short|record,chunk,combine}_kernel (") +
                       "FM backward + sorted-run reduction + row-wise Adam; table layout: " +
                       ("256-byte [var|m|v] records" if layer.table.record else "three plain arrays") + ")",
